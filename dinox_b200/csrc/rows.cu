@@ -1,0 +1,549 @@
+// Row / column statistics and cross-entropy on MATERIALISED logits.
+// This is the drop-in path behind DINOLoss.forward(student_out, teacher_out, ...)
+// (scripts/phase5_big_run.py:692-720) plus the Sinkhorn-Knopp (E2) passes.  All kernels are
+// HBM/L2-bound streaming reductions: 128-bit loads where alignment allows, fp32 math in log2
+// units (one FFMA + one MUFU.EX2 per element), warp-shuffle + shared-memory block reductions in
+// a fixed order (deterministic; no fp32 atomics).
+#include "common.cuh"
+
+namespace dinox {
+
+constexpr int kRowThreads = 512;
+constexpr int kMaxGlobalViews = 4;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&o)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[4]) {
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+    o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&o)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = v;
+  }
+};
+template <> struct Vec4<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&o)[4]) {
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    float2 a = __half22float2(*reinterpret_cast<__half2*>(&v.x));
+    float2 b = __half22float2(*reinterpret_cast<__half2*>(&v.y));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&o)[4]) {
+    __half2 a = __floats2half2_rn(o[0], o[1]);
+    __half2 b = __floats2half2_rn(o[2], o[3]);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = v;
+  }
+};
+
+// loads 4 consecutive elements starting at column k (vector path) or up to `n` scalars (tail / unaligned)
+template <typename T, bool kVec>
+__device__ __forceinline__ void load4(const T* row, int64_t k, int64_t K, float (&o)[4], float fill) {
+  if (kVec) {
+    Vec4<T>::load(row + k, o);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = (k + j < K) ? to_f32<T>(row[k + j]) : fill;
+  }
+}
+template <bool kVec>
+__device__ __forceinline__ void loadf4(const float* p, int64_t k, int64_t K, float (&o)[4], float fill) {
+  if (p == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fill;
+  } else {
+    load4<float, kVec>(p, k, K, o, fill);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rows_lse: one CTA per row.  lse[i] = ln sum_k exp(u[i,k]),  entropy[i] = lse - sum_k p_k u_k
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kRowThreads)
+rows_lse_kernel(const T* __restrict__ x, int64_t K, int64_t ld, float scale2 /* inv_tau*log2e */,
+                const float* __restrict__ colbias, float* __restrict__ lse, float* __restrict__ entropy) {
+  __shared__ float red[64];
+  const T* row = x + (int64_t)blockIdx.x * ld;
+  float m = -INFINITY, s = 0.f, e = 0.f;
+  const bool want_ent = entropy != nullptr;
+  for (int64_t k = (int64_t)threadIdx.x * 4; k < K; k += (int64_t)kRowThreads * 4) {
+    float v[4], cb[4];
+    load4<T, kVec>(row, k, K, v, 0.f);
+    loadf4<kVec>(colbias, k, K, cb, 0.f);
+    float u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      u[j] = fmaf(v[j], scale2, -cb[j] * DINOX_LOG2E);
+      if (!kVec && k + j >= K) u[j] = -INFINITY;
+    }
+    float mv = fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3]));
+    float mn = fmaxf(m, mv);
+    if (mn == -INFINITY) continue;
+    float r = exp2f(m - mn);  // m == -inf -> 0
+    s *= r;
+    e *= r;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float p = exp2f(u[j] - mn);
+      s += p;
+      if (want_ent) e += (u[j] == -INFINITY) ? 0.f : p * u[j];
+    }
+    m = mn;
+  }
+  // block combine
+  MaxSum ms{m, s};
+  MaxSum tot = block_maxsum<kRowThreads>(ms, red);
+  if (want_ent) {
+    float escaled = (m == -INFINITY) ? 0.f : e * exp2f(m - tot.m);
+    float etot = block_sum<kRowThreads>(escaled, red);
+    if (threadIdx.x == 0) {
+      float l2 = tot.m + log2f(tot.s);
+      entropy[blockIdx.x] = DINOX_LN2 * (l2 - etot / tot.s);
+    }
+  }
+  if (threadIdx.x == 0) lse[blockIdx.x] = DINOX_LN2 * (tot.m + log2f(tot.s));
+}
+
+// ---------------------------------------------------------------------------------------------
+// column passes: each thread owns 4 adjacent columns and walks all rows
+// ---------------------------------------------------------------------------------------------
+constexpr int kColThreads = 128;
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kColThreads)
+cols_lse_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, float scale2,
+                const float* __restrict__ rowbias, float* __restrict__ out) {
+  const int64_t k = ((int64_t)blockIdx.x * kColThreads + threadIdx.x) * 4;
+  if (k >= K) return;
+  float m[4], s[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { m[j] = -INFINITY; s[j] = 0.f; }
+  for (int64_t i = 0; i < rows; ++i) {
+    float v[4];
+    load4<T, kVec>(x + i * ld, k, K, v, 0.f);
+    const float rb = rowbias ? rowbias[i] * DINOX_LOG2E : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = fmaf(v[j], scale2, -rb);
+      float mn = fmaxf(m[j], u);
+      if (mn != -INFINITY) {
+        s[j] = s[j] * exp2f(m[j] - mn) + exp2f(u - mn);
+        m[j] = mn;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (k + j < K) out[k + j] = DINOX_LN2 * (m[j] + log2f(s[j]));
+}
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kColThreads)
+cols_sum_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, float* __restrict__ out) {
+  const int64_t k = ((int64_t)blockIdx.x * kColThreads + threadIdx.x) * 4;
+  if (k >= K) return;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  int64_t i = 0;
+  for (; i + 4 <= rows; i += 4) {  // 4 independent loads in flight
+    float v0[4], v1[4], v2[4], v3[4];
+    load4<T, kVec>(x + (i + 0) * ld, k, K, v0, 0.f);
+    load4<T, kVec>(x + (i + 1) * ld, k, K, v1, 0.f);
+    load4<T, kVec>(x + (i + 2) * ld, k, K, v2, 0.f);
+    load4<T, kVec>(x + (i + 3) * ld, k, K, v3, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+  }
+  for (; i < rows; ++i) {
+    float v[4];
+    load4<T, kVec>(x + i * ld, k, K, v, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (k + j < K) out[k + j] = a[j];
+}
+
+__global__ void lse_combine_kernel(const float* __restrict__ g, int world, int64_t K, float add,
+                                   float* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float m = -INFINITY;
+  for (int r = 0; r < world; ++r) m = fmaxf(m, g[(int64_t)r * K + k]);
+  float s = 0.f;
+  for (int r = 0; r < world; ++r) s += (m == -INFINITY) ? 0.f : expf(g[(int64_t)r * K + k] - m);
+  out[k] = m + logf(s) + add;
+}
+
+__global__ void center_ema_kernel(float* __restrict__ center, const float* __restrict__ colsum,
+                                  float inv_rows, float m, float om, int64_t K) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  // reference op order (scripts/phase5_big_run.py:689): center*m + batch_center*(1-m)
+  const float bc = colsum[k] * inv_rows;
+  center[k] = __fadd_rn(__fmul_rn(center[k], m), __fmul_rn(bc, om));
+}
+
+__global__ void axpb_kernel(const float* __restrict__ a, float alpha, float beta,
+                            float* __restrict__ out, int64_t n) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = fmaf(a[k], alpha, beta);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross-entropy forward / backward over groups x K-splits
+// ---------------------------------------------------------------------------------------------
+constexpr int kCeThreads = 256;
+
+struct CeArgs {
+  int64_t groups, K, ld_s, ld_t, ld_g;
+  int V, Vg, exclude_same, ksplit;
+  float s2, t2;  // inv_tau * log2e
+  const float* colbias_t;
+  const float* rowbias_t;
+  const float* lse_s;
+  const float* group_w;
+  float norm;
+};
+
+template <typename TS, typename TT, bool kVec>
+__global__ void __launch_bounds__(kCeThreads)
+ce_fwd_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, CeArgs a,
+              float* __restrict__ partial /* [groups][ksplit][Vg][2] */) {
+  __shared__ float red[64];
+  const int64_t g = blockIdx.x;
+  const int split = blockIdx.y;
+  const int64_t per = ((a.K + a.ksplit - 1) / a.ksplit + 3) & ~int64_t(3);
+  const int64_t k0 = split * per, k1 = (k0 + per < a.K) ? k0 + per : a.K;
+  float rb2[kMaxGlobalViews];
+#pragma unroll
+  for (int q = 0; q < kMaxGlobalViews; ++q)
+    rb2[q] = (q < a.Vg) ? a.rowbias_t[q * a.groups + g] * DINOX_LOG2E : 0.f;
+  float qsum[kMaxGlobalViews], cross[kMaxGlobalViews];
+#pragma unroll
+  for (int q = 0; q < kMaxGlobalViews; ++q) { qsum[q] = 0.f; cross[q] = 0.f; }
+
+  for (int64_t k = k0 + (int64_t)threadIdx.x * 4; k < k1; k += (int64_t)kCeThreads * 4) {
+    float cb[4];
+    loadf4<kVec>(a.colbias_t, k, k1, cb, 0.f);
+    float qv[kMaxGlobalViews][4];
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) {
+        float t[4];
+        load4<TT, kVec>(teacher + (q * a.groups + g) * a.ld_t, k, k1, t, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float u = fmaf(t[j], a.t2, -cb[j] * DINOX_LOG2E) - rb2[q];
+          qv[q][j] = (!kVec && k + j >= k1) ? 0.f : exp2f(u);
+        }
+      }
+    }
+    float stot[4] = {0.f, 0.f, 0.f, 0.f};
+    float sown[kMaxGlobalViews][4];
+    for (int v = 0; v < a.V; ++v) {
+      float s[4];
+      load4<TS, kVec>(student + (v * a.groups + g) * a.ld_s, k, k1, s, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) stot[j] += s[j];
+#pragma unroll
+      for (int q = 0; q < kMaxGlobalViews; ++q)
+        if (q == v) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sown[q][j] = s[j];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float other = a.exclude_same ? (stot[j] - sown[q][j]) : stot[j];
+          qsum[q] += qv[q][j];
+          cross[q] = fmaf(qv[q][j], other, cross[q]);
+        }
+      }
+    }
+  }
+  for (int q = 0; q < a.Vg; ++q) {
+    float qs = block_sum<kCeThreads>(qsum[q], red);
+    float cr = block_sum<kCeThreads>(cross[q], red);
+    if (threadIdx.x == 0) {
+      float* p = partial + (((int64_t)g * a.ksplit + split) * a.Vg + q) * 2;
+      p[0] = qs;
+      p[1] = cr;
+    }
+  }
+}
+
+// single CTA, fixed summation order => deterministic loss
+__global__ void __launch_bounds__(1024)
+ce_finalize_kernel(const float* __restrict__ partial, CeArgs a, float inv_tau_s, float* __restrict__ loss_out) {
+  __shared__ float red[64];
+  float acc = 0.f;
+  for (int64_t g = threadIdx.x; g < a.groups; g += 1024) {
+    float lg = 0.f;
+    for (int q = 0; q < a.Vg; ++q) {
+      float qs = 0.f, cr = 0.f;
+      for (int sp = 0; sp < a.ksplit; ++sp) {
+        const float* p = partial + ((g * a.ksplit + sp) * a.Vg + q) * 2;
+        qs += p[0];
+        cr += p[1];
+      }
+      float lse_sum = 0.f;
+      for (int v = 0; v < a.V; ++v)
+        if (!(a.exclude_same && v == q)) lse_sum += a.lse_s[v * a.groups + g];
+      // sum over pairs of [ lse_v * sum_k q - sum_k q * us ] ; us = s*inv_tau_s
+      lg += qs * lse_sum - cr * inv_tau_s;
+    }
+    acc += lg * (a.group_w ? a.group_w[g] : 1.f);
+  }
+  float tot = block_sum<1024>(acc, red);
+  if (threadIdx.x == 0) *loss_out = tot * a.norm;
+}
+
+template <typename TS, typename TT, bool kVec>
+__global__ void __launch_bounds__(kCeThreads)
+ce_bwd_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, CeArgs a,
+              const float* __restrict__ upstream, TS* __restrict__ grad) {
+  const int64_t g = blockIdx.x;
+  const int split = blockIdx.y;
+  const int64_t per = ((a.K + a.ksplit - 1) / a.ksplit + 3) & ~int64_t(3);
+  const int64_t k0 = split * per, k1 = (k0 + per < a.K) ? k0 + per : a.K;
+  const float w = (a.group_w ? a.group_w[g] : 1.f) * a.norm * (*upstream) * (a.s2 * DINOX_LN2);
+  float rb2[kMaxGlobalViews];
+#pragma unroll
+  for (int q = 0; q < kMaxGlobalViews; ++q)
+    rb2[q] = (q < a.Vg) ? a.rowbias_t[q * a.groups + g] * DINOX_LOG2E : 0.f;
+
+  for (int64_t k = k0 + (int64_t)threadIdx.x * 4; k < k1; k += (int64_t)kCeThreads * 4) {
+    float cb[4];
+    loadf4<kVec>(a.colbias_t, k, k1, cb, 0.f);
+    float qv[kMaxGlobalViews][4];
+    float qtot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) {
+        float t[4];
+        load4<TT, kVec>(teacher + (q * a.groups + g) * a.ld_t, k, k1, t, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float u = fmaf(t[j], a.t2, -cb[j] * DINOX_LOG2E) - rb2[q];
+          qv[q][j] = exp2f(u);
+          qtot[j] += qv[q][j];
+        }
+      }
+    }
+    for (int v = 0; v < a.V; ++v) {
+      float s[4], o[4];
+      const int64_t r = v * a.groups + g;
+      load4<TS, kVec>(student + r * a.ld_s, k, k1, s, 0.f);
+      const float lse2 = a.lse_s[r] * DINOX_LOG2E;
+      const bool own = a.exclude_same && v < a.Vg;
+      const float nq = (float)(a.Vg - (own ? 1 : 0));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float p = exp2f(fmaf(s[j], a.s2, -lse2));
+        float target = qtot[j];
+#pragma unroll
+        for (int q = 0; q < kMaxGlobalViews; ++q)
+          if (own && q == v) target -= qv[q][j];
+        o[j] = w * (nq * p - target);
+      }
+      if (kVec) {
+        Vec4<TS>::store(grad + r * a.ld_g + k, o);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k + j < k1) grad[r * a.ld_g + k + j] = from_f32<TS>(o[j]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch helpers
+// ---------------------------------------------------------------------------------------------
+static inline size_t elt_size(int dtype) { return dtype == DINOX_F32 ? 4 : 2; }
+static inline bool vec_ok(const void* p, int dtype, int64_t K, int64_t ld) {
+  return (K % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) % (4 * elt_size(dtype))) == 0);
+}
+static inline bool fvec_ok(const float* p) { return p == nullptr || aligned16(p); }
+
+static int pick_ksplit(int64_t groups, int64_t K) {
+  int target = 2 * num_sms();
+  int64_t ks = (target + groups - 1) / groups;
+  int64_t maxs = K / 1024;
+  if (maxs < 1) maxs = 1;
+  if (ks > maxs) ks = maxs;
+  if (ks < 1) ks = 1;
+  if (ks > 64) ks = 64;
+  return (int)ks;
+}
+
+#define DISPATCH_T(dtype, T, ...)                                  \
+  switch (dtype) {                                                 \
+    case DINOX_F32: { using T = float; __VA_ARGS__; break; }       \
+    case DINOX_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; } \
+    case DINOX_F16: { using T = __half; __VA_ARGS__; break; }      \
+    default: set_error("unknown dtype code %d", dtype); return DINOX_E_BADARG; \
+  }
+
+}  // namespace dinox
+
+extern "C" {
+using namespace dinox;
+
+int dinox_rows_lse(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, float inv_tau,
+                   const float* colbias, float* lse, float* entropy, dinox_stream_t stream) {
+  DINOX_REQUIRE(x && lse && rows >= 0 && K > 0 && ld >= K, DINOX_E_BADARG, "rows_lse: bad arguments");
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (rows == 0) return DINOX_OK;
+  DINOX_REQUIRE(rows < (1ll << 31), DINOX_E_BADARG, "rows_lse: too many rows");
+  const bool vec = vec_ok(x, dtype, K, ld) && fvec_ok(colbias);
+  const float s2 = inv_tau * DINOX_LOG2E;
+  DISPATCH_T(dtype, T, {
+    if (vec) rows_lse_kernel<T, true><<<(unsigned)rows, kRowThreads, 0, stream>>>((const T*)x, K, ld, s2, colbias, lse, entropy);
+    else rows_lse_kernel<T, false><<<(unsigned)rows, kRowThreads, 0, stream>>>((const T*)x, K, ld, s2, colbias, lse, entropy);
+  });
+  return check_launch("rows_lse_kernel", stream);
+}
+
+int dinox_cols_lse(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, float inv_tau,
+                   const float* rowbias, float* out, dinox_stream_t stream) {
+  DINOX_REQUIRE(x && out && rows > 0 && K > 0 && ld >= K, DINOX_E_BADARG, "cols_lse: bad arguments");
+  int rc = require_sm100();
+  if (rc) return rc;
+  const bool vec = vec_ok(x, dtype, K, ld);
+  const unsigned grid = (unsigned)((K + kColThreads * 4 - 1) / (kColThreads * 4));
+  const float s2 = inv_tau * DINOX_LOG2E;
+  DISPATCH_T(dtype, T, {
+    if (vec) cols_lse_kernel<T, true><<<grid, kColThreads, 0, stream>>>((const T*)x, rows, K, ld, s2, rowbias, out);
+    else cols_lse_kernel<T, false><<<grid, kColThreads, 0, stream>>>((const T*)x, rows, K, ld, s2, rowbias, out);
+  });
+  return check_launch("cols_lse_kernel", stream);
+}
+
+int dinox_lse_combine(const float* gathered, int world, int64_t K, float add, float* out,
+                      dinox_stream_t stream) {
+  DINOX_REQUIRE(gathered && out && world > 0 && K > 0, DINOX_E_BADARG, "lse_combine: bad arguments");
+  lse_combine_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(gathered, world, K, add, out);
+  return check_launch("lse_combine_kernel", stream);
+}
+
+int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, float* out,
+                   dinox_stream_t stream) {
+  DINOX_REQUIRE(x && out && rows > 0 && K > 0 && ld >= K, DINOX_E_BADARG, "cols_sum: bad arguments");
+  int rc = require_sm100();
+  if (rc) return rc;
+  const bool vec = vec_ok(x, dtype, K, ld);
+  const unsigned grid = (unsigned)((K + kColThreads * 4 - 1) / (kColThreads * 4));
+  DISPATCH_T(dtype, T, {
+    if (vec) cols_sum_kernel<T, true><<<grid, kColThreads, 0, stream>>>((const T*)x, rows, K, ld, out);
+    else cols_sum_kernel<T, false><<<grid, kColThreads, 0, stream>>>((const T*)x, rows, K, ld, out);
+  });
+  return check_launch("cols_sum_kernel", stream);
+}
+
+int dinox_center_ema(float* center, const float* colsum, float inv_rows, float m, int64_t K,
+                     dinox_stream_t stream) {
+  DINOX_REQUIRE(center && colsum && K > 0, DINOX_E_BADARG, "center_ema: bad arguments");
+  // (1 - m) evaluated in double then rounded, as Python does for `1 - self.center_momentum`
+  const float om = (float)(1.0 - (double)m);
+  center_ema_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(center, colsum, inv_rows, m, om, K);
+  return check_launch("center_ema_kernel", stream);
+}
+
+int dinox_axpb(const float* a, float alpha, float beta, float* out, int64_t n, dinox_stream_t stream) {
+  DINOX_REQUIRE(a && out && n > 0, DINOX_E_BADARG, "axpb: bad arguments");
+  axpb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, alpha, beta, out, n);
+  return check_launch("axpb_kernel", stream);
+}
+
+size_t dinox_ce_workspace_bytes(int64_t groups, int64_t K) {
+  if (groups <= 0 || K <= 0) return 0;
+  return (size_t)groups * 64 * kMaxGlobalViews * 2 * sizeof(float);
+}
+
+static int ce_args(CeArgs& a, const void* student, const void* teacher, int64_t groups, int V, int Vg,
+                   int64_t K, int64_t ld_s, int64_t ld_t, float inv_tau_s, float inv_tau_t,
+                   const float* colbias_t, const float* rowbias_t, const float* lse_s,
+                   const float* group_w, float norm, int exclude_same) {
+  DINOX_REQUIRE(student && teacher && rowbias_t && lse_s, DINOX_E_BADARG, "ce: null pointer");
+  DINOX_REQUIRE(groups > 0 && K > 0 && V >= 1 && Vg >= 1 && Vg <= kMaxGlobalViews && Vg <= V,
+                DINOX_E_BADARG, "ce: need groups>0, K>0, 1<=Vg<=%d, Vg<=V (got groups=%lld V=%d Vg=%d)",
+                kMaxGlobalViews, (long long)groups, V, Vg);
+  DINOX_REQUIRE(ld_s >= K && ld_t >= K, DINOX_E_BADARG, "ce: leading dimension < K");
+  DINOX_REQUIRE(groups < (1ll << 31), DINOX_E_BADARG, "ce: too many groups");
+  a.groups = groups; a.K = K; a.ld_s = ld_s; a.ld_t = ld_t; a.ld_g = ld_s;
+  a.V = V; a.Vg = Vg; a.exclude_same = exclude_same ? 1 : 0;
+  a.ksplit = pick_ksplit(groups, K);
+  a.s2 = inv_tau_s * DINOX_LOG2E; a.t2 = inv_tau_t * DINOX_LOG2E;
+  a.colbias_t = colbias_t; a.rowbias_t = rowbias_t; a.lse_s = lse_s; a.group_w = group_w; a.norm = norm;
+  return require_sm100();
+}
+
+int dinox_ce_fwd(const void* student, int s_dtype, const void* teacher, int t_dtype, int64_t groups,
+                 int V, int Vg, int64_t K, int64_t ld_s, int64_t ld_t, float inv_tau_s, float inv_tau_t,
+                 const float* colbias_t, const float* rowbias_t, const float* lse_s,
+                 const float* group_w, float norm, int exclude_same, float* loss_out, void* workspace,
+                 dinox_stream_t stream) {
+  CeArgs a;
+  int rc = ce_args(a, student, teacher, groups, V, Vg, K, ld_s, ld_t, inv_tau_s, inv_tau_t, colbias_t,
+                   rowbias_t, lse_s, group_w, norm, exclude_same);
+  if (rc) return rc;
+  DINOX_REQUIRE(loss_out && workspace, DINOX_E_BADARG, "ce_fwd: null output/workspace");
+  const bool vec = vec_ok(student, s_dtype, K, ld_s) && vec_ok(teacher, t_dtype, K, ld_t) && fvec_ok(colbias_t);
+  dim3 grid((unsigned)groups, (unsigned)a.ksplit);
+  float* partial = (float*)workspace;
+  DISPATCH_T(s_dtype, TS, DISPATCH_T(t_dtype, TT, {
+    if (vec) ce_fwd_kernel<TS, TT, true><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, partial);
+    else ce_fwd_kernel<TS, TT, false><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, partial);
+  }));
+  rc = check_launch("ce_fwd_kernel", stream);
+  if (rc) return rc;
+  ce_finalize_kernel<<<1, 1024, 0, stream>>>(partial, a, inv_tau_s, loss_out);
+  return check_launch("ce_finalize_kernel", stream);
+}
+
+int dinox_ce_bwd(const void* student, int s_dtype, const void* teacher, int t_dtype, int64_t groups,
+                 int V, int Vg, int64_t K, int64_t ld_s, int64_t ld_t, float inv_tau_s, float inv_tau_t,
+                 const float* colbias_t, const float* rowbias_t, const float* lse_s,
+                 const float* group_w, float norm, int exclude_same, const float* upstream, void* grad,
+                 int64_t ld_g, dinox_stream_t stream) {
+  CeArgs a;
+  int rc = ce_args(a, student, teacher, groups, V, Vg, K, ld_s, ld_t, inv_tau_s, inv_tau_t, colbias_t,
+                   rowbias_t, lse_s, group_w, norm, exclude_same);
+  if (rc) return rc;
+  DINOX_REQUIRE(upstream && grad && ld_g >= K, DINOX_E_BADARG, "ce_bwd: null upstream/grad or ld_g < K");
+  a.ld_g = ld_g;
+  const bool vec = vec_ok(student, s_dtype, K, ld_s) && vec_ok(teacher, t_dtype, K, ld_t) &&
+                   vec_ok(grad, s_dtype, K, ld_g) && fvec_ok(colbias_t);
+  dim3 grid((unsigned)groups, (unsigned)a.ksplit);
+  DISPATCH_T(s_dtype, TS, DISPATCH_T(t_dtype, TT, {
+    if (vec) ce_bwd_kernel<TS, TT, true><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, upstream, (TS*)grad);
+    else ce_bwd_kernel<TS, TT, false><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, upstream, (TS*)grad);
+  }));
+  return check_launch("ce_bwd_kernel", stream);
+}
+
+}  // extern "C"

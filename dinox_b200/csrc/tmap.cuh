@@ -1,0 +1,64 @@
+// Host-side TMA tensor-map construction (cuTensorMapEncodeTiled through the runtime's driver
+// entry point, so the library does not link libcuda directly).
+#pragma once
+#include "common.cuh"
+#include <cudaTypedefs.h>
+
+namespace dinox {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor, row-major: `rows` x `cols` with leading dimension ld (elements); the box is
+// box_rows x 64 elements (128 B inner extent, SWIZZLE_128B).  OOB elements read as zero.
+inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                             int box_rows, const char* what) {
+  PFN_encodeTiled enc = get_encode_fn();
+  DINOX_REQUIRE(enc, DINOX_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  DINOX_REQUIRE(aligned16(base), DINOX_E_ALIGN, "%s: base pointer not 16-byte aligned", what);
+  DINOX_REQUIRE((ld * 2) % 16 == 0, DINOX_E_ALIGN, "%s: leading dimension %lld not a multiple of 8 elements",
+                what, (long long)ld);
+  DINOX_REQUIRE(rows > 0 && cols > 0 && box_rows > 0 && box_rows <= 256, DINOX_E_BADARG, "%s: bad extent", what);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DINOX_REQUIRE(r == CUDA_SUCCESS, DINOX_E_CUDA, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
+  return DINOX_OK;
+}
+
+// 3-D bf16 tensor (batch, rows, cols) row-major with batch stride `bs` elements; box 1 x box_rows x 64.
+inline int make_tmap_bf16_3d(CUtensorMap* out, const void* base, int64_t batch, int64_t rows, int64_t cols,
+                             int64_t ld, int64_t bs, int box_rows, const char* what) {
+  PFN_encodeTiled enc = get_encode_fn();
+  DINOX_REQUIRE(enc, DINOX_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  DINOX_REQUIRE(aligned16(base), DINOX_E_ALIGN, "%s: base pointer not 16-byte aligned", what);
+  DINOX_REQUIRE((ld * 2) % 16 == 0 && (bs * 2) % 16 == 0, DINOX_E_ALIGN, "%s: strides not 16-byte multiples", what);
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bs * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DINOX_REQUIRE(r == CUDA_SUCCESS, DINOX_E_CUDA, "%s: cuTensorMapEncodeTiled(3d) failed with CUresult %d", what, (int)r);
+  return DINOX_OK;
+}
+
+}  // namespace dinox

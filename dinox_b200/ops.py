@@ -1,0 +1,223 @@
+"""Thin torch-tensor wrappers over the C ABI (include/dinox_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every computation below is one
+call into libdinox_b200.so with raw pointers.  Nothing in this file computes on the CPU or
+through ATen - if the library is missing or the device is not a B200 the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _ext
+
+DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+LOG2E = 1.4426950408889634
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _ext.DinoxError("dinox_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _rowmajor(t: torch.Tensor) -> int:
+    """leading dimension of a 2-D tensor whose last dim is contiguous"""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _ext.DinoxError(f"expected a 2-D tensor with contiguous rows, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def launch_count() -> int:
+    return int(_ext.lib().dinox_launch_count())
+
+
+def launch_count_reset() -> None:
+    _ext.lib().dinox_launch_count_reset()
+
+
+# ------------------------------------------------------------------------------------------------
+# a8 EMA
+# ------------------------------------------------------------------------------------------------
+class EmaPlan:
+    """Multi-tensor EMA plan over (student, teacher) parameter pairs (fp32, same shapes)."""
+
+    def __init__(self, student: Sequence[torch.Tensor], teacher: Sequence[torch.Tensor]):
+        student, teacher = list(student), list(teacher)
+        if len(student) != len(teacher):
+            raise ValueError("student/teacher parameter lists differ in length")
+        _chk_cuda(*student, *teacher)
+        for s, t in zip(student, teacher):
+            if s.shape != t.shape or s.dtype != torch.float32 or t.dtype != torch.float32:
+                raise ValueError("EMA needs fp32 parameters of identical shapes")
+            if not (s.is_contiguous() and t.is_contiguous()):
+                raise ValueError("EMA needs contiguous parameters")
+        n = len(student)
+        ps = (ctypes.c_void_p * n)(*[s.data_ptr() for s in student])
+        pt = (ctypes.c_void_p * n)(*[t.data_ptr() for t in teacher])
+        ne = (ctypes.c_int64 * n)(*[s.numel() for s in student])
+        self._h = ctypes.c_void_p()
+        self._keys = [(s.data_ptr(), t.data_ptr(), s.numel()) for s, t in zip(student, teacher)]
+        _ext.call("dinox_ema_plan_create", ps, pt, ne, n, ctypes.byref(self._h))
+        self.numel = int(_ext.lib().dinox_ema_plan_numel(self._h))
+
+    def matches(self, student, teacher) -> bool:
+        keys = [(s.data_ptr(), t.data_ptr(), s.numel()) for s, t in zip(student, teacher)]
+        return keys == self._keys
+
+    def apply(self, m: float) -> None:
+        # alpha = 1.0 - m is evaluated in double like the reference's python expression
+        _ext.call("dinox_ema_apply", self._h, float(m), float(1.0 - float(m)), _stream())
+
+    def __del__(self):
+        try:
+            if self._h:
+                _ext.lib().dinox_ema_plan_destroy(self._h)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# row / column statistics on materialised logits
+# ------------------------------------------------------------------------------------------------
+def rows_lse(x: torch.Tensor, inv_tau: float, colbias: Optional[torch.Tensor] = None,
+             want_entropy: bool = False):
+    _chk_cuda(x, colbias)
+    ld = _rowmajor(x)
+    rows, K = x.shape
+    lse = torch.empty(rows, dtype=torch.float32, device=x.device)
+    ent = torch.empty(rows, dtype=torch.float32, device=x.device) if want_entropy else None
+    _ext.call("dinox_rows_lse", _p(x), DT[x.dtype], rows, K, ld, float(inv_tau), _p(colbias), _p(lse), _p(ent), _stream())
+    return (lse, ent) if want_entropy else lse
+
+
+def cols_lse(x: torch.Tensor, inv_tau: float, rowbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk_cuda(x, rowbias)
+    ld = _rowmajor(x)
+    rows, K = x.shape
+    out = torch.empty(K, dtype=torch.float32, device=x.device)
+    _ext.call("dinox_cols_lse", _p(x), DT[x.dtype], rows, K, ld, float(inv_tau), _p(rowbias), _p(out), _stream())
+    return out
+
+
+def lse_combine(gathered: torch.Tensor, add: float = 0.0) -> torch.Tensor:
+    world, K = gathered.shape
+    out = torch.empty(K, dtype=torch.float32, device=gathered.device)
+    _ext.call("dinox_lse_combine", _p(gathered), world, K, float(add), _p(out), _stream())
+    return out
+
+
+def cols_sum(x: torch.Tensor) -> torch.Tensor:
+    _chk_cuda(x)
+    ld = _rowmajor(x)
+    rows, K = x.shape
+    out = torch.empty(K, dtype=torch.float32, device=x.device)
+    _ext.call("dinox_cols_sum", _p(x), DT[x.dtype], rows, K, ld, _p(out), _stream())
+    return out
+
+
+def center_ema_(center: torch.Tensor, colsum: torch.Tensor, global_rows: int, momentum: float) -> None:
+    _chk_cuda(center, colsum)
+    K = center.numel()
+    _ext.call("dinox_center_ema", _p(center), _p(colsum), float(1.0 / global_rows), float(momentum), K, _stream())
+
+
+def axpb(a: torch.Tensor, alpha: float, beta: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    out = torch.empty_like(a) if out is None else out
+    _ext.call("dinox_axpb", _p(a), float(alpha), float(beta), _p(out), a.numel(), _stream())
+    return out
+
+
+def ce_fwd(student, teacher, groups: int, V: int, Vg: int, inv_tau_s: float, inv_tau_t: float,
+           colbias_t, rowbias_t, lse_s, group_w, norm: float, exclude_same: bool) -> torch.Tensor:
+    _chk_cuda(student, teacher)
+    K = student.shape[1]
+    ws = torch.empty(int(_ext.lib().dinox_ce_workspace_bytes(groups, K)), dtype=torch.uint8, device=student.device)
+    loss = torch.empty((), dtype=torch.float32, device=student.device)
+    _ext.call("dinox_ce_fwd", _p(student), DT[student.dtype], _p(teacher), DT[teacher.dtype], groups, V, Vg, K,
+              _rowmajor(student), _rowmajor(teacher), float(inv_tau_s), float(inv_tau_t), _p(colbias_t),
+              _p(rowbias_t), _p(lse_s), _p(group_w), float(norm), int(exclude_same), _p(loss), _p(ws), _stream())
+    return loss
+
+
+def ce_bwd(student, teacher, groups: int, V: int, Vg: int, inv_tau_s: float, inv_tau_t: float,
+           colbias_t, rowbias_t, lse_s, group_w, norm: float, exclude_same: bool,
+           upstream: torch.Tensor) -> torch.Tensor:
+    K = student.shape[1]
+    grad = torch.empty_like(student, memory_format=torch.contiguous_format)
+    up = upstream.to(torch.float32).reshape(1).contiguous()
+    _ext.call("dinox_ce_bwd", _p(student), DT[student.dtype], _p(teacher), DT[teacher.dtype], groups, V, Vg, K,
+              _rowmajor(student), _rowmajor(teacher), float(inv_tau_s), float(inv_tau_t), _p(colbias_t),
+              _p(rowbias_t), _p(lse_s), _p(group_w), float(norm), int(exclude_same), _p(up), _p(grad),
+              _rowmajor(grad), _stream())
+    return grad
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMMs
+# ------------------------------------------------------------------------------------------------
+def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False,
+              out: Optional[torch.Tensor] = None, out_dtype=torch.float32, accumulate: bool = False,
+              alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
+              bias_n: Optional[torch.Tensor] = None, m_fastest: bool = True) -> torch.Tensor:
+    """C[M,N] (+)= alpha * A @ B^T + bias_n.   a: (M,K) [or (K,M) if a_mn_major], b: (N,K) [or (K,N)]."""
+    _chk_cuda(a, b, out, bias_n, alpha_dev)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise _ext.DinoxError("gemm_bf16 needs bf16 operands")
+    M, Ka = (a.shape[1], a.shape[0]) if a_mn_major else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn_major else b.shape
+    if Ka != Kb:
+        raise _ext.DinoxError(f"gemm_bf16: reduction dims differ ({Ka} vs {Kb})")
+    if out is None:
+        if accumulate:
+            raise _ext.DinoxError("accumulate=True needs an output tensor")
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    _ext.call("dinox_gemm_bf16", _p(a), _p(b), _p(out), M, N, Ka, _rowmajor(a), _rowmajor(b), _rowmajor(out),
+              int(a_mn_major), int(b_mn_major), DT[out.dtype], int(accumulate), float(alpha), _p(alpha_dev),
+              _p(bias_n), int(m_fastest), _stream())
+    return out
+
+
+def head_stats(h: torch.Tensor, w2: torch.Tensor, inv_tau: float, col2: Optional[torch.Tensor] = None,
+               want_nat: bool = True, want_log2: bool = True):
+    """Row-wise LSE of (h @ w2^T)*inv_tau + col2/log2e without materialising the logits."""
+    _chk_cuda(h, w2, col2)
+    rows, D = h.shape
+    K = w2.shape[0]
+    ws = torch.empty(int(_ext.lib().dinox_head_stats_workspace_bytes(rows, K)), dtype=torch.uint8, device=h.device)
+    nat = torch.empty(rows, dtype=torch.float32, device=h.device) if want_nat else None
+    l2 = torch.empty(rows, dtype=torch.float32, device=h.device) if want_log2 else None
+    _ext.call("dinox_head_stats", _p(h), _p(w2), rows, K, D, _rowmajor(h), _rowmajor(w2), float(inv_tau), _p(col2),
+              _p(nat), _p(l2), _p(ws), _stream())
+    return nat, l2
+
+
+def head_grad(w2s, w2t, hs_e, ht_e, inv_tau_s, inv_tau_t, cs2, ct2, ct2_alt, alt_from, lse2_e, rb2_e, cw_e,
+              loss_out: torch.Tensor, loss_accumulate: bool = False, want_db2: bool = True,
+              gt: Optional[torch.Tensor] = None):
+    """Pass 2.  Returns (Gt (K, E_pad) bf16, db2_partial or None)."""
+    _chk_cuda(w2s, w2t, hs_e, ht_e)
+    K, D = w2s.shape
+    E = hs_e.shape[0]
+    e_pad = (E + 127) // 128 * 128
+    if gt is None:
+        gt = torch.empty(K, e_pad, dtype=torch.bfloat16, device=w2s.device)
+    n_et = e_pad // 128
+    db2p = torch.empty(2 * n_et, K, dtype=torch.float32, device=w2s.device) if want_db2 else None
+    ws = torch.empty(int(_ext.lib().dinox_head_grad_workspace_bytes(K, E)), dtype=torch.uint8, device=w2s.device)
+    _ext.call("dinox_head_grad", _p(w2s), _p(w2t), _p(hs_e), _p(ht_e), K, D, E, _rowmajor(w2s), _rowmajor(w2t),
+              _rowmajor(hs_e), _rowmajor(ht_e), float(inv_tau_s), float(inv_tau_t), _p(cs2), _p(ct2), _p(ct2_alt),
+              int(alt_from), _p(lse2_e), _p(rb2_e), _p(cw_e), _p(gt), _rowmajor(gt), _p(db2p), _p(loss_out),
+              int(loss_accumulate), _p(ws), _stream())
+    return gt, db2p

@@ -1,0 +1,169 @@
+/* dinox_b200 - C ABI of the B200-native (sm_100a) DINO-X loss head.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * launches asynchronously on the given stream, never allocates persistent device memory except
+ * through an explicit plan/workspace object, and returns DINOX_OK or a negative DINOX_E_* code
+ * (message via dinox_last_error_string()).  All device pointers must be 16-byte aligned and the
+ * tensors contiguous unless a leading dimension is given.  There is no CPU fallback.
+ *
+ * Each function cites the reference code it replaces (paths relative to timlawrenz/DINO-X).
+ * Python binding: dinox_b200/_ext.py (ctypes).  Reference-side stub: INTEGRATION.md.
+ */
+#ifndef DINOX_B200_H_
+#define DINOX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef DINOX_API
+#define DINOX_API __attribute__((visibility("default")))
+#endif
+
+/* cudaStream_t without pulling in cuda_runtime.h for pure-C consumers */
+typedef struct CUstream_st* dinox_stream_t;
+
+#define DINOX_OK 0
+#define DINOX_E_BADARG (-1)      /* bad shape / null pointer / unsupported size */
+#define DINOX_E_ALIGN (-2)       /* pointer or leading dimension not 16-byte aligned */
+#define DINOX_E_ARCH (-3)        /* device is not sm_100 (B200); there is no fallback */
+#define DINOX_E_CUDA (-4)        /* CUDA runtime/driver error, see dinox_last_error_string */
+#define DINOX_E_UNSUPPORTED (-5) /* valid request that this build does not implement */
+
+/* element types of tensors that may arrive in several precisions */
+#define DINOX_F32 0
+#define DINOX_BF16 1
+#define DINOX_F16 2
+
+DINOX_API int dinox_version(void);
+DINOX_API const char* dinox_last_error_string(void);
+/* DINOX_OK iff the current device is compute capability 10.x */
+DINOX_API int dinox_device_check(void);
+/* number of kernels this library has launched on the calling thread since the last reset */
+DINOX_API int64_t dinox_launch_count(void);
+DINOX_API void dinox_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a8  EMA teacher update.  Replaces the per-tensor loop
+ *     `p_t.data.mul_(m).add_(p_s.data, alpha=1-m)` (scripts/phase5_big_run.py:1798-1802,
+ *     scripts/phase3_micro_run.py:152-155) by ONE multi-tensor launch.
+ *     A plan uploads a chunk table (pointer pairs, 128-bit vectorised) once; parameters keep
+ *     their addresses across steps.  All tensors fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dinox_ema_plan dinox_ema_plan;
+DINOX_API int dinox_ema_plan_create(const void* const* student, void* const* teacher,
+                                    const int64_t* numel, int n_tensors, dinox_ema_plan** out);
+DINOX_API int dinox_ema_plan_destroy(dinox_ema_plan* plan);
+DINOX_API int64_t dinox_ema_plan_numel(const dinox_ema_plan* plan);
+/* p_t <- fl(p_t*m) (+) one_minus_m*p_s  (fma), in place */
+DINOX_API int dinox_ema_apply(const dinox_ema_plan* plan, float m, float one_minus_m,
+                              dinox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row/column statistics on MATERIALISED logits (the DINOLoss.forward(student_out, teacher_out)
+ * drop-in path, scripts/phase5_big_run.py:692-720).  u[i,k] = x[i,k]*inv_tau - colbias[k]
+ * (colbias may be NULL).  ld = row stride in elements.
+ * ------------------------------------------------------------------------------------------ */
+/* a2/a3: lse[i] = ln sum_k exp(u[i,k] - rowshift) ... returns natural-log LSE per row; optional
+ * entropy[i] = -sum_k p log p of softmax(u[i,:]) (a10, scripts/phase5_big_run.py:1843-1853). */
+DINOX_API int dinox_rows_lse(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld,
+                             float inv_tau, const float* colbias, float* lse, float* entropy,
+                             dinox_stream_t stream);
+/* E2: per-column LSE over rows of (u[i,k] - rowbias[i]); rowbias may be NULL. out[k] natural log */
+DINOX_API int dinox_cols_lse(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld,
+                             float inv_tau, const float* rowbias, float* out,
+                             dinox_stream_t stream);
+/* combine per-rank LSE vectors gathered as (world, K): out[k] = ln sum_r exp(g[r,k]) + add */
+DINOX_API int dinox_lse_combine(const float* gathered, int world, int64_t K, float add, float* out,
+                                dinox_stream_t stream);
+/* a5: column sums of x (rows, K) -> out (K) fp32 (torch.mean(teacher_output, dim=0) numerator,
+ * scripts/phase5_big_run.py:688) */
+DINOX_API int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld,
+                             float* out, dinox_stream_t stream);
+/* a5: center <- center*m + (colsum*inv_rows)*(1-m)   (scripts/phase5_big_run.py:689) */
+DINOX_API int dinox_center_ema(float* center, const float* colsum, float inv_rows, float m,
+                               int64_t K, dinox_stream_t stream);
+/* vector helper: out[k] = a[k]*alpha + beta (colbias = center*inv_tau etc.) */
+DINOX_API int dinox_axpb(const float* a, float alpha, float beta, float* out, int64_t n,
+                         dinox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a4 / E1 / E3: cross-entropy between teacher and student rows on materialised logits.
+ * Rows are organised in `groups` (multi-crop: group = image b, student row v*groups+b, teacher
+ * row iq*groups+b; iBOT: group = masked token, V = Vg = 1).  Pairs (iq, v) with v != iq are
+ * summed when exclude_same != 0, all pairs otherwise:
+ *   loss = norm * sum_g w[g] * sum_pairs ( lse_s[v,g] - sum_k q[iq,g,k] * us[v,g,k] )
+ *   q[i,k] = exp(t[i,k]*inv_tau_t - colbias_t[k] - rowbias_t[i]),  us = s*inv_tau_s
+ * scripts/phase5_big_run.py:703-717 is (V=Vg=2, exclude_same=1, norm=1/(2B), w=NULL).
+ * `loss_out` is one fp32 on device.  workspace: dinox_ce_workspace_bytes(groups, K) bytes.
+ * ------------------------------------------------------------------------------------------ */
+DINOX_API size_t dinox_ce_workspace_bytes(int64_t groups, int64_t K);
+DINOX_API int dinox_ce_fwd(const void* student, int s_dtype, const void* teacher, int t_dtype,
+                           int64_t groups, int V, int Vg, int64_t K, int64_t ld_s, int64_t ld_t,
+                           float inv_tau_s, float inv_tau_t, const float* colbias_t,
+                           const float* rowbias_t, const float* lse_s, const float* group_w,
+                           float norm, int exclude_same, float* loss_out, void* workspace,
+                           dinox_stream_t stream);
+/* grad[v,g,k] = (*upstream) * norm * w[g] * inv_tau_s * ( n_q(v) * softmax(us)[k] - sum_{iq} q[iq,g,k] )
+ * written in the student's dtype (autograd of log_softmax(s/tau), :706). upstream: device fp32. */
+DINOX_API int dinox_ce_bwd(const void* student, int s_dtype, const void* teacher, int t_dtype,
+                           int64_t groups, int V, int Vg, int64_t K, int64_t ld_s, int64_t ld_t,
+                           float inv_tau_s, float inv_tau_t, const float* colbias_t,
+                           const float* rowbias_t, const float* lse_s, const float* group_w,
+                           float norm, int exclude_same, const float* upstream, void* grad,
+                           int64_t ld_g, dinox_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * a1 and the dense contractions of its autograd: bf16 x bf16 -> fp32 tcgen05 GEMM.
+ *   C[M,N] (+)= alpha * (*alpha_dev) * sum_k A[m,k] B[n,k] + bias_n[n]
+ * A operand: a_mn_major=0 -> stored (M,K) row-major with ld lda; 1 -> stored (K,M) row-major.
+ * B operand likewise with N.  out_dtype DINOX_F32 or DINOX_BF16.  m_fastest picks the tile
+ * walk order (which operand stays L2/SMEM-hot).  Replaces nn.Linear forward/backward GEMMs of
+ * the projection head (zoo/arch.py:252-256) that PyTorch dispatches to cuBLAS.
+ * ------------------------------------------------------------------------------------------ */
+DINOX_API int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K,
+                              int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major,
+                              int out_dtype, int accumulate, float alpha, const float* alpha_dev,
+                              const float* bias_n, int m_fastest, dinox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused pass 1: prototype logits (H . W2^T, bf16 operands, fp32 TMEM accumulators) with the
+ * row-wise online log-sum-exp of  u = logits*inv_tau + col2/log2e  computed in the GEMM epilogue;
+ * the (rows x K) logit matrix is never written.  col2[k] is a per-prototype offset in LOG2 units
+ * (e.g. (b2[k]-center[k])*inv_tau*log2e).  Outputs natural-log LSE and/or log2 LSE per row.
+ * Replaces F.softmax/F.log_softmax statistics of scripts/phase5_big_run.py:703,706.
+ * ------------------------------------------------------------------------------------------ */
+DINOX_API size_t dinox_head_stats_workspace_bytes(int64_t rows, int64_t K);
+DINOX_API int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D,
+                               int64_t ldh, int64_t ldw, float inv_tau, const float* col2,
+                               float* lse_nat, float* lse2, void* workspace, dinox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused pass 2: for E (student row, teacher row) entries recompute both logit tiles side by side
+ * in TMEM and emit, without materialising logits or probabilities in HBM:
+ *   Gt[k,e]  = cw[e]*inv_tau_s*( softmax_s[e,k] - q_t[e,k] )          (bf16, (K, ldg) = dL/dlogits^T)
+ *   loss     (+)= sum_e cw[e] * sum_k q_t[e,k] * (-ln softmax_s[e,k])  (one fp32 on device)
+ *   db2_partial[(2*ceil(E/128)), K]  column partial sums of Gt (reduce with dinox_cols_sum), optional
+ * with softmax_s = 2^(S*inv_tau_s*log2e + cs2[k] - lse2[e]), q_t = 2^(T*inv_tau_t*log2e + ct2[k] - rb2[e]);
+ * entries >= alt_from (multiple of 128) use ct2_alt (iBOT patch centre).  HsE/HtE: (E, D) bf16
+ * gathered head activations of the entry's student / teacher row.  Cross-entropy of
+ * scripts/phase5_big_run.py:703-717 and its autograd (grad of log_softmax) in one kernel.
+ * ------------------------------------------------------------------------------------------ */
+DINOX_API size_t dinox_head_grad_workspace_bytes(int64_t K, int64_t E);
+DINOX_API int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const void* HtE,
+                              int64_t K, int64_t D, int64_t E, int64_t ldw_s, int64_t ldw_t,
+                              int64_t ldh_s, int64_t ldh_t, float inv_tau_s, float inv_tau_t,
+                              const float* cs2, const float* ct2, const float* ct2_alt,
+                              int64_t alt_from, const float* lse2_e, const float* rb2_e,
+                              const float* cw_e, void* Gt, int64_t ldg, float* db2_partial,
+                              float* loss_out, int loss_accumulate, void* workspace,
+                              dinox_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINOX_B200_H_ */

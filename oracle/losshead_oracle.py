@@ -146,20 +146,16 @@ def sinkhorn_knopp(teacher_out: torch.Tensor, teacher_temp: float, n_iterations:
     """Q = exp(t/tau)^T; Q/=sum(Q); repeat n_it x { Q/=rowsum (per prototype); Q/=K;
     Q/=colsum (per sample); Q/=B }; Q*=B.  ``teacher_out`` holds the GLOBAL batch (a
     data-parallel run all-reduces the per-prototype sums, so concatenating the ranks' rows is
-    the definition of the distributed result).  A common shift by the global max keeps exp in
-    range; it cancels in the first normalisation.  Returns (rows, K) with rows summing to 1."""
-    t = teacher_out.float() / teacher_temp
-    t = t - t.max()
-    Q = torch.exp(t).t()  # (K, Bg)
-    K, Bg = Q.shape
-    Q = Q / Q.sum()
+    the definition of the distributed result).  Evaluated in the log domain (a common shift
+    cancels in the first normalisation, so this is the same algebra without under/overflow).  Returns (rows, K) with rows summing to 1."""
+    logq = (teacher_out.float() / teacher_temp).t()  # (K, Bg), log domain: exact same algebra,
+    K, Bg = logq.shape                                # but rows far below the global max cannot
+    logq = logq - torch.logsumexp(logq.reshape(-1), 0)  # underflow to 0/0
     for _ in range(n_iterations):
-        Q = Q / Q.sum(dim=1, keepdim=True)
-        Q = Q / K
-        Q = Q / Q.sum(dim=0, keepdim=True)
-        Q = Q / Bg
-    Q = Q * Bg
-    return Q.t()
+        logq = logq - torch.logsumexp(logq, dim=1, keepdim=True) - math.log(K)
+        logq = logq - torch.logsumexp(logq, dim=0, keepdim=True) - math.log(Bg)
+    logq = logq + math.log(Bg)
+    return torch.exp(logq).t()
 
 
 def teacher_probs(teacher_out, center, teacher_temp, teacher_mode="center", sk_iters=3):
