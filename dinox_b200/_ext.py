@@ -121,6 +121,7 @@ SIGNATURES = {
     "dinox_cols_sum": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "dinox_center_ema": (c_int, [c_void_p, c_void_p, c_f32, c_f32, c_i64, c_void_p]),
     "dinox_axpb": (c_int, [c_void_p, c_f32, c_f32, c_void_p, c_i64, c_void_p]),
+    "dinox_axpby": (c_int, [c_void_p, c_f32, c_void_p, c_void_p, c_f32, c_void_p, c_i64, c_void_p]),
     "dinox_ce_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_ce_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_int, c_int, c_i64, c_i64, c_i64,
                              c_f32, c_f32, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_int,
@@ -137,6 +138,22 @@ SIGNATURES = {
     "dinox_head_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_f32, c_f32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_i64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dinox_gemm_bf16_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                        c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_f32, c_void_p, c_void_p]),
+    "dinox_normalize_tokens": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "dinox_normalize_tokens_bwd": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_f32, c_void_p, c_i64, c_i64, c_void_p]),
+    "dinox_gram_diff_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_gram_diff": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_f32, c_void_p, c_void_p, c_void_p]),
+    "dinox_gather_cast_bf16": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p]),
+    "dinox_gather_f32": (c_int, [c_void_p, c_void_p, c_i64, c_f32, c_void_p, c_void_p]),
+    "dinox_gelu_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
+    "dinox_gelu_bwd_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_gelu_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dinox_gemv_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_f32, c_void_p, c_f32, c_void_p, c_void_p]),
+    "dinox_gather_sum_rows": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_f32, c_void_p, c_i64,
+                                      c_int, c_void_p]),
+    "dinox_fill_f32": (c_int, [c_void_p, c_i64, c_f32, c_void_p]),
 }
 
 

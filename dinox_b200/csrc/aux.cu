@@ -1,0 +1,287 @@
+// Small HBM-bound helper kernels around the tensor-core contractions of the loss head:
+// row gather + cast to bf16 (CLS / masked-patch staging), GELU forward/backward of the projection
+// head (zoo/arch.py:254, exact erf form), bf16 GEMV for the teacher-centre batch mean, indexed
+// row gather-sum (dL/dh of entries -> rows), token L2-normalise forward/backward for Gram
+// anchoring (scripts/phase5_big_run.py:726).  128-bit accesses, one warp per row.
+#include "common.cuh"
+
+namespace dinox {
+
+// ---------------------------------------------------------------------------------------------
+// dst[r, :] = bf16( src[idx ? idx[r] : r, :] * scale )     src fp32 or bf16, row stride ld_src
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gather_cast_kernel(const T* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ idx,
+                                   int64_t rows, int D, __nv_bfloat16* __restrict__ dst, int64_t ld_dst) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int64_t sr = idx ? idx[r] : r;
+  __nv_bfloat16* d = dst + r * ld_dst;
+  if (sr < 0) {  // padding entry: zero row
+    for (int c = lane * 2; c < D; c += 64) *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(0.f, 0.f);
+    return;
+  }
+  const T* s = src + sr * ld_src;
+  for (int c = lane * 2; c < D; c += 64) {
+    float a = to_f32<T>(s[c]), b = to_f32<T>(s[c + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(a, b);
+  }
+}
+
+// out[r] = src[idx[r]] (fp32 scalars; idx < 0 -> fill)
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t n,
+                                  float fill, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = idx[i] >= 0 ? src[idx[i]] : fill;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GELU (erf):  h = bf16(gelu(a));   backward: da = bf16(dh * gelu'(a)), colsum(da) for db1
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__global__ void gelu_fwd_kernel(const float* __restrict__ a, int64_t n4, __nv_bfloat16* __restrict__ h) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(a)[i];
+  __nv_bfloat162 lo = __floats2bfloat162_rn(gelu_f(v.x), gelu_f(v.y));
+  __nv_bfloat162 hi = __floats2bfloat162_rn(gelu_f(v.z), gelu_f(v.w));
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo);
+  o.y = *reinterpret_cast<uint32_t*>(&hi);
+  reinterpret_cast<uint2*>(h)[i] = o;
+}
+
+// da[r, c] = bf16(dh[r,c] * scale * gelu'(a[r,c])); each thread owns 4 columns of a 64-row slab and
+// emits one partial column sum per slab (fixed order => deterministic db1)
+__global__ void gelu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ a, int64_t rows, int D,
+                                const float* __restrict__ scale_dev, __nv_bfloat16* __restrict__ da,
+                                float* __restrict__ colsum_partial /* (gridDim.y, D) */) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= D) return;
+  const float sc = scale_dev ? *scale_dev : 1.f;
+  const int64_t r0 = (int64_t)blockIdx.y * 64;
+  const int64_t r1 = r0 + 64 < rows ? r0 + 64 : rows;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float4 g = *reinterpret_cast<const float4*>(dh + r * D + c);
+    const float4 x = *reinterpret_cast<const float4*>(a + r * D + c);
+    const float d0 = g.x * sc * gelu_grad_f(x.x), d1 = g.y * sc * gelu_grad_f(x.y);
+    const float d2 = g.z * sc * gelu_grad_f(x.z), d3 = g.w * sc * gelu_grad_f(x.w);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(d0, d1), hi = __floats2bfloat162_rn(d2, d3);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(da + r * D + c) = o;
+    s0 += d0; s1 += d1; s2 += d2; s3 += d3;
+  }
+  if (colsum_partial) *reinterpret_cast<float4*>(colsum_partial + (int64_t)blockIdx.y * D + c) = make_float4(s0, s1, s2, s3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[k] = (sum_d W[k,d] * x[d]) * alpha + bias[k] * beta     W bf16 (K, D), x fp32 (D); warp per row
+// ---------------------------------------------------------------------------------------------
+__global__ void gemv_bf16_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, const float* __restrict__ x,
+                                 int64_t K, int D, float alpha, const float* __restrict__ bias, float beta,
+                                 float* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const __nv_bfloat16* w = W + k * ldw;
+  float acc = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 v = ldg_stream_u4(reinterpret_cast<const uint4*>(w + c));
+    const float4 x0 = *reinterpret_cast<const float4*>(x + c), x1 = *reinterpret_cast<const float4*>(x + c + 4);
+    acc = fmaf(__uint_as_float(v.x << 16), x0.x, acc); acc = fmaf(__uint_as_float(v.x & 0xffff0000u), x0.y, acc);
+    acc = fmaf(__uint_as_float(v.y << 16), x0.z, acc); acc = fmaf(__uint_as_float(v.y & 0xffff0000u), x0.w, acc);
+    acc = fmaf(__uint_as_float(v.z << 16), x1.x, acc); acc = fmaf(__uint_as_float(v.z & 0xffff0000u), x1.y, acc);
+    acc = fmaf(__uint_as_float(v.w << 16), x1.z, acc); acc = fmaf(__uint_as_float(v.w & 0xffff0000u), x1.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[k] = acc * alpha + (bias ? bias[k] * beta : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dst[r, :] (+)= scale * sum_{i in [ptr[r], ptr[r+1])} src[ent[i], :]       fp32, warp per row
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_sum_kernel(const float* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ ptr,
+                                  const int64_t* __restrict__ ent, int64_t rows, int D, const float* __restrict__ scale_dev,
+                                  float scale, float* __restrict__ dst, int64_t ld_dst, int accumulate) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float sc = scale * (scale_dev ? *scale_dev : 1.f);
+  const int64_t i0 = ptr[r], i1 = ptr[r + 1];
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = i0; i < i1; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(src + ent[i] * ld_src + c);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    float4* d = reinterpret_cast<float4*>(dst + r * ld_dst + c);
+    float4 o = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc);
+    if (accumulate) { const float4 old = *d; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+    *d = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram anchoring staging: token rows of feats (B, T, D) [fp32 | bf16] without CLS:
+//   xn[b, t, :] = bf16( x / max(||x||, 1e-12) ),  inv_norm[b, t] = 1 / max(||x||, 1e-12)
+// backward of the normalise:  dx = (dxn - xn_f * <xn_f, dxn>) * inv_norm  with xn_f = x*inv_norm,
+// written to grad (B, T, D) fp32 at token t+1 (+)=, CLS row untouched (zeroed by the caller).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void normalize_tokens_kernel(const T* __restrict__ feats, int64_t stride_b, int64_t stride_t, int tokens,
+                                        int skip, int D, int64_t n_rows, __nv_bfloat16* __restrict__ xn,
+                                        float* __restrict__ inv_norm) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const int64_t b = r / tokens, t = r % tokens;
+  const T* x = feats + b * stride_b + (t + skip) * stride_t;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) { const float v = to_f32<T>(x[c]); ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  __nv_bfloat16* o = xn + r * D;
+  for (int c = lane * 2; c < D; c += 64)
+    *reinterpret_cast<__nv_bfloat162*>(o + c) = __floats2bfloat162_rn(to_f32<T>(x[c]) * inv, to_f32<T>(x[c + 1]) * inv);
+  if (lane == 0) inv_norm[r] = inv;
+}
+
+template <typename T>
+__global__ void normalize_bwd_kernel(const T* __restrict__ feats, int64_t stride_b, int64_t stride_t, int tokens,
+                                     int skip, int D, int64_t n_rows, const float* __restrict__ dxn /* (n_rows, D) */,
+                                     const float* __restrict__ inv_norm, const float* __restrict__ scale_dev, float scale,
+                                     float* __restrict__ grad, int64_t gstride_b, int64_t gstride_t) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const int64_t b = r / tokens, t = r % tokens;
+  const T* x = feats + b * stride_b + (t + skip) * stride_t;
+  const float* g = dxn + r * D;
+  const float inv = inv_norm[r];
+  const float sc = scale * (scale_dev ? *scale_dev : 1.f);
+  float dot = 0.f;
+  for (int c = lane; c < D; c += 32) dot = fmaf(to_f32<T>(x[c]) * inv, g[c], dot);
+  dot = warp_sum(dot);
+  float* o = grad + b * gstride_b + (t + skip) * gstride_t;
+  for (int c = lane; c < D; c += 32) o[c] = (g[c] - to_f32<T>(x[c]) * inv * dot) * inv * sc;
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace dinox
+
+extern "C" {
+using namespace dinox;
+
+int dinox_gather_cast_bf16(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx, int64_t rows,
+                           int64_t D, void* dst, int64_t ld_dst, dinox_stream_t stream) {
+  DINOX_REQUIRE(src && dst && rows >= 0 && D > 0 && D % 2 == 0 && ld_dst >= D, DINOX_E_BADARG, "gather_cast: bad arguments");
+  DINOX_REQUIRE((reinterpret_cast<uintptr_t>(dst) % 4) == 0 && ld_dst % 2 == 0, DINOX_E_ALIGN, "gather_cast: dst misaligned");
+  if (rows == 0) return DINOX_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (src_dtype == DINOX_F32)
+    gather_cast_kernel<float><<<grid, 256, 0, stream>>>((const float*)src, ld_src, idx, rows, (int)D, (__nv_bfloat16*)dst, ld_dst);
+  else if (src_dtype == DINOX_BF16)
+    gather_cast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, ld_src, idx, rows, (int)D, (__nv_bfloat16*)dst, ld_dst);
+  else if (src_dtype == DINOX_F16)
+    gather_cast_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)src, ld_src, idx, rows, (int)D, (__nv_bfloat16*)dst, ld_dst);
+  else { set_error("gather_cast: unknown dtype %d", src_dtype); return DINOX_E_BADARG; }
+  return check_launch("gather_cast_kernel", stream);
+}
+
+int dinox_gather_f32(const float* src, const int64_t* idx, int64_t n, float fill, float* out, dinox_stream_t stream) {
+  DINOX_REQUIRE(src && idx && out && n >= 0, DINOX_E_BADARG, "gather_f32: bad arguments");
+  if (n == 0) return DINOX_OK;
+  gather_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, idx, n, fill, out);
+  return check_launch("gather_f32_kernel", stream);
+}
+
+int dinox_gelu_fwd(const float* a, int64_t n, void* h_bf16, dinox_stream_t stream) {
+  DINOX_REQUIRE(a && h_bf16 && n > 0 && n % 4 == 0, DINOX_E_BADARG, "gelu_fwd: n must be a positive multiple of 4");
+  DINOX_REQUIRE(aligned16(a) && (reinterpret_cast<uintptr_t>(h_bf16) % 8) == 0, DINOX_E_ALIGN, "gelu_fwd: misaligned");
+  gelu_fwd_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(a, n / 4, (__nv_bfloat16*)h_bf16);
+  return check_launch("gelu_fwd_kernel", stream);
+}
+
+size_t dinox_gelu_bwd_workspace_bytes(int64_t rows, int64_t D) { return (size_t)((rows + 63) / 64) * D * sizeof(float); }
+
+int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int64_t D, const float* scale_dev, void* da_bf16,
+                   float* colsum_partial, dinox_stream_t stream) {
+  DINOX_REQUIRE(dh && a && da_bf16 && rows > 0 && D > 0 && D % 4 == 0, DINOX_E_BADARG, "gelu_bwd: bad arguments");
+  dim3 grid((unsigned)((D / 4 + 127) / 128), (unsigned)((rows + 63) / 64));
+  gelu_bwd_kernel<<<grid, 128, 0, stream>>>(dh, a, rows, (int)D, scale_dev, (__nv_bfloat16*)da_bf16, colsum_partial);
+  return check_launch("gelu_bwd_kernel", stream);
+}
+
+int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64_t D, float alpha, const float* bias,
+                    float beta, float* out, dinox_stream_t stream) {
+  DINOX_REQUIRE(W && x && out && K > 0 && D > 0 && D % 8 == 0 && ldw % 8 == 0, DINOX_E_BADARG, "gemv_bf16: bad arguments (D, ldw multiples of 8)");
+  DINOX_REQUIRE(aligned16(W) && aligned16(x), DINOX_E_ALIGN, "gemv_bf16: misaligned");
+  gemv_bf16_kernel<<<(unsigned)((K + 7) / 8), 256, 0, stream>>>((const __nv_bfloat16*)W, ldw, x, K, (int)D, alpha, bias, beta, out);
+  return check_launch("gemv_bf16_kernel", stream);
+}
+
+int dinox_gather_sum_rows(const float* src, int64_t ld_src, const int64_t* ptr, const int64_t* ent, int64_t rows,
+                          int64_t D, const float* scale_dev, float scale, float* dst, int64_t ld_dst, int accumulate,
+                          dinox_stream_t stream) {
+  DINOX_REQUIRE(src && ptr && ent && dst && rows >= 0 && D > 0 && D % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0,
+                DINOX_E_BADARG, "gather_sum_rows: bad arguments");
+  if (rows == 0) return DINOX_OK;
+  gather_sum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(src, ld_src, ptr, ent, rows, (int)D, scale_dev, scale, dst, ld_dst, accumulate);
+  return check_launch("gather_sum_kernel", stream);
+}
+
+int dinox_normalize_tokens(const void* feats, int dtype, int64_t batch, int64_t tokens_total, int64_t D,
+                           int64_t stride_b, int64_t stride_t, int skip, void* xn_bf16, float* inv_norm,
+                           dinox_stream_t stream) {
+  DINOX_REQUIRE(feats && xn_bf16 && inv_norm && batch > 0 && tokens_total > skip && D > 0 && D % 2 == 0, DINOX_E_BADARG,
+                "normalize_tokens: bad arguments");
+  const int tokens = (int)(tokens_total - skip);
+  const int64_t n_rows = batch * tokens;
+  const unsigned grid = (unsigned)((n_rows + 7) / 8);
+  if (dtype == DINOX_F32)
+    normalize_tokens_kernel<float><<<grid, 256, 0, stream>>>((const float*)feats, stride_b, stride_t, tokens, skip, (int)D, n_rows, (__nv_bfloat16*)xn_bf16, inv_norm);
+  else if (dtype == DINOX_BF16)
+    normalize_tokens_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)feats, stride_b, stride_t, tokens, skip, (int)D, n_rows, (__nv_bfloat16*)xn_bf16, inv_norm);
+  else { set_error("normalize_tokens: dtype must be f32 or bf16"); return DINOX_E_BADARG; }
+  return check_launch("normalize_tokens_kernel", stream);
+}
+
+int dinox_normalize_tokens_bwd(const void* feats, int dtype, int64_t batch, int64_t tokens_total, int64_t D,
+                               int64_t stride_b, int64_t stride_t, int skip, const float* dxn, const float* inv_norm,
+                               const float* scale_dev, float scale, float* grad, int64_t gstride_b, int64_t gstride_t,
+                               dinox_stream_t stream) {
+  DINOX_REQUIRE(feats && dxn && inv_norm && grad && batch > 0 && tokens_total > skip && D > 0, DINOX_E_BADARG,
+                "normalize_tokens_bwd: bad arguments");
+  const int tokens = (int)(tokens_total - skip);
+  const int64_t n_rows = batch * tokens;
+  const unsigned grid = (unsigned)((n_rows + 7) / 8);
+  if (dtype == DINOX_F32)
+    normalize_bwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)feats, stride_b, stride_t, tokens, skip, (int)D, n_rows, dxn, inv_norm, scale_dev, scale, grad, gstride_b, gstride_t);
+  else if (dtype == DINOX_BF16)
+    normalize_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)feats, stride_b, stride_t, tokens, skip, (int)D, n_rows, dxn, inv_norm, scale_dev, scale, grad, gstride_b, gstride_t);
+  else { set_error("normalize_tokens_bwd: dtype must be f32 or bf16"); return DINOX_E_BADARG; }
+  return check_launch("normalize_bwd_kernel", stream);
+}
+
+int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream) {
+  DINOX_REQUIRE(p && n >= 0, DINOX_E_BADARG, "fill_f32: bad arguments");
+  if (n == 0) return DINOX_OK;
+  fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, n, v);
+  return check_launch("fill_f32_kernel", stream);
+}
+
+}  // extern "C"

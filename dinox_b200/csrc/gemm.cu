@@ -26,6 +26,7 @@ struct EpiStore {
     float alpha;
     const float* alpha_dev;  // optional device scalar multiplied into alpha
     const float* bias_n;     // optional per-column bias
+    int64_t batch_stride;    // output elements between problems of a batched launch
   };
   template <int BN>
   struct Impl {
@@ -49,7 +50,7 @@ struct EpiStore {
             v[j] = fmaf(v[j], alpha, b);
           }
           if (e.out_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + (int64_t)row * e.ldo + col0;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + tc.batch * e.batch_stride + (int64_t)row * e.ldo + col0;
             if (full && !e.accumulate) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
@@ -67,7 +68,7 @@ struct EpiStore {
                 if (col0 + j < p.N) o[j] = __float2bfloat16_rn(v[j] + (e.accumulate ? __bfloat162float(o[j]) : 0.f));
             }
           } else {
-            float* o = reinterpret_cast<float*>(e.out) + (int64_t)row * e.ldo + col0;
+            float* o = reinterpret_cast<float*>(e.out) + tc.batch * e.batch_stride + (int64_t)row * e.ldo + col0;
             if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -255,6 +256,88 @@ struct EpiGradT {
   };
 };
 
+
+// =============================================================================================
+// Epilogue 4 (Gram anchoring): per image, sub-GEMM 0 = student Gram tile, sub-GEMM 1 = teacher
+// Gram tile (tokens already L2-normalised, bf16).  delta = Gs - Gt never leaves the SM in fp32:
+//   loss_partial += sum delta^2 ;  delta -> bf16 (B, T', ldd) as the operand of the backward GEMM.
+// scripts/phase5_big_run.py:727 (bmm) + :738 (mse_loss) fused.
+// =============================================================================================
+struct EpiGramDiff {
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kEpiSmemBytes = 0;
+  struct Params {
+    __nv_bfloat16* delta;   // (B, T', ldd) or NULL (forward only)
+    int64_t ldd, batch_stride;
+    float* loss_partial;    // (num_tiles*8)
+  };
+  template <int BN>
+  struct Impl {
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
+    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int t, uint32_t tmem_acc,
+                                                int, int epi_warp, int lane, uint8_t*) {
+      static_assert(BN == 128, "EpiGramDiff is written for 128-wide tiles");
+      const int q = epi_quarter();
+      const int half = epi_warp >> 2;
+      const int i = tc.m_tile * BM + q * 32 + lane;
+      const bool iok = i < p.M;
+      const uint32_t ts = tmem_acc + ((uint32_t)(q * 32) << 16) + half * 64;
+      const uint32_t tt = ts + BN;
+      float loss = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float sv[32], tv[32];
+        sm100::tmem_ld32x2(ts + c * 32, tt + c * 32, sv, tv);
+        const int j0 = tc.n_tile * BN + half * 64 + c * 32;
+        if (j0 >= p.N) break;
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d = (iok && j0 + j < p.N) ? (sv[j] - tv[j]) : 0.f;
+          loss = fmaf(d, d, loss);
+          sv[j] = d;
+        }
+        if (e.delta && iok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(sv[2 * j], sv[2 * j + 1]);
+            packed[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          __nv_bfloat16* o = e.delta + tc.batch * e.batch_stride + (int64_t)i * e.ldd + j0;
+          if (j0 + 32 <= e.ldd) {  // padding columns [N, ldd) receive zeros
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (j0 + j < e.ldd) o[j] = __float2bfloat16_rn(sv[j]);
+          }
+        }
+      }
+      loss = warp_sum(loss);
+      if (lane == 0) e.loss_partial[(int64_t)t * 8 + epi_warp] = loss;
+    }
+  };
+};
+
+// per-tile loss partials of pass 2 -> out[0] (entry tiles < split) and out[1] (entry tiles >= split);
+// tiles are numbered m_tile*num_n_tiles + n_tile (entry tiles fastest), 8 partials per tile
+__global__ void __launch_bounds__(1024) split_sum_kernel(const float* __restrict__ x, int64_t n_tiles, int num_n_tiles,
+                                                          int split, float* __restrict__ out, int accumulate) {
+  __shared__ float red[64];
+  float a = 0.f, b = 0.f;
+  for (int64_t i = threadIdx.x; i < n_tiles * 8; i += 1024) {
+    const int nt = (int)((i >> 3) % num_n_tiles);
+    if (nt < split) a += x[i]; else b += x[i];
+  }
+  a = block_sum<1024>(a, red);
+  b = block_sum<1024>(b, red);
+  if (threadIdx.x == 0) {
+    out[0] = a + (accumulate ? out[0] : 0.f);
+    out[1] = b + (accumulate ? out[1] : 0.f);
+  }
+}
+
 // single CTA deterministic sum of n floats (optionally scaled) into *out
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ out,
                                                     int accumulate) {
@@ -294,28 +377,35 @@ struct Operand {
   int64_t rows;      // M (or N) extent
   int64_t ld;        // leading dimension in elements of the stored matrix
   int mn_major;      // 0: stored (rows, K) ; 1: stored (K, rows)
+  int64_t batch_stride = 0;  // elements between consecutive problems (batched launches)
 };
 
-static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int tile_rows, const char* what) {
+static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int tile_rows, int64_t batches, const char* what) {
+  if (batches > 1) {
+    if (!o.mn_major) return make_tmap_bf16_3d(tm, o.ptr, batches, o.rows, K, o.ld, o.batch_stride, tile_rows, what);
+    return make_tmap_bf16_3d(tm, o.ptr, batches, K, o.rows, o.ld, o.batch_stride, BK, what);
+  }
   if (!o.mn_major) return make_tmap_bf16_2d(tm, o.ptr, o.rows, K, o.ld, tile_rows, what);
   return make_tmap_bf16_2d(tm, o.ptr, K, o.rows, o.ld, BK, what);  // box = 64 k-rows x 64 mn-elements
 }
 
 template <int BN, int NSUB, class Epi>
 static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const Operand* b1, int64_t M, int64_t N,
-                  int64_t K, int m_fastest, const typename Epi::Params& ep, cudaStream_t stream, const char* name) {
+                  int64_t K, int m_fastest, const typename Epi::Params& ep, cudaStream_t stream, const char* name,
+                  int64_t batches = 1) {
   DINOX_REQUIRE(M > 0 && N > 0 && K > 0, DINOX_E_BADARG, "%s: empty problem", name);
   DINOX_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), DINOX_E_BADARG, "%s: dimension too large", name);
   CUtensorMap tA0, tB0, tA1, tB1;
   int rc;
-  if ((rc = make_operand_tmap(&tA0, a0, K, BM, "A"))) return rc;
-  if ((rc = make_operand_tmap(&tB0, b0, K, BN, "B"))) return rc;
+  DINOX_REQUIRE(batches >= 1 && batches < (1 << 20), DINOX_E_BADARG, "%s: bad batch count", name);
+  if ((rc = make_operand_tmap(&tA0, a0, K, BM, batches, "A"))) return rc;
+  if ((rc = make_operand_tmap(&tB0, b0, K, BN, batches, "B"))) return rc;
   tA1 = tA0; tB1 = tB0;
   if (NSUB == 2) {
     DINOX_REQUIRE(a1 && b1 && a1->mn_major == a0.mn_major && b1->mn_major == b0.mn_major, DINOX_E_BADARG,
                   "%s: second operand pair missing or layout mismatch", name);
-    if ((rc = make_operand_tmap(&tA1, *a1, K, BM, "A1"))) return rc;
-    if ((rc = make_operand_tmap(&tB1, *b1, K, BN, "B1"))) return rc;
+    if ((rc = make_operand_tmap(&tA1, *a1, K, BM, batches, "A1"))) return rc;
+    if ((rc = make_operand_tmap(&tB1, *b1, K, BN, batches, "B1"))) return rc;
   }
   CoreParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -323,6 +413,7 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   p.num_n_tiles = (int)((N + BN - 1) / BN);
   p.num_k_blocks = (int)((K + BK - 1) / BK);
   p.a_mn_major = a0.mn_major; p.b_mn_major = b0.mn_major; p.m_fastest = m_fastest;
+  p.batches = (int)batches;
   auto kern = gemm_kernel<BN, NSUB, Epi>;
   constexpr int smem = smem_bytes<BN, Epi>();
   static bool attr_set = false;
@@ -330,7 +421,8 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
     DINOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
+  const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles * batches;
+  DINOX_REQUIRE(tiles < (1ll << 31), DINOX_E_BADARG, "%s: too many tiles", name);
   int grid = num_sms();
   if (grid > tiles) grid = (int)tiles;
   kern<<<grid, (2 + Epi::kEpiWarps) * 32, smem, stream>>>(tA0, tB0, tA1, tB1, p, ep);
@@ -356,7 +448,7 @@ int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N,
   int rc = require_sm100();
   if (rc) return rc;
   Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
-  EpiStore::Params ep{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, bias_n};
+  EpiStore::Params ep{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, bias_n, 0};
   // widest tile that divides N without waste; ragged N falls back to 128-wide tiles
   if (N % 256 == 0 || N > 2048) return launch<256, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<256>");
   if (N % 192 == 0) return launch<192, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<192>");
@@ -413,8 +505,51 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
   // entry tiles fastest: the 2 x (K-tile of W2) operands stay put while HsE/HtE (L2-resident) stream
   rc = launch<128, 2, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, stream, "head_grad");
   if (rc) return rc;
-  const int64_t n = ((K + 127) / 128) * ((E + 127) / 128) * 8;
-  sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), n, 1.f, loss_out, loss_accumulate);
+  const int num_n_tiles = (int)((E + 127) / 128);
+  const int split = ct2_alt ? (int)(alt_from / 128) : num_n_tiles;
+  split_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), ((K + 127) / 128) * num_n_tiles,
+                                           num_n_tiles, split, loss_out, loss_accumulate);
+  return check_launch("split_sum_kernel", stream);
+}
+
+int dinox_gemm_bf16_batched(const void* A, const void* B, void* C, int64_t batches, int64_t M, int64_t N, int64_t K,
+                            int64_t lda, int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c,
+                            int a_mn_major, int b_mn_major, int out_dtype, int accumulate, float alpha,
+                            const float* alpha_dev, dinox_stream_t stream) {
+  DINOX_REQUIRE(A && B && C && batches >= 1, DINOX_E_BADARG, "gemm_bf16_batched: bad arguments");
+  DINOX_REQUIRE(out_dtype == DINOX_F32 || out_dtype == DINOX_BF16, DINOX_E_BADARG, "gemm_bf16_batched: out dtype must be f32 or bf16");
+  const int es = out_dtype == DINOX_F32 ? 4 : 2;
+  DINOX_REQUIRE(aligned16(C) && (ldc * es) % 16 == 0 && (stride_c * es) % 16 == 0 && ldc >= N, DINOX_E_ALIGN,
+                "gemm_bf16_batched: C / ldc / stride_c misaligned");
+  int rc = require_sm100();
+  if (rc) return rc;
+  Operand a{A, M, lda, a_mn_major ? 1 : 0, stride_a}, b{B, N, ldb, b_mn_major ? 1 : 0, stride_b};
+  EpiStore::Params ep{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, nullptr, stride_c};
+  if (N % 256 == 0 || N > 2048) return launch<256, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, 1, ep, stream, "gemm_bf16_batched<256>", batches);
+  if (N % 192 == 0) return launch<192, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, 1, ep, stream, "gemm_bf16_batched<192>", batches);
+  return launch<128, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, 1, ep, stream, "gemm_bf16_batched<128>", batches);
+}
+
+size_t dinox_gram_diff_workspace_bytes(int64_t batches, int64_t tokens) {
+  if (batches <= 0 || tokens <= 0) return 0;
+  const int64_t mt = (tokens + 127) / 128;
+  return (size_t)(batches * mt * mt * 8) * sizeof(float) + 256;
+}
+
+int dinox_gram_diff(const void* xn_s, const void* xn_t, int64_t batches, int64_t tokens, int64_t D, void* delta,
+                    int64_t ldd, float loss_scale, float* loss_out, void* workspace, dinox_stream_t stream) {
+  DINOX_REQUIRE(xn_s && xn_t && loss_out && workspace && batches >= 1 && tokens > 0 && D > 0, DINOX_E_BADARG,
+                "gram_diff: bad arguments");
+  DINOX_REQUIRE(!delta || (aligned16(delta) && ldd % 8 == 0 && ldd >= tokens), DINOX_E_ALIGN, "gram_diff: delta / ldd misaligned");
+  int rc = require_sm100();
+  if (rc) return rc;
+  // a single image still goes through the 3-D path (batches = 1 uses 2-D maps over (tokens, D))
+  Operand a0{xn_s, tokens, D, 0, tokens * D}, a1{xn_t, tokens, D, 0, tokens * D};
+  EpiGramDiff::Params ep{reinterpret_cast<__nv_bfloat16*>(delta), ldd, tokens * ldd, reinterpret_cast<float*>(workspace)};
+  rc = launch<128, 2, EpiGramDiff>(a0, a0, &a1, &a1, tokens, tokens, D, 1, ep, stream, "gram_diff", batches);
+  if (rc) return rc;
+  const int64_t mt = (tokens + 127) / 128;
+  sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), batches * mt * mt * 8, loss_scale, loss_out, 0);
   return check_launch("sum_kernel", stream);
 }
 

@@ -19,7 +19,7 @@ constexpr int UMMA_K = 16;
 constexpr int kFirstEpiWarp = 2;
 
 struct TileCoord {
-  int m_tile, n_tile;
+  int m_tile, n_tile, batch;
 };
 
 struct CoreParams {
@@ -27,6 +27,7 @@ struct CoreParams {
   int num_m_tiles, num_n_tiles, num_k_blocks;
   int a_mn_major, b_mn_major;  // operand layouts in global memory
   int m_fastest;               // tile order: consecutive CTAs walk M (1) or N (0)
+  int batches;                 // > 1: independent problems along a third tensor-map dimension
 };
 
 template <int BN>
@@ -41,6 +42,9 @@ struct SmemLayout {
 
 __device__ __forceinline__ TileCoord tile_coord(const CoreParams& p, int t) {
   TileCoord c;
+  const int per = p.num_m_tiles * p.num_n_tiles;
+  c.batch = t / per;
+  t -= c.batch * per;
   if (p.m_fastest) { c.m_tile = t % p.num_m_tiles; c.n_tile = t / p.num_m_tiles; }
   else { c.n_tile = t % p.num_n_tiles; c.m_tile = t / p.num_n_tiles; }
   return c;
@@ -97,7 +101,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.batches;
 
   if (warp == 0 && lane == 0) {
     sm100::prefetch_tmap(tmA0);
@@ -132,19 +136,36 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             uint8_t* sb = sa + L::kABytes;
             sm100::mbar_expect_tx(&ctl->full[st.stage], L::kStageBytes);
             const int k0 = kb * BK;
-            if (!p.a_mn_major) {
-              sm100::tma_load_2d(sa, ma, &ctl->full[st.stage], k0, m0);
-            } else {
+            if (p.batches > 1) {
+              if (!p.a_mn_major) {
+                sm100::tma_load_3d(sa, ma, &ctl->full[st.stage], k0, m0, tc.batch);
+              } else {
 #pragma unroll
-              for (int c = 0; c < BM / 64; ++c)
-                sm100::tma_load_2d(sa + c * (BK * 128), ma, &ctl->full[st.stage], m0 + c * 64, k0);
-            }
-            if (!p.b_mn_major) {
-              sm100::tma_load_2d(sb, mb, &ctl->full[st.stage], k0, n0);
-            } else {
+                for (int c = 0; c < BM / 64; ++c)
+                  sm100::tma_load_3d(sa + c * (BK * 128), ma, &ctl->full[st.stage], m0 + c * 64, k0, tc.batch);
+              }
+              if (!p.b_mn_major) {
+                sm100::tma_load_3d(sb, mb, &ctl->full[st.stage], k0, n0, tc.batch);
+              } else {
 #pragma unroll
-              for (int c = 0; c < BN / 64; ++c)
-                sm100::tma_load_2d(sb + c * (BK * 128), mb, &ctl->full[st.stage], n0 + c * 64, k0);
+                for (int c = 0; c < BN / 64; ++c)
+                  sm100::tma_load_3d(sb + c * (BK * 128), mb, &ctl->full[st.stage], n0 + c * 64, k0, tc.batch);
+              }
+            } else {
+              if (!p.a_mn_major) {
+                sm100::tma_load_2d(sa, ma, &ctl->full[st.stage], k0, m0);
+              } else {
+#pragma unroll
+                for (int c = 0; c < BM / 64; ++c)
+                  sm100::tma_load_2d(sa + c * (BK * 128), ma, &ctl->full[st.stage], m0 + c * 64, k0);
+              }
+              if (!p.b_mn_major) {
+                sm100::tma_load_2d(sb, mb, &ctl->full[st.stage], k0, n0);
+              } else {
+#pragma unroll
+                for (int c = 0; c < BN / 64; ++c)
+                  sm100::tma_load_2d(sb + c * (BK * 128), mb, &ctl->full[st.stage], n0 + c * 64, k0);
+              }
             }
             st.advance<kStages>();
           }

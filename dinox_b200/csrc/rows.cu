@@ -208,6 +208,13 @@ __global__ void axpb_kernel(const float* __restrict__ a, float alpha, float beta
   if (k < n) out[k] = fmaf(a[k], alpha, beta);
 }
 
+__global__ void axpby_kernel(const float* __restrict__ x, float alpha, const float* __restrict__ alpha_dev,
+                             const float* __restrict__ y, float beta, float* __restrict__ out, int64_t n) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float a = alpha * (alpha_dev ? *alpha_dev : 1.f);
+  if (k < n) out[k] = fmaf(x[k], a, (y ? y[k] : 0.f) * beta);
+}
+
 // ---------------------------------------------------------------------------------------------
 // cross-entropy forward / backward over groups x K-splits
 // ---------------------------------------------------------------------------------------------
@@ -477,6 +484,13 @@ int dinox_axpb(const float* a, float alpha, float beta, float* out, int64_t n, d
   DINOX_REQUIRE(a && out && n > 0, DINOX_E_BADARG, "axpb: bad arguments");
   axpb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, alpha, beta, out, n);
   return check_launch("axpb_kernel", stream);
+}
+
+int dinox_axpby(const float* x, float alpha, const float* alpha_dev, const float* y, float beta, float* out,
+                int64_t n, dinox_stream_t stream) {
+  DINOX_REQUIRE(x && out && n > 0, DINOX_E_BADARG, "axpby: bad arguments");
+  axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, alpha, alpha_dev, y, beta, out, n);
+  return check_launch("axpby_kernel", stream);
 }
 
 size_t dinox_ce_workspace_bytes(int64_t groups, int64_t K) {

@@ -1,0 +1,609 @@
+"""Host-side mirror of the reference's loss-head API, backed by the CUDA kernels.
+
+Drop-in names and signatures (reference: timlawrenz/DINO-X):
+  DINOLoss(out_dim, center_momentum)(student_out, teacher_out, student_temp, teacher_temp)
+                                              scripts/phase5_big_run.py:679-720
+  compute_gram_matrix(feats)                  scripts/phase5_big_run.py:723-728
+  compute_gram_anchoring_loss(s_feats, t_feats)  scripts/phase5_big_run.py:731-739
+  DinoStudentTeacher(backbone, out_dim).head  zoo/arch.py:246-261 (state-dict keys head.{0,2}.*)
+  _ema_update(teacher, student, m)            scripts/phase3_micro_run.py:152-155; inline loop at
+                                              scripts/phase5_big_run.py:1798-1802
+  KoLeoLoss is out of scope.
+Extensions enter only through keyword arguments whose defaults reproduce the reference
+(n_global=2, n_local=0, teacher_mode="center", process_group=None) and through the fused entry
+point ``fused_head_dino_loss`` (projection head + multi-crop CE + iBOT in tcgen05 GEMM epilogues,
+logits never written to HBM).
+
+Everything computes through libdinox_b200.so; CPU tensors raise (no fallback).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _ext, ops
+
+LOG2E = ops.LOG2E
+
+
+# =================================================================================================
+# data-parallel statistics: only tiny all-reduces of global statistics
+# =================================================================================================
+def _world(pg) -> int:
+    if pg is None:
+        return 1
+    import torch.distributed as dist
+    return dist.get_world_size(pg) if pg is not True else dist.get_world_size()
+
+
+def _group(pg):
+    return None if pg is True else pg
+
+
+def allreduce_sum_(t: torch.Tensor, pg) -> torch.Tensor:
+    """In-place SUM all-reduce over the data-parallel group (NCCL over NVLink on B200)."""
+    if _world(pg) > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group(pg))
+    return t
+
+
+def allreduce_lse(local_lse: torch.Tensor, pg, add: float = 0.0) -> torch.Tensor:
+    """log-sum-exp all-reduce of per-rank LSE vectors: all_gather + one combine kernel.  Exact in
+    the log domain (no common shift needed), one collective per Sinkhorn half-iteration."""
+    w = _world(pg)
+    if w == 1:
+        return ops.lse_combine(local_lse.reshape(1, -1), add) if add != 0.0 else local_lse
+    import torch.distributed as dist
+    gathered = torch.empty(w, local_lse.numel(), dtype=torch.float32, device=local_lse.device)
+    dist.all_gather_into_tensor(gathered, local_lse.contiguous(), group=_group(pg))
+    return ops.lse_combine(gathered, add)
+
+
+# =================================================================================================
+# E2 Sinkhorn-Knopp on materialised teacher logits (small: CLS rows only)
+# =================================================================================================
+@torch.no_grad()
+def sinkhorn_knopp_biases(teacher_out: torch.Tensor, teacher_temp: float, n_iterations: int = 3,
+                          process_group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Log-domain Sinkhorn-Knopp (DINOv2 formulation, see oracle.sinkhorn_knopp).  Returns
+    (colbias a[K], rowbias b[rows]) with q[i,k] = exp(t[i,k]/tau - a[k] - b[i]); rows of q sum to 1.
+    Per-prototype sums are all-reduced over `process_group`; per-sample sums are local."""
+    rows, K = teacher_out.shape
+    w = _world(process_group)
+    inv_tau = 1.0 / teacher_temp
+    log_bg = math.log(rows * w)
+    b = None
+    a = None
+    for _ in range(n_iterations):
+        a_local = ops.cols_lse(teacher_out, inv_tau, b)            # LSE_i(x - b_i) over local samples
+        a = allreduce_lse(a_local, process_group, add=math.log(K))  # global, then Q /= K
+        b = ops.rows_lse(teacher_out, inv_tau, a)                   # LSE_k(x - a_k)
+        b = ops.axpb(b, 1.0, log_bg)                                # Q /= B
+    # final Q *= B
+    b = ops.axpb(b, 1.0, -log_bg)
+    return a, b
+
+
+@torch.no_grad()
+def sinkhorn_knopp_teacher(teacher_out: torch.Tensor, teacher_temp: float, n_iterations: int = 3,
+                           process_group=None) -> torch.Tensor:
+    """Materialised SK assignment (rows, K) fp32 - convenience for tests / diagnostics."""
+    a, b = sinkhorn_knopp_biases(teacher_out, teacher_temp, n_iterations, process_group)
+    # q = exp(t/tau - a - b): reuse the CE backward kernel algebra is overkill; this is a debug helper
+    return torch.exp(teacher_out.float() / teacher_temp - a[None, :] - b[:, None])
+
+
+# =================================================================================================
+# a2-a5, E1: DINOLoss on materialised logits
+# =================================================================================================
+class _RowCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher, colbias_t, rowbias_t, lse_s, group_w, groups, V, Vg, inv_ts, inv_tt,
+                norm, exclude_same):
+        loss = ops.ce_fwd(student, teacher, groups, V, Vg, inv_ts, inv_tt, colbias_t, rowbias_t, lse_s, group_w,
+                          norm, exclude_same)
+        ctx.save_for_backward(student, teacher, colbias_t, rowbias_t, lse_s, group_w)
+        ctx.cfg = (groups, V, Vg, inv_ts, inv_tt, norm, exclude_same)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        student, teacher, colbias_t, rowbias_t, lse_s, group_w = ctx.saved_tensors
+        groups, V, Vg, inv_ts, inv_tt, norm, exclude_same = ctx.cfg
+        grad = ops.ce_bwd(student, teacher, groups, V, Vg, inv_ts, inv_tt, colbias_t, rowbias_t, lse_s, group_w,
+                          norm, exclude_same, g)
+        return (grad,) + (None,) * 12
+
+
+def _as_rows(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
+    if t.dim() != 2:
+        raise ValueError(f"expected (rows, K) logits, got {tuple(t.shape)}")
+    return t if t.stride(1) == 1 else t.contiguous()
+
+
+class DINOLoss(nn.Module):
+    """DINO loss with centering and sharpening - drop-in for scripts/phase5_big_run.py:679-720.
+
+    Extra keyword arguments (all defaulting to the reference behaviour):
+      n_global / n_local : multi-crop layout of `student_out` (view-major rows), E1
+      teacher_mode       : "center" (reference) or "sinkhorn" (E2; center buffer untouched)
+      process_group      : data-parallel group for the centre / Sinkhorn statistics (True = WORLD)
+    """
+
+    def __init__(self, out_dim: int, center_momentum: float = 0.999, *, n_global: int = 2, n_local: int = 0,
+                 teacher_mode: str = "center", sk_iterations: int = 3, process_group=None) -> None:
+        super().__init__()
+        self.center_momentum = center_momentum
+        self.register_buffer("center", torch.zeros(1, out_dim))
+        self.n_global, self.n_local = n_global, n_local
+        self.teacher_mode, self.sk_iterations = teacher_mode, sk_iterations
+        self.process_group = process_group
+
+    @torch.no_grad()
+    def update_center(self, teacher_output: torch.Tensor) -> None:
+        """center <- center*m + mean_rows(teacher_output)*(1-m)  (:686-690); in DP the column sums are
+        all-reduced and divided by the global row count."""
+        t = _as_rows(teacher_output)
+        colsum = ops.cols_sum(t)
+        allreduce_sum_(colsum, self.process_group)
+        ops.center_ema_(self.center, colsum, t.shape[0] * _world(self.process_group), self.center_momentum)
+
+    def teacher_biases(self, teacher_out: torch.Tensor, teacher_temp: float):
+        if self.teacher_mode == "center":
+            colbias = ops.axpb(self.center.reshape(-1), 1.0 / teacher_temp)
+            rowbias = ops.rows_lse(teacher_out, 1.0 / teacher_temp, colbias)
+            return colbias, rowbias
+        if self.teacher_mode == "sinkhorn":
+            return sinkhorn_knopp_biases(teacher_out, teacher_temp, self.sk_iterations, self.process_group)
+        raise ValueError(f"unknown teacher_mode {self.teacher_mode!r}")
+
+    def forward(self, student_out: torch.Tensor, teacher_out: torch.Tensor, student_temp: float,
+                teacher_temp: float) -> torch.Tensor:
+        s, t = _as_rows(student_out), _as_rows(teacher_out.detach())
+        Vg = self.n_global
+        if t.shape[0] % Vg:
+            raise ValueError("teacher rows must be a multiple of n_global")
+        B = t.shape[0] // Vg
+        if s.shape[0] % B:
+            raise ValueError("student rows must be a multiple of the per-view batch")
+        V = s.shape[0] // B
+        if self.n_local and V != Vg + self.n_local:
+            raise ValueError(f"student rows imply {V} views, expected {Vg + self.n_local}")
+        with torch.no_grad():
+            colbias, rowbias = self.teacher_biases(t, teacher_temp)
+            lse_s = ops.rows_lse(s.detach(), 1.0 / student_temp)
+        n_terms = Vg * V - Vg
+        loss = _RowCE.apply(s, t, colbias, rowbias, lse_s, None, B, V, Vg, 1.0 / student_temp, 1.0 / teacher_temp,
+                            1.0 / (n_terms * B), True)
+        if self.teacher_mode == "center":
+            self.update_center(t)
+        return loss
+
+
+@torch.no_grad()
+def entropy_diagnostics(student_out, teacher_out, center, student_temp, teacher_temp):
+    """Teacher / student softmax entropies (scripts/phase5_big_run.py:1843-1853) from one LSE pass each."""
+    t, s = _as_rows(teacher_out), _as_rows(student_out.detach())
+    colbias = ops.axpb(center.reshape(-1).float(), 1.0 / teacher_temp)
+    _, t_ent = ops.rows_lse(t, 1.0 / teacher_temp, colbias, want_entropy=True)
+    _, s_ent = ops.rows_lse(s, 1.0 / student_temp, None, want_entropy=True)
+    return t_ent.mean(), s_ent.mean()
+
+
+# =================================================================================================
+# a6-a7 Gram anchoring
+# =================================================================================================
+class _GramMatrix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats):
+        xn, inv = ops.normalize_tokens(feats, skip=0)
+        gram = ops.gemm_bf16_batched(xn, xn)
+        ctx.save_for_backward(feats, xn, inv)
+        return gram
+
+    @staticmethod
+    def backward(ctx, dg):
+        feats, xn, inv = ctx.saved_tensors
+        Bt, T, D = feats.shape
+        ld = (T + 7) // 8 * 8
+        dgb = torch.zeros(Bt, T, ld, dtype=torch.bfloat16, device=dg.device)
+        dgb[:, :, :T] = dg  # cast; rare path (the training loop uses compute_gram_anchoring_loss)
+        dgv = dgb[:, :, :T]
+        dxn = ops.gemm_bf16_batched(dgv, xn, b_mn_major=True)                       # dG   @ Xn
+        ops.gemm_bf16_batched(dgv, xn, a_mn_major=True, b_mn_major=True, out=dxn, accumulate=True)  # dG^T @ Xn
+        grad = torch.empty(Bt, T, D, dtype=torch.float32, device=dg.device)
+        ops.normalize_tokens_bwd(feats, dxn, inv, grad, skip=0)
+        return grad.to(feats.dtype)
+
+
+def compute_gram_matrix(feats: torch.Tensor) -> torch.Tensor:
+    """Gram matrix of L2-normalised tokens, (B, N, D) -> (B, N, N)  (scripts/phase5_big_run.py:723-728)."""
+    if not feats.is_cuda:
+        raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
+    return _GramMatrix.apply(feats)
+
+
+class _GramAnchor(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student_feats, teacher_feats):
+        Bt, T, D = student_feats.shape
+        xs, inv_s = ops.normalize_tokens(student_feats, skip=1)
+        xt, _ = ops.normalize_tokens(teacher_feats, skip=1)
+        n = Bt * (T - 1) * (T - 1)
+        need_grad = student_feats.requires_grad
+        loss, delta = ops.gram_diff(xs, xt, 1.0 / n, want_delta=need_grad)
+        if need_grad:
+            ctx.save_for_backward(student_feats, xs, inv_s, delta)
+            ctx.n = n
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        student_feats, xs, inv_s, delta = ctx.saved_tensors
+        Bt, T, D = student_feats.shape
+        dv = delta[:, :, :T - 1]
+        # dL/dXn = (dG + dG^T) Xn = (4/n) * Delta @ Xn   (Delta symmetric)
+        dxn = ops.gemm_bf16_batched(dv, xs, b_mn_major=True, alpha=4.0 / ctx.n)
+        grad = torch.empty(Bt, T, D, dtype=torch.float32, device=g.device)
+        grad[:, 0].zero_()  # CLS row receives no gradient (the reference slices feats[:, 1:])
+        up = g.to(torch.float32).reshape(1).contiguous()
+        ops.normalize_tokens_bwd(student_feats, dxn, inv_s, grad, skip=1, scale_dev=up)
+        return grad.to(student_feats.dtype), None
+
+
+def compute_gram_anchoring_loss(student_feats: torch.Tensor, teacher_feats: torch.Tensor) -> torch.Tensor:
+    """mse_loss(Gram(student[:,1:]), Gram(teacher[:,1:]))  (scripts/phase5_big_run.py:731-739); the two
+    Gram matrices live only in TMEM, only their bf16 difference is kept for the backward GEMM."""
+    if not (student_feats.is_cuda and teacher_feats.is_cuda):
+        raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
+    if student_feats.shape != teacher_feats.shape or student_feats.dim() != 3:
+        raise ValueError("student/teacher feats must both be (B, T, D)")
+    return _GramAnchor.apply(student_feats, teacher_feats.detach())
+
+
+# =================================================================================================
+# a8 EMA
+# =================================================================================================
+_EMA_PLANS: Dict[int, ops.EmaPlan] = {}
+
+
+@torch.no_grad()
+def ema_update(teacher_params: Sequence[torch.Tensor], student_params: Sequence[torch.Tensor], m: float,
+               plan_key: Optional[int] = None) -> None:
+    """p_t <- m*p_t + (1-m)*p_s for every pair, ONE kernel launch (scripts/phase5_big_run.py:1798-1802)."""
+    tp = [p.data for p in teacher_params]
+    sp = [p.data for p in student_params]
+    key = plan_key if plan_key is not None else hash(tuple(t.data_ptr() for t in tp))
+    plan = _EMA_PLANS.get(key)
+    if plan is None or not plan.matches(sp, tp):
+        plan = ops.EmaPlan(sp, tp)
+        _EMA_PLANS[key] = plan
+    plan.apply(m)
+    _WEIGHT_EPOCH[0] += 1
+
+
+def _ema_update(teacher: nn.Module, student: nn.Module, m: float) -> None:
+    """Same name/arguments as scripts/phase3_micro_run.py:152-155."""
+    ema_update(list(teacher.parameters()), list(student.parameters()), m, plan_key=id(teacher))
+
+
+# =================================================================================================
+# a1 projection head as an nn.Sequential with the reference's parameter keys
+# =================================================================================================
+_BF16_CACHE: Dict[int, Tuple[int, int, int, torch.Tensor]] = {}
+_WEIGHT_EPOCH = [0]  # bumped by ema_update: raw-pointer kernels do not touch tensor version counters
+
+
+def bf16_weight(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a weight, cached until the parameter is modified in place (autocast does the same
+    per forward).  Keyed on storage pointer + version counter."""
+    key = id(p)
+    ver = p._version
+    hit = _BF16_CACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[1] == p.data_ptr() and hit[2] == _WEIGHT_EPOCH[0]:
+        return hit[3]
+    w = p.detach()
+    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    ops.gather_cast_bf16(w.reshape(w.shape[0], -1), None, out.reshape(w.shape[0], -1))
+    _BF16_CACHE[key] = (ver, p.data_ptr(), _WEIGHT_EPOCH[0], out)
+    return out
+
+
+def _to_bf16_rows(x: torch.Tensor) -> torch.Tensor:
+    x = x if x.stride(-1) == 1 else x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    ops.gather_cast_bf16(x, None, out)
+    return out
+
+
+class _HeadFn(torch.autograd.Function):
+    """logits = W2 . gelu(W1 . x + b1) + b2 with bf16 tensor-core operands / fp32 accumulation, and
+    the matching backward GEMMs (operands taken in place through MN-major descriptors)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, out_dtype):
+        xb = _to_bf16_rows(x.detach())
+        w1b, w2b = bf16_weight(w1), bf16_weight(w2)
+        a = ops.gemm_bf16(xb, w1b, bias_n=b1.detach())
+        h = ops.gelu_fwd(a)
+        z = ops.gemm_bf16(h, w2b, bias_n=b2.detach(), out_dtype=out_dtype)
+        ctx.save_for_backward(xb, a, h, w1b, w2b)
+        ctx.in_dtype = x.dtype
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        xb, a, h, w1b, w2b = ctx.saved_tensors
+        dzb = dz if dz.dtype == torch.bfloat16 and dz.stride(1) == 1 else _to_bf16_rows(dz)
+        db2 = ops.cols_sum(dzb)
+        dw2 = ops.gemm_bf16(dzb, h, a_mn_major=True, b_mn_major=True)        # dz^T h   (K, D)
+        dh = ops.gemm_bf16(dzb, w2b, b_mn_major=True)                         # dz W2    (rows, D)
+        da, part = ops.gelu_bwd(dh, a)
+        db1 = ops.cols_sum(part)
+        dw1 = ops.gemm_bf16(da, xb, a_mn_major=True, b_mn_major=True)         # da^T x   (D, D)
+        dx = ops.gemm_bf16(da, w1b, b_mn_major=True)                          # da W1    (rows, D)
+        return dx.to(ctx.in_dtype), dw1, db1, dw2, db2, None
+
+
+class ProjectionHead(nn.Sequential):
+    """nn.Sequential(Linear(D,D), GELU(), Linear(D,K)) - identical parameters / state-dict keys
+    (`0.weight`, `0.bias`, `2.weight`, `2.bias`) to zoo/arch.py:252-256, forward on tcgen05 GEMMs."""
+
+    def __init__(self, dim: int, out_dim: int) -> None:
+        super().__init__(nn.Linear(dim, dim), nn.GELU(), nn.Linear(dim, out_dim))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        out_dtype = torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
+        z = _HeadFn.apply(x2, self[0].weight, self[0].bias, self[2].weight, self[2].bias, out_dtype)
+        return z.reshape(*lead, z.shape[-1])
+
+
+class DinoStudentTeacher(nn.Module):
+    """DINO student/teacher wrapper with projection head (zoo/arch.py:246-261)."""
+
+    def __init__(self, backbone: nn.Module, out_dim: int = 8192) -> None:
+        super().__init__()
+        self.backbone = backbone
+        self.head = ProjectionHead(backbone.dim, out_dim)
+
+    def forward(self, x: torch.Tensor, spacing: Optional[torch.Tensor] = None) -> torch.Tensor:
+        feats = self.backbone(x, spacing=spacing)
+        return self.head(feats[:, 0])
+
+
+# =================================================================================================
+# Fused path: head + multi-crop CE + iBOT with logits living only in TMEM
+# =================================================================================================
+class _EntryPlan:
+    """Host-built (cached) index tables pairing student rows with teacher rows.
+
+    CLS entries: every (teacher view iq, student view v != iq, image b) -> student row v*B+b,
+    teacher row iq*B+b, weight 1/(n_terms*B); padded to a multiple of 128.  iBOT entries: masked
+    token m -> student row Ms+m, teacher row Mt+m (weights come from masks_weight on device)."""
+
+    def __init__(self, B: int, Vg: int, V: int, Mm: int, device):
+        Ms, Mt = B * V, B * Vg
+        es, et = [], []
+        for iq in range(Vg):
+            for v in range(V):
+                if v == iq:
+                    continue
+                for b in range(B):
+                    es.append(v * B + b)
+                    et.append(iq * B + b)
+        self.n_cls = len(es)
+        self.n_terms = Vg * V - Vg
+        pad = (-self.n_cls) % 128
+        es += [-1] * pad
+        et += [-1] * pad
+        self.e_cls_pad = len(es)
+        es += [Ms + m for m in range(Mm)]
+        et += [Mt + m for m in range(Mm)]
+        self.E = len(es)
+        self.e_pad = (self.E + 127) // 128 * 128
+        pad2 = self.e_pad - self.E
+        es += [-1] * pad2
+        et += [-1] * pad2
+        # CSR: entries of every student row (for dH_row = sum of its entries' dH)
+        rows = Ms + Mm
+        buckets: List[List[int]] = [[] for _ in range(rows)]
+        for e, r in enumerate(es):
+            if r >= 0:
+                buckets[r].append(e)
+        ptr = [0]
+        ent = []
+        for bkt in buckets:
+            ent += bkt
+            ptr.append(len(ent))
+        cw = [1.0 / (self.n_terms * B)] * self.n_cls + [0.0] * (self.e_pad - self.n_cls)
+        t = lambda x, dt: torch.tensor(x, dtype=dt, device=device)
+        self.ent_s, self.ent_t = t(es, torch.int64), t(et, torch.int64)
+        self.csr_ptr, self.csr_ent = t(ptr, torch.int64), t(ent, torch.int64)
+        self.cw_base = t(cw, torch.float32)
+        self.Ms, self.Mt, self.Mm, self.B, self.V, self.Vg = Ms, Mt, Mm, B, V, Vg
+
+
+_PLANS: Dict[Tuple, _EntryPlan] = {}
+
+
+def _entry_plan(B, Vg, V, Mm, device) -> _EntryPlan:
+    key = (B, Vg, V, Mm, str(device))
+    p = _PLANS.get(key)
+    if p is None:
+        p = _EntryPlan(B, Vg, V, Mm, device)
+        _PLANS[key] = p
+    return p
+
+
+def _accumulate_grad(p: torch.Tensor, fn) -> None:
+    """fn(out_tensor, accumulate: bool) writes/accumulates dL/dp straight into p.grad (fp32)."""
+    if p.grad is None:
+        p.grad = torch.empty_like(p, memory_format=torch.contiguous_format)
+        fn(p.grad, False)
+    else:
+        fn(p.grad, True)
+
+
+class _FusedHeadLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student_cls, student_patch, teacher_cls, teacher_patch, masks_weight, s_head, t_head, loss_mod,
+                center_patch, cfg):
+        (student_temp, teacher_temp, Vg, n_local, ibot_weight, teacher_mode, sk_iters, pg, update_center,
+         patch_momentum) = cfg
+        dev = student_cls.device
+        D = student_cls.shape[1]
+        K = s_head[2].weight.shape[0]
+        Mt = teacher_cls.shape[0]
+        B = Mt // Vg
+        V = student_cls.shape[0] // B
+        Ms = B * V
+        Mm = 0 if student_patch is None else student_patch.shape[0]
+        plan = _entry_plan(B, Vg, V, Mm, dev)
+        inv_ts, inv_tt = 1.0 / student_temp, 1.0 / teacher_temp
+        w1s, w2s = bf16_weight(s_head[0].weight), bf16_weight(s_head[2].weight)
+        w1t, w2t = bf16_weight(t_head[0].weight), bf16_weight(t_head[2].weight)
+
+        # ---- stage inputs: [CLS rows | masked patch rows] as contiguous bf16
+        xs = torch.empty(Ms + Mm, D, dtype=torch.bfloat16, device=dev)
+        xt = torch.empty(Mt + Mm, D, dtype=torch.bfloat16, device=dev)
+        ops.gather_cast_bf16(student_cls.detach(), None, xs[:Ms])
+        ops.gather_cast_bf16(teacher_cls.detach(), None, xt[:Mt])
+        if Mm:
+            ops.gather_cast_bf16(student_patch.detach(), None, xs[Ms:])
+            ops.gather_cast_bf16(teacher_patch.detach(), None, xt[Mt:])
+        # ---- layer 1 (zoo/arch.py:253-254)
+        a_s = ops.gemm_bf16(xs, w1s, bias_n=s_head[0].bias.detach())
+        hs = ops.gelu_fwd(a_s)
+        a_t = ops.gemm_bf16(xt, w1t, bias_n=t_head[0].bias.detach())
+        ht = ops.gelu_fwd(a_t)
+        del a_t
+        # ---- pass 1: row statistics with logits kept on chip
+        b2s, b2t = s_head[2].bias.detach(), t_head[2].bias.detach()
+        cs2 = ops.axpb(b2s, inv_ts * LOG2E)
+        _, lse2_s = ops.head_stats(hs, w2s, inv_ts, cs2, want_nat=False)
+        center = loss_mod.center.reshape(-1)
+        rb2_t = torch.empty(Mt + Mm, dtype=torch.float32, device=dev)
+        if teacher_mode == "center":
+            ct2 = ops.axpby(b2t, inv_tt * LOG2E, center, -inv_tt * LOG2E)
+            ops.head_stats(ht[:Mt], w2t, inv_tt, ct2, want_nat=False, out_log2=rb2_t[:Mt])
+        else:  # Sinkhorn-Knopp on the (small) materialised CLS teacher logits
+            t_cls = ops.gemm_bf16(ht[:Mt], w2t, bias_n=b2t)
+            a_col, b_row = sinkhorn_knopp_biases(t_cls, teacher_temp, sk_iters, pg)
+            ct2 = ops.axpby(b2t, inv_tt * LOG2E, a_col, -LOG2E)
+            ops.axpb(b_row, LOG2E, out=rb2_t[:Mt])
+            del t_cls
+        ct2_patch = None
+        if Mm:
+            ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E)
+            ops.head_stats(ht[Mt:], w2t, inv_tt, ct2_patch, want_nat=False, out_log2=rb2_t[Mt:])
+        # ---- entries
+        hs_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
+        ht_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
+        ops.gather_cast_bf16(hs, plan.ent_s, hs_e)
+        ops.gather_cast_bf16(ht, plan.ent_t, ht_e)
+        lse2_e = ops.gather_f32(lse2_s, plan.ent_s)
+        rb2_e = ops.gather_f32(rb2_t, plan.ent_t)
+        cw = plan.cw_base
+        if Mm:
+            cw = plan.cw_base.clone()
+            ops.axpb(masks_weight.detach().float().contiguous(), ibot_weight / Mt,
+                     0.0, out=cw[plan.e_cls_pad:plan.e_cls_pad + Mm])
+        # ---- pass 2
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad[:2]) or s_head[2].weight.requires_grad
+        gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
+                                 lse2_e, rb2_e, cw, losses, want_db2=need_grad)
+        # ---- centre updates AFTER the loss (scripts/phase5_big_run.py:719): batch-mean logits are
+        # W2t . mean(h_t) + b2t by linearity -> a D-vector all-reduce instead of a K-vector one
+        if update_center and teacher_mode == "center":
+            w = _world(pg)
+            hsum = ops.cols_sum(ht[:Mt])
+            allreduce_sum_(hsum, pg)
+            mean_logits = ops.gemv_bf16(w2t, hsum, 1.0 / (Mt * w), b2t, 1.0)
+            ops.center_ema_(loss_mod.center, mean_logits, 1, loss_mod.center_momentum)
+            if Mm:
+                hsum = ops.cols_sum(ht[Mt:])
+                allreduce_sum_(hsum, pg)  # every rank masks the same number of tokens (no host sync)
+                mean_logits = ops.gemv_bf16(w2t, hsum, 1.0 / (Mm * w), b2t, 1.0)
+                ops.center_ema_(center_patch, mean_logits, 1, patch_momentum)
+        if need_grad:
+            ctx.save_for_backward(xs, a_s, hs_e, gt, db2p, w1s, w2s)
+            ctx.plan, ctx.s_head = plan, s_head
+            ctx.in_dtypes = (student_cls.dtype, None if student_patch is None else student_patch.dtype)
+        ctx.mark_non_differentiable(losses)
+        total = losses.sum() if Mm else losses[0].clone()
+        return total, losses
+
+    @staticmethod
+    def backward(ctx, g, _g_losses):
+        xs, a_s, hs_e, gt, db2p, w1s, w2s = ctx.saved_tensors
+        plan, s_head = ctx.plan, ctx.s_head
+        up = g.to(torch.float32).reshape(1).contiguous()
+        K, D = w2s.shape
+        rows = plan.Ms + plan.Mm
+        # dW2 (K, D) += g * Gt . HsE   (A = Gt K-major over entries, B = HsE MN-major)
+        _accumulate_grad(s_head[2].weight, lambda out, acc: ops.gemm_bf16(
+            gt, hs_e, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up))
+        db2 = ops.cols_sum(db2p)
+        _accumulate_grad(s_head[2].bias, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out,
+                                                                   alpha_dev=up))
+        # dH per entry = G . W2  (A = Gt MN-major, B = W2 MN-major), then sum the entries of each row
+        dh_e = ops.gemm_bf16(gt, w2s, a_mn_major=True, b_mn_major=True, m_fastest=True)
+        dh = torch.empty(rows, D, dtype=torch.float32, device=gt.device)
+        ops.gather_sum_rows(dh_e, plan.csr_ptr, plan.csr_ent, rows, dh)
+        da, part = ops.gelu_bwd(dh, a_s, scale_dev=up)
+        db1 = ops.cols_sum(part)
+        _accumulate_grad(s_head[0].bias, lambda out, acc: ops.axpby(db1, 1.0, out if acc else None, 1.0, out=out))
+        _accumulate_grad(s_head[0].weight, lambda out, acc: ops.gemm_bf16(
+            da, xs, a_mn_major=True, b_mn_major=True, out=out, accumulate=acc))
+        dx = ops.gemm_bf16(da, w1s, b_mn_major=True)
+        d_cls = dx[:plan.Ms].to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
+        d_patch = dx[plan.Ms:].to(ctx.in_dtypes[1]) if (plan.Mm and ctx.needs_input_grad[1]) else None
+        return d_cls, d_patch, None, None, None, None, None, None, None, None
+
+
+def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, student_head: nn.Sequential,
+                         teacher_head: nn.Sequential, dino_loss: DINOLoss, student_temp: float, teacher_temp: float,
+                         *, student_patch: Optional[torch.Tensor] = None, teacher_patch: Optional[torch.Tensor] = None,
+                         masks_weight: Optional[torch.Tensor] = None, center_patch: Optional[torch.Tensor] = None,
+                         ibot_weight: float = 1.0, patch_center_momentum: Optional[float] = None,
+                         update_center: bool = True) -> Dict[str, torch.Tensor]:
+    """Projection head + multi-crop DINO CE (+ iBOT masked-patch CE) in one fused path.
+
+    Equivalent to `dino_loss(student_head(student_cls), teacher_head(teacher_cls), ...)` of the reference
+    loop (scripts/phase5_big_run.py:1746-1754) but the (rows x K) logits exist only in TMEM.
+    Gradients of the student head parameters are accumulated straight into their `.grad` during
+    `backward()` (scaled by the upstream gradient, so `loss / accumulation_steps` and GradScaler work);
+    gradients w.r.t. `student_cls` / `student_patch` flow through autograd.
+    Returns {"loss": differentiable total, "loss_dino", "loss_ibot"}."""
+    for t in (student_cls, teacher_cls):
+        if not t.is_cuda:
+            raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
+    has_ibot = student_patch is not None
+    if has_ibot:
+        if teacher_patch is None or masks_weight is None or center_patch is None:
+            raise ValueError("iBOT needs teacher_patch, masks_weight and center_patch")
+    cfg = (student_temp, teacher_temp, dino_loss.n_global, dino_loss.n_local, ibot_weight, dino_loss.teacher_mode,
+           dino_loss.sk_iterations, dino_loss.process_group, update_center,
+           dino_loss.center_momentum if patch_center_momentum is None else patch_center_momentum)
+    total, losses = _FusedHeadLoss.apply(student_cls, student_patch, teacher_cls.detach(),
+                                         None if teacher_patch is None else teacher_patch.detach(), masks_weight,
+                                         student_head, teacher_head, dino_loss, center_patch, cfg)
+    return {"loss": total, "loss_dino": losses[0], "loss_ibot": losses[1]}
+
+
+class KoLeoLoss(nn.Module):  # pragma: no cover - named for API completeness only
+    """Not part of the hot path."""
+
+    def forward(self, *a, **k):
+        raise _ext.DinoxError("KoLeoLoss is outside the B200 loss-head scope of this round (SURVEY 8f)")

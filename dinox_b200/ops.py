@@ -190,14 +190,15 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_m
 
 
 def head_stats(h: torch.Tensor, w2: torch.Tensor, inv_tau: float, col2: Optional[torch.Tensor] = None,
-               want_nat: bool = True, want_log2: bool = True):
+               want_nat: bool = True, want_log2: bool = True, out_log2: Optional[torch.Tensor] = None):
     """Row-wise LSE of (h @ w2^T)*inv_tau + col2/log2e without materialising the logits."""
     _chk_cuda(h, w2, col2)
     rows, D = h.shape
     K = w2.shape[0]
     ws = torch.empty(int(_ext.lib().dinox_head_stats_workspace_bytes(rows, K)), dtype=torch.uint8, device=h.device)
     nat = torch.empty(rows, dtype=torch.float32, device=h.device) if want_nat else None
-    l2 = torch.empty(rows, dtype=torch.float32, device=h.device) if want_log2 else None
+    l2 = out_log2 if out_log2 is not None else (
+        torch.empty(rows, dtype=torch.float32, device=h.device) if want_log2 else None)
     _ext.call("dinox_head_stats", _p(h), _p(w2), rows, K, D, _rowmajor(h), _rowmajor(w2), float(inv_tau), _p(col2),
               _p(nat), _p(l2), _p(ws), _stream())
     return nat, l2
@@ -206,7 +207,9 @@ def head_stats(h: torch.Tensor, w2: torch.Tensor, inv_tau: float, col2: Optional
 def head_grad(w2s, w2t, hs_e, ht_e, inv_tau_s, inv_tau_t, cs2, ct2, ct2_alt, alt_from, lse2_e, rb2_e, cw_e,
               loss_out: torch.Tensor, loss_accumulate: bool = False, want_db2: bool = True,
               gt: Optional[torch.Tensor] = None):
-    """Pass 2.  Returns (Gt (K, E_pad) bf16, db2_partial or None)."""
+    """Pass 2.  loss_out: 2 fp32 ([0] entries < alt_from, [1] the rest).  Returns (Gt (K, E_pad) bf16,
+    db2_partial or None)."""
+    assert loss_out.numel() >= 2
     _chk_cuda(w2s, w2t, hs_e, ht_e)
     K, D = w2s.shape
     E = hs_e.shape[0]
@@ -221,3 +224,109 @@ def head_grad(w2s, w2t, hs_e, ht_e, inv_tau_s, inv_tau_t, cs2, ct2, ct2_alt, alt
               int(alt_from), _p(lse2_e), _p(rb2_e), _p(cw_e), _p(gt), _rowmajor(gt), _p(db2p), _p(loss_out),
               int(loss_accumulate), _p(ws), _stream())
     return gt, db2p
+
+
+def axpby(x: torch.Tensor, alpha: float, y: Optional[torch.Tensor], beta: float,
+          out: Optional[torch.Tensor] = None, alpha_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    out = torch.empty_like(x) if out is None else out
+    _ext.call("dinox_axpby", _p(x), float(alpha), _p(alpha_dev), _p(y), float(beta), _p(out), x.numel(), _stream())
+    return out
+
+
+def gemm_bf16_batched(a: torch.Tensor, b: torch.Tensor, *, a_mn_major=False, b_mn_major=False,
+                      out: Optional[torch.Tensor] = None, out_dtype=torch.float32, accumulate=False, alpha=1.0,
+                      alpha_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a: (B, M, K) [or (B, K, M)], b: (B, N, K) [or (B, K, N)], contiguous inner matrices."""
+    _chk_cuda(a, b, out)
+    Bt = a.shape[0]
+    M, Ka = (a.shape[2], a.shape[1]) if a_mn_major else (a.shape[1], a.shape[2])
+    N, Kb = (b.shape[2], b.shape[1]) if b_mn_major else (b.shape[1], b.shape[2])
+    assert Ka == Kb and b.shape[0] == Bt and a.stride(2) == 1 and b.stride(2) == 1
+    if out is None:
+        out = torch.empty(Bt, M, N, dtype=out_dtype, device=a.device)
+    _ext.call("dinox_gemm_bf16_batched", _p(a), _p(b), _p(out), Bt, M, N, Ka, a.stride(1), b.stride(1), out.stride(1),
+              a.stride(0), b.stride(0), out.stride(0), int(a_mn_major), int(b_mn_major), DT[out.dtype], int(accumulate),
+              float(alpha), _p(alpha_dev), _stream())
+    return out
+
+
+def normalize_tokens(feats: torch.Tensor, skip: int = 1):
+    """feats (B, T, D) fp32|bf16 with contiguous last dim -> xn (B, T-skip, D) bf16, inv_norm (B, T-skip)."""
+    _chk_cuda(feats)
+    Bt, T, D = feats.shape
+    if feats.stride(2) != 1:
+        feats = feats.contiguous()
+    xn = torch.empty(Bt, T - skip, D, dtype=torch.bfloat16, device=feats.device)
+    inv = torch.empty(Bt, T - skip, dtype=torch.float32, device=feats.device)
+    _ext.call("dinox_normalize_tokens", _p(feats), DT[feats.dtype], Bt, T, D, feats.stride(0), feats.stride(1), skip,
+              _p(xn), _p(inv), _stream())
+    return xn, inv
+
+
+def normalize_tokens_bwd(feats: torch.Tensor, dxn: torch.Tensor, inv_norm: torch.Tensor, grad: torch.Tensor,
+                         skip: int = 1, scale: float = 1.0, scale_dev: Optional[torch.Tensor] = None) -> None:
+    Bt, T, D = feats.shape
+    _ext.call("dinox_normalize_tokens_bwd", _p(feats), DT[feats.dtype], Bt, T, D, feats.stride(0), feats.stride(1), skip,
+              _p(dxn), _p(inv_norm), _p(scale_dev), float(scale), _p(grad), grad.stride(0), grad.stride(1), _stream())
+
+
+def gram_diff(xn_s: torch.Tensor, xn_t: torch.Tensor, loss_scale: float, want_delta: bool = True):
+    """loss = loss_scale * sum_b ||Xs Xs^T - Xt Xt^T||_F^2 ; delta (B, T', ldd) bf16 (optional)."""
+    Bt, Tp, D = xn_s.shape
+    ldd = (Tp + 7) // 8 * 8
+    delta = torch.empty(Bt, Tp, ldd, dtype=torch.bfloat16, device=xn_s.device) if want_delta else None
+    ws = torch.empty(int(_ext.lib().dinox_gram_diff_workspace_bytes(Bt, Tp)), dtype=torch.uint8, device=xn_s.device)
+    loss = torch.empty((), dtype=torch.float32, device=xn_s.device)
+    _ext.call("dinox_gram_diff", _p(xn_s), _p(xn_t), Bt, Tp, D, _p(delta), ldd, float(loss_scale), _p(loss), _p(ws), _stream())
+    return loss, delta
+
+
+def gather_cast_bf16(src: torch.Tensor, idx: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """out[r] = bf16(src[idx[r]]) (idx None: identity; idx < 0: zero row). src rows may be strided."""
+    _chk_cuda(src, out)
+    assert src.dim() == 2 and src.stride(1) == 1 and out.stride(1) == 1
+    rows = out.shape[0]
+    _ext.call("dinox_gather_cast_bf16", _p(src), DT[src.dtype], src.stride(0), _p(idx), rows, src.shape[1], _p(out),
+              out.stride(0), _stream())
+    return out
+
+
+def gather_f32(src: torch.Tensor, idx: torch.Tensor, fill: float = 0.0) -> torch.Tensor:
+    out = torch.empty(idx.numel(), dtype=torch.float32, device=src.device)
+    _ext.call("dinox_gather_f32", _p(src), _p(idx), idx.numel(), float(fill), _p(out), _stream())
+    return out
+
+
+def gelu_fwd(a: torch.Tensor) -> torch.Tensor:
+    h = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    _ext.call("dinox_gelu_fwd", _p(a), a.numel(), _p(h), _stream())
+    return h
+
+
+def gelu_bwd(dh: torch.Tensor, a: torch.Tensor, scale_dev: Optional[torch.Tensor] = None):
+    rows, D = a.shape
+    da = torch.empty(rows, D, dtype=torch.bfloat16, device=a.device)
+    part = torch.empty((rows + 63) // 64, D, dtype=torch.float32, device=a.device)
+    _ext.call("dinox_gelu_bwd", _p(dh), _p(a), rows, D, _p(scale_dev), _p(da), _p(part), _stream())
+    return da, part
+
+
+def gemv_bf16(w: torch.Tensor, x: torch.Tensor, alpha: float = 1.0, bias: Optional[torch.Tensor] = None,
+              beta: float = 1.0) -> torch.Tensor:
+    K, D = w.shape
+    out = torch.empty(K, dtype=torch.float32, device=w.device)
+    _ext.call("dinox_gemv_bf16", _p(w), _rowmajor(w), _p(x), K, D, float(alpha), _p(bias), float(beta), _p(out), _stream())
+    return out
+
+
+def gather_sum_rows(src: torch.Tensor, ptr: torch.Tensor, ent: torch.Tensor, rows: int, out: torch.Tensor,
+                    scale: float = 1.0, scale_dev: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    _ext.call("dinox_gather_sum_rows", _p(src), _rowmajor(src), _p(ptr), _p(ent), rows, src.shape[1], _p(scale_dev),
+              float(scale), _p(out), _rowmajor(out), int(accumulate), _stream())
+    return out
+
+
+def fill_(t: torch.Tensor, v: float = 0.0) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    _ext.call("dinox_fill_f32", _p(t), t.numel(), float(v), _stream())
+    return t

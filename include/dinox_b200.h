@@ -89,6 +89,10 @@ DINOX_API int dinox_center_ema(float* center, const float* colsum, float inv_row
 /* vector helper: out[k] = a[k]*alpha + beta (colbias = center*inv_tau etc.) */
 DINOX_API int dinox_axpb(const float* a, float alpha, float beta, float* out, int64_t n,
                          dinox_stream_t stream);
+/* out[k] = x[k]*alpha*(*alpha_dev) + y[k]*beta   (alpha_dev, y optional; e.g. col offsets
+ * (b2 - center)*inv_tau*log2e, or bias.grad += upstream * db) */
+DINOX_API int dinox_axpby(const float* x, float alpha, const float* alpha_dev, const float* y, float beta,
+                          float* out, int64_t n, dinox_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a4 / E1 / E3: cross-entropy between teacher and student rows on materialised logits.
@@ -146,7 +150,8 @@ DINOX_API int dinox_head_stats(const void* H, const void* W2, int64_t rows, int6
  * Fused pass 2: for E (student row, teacher row) entries recompute both logit tiles side by side
  * in TMEM and emit, without materialising logits or probabilities in HBM:
  *   Gt[k,e]  = cw[e]*inv_tau_s*( softmax_s[e,k] - q_t[e,k] )          (bf16, (K, ldg) = dL/dlogits^T)
- *   loss     (+)= sum_e cw[e] * sum_k q_t[e,k] * (-ln softmax_s[e,k])  (one fp32 on device)
+ *   loss[0..1] (+)= sum_e cw[e] * sum_k q_t[e,k] * (-ln softmax_s[e,k])  (two fp32 on device:
+ *              [0] entries < alt_from (CLS pairs), [1] entries >= alt_from (iBOT), [1]=0 if no alt)
  *   db2_partial[(2*ceil(E/128)), K]  column partial sums of Gt (reduce with dinox_cols_sum), optional
  * with softmax_s = 2^(S*inv_tau_s*log2e + cs2[k] - lse2[e]), q_t = 2^(T*inv_tau_t*log2e + ct2[k] - rb2[e]);
  * entries >= alt_from (multiple of 128) use ct2_alt (iBOT patch centre).  HsE/HtE: (E, D) bf16
@@ -162,6 +167,63 @@ DINOX_API int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE,
                               const float* cw_e, void* Gt, int64_t ldg, float* db2_partial,
                               float* loss_out, int loss_accumulate, void* workspace,
                               dinox_stream_t stream);
+
+/* batched variant: `batches` independent problems, element strides between problems.  Used for the
+ * per-image Gram backward  dXn[b] = alpha * Delta[b] @ Xn[b]  (autograd of torch.bmm,
+ * scripts/phase5_big_run.py:727). */
+DINOX_API int dinox_gemm_bf16_batched(const void* A, const void* B, void* C, int64_t batches, int64_t M,
+                                      int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                                      int64_t stride_a, int64_t stride_b, int64_t stride_c,
+                                      int a_mn_major, int b_mn_major, int out_dtype, int accumulate,
+                                      float alpha, const float* alpha_dev, dinox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6/a7  Gram anchoring (scripts/phase5_big_run.py:723-739).
+ * dinox_normalize_tokens: xn[b,t,:] = bf16(x / max(||x||,1e-12)) for tokens skip..T-1 of feats
+ *   (B, T, D) given by element strides (F.normalize, :726); inv_norm kept for the backward.
+ * dinox_gram_diff: per image Gs = Xs Xs^T and Gt = Xt Xt^T as two TMEM accumulators of one tile,
+ *   loss = loss_scale * sum (Gs-Gt)^2 (mse_loss, :738) and Delta = Gs-Gt as bf16 (B, tokens, ldd)
+ *   for the backward GEMM; the Gram matrices themselves are never written.
+ * dinox_normalize_tokens_bwd: dX = (dXn - xn <xn,dXn>) * inv_norm * scale into grad (B, T, D).
+ * ------------------------------------------------------------------------------------------ */
+DINOX_API int dinox_normalize_tokens(const void* feats, int dtype, int64_t batch, int64_t tokens_total,
+                                     int64_t D, int64_t stride_b, int64_t stride_t, int skip,
+                                     void* xn_bf16, float* inv_norm, dinox_stream_t stream);
+DINOX_API int dinox_normalize_tokens_bwd(const void* feats, int dtype, int64_t batch, int64_t tokens_total,
+                                         int64_t D, int64_t stride_b, int64_t stride_t, int skip,
+                                         const float* dxn, const float* inv_norm, const float* scale_dev,
+                                         float scale, float* grad, int64_t gstride_b, int64_t gstride_t,
+                                         dinox_stream_t stream);
+DINOX_API size_t dinox_gram_diff_workspace_bytes(int64_t batches, int64_t tokens);
+DINOX_API int dinox_gram_diff(const void* xn_s, const void* xn_t, int64_t batches, int64_t tokens, int64_t D,
+                              void* delta, int64_t ldd, float loss_scale, float* loss_out, void* workspace,
+                              dinox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Staging helpers around the contractions (caller-side glue of scripts/phase5_big_run.py:1746-1747:
+ * `feats[:, 0]` slicing, autocast's fp32->bf16 casts, nn.GELU of zoo/arch.py:254).
+ * ------------------------------------------------------------------------------------------ */
+/* dst[r,:] = bf16(src[idx ? idx[r] : r, :]); idx[r] < 0 writes a zero row (padding entries) */
+DINOX_API int dinox_gather_cast_bf16(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx,
+                                     int64_t rows, int64_t D, void* dst, int64_t ld_dst,
+                                     dinox_stream_t stream);
+DINOX_API int dinox_gather_f32(const float* src, const int64_t* idx, int64_t n, float fill, float* out,
+                               dinox_stream_t stream);
+/* h = bf16(gelu_erf(a)), n elements */
+DINOX_API int dinox_gelu_fwd(const float* a, int64_t n, void* h_bf16, dinox_stream_t stream);
+/* da = bf16(dh * (*scale_dev) * gelu'(a)); colsum_partial (ceil(rows/64), D) partial column sums */
+DINOX_API size_t dinox_gelu_bwd_workspace_bytes(int64_t rows, int64_t D);
+DINOX_API int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int64_t D, const float* scale_dev,
+                             void* da_bf16, float* colsum_partial, dinox_stream_t stream);
+/* out[k] = alpha * sum_d W[k,d] x[d] + beta * bias[k]   (W bf16 (K,D), x fp32): batch-mean teacher
+ * logits from the mean head activation, used for the centre update of the fused path (:686-690) */
+DINOX_API int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64_t D, float alpha,
+                              const float* bias, float beta, float* out, dinox_stream_t stream);
+/* dst[r,:] (+)= scale*(*scale_dev) * sum_{i in [ptr[r],ptr[r+1])} src[ent[i],:]  (fp32) */
+DINOX_API int dinox_gather_sum_rows(const float* src, int64_t ld_src, const int64_t* ptr, const int64_t* ent,
+                                    int64_t rows, int64_t D, const float* scale_dev, float scale, float* dst,
+                                    int64_t ld_dst, int accumulate, dinox_stream_t stream);
+DINOX_API int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,466 @@
+"""GPU parity tests: the CUDA path (through the public drop-in API -> ctypes -> C ABI) against the
+CPU oracle and the golden vectors generated from the reference.  Run with `pytest -m gpu`.
+
+Tolerances (north_star): fp32 data through the row-wise kernels rtol 1e-5; anything that passes a
+bf16 tensor-core contraction rtol 1e-3 on losses (fp32 accumulate) against the oracle evaluated
+with the same bf16 operand policy, and the looser documented bound against the pure-fp32 oracle.
+Gradients that pass a bf16 backward GEMM carry the operand rounding of dL/dlogits (2^-9 relative
+per element, same as the reference under autocast): relative L2 error <= 4e-3.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losshead_oracle as O
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def assert_close(a, b, rtol, what=""):
+    r = rel(torch.as_tensor(a), torch.as_tensor(b))
+    assert r <= rtol, f"{what}: relative L2 error {r:.3e} > {rtol:.1e}"
+
+
+@pytest.fixture(scope="module")
+def dx():
+    import dinox_b200
+    from dinox_b200 import losshead, ops, _ext
+    assert _ext.lib().dinox_device_check() == 0, "needs a B200"
+    return losshead
+
+
+# ------------------------------------------------------------------------------------------------
+# a8 EMA
+# ------------------------------------------------------------------------------------------------
+def test_ema_golden_bit_exact(dx, golden):
+    g = golden("head_ema.npz")
+    n = int(g["n_params"])
+    ps = [T(g[f"ps_{i}"]).to(DEV) for i in range(n)]
+    pt = [T(g[f"pt0_{i}"]).to(DEV) for i in range(n)]
+    dx.ema_update(pt, ps, float(g["ema"]))
+    torch.cuda.synchronize()
+    for i in range(n):
+        ref = T(g[f"pt1_{i}"])
+        ulp = (pt[i].cpu().view(torch.int32) - ref.view(torch.int32)).abs().max().item()
+        assert ulp <= 1, (i, ulp)
+
+
+def test_ema_module_api_and_ragged_sizes(dx):
+    torch.manual_seed(0)
+    s = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(n, device=DEV)) for n in (1, 3, 96, 4097, 384 * 384 + 4)])
+    t = torch.nn.ParameterList([torch.nn.Parameter(torch.randn_like(p)) for p in s])
+    ref = [q.detach().cpu().clone() for q in t]
+    O.ema_update(ref, [p.detach().cpu() for p in s], 0.99)
+    dx._ema_update(t, s, 0.99)
+    dx._ema_update(t, s, 0.99)  # second call re-uses the plan
+    O.ema_update(ref, [p.detach().cpu() for p in s], 0.99)
+    for a, b in zip(t, ref):
+        assert torch.allclose(a.detach().cpu(), b, rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# a2-a5 DINOLoss drop-in on materialised logits
+# ------------------------------------------------------------------------------------------------
+def test_dino_loss_uniform_entropy_wall(dx, golden):
+    g = golden("dino_uniform.npz")
+    k = int(g["out_dim"])
+    l = dx.DINOLoss(k, 0.9).to(DEV)
+    loss = l(torch.zeros(4, k, device=DEV), torch.zeros(4, k, device=DEV), 0.1, 0.04)
+    assert abs(loss.item() - math.log(k)) < 1e-4
+    assert abs(loss.item() - float(g["loss"])) < 1e-4
+
+
+def test_dino_loss_seeded_two_calls(dx, golden):
+    g = golden("dino_seeded.npz")
+    l = dx.DINOLoss(128, 0.9).to(DEV)
+    for tag in ("a", "b"):
+        s = T(g["student"]).to(DEV).requires_grad_(True)
+        loss = l(s, T(g["teacher"]).to(DEV), 0.1, 0.04)
+        loss.backward()
+        assert abs(loss.item() - float(g[f"loss_{tag}"])) <= 1e-5 * abs(float(g[f"loss_{tag}"]))
+        assert_close(s.grad, T(g[f"grad_{tag}"]), 1e-5, f"grad_{tag}")
+        assert_close(l.center, T(g[f"center_{tag}"]), 1e-5, f"center_{tag}")
+    assert list(l.state_dict().keys()) == ["center"] and l.center.shape == (1, 128)
+
+
+@pytest.mark.parametrize("name", ["k1000", "k4099", "k65536"])
+def test_dino_loss_shapes(dx, golden, name):
+    g = golden("dino_shapes.npz")
+    rows, k = [int(v) for v in g[f"{name}_shape"]]
+    gen = torch.Generator().manual_seed(int(g[f"{name}_seed"]))
+    scale = float(g[f"{name}_scale"])
+    s = (torch.randn(rows, k, generator=gen) * scale).to(DEV).requires_grad_(True)
+    t = (torch.randn(rows, k, generator=gen) * scale).to(DEV)
+    c0 = torch.randn(1, k, generator=gen) * 0.1
+    l = dx.DINOLoss(k, float(g[f"{name}_mom"])).to(DEV)
+    l.center.copy_(c0)
+    loss = l(s, t, 0.1, 0.04)
+    loss.backward()
+    assert abs(loss.item() - float(g[f"{name}_loss"])) <= 1e-5 * abs(float(g[f"{name}_loss"]))
+    if f"{name}_grad" in g:
+        assert_close(s.grad, T(g[f"{name}_grad"]), 1e-5, "grad")
+        assert_close(l.center, T(g[f"{name}_center1"]), 1e-5, "center")
+    else:
+        assert abs(s.grad.norm().item() - float(g[f"{name}_grad_norm"])) <= 1e-5 * float(g[f"{name}_grad_norm"])
+        assert_close(s.grad[:, :64], T(g[f"{name}_grad_head"]), 1e-5, "grad head")
+        assert_close(l.center[:, :64], T(g[f"{name}_center1"]), 1e-5, "center head")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_multicrop_vs_oracle(dx, dtype):
+    gen = torch.Generator().manual_seed(5)
+    B, Vg, Vl, K = 6, 2, 8, 2048
+    V = Vg + Vl
+    s = torch.randn(B * V, K, generator=gen).to(dtype)
+    t = torch.randn(B * Vg, K, generator=gen).to(dtype)
+    c = torch.randn(1, K, generator=gen) * 0.1
+    so = s.float().clone().requires_grad_(True)
+    ref = O.multicrop_dino_loss(so, t.float(), c, 0.1, 0.04, Vg, Vl)
+    ref.backward()
+    l = dx.DINOLoss(K, 0.9, n_global=Vg, n_local=Vl).to(DEV)
+    l.center.copy_(c)
+    sd = s.to(DEV).requires_grad_(True)
+    loss = l(sd, t.to(DEV), 0.1, 0.04)
+    (loss * 0.25).backward()  # upstream gradient as with loss / accumulation_steps
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert sd.grad.dtype == dtype
+    assert_close(sd.grad, so.grad * 0.25, 1e-5 if dtype == torch.float32 else 4e-3, "grad")
+    assert_close(l.center, O.center_update(c, t.float(), 0.9), 1e-5, "center")
+
+
+def test_sinkhorn_vs_oracle(dx):
+    gen = torch.Generator().manual_seed(6)
+    B, Vg, Vl, K = 8, 2, 2, 1024
+    V = Vg + Vl
+    s = torch.randn(B * V, K, generator=gen)
+    t = torch.randn(B * Vg, K, generator=gen) * 2.0
+    q_ref = O.sinkhorn_knopp(t, 0.04, 3)
+    q = dx.sinkhorn_knopp_teacher(t.to(DEV), 0.04, 3)
+    assert_close(q, q_ref, 1e-4, "sinkhorn q")
+    so = s.clone().requires_grad_(True)
+    ref = O.multicrop_dino_loss(so, t, torch.zeros(1, K), 0.1, 0.04, Vg, Vl, teacher_mode="sinkhorn")
+    ref.backward()
+    l = dx.DINOLoss(K, 0.9, n_global=Vg, n_local=Vl, teacher_mode="sinkhorn").to(DEV)
+    sd = s.to(DEV).requires_grad_(True)
+    loss = l(sd, t.to(DEV), 0.1, 0.04)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-5 * abs(ref.item())
+    assert_close(sd.grad, so.grad, 1e-4, "grad")
+    assert l.center.abs().max().item() == 0.0  # centre untouched in sinkhorn mode
+    # extreme logits stay finite (log-domain)
+    assert torch.isfinite(dx.sinkhorn_knopp_teacher((t * 50).to(DEV), 0.04, 3)).all()
+
+
+def test_ibot_rows_materialised(dx):
+    from dinox_b200 import ops
+    gen = torch.Generator().manual_seed(7)
+    Mm, K, n_img = 40, 512, 4
+    s = torch.randn(Mm, K, generator=gen)
+    t = torch.randn(Mm, K, generator=gen)
+    c = torch.randn(1, K, generator=gen) * 0.1
+    w = torch.rand(Mm, generator=gen)
+    so = s.clone().requires_grad_(True)
+    ref = O.ibot_patch_loss(so, t, c, 0.1, 0.04, w, n_img)
+    ref.backward()
+    sd, td = s.to(DEV), t.to(DEV)
+    colb = ops.axpb(c.reshape(-1).to(DEV), 1 / 0.04)
+    rb = ops.rows_lse(td, 1 / 0.04, colb)
+    lse = ops.rows_lse(sd, 1 / 0.1)
+    loss = ops.ce_fwd(sd, td, Mm, 1, 1, 10.0, 25.0, colb, rb, lse, w.to(DEV), 1.0 / n_img, False)
+    grad = ops.ce_bwd(sd, td, Mm, 1, 1, 10.0, 25.0, colb, rb, lse, w.to(DEV), 1.0 / n_img, False,
+                      torch.ones((), device=DEV))
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert_close(grad, so.grad, 1e-5, "grad")
+
+
+def test_entropy_diagnostics(dx):
+    gen = torch.Generator().manual_seed(8)
+    s = torch.randn(12, 3000, generator=gen)
+    t = torch.randn(12, 3000, generator=gen)
+    c = torch.randn(1, 3000, generator=gen) * 0.1
+    te, se = O.entropy_diagnostics(s, t, c, 0.1, 0.04)
+    te2, se2 = dx.entropy_diagnostics(s.to(DEV), t.to(DEV), c.to(DEV), 0.1, 0.04)
+    assert abs(te2.item() - te.item()) < 1e-4 * max(1.0, abs(te.item()))
+    assert abs(se2.item() - se.item()) < 1e-4 * max(1.0, abs(se.item()))
+
+
+# ------------------------------------------------------------------------------------------------
+# a6-a7 Gram anchoring
+# ------------------------------------------------------------------------------------------------
+def test_gram_golden(dx, golden):
+    g = golden("dino_seeded.npz")
+    # D = 32 is below one 64-wide K block: zero-filled by TMA
+    sf = T(g["gram_student"]).to(DEV).requires_grad_(True)
+    tf = T(g["gram_teacher"]).to(DEV)
+    loss = dx.compute_gram_anchoring_loss(sf, tf)
+    loss.backward()
+    ref = float(g["gram_loss"])
+    assert abs(loss.item() - ref) <= 5e-3 * ref, (loss.item(), ref)   # bf16 operands vs fp32 reference
+    assert_close(sf.grad, T(g["gram_grad"]), 2e-2, "gram grad vs fp32 reference")
+    assert sf.grad[:, 0].abs().max().item() == 0.0
+    assert dx.compute_gram_anchoring_loss(tf, tf).item() == 0.0
+    gm = dx.compute_gram_matrix(T(g["gram_student"])[:, 1:].contiguous().to(DEV))
+    assert_close(gm, T(g["gram_matrix"]), 5e-3, "gram matrix")
+
+
+@pytest.mark.parametrize("shape", [(3, 201, 384), (2, 261, 64), (1, 1029, 128)])
+def test_gram_vs_oracle_bf16_policy(dx, shape):
+    gen = torch.Generator().manual_seed(9)
+    sf = torch.randn(*shape, generator=gen)
+    tf = sf + 0.3 * torch.randn(*shape, generator=gen)
+    so = sf.clone().requires_grad_(True)
+    ref = O.gram_anchoring_loss(so, tf, policy="bf16")
+    (ref * 3.0).backward()
+    sd = sf.to(DEV).requires_grad_(True)
+    loss = dx.compute_gram_anchoring_loss(sd, tf.to(DEV))
+    (loss * 3.0).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-3 * abs(ref.item()), (loss.item(), ref.item())
+    assert_close(sd.grad, so.grad, 4e-3, "gram grad")
+    ref32 = O.gram_anchoring_loss(sf, tf, policy="fp32")
+    assert abs(loss.item() - ref32.item()) <= 1e-2 * abs(ref32.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# a1 projection head
+# ------------------------------------------------------------------------------------------------
+def test_head_golden_and_state_dict(dx, golden):
+    g = golden("head_ema.npz")
+    head = dx.ProjectionHead(32, 96).to(DEV)
+    assert list(head.state_dict().keys()) == ["0.weight", "0.bias", "2.weight", "2.bias"]
+    head.load_state_dict({k: T(g["head_" + k.replace(".", "_")]) for k in head.state_dict().keys()})
+    out = head(T(g["cls"]).to(DEV))
+    assert out.dtype == torch.float32
+    assert_close(out, T(g["head_out"]), 1e-2, "head vs fp32 reference (bf16 operands)")
+    p = O.HeadParams(*[T(g[f"head_{k}"]) for k in ("0_weight", "0_bias", "2_weight", "2_bias")])
+    assert_close(out, O.head_forward(T(g["cls"]), p, policy="bf16"), 1e-4, "head vs bf16-policy oracle")
+    with torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        assert head(T(g["cls"]).to(DEV)).dtype == torch.bfloat16
+
+
+def test_head_backward_vs_oracle(dx):
+    gen = torch.Generator().manual_seed(10)
+    rows, D, K = 200, 128, 1000
+    from dinox_b200 import synth
+    sd = synth.head_weights(D, K, gen)
+    x = torch.randn(rows, D, generator=gen)
+    dz = torch.randn(rows, K, generator=gen) / K
+    p = O.HeadParams(*[sd[k].clone().requires_grad_(True) for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    xo = x.clone().requires_grad_(True)
+    z = O.head_forward(xo, p, policy="bf16")
+    z.backward(dz)
+    head = dx.ProjectionHead(D, K).to(DEV)
+    head.load_state_dict(sd)
+    xd = x.to(DEV).requires_grad_(True)
+    zd = head(xd)
+    zd.backward(dz.to(DEV))
+    assert_close(zd, z, 1e-4, "logits")
+    assert_close(xd.grad, xo.grad, 4e-3, "dx")
+    for (n, q), r in zip(head.named_parameters(), p.tensors()):
+        assert_close(q.grad, r.grad, 4e-3, n)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused head + CE (+ iBOT): logits never materialised
+# ------------------------------------------------------------------------------------------------
+def _fused_case(dx, B, Vg, Vl, D, K, n_mask, teacher_mode="center", seed=11, accum=4):
+    from dinox_b200 import synth
+    gen = torch.Generator().manual_seed(seed)
+    V = Vg + Vl
+    Mm = B * Vg * n_mask
+    s_sd, t_sd = synth.head_weights(D, K, gen), synth.head_weights(D, K, gen)
+    feats = dict(student_cls=torch.randn(B * V, D, generator=gen), teacher_cls=torch.randn(B * Vg, D, generator=gen))
+    if Mm:
+        feats.update(student_patch=torch.randn(Mm, D, generator=gen), teacher_patch=torch.randn(Mm, D, generator=gen),
+                     masks_weight=torch.full((Mm,), 1.0 / n_mask))
+    c0 = torch.randn(1, K, generator=gen) * 0.05
+    cp0 = torch.randn(1, K, generator=gen) * 0.05
+    # ---- oracle
+    sp = O.HeadParams(*[s_sd[k].clone().requires_grad_(True) for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    tp = O.HeadParams(*[t_sd[k].clone() for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    orc = O.LossHeadOracle(sp, tp, K, center_momentum=0.9, n_global=Vg, n_local=Vl, teacher_mode=teacher_mode,
+                           policy="bf16")
+    orc.center, orc.center_patch = c0.clone(), cp0.clone()
+    of = {k: (v.clone().requires_grad_(True) if k.startswith("student") else v) for k, v in feats.items()}
+    out_ref = orc.step(of["student_cls"], of["teacher_cls"], 0.1, 0.04, student_patch=of.get("student_patch"),
+                       teacher_patch=of.get("teacher_patch"), masks_weight=of.get("masks_weight"), accum=accum)
+    # ---- CUDA
+    s_head, t_head = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+    s_head.load_state_dict(s_sd); t_head.load_state_dict(t_sd)
+    for q in t_head.parameters():
+        q.requires_grad_(False)
+    dl = dx.DINOLoss(K, 0.9, n_global=Vg, n_local=Vl, teacher_mode=teacher_mode).to(DEV)
+    dl.center.copy_(c0)
+    cpatch = cp0.clone().to(DEV)
+    df = {k: (v.to(DEV).requires_grad_(True) if k.startswith("student") else v.to(DEV)) for k, v in feats.items()}
+    out = dx.fused_head_dino_loss(df["student_cls"], df["teacher_cls"], s_head, t_head, dl, 0.1, 0.04,
+                                  student_patch=df.get("student_patch"), teacher_patch=df.get("teacher_patch"),
+                                  masks_weight=df.get("masks_weight"), center_patch=cpatch if Mm else None)
+    (out["loss"] / accum).backward()
+    torch.cuda.synchronize()
+    return out, out_ref, df, of, s_head, sp, dl, orc, cpatch
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=4, Vg=2, Vl=0, D=64, K=1024, n_mask=0),        # reference-shaped: 2 global views, no iBOT
+    dict(B=4, Vg=2, Vl=3, D=64, K=1024, n_mask=6),        # multi-crop + iBOT, ragged entry count
+    dict(B=8, Vg=2, Vl=8, D=384, K=4096, n_mask=58),      # C1-like rows at reduced K
+    dict(B=3, Vg=2, Vl=2, D=128, K=1000, n_mask=5),       # K not a multiple of the tile
+])
+def test_fused_head_loss_vs_oracle(dx, cfg):
+    out, ref, df, of, s_head, sp, dl, orc, cpatch = _fused_case(dx, **cfg)
+    assert abs(out["loss_dino"].item() - ref["loss_dino"].item()) <= 1e-3 * abs(ref["loss_dino"].item())
+    if cfg["n_mask"]:
+        assert abs(out["loss_ibot"].item() - ref["loss_ibot"].item()) <= 1e-3 * abs(ref["loss_ibot"].item())
+        assert_close(df["student_patch"].grad, of["student_patch"].grad, 4e-3, "d student_patch")
+        assert_close(cpatch, orc.center_patch, 1e-4, "center_patch")
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())
+    assert_close(df["student_cls"].grad, of["student_cls"].grad, 4e-3, "d student_cls")
+    for (n, q), r in zip(s_head.named_parameters(), sp.tensors()):
+        assert_close(q.grad, r.grad, 4e-3, n)
+    assert_close(dl.center, orc.center, 1e-4, "center")
+
+
+def test_fused_sinkhorn_vs_oracle(dx):
+    out, ref, df, of, s_head, sp, dl, orc, _ = _fused_case(dx, B=8, Vg=2, Vl=2, D=64, K=512, n_mask=0,
+                                                           teacher_mode="sinkhorn")
+    assert abs(out["loss_dino"].item() - ref["loss_dino"].item()) <= 1e-3 * abs(ref["loss_dino"].item())
+    assert_close(df["student_cls"].grad, of["student_cls"].grad, 4e-3, "d student_cls")
+    assert_close(s_head[2].weight.grad, sp.w2.grad, 4e-3, "dW2")
+
+
+def test_fused_equals_materialised_path(dx):
+    """Degenerate-case identity on the GPU: fused kernels == head GEMMs + DINOLoss row kernels
+    (same bf16 operands, logits kept fp32 on both sides)."""
+    from dinox_b200 import synth
+    gen = torch.Generator().manual_seed(21)
+    B, Vg, Vl, D, K = 4, 2, 2, 64, 1024
+    V = Vg + Vl
+    s_sd, t_sd = synth.head_weights(D, K, gen), synth.head_weights(D, K, gen)
+    xs, xt = torch.randn(B * V, D, generator=gen).to(DEV), torch.randn(B * Vg, D, generator=gen).to(DEV)
+    c0 = (torch.randn(1, K, generator=gen) * 0.05).to(DEV)
+    res = []
+    for fused in (True, False):
+        sh, th = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+        sh.load_state_dict(s_sd); th.load_state_dict(t_sd)
+        dl = dx.DINOLoss(K, 0.9, n_global=Vg, n_local=Vl).to(DEV)
+        dl.center.copy_(c0)
+        x = xs.clone().requires_grad_(True)
+        if fused:
+            loss = dx.fused_head_dino_loss(x, xt, sh, th, dl, 0.1, 0.04)["loss"]
+        else:
+            loss = dl(sh(x), th(xt), 0.1, 0.04)
+        loss.backward()
+        res.append((loss.item(), x.grad.clone(), sh[2].weight.grad.clone(), sh[0].weight.grad.clone(), dl.center.clone()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[1][0])
+    assert_close(res[0][1], res[1][1], 4e-3, "dx")
+    assert_close(res[0][2], res[1][2], 4e-3, "dW2")
+    assert_close(res[0][3], res[1][3], 4e-3, "dW1")
+    assert_close(res[0][4], res[1][4], 1e-5, "center")
+
+
+def test_grad_accumulation_over_micro_steps(dx):
+    """Two backward passes accumulate into .grad like autograd does (accumulation window), and the
+    upstream gradient (loss / accumulation_steps) scales every gradient."""
+    from dinox_b200 import synth
+    gen = torch.Generator().manual_seed(22)
+    B, D, K = 4, 64, 512
+    sh, th = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+    dl = dx.DINOLoss(K, 0.9).to(DEV)
+    xs, xt = torch.randn(2 * B, D, generator=gen).to(DEV), torch.randn(2 * B, D, generator=gen).to(DEV)
+    x1 = xs.clone().requires_grad_(True)
+    dx.fused_head_dino_loss(x1, xt, sh, th, dl, 0.1, 0.04, update_center=False)["loss"].backward()
+    g1 = [q.grad.clone() for q in sh.parameters()]
+    x2 = xs.clone().requires_grad_(True)
+    (dx.fused_head_dino_loss(x2, xt, sh, th, dl, 0.1, 0.04, update_center=False)["loss"] * 0.5).backward()
+    for q, g in zip(sh.parameters(), g1):
+        assert_close(q.grad, g * 1.5, 1e-5, "accumulated grad")
+    assert_close(x2.grad, x1.grad * 0.5, 1e-5, "scaled dx")
+
+
+# ------------------------------------------------------------------------------------------------
+# whole reference micro-step (golden, produced by the reference loop on synthetic CT crops)
+# ------------------------------------------------------------------------------------------------
+def test_microstep_golden(dx, golden):
+    g = golden("microstep.npz")
+    K, D = 256, 32
+    s_head, t_head = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+    s_head.load_state_dict({k: T(g["s_head_" + k.replace(".", "_")]) for k in s_head.state_dict()})
+    t_head.load_state_dict({k: T(g["t_head_" + k.replace(".", "_")]) for k in t_head.state_dict()})
+    dl = dx.DINOLoss(K, float(g["momentum"])).to(DEV)
+    dl.center.copy_(T(g["center0"]))
+    sf = T(g["student_feats"]).to(DEV).requires_grad_(True)
+    tf = T(g["teacher_feats"]).to(DEV)
+    accum = int(g["accum"])
+    # the reference call sequence (scripts/phase5_big_run.py:1746-1772) with the drop-in modules
+    student_out = s_head(sf[:, 0])
+    teacher_out = t_head(tf[:, 0])
+    loss_dino = dl(student_out, teacher_out, float(g["student_temp"]), float(g["teacher_temp"]))
+    loss_gram = dx.compute_gram_anchoring_loss(sf, tf)
+    loss = (loss_dino + 1.0 * loss_gram) / accum
+    loss.backward()
+    assert abs(loss_dino.item() - float(g["loss_dino"])) <= 2e-3 * float(g["loss_dino"])
+    assert abs(loss_gram.item() - float(g["loss_gram"])) <= 1e-2 * float(g["loss_gram"])
+    assert_close(dl.center, T(g["center1"]), 2e-3, "center")
+    assert_close(sf.grad, T(g["d_student_feats"]), 2e-2, "d feats vs fp32 reference")
+    for k in ("0_weight", "0_bias", "2_weight", "2_bias"):
+        q = dict(s_head.named_parameters())[k.replace("_", ".")]
+        assert_close(q.grad, T(g[f"g_head_{k}"]), 2e-2, k)
+    # fused path on the same inputs gives the same DINO loss
+    dl2 = dx.DINOLoss(K, float(g["momentum"])).to(DEV)
+    dl2.center.copy_(T(g["center0"]))
+    out = dx.fused_head_dino_loss(sf[:, 0].detach(), tf[:, 0], s_head, t_head, dl2, float(g["student_temp"]),
+                                  float(g["teacher_temp"]))
+    assert abs(out["loss_dino"].item() - loss_dino.item()) <= 1e-4 * abs(loss_dino.item())
+    assert_close(dl2.center, dl.center, 1e-5, "fused center == row-kernel center")
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties at the BASELINE configs (no CPU oracle at this size)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties_c1(dx):
+    from dinox_b200 import synth
+    sh = synth.LossHeadShapes(**synth.CONFIGS["C1"])
+    gen = synth.seeded_generator(1, 0)
+    K, D = sh.out_dim, sh.dim
+    s_head, t_head = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+    t_head.load_state_dict(s_head.state_dict())
+    f = {k: v.to(DEV) for k, v in synth.feature_batch(sh, gen, with_tokens=False).items()}
+    dl = dx.DINOLoss(K, 0.9, n_global=2, n_local=8).to(DEV)
+    cp = torch.zeros(1, K, device=DEV)
+    # (1) teacher == student weights and identical rows => CE >= entropy, finite, > 0
+    out = dx.fused_head_dino_loss(f["student_cls"], f["teacher_cls"], s_head, t_head, dl, 0.1, 0.04,
+                                  student_patch=f["student_patch"], teacher_patch=f["teacher_patch"],
+                                  masks_weight=f["masks_weight"], center_patch=cp, update_center=False)
+    assert torch.isfinite(out["loss"]) and out["loss_dino"].item() > 0 and out["loss_ibot"].item() > 0
+    # (2) zero head weights => uniform student => loss == ln K for both terms (entropy wall)
+    with torch.no_grad():
+        for q in s_head.parameters():
+            q.zero_()
+    out = dx.fused_head_dino_loss(f["student_cls"], f["teacher_cls"], s_head, t_head, dl, 0.1, 0.04,
+                                  student_patch=f["student_patch"], teacher_patch=f["teacher_patch"],
+                                  masks_weight=f["masks_weight"], center_patch=cp, update_center=False)
+    assert abs(out["loss_dino"].item() - math.log(K)) < 1e-3
+    assert abs(out["loss_ibot"].item() - math.log(K)) < 1e-3
+    # (3) determinism: same inputs, bitwise same loss
+    out2 = dx.fused_head_dino_loss(f["student_cls"], f["teacher_cls"], s_head, t_head, dl, 0.1, 0.04,
+                                   student_patch=f["student_patch"], teacher_patch=f["teacher_patch"],
+                                   masks_weight=f["masks_weight"], center_patch=cp, update_center=False)
+    assert out2["loss"].item() == out["loss"].item()
+
+
+def test_no_cpu_fallback(dx):
+    with pytest.raises(Exception):
+        dx.DINOLoss(16)(torch.zeros(2, 16), torch.zeros(2, 16), 0.1, 0.04)
+    with pytest.raises(Exception):
+        dx.compute_gram_anchoring_loss(torch.zeros(1, 5, 8), torch.zeros(1, 5, 8))
+    with pytest.raises(Exception):
+        dx.ProjectionHead(8, 16)(torch.zeros(2, 8))

@@ -200,10 +200,10 @@ def g_grad():
         G = cw[:, None] * its * (p - q)
         loss_ref = (cw * (-(q * (S - lse_s[:, None])).sum(-1))).sum()
         cs2 = b2s * (its * ops.LOG2E); ct2 = (b2t - cen) * (itt * ops.LOG2E)
-        loss = torch.zeros((), device=dev)
+        loss = torch.zeros(2, device=dev)
         gt, db2p = ops.head_grad(ws, wt, hs, ht, its, itt, cs2, ct2, None, 0, lse_s * ops.LOG2E, lse_t * ops.LOG2E, cw, loss)
         torch.cuda.synchronize()
-        print(f"grad E={E} K={K} D={D}: G {relerr(gt[:, :E].t(), G)} loss {loss.item():.6f} ref {loss_ref.item():.6f} "
+        print(f"grad E={E} K={K} D={D}: G {relerr(gt[:, :E].t(), G)} loss {loss[0].item():.6f} ref {loss_ref.item():.6f} "
               f"db2 {relerr(db2p.sum(0), G.sum(0))}")
         if E >= 1152:
             for _ in range(2): ops.head_grad(ws, wt, hs, ht, its, itt, cs2, ct2, None, 0, lse_s * ops.LOG2E, lse_t * ops.LOG2E, cw, loss, gt=gt)
