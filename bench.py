@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Loss-head throughput benchmark (BASELINE.json metric: loss-head crops/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host CPUs
+
+A step = one micro-step of the loss head on one batch of synthetic backbone features: projection
+head + multi-crop DINO CE + iBOT masked-patch CE (fused, logits never in HBM), Gram anchoring,
+backward to d(features) and .grad of the head, centre updates, and the EMA of ALL student
+parameters once per `accum` micro-steps.  Workload at N=1: BASELINE.json configs[1]
+("C2": ViT-S/16, batch 64 x accum 4, 2 global + 8 local crops, K=65536, Gram on).  N>1: the same
+per-GPU batch on every rank (weak scaling), centre statistics all-reduced over NCCL.
+
+Prints ONE JSON line (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "loss_head_crops_per_sec"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs: the oracle (a port of the reference algorithm) timed on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_step_time(cfg_name: str, sample_batch: int, steps: int, warmup: int, accum: int):
+    """Times oracle.LossHeadOracle.step (+ amortised EMA of the full parameter list) on a
+    `sample_batch`-image slice of the workload.  Returns (crops/s, cores, description)."""
+    from dinox_b200 import synth
+    from oracle import losshead_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(synth.CONFIGS[cfg_name])
+    cfg["batch"] = sample_batch
+    sh = synth.LossHeadShapes(**cfg)
+    g = synth.seeded_generator(2, 0)
+    D, K = sh.dim, sh.out_dim
+    sw, tw = synth.head_weights(D, K, g), synth.head_weights(D, K, g)
+    sp = O.HeadParams(*[sw[k].requires_grad_(True) for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    tp = O.HeadParams(*[tw[k] for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    orc = O.LossHeadOracle(sp, tp, K, center_momentum=0.9, n_global=sh.n_global, n_local=sh.n_local, policy="fp32")
+    depth = synth.BACKBONES.get(D, dict(depth=12))["depth"]
+    shapes = synth.student_param_shapes(D, depth, K)[:-4]
+    s_all = [torch.randn(s) * 0.02 for s in shapes] + [p.detach() for p in sp.tensors()]
+    t_all = [torch.randn(s) * 0.02 for s in shapes] + [p.detach().clone() for p in tp.tensors()]
+    f = synth.feature_batch(sh, g)
+    times = []
+    for i in range(warmup + steps):
+        fs = {k: (v.clone().requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()}
+        t0 = time.perf_counter()
+        orc.step(fs["student_cls"], fs["teacher_cls"], 0.1, 0.04, student_tok=fs["student_tok"],
+                 teacher_tok=fs["teacher_tok"], student_patch=fs.get("student_patch"),
+                 teacher_patch=fs.get("teacher_patch"), masks_weight=fs.get("masks_weight"), accum=accum)
+        if (i + 1) % accum == 0:
+            orc.ema(s_all, t_all, 0.996)
+            for p in sp.tensors():
+                p.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per_step = sum(times) / len(times)
+    desc = (f"{cfg_name} shapes at batch {sample_batch} ({sh.student_rows} student / {sh.teacher_rows} teacher / "
+            f"{sh.masked_rows} masked rows, K={K}), {steps} steps after {warmup} warm-up, fp32, "
+            f"torch {torch.__version__} CPU, oracle port of the reference algorithm")
+    return sh.student_rows / per_step, cores, desc, per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, cores, desc, per_step = cpu_oracle_step_time(args.config, args.cpu_sample_batch, args.steps, args.warmup,
+                                                         args.accum)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: ViT-S/16 loss head, 2 global + 8 local crops, K=65536, iBOT r=0.3, "
+                               f"Gram on, accum {args.accum}; CPU sample batch {args.cpu_sample_batch}"},
+        "cpu_baseline": {"value": value, "unit": "crops/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from dinox_b200 import ops, synth
+    from dinox_b200.step import LossHeadStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = True
+
+    sh = synth.LossHeadShapes(**synth.CONFIGS[args.config])
+    step = LossHeadStep(sh, dev, accum=args.accum, process_group=pg)
+    g = synth.seeded_generator(2, rank)
+    host = {k: v.pin_memory() for k, v in synth.feature_batch(sh, g).items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def to_leaves(f):
+        return {k: (v.requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- leg 1: inputs resident in HBM ----------------
+    resident = {k: v.to(dev) for k, v in host.items()}
+    for _ in range(args.warmup):
+        step.micro_step(to_leaves({k: v.detach() for k, v in resident.items()}))
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.launch_count_reset()
+    ops.TIMER.reset()
+    ops.TIMER.enabled = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step.micro_step(to_leaves({k: v.detach() for k, v in resident.items()}))
+    e1.record()
+    barrier()
+    ops.TIMER.enabled = False
+    ops.TIMER.resolve()
+    clocks = sampler.stop()
+    launches = ops.launch_count()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms / args.steps
+    crops_per_step = sh.student_rows * world
+    value = crops_per_step / (ms_per_step * 1e-3)
+    loss_val = float(out["loss_total"].item())
+
+    # ---------------- leg 2: end to end from pinned host buffers ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def prefetch(i):
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            for k, v in host.items():
+                bufs[b][k].copy_(v, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream()
+        for b in range(2):
+            consumed[b].record(cur)
+        prefetch(0)
+        for i in range(n):
+            b = i & 1
+            if i + 1 < n:
+                prefetch(i + 1)          # H2D of the next step overlaps this step's kernels
+            cur.wait_event(ready[b])
+            o = step.micro_step(to_leaves({k: v.detach() for k, v in bufs[b].items()}))
+            consumed[b].record(cur)
+            loss_host.copy_(o["loss_total"].reshape(1), non_blocking=True)   # D2H of the step's result
+        cur.synchronize()
+
+    e2e_loop(max(args.warmup, 2))
+    barrier()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = crops_per_step / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = _peaks()
+    D, K = sh.dim, sh.out_dim
+    rows_s, rows_t = sh.student_rows + sh.masked_rows, sh.teacher_rows + sh.masked_rows
+    kt = {k: ops.TIMER.totals[k] / ops.TIMER.counts[k] for k in ops.TIMER.totals}
+    dom = max(kt, key=kt.get)
+    alg_flops = {
+        "head_grad": 2.0 * D * K * (rows_s + rows_t),          # student + teacher logit tiles (forward logits)
+        "head_stats_student": 0.0, "head_stats_teacher_cls": 0.0, "head_stats_teacher_patch": 0.0,  # recompute
+        "gemm_dW2": 2.0 * D * K * rows_s, "gemm_dH": 2.0 * D * K * rows_s,
+    }
+    ach = alg_flops.get(dom, 0.0) / (kt[dom] * 1e-3) / 1e12
+    peak_tf = peaks["tf_sustained"]
+    step_alg_tf = sh.flops() / (ms_per_step * 1e-3) / 1e12
+    roofline = {
+        "kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": ach / peak_tf, "traffic": None, "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
+        "kernel_ms": kt[dom], "kernels_ms": kt,
+        "step_algorithmic_tflops": step_alg_tf, "step_frac": step_alg_tf / peak_tf,
+        "ema_gbs": (12.0 * step.n_params / (kt["ema_multi"] * 1e-3) / 1e9) if "ema_multi" in kt else None,
+        "hbm_peak_gbs": peaks["hbm"],
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, desc, _ = cpu_oracle_step_time(args.config, args.cpu_sample_batch, 2, 1, args.accum)
+        cpu_baseline = {"value": v, "unit": "crops/s", "cores": cores, "kind": "port", "sample": desc}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"{args.config}: ViT-S/16 loss head, per-GPU batch {sh.batch} x accum {args.accum}, "
+                        f"{sh.n_global} global + {sh.n_local} local crops, K={K}, D={D}, iBOT r={sh.mask_ratio} "
+                        f"({sh.masked_rows} masked rows), Gram anchoring on ({sh.tokens - 1} tokens), "
+                        f"EMA of {step.n_params / 1e6:.1f} M params every {args.accum} micro-steps",
+            "rows": {"student": sh.student_rows, "teacher": sh.teacher_rows, "masked": sh.masked_rows},
+            "parallelism": f"dp{world}", "l2": "per-step working set (bf16 W2 x2 = 100 MB, dL/dlogits 1.1 GB) exceeds the 126 MB L2; no explicit flush",
+            "algorithmic_gflop_per_step": sh.flops() / 1e9,
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "crops/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "loss": loss_val,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--accum", type=int, default=4)
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device - the dinox_b200 path has no CPU fallback "
+                             "(use --impl reference for the CPU arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

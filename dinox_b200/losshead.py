@@ -237,7 +237,8 @@ class _GramAnchor(torch.autograd.Function):
         xt, _ = ops.normalize_tokens(teacher_feats, skip=1)
         n = Bt * (T - 1) * (T - 1)
         need_grad = student_feats.requires_grad
-        loss, delta = ops.gram_diff(xs, xt, 1.0 / n, want_delta=need_grad)
+        with ops.TIMER.region("gram_diff"):
+            loss, delta = ops.gram_diff(xs, xt, 1.0 / n, want_delta=need_grad)
         if need_grad:
             ctx.save_for_backward(student_feats, xs, inv_s, delta)
             ctx.n = n
@@ -284,7 +285,8 @@ def ema_update(teacher_params: Sequence[torch.Tensor], student_params: Sequence[
     if plan is None or not plan.matches(sp, tp):
         plan = ops.EmaPlan(sp, tp)
         _EMA_PLANS[key] = plan
-    plan.apply(m)
+    with ops.TIMER.region("ema_multi"):
+        plan.apply(m)
     _WEIGHT_EPOCH[0] += 1
 
 
@@ -490,12 +492,14 @@ class _FusedHeadLoss(torch.autograd.Function):
         # ---- pass 1: row statistics with logits kept on chip
         b2s, b2t = s_head[2].bias.detach(), t_head[2].bias.detach()
         cs2 = ops.axpb(b2s, inv_ts * LOG2E)
-        _, lse2_s = ops.head_stats(hs, w2s, inv_ts, cs2, want_nat=False)
+        with ops.TIMER.region("head_stats_student"):
+            _, lse2_s = ops.head_stats(hs, w2s, inv_ts, cs2, want_nat=False)
         center = loss_mod.center.reshape(-1)
         rb2_t = torch.empty(Mt + Mm, dtype=torch.float32, device=dev)
         if teacher_mode == "center":
             ct2 = ops.axpby(b2t, inv_tt * LOG2E, center, -inv_tt * LOG2E)
-            ops.head_stats(ht[:Mt], w2t, inv_tt, ct2, want_nat=False, out_log2=rb2_t[:Mt])
+            with ops.TIMER.region("head_stats_teacher_cls"):
+                ops.head_stats(ht[:Mt], w2t, inv_tt, ct2, want_nat=False, out_log2=rb2_t[:Mt])
         else:  # Sinkhorn-Knopp on the (small) materialised CLS teacher logits
             t_cls = ops.gemm_bf16(ht[:Mt], w2t, bias_n=b2t)
             a_col, b_row = sinkhorn_knopp_biases(t_cls, teacher_temp, sk_iters, pg)
@@ -505,7 +509,8 @@ class _FusedHeadLoss(torch.autograd.Function):
         ct2_patch = None
         if Mm:
             ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E)
-            ops.head_stats(ht[Mt:], w2t, inv_tt, ct2_patch, want_nat=False, out_log2=rb2_t[Mt:])
+            with ops.TIMER.region("head_stats_teacher_patch"):
+                ops.head_stats(ht[Mt:], w2t, inv_tt, ct2_patch, want_nat=False, out_log2=rb2_t[Mt:])
         # ---- entries
         hs_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
         ht_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
@@ -521,8 +526,9 @@ class _FusedHeadLoss(torch.autograd.Function):
         # ---- pass 2
         losses = torch.zeros(2, dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad[:2]) or s_head[2].weight.requires_grad
-        gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
-                                 lse2_e, rb2_e, cw, losses, want_db2=need_grad)
+        with ops.TIMER.region("head_grad"):
+            gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
+                                     lse2_e, rb2_e, cw, losses, want_db2=need_grad)
         # ---- centre updates AFTER the loss (scripts/phase5_big_run.py:719): batch-mean logits are
         # W2t . mean(h_t) + b2t by linearity -> a D-vector all-reduce instead of a K-vector one
         if update_center and teacher_mode == "center":
@@ -552,13 +558,15 @@ class _FusedHeadLoss(torch.autograd.Function):
         K, D = w2s.shape
         rows = plan.Ms + plan.Mm
         # dW2 (K, D) += g * Gt . HsE   (A = Gt K-major over entries, B = HsE MN-major)
-        _accumulate_grad(s_head[2].weight, lambda out, acc: ops.gemm_bf16(
-            gt, hs_e, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up))
+        with ops.TIMER.region("gemm_dW2"):
+            _accumulate_grad(s_head[2].weight, lambda out, acc: ops.gemm_bf16(
+                gt, hs_e, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up))
         db2 = ops.cols_sum(db2p)
         _accumulate_grad(s_head[2].bias, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out,
                                                                    alpha_dev=up))
         # dH per entry = G . W2  (A = Gt MN-major, B = W2 MN-major), then sum the entries of each row
-        dh_e = ops.gemm_bf16(gt, w2s, a_mn_major=True, b_mn_major=True, m_fastest=True)
+        with ops.TIMER.region("gemm_dH"):
+            dh_e = ops.gemm_bf16(gt, w2s, a_mn_major=True, b_mn_major=True, m_fastest=True)
         dh = torch.empty(rows, D, dtype=torch.float32, device=gt.device)
         ops.gather_sum_rows(dh_e, plan.csr_ptr, plan.csr_ent, rows, dh)
         da, part = ops.gelu_bwd(dh, a_s, scale_dev=up)

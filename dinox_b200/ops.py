@@ -330,3 +330,49 @@ def fill_(t: torch.Tensor, v: float = 0.0) -> torch.Tensor:
     assert t.dtype == torch.float32 and t.is_contiguous()
     _ext.call("dinox_fill_f32", _p(t), t.numel(), float(v), _stream())
     return t
+
+
+# ------------------------------------------------------------------------------------------------
+# optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg)
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """`with ops.TIMER.region("head_grad"):` brackets a launch with two CUDA events on the current
+    stream when enabled; elapsed times are resolved after the caller synchronises."""
+
+    def __init__(self):
+        self.enabled = False
+        self._pending = []
+        self.totals = {}
+        self.counts = {}
+
+    class _Region:
+        def __init__(self, timer, name):
+            self.t, self.name = timer, name
+
+        def __enter__(self):
+            if self.t.enabled:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.t.enabled:
+                self.e1.record()
+                self.t._pending.append((self.name, self.e0, self.e1))
+            return False
+
+    def region(self, name):
+        return KernelTimer._Region(self, name)
+
+    def resolve(self):
+        for name, e0, e1 in self._pending:
+            self.totals[name] = self.totals.get(name, 0.0) + e0.elapsed_time(e1)
+            self.counts[name] = self.counts.get(name, 0) + 1
+        self._pending = []
+
+    def reset(self):
+        self._pending, self.totals, self.counts = [], {}, {}
+
+
+TIMER = KernelTimer()

@@ -1,0 +1,73 @@
+"""One loss-head micro-step: the step glue of the reference training loop
+(scripts/phase5_big_run.py:1738-1802) around the drop-in modules, on pre-extracted features.
+
+  loss = L_dino (+ w_ibot * L_ibot) + w_gram * L_gram ; loss / accum ; backward ;
+  every `accum`-th micro-step: [optimizer step is the host's] EMA of all parameters, grads reset.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import losshead, ops, synth
+
+
+class LossHeadStep:
+    def __init__(self, shapes: synth.LossHeadShapes, device, seed_cfg: int = 2, rank: int = 0,
+                 accum: int = 4, gram_weight: float = 1.0, ibot_weight: float = 1.0, ema: float = 0.996,
+                 center_momentum: float = 0.9, student_temp: float = 0.1, teacher_temp: float = 0.04,
+                 teacher_mode: str = "center", process_group=None, with_backbone_params: bool = True):
+        self.shapes, self.device, self.accum = shapes, device, accum
+        self.gram_weight, self.ibot_weight, self.ema = gram_weight, ibot_weight, ema
+        self.student_temp, self.teacher_temp = student_temp, teacher_temp
+        g = synth.seeded_generator(seed_cfg, 0)  # identical replicas on every rank
+        D, K = shapes.dim, shapes.out_dim
+        self.student_head = losshead.ProjectionHead(D, K)
+        self.teacher_head = losshead.ProjectionHead(D, K)
+        self.student_head.load_state_dict(synth.head_weights(D, K, g))
+        self.teacher_head.load_state_dict(synth.head_weights(D, K, g))
+        self.student_head.to(device)
+        self.teacher_head.to(device)
+        for p in self.teacher_head.parameters():
+            p.requires_grad_(False)
+        self.dino_loss = losshead.DINOLoss(K, center_momentum, n_global=shapes.n_global, n_local=shapes.n_local,
+                                           teacher_mode=teacher_mode, process_group=process_group).to(device)
+        self.center_patch = torch.zeros(1, K, device=device)
+        # every other student/teacher parameter (backbone, scale-embed): random stand-ins with the
+        # reference's shapes so that the EMA walks the real 161 / 305 tensor list
+        self.student_params: List[torch.Tensor] = []
+        self.teacher_params: List[torch.Tensor] = []
+        if with_backbone_params:
+            depth = synth.BACKBONES.get(D, dict(depth=12))["depth"]
+            for shp in synth.student_param_shapes(D, depth, K)[:-4]:
+                self.student_params.append(torch.randn(shp, device=device) * 0.02)
+                self.teacher_params.append(torch.randn(shp, device=device) * 0.02)
+        self.student_params += list(self.student_head.parameters())
+        self.teacher_params += list(self.teacher_head.parameters())
+        self.n_params = sum(p.numel() for p in self.student_params)
+        self.micro = 0
+
+    def micro_step(self, f: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """f: student_cls, teacher_cls (+ student_tok, teacher_tok) (+ student_patch, teacher_patch,
+        masks_weight); student tensors may require grad.  Returns the component losses."""
+        out = losshead.fused_head_dino_loss(
+            f["student_cls"], f["teacher_cls"], self.student_head, self.teacher_head, self.dino_loss,
+            self.student_temp, self.teacher_temp, student_patch=f.get("student_patch"),
+            teacher_patch=f.get("teacher_patch"), masks_weight=f.get("masks_weight"),
+            center_patch=self.center_patch if "student_patch" in f else None, ibot_weight=self.ibot_weight)
+        loss = out["loss"]
+        if "student_tok" in f:
+            out["loss_gram"] = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
+            loss = loss + self.gram_weight * out["loss_gram"]
+        out["loss_total"] = loss.detach()
+        (loss / self.accum).backward()
+        self.micro += 1
+        if self.micro % self.accum == 0:
+            # the optimizer step belongs to the host loop (scripts/phase5_big_run.py:1794-1796); then EMA
+            losshead.ema_update(self.teacher_params, self.student_params, self.ema, plan_key=id(self))
+            for p in self.student_head.parameters():
+                p.grad = None
+        return out

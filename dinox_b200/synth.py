@@ -181,3 +181,21 @@ CONFIGS = {
     "C4": dict(batch=32, dim=1024, out_dim=65536, n_patches=196),
     "C5lo": dict(batch=64, dim=384, out_dim=8192, n_patches=196),
 }
+
+
+def student_param_shapes(dim: int, depth: int, out_dim: int, patch: int = 16, img: int = 224,
+                         mlp_ratio: int = 4, scale_aware: bool = True) -> List[Tuple[int, ...]]:
+    """Shapes of `DinoStudentTeacher(PatchViT(...), out_dim).parameters()` in iteration order
+    (zoo/arch.py:150-261) - what the EMA loop walks."""
+    n_patches = (img // patch) ** 2
+    shapes: List[Tuple[int, ...]] = [(1, 1, dim), (1, 1 + n_patches, dim), (1, 4, dim), (dim, 3, patch, patch), (dim,)]
+    if scale_aware:
+        shapes += [(dim // 4, 3), (dim // 4,), (dim, dim // 4), (dim,), (dim,), (dim,)]
+    for _ in range(depth):
+        shapes += [(dim,), (dim,), (3 * dim, dim), (3 * dim,), (dim, dim), (dim,), (dim,), (dim,),
+                   (mlp_ratio * dim, dim), (mlp_ratio * dim,), (dim, mlp_ratio * dim), (dim,)]
+    shapes += [(dim,), (dim,), (dim, dim), (dim,), (out_dim, dim), (out_dim,)]
+    return shapes
+
+
+BACKBONES = {384: dict(depth=12), 1024: dict(depth=24)}  # ViT-S/16, ViT-L/16
