@@ -28,11 +28,13 @@ struct EpiStore {
     const float* bias_n;     // optional per-column bias
     int64_t batch_stride;    // output elements between problems of a batched launch
   };
+  struct State {};
+  static __device__ __forceinline__ void finish(const Params&, const CoreParams&, int, int, State&) {}
   template <int BN>
   struct Impl {
     static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int, uint32_t tmem_acc,
-                                                int, int, int lane, uint8_t*) {
+                                                int, int, int lane, uint8_t*, State&) {
       const int q = epi_quarter();
       const int row = tc.m_tile * BM + q * 32 + lane;
       const float alpha = e.alpha * (e.alpha_dev ? *e.alpha_dev : 1.f);
@@ -103,11 +105,13 @@ struct EpiStats {
     const float* col2;   // (N) log2-unit column offsets, may be NULL
     float2* partial;     // (M, 2*num_n_tiles)
   };
+  struct State {};
+  static __device__ __forceinline__ void finish(const Params&, const CoreParams&, int, int, State&) {}
   template <int BN>
   struct Impl {
     static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int, uint32_t tmem_acc,
-                                                int, int epi_warp, int lane, uint8_t*) {
+                                                int, int epi_warp, int lane, uint8_t*, State&) {
       const int q = epi_quarter();
       const int half = epi_warp >> 2;
       const int row = tc.m_tile * BM + q * 32 + lane;
@@ -182,8 +186,18 @@ struct EpiGradT {
     __nv_bfloat16* gt;      // (K, ldg)
     int64_t ldg;
     float* db2_partial;     // (2*num_n_tiles, M) or NULL
-    float* loss_partial;    // (num_tiles*8)
+    float* loss_partial;    // (gridDim.x * 8 * 2): per CTA, per epilogue warp, {entries < alt_from, >= alt_from}
   };
+  struct State {
+    float loss_a = 0.f, loss_b = 0.f;
+  };
+  static __device__ __forceinline__ void finish(const Params& e, const CoreParams&, int epi_warp, int lane, State& st) {
+    const float a = warp_sum(st.loss_a), b = warp_sum(st.loss_b);
+    if (lane == 0) {
+      e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 0] = a * DINOX_LN2;
+      e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 1] = b * DINOX_LN2;
+    }
+  }
   template <int BN>
   struct Impl {
     static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int acc_stage,
@@ -200,7 +214,7 @@ struct EpiGradT {
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int t, uint32_t tmem_acc,
-                                                int acc_stage, int epi_warp, int lane, uint8_t* smem) {
+                                                int acc_stage, int epi_warp, int lane, uint8_t* smem, State& st) {
       static_assert(BN == 128, "EpiGradT is written for 128-entry tiles");
       const float* buf = reinterpret_cast<const float*>(smem) + acc_stage * 3 * 128;
       const int q = epi_quarter();
@@ -250,8 +264,7 @@ struct EpiGradT {
       }
       if (!kok) { loss = 0.f; db2 = 0.f; }
       if (e.db2_partial && kok) e.db2_partial[(int64_t)(tc.n_tile * 2 + half) * p.M + k] = db2;
-      loss = warp_sum(loss);
-      if (lane == 0) e.loss_partial[(int64_t)t * 8 + epi_warp] = loss * DINOX_LN2;
+      if (e.ct2_alt && tc.n_tile * BN >= e.alt_from) st.loss_b += loss; else st.loss_a += loss;
     }
   };
 };
@@ -269,13 +282,20 @@ struct EpiGramDiff {
   struct Params {
     __nv_bfloat16* delta;   // (B, T', ldd) or NULL (forward only)
     int64_t ldd, batch_stride;
-    float* loss_partial;    // (num_tiles*8)
+    float* loss_partial;    // (gridDim.x * 8)
   };
+  struct State {
+    float loss = 0.f;
+  };
+  static __device__ __forceinline__ void finish(const Params& e, const CoreParams&, int epi_warp, int lane, State& st) {
+    const float a = warp_sum(st.loss);
+    if (lane == 0) e.loss_partial[(int64_t)blockIdx.x * 8 + epi_warp] = a;
+  }
   template <int BN>
   struct Impl {
     static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int t, uint32_t tmem_acc,
-                                                int, int epi_warp, int lane, uint8_t*) {
+                                                int, int epi_warp, int lane, uint8_t*, State& st) {
       static_assert(BN == 128, "EpiGramDiff is written for 128-wide tiles");
       const int q = epi_quarter();
       const int half = epi_warp >> 2;
@@ -314,22 +334,17 @@ struct EpiGramDiff {
           }
         }
       }
-      loss = warp_sum(loss);
-      if (lane == 0) e.loss_partial[(int64_t)t * 8 + epi_warp] = loss;
+      st.loss += loss;
     }
   };
 };
 
-// per-tile loss partials of pass 2 -> out[0] (entry tiles < split) and out[1] (entry tiles >= split);
-// tiles are numbered m_tile*num_n_tiles + n_tile (entry tiles fastest), 8 partials per tile
-__global__ void __launch_bounds__(1024) split_sum_kernel(const float* __restrict__ x, int64_t n_tiles, int num_n_tiles,
-                                                          int split, float* __restrict__ out, int accumulate) {
+// per-CTA loss partials of pass 2, interleaved {a, b}: out[0] (+)= sum a, out[1] (+)= sum b (fixed order)
+__global__ void __launch_bounds__(1024) pair_sum_kernel(const float* __restrict__ x, int64_t n_pairs,
+                                                         float* __restrict__ out, int accumulate) {
   __shared__ float red[64];
   float a = 0.f, b = 0.f;
-  for (int64_t i = threadIdx.x; i < n_tiles * 8; i += 1024) {
-    const int nt = (int)((i >> 3) % num_n_tiles);
-    if (nt < split) a += x[i]; else b += x[i];
-  }
+  for (int64_t i = threadIdx.x; i < n_pairs; i += 1024) { a += x[2 * i]; b += x[2 * i + 1]; }
   a = block_sum<1024>(a, red);
   b = block_sum<1024>(b, red);
   if (threadIdx.x == 0) {
@@ -355,11 +370,15 @@ template <int BN, class Epi>
 struct EpiAdapter {
   static constexpr int kEpiWarps = Epi::kEpiWarps;
   using Params = typename Epi::Params;
+  using State = typename Epi::State;
   static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int a, int w, int l, uint8_t* s) {
     Epi::template Impl<BN>::prologue(e, p, tc, a, w, l, s);
   }
-  static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int t, uint32_t tm, int a, int w, int l, uint8_t* s) {
-    Epi::template Impl<BN>::tile(e, p, tc, t, tm, a, w, l, s);
+  static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int t, uint32_t tm, int a, int w, int l, uint8_t* s, State& st) {
+    Epi::template Impl<BN>::tile(e, p, tc, t, tm, a, w, l, s, st);
+  }
+  static __device__ __forceinline__ void finish(const Params& e, const CoreParams& p, int w, int l, State& st) {
+    Epi::finish(e, p, w, l, st);
   }
 };
 
@@ -370,6 +389,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             const CoreParams p, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   gemm_body<BN, NSUB, EpiAdapter<BN, Epi>>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, smem_raw);
+}
+
+static inline int launch_grid(int64_t tiles) {
+  int grid = num_sms();
+  return grid > tiles ? (int)tiles : grid;
 }
 
 struct Operand {
@@ -423,8 +447,7 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   }
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles * batches;
   DINOX_REQUIRE(tiles < (1ll << 31), DINOX_E_BADARG, "%s: too many tiles", name);
-  int grid = num_sms();
-  if (grid > tiles) grid = (int)tiles;
+  int grid = launch_grid(tiles);
   kern<<<grid, (2 + Epi::kEpiWarps) * 32, smem, stream>>>(tA0, tB0, tA1, tB1, p, ep);
   return check_launch(name, stream);
 }
@@ -479,8 +502,7 @@ int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int
 
 size_t dinox_head_grad_workspace_bytes(int64_t K, int64_t E) {
   if (K <= 0 || E <= 0) return 0;
-  const int64_t mt = (K + 127) / 128, nt = (E + 127) / 128;
-  return (size_t)(mt * nt * 8) * sizeof(float) + 256;
+  return (size_t)(1024 * 8 * 2) * sizeof(float) + 256;  // per-CTA partials, grid <= 1024
 }
 
 int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const void* HtE, int64_t K, int64_t D,
@@ -505,11 +527,9 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
   // entry tiles fastest: the 2 x (K-tile of W2) operands stay put while HsE/HtE (L2-resident) stream
   rc = launch<128, 2, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, stream, "head_grad");
   if (rc) return rc;
-  const int num_n_tiles = (int)((E + 127) / 128);
-  const int split = ct2_alt ? (int)(alt_from / 128) : num_n_tiles;
-  split_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), ((K + 127) / 128) * num_n_tiles,
-                                           num_n_tiles, split, loss_out, loss_accumulate);
-  return check_launch("split_sum_kernel", stream);
+  const int grid = launch_grid(((K + 127) / 128) * ((E + 127) / 128));
+  pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * 8, loss_out, loss_accumulate);
+  return check_launch("pair_sum_kernel", stream);
 }
 
 int dinox_gemm_bf16_batched(const void* A, const void* B, void* C, int64_t batches, int64_t M, int64_t N, int64_t K,
@@ -532,8 +552,7 @@ int dinox_gemm_bf16_batched(const void* A, const void* B, void* C, int64_t batch
 
 size_t dinox_gram_diff_workspace_bytes(int64_t batches, int64_t tokens) {
   if (batches <= 0 || tokens <= 0) return 0;
-  const int64_t mt = (tokens + 127) / 128;
-  return (size_t)(batches * mt * mt * 8) * sizeof(float) + 256;
+  return (size_t)(1024 * 8) * sizeof(float) + 256;  // per-CTA partials, grid <= 1024
 }
 
 int dinox_gram_diff(const void* xn_s, const void* xn_t, int64_t batches, int64_t tokens, int64_t D, void* delta,
@@ -549,7 +568,8 @@ int dinox_gram_diff(const void* xn_s, const void* xn_t, int64_t batches, int64_t
   rc = launch<128, 2, EpiGramDiff>(a0, a0, &a1, &a1, tokens, tokens, D, 1, ep, stream, "gram_diff", batches);
   if (rc) return rc;
   const int64_t mt = (tokens + 127) / 128;
-  sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), batches * mt * mt * 8, loss_scale, loss_out, 0);
+  sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)launch_grid(batches * mt * mt) * 8,
+                                     loss_scale, loss_out, 0);
   return check_launch("sum_kernel", stream);
 }
 

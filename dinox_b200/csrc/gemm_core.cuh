@@ -213,18 +213,20 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     const int epi_warp = warp - kFirstEpiWarp;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
+    typename Epi::State state;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const TileCoord tc = tile_coord(p, t);
       Epi::prologue(ep, p, tc, acc_stage, epi_warp, lane, epi_smem);
       sm100::mbar_wait(&ctl->tmem_full[acc_stage], acc_phase, 4);
       sm100::tc_fence_after();
-      Epi::tile(ep, p, tc, t, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem);
+      Epi::tile(ep, p, tc, t, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
       sm100::tc_fence_before();
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(&ctl->tmem_empty[acc_stage]);
       acc_stage ^= 1;
       if (acc_stage == 0) acc_phase ^= 1;
     }
+    Epi::finish(ep, p, epi_warp, lane, state);
   }
 
   sm100::tc_fence_before();

@@ -155,31 +155,48 @@ cols_lse_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, fl
     if (k + j < K) out[k + j] = DINOX_LN2 * (m[j] + log2f(s[j]));
 }
 
+// column sums: block = 32 column-threads (4 columns each) x kRowGroups row groups; the row groups
+// stride over the rows (4 loads in flight each) and are combined through shared memory in a fixed
+// order.  Tall-skinny inputs (7424 x 384 head activations) still fill the SM this way.
+constexpr int kColSumGroups = 16;
+
 template <typename T, bool kVec>
-__global__ void __launch_bounds__(kColThreads)
+__global__ void __launch_bounds__(32 * kColSumGroups)
 cols_sum_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, float* __restrict__ out) {
-  const int64_t k = ((int64_t)blockIdx.x * kColThreads + threadIdx.x) * 4;
-  if (k >= K) return;
+  __shared__ float red[kColSumGroups][32][4];
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int64_t k = ((int64_t)blockIdx.x * 32 + cx) * 4;
   float a[4] = {0.f, 0.f, 0.f, 0.f};
-  int64_t i = 0;
-  for (; i + 4 <= rows; i += 4) {  // 4 independent loads in flight
-    float v0[4], v1[4], v2[4], v3[4];
-    load4<T, kVec>(x + (i + 0) * ld, k, K, v0, 0.f);
-    load4<T, kVec>(x + (i + 1) * ld, k, K, v1, 0.f);
-    load4<T, kVec>(x + (i + 2) * ld, k, K, v2, 0.f);
-    load4<T, kVec>(x + (i + 3) * ld, k, K, v3, 0.f);
+  if (k < K) {
+    int64_t i = gy;
+    for (; i + 3 * kColSumGroups < rows; i += 4 * kColSumGroups) {
+      float v0[4], v1[4], v2[4], v3[4];
+      load4<T, kVec>(x + (i + 0 * kColSumGroups) * ld, k, K, v0, 0.f);
+      load4<T, kVec>(x + (i + 1 * kColSumGroups) * ld, k, K, v1, 0.f);
+      load4<T, kVec>(x + (i + 2 * kColSumGroups) * ld, k, K, v2, 0.f);
+      load4<T, kVec>(x + (i + 3 * kColSumGroups) * ld, k, K, v3, 0.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+      for (int j = 0; j < 4; ++j) a[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+    for (; i < rows; i += kColSumGroups) {
+      float v[4];
+      load4<T, kVec>(x + i * ld, k, K, v, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] += v[j];
+    }
   }
-  for (; i < rows; ++i) {
-    float v[4];
-    load4<T, kVec>(x + i * ld, k, K, v, 0.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] += v[j];
+  for (int j = 0; j < 4; ++j) red[gy][cx][j] = a[j];
+  __syncthreads();
+  if (gy == 0 && k < K) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < kColSumGroups; ++g) t += red[g][cx][j];
+      if (k + j < K) out[k + j] = t;
+    }
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (k + j < K) out[k + j] = a[j];
 }
 
 __global__ void lse_combine_kernel(const float* __restrict__ g, int world, int64_t K, float add,
@@ -463,10 +480,10 @@ int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld
   int rc = require_sm100();
   if (rc) return rc;
   const bool vec = vec_ok(x, dtype, K, ld);
-  const unsigned grid = (unsigned)((K + kColThreads * 4 - 1) / (kColThreads * 4));
+  const unsigned grid = (unsigned)((K + 127) / 128);
   DISPATCH_T(dtype, T, {
-    if (vec) cols_sum_kernel<T, true><<<grid, kColThreads, 0, stream>>>((const T*)x, rows, K, ld, out);
-    else cols_sum_kernel<T, false><<<grid, kColThreads, 0, stream>>>((const T*)x, rows, K, ld, out);
+    if (vec) cols_sum_kernel<T, true><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out);
+    else cols_sum_kernel<T, false><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out);
   });
   return check_launch("cols_sum_kernel", stream);
 }

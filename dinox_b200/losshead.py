@@ -560,7 +560,7 @@ class _FusedHeadLoss(torch.autograd.Function):
         # dW2 (K, D) += g * Gt . HsE   (A = Gt K-major over entries, B = HsE MN-major)
         with ops.TIMER.region("gemm_dW2"):
             _accumulate_grad(s_head[2].weight, lambda out, acc: ops.gemm_bf16(
-                gt, hs_e, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up))
+                gt, hs_e, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
         db2 = ops.cols_sum(db2p)
         _accumulate_grad(s_head[2].bias, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out,
                                                                    alpha_dev=up))
