@@ -51,16 +51,16 @@ def allreduce_sum_(t: torch.Tensor, pg) -> torch.Tensor:
     return t
 
 
-def allreduce_lse(local_lse: torch.Tensor, pg, add: float = 0.0) -> torch.Tensor:
+def allreduce_lse(local_lse: torch.Tensor, pg, add: float = 0.0, _k=ops) -> torch.Tensor:
     """log-sum-exp all-reduce of per-rank LSE vectors: all_gather + one combine kernel.  Exact in
     the log domain (no common shift needed), one collective per Sinkhorn half-iteration."""
     w = _world(pg)
     if w == 1:
-        return ops.lse_combine(local_lse.reshape(1, -1), add) if add != 0.0 else local_lse
+        return _k.lse_combine(local_lse.reshape(1, -1), add) if add != 0.0 else local_lse
     import torch.distributed as dist
-    gathered = torch.empty(w, local_lse.numel(), dtype=torch.float32, device=local_lse.device)
-    dist.all_gather_into_tensor(gathered, local_lse.contiguous(), group=_group(pg))
-    return ops.lse_combine(gathered, add)
+    gathered = [torch.empty_like(local_lse) for _ in range(w)]
+    dist.all_gather(gathered, local_lse.contiguous(), group=_group(pg))
+    return _k.lse_combine(torch.stack(gathered, 0), add)
 
 
 # =================================================================================================
@@ -68,7 +68,7 @@ def allreduce_lse(local_lse: torch.Tensor, pg, add: float = 0.0) -> torch.Tensor
 # =================================================================================================
 @torch.no_grad()
 def sinkhorn_knopp_biases(teacher_out: torch.Tensor, teacher_temp: float, n_iterations: int = 3,
-                          process_group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                          process_group=None, _k=ops) -> Tuple[torch.Tensor, torch.Tensor]:
     """Log-domain Sinkhorn-Knopp (DINOv2 formulation, see oracle.sinkhorn_knopp).  Returns
     (colbias a[K], rowbias b[rows]) with q[i,k] = exp(t[i,k]/tau - a[k] - b[i]); rows of q sum to 1.
     Per-prototype sums are all-reduced over `process_group`; per-sample sums are local."""
@@ -79,12 +79,12 @@ def sinkhorn_knopp_biases(teacher_out: torch.Tensor, teacher_temp: float, n_iter
     b = None
     a = None
     for _ in range(n_iterations):
-        a_local = ops.cols_lse(teacher_out, inv_tau, b)            # LSE_i(x - b_i) over local samples
-        a = allreduce_lse(a_local, process_group, add=math.log(K))  # global, then Q /= K
-        b = ops.rows_lse(teacher_out, inv_tau, a)                   # LSE_k(x - a_k)
-        b = ops.axpb(b, 1.0, log_bg)                                # Q /= B
+        a_local = _k.cols_lse(teacher_out, inv_tau, b)             # LSE_i(x - b_i) over local samples
+        a = allreduce_lse(a_local, process_group, add=math.log(K), _k=_k)  # global, then Q /= K
+        b = _k.rows_lse(teacher_out, inv_tau, a)                    # LSE_k(x - a_k)
+        b = _k.axpb(b, 1.0, log_bg)                                 # Q /= B
     # final Q *= B
-    b = ops.axpb(b, 1.0, -log_bg)
+    b = _k.axpb(b, 1.0, -log_bg)
     return a, b
 
 
@@ -146,13 +146,13 @@ class DINOLoss(nn.Module):
         self.process_group = process_group
 
     @torch.no_grad()
-    def update_center(self, teacher_output: torch.Tensor) -> None:
+    def update_center(self, teacher_output: torch.Tensor, _k=ops) -> None:
         """center <- center*m + mean_rows(teacher_output)*(1-m)  (:686-690); in DP the column sums are
         all-reduced and divided by the global row count."""
-        t = _as_rows(teacher_output)
-        colsum = ops.cols_sum(t)
+        t = _as_rows(teacher_output) if _k is ops else teacher_output
+        colsum = _k.cols_sum(t)
         allreduce_sum_(colsum, self.process_group)
-        ops.center_ema_(self.center, colsum, t.shape[0] * _world(self.process_group), self.center_momentum)
+        _k.center_ema_(self.center, colsum, t.shape[0] * _world(self.process_group), self.center_momentum)
 
     def teacher_biases(self, teacher_out: torch.Tensor, teacher_temp: float):
         if self.teacher_mode == "center":

@@ -1,0 +1,105 @@
+"""Host-side logic that needs no GPU: entry pairing tables of the fused path, workload bookkeeping
+(BASELINE.md section 4 numbers), module state-dict contract, loud failure without CUDA."""
+import math
+
+import pytest
+import torch
+
+from dinox_b200 import losshead, synth
+from oracle import losshead_oracle as O
+
+
+def test_entry_plan_matches_multicrop_definition():
+    B, Vg, V, Mm = 3, 2, 5, 7
+    plan = losshead._EntryPlan(B, Vg, V, Mm, "cpu")
+    es, et, cw = plan.ent_s.tolist(), plan.ent_t.tolist(), plan.cw_base.tolist()
+    pairs = {(iq * B + b, v * B + b) for iq in range(Vg) for v in range(V) if v != iq for b in range(B)}
+    got = {(t, s) for s, t, w in zip(es[:plan.n_cls], et[:plan.n_cls], cw) if s >= 0}
+    assert got == pairs and plan.n_cls == (Vg * V - Vg) * B
+    assert plan.e_cls_pad % 128 == 0 and plan.e_pad % 128 == 0
+    assert all(abs(w - 1.0 / ((Vg * V - Vg) * B)) < 1e-7 for w in cw[:plan.n_cls])
+    assert all(w == 0.0 for w in cw[plan.n_cls:])
+    # iBOT entries: 1:1 after the padded CLS block
+    for m in range(Mm):
+        assert es[plan.e_cls_pad + m] == B * V + m and et[plan.e_cls_pad + m] == B * Vg + m
+    # CSR covers every non-padding entry exactly once, grouped by student row
+    ptr, ent = plan.csr_ptr.tolist(), plan.csr_ent.tolist()
+    assert len(ptr) == B * V + Mm + 1 and sorted(ent) == [e for e, s in enumerate(es) if s >= 0]
+    for r in range(B * V + Mm):
+        assert all(es[e] == r for e in ent[ptr[r]:ptr[r + 1]])
+
+
+def test_entry_weights_reproduce_oracle_loss():
+    """sum over entries of cw * CE(teacher row, student row) == multicrop_dino_loss (pure torch)."""
+    g = torch.Generator().manual_seed(0)
+    B, Vg, V, K = 4, 2, 6, 64
+    s = torch.randn(B * V, K, generator=g)
+    t = torch.randn(B * Vg, K, generator=g)
+    c = torch.zeros(1, K)
+    ref = O.multicrop_dino_loss(s, t, c, 0.1, 0.04, Vg, V - Vg)
+    plan = losshead._EntryPlan(B, Vg, V, 0, "cpu")
+    q = torch.softmax(t / 0.04, -1)
+    logp = torch.log_softmax(s / 0.1, -1)
+    tot = 0.0
+    for e in range(plan.n_cls):
+        tot += plan.cw_base[e] * -(q[plan.ent_t[e]] * logp[plan.ent_s[e]]).sum()
+    assert abs(float(tot) - ref.item()) < 1e-5 * abs(ref.item())
+
+
+def test_workload_bookkeeping_matches_baseline_md():
+    c2 = synth.LossHeadShapes(**synth.CONFIGS["C2"])
+    assert (c2.student_rows, c2.teacher_rows, c2.masked_rows, c2.tokens) == (640, 128, 7424, 201)
+    assert abs(c2.flops() / 1e9 - 1618.9) < 0.2
+    assert abs(c2.hbm_bytes(47_084_800, 4) / 1e6 - 639) < 2
+    c1 = synth.LossHeadShapes(**synth.CONFIGS["C1"])
+    assert (c1.student_rows, c1.teacher_rows, c1.masked_rows) == (80, 16, 928)
+    assert abs(c1.flops() / 1e9 - 202.4) < 0.1
+    c4 = synth.LossHeadShapes(**synth.CONFIGS["C4"])
+    assert abs(c4.flops() / 1e9 - 2179.3) < 0.5
+
+
+def test_student_param_shapes_match_survey_appendix_a():
+    s = synth.student_param_shapes(384, 12, 65536)
+    assert len(s) == 161 and sum(math.prod(x) for x in s) == 47_084_800
+    small = sum(1 for x in s if math.prod(x) < 1024)
+    assert small == 82 and s[-2] == (65536, 384) and s[1] == (1, 197, 384)
+    l = synth.student_param_shapes(1024, 24, 65536)
+    assert len(l) == 305 and abs(sum(math.prod(x) for x in l) / 1e6 - 371.8) < 0.1
+
+
+def test_module_contract_without_gpu():
+    dl = losshead.DINOLoss(4096, 0.9)
+    assert list(dl.state_dict()) == ["center"] and dl.center.shape == (1, 4096) and dl.center.dtype == torch.float32
+    dl.load_state_dict({"center": torch.ones(1, 4096)})
+    head = losshead.ProjectionHead(32, 96)
+    assert list(head.state_dict()) == ["0.weight", "0.bias", "2.weight", "2.bias"]
+    assert head[0].weight.shape == (32, 32) and head[2].weight.shape == (96, 32)
+
+    class BB(torch.nn.Module):
+        dim = 32
+    m = losshead.DinoStudentTeacher(BB(), out_dim=96)
+    assert [k for k in m.state_dict()] == ["head.0.weight", "head.0.bias", "head.2.weight", "head.2.bias"]
+
+
+def test_cpu_tensors_fail_loudly():
+    with pytest.raises(Exception, match="CUDA|fallback"):
+        losshead.DINOLoss(16)(torch.zeros(4, 16), torch.zeros(4, 16), 0.1, 0.04)
+    with pytest.raises(Exception, match="CUDA|fallback"):
+        losshead.compute_gram_anchoring_loss(torch.zeros(1, 5, 8), torch.zeros(1, 5, 8))
+    with pytest.raises(Exception, match="CUDA|fallback"):
+        losshead.ProjectionHead(8, 16)(torch.zeros(2, 8))
+    with pytest.raises(Exception):
+        losshead.ema_update([torch.zeros(4)], [torch.zeros(4)], 0.9)
+
+
+def test_synthetic_ct_crops_are_seeded_and_in_range():
+    g1, g2 = synth.seeded_generator(1, 0), synth.seeded_generator(1, 0)
+    v1, s1 = synth.multicrop_batch(2, g1, 2, 2, 32, 16)
+    v2, s2 = synth.multicrop_batch(2, g2, 2, 2, 32, 16)
+    assert all(torch.equal(a, b) for a, b in zip(v1, v2)) and torch.equal(s1, s2)
+    assert v1[0].shape == (2, 3, 32, 32) and v1[2].shape == (2, 3, 16, 16) and s1.shape == (2, 3)
+    for v in v1:
+        assert v.min() >= -2.2 and v.max() <= 2.7
+    assert (s1[:, 0] >= 0.46).all() and (s1[:, 2] <= 5.0).all()
+    g3 = synth.seeded_generator(1, 1)
+    assert not torch.equal(synth.multicrop_batch(2, g3, 2, 2, 32, 16)[0][0], v1[0])
