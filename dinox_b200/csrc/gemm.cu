@@ -8,6 +8,7 @@
 //                        scripts/phase5_big_run.py:703-717 + its autograd
 #include "gemm_core.cuh"
 #include "tmap.cuh"
+#include <stdlib.h>
 
 namespace dinox {
 namespace gemm {
@@ -96,10 +97,21 @@ struct EpiStore {
 // Epilogue 2: row statistics of u2 = acc*scale2 + col2[n]  (log2 units).
 // Each epilogue warp owns 32 rows x (BN/2) columns; it writes one (max, sumexp2) pair per row
 // into partial[row][n_tile*2 + half]; dinox_head_stats then merges the pairs per row.
+// The column offsets of the tile are staged in shared memory by the prologue, with -inf for
+// columns >= N: out-of-range columns then contribute exp2(-inf) = 0 without any per-element
+// bounds check (the accumulator itself is 0 there because TMA zero-fills the W2 rows).
+// Issue budget per element: FFMA, 1/2 FMNMX3, FADD, MUFU.EX2, FADD (+ 1/4 LDS.128).
 // =============================================================================================
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sm100::smem_u32(p)));
+  return v;
+}
+
 struct EpiStats {
   static constexpr int kEpiWarps = 8;
-  static constexpr int kEpiSmemBytes = 0;
+  static constexpr int kEpiSmemBytes = 2 * 256 * 4;
   struct Params {
     float scale2;
     const float* col2;   // (N) log2-unit column offsets, may be NULL
@@ -109,34 +121,55 @@ struct EpiStats {
   static __device__ __forceinline__ void finish(const Params&, const CoreParams&, int, int, State&) {}
   template <int BN>
   struct Impl {
-    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
+    static_assert(BN == 256, "EpiStats is written for 256-wide tiles");
+    static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int acc_stage,
+                                                    int epi_warp, int lane, uint8_t* smem) {
+      float* buf = reinterpret_cast<float*>(smem) + acc_stage * 256;
+      const int i = epi_warp * 32 + lane;  // 0..255
+      const int col = tc.n_tile * BN + i;
+      buf[i] = (col < p.N) ? (e.col2 ? __ldg(e.col2 + col) : 0.f) : -INFINITY;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int, uint32_t tmem_acc,
-                                                int, int epi_warp, int lane, uint8_t*, State&) {
+                                                int acc_stage, int epi_warp, int lane, uint8_t* smem, State&) {
+      const float* buf = reinterpret_cast<const float*>(smem) + acc_stage * 256;
       const int q = epi_quarter();
       const int half = epi_warp >> 2;
       const int row = tc.m_tile * BM + q * 32 + lane;
       const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
       float m = -INFINITY, s = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        float v[32];
-        sm100::tmem_ld32(taddr + c * 32, v);
-        const int col0 = tc.n_tile * BN + half * (BN / 2) + c * 32;
-        if (col0 >= p.N) break;
-        float cm = -INFINITY;
+      for (int c = 0; c < 2; ++c) {
+        float v[2][32];
+        sm100::tmem_ld32x2(taddr + c * 64, taddr + c * 64 + 32, v[0], v[1]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = (col0 + j < p.N);
-          const float cb = (e.col2 && ok) ? __ldg(e.col2 + col0 + j) : 0.f;
-          v[j] = ok ? fmaf(v[j], e.scale2, cb) : -INFINITY;
-          cm = fmaxf(cm, v[j]);
+        for (int h = 0; h < 2; ++h) {
+          const float* cb = buf + half * (BN / 2) + c * 64 + h * 32;
+          float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = lds128(cb + j);
+            v[h][j] = fmaf(v[h][j], e.scale2, b4.x);
+            v[h][j + 1] = fmaf(v[h][j + 1], e.scale2, b4.y);
+            v[h][j + 2] = fmaf(v[h][j + 2], e.scale2, b4.z);
+            v[h][j + 3] = fmaf(v[h][j + 3], e.scale2, b4.w);
+            cm0 = fmaxf(cm0, fmaxf(v[h][j], v[h][j + 1]));
+            cm1 = fmaxf(cm1, fmaxf(v[h][j + 2], v[h][j + 3]));
+          }
+          const float mn = fmaxf(m, fmaxf(cm0, cm1));
+          // a chunk that is entirely out of range keeps (m, s) untouched (mn may still be -inf)
+          const float msafe = (mn == -INFINITY) ? 0.f : mn;
+          float a0 = s * fast_ex2(m - msafe), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            a0 += fast_ex2(v[h][j] - msafe);
+            a1 += fast_ex2(v[h][j + 1] - msafe);
+            a2 += fast_ex2(v[h][j + 2] - msafe);
+            a3 += fast_ex2(v[h][j + 3] - msafe);
+          }
+          s = (a0 + a1) + (a2 + a3);
+          m = mn;
         }
-        const float mn = fmaxf(m, cm);
-        float acc = s * fast_ex2(m - mn);   // m = -inf -> 0
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc += fast_ex2(v[j] - mn);
-        s = acc;
-        m = mn;
       }
       if (row < p.M) e.partial[(int64_t)row * (2 * p.num_n_tiles) + tc.n_tile * 2 + half] = make_float2(m, s);
     }
@@ -165,11 +198,14 @@ __global__ void stats_merge_kernel(const float2* __restrict__ partial, int64_t r
 // =============================================================================================
 // Epilogue 3 (pass 2, "transposed"): TMEM lanes = prototypes k, columns = entries e.
 // Sub-GEMM 0 = student logits  S[k,e] = W2s[k,:] . Hs[e,:],  sub-GEMM 1 = teacher T[k,e].
-//   p = 2^(S*as2 + cs2[k] - lse2[e])       student softmax prob
-//   q = 2^(T*at2 + ct2[k] - rb2[e])        teacher prob (centre or Sinkhorn biases)
-//   G[k,e]  = cw[e] * inv_tau_s * (p - q)                 -> bf16, Gt (K, ldg)
-//   loss   += cw[e] * q * ln2 * (lse2[e] - s2)            (-q ln p)
+//   u = S*as2 - lse2[e] + cs2[k]            log2 of the student softmax prob,  p = 2^u
+//   w = T*at2 - rb2[e]  + ct2[k]            log2 of the teacher prob,          q = 2^w
+//   G[k,e]  = cw[e]/tau_s * (p - q)                       -> bf16, Gt (K, ldg)
+//   loss   -= cw[e] * q * ln2 * u                         (-q ln p)
 //   db2[k] += G[k,e]                                      (fp32, before rounding)
+// Per-entry constants (-lse2, -rb2, cw/tau_s; zero weight for padding / out-of-range entries) are
+// staged in shared memory once per tile.  Issue budget per element: 2 FFMA + 2 FADD + 2 MUFU
+// (logits -> probs), FMUL + 2 FFMA + FADD (gradient, loss, bias grad), 1/2 F2FP, 3/4 LDS.128.
 // =============================================================================================
 struct EpiGradT {
   static constexpr int kEpiWarps = 8;
@@ -193,9 +229,10 @@ struct EpiGradT {
   };
   static __device__ __forceinline__ void finish(const Params& e, const CoreParams&, int epi_warp, int lane, State& st) {
     const float a = warp_sum(st.loss_a), b = warp_sum(st.loss_b);
+    const float sc = -DINOX_LN2 / e.inv_tau_s;   // the tiles accumulate (cw/tau_s) * q * u
     if (lane == 0) {
-      e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 0] = a * DINOX_LN2;
-      e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 1] = b * DINOX_LN2;
+      e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 0] = a * sc;
+      e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 1] = b * sc;
     }
   }
   template <int BN>
@@ -207,9 +244,9 @@ struct EpiGradT {
       if (i < BN) {
         const int ent = tc.n_tile * BN + i;
         const bool ok = ent < p.N;
-        buf[i] = ok ? e.lse2[ent] : 0.f;
-        buf[128 + i] = ok ? e.rb2[ent] : 0.f;
-        buf[256 + i] = ok ? e.cw[ent] : 0.f;
+        buf[i] = ok ? -__ldg(e.lse2 + ent) : 0.f;
+        buf[128 + i] = ok ? -__ldg(e.rb2 + ent) : 0.f;
+        buf[256 + i] = ok ? __ldg(e.cw + ent) * e.inv_tau_s : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
@@ -221,12 +258,13 @@ struct EpiGradT {
       const int half = epi_warp >> 2;
       const int k = tc.m_tile * BM + q * 32 + lane;   // prototype
       const bool kok = k < p.M;
-      const float* ctp = (e.ct2_alt && tc.n_tile * BN >= e.alt_from) ? e.ct2_alt : e.ct2;
+      const bool alt = e.ct2_alt && tc.n_tile * BN >= e.alt_from;
+      const float* ctp = alt ? e.ct2_alt : e.ct2;
       const float cs = kok ? __ldg(e.cs2 + k) : 0.f;
       const float ct = kok ? __ldg(ctp + k) : 0.f;
       const uint32_t ts = tmem_acc + ((uint32_t)(q * 32) << 16) + half * 64;
       const uint32_t tt = ts + BN;
-      float loss = 0.f, db2 = 0.f;
+      float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         float sv[32], tv[32];
@@ -234,15 +272,21 @@ struct EpiGradT {
         const int e0 = half * 64 + c * 32;
         uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float lse2 = buf[e0 + j], rb2 = buf[128 + e0 + j], cw = buf[256 + e0 + j];
-          const float s2 = fmaf(sv[j], e.as2, cs);
-          const float pp = fast_ex2(s2 - lse2);
-          const float qq = fast_ex2(fmaf(tv[j], e.at2, ct) - rb2);
-          const float g = cw * e.inv_tau_s * (pp - qq);
-          loss = fmaf(cw * qq, lse2 - s2, loss);
-          db2 += g;
-          sv[j] = g;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 nl = lds128(buf + e0 + j), nr = lds128(buf + 128 + e0 + j), cw = lds128(buf + 256 + e0 + j);
+          const float nls[4] = {nl.x, nl.y, nl.z, nl.w}, nrs[4] = {nr.x, nr.y, nr.z, nr.w}, cws[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float u = fmaf(sv[j + i], e.as2, nls[i]) + cs;
+            const float w = fmaf(tv[j + i], e.at2, nrs[i]) + ct;
+            const float pp = fast_ex2(u);
+            const float qq = fast_ex2(w);
+            const float cwq = cws[i] * qq;
+            const float g = fmaf(cws[i], pp, -cwq);
+            if (i & 1) { l1 = fmaf(cwq, u, l1); d1 += g; }
+            else { l0 = fmaf(cwq, u, l0); d0 += g; }
+            sv[j + i] = g;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -262,13 +306,13 @@ struct EpiGradT {
           }
         }
       }
-      if (!kok) { loss = 0.f; db2 = 0.f; }
-      if (e.db2_partial && kok) e.db2_partial[(int64_t)(tc.n_tile * 2 + half) * p.M + k] = db2;
-      if (e.ct2_alt && tc.n_tile * BN >= e.alt_from) st.loss_b += loss; else st.loss_a += loss;
+      if (kok) {
+        if (e.db2_partial) e.db2_partial[(int64_t)(tc.n_tile * 2 + half) * p.M + k] = d0 + d1;
+        if (alt) st.loss_b += l0 + l1; else st.loss_a += l0 + l1;
+      }
     }
   };
 };
-
 
 // =============================================================================================
 // Epilogue 4 (Gram anchoring): per image, sub-GEMM 0 = student Gram tile, sub-GEMM 1 = teacher
@@ -382,18 +426,21 @@ struct EpiAdapter {
   }
 };
 
-template <int BN, int NSUB, class Epi>
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi>
 __global__ void __launch_bounds__((2 + Epi::kEpiWarps) * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
             const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
             const CoreParams p, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
-  gemm_body<BN, NSUB, EpiAdapter<BN, Epi>>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, smem_raw);
+  gemm_body<BN, NSPLIT, NSUB, CL, EpiAdapter<BN, Epi>>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, smem_raw);
 }
 
-static inline int launch_grid(int64_t tiles) {
-  int grid = num_sms();
-  return grid > tiles ? (int)tiles : grid;
+// number of CTAs for `tiles` super tiles of a CL-cluster kernel: one CTA per SM, whole clusters
+static inline int launch_grid(int64_t super_tiles, int cl) {
+  int64_t clusters = num_sms() / cl;
+  if (clusters > super_tiles) clusters = super_tiles;
+  if (clusters < 1) clusters = 1;
+  return (int)(clusters * cl);
 }
 
 struct Operand {
@@ -413,23 +460,25 @@ static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int t
   return make_tmap_bf16_2d(tm, o.ptr, K, o.rows, o.ld, BK, what);  // box = 64 k-rows x 64 mn-elements
 }
 
-template <int BN, int NSUB, class Epi>
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi>
 static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const Operand* b1, int64_t M, int64_t N,
                   int64_t K, int m_fastest, const typename Epi::Params& ep, cudaStream_t stream, const char* name,
                   int64_t batches = 1) {
   DINOX_REQUIRE(M > 0 && N > 0 && K > 0, DINOX_E_BADARG, "%s: empty problem", name);
   DINOX_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), DINOX_E_BADARG, "%s: dimension too large", name);
+  DINOX_REQUIRE(batches >= 1 && batches < (1 << 20), DINOX_E_BADARG, "%s: bad batch count", name);
+  DINOX_REQUIRE(!(b0.mn_major && ((BN / NSPLIT / CL) % 64) != 0), DINOX_E_UNSUPPORTED,
+                "%s: MN-major B needs 64-element atoms per CTA at this tile shape", name);
   CUtensorMap tA0, tB0, tA1, tB1;
   int rc;
-  DINOX_REQUIRE(batches >= 1 && batches < (1 << 20), DINOX_E_BADARG, "%s: bad batch count", name);
   if ((rc = make_operand_tmap(&tA0, a0, K, BM, batches, "A"))) return rc;
-  if ((rc = make_operand_tmap(&tB0, b0, K, BN, batches, "B"))) return rc;
+  if ((rc = make_operand_tmap(&tB0, b0, K, BN / NSPLIT / CL, batches, "B"))) return rc;   // one box per (N sub-tile, CTA)
   tA1 = tA0; tB1 = tB0;
   if (NSUB == 2) {
     DINOX_REQUIRE(a1 && b1 && a1->mn_major == a0.mn_major && b1->mn_major == b0.mn_major, DINOX_E_BADARG,
                   "%s: second operand pair missing or layout mismatch", name);
     if ((rc = make_operand_tmap(&tA1, *a1, K, BM, batches, "A1"))) return rc;
-    if ((rc = make_operand_tmap(&tB1, *b1, K, BN, batches, "B1"))) return rc;
+    if ((rc = make_operand_tmap(&tB1, *b1, K, BN / NSPLIT / CL, batches, "B1"))) return rc;
   }
   CoreParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -438,18 +487,57 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   p.num_k_blocks = (int)((K + BK - 1) / BK);
   p.a_mn_major = a0.mn_major; p.b_mn_major = b0.mn_major; p.m_fastest = m_fastest;
   p.batches = (int)batches;
-  auto kern = gemm_kernel<BN, NSUB, Epi>;
-  constexpr int smem = smem_bytes<BN, Epi>();
+  auto kern = gemm_kernel<BN, NSPLIT, NSUB, CL, Epi>;
+  constexpr int smem = smem_bytes<BN, CL, Epi>();
   static bool attr_set = false;
   if (!attr_set) {
     DINOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles * batches;
-  DINOX_REQUIRE(tiles < (1ll << 31), DINOX_E_BADARG, "%s: too many tiles", name);
-  int grid = launch_grid(tiles);
-  kern<<<grid, (2 + Epi::kEpiWarps) * 32, smem, stream>>>(tA0, tB0, tA1, tB1, p, ep);
+  const int64_t super = (int64_t)((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * batches;
+  DINOX_REQUIRE(super < (1ll << 31), DINOX_E_BADARG, "%s: too many tiles", name);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)launch_grid(super, CL));
+  cfg.blockDim = dim3((2 + Epi::kEpiWarps) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA0, tB0, tA1, tB1, p, ep);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaLaunchKernelEx failed: %s", name, cudaGetErrorString(e));
+    return DINOX_E_CUDA;
+  }
   return check_launch(name, stream);
+}
+
+// CTA-pair (cta_group::2) mode can be switched per process for A/B measurements: DINOX_PAIR=0|1
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DINOX_PAIR");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
+
+// tile-shape dispatch of the plain GEMM: widest tile without N waste; clusters of 2 share the B tile
+static int launch_store(int64_t M, int64_t N, bool b_mn, const Operand& a, const Operand& b, int64_t K, int m_fastest,
+                        const EpiStore::Params& ep, cudaStream_t stream, int64_t batches) {
+  const bool cl2 = M > BM && pair_enabled();   // a single M tile has nobody to pair with
+  if (N % 384 == 0) {
+    return cl2 ? launch<384, 3, 1, 2, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<384,pair>", batches)
+               : launch<384, 3, 1, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<384>", batches);
+  }
+  if (N % 256 == 0 || N > 2048) {
+    return cl2 ? launch<256, 1, 1, 2, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<256,cl2>", batches)
+               : launch<256, 1, 1, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<256>", batches);
+  }
+  return cl2 ? launch<128, 1, 1, 2, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<128,cl2>", batches)
+             : launch<128, 1, 1, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<128>", batches);
 }
 
 }  // namespace gemm
@@ -472,10 +560,7 @@ int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N,
   if (rc) return rc;
   Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
   EpiStore::Params ep{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, bias_n, 0};
-  // widest tile that divides N without waste; ragged N falls back to 128-wide tiles
-  if (N % 256 == 0 || N > 2048) return launch<256, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<256>");
-  if (N % 192 == 0) return launch<192, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<192>");
-  return launch<128, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<128>");
+  return launch_store(M, N, b_mn_major != 0, a, b, K, m_fastest, ep, stream, 1);
 }
 
 size_t dinox_head_stats_workspace_bytes(int64_t rows, int64_t K) {
@@ -492,7 +577,8 @@ int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int
   if (rc) return rc;
   Operand a{H, rows, ldh, 0}, b{W2, K, ldw, 0};
   EpiStats::Params ep{inv_tau * DINOX_LOG2E, col2, reinterpret_cast<float2*>(workspace)};
-  rc = launch<256, 1, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, stream, "head_stats");
+  rc = (rows > BM && pair_enabled()) ? launch<256, 1, 1, 2, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, stream, "head_stats<cl2>")
+                 : launch<256, 1, 1, 1, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, stream, "head_stats");
   if (rc) return rc;
   const int n_part = 2 * (int)((K + 255) / 256);
   stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows, n_part,
@@ -525,9 +611,12 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
   ep.gt = reinterpret_cast<__nv_bfloat16*>(Gt); ep.ldg = ldg;
   ep.db2_partial = db2_partial; ep.loss_partial = reinterpret_cast<float*>(workspace);
   // entry tiles fastest: the 2 x (K-tile of W2) operands stay put while HsE/HtE (L2-resident) stream
-  rc = launch<128, 2, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, stream, "head_grad");
+  const bool cl2 = K > BM && pair_enabled();
+  rc = cl2 ? launch<128, 1, 2, 2, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, stream, "head_grad<cl2>")
+           : launch<128, 1, 2, 1, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, stream, "head_grad");
   if (rc) return rc;
-  const int grid = launch_grid(((K + 127) / 128) * ((E + 127) / 128));
+  const int cl = cl2 ? 2 : 1;
+  const int grid = launch_grid((((K + 127) / 128 + cl - 1) / cl) * ((E + 127) / 128), cl);
   pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * 8, loss_out, loss_accumulate);
   return check_launch("pair_sum_kernel", stream);
 }
@@ -545,9 +634,7 @@ int dinox_gemm_bf16_batched(const void* A, const void* B, void* C, int64_t batch
   if (rc) return rc;
   Operand a{A, M, lda, a_mn_major ? 1 : 0, stride_a}, b{B, N, ldb, b_mn_major ? 1 : 0, stride_b};
   EpiStore::Params ep{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, nullptr, stride_c};
-  if (N % 256 == 0 || N > 2048) return launch<256, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, 1, ep, stream, "gemm_bf16_batched<256>", batches);
-  if (N % 192 == 0) return launch<192, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, 1, ep, stream, "gemm_bf16_batched<192>", batches);
-  return launch<128, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, 1, ep, stream, "gemm_bf16_batched<128>", batches);
+  return launch_store(M, N, b_mn_major != 0, a, b, K, 1, ep, stream, batches);
 }
 
 size_t dinox_gram_diff_workspace_bytes(int64_t batches, int64_t tokens) {
@@ -565,10 +652,10 @@ int dinox_gram_diff(const void* xn_s, const void* xn_t, int64_t batches, int64_t
   // a single image still goes through the 3-D path (batches = 1 uses 2-D maps over (tokens, D))
   Operand a0{xn_s, tokens, D, 0, tokens * D}, a1{xn_t, tokens, D, 0, tokens * D};
   EpiGramDiff::Params ep{reinterpret_cast<__nv_bfloat16*>(delta), ldd, tokens * ldd, reinterpret_cast<float*>(workspace)};
-  rc = launch<128, 2, EpiGramDiff>(a0, a0, &a1, &a1, tokens, tokens, D, 1, ep, stream, "gram_diff", batches);
+  rc = launch<128, 1, 2, 1, EpiGramDiff>(a0, a0, &a1, &a1, tokens, tokens, D, 1, ep, stream, "gram_diff", batches);
   if (rc) return rc;
   const int64_t mt = (tokens + 127) / 128;
-  sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)launch_grid(batches * mt * mt) * 8,
+  sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)launch_grid(batches * mt * mt, 1) * 8,
                                      loss_scale, loss_out, 0);
   return check_launch("sum_kernel", stream);
 }

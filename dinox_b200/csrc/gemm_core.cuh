@@ -30,13 +30,14 @@ struct CoreParams {
   int batches;                 // > 1: independent problems along a third tensor-map dimension
 };
 
-template <int BN>
+template <int BN, int CL = 1>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CL) * BK * 2;   // a CTA of a pair holds 1/CL of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBudget = 196 * 1024;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static_assert(kStages >= 2, "tile too large for the smem pipeline");
   static constexpr int kPipeBytes = kStages * kStageBytes;
 };
 
@@ -74,24 +75,34 @@ __device__ __forceinline__ float fast_ex2(float x) {
   return y;
 }
 
-// The kernel body shared by all GEMM flavours.  `Epi` provides:
-//   static constexpr int kEpiWarps;                      // 4 or 8
-//   struct Params;                                       // POD, passed by value
-//   __device__ static void tile(const Params&, const CoreParams&, TileCoord, uint32_t tmem_acc,
-//                               int acc_stage, int epi_warp, int lane, uint8_t* epi_smem);
-//   static constexpr int kEpiSmemBytes;
-template <int BN, int NSUB, class Epi>
+// The kernel body shared by all GEMM flavours.
+//   BN     : tile width (N);  NSPLIT : MMA instructions along N per k-step sharing the A tile
+//            (BN/NSPLIT <= 256 is the UMMA N);  NSUB : independent sub-GEMMs per tile
+//   CL     : 1 = one CTA per 128 x BN tile (tcgen05 cta_group::1)
+//            2 = CTA pair (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile over two SMs.  Each
+//                CTA loads its own 128 A rows and HALF of the B tile; the leader CTA issues the MMAs
+//                for both; each CTA's epilogue drains the 128 rows that live in its own TMEM.  This
+//                halves the B-operand bytes every SM pulls from L2 per FLOP - the K<=1024 GEMMs of
+//                the loss head are bound by L2->SMEM operand traffic, not by the tensor pipe.
+// `Epi` provides kEpiWarps, Params, State, prologue(), tile(), finish().
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi>
 __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Epi::Params& ep,
                                           const CUtensorMap* tmA0, const CUtensorMap* tmB0,
                                           const CUtensorMap* tmA1, const CUtensorMap* tmB1,
                                           uint8_t* smem_raw) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CL>;
   constexpr int kStages = L::kStages;
-  constexpr int kAccCols = NSUB * BN;                       // TMEM columns per accumulator stage
-  constexpr uint32_t kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64
-                                 : (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256) ? 256 : 512;
-  static_assert(2 * kAccCols <= 512, "accumulators do not fit TMEM");
-  static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64 (MN-major TMA atoms), <= 256");
+  constexpr int BNI = BN / NSPLIT;                           // UMMA N
+  constexpr int BNL = BNI / CL;                              // rows of one N sub-tile held by this CTA
+  constexpr int kAccCols = NSUB * BN;                        // TMEM columns per accumulator stage
+  constexpr int kAccStages = (2 * kAccCols <= 512) ? 2 : 1;  // double-buffer when it fits
+  constexpr uint32_t kNeed = kAccStages * kAccCols;
+  constexpr uint32_t kTmemCols = kNeed <= 32 ? 32 : kNeed <= 64 ? 64 : kNeed <= 128 ? 128 : kNeed <= 256 ? 256 : 512;
+  static_assert(kAccCols <= 512, "accumulators do not fit TMEM");
+  static_assert(BNI % 16 == 0 && BNI <= 256 && BN % 64 == 0, "invalid tile shape");
+  static_assert(CL == 1 || CL == 2, "cluster size 1 or 2");
+  static_assert(BNL % 8 == 0, "per-CTA B slice must be whole 8-row swizzle groups");
+  constexpr bool kPair = (CL == 2);
 
   // 1024-B aligned carve-up (swizzle-128B atoms need it)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -101,31 +112,43 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.batches;
+  const int crank = kPair ? (int)sm100::cluster_ctarank() : 0;
+  const bool leader = (crank == 0);
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+  // pairs walk "super tiles" of CL adjacent M tiles; a ragged last M super tile computes on
+  // zero-filled (out-of-bounds) rows and the epilogues mask it
+  CoreParams ps = p;
+  ps.num_m_tiles = (p.num_m_tiles + CL - 1) / CL;
+  const int num_super = ps.num_m_tiles * ps.num_n_tiles * ps.batches;
 
   if (warp == 0 && lane == 0) {
     sm100::prefetch_tmap(tmA0);
     sm100::prefetch_tmap(tmB0);
     if (NSUB == 2) { sm100::prefetch_tmap(tmA1); sm100::prefetch_tmap(tmB1); }
     for (int i = 0; i < kStages; ++i) { sm100::mbar_init(&ctl->full[i], 1); sm100::mbar_init(&ctl->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { sm100::mbar_init(&ctl->tmem_full[i], 1); sm100::mbar_init(&ctl->tmem_empty[i], Epi::kEpiWarps); }
+    for (int i = 0; i < 2; ++i) {
+      sm100::mbar_init(&ctl->tmem_full[i], 1);
+      sm100::mbar_init(&ctl->tmem_empty[i], CL * Epi::kEpiWarps);   // pair: both CTAs' epilogues report to the leader
+    }
     sm100::fence_barrier_init();
   }
   if (warp == 1) {
-    sm100::tmem_alloc(&ctl->tmem_base, kTmemCols);
-    sm100::tmem_relinquish();
+    if (kPair) { sm100::tmem_alloc_pair(&ctl->tmem_base, kTmemCols); sm100::tmem_relinquish_pair(); }
+    else { sm100::tmem_alloc(&ctl->tmem_base, kTmemCols); sm100::tmem_relinquish(); }
   }
   sm100::tc_fence_before();
   __syncthreads();
+  if (kPair) sm100::cluster_sync();   // the peer's barriers / TMEM are set up before anyone signals them
   sm100::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====
     if (lane == 0) {
       PipeState st;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(p, t);
+      for (int u = cid; u < num_super; u += ncl) {
+        TileCoord tc = tile_coord(ps, u);
+        tc.m_tile = tc.m_tile * CL + crank;
         const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
         for (int sub = 0; sub < NSUB; ++sub) {
           const CUtensorMap* ma = sub ? tmA1 : tmA0;
@@ -134,37 +157,39 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             sm100::mbar_wait(&ctl->empty[st.stage], st.phase ^ 1, 1);
             uint8_t* sa = pipe + st.stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
-            sm100::mbar_expect_tx(&ctl->full[st.stage], L::kStageBytes);
+            uint64_t* full = &ctl->full[st.stage];
+            // pair: all bytes (both CTAs) are counted on the leader's barrier
+            const uint32_t full_addr = kPair ? sm100::mapa_u32(sm100::smem_u32(full), 0) : 0;
+            if (leader) sm100::mbar_expect_tx(full, CL * L::kStageBytes);
             const int k0 = kb * BK;
-            if (p.batches > 1) {
-              if (!p.a_mn_major) {
-                sm100::tma_load_3d(sa, ma, &ctl->full[st.stage], k0, m0, tc.batch);
+            const bool b3 = p.batches > 1;
+            auto load = [&](uint8_t* dst, const CUtensorMap* tm, int c0, int c1) {
+              if (kPair) {
+                if (b3) sm100::tma_load_3d_pair(dst, tm, full_addr, c0, c1, tc.batch);
+                else sm100::tma_load_2d_pair(dst, tm, full_addr, c0, c1);
               } else {
-#pragma unroll
-                for (int c = 0; c < BM / 64; ++c)
-                  sm100::tma_load_3d(sa + c * (BK * 128), ma, &ctl->full[st.stage], m0 + c * 64, k0, tc.batch);
+                if (b3) sm100::tma_load_3d(dst, tm, full, c0, c1, tc.batch);
+                else sm100::tma_load_2d(dst, tm, full, c0, c1);
               }
-              if (!p.b_mn_major) {
-                sm100::tma_load_3d(sb, mb, &ctl->full[st.stage], k0, n0, tc.batch);
-              } else {
-#pragma unroll
-                for (int c = 0; c < BN / 64; ++c)
-                  sm100::tma_load_3d(sb + c * (BK * 128), mb, &ctl->full[st.stage], n0 + c * 64, k0, tc.batch);
-              }
+            };
+            // ---- A: this CTA's own 128 rows
+            if (!p.a_mn_major) {
+              load(sa, ma, k0, m0);
             } else {
-              if (!p.a_mn_major) {
-                sm100::tma_load_2d(sa, ma, &ctl->full[st.stage], k0, m0);
-              } else {
 #pragma unroll
-                for (int c = 0; c < BM / 64; ++c)
-                  sm100::tma_load_2d(sa + c * (BK * 128), ma, &ctl->full[st.stage], m0 + c * 64, k0);
-              }
+              for (int c = 0; c < BM / 64; ++c) load(sa + c * (BK * 128), ma, m0 + c * 64, k0);
+            }
+            // ---- B: for every N sub-tile h, this CTA's BNL of its BNI rows
+#pragma unroll
+            for (int h = 0; h < NSPLIT; ++h) {
+              const int r0 = n0 + h * BNI + crank * BNL;
               if (!p.b_mn_major) {
-                sm100::tma_load_2d(sb, mb, &ctl->full[st.stage], k0, n0);
+                load(sb + h * (BNL * 128), mb, k0, r0);
               } else {
+                constexpr int kAtoms = BNL / 64;   // host guarantees BNL % 64 == 0 for MN-major B
 #pragma unroll
-                for (int c = 0; c < BN / 64; ++c)
-                  sm100::tma_load_2d(sb + c * (BK * 128), mb, &ctl->full[st.stage], n0 + c * 64, k0);
+                for (int c = 0; c < (kAtoms > 0 ? kAtoms : 1); ++c)
+                  load(sb + (h * (kAtoms > 0 ? kAtoms : 1) + c) * (BK * 128), mb, r0 + c * 64, k0);
               }
             }
             st.advance<kStages>();
@@ -173,17 +198,19 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = sm100::umma_idesc_bf16(BM, BN, p.a_mn_major, p.b_mn_major);
-      // per-UMMA_K advance of the descriptor start address, and LBO/SBO per layout
+    // ===================== MMA issuer (one thread; pair: the leader CTA only) =====================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = sm100::umma_idesc_bf16(BM * CL, BNI, p.a_mn_major, p.b_mn_major);
+      // per-UMMA_K advance of the descriptor start address, and LBO per layout
       const uint32_t a_adv = p.a_mn_major ? (UMMA_K * 128) : (UMMA_K * 2);
       const uint32_t b_adv = p.b_mn_major ? (UMMA_K * 128) : (UMMA_K * 2);
       const uint32_t a_lbo = p.a_mn_major ? (BK * 128) : 16, b_lbo = p.b_mn_major ? (BK * 128) : 16;
+      // byte offset of N sub-tile h inside this CTA's B stage buffer
+      const uint32_t b_split = p.b_mn_major ? (BNL / 64) * (BK * 128) : BNL * 128;
       PipeState st;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int u = cid; u < num_super; u += ncl) {
         sm100::mbar_wait(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, 2);
         sm100::tc_fence_after();
         for (int sub = 0; sub < NSUB; ++sub) {
@@ -196,16 +223,24 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = sm100::umma_smem_desc(sa + k * a_adv, a_lbo, 1024);
-              const uint64_t db = sm100::umma_smem_desc(sb + k * b_adv, b_lbo, 1024);
-              sm100::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+#pragma unroll
+              for (int h = 0; h < NSPLIT; ++h) {
+                const uint64_t db = sm100::umma_smem_desc(sb + h * b_split + k * b_adv, b_lbo, 1024);
+                if (kPair) sm100::umma_bf16_pair(d_tmem + h * BNI, da, db, idesc, (kb | k) != 0);
+                else sm100::umma_bf16(d_tmem + h * BNI, da, db, idesc, (kb | k) != 0);
+              }
             }
-            sm100::umma_commit(&ctl->empty[st.stage]);  // frees the smem slot when these MMAs retire
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if (kPair) sm100::umma_commit_pair(&ctl->empty[st.stage]);
+            else sm100::umma_commit(&ctl->empty[st.stage]);
             st.advance<kStages>();
           }
         }
-        sm100::umma_commit(&ctl->tmem_full[acc_stage]);  // accumulators complete -> epilogue
-        acc_stage ^= 1;
-        if (acc_stage == 0) acc_phase ^= 1;
+        // accumulators complete -> epilogue (of both CTAs)
+        if (kPair) sm100::umma_commit_pair(&ctl->tmem_full[acc_stage]);
+        else sm100::umma_commit(&ctl->tmem_full[acc_stage]);
+        if (kAccStages == 2) { acc_stage ^= 1; if (acc_stage == 0) acc_phase ^= 1; }
+        else acc_phase ^= 1;
       }
     }
   } else {
@@ -214,32 +249,38 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     typename Epi::State state;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const TileCoord tc = tile_coord(p, t);
+    for (int u = cid; u < num_super; u += ncl) {
+      TileCoord tc = tile_coord(ps, u);
+      tc.m_tile = tc.m_tile * CL + crank;
       Epi::prologue(ep, p, tc, acc_stage, epi_warp, lane, epi_smem);
       sm100::mbar_wait(&ctl->tmem_full[acc_stage], acc_phase, 4);
       sm100::tc_fence_after();
-      Epi::tile(ep, p, tc, t, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
+      Epi::tile(ep, p, tc, u, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
       sm100::tc_fence_before();
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&ctl->tmem_empty[acc_stage]);
-      acc_stage ^= 1;
-      if (acc_stage == 0) acc_phase ^= 1;
+      if (lane == 0) {
+        if (kPair) sm100::mbar_arrive_cluster(sm100::mapa_u32(sm100::smem_u32(&ctl->tmem_empty[acc_stage]), 0));
+        else sm100::mbar_arrive(&ctl->tmem_empty[acc_stage]);
+      }
+      if (kAccStages == 2) { acc_stage ^= 1; if (acc_stage == 0) acc_phase ^= 1; }
+      else acc_phase ^= 1;
     }
     Epi::finish(ep, p, epi_warp, lane, state);
   }
 
   sm100::tc_fence_before();
   __syncthreads();
+  if (kPair) sm100::cluster_sync();   // nobody exits while the peer may still signal / read its smem
   if (warp == 1) {
     sm100::tc_fence_after();
-    sm100::tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) sm100::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else sm100::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int BN, class Epi>
+template <int BN, int CL, class Epi>
 constexpr int smem_bytes() {
-  return SmemLayout<BN>::kPipeBytes + 256 + Epi::kEpiSmemBytes + 1024 /* alignment slack */;
+  return SmemLayout<BN, CL>::kPipeBytes + 256 + Epi::kEpiSmemBytes + 1024 /* alignment slack */;
 }
 
 // lane quarter of TMEM this warp may read (hardware: warp_id % 4), and which column half it owns
