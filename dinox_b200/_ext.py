@@ -131,6 +131,9 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_i64, c_void_p]),
     "dinox_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                 c_int, c_int, c_f32, c_void_p, c_void_p, c_int, c_void_p]),
+    "dinox_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                       c_int, c_int, c_int, c_f32, c_void_p, c_int, c_void_p]),
+    "dinox_gemm_splitk_plan": (c_int, [c_i64, c_i64, c_i64]),
     "dinox_head_stats_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_head_stats": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
@@ -151,8 +154,8 @@ SIGNATURES = {
     "dinox_gelu_bwd_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_gelu_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dinox_gemv_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_f32, c_void_p, c_f32, c_void_p, c_void_p]),
-    "dinox_gather_sum_rows": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_f32, c_void_p, c_i64,
-                                      c_int, c_void_p]),
+    "dinox_gather_sum_rows": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_f32,
+                                      c_void_p, c_i64, c_int, c_void_p]),
     "dinox_fill_f32": (c_int, [c_void_p, c_i64, c_f32, c_void_p]),
 }
 

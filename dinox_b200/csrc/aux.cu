@@ -108,9 +108,11 @@ __global__ void gemv_bf16_kernel(const __nv_bfloat16* __restrict__ W, int64_t ld
 }
 
 // ---------------------------------------------------------------------------------------------
-// dst[r, :] (+)= scale * sum_{i in [ptr[r], ptr[r+1])} src[ent[i], :]       fp32, warp per row
+// dst[r, :] (+)= scale * sum_{i in [ptr[r], ptr[r+1])} sum_{s < slabs} src[s*slab_stride + ent[i]*ld, :]
+// fp32, warp per row, fixed summation order (entries outer, split-K slabs inner)
 // ---------------------------------------------------------------------------------------------
-__global__ void gather_sum_kernel(const float* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ ptr,
+__global__ void gather_sum_kernel(const float* __restrict__ src, int64_t ld_src, int slabs, int64_t slab_stride,
+                                  const int64_t* __restrict__ ptr,
                                   const int64_t* __restrict__ ent, int64_t rows, int D, const float* __restrict__ scale_dev,
                                   float scale, float* __restrict__ dst, int64_t ld_dst, int accumulate) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -121,8 +123,11 @@ __global__ void gather_sum_kernel(const float* __restrict__ src, int64_t ld_src,
   for (int c = lane * 4; c < D; c += 128) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t i = i0; i < i1; ++i) {
-      const float4 v = *reinterpret_cast<const float4*>(src + ent[i] * ld_src + c);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      const float* base = src + ent[i] * ld_src + c;
+      for (int sl = 0; sl < slabs; ++sl) {
+        const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(base + sl * slab_stride));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
     }
     float4* d = reinterpret_cast<float4*>(dst + r * ld_dst + c);
     float4 o = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc);
@@ -234,13 +239,14 @@ int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64
   return check_launch("gemv_bf16_kernel", stream);
 }
 
-int dinox_gather_sum_rows(const float* src, int64_t ld_src, const int64_t* ptr, const int64_t* ent, int64_t rows,
-                          int64_t D, const float* scale_dev, float scale, float* dst, int64_t ld_dst, int accumulate,
-                          dinox_stream_t stream) {
-  DINOX_REQUIRE(src && ptr && ent && dst && rows >= 0 && D > 0 && D % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0,
+int dinox_gather_sum_rows(const float* src, int64_t ld_src, int slabs, int64_t slab_stride, const int64_t* ptr,
+                          const int64_t* ent, int64_t rows, int64_t D, const float* scale_dev, float scale, float* dst,
+                          int64_t ld_dst, int accumulate, dinox_stream_t stream) {
+  DINOX_REQUIRE(src && ptr && ent && dst && rows >= 0 && D > 0 && D % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 &&
+                    slabs >= 1 && slab_stride % 4 == 0,
                 DINOX_E_BADARG, "gather_sum_rows: bad arguments");
   if (rows == 0) return DINOX_OK;
-  gather_sum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(src, ld_src, ptr, ent, rows, (int)D, scale_dev, scale, dst, ld_dst, accumulate);
+  gather_sum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(src, ld_src, slabs, slab_stride, ptr, ent, rows, (int)D, scale_dev, scale, dst, ld_dst, accumulate);
   return check_launch("gather_sum_kernel", stream);
 }
 

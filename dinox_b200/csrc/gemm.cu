@@ -15,8 +15,126 @@ namespace gemm {
 
 // =============================================================================================
 // Epilogue 1: store   C = alpha * acc (+ bias[n])  ->  fp32 | bf16, optional C += ...
+// Each epilogue warp owns 32 accumulator rows.  It drains them in 128-byte-per-row chunks
+// (32 fp32 or 64 bf16 columns): TMEM -> registers (next chunk's tcgen05.ld already in flight) ->
+// swizzled per-warp staging buffer in shared memory -> one TMA store per chunk, so global writes
+// are full 128 B lines issued asynchronously instead of 32 scattered 16-byte stores per instruction.
+// accumulate = TMA reduce-add: the += happens in L2, the old values never pass through the SM.
+// Split-K / batched launches address output slab tc.batch + tc.split through the 3rd coordinate.
 // =============================================================================================
 struct EpiStore {
+  static constexpr bool kUsesTmaStore = true;
+  static constexpr int kEpiWarps = 4;
+  static constexpr int kBufs = 2;
+  static constexpr int kEpiSmemBytes = kEpiWarps * kBufs * 4096;
+  struct Params {
+    int out_bf16;
+    int accumulate;
+    float alpha;
+    const float* alpha_dev;  // optional device scalar multiplied into alpha
+    const float* bias_n;     // optional per-column bias
+  };
+  struct State {
+    int flip = 0;
+  };
+  static __device__ __forceinline__ void finish(const Params&, const CoreParams&, int, int lane, State&) {
+    if (lane == 0) sm100::tma_store_wait_all<0>();
+  }
+  template <int BN>
+  struct Impl {
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
+
+    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap* tmC,
+                                                uint32_t tmem_acc, int, int epi_warp, int lane, uint8_t* smem, State& st) {
+      const int q = epi_quarter();
+      const int row0 = tc.m_tile * BM + q * 32;
+      const float alpha = e.alpha * (e.alpha_dev ? *e.alpha_dev : 1.f);
+      const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+      const int slab = tc.batch + tc.split;
+      uint8_t* wbase = smem + epi_warp * (kBufs * 4096);
+      constexpr int kChunks = BN / 32;           // 32-column TMEM chunks
+      uint32_t ra[32], rb[32];
+      sm100::tmem_ld32_nowait(taddr, ra);
+      sm100::tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+        uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+        if (c + 1 < kChunks) sm100::tmem_ld32_nowait(taddr + (c + 1) * 32, nxt);
+        const int col0 = tc.n_tile * BN + c * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) * alpha;
+        if (e.bias_n) {
+          if (col0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias_n + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.N) ? __ldg(e.bias_n + col0 + j) : 0.f;
+          }
+        }
+        WarpStage stg;
+        if (e.out_bf16) {
+          // two TMEM chunks (64 columns) fill one 128-byte row; flush after the odd chunk
+          const bool first = (c & 1) == 0;
+          uint8_t* wbuf = wbase + st.flip * 4096;
+          if (first) {
+            if (lane == 0) sm100::tma_store_wait_read<kBufs - 1>();
+            __syncwarp();
+          }
+          stg.init(wbuf, lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+            stg.put((first ? 0 : 4) + j, *reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1),
+                    *reinterpret_cast<uint32_t*>(&t2), *reinterpret_cast<uint32_t*>(&t3));
+          }
+          if (!first || c + 1 == kChunks) {
+            sm100::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M && col0 - (first ? 0 : 32) < p.N) {
+              sm100::tma_store_3d(tmC, wbuf, col0 - (first ? 0 : 32), row0, slab);
+              sm100::tma_store_commit();
+            }
+            st.flip ^= 1;
+          }
+        } else {
+          uint8_t* wbuf = wbase + st.flip * 4096;
+          if (lane == 0) sm100::tma_store_wait_read<kBufs - 1>();
+          __syncwarp();
+          stg.init(wbuf, lane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            stg.put(j, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                    __float_as_uint(v[4 * j + 3]));
+          sm100::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && col0 < p.N) {
+            if (e.accumulate) sm100::tma_reduce_add_3d(tmC, wbuf, col0, row0, slab);
+            else sm100::tma_store_3d(tmC, wbuf, col0, row0, slab);
+            sm100::tma_store_commit();
+          }
+          st.flip ^= 1;
+        }
+        if (c + 1 < kChunks) sm100::tmem_wait_ld();
+      }
+    }
+  };
+};
+
+// =============================================================================================
+// Epilogue 1b: direct stores (one output row per thread).  Only the rare bf16 read-modify-write
+// (accumulate into a bf16 matrix) still goes this way; everything else uses EpiStore below.
+// =============================================================================================
+struct EpiStoreDirect {
+  static constexpr bool kUsesTmaStore = false;
   static constexpr int kEpiWarps = 4;
   static constexpr int kEpiSmemBytes = 0;
   struct Params {
@@ -34,8 +152,8 @@ struct EpiStore {
   template <int BN>
   struct Impl {
     static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
-    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int, uint32_t tmem_acc,
-                                                int, int, int lane, uint8_t*, State&) {
+    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap*,
+                                                uint32_t tmem_acc, int, int, int lane, uint8_t*, State&) {
       const int q = epi_quarter();
       const int row = tc.m_tile * BM + q * 32 + lane;
       const float alpha = e.alpha * (e.alpha_dev ? *e.alpha_dev : 1.f);
@@ -110,6 +228,7 @@ __device__ __forceinline__ float4 lds128(const float* p) {
 }
 
 struct EpiStats {
+  static constexpr bool kUsesTmaStore = false;
   static constexpr int kEpiWarps = 8;
   static constexpr int kEpiSmemBytes = 2 * 256 * 4;
   struct Params {
@@ -130,8 +249,8 @@ struct EpiStats {
       buf[i] = (col < p.N) ? (e.col2 ? __ldg(e.col2 + col) : 0.f) : -INFINITY;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int, uint32_t tmem_acc,
-                                                int acc_stage, int epi_warp, int lane, uint8_t* smem, State&) {
+    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap*,
+                                                uint32_t tmem_acc, int acc_stage, int epi_warp, int lane, uint8_t* smem, State&) {
       const float* buf = reinterpret_cast<const float*>(smem) + acc_stage * 256;
       const int q = epi_quarter();
       const int half = epi_warp >> 2;
@@ -208,8 +327,11 @@ __global__ void stats_merge_kernel(const float2* __restrict__ partial, int64_t r
 // (logits -> probs), FMUL + 2 FFMA + FADD (gradient, loss, bias grad), 1/2 F2FP, 3/4 LDS.128.
 // =============================================================================================
 struct EpiGradT {
+  static constexpr bool kUsesTmaStore = true;
   static constexpr int kEpiWarps = 8;
-  static constexpr int kEpiSmemBytes = 2 * 3 * 128 * 4;
+  static constexpr int kBufs = 2;
+  static constexpr int kStageBytes = kEpiWarps * kBufs * 4096;     // per-warp G staging (TMA store source)
+  static constexpr int kEpiSmemBytes = kStageBytes + 2 * 3 * 128 * 4;
   struct Params {
     float as2, at2, inv_tau_s;
     const float* cs2;       // (K)
@@ -219,13 +341,12 @@ struct EpiGradT {
     const float* lse2;      // (E) student LSE (log2) per entry
     const float* rb2;       // (E) teacher row bias (log2) per entry
     const float* cw;        // (E) entry weight (norm * group weight), 0 for padding
-    __nv_bfloat16* gt;      // (K, ldg)
-    int64_t ldg;
     float* db2_partial;     // (2*num_n_tiles, M) or NULL
     float* loss_partial;    // (gridDim.x * 8 * 2): per CTA, per epilogue warp, {entries < alt_from, >= alt_from}
   };
   struct State {
     float loss_a = 0.f, loss_b = 0.f;
+    int flip = 0;
   };
   static __device__ __forceinline__ void finish(const Params& e, const CoreParams&, int epi_warp, int lane, State& st) {
     const float a = warp_sum(st.loss_a), b = warp_sum(st.loss_b);
@@ -233,13 +354,14 @@ struct EpiGradT {
     if (lane == 0) {
       e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 0] = a * sc;
       e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 1] = b * sc;
+      sm100::tma_store_wait_all<0>();
     }
   }
   template <int BN>
   struct Impl {
     static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int acc_stage,
                                                     int epi_warp, int lane, uint8_t* smem) {
-      float* buf = reinterpret_cast<float*>(smem) + acc_stage * 3 * 128;
+      float* buf = reinterpret_cast<float*>(smem + kStageBytes) + acc_stage * 3 * 128;
       const int i = epi_warp * 32 + lane;  // 0..255
       if (i < BN) {
         const int ent = tc.n_tile * BN + i;
@@ -250,13 +372,46 @@ struct EpiGradT {
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int t, uint32_t tmem_acc,
-                                                int acc_stage, int epi_warp, int lane, uint8_t* smem, State& st) {
+
+    // 16 entries of one prototype row: logits -> (p, q) -> gradient, loss and bias-gradient terms;
+    // the bf16 gradients go to pieces 2*c16, 2*c16+1 of this thread's staging row
+    static __device__ __forceinline__ void chunk16(const Params& e, const uint32_t (&sr)[16], const uint32_t (&tr)[16],
+                                                   const float* cb, float cs, float ct, const WarpStage& stg, int c16,
+                                                   float& l0, float& l1, float& d0, float& d1) {
+      uint32_t packed[8];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 nl = lds128(cb + j), nr = lds128(cb + 128 + j), cw = lds128(cb + 256 + j);
+        const float nls[4] = {nl.x, nl.y, nl.z, nl.w}, nrs[4] = {nr.x, nr.y, nr.z, nr.w}, cws[4] = {cw.x, cw.y, cw.z, cw.w};
+        float g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float u = fmaf(__uint_as_float(sr[j + i]), e.as2, nls[i]) + cs;
+          const float w = fmaf(__uint_as_float(tr[j + i]), e.at2, nrs[i]) + ct;
+          const float pp = fast_ex2(u);
+          const float qq = fast_ex2(w);
+          const float cwq = cws[i] * qq;
+          g[i] = fmaf(cws[i], pp, -cwq);
+          if (i & 1) { l1 = fmaf(cwq, u, l1); d1 += g[i]; }
+          else { l0 = fmaf(cwq, u, l0); d0 += g[i]; }
+        }
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(g[0], g[1]), h1 = __floats2bfloat162_rn(g[2], g[3]);
+        packed[j / 2] = *reinterpret_cast<uint32_t*>(&h0);
+        packed[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+      }
+      stg.put(2 * c16, packed[0], packed[1], packed[2], packed[3]);
+      stg.put(2 * c16 + 1, packed[4], packed[5], packed[6], packed[7]);
+    }
+
+    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap* tmC,
+                                                uint32_t tmem_acc, int acc_stage, int epi_warp, int lane, uint8_t* smem,
+                                                State& st) {
       static_assert(BN == 128, "EpiGradT is written for 128-entry tiles");
-      const float* buf = reinterpret_cast<const float*>(smem) + acc_stage * 3 * 128;
+      const float* buf = reinterpret_cast<const float*>(smem + kStageBytes) + acc_stage * 3 * 128;
       const int q = epi_quarter();
       const int half = epi_warp >> 2;
-      const int k = tc.m_tile * BM + q * 32 + lane;   // prototype
+      const int k0 = tc.m_tile * BM + q * 32;
+      const int k = k0 + lane;   // prototype
       const bool kok = k < p.M;
       const bool alt = e.ct2_alt && tc.n_tile * BN >= e.alt_from;
       const float* ctp = alt ? e.ct2_alt : e.ct2;
@@ -264,48 +419,40 @@ struct EpiGradT {
       const float ct = kok ? __ldg(ctp + k) : 0.f;
       const uint32_t ts = tmem_acc + ((uint32_t)(q * 32) << 16) + half * 64;
       const uint32_t tt = ts + BN;
+      const float* cb = buf + half * 64;
+      uint8_t* wbuf = smem + (epi_warp * kBufs + st.flip) * 4096;
+      WarpStage stg;
+      stg.init(wbuf, lane);
       float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float sv[32], tv[32];
-        sm100::tmem_ld32x2(ts + c * 32, tt + c * 32, sv, tv);
-        const int e0 = half * 64 + c * 32;
-        uint32_t packed[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 nl = lds128(buf + e0 + j), nr = lds128(buf + 128 + e0 + j), cw = lds128(buf + 256 + e0 + j);
-          const float nls[4] = {nl.x, nl.y, nl.z, nl.w}, nrs[4] = {nr.x, nr.y, nr.z, nr.w}, cws[4] = {cw.x, cw.y, cw.z, cw.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float u = fmaf(sv[j + i], e.as2, nls[i]) + cs;
-            const float w = fmaf(tv[j + i], e.at2, nrs[i]) + ct;
-            const float pp = fast_ex2(u);
-            const float qq = fast_ex2(w);
-            const float cwq = cws[i] * qq;
-            const float g = fmaf(cws[i], pp, -cwq);
-            if (i & 1) { l1 = fmaf(cwq, u, l1); d1 += g; }
-            else { l0 = fmaf(cwq, u, l0); d0 += g; }
-            sv[j + i] = g;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(sv[2 * j], sv[2 * j + 1]);
-          packed[j] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        const int ent0 = tc.n_tile * BN + e0;
-        if (kok) {
-          __nv_bfloat16* o = e.gt + (int64_t)k * e.ldg + ent0;
-          if (ent0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(o + j * 8) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (ent0 + j < p.N) o[j] = __float2bfloat16_rn(sv[j]);
-          }
-        }
+      uint32_t sa[16], ta[16], sb[16], tb[16];
+      sm100::tmem_ld16_nowait(ts, sa);
+      sm100::tmem_ld16_nowait(tt, ta);
+      // the staging buffer about to be refilled must no longer be read by the store issued 2 tiles ago
+      if (lane == 0) sm100::tma_store_wait_read<kBufs - 1>();
+      __syncwarp();
+      sm100::tmem_wait_ld();
+      sm100::tmem_ld16_nowait(ts + 16, sb);
+      sm100::tmem_ld16_nowait(tt + 16, tb);
+      chunk16(e, sa, ta, cb, cs, ct, stg, 0, l0, l1, d0, d1);
+      sm100::tmem_wait_ld();
+      sm100::tmem_ld16_nowait(ts + 32, sa);
+      sm100::tmem_ld16_nowait(tt + 32, ta);
+      chunk16(e, sb, tb, cb + 16, cs, ct, stg, 1, l0, l1, d0, d1);
+      sm100::tmem_wait_ld();
+      sm100::tmem_ld16_nowait(ts + 48, sb);
+      sm100::tmem_ld16_nowait(tt + 48, tb);
+      chunk16(e, sa, ta, cb + 32, cs, ct, stg, 2, l0, l1, d0, d1);
+      sm100::tmem_wait_ld();
+      chunk16(e, sb, tb, cb + 48, cs, ct, stg, 3, l0, l1, d0, d1);
+      // G tile rows [k0, k0+32) x entries [ent0, ent0+64) leave as one TMA store (clipped at K and E)
+      sm100::fence_proxy_async_smem();
+      __syncwarp();
+      const int ent0 = tc.n_tile * BN + half * 64;
+      if (lane == 0 && k0 < p.M && ent0 < p.N) {
+        sm100::tma_store_3d(tmC, wbuf, ent0, k0, 0);
+        sm100::tma_store_commit();
       }
+      st.flip ^= 1;
       if (kok) {
         if (e.db2_partial) e.db2_partial[(int64_t)(tc.n_tile * 2 + half) * p.M + k] = d0 + d1;
         if (alt) st.loss_b += l0 + l1; else st.loss_a += l0 + l1;
@@ -321,6 +468,7 @@ struct EpiGradT {
 // scripts/phase5_big_run.py:727 (bmm) + :738 (mse_loss) fused.
 // =============================================================================================
 struct EpiGramDiff {
+  static constexpr bool kUsesTmaStore = false;
   static constexpr int kEpiWarps = 8;
   static constexpr int kEpiSmemBytes = 0;
   struct Params {
@@ -338,8 +486,8 @@ struct EpiGramDiff {
   template <int BN>
   struct Impl {
     static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
-    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int t, uint32_t tmem_acc,
-                                                int, int epi_warp, int lane, uint8_t*, State& st) {
+    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap*,
+                                                uint32_t tmem_acc, int, int epi_warp, int lane, uint8_t*, State& st) {
       static_assert(BN == 128, "EpiGramDiff is written for 128-wide tiles");
       const int q = epi_quarter();
       const int half = epi_warp >> 2;
@@ -412,14 +560,17 @@ __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, 
 // =============================================================================================
 template <int BN, class Epi>
 struct EpiAdapter {
+  static constexpr bool kUsesTmaStore = Epi::kUsesTmaStore;
   static constexpr int kEpiWarps = Epi::kEpiWarps;
+  static constexpr int kEpiSmemBytes = Epi::kEpiSmemBytes;
   using Params = typename Epi::Params;
   using State = typename Epi::State;
   static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int a, int w, int l, uint8_t* s) {
     Epi::template Impl<BN>::prologue(e, p, tc, a, w, l, s);
   }
-  static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, int t, uint32_t tm, int a, int w, int l, uint8_t* s, State& st) {
-    Epi::template Impl<BN>::tile(e, p, tc, t, tm, a, w, l, s, st);
+  static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap* tmC,
+                                              uint32_t tm, int a, int w, int l, uint8_t* s, State& st) {
+    Epi::template Impl<BN>::tile(e, p, tc, tmC, tm, a, w, l, s, st);
   }
   static __device__ __forceinline__ void finish(const Params& e, const CoreParams& p, int w, int l, State& st) {
     Epi::finish(e, p, w, l, st);
@@ -430,9 +581,9 @@ template <int BN, int NSPLIT, int NSUB, int CL, class Epi>
 __global__ void __launch_bounds__((2 + Epi::kEpiWarps) * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
             const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-            const CoreParams p, const typename Epi::Params ep) {
+            const __grid_constant__ CUtensorMap tmC, const CoreParams p, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
-  gemm_body<BN, NSPLIT, NSUB, CL, EpiAdapter<BN, Epi>>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, smem_raw);
+  gemm_body<BN, NSPLIT, NSUB, CL, EpiAdapter<BN, Epi>>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, &tmC, smem_raw);
 }
 
 // number of CTAs for `tiles` super tiles of a CL-cluster kernel: one CTA per SM, whole clusters
@@ -451,6 +602,13 @@ struct Operand {
   int64_t batch_stride = 0;  // elements between consecutive problems (batched launches)
 };
 
+// output of the TMA-store epilogues: (slabs, M, N) with leading dimension ld and slab stride
+struct OutDesc {
+  void* ptr = nullptr;
+  int is_bf16 = 0;
+  int64_t ld = 0, slab_stride = 0, slabs = 1;
+};
+
 static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int tile_rows, int64_t batches, const char* what) {
   if (batches > 1) {
     if (!o.mn_major) return make_tmap_bf16_3d(tm, o.ptr, batches, o.rows, K, o.ld, o.batch_stride, tile_rows, what);
@@ -462,14 +620,15 @@ static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int t
 
 template <int BN, int NSPLIT, int NSUB, int CL, class Epi>
 static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const Operand* b1, int64_t M, int64_t N,
-                  int64_t K, int m_fastest, const typename Epi::Params& ep, cudaStream_t stream, const char* name,
-                  int64_t batches = 1) {
+                  int64_t K, int m_fastest, const typename Epi::Params& ep, const OutDesc& od, cudaStream_t stream,
+                  const char* name, int64_t batches = 1, int64_t splits = 1) {
   DINOX_REQUIRE(M > 0 && N > 0 && K > 0, DINOX_E_BADARG, "%s: empty problem", name);
   DINOX_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), DINOX_E_BADARG, "%s: dimension too large", name);
   DINOX_REQUIRE(batches >= 1 && batches < (1 << 20), DINOX_E_BADARG, "%s: bad batch count", name);
+  DINOX_REQUIRE(splits >= 1 && (splits == 1 || batches == 1), DINOX_E_BADARG, "%s: split-K cannot be batched", name);
   DINOX_REQUIRE(!(b0.mn_major && ((BN / NSPLIT / CL) % 64) != 0), DINOX_E_UNSUPPORTED,
                 "%s: MN-major B needs 64-element atoms per CTA at this tile shape", name);
-  CUtensorMap tA0, tB0, tA1, tB1;
+  CUtensorMap tA0, tB0, tA1, tB1, tC;
   int rc;
   if ((rc = make_operand_tmap(&tA0, a0, K, BM, batches, "A"))) return rc;
   if ((rc = make_operand_tmap(&tB0, b0, K, BN / NSPLIT / CL, batches, "B"))) return rc;   // one box per (N sub-tile, CTA)
@@ -480,6 +639,11 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
     if ((rc = make_operand_tmap(&tA1, *a1, K, BM, batches, "A1"))) return rc;
     if ((rc = make_operand_tmap(&tB1, *b1, K, BN / NSPLIT / CL, batches, "B1"))) return rc;
   }
+  tC = tA0;
+  if (Epi::kUsesTmaStore) {
+    DINOX_REQUIRE(od.ptr, DINOX_E_BADARG, "%s: output descriptor missing", name);
+    if ((rc = make_tmap_out_3d(&tC, od.ptr, od.is_bf16 != 0, od.slabs, M, N, od.ld, od.slab_stride, "C"))) return rc;
+  }
   CoreParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.num_m_tiles = (int)((M + BM - 1) / BM);
@@ -487,14 +651,19 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   p.num_k_blocks = (int)((K + BK - 1) / BK);
   p.a_mn_major = a0.mn_major; p.b_mn_major = b0.mn_major; p.m_fastest = m_fastest;
   p.batches = (int)batches;
+  p.splits = (int)splits;
+  p.kb_per_split = (int)((p.num_k_blocks + splits - 1) / splits);
+  DINOX_REQUIRE(splits == 1 || (int64_t)p.kb_per_split * (splits - 1) < p.num_k_blocks, DINOX_E_BADARG,
+                "%s: %lld splits leave an empty K range", name, (long long)splits);
   auto kern = gemm_kernel<BN, NSPLIT, NSUB, CL, Epi>;
   constexpr int smem = smem_bytes<BN, CL, Epi>();
+  static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
     DINOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int64_t super = (int64_t)((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * batches;
+  const int64_t super = (int64_t)((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * (splits > 1 ? splits : batches);
   DINOX_REQUIRE(super < (1ll << 31), DINOX_E_BADARG, "%s: too many tiles", name);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)launch_grid(super, CL));
@@ -506,7 +675,7 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA0, tB0, tA1, tB1, p, ep);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA0, tB0, tA1, tB1, tC, p, ep);
   if (e != cudaSuccess) {
     set_error("%s: cudaLaunchKernelEx failed: %s", name, cudaGetErrorString(e));
     return DINOX_E_CUDA;
@@ -514,30 +683,59 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   return check_launch(name, stream);
 }
 
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 // CTA-pair (cta_group::2) mode can be switched per process for A/B measurements: DINOX_PAIR=0|1
 static bool pair_enabled() {
   static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DINOX_PAIR");
-    v = e ? (atoi(e) != 0) : 0;
-  }
+  if (v < 0) v = env_flag("DINOX_PAIR", 0) != 0;
   return v != 0;
 }
 
 // tile-shape dispatch of the plain GEMM: widest tile without N waste; clusters of 2 share the B tile
-static int launch_store(int64_t M, int64_t N, bool b_mn, const Operand& a, const Operand& b, int64_t K, int m_fastest,
-                        const EpiStore::Params& ep, cudaStream_t stream, int64_t batches) {
+struct StoreArgs {
+  void* out;
+  int64_t ldo;
+  int out_bf16, accumulate;
+  float alpha;
+  const float* alpha_dev;
+  const float* bias_n;
+  int64_t slab_stride;   // output elements between batches / splits
+};
+
+template <class Epi>
+static int launch_store_t(int64_t M, int64_t N, const Operand& a, const Operand& b, int64_t K, int m_fastest,
+                          const typename Epi::Params& ep, const OutDesc& od, cudaStream_t stream, int64_t batches,
+                          int64_t splits) {
   const bool cl2 = M > BM && pair_enabled();   // a single M tile has nobody to pair with
   if (N % 384 == 0) {
-    return cl2 ? launch<384, 3, 1, 2, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<384,pair>", batches)
-               : launch<384, 3, 1, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<384>", batches);
+    return cl2 ? launch<384, 3, 1, 2, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<384,pair>", batches, splits)
+               : launch<384, 3, 1, 1, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<384>", batches, splits);
   }
   if (N % 256 == 0 || N > 2048) {
-    return cl2 ? launch<256, 1, 1, 2, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<256,cl2>", batches)
-               : launch<256, 1, 1, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<256>", batches);
+    return cl2 ? launch<256, 1, 1, 2, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<256,pair>", batches, splits)
+               : launch<256, 1, 1, 1, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<256>", batches, splits);
   }
-  return cl2 ? launch<128, 1, 1, 2, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<128,cl2>", batches)
-             : launch<128, 1, 1, 1, EpiStore>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, stream, "gemm_bf16<128>", batches);
+  return cl2 ? launch<128, 1, 1, 2, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<128,pair>", batches, splits)
+             : launch<128, 1, 1, 1, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<128>", batches, splits);
+}
+
+static int launch_store(int64_t M, int64_t N, const Operand& a, const Operand& b, int64_t K, int m_fastest,
+                        const StoreArgs& sa, cudaStream_t stream, int64_t batches, int64_t splits) {
+  static int direct = -1;
+  if (direct < 0) direct = env_flag("DINOX_DIRECT_STORE", 0);
+  if ((sa.out_bf16 && sa.accumulate) || direct) {
+    DINOX_REQUIRE(splits == 1, DINOX_E_UNSUPPORTED, "gemm_bf16: split-K needs the TMA-store epilogue");
+    EpiStoreDirect::Params ep{sa.out, sa.ldo, sa.out_bf16, sa.accumulate, sa.alpha, sa.alpha_dev, sa.bias_n, sa.slab_stride};
+    return launch_store_t<EpiStoreDirect>(M, N, a, b, K, m_fastest, ep, OutDesc{}, stream, batches, 1);
+  }
+  EpiStore::Params ep{sa.out_bf16, sa.accumulate, sa.alpha, sa.alpha_dev, sa.bias_n};
+  OutDesc od;
+  od.ptr = sa.out; od.is_bf16 = sa.out_bf16; od.ld = sa.ldo; od.slab_stride = sa.slab_stride;
+  od.slabs = splits > 1 ? splits : batches;
+  return launch_store_t<EpiStore>(M, N, a, b, K, m_fastest, ep, od, stream, batches, splits);
 }
 
 }  // namespace gemm
@@ -547,20 +745,60 @@ extern "C" {
 using namespace dinox;
 using namespace dinox::gemm;
 
+static int gemm_common_checks(const void* A, const void* B, void* C, int64_t N, int64_t ldc, int out_dtype, const char* name) {
+  DINOX_REQUIRE(A && B && C, DINOX_E_BADARG, "%s: null pointer", name);
+  DINOX_REQUIRE(out_dtype == DINOX_F32 || out_dtype == DINOX_BF16, DINOX_E_BADARG, "%s: out dtype must be f32 or bf16", name);
+  DINOX_REQUIRE(aligned16(C) && (ldc * (out_dtype == DINOX_F32 ? 4 : 2)) % 16 == 0, DINOX_E_ALIGN,
+                "%s: C / ldc not 16-byte aligned", name);
+  DINOX_REQUIRE(ldc >= N, DINOX_E_BADARG, "%s: ldc < N", name);
+  return require_sm100();
+}
+
 int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                     int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int out_dtype, int accumulate,
                     float alpha, const float* alpha_dev, const float* bias_n, int m_fastest,
                     dinox_stream_t stream) {
-  DINOX_REQUIRE(A && B && C, DINOX_E_BADARG, "gemm_bf16: null pointer");
-  DINOX_REQUIRE(out_dtype == DINOX_F32 || out_dtype == DINOX_BF16, DINOX_E_BADARG, "gemm_bf16: out dtype must be f32 or bf16");
-  DINOX_REQUIRE(aligned16(C) && (ldc * (out_dtype == DINOX_F32 ? 4 : 2)) % 16 == 0, DINOX_E_ALIGN,
-                "gemm_bf16: C / ldc not 16-byte aligned");
-  DINOX_REQUIRE(ldc >= N, DINOX_E_BADARG, "gemm_bf16: ldc < N");
-  int rc = require_sm100();
+  int rc = gemm_common_checks(A, B, C, N, ldc, out_dtype, "gemm_bf16");
   if (rc) return rc;
   Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
-  EpiStore::Params ep{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, bias_n, 0};
-  return launch_store(M, N, b_mn_major != 0, a, b, K, m_fastest, ep, stream, 1);
+  StoreArgs sa{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, bias_n, 0};
+  return launch_store(M, N, a, b, K, m_fastest, sa, stream, 1, 1);
+}
+
+int dinox_gemm_bf16_splitk(const void* A, const void* B, float* C_partials, int64_t M, int64_t N, int64_t K,
+                           int64_t lda, int64_t ldb, int64_t ldc, int64_t split_stride, int splits, int a_mn_major,
+                           int b_mn_major, float alpha, const float* alpha_dev, int m_fastest,
+                           dinox_stream_t stream) {
+  int rc = gemm_common_checks(A, B, C_partials, N, ldc, DINOX_F32, "gemm_bf16_splitk");
+  if (rc) return rc;
+  DINOX_REQUIRE(splits >= 1 && splits <= 64, DINOX_E_BADARG, "gemm_bf16_splitk: splits must be in [1, 64]");
+  DINOX_REQUIRE(split_stride >= M * ldc && (split_stride * 4) % 16 == 0, DINOX_E_BADARG,
+                "gemm_bf16_splitk: split_stride smaller than one (M, ldc) slab or misaligned");
+  Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
+  StoreArgs sa{C_partials, ldc, 0, 0, alpha, alpha_dev, nullptr, split_stride};
+  return launch_store(M, N, a, b, K, m_fastest, sa, stream, 1, splits);
+}
+
+int dinox_gemm_splitk_plan(int64_t M, int64_t N, int64_t K) {
+  // number of K splits that fills whole waves of the persistent grid (one CTA per SM) for a GEMM
+  // with few output tiles and a long reduction; 1 when the tile count already fills the machine
+  if (M <= 0 || N <= 0 || K <= 0) return 1;
+  const int64_t bn = (N % 384 == 0) ? 384 : ((N % 256 == 0 || N > 2048) ? 256 : 128);
+  const int64_t tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  const int64_t kb = (K + 63) / 64;
+  const int sms = num_sms();
+  if (tiles >= 3 * (int64_t)sms || kb < 16) return 1;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 32 && s * 8 <= kb; ++s) {
+    const int64_t kbs = (kb + s - 1) / s;
+    if (kbs * (s - 1) >= kb) continue;                  // an empty last split
+    const int64_t waves = (tiles * s + sms - 1) / sms;
+    // time ~ waves * (k-blocks per split + fixed per-tile epilogue cost in k-block units)
+    const double cost = (double)waves * ((double)kbs + 6.0);
+    if (cost < best_cost * 0.97) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 size_t dinox_head_stats_workspace_bytes(int64_t rows, int64_t K) {
@@ -577,8 +815,8 @@ int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int
   if (rc) return rc;
   Operand a{H, rows, ldh, 0}, b{W2, K, ldw, 0};
   EpiStats::Params ep{inv_tau * DINOX_LOG2E, col2, reinterpret_cast<float2*>(workspace)};
-  rc = (rows > BM && pair_enabled()) ? launch<256, 1, 1, 2, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, stream, "head_stats<cl2>")
-                 : launch<256, 1, 1, 1, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, stream, "head_stats");
+  rc = (rows > BM && pair_enabled()) ? launch<256, 1, 1, 2, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats<pair>")
+                 : launch<256, 1, 1, 1, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats");
   if (rc) return rc;
   const int n_part = 2 * (int)((K + 255) / 256);
   stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows, n_part,
@@ -608,12 +846,13 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
   ep.as2 = inv_tau_s * DINOX_LOG2E; ep.at2 = inv_tau_t * DINOX_LOG2E; ep.inv_tau_s = inv_tau_s;
   ep.cs2 = cs2; ep.ct2 = ct2; ep.ct2_alt = ct2_alt; ep.alt_from = (int)alt_from;
   ep.lse2 = lse2_e; ep.rb2 = rb2_e; ep.cw = cw_e;
-  ep.gt = reinterpret_cast<__nv_bfloat16*>(Gt); ep.ldg = ldg;
   ep.db2_partial = db2_partial; ep.loss_partial = reinterpret_cast<float*>(workspace);
+  OutDesc od;
+  od.ptr = Gt; od.is_bf16 = 1; od.ld = ldg; od.slab_stride = K * ldg; od.slabs = 1;
   // entry tiles fastest: the 2 x (K-tile of W2) operands stay put while HsE/HtE (L2-resident) stream
   const bool cl2 = K > BM && pair_enabled();
-  rc = cl2 ? launch<128, 1, 2, 2, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, stream, "head_grad<cl2>")
-           : launch<128, 1, 2, 1, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, stream, "head_grad");
+  rc = cl2 ? launch<128, 1, 2, 2, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, od, stream, "head_grad<pair>")
+           : launch<128, 1, 2, 1, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, od, stream, "head_grad");
   if (rc) return rc;
   const int cl = cl2 ? 2 : 1;
   const int grid = launch_grid((((K + 127) / 128 + cl - 1) / cl) * ((E + 127) / 128), cl);
@@ -625,16 +864,14 @@ int dinox_gemm_bf16_batched(const void* A, const void* B, void* C, int64_t batch
                             int64_t lda, int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c,
                             int a_mn_major, int b_mn_major, int out_dtype, int accumulate, float alpha,
                             const float* alpha_dev, dinox_stream_t stream) {
-  DINOX_REQUIRE(A && B && C && batches >= 1, DINOX_E_BADARG, "gemm_bf16_batched: bad arguments");
-  DINOX_REQUIRE(out_dtype == DINOX_F32 || out_dtype == DINOX_BF16, DINOX_E_BADARG, "gemm_bf16_batched: out dtype must be f32 or bf16");
-  const int es = out_dtype == DINOX_F32 ? 4 : 2;
-  DINOX_REQUIRE(aligned16(C) && (ldc * es) % 16 == 0 && (stride_c * es) % 16 == 0 && ldc >= N, DINOX_E_ALIGN,
-                "gemm_bf16_batched: C / ldc / stride_c misaligned");
-  int rc = require_sm100();
+  DINOX_REQUIRE(batches >= 1, DINOX_E_BADARG, "gemm_bf16_batched: bad arguments");
+  int rc = gemm_common_checks(A, B, C, N, ldc, out_dtype, "gemm_bf16_batched");
   if (rc) return rc;
+  const int es = out_dtype == DINOX_F32 ? 4 : 2;
+  DINOX_REQUIRE((stride_c * es) % 16 == 0, DINOX_E_ALIGN, "gemm_bf16_batched: stride_c misaligned");
   Operand a{A, M, lda, a_mn_major ? 1 : 0, stride_a}, b{B, N, ldb, b_mn_major ? 1 : 0, stride_b};
-  EpiStore::Params ep{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, nullptr, stride_c};
-  return launch_store(M, N, b_mn_major != 0, a, b, K, 1, ep, stream, batches);
+  StoreArgs sa{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, nullptr, stride_c};
+  return launch_store(M, N, a, b, K, 1, sa, stream, batches, 1);
 }
 
 size_t dinox_gram_diff_workspace_bytes(int64_t batches, int64_t tokens) {
@@ -652,7 +889,7 @@ int dinox_gram_diff(const void* xn_s, const void* xn_t, int64_t batches, int64_t
   // a single image still goes through the 3-D path (batches = 1 uses 2-D maps over (tokens, D))
   Operand a0{xn_s, tokens, D, 0, tokens * D}, a1{xn_t, tokens, D, 0, tokens * D};
   EpiGramDiff::Params ep{reinterpret_cast<__nv_bfloat16*>(delta), ldd, tokens * ldd, reinterpret_cast<float*>(workspace)};
-  rc = launch<128, 1, 2, 1, EpiGramDiff>(a0, a0, &a1, &a1, tokens, tokens, D, 1, ep, stream, "gram_diff", batches);
+  rc = launch<128, 1, 2, 1, EpiGramDiff>(a0, a0, &a1, &a1, tokens, tokens, D, 1, ep, OutDesc{}, stream, "gram_diff", batches);
   if (rc) return rc;
   const int64_t mt = (tokens + 127) / 128;
   sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)launch_grid(batches * mt * mt, 1) * 8,

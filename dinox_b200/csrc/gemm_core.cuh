@@ -19,7 +19,7 @@ constexpr int UMMA_K = 16;
 constexpr int kFirstEpiWarp = 2;
 
 struct TileCoord {
-  int m_tile, n_tile, batch;
+  int m_tile, n_tile, batch, split;
 };
 
 struct CoreParams {
@@ -28,28 +28,62 @@ struct CoreParams {
   int a_mn_major, b_mn_major;  // operand layouts in global memory
   int m_fastest;               // tile order: consecutive CTAs walk M (1) or N (0)
   int batches;                 // > 1: independent problems along a third tensor-map dimension
+  int splits;                  // > 1: split-K, split s reduces k-blocks [s*kb_per_split, ...) into output slab s
+  int kb_per_split;
 };
 
-template <int BN, int CL = 1>
+template <int BN, int CL, int EPI_SMEM>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
   static constexpr int kBBytes = (BN / CL) * BK * 2;   // a CTA of a pair holds 1/CL of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBudget = 196 * 1024;
+  static constexpr int kEpiBytes = (EPI_SMEM + 1023) / 1024 * 1024;
+  // 227 KB per CTA minus alignment slack (1 KB), control block (256 B) and the epilogue's staging area
+  static constexpr int kBudget = 227 * 1024 - 1024 - 256 - kEpiBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static_assert(kStages >= 2, "tile too large for the smem pipeline");
   static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kTotal = kPipeBytes + kEpiBytes + 256 + 1024;
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const CoreParams& p, int t) {
-  TileCoord c;
-  const int per = p.num_m_tiles * p.num_n_tiles;
-  c.batch = t / per;
-  t -= c.batch * per;
-  if (p.m_fastest) { c.m_tile = t % p.num_m_tiles; c.n_tile = t / p.num_m_tiles; }
-  else { c.n_tile = t % p.num_n_tiles; c.m_tile = t / p.num_n_tiles; }
-  return c;
-}
+// Walks the tile indices cid, cid + ncl, cid + 2 ncl, ... of a persistent CTA without a division per
+// tile: the stride is decomposed once into (fast, slow, outer) digits and added with carries.
+// Digit order: fast = M tiles (m_fastest) or N tiles, slow = the other, outer = batch / split.
+struct TileWalker {
+  int fast, slow, outer;
+  int dfast, dslow, douter;
+  int nfast, nslow;
+  int remaining;
+  bool m_fastest;
+  __device__ __forceinline__ void init(const CoreParams& p, int num_m_super, int first, int stride, int total) {
+    m_fastest = p.m_fastest != 0;
+    nfast = m_fastest ? num_m_super : p.num_n_tiles;
+    nslow = m_fastest ? p.num_n_tiles : num_m_super;
+    fast = first % nfast; int t = first / nfast; slow = t % nslow; outer = t / nslow;
+    dfast = stride % nfast; t = stride / nfast; dslow = t % nslow; douter = t / nslow;
+    remaining = first < total ? (total - first + stride - 1) / stride : 0;
+  }
+  __device__ __forceinline__ bool valid() const { return remaining > 0; }
+  __device__ __forceinline__ void next() {
+    --remaining;
+    fast += dfast;
+    int carry = 0;
+    if (fast >= nfast) { fast -= nfast; carry = 1; }
+    slow += dslow + carry;
+    carry = 0;
+    if (slow >= nslow) { slow -= nslow; carry = 1; }
+    outer += douter + carry;
+  }
+  // CL-wide super tile -> this CTA's tile
+  __device__ __forceinline__ TileCoord coord(const CoreParams& p, int cl, int crank) const {
+    TileCoord c;
+    c.m_tile = (m_fastest ? fast : slow) * cl + crank;
+    c.n_tile = m_fastest ? slow : fast;
+    c.batch = p.splits > 1 ? 0 : outer;
+    c.split = p.splits > 1 ? outer : 0;
+    return c;
+  }
+};
 
 struct PipeState {
   int stage = 0;
@@ -84,13 +118,14 @@ __device__ __forceinline__ float fast_ex2(float x) {
 //                for both; each CTA's epilogue drains the 128 rows that live in its own TMEM.  This
 //                halves the B-operand bytes every SM pulls from L2 per FLOP - the K<=1024 GEMMs of
 //                the loss head are bound by L2->SMEM operand traffic, not by the tensor pipe.
-// `Epi` provides kEpiWarps, Params, State, prologue(), tile(), finish().
+// `Epi` provides kEpiWarps, kEpiSmemBytes, Params, State, prologue(), tile(), finish().
+// `tmC` is the output tensor map of epilogues that store through TMA (others ignore it).
 template <int BN, int NSPLIT, int NSUB, int CL, class Epi>
 __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Epi::Params& ep,
                                           const CUtensorMap* tmA0, const CUtensorMap* tmB0,
                                           const CUtensorMap* tmA1, const CUtensorMap* tmB1,
-                                          uint8_t* smem_raw) {
-  using L = SmemLayout<BN, CL>;
+                                          const CUtensorMap* tmC, uint8_t* smem_raw) {
+  using L = SmemLayout<BN, CL, Epi::kEpiSmemBytes>;
   constexpr int kStages = L::kStages;
   constexpr int BNI = BN / NSPLIT;                           // UMMA N
   constexpr int BNL = BNI / CL;                              // rows of one N sub-tile held by this CTA
@@ -104,11 +139,11 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
   static_assert(BNL % 8 == 0, "per-CTA B slice must be whole 8-row swizzle groups");
   constexpr bool kPair = (CL == 2);
 
-  // 1024-B aligned carve-up (swizzle-128B atoms need it)
+  // 1024-B aligned carve-up (swizzle-128B atoms need it): [pipeline stages][epilogue staging][control]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* pipe = smem;
-  SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem + L::kPipeBytes);
-  uint8_t* epi_smem = smem + L::kPipeBytes + 256;
+  uint8_t* epi_smem = smem + L::kPipeBytes;
+  SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem + L::kPipeBytes + L::kEpiBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,14 +152,14 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
   // pairs walk "super tiles" of CL adjacent M tiles; a ragged last M super tile computes on
   // zero-filled (out-of-bounds) rows and the epilogues mask it
-  CoreParams ps = p;
-  ps.num_m_tiles = (p.num_m_tiles + CL - 1) / CL;
-  const int num_super = ps.num_m_tiles * ps.num_n_tiles * ps.batches;
+  const int num_m_super = (p.num_m_tiles + CL - 1) / CL;
+  const int num_super = num_m_super * p.num_n_tiles * (p.splits > 1 ? p.splits : p.batches);
 
   if (warp == 0 && lane == 0) {
     sm100::prefetch_tmap(tmA0);
     sm100::prefetch_tmap(tmB0);
     if (NSUB == 2) { sm100::prefetch_tmap(tmA1); sm100::prefetch_tmap(tmB1); }
+    if (Epi::kUsesTmaStore) sm100::prefetch_tmap(tmC);
     for (int i = 0; i < kStages; ++i) { sm100::mbar_init(&ctl->full[i], 1); sm100::mbar_init(&ctl->empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&ctl->tmem_full[i], 1);
@@ -142,18 +177,22 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
   sm100::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
+  TileWalker walk;
+  walk.init(p, num_m_super, cid, ncl, num_super);
+
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====
     if (lane == 0) {
       PipeState st;
-      for (int u = cid; u < num_super; u += ncl) {
-        TileCoord tc = tile_coord(ps, u);
-        tc.m_tile = tc.m_tile * CL + crank;
+      for (; walk.valid(); walk.next()) {
+        const TileCoord tc = walk.coord(p, CL, crank);
         const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
+        const int kb0 = tc.split * p.kb_per_split;
+        const int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
         for (int sub = 0; sub < NSUB; ++sub) {
           const CUtensorMap* ma = sub ? tmA1 : tmA0;
           const CUtensorMap* mb = sub ? tmB1 : tmB0;
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             sm100::mbar_wait(&ctl->empty[st.stage], st.phase ^ 1, 1);
             uint8_t* sa = pipe + st.stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
@@ -210,12 +249,15 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
       PipeState st;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int u = cid; u < num_super; u += ncl) {
+      for (; walk.valid(); walk.next()) {
+        const TileCoord tc = walk.coord(p, CL, crank);
+        const int kb0 = tc.split * p.kb_per_split;
+        const int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
         sm100::mbar_wait(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, 2);
         sm100::tc_fence_after();
         for (int sub = 0; sub < NSUB; ++sub) {
           const uint32_t d_tmem = tmem_base + acc_stage * kAccCols + sub * BN;
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             sm100::mbar_wait(&ctl->full[st.stage], st.phase, 3);
             sm100::tc_fence_after();
             const uint32_t sa = sm100::smem_u32(pipe + st.stage * L::kStageBytes);
@@ -226,8 +268,8 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 #pragma unroll
               for (int h = 0; h < NSPLIT; ++h) {
                 const uint64_t db = sm100::umma_smem_desc(sb + h * b_split + k * b_adv, b_lbo, 1024);
-                if (kPair) sm100::umma_bf16_pair(d_tmem + h * BNI, da, db, idesc, (kb | k) != 0);
-                else sm100::umma_bf16(d_tmem + h * BNI, da, db, idesc, (kb | k) != 0);
+                if (kPair) sm100::umma_bf16_pair(d_tmem + h * BNI, da, db, idesc, (uint32_t)((kb != kb0) | (k != 0)));
+                else sm100::umma_bf16(d_tmem + h * BNI, da, db, idesc, (uint32_t)((kb != kb0) | (k != 0)));
               }
             }
             // frees the smem slot (in both CTAs of a pair) when these MMAs retire
@@ -249,13 +291,12 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     typename Epi::State state;
-    for (int u = cid; u < num_super; u += ncl) {
-      TileCoord tc = tile_coord(ps, u);
-      tc.m_tile = tc.m_tile * CL + crank;
+    for (; walk.valid(); walk.next()) {
+      const TileCoord tc = walk.coord(p, CL, crank);
       Epi::prologue(ep, p, tc, acc_stage, epi_warp, lane, epi_smem);
       sm100::mbar_wait(&ctl->tmem_full[acc_stage], acc_phase, 4);
       sm100::tc_fence_after();
-      Epi::tile(ep, p, tc, u, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
+      Epi::tile(ep, p, tc, tmC, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
       sm100::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -280,11 +321,31 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 
 template <int BN, int CL, class Epi>
 constexpr int smem_bytes() {
-  return SmemLayout<BN, CL>::kPipeBytes + 256 + Epi::kEpiSmemBytes + 1024 /* alignment slack */;
+  return SmemLayout<BN, CL, Epi::kEpiSmemBytes>::kTotal;
 }
 
 // lane quarter of TMEM this warp may read (hardware: warp_id % 4), and which column half it owns
 __device__ __forceinline__ int epi_quarter() { return (threadIdx.x >> 5) & 3; }
+
+// ---------------------------------------------------------------------------------------------------
+// Per-warp output staging for TMA stores: 32 rows x 128 B, SWIZZLE_128B (1024-B aligned, 4 KB).
+// Row r = lane; 16-byte piece j of the row lives at r*128 + ((j ^ (r & 7)) << 4): a quarter warp's
+// STS.128 of one logical piece covers all 32 banks -> conflict free, and it is exactly the layout
+// a SWIZZLE_128B tensor map reads.
+// ---------------------------------------------------------------------------------------------------
+struct WarpStage {
+  uint32_t base;   // shared-space address of this warp's 4 KB buffer
+  uint32_t row;    // base + lane*128
+  uint32_t sw;     // (lane & 7) << 4
+  __device__ __forceinline__ void init(uint8_t* buf, int lane) {
+    base = sm100::smem_u32(buf);
+    row = base + lane * 128;
+    sw = (lane & 7) << 4;
+  }
+  __device__ __forceinline__ void put(int piece, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + ((piece << 4) ^ sw)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  }
+};
 
 }  // namespace gemm
 }  // namespace dinox

@@ -566,7 +566,7 @@ class _FusedHeadLoss(torch.autograd.Function):
                                                                    alpha_dev=up))
         # dH per entry = G . W2  (A = Gt MN-major, B = W2 MN-major), then sum the entries of each row
         with ops.TIMER.region("gemm_dH"):
-            dh_e = ops.gemm_bf16(gt, w2s, a_mn_major=True, b_mn_major=True, m_fastest=True)
+            dh_e = ops.gemm_bf16_splitk(gt, w2s, a_mn_major=True, b_mn_major=True, m_fastest=True)
         dh = torch.empty(rows, D, dtype=torch.float32, device=gt.device)
         ops.gather_sum_rows(dh_e, plan.csr_ptr, plan.csr_ent, rows, dh)
         da, part = ops.gelu_bwd(dh, a_s, scale_dev=up)

@@ -189,6 +189,30 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_m
     return out
 
 
+def gemm_splitk_plan(M: int, N: int, K: int) -> int:
+    return int(_ext.lib().dinox_gemm_splitk_plan(M, N, K))
+
+
+def gemm_bf16_splitk(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False,
+                     splits: Optional[int] = None, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
+                     m_fastest: bool = True) -> torch.Tensor:
+    """Split-K GEMM: returns the (splits, M, N) fp32 partial slabs (sum over dim 0 = alpha * A @ B^T).
+    splits=None asks the library for the count that fills whole waves of the persistent grid."""
+    _chk_cuda(a, b, alpha_dev)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise _ext.DinoxError("gemm_bf16_splitk needs bf16 operands")
+    M, Ka = (a.shape[1], a.shape[0]) if a_mn_major else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn_major else b.shape
+    if Ka != Kb:
+        raise _ext.DinoxError(f"gemm_bf16_splitk: reduction dims differ ({Ka} vs {Kb})")
+    if splits is None:
+        splits = gemm_splitk_plan(M, N, Ka)
+    out = torch.empty(splits, M, N, dtype=torch.float32, device=a.device)
+    _ext.call("dinox_gemm_bf16_splitk", _p(a), _p(b), _p(out), M, N, Ka, _rowmajor(a), _rowmajor(b), N, M * N, splits,
+              int(a_mn_major), int(b_mn_major), float(alpha), _p(alpha_dev), int(m_fastest), _stream())
+    return out
+
+
 def head_stats(h: torch.Tensor, w2: torch.Tensor, inv_tau: float, col2: Optional[torch.Tensor] = None,
                want_nat: bool = True, want_log2: bool = True, out_log2: Optional[torch.Tensor] = None):
     """Row-wise LSE of (h @ w2^T)*inv_tau + col2/log2e without materialising the logits."""
@@ -321,7 +345,13 @@ def gemv_bf16(w: torch.Tensor, x: torch.Tensor, alpha: float = 1.0, bias: Option
 
 def gather_sum_rows(src: torch.Tensor, ptr: torch.Tensor, ent: torch.Tensor, rows: int, out: torch.Tensor,
                     scale: float = 1.0, scale_dev: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    _ext.call("dinox_gather_sum_rows", _p(src), _rowmajor(src), _p(ptr), _p(ent), rows, src.shape[1], _p(scale_dev),
+    """src: (E, D) fp32, or (S, E, D) split-K partial slabs that are summed as well."""
+    if src.dim() == 3:
+        slabs, slab_stride, ld, D = src.shape[0], src.stride(0), src.stride(1), src.shape[2]
+        assert src.stride(2) == 1
+    else:
+        slabs, slab_stride, ld, D = 1, 0, _rowmajor(src), src.shape[1]
+    _ext.call("dinox_gather_sum_rows", _p(src), ld, slabs, slab_stride, _p(ptr), _p(ent), rows, D, _p(scale_dev),
               float(scale), _p(out), _rowmajor(out), int(accumulate), _stream())
     return out
 

@@ -134,6 +134,17 @@ DINOX_API int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, 
                               int out_dtype, int accumulate, float alpha, const float* alpha_dev,
                               const float* bias_n, int m_fastest, dinox_stream_t stream);
 
+/* Split-K flavour for GEMMs with few output tiles and a long reduction (dH = G . W2: 67 tiles,
+ * K = 65536): split s reduces its share of K into the fp32 slab C_partials + s*split_stride;
+ * the caller sums the slabs in fixed order (dinox_gather_sum_rows does), so the result is
+ * deterministic.  dinox_gemm_splitk_plan() returns the split count that fills whole waves of
+ * the persistent one-CTA-per-SM grid (1 = do not split). */
+DINOX_API int dinox_gemm_bf16_splitk(const void* A, const void* B, float* C_partials, int64_t M, int64_t N,
+                                     int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t split_stride,
+                                     int splits, int a_mn_major, int b_mn_major, float alpha,
+                                     const float* alpha_dev, int m_fastest, dinox_stream_t stream);
+DINOX_API int dinox_gemm_splitk_plan(int64_t M, int64_t N, int64_t K);
+
 /* ------------------------------------------------------------------------------------------
  * Fused pass 1: prototype logits (H . W2^T, bf16 operands, fp32 TMEM accumulators) with the
  * row-wise online log-sum-exp of  u = logits*inv_tau + col2/log2e  computed in the GEMM epilogue;
@@ -219,10 +230,12 @@ DINOX_API int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int6
  * logits from the mean head activation, used for the centre update of the fused path (:686-690) */
 DINOX_API int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64_t D, float alpha,
                               const float* bias, float beta, float* out, dinox_stream_t stream);
-/* dst[r,:] (+)= scale*(*scale_dev) * sum_{i in [ptr[r],ptr[r+1])} src[ent[i],:]  (fp32) */
-DINOX_API int dinox_gather_sum_rows(const float* src, int64_t ld_src, const int64_t* ptr, const int64_t* ent,
-                                    int64_t rows, int64_t D, const float* scale_dev, float scale, float* dst,
-                                    int64_t ld_dst, int accumulate, dinox_stream_t stream);
+/* dst[r,:] (+)= scale*(*scale_dev) * sum_{i in [ptr[r],ptr[r+1])} sum_{s<slabs} src[s*slab_stride + ent[i]*ld_src,:]
+ * (fp32; slabs > 1 sums the partial outputs of dinox_gemm_bf16_splitk in fixed order) */
+DINOX_API int dinox_gather_sum_rows(const float* src, int64_t ld_src, int slabs, int64_t slab_stride,
+                                    const int64_t* ptr, const int64_t* ent, int64_t rows, int64_t D,
+                                    const float* scale_dev, float scale, float* dst, int64_t ld_dst,
+                                    int accumulate, dinox_stream_t stream);
 DINOX_API int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream);
 
 #ifdef __cplusplus

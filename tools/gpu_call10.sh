@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+bash tools/run_probes.sh gemm stats grad > gpurun_out/probes.log 2>&1
+grep -E "MISMATCH|EXC|Error|error|timeout|time |exit|ragged|guard|batched|split|dW2|dH|accumulate|bf16 out|alpha" gpurun_out/probes.log | head -70
+bash tools/gpu_quick.sh

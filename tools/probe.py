@@ -140,6 +140,57 @@ def g_gemm():
     acc = c0.to(dev).clone()
     ops.gemm_bf16(a.to(dev), b.to(dev), out=acc, accumulate=True, alpha=2.0, alpha_dev=torch.tensor([0.25], device=dev))
     print("gemm accumulate", relerr(acc.cpu(), c0 + 0.5 * (a.float() @ b.float().t())))
+    # ragged shapes through the TMA-store epilogue: fp32 / bf16 out, accumulate
+    for (M, N, K) in [(200, 200, 384), (300, 1000, 200), (129, 72, 64)]:
+        a = torch.randn(M, K, generator=g).to(torch.bfloat16); b = torch.randn(N, K, generator=g).to(torch.bfloat16)
+        ref = a.float() @ b.float().t()
+        ld = (N + 7) // 8 * 8
+        buf = torch.full((M + 3, ld + 8), 7.0, device=dev)
+        ops.gemm_bf16(a.to(dev), b.to(dev), out=buf[:M, :N])
+        ok_guard = bool((buf[M:] == 7).all() and (buf[:, N:] == 7).all())
+        print(f"gemm ragged f32 M={M} N={N} K={K}", relerr(buf[:M, :N].cpu(), ref), "guard", ok_guard)
+        ops.gemm_bf16(a.to(dev), b.to(dev), out=buf[:M, :N], accumulate=True, alpha=-1.0)
+        print(f"   accumulate -> ~0: max {buf[:M, :N].abs().max().item():.3e} guard", bool((buf[M:] == 7).all() and (buf[:, N:] == 7).all()))
+        bb = torch.full((M + 3, ld + 8), 7.0, device=dev, dtype=torch.bfloat16)
+        ops.gemm_bf16(a.to(dev), b.to(dev), out=bb[:M, :N])
+        print(f"   bf16 out", relerr(bb[:M, :N].float().cpu(), ref), "guard", bool((bb[M:] == 7).all() and (bb[:, N:] == 7).all()))
+    # batched (Gram shapes) and split-K
+    Bt, T, D = 5, 200, 384
+    x = torch.randn(Bt, T, D, generator=g).to(torch.bfloat16)
+    ref = torch.bmm(x.float(), x.float().transpose(1, 2))
+    out = ops.gemm_bf16_batched(x.to(dev), x.to(dev))
+    print("gemm batched f32", relerr(out.cpu(), ref))
+    outb = ops.gemm_bf16_batched(x.to(dev), x.to(dev), out_dtype=torch.bfloat16)
+    print("gemm batched bf16", relerr(outb.float().cpu(), ref))
+    for (M, N, K, S) in [(256, 384, 4096, 3), (200, 384, 8000, 7), (384, 384, 8064, None)]:
+        a = torch.randn(K, M, generator=g).to(torch.bfloat16); b = torch.randn(K, N, generator=g).to(torch.bfloat16)
+        ref = a.float().t() @ b.float()
+        parts = ops.gemm_bf16_splitk(a.to(dev), b.to(dev), a_mn_major=True, b_mn_major=True, splits=S)
+        print(f"gemm split-K M={M} N={N} K={K} splits={parts.shape[0]}", relerr(parts.sum(0).cpu(), ref))
+    # the two backward GEMMs of the prototype layer at C2 shapes
+    E, Kp, D = 8576, 65536, 384
+    gt = (torch.randn(Kp, E, device=dev) * 0.01).to(torch.bfloat16)
+    hs = torch.randn(E, D, device=dev).to(torch.bfloat16)
+    w2 = (torch.randn(Kp, D, device=dev) / math.sqrt(D)).to(torch.bfloat16)
+    w2g = torch.zeros(Kp, D, device=dev)
+    def timeit(fn, n=5):
+        for _ in range(2): fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n): fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    ms = timeit(lambda: ops.gemm_bf16(gt, hs, b_mn_major=True, out=w2g, accumulate=True, m_fastest=False))
+    print(f"dW2 (K,E)x(E,D) accumulate: {ms:.3f} ms {2*E*Kp*D/ms/1e9:.1f} TF/s")
+    ms = timeit(lambda: ops.gemm_bf16(gt, w2, a_mn_major=True, b_mn_major=True, m_fastest=True))
+    print(f"dH unsplit: {ms:.3f} ms {2*E*Kp*D/ms/1e9:.1f} TF/s")
+    for S in (2, 5, 11, 13):
+        ms = timeit(lambda: ops.gemm_bf16_splitk(gt, w2, a_mn_major=True, b_mn_major=True, splits=S))
+        print(f"dH split-K {S}: {ms:.3f} ms {2*E*Kp*D/ms/1e9:.1f} TF/s")
+    ref = (gt[:, :256].float().t() @ w2.float())
+    parts = ops.gemm_bf16_splitk(gt, w2, a_mn_major=True, b_mn_major=True)
+    print("dH split-K parity (first 256 rows)", relerr(parts.sum(0)[:256].cpu(), ref.cpu()), "splits", parts.shape[0])
+    del gt, hs, w2, w2g, parts
     # timing
     for (M, N, K) in [(8192, 8192, 8192), (8064, 65536, 384), (65536, 384, 8576)]:
         a = torch.randn(M, K, device=dev).to(torch.bfloat16); b = torch.randn(N, K, device=dev).to(torch.bfloat16)
