@@ -16,8 +16,11 @@ from typing import List, Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libdinox_b200.so")
-BUILD_DIR = os.path.join(HERE, "build")
+# Experiment variants (tools/ only): DINOX_LIB_TAG=<tag> loads / builds libdinox_b200_<tag>.so, compiled
+# with the extra -D flags given to build(extra_flags=...).  The product library has no tag.
+_TAG = os.environ.get("DINOX_LIB_TAG", "")
+LIB_PATH = os.path.join(HERE, f"libdinox_b200{'_' + _TAG if _TAG else ''}.so")
+BUILD_DIR = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -47,8 +50,9 @@ def _stale(target: str, deps: List[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags: Optional[List[str]] = None) -> str:
     """Compile every .cu under csrc/ for sm_100a and link libdinox_b200.so (in-tree)."""
+    extra_flags = list(extra_flags or [])
     os.makedirs(BUILD_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "dinox_b200.h"))
@@ -59,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src, obj = args
         if not force and not _stale(obj, [src] + headers):
             return ""
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + extra_flags + ["-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -134,10 +138,12 @@ SIGNATURES = {
     "dinox_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                        c_int, c_int, c_int, c_f32, c_void_p, c_int, c_void_p]),
     "dinox_gemm_splitk_plan": (c_int, [c_i64, c_i64, c_i64]),
+    "dinox_debug_max_active_clusters": (c_int, [c_int]),
     "dinox_head_stats_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_head_stats": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     "dinox_head_grad_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_head_grad_db2_rows": (c_i64, [c_i64]),
     "dinox_head_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_f32, c_f32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_i64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -42,7 +42,8 @@ struct EpiStore {
   }
   template <int BN>
   struct Impl {
-    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
+    static __device__ __forceinline__ void fetch(const Params&, const CoreParams&, TileCoord, int, int, State&) {}
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*, State&) {}
 
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap* tmC,
                                                 uint32_t tmem_acc, int, int epi_warp, int lane, uint8_t* smem, State& st) {
@@ -61,6 +62,7 @@ struct EpiStore {
         uint32_t (&cur)[32] = (c & 1) ? rb : ra;
         uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
         if (c + 1 < kChunks) sm100::tmem_ld32_nowait(taddr + (c + 1) * 32, nxt);
+        sm100::pin32(cur);
         const int col0 = tc.n_tile * BN + c * 32;
         float v[32];
 #pragma unroll
@@ -99,8 +101,11 @@ struct EpiStore {
           if (!first || c + 1 == kChunks) {
             sm100::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && row0 < p.M && col0 - (first ? 0 : 32) < p.N) {
-              sm100::tma_store_3d(tmC, wbuf, col0 - (first ? 0 : 32), row0, slab);
+            // the group is committed even when the box is entirely out of range: wait_read<kBufs-1>
+            // counts groups, so a skipped commit would let the NEXT chunk overwrite a buffer whose
+            // store (from the previous tile) is still being read
+            if (lane == 0) {
+              if (row0 < p.M && col0 - (first ? 0 : 32) < p.N) sm100::tma_store_3d(tmC, wbuf, col0 - (first ? 0 : 32), row0, slab);
               sm100::tma_store_commit();
             }
             st.flip ^= 1;
@@ -116,10 +121,12 @@ struct EpiStore {
                     __float_as_uint(v[4 * j + 3]));
           sm100::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && col0 < p.N) {
-            if (e.accumulate) sm100::tma_reduce_add_3d(tmC, wbuf, col0, row0, slab);
-            else sm100::tma_store_3d(tmC, wbuf, col0, row0, slab);
-            sm100::tma_store_commit();
+          if (lane == 0) {
+            if (row0 < p.M && col0 < p.N) {
+              if (e.accumulate) sm100::tma_reduce_add_3d(tmC, wbuf, col0, row0, slab);
+              else sm100::tma_store_3d(tmC, wbuf, col0, row0, slab);
+            }
+            sm100::tma_store_commit();   // always: see the bf16 branch
           }
           st.flip ^= 1;
         }
@@ -151,7 +158,8 @@ struct EpiStoreDirect {
   static __device__ __forceinline__ void finish(const Params&, const CoreParams&, int, int, State&) {}
   template <int BN>
   struct Impl {
-    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
+    static __device__ __forceinline__ void fetch(const Params&, const CoreParams&, TileCoord, int, int, State&) {}
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*, State&) {}
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap*,
                                                 uint32_t tmem_acc, int, int, int lane, uint8_t*, State&) {
       const int q = epi_quarter();
@@ -227,43 +235,56 @@ __device__ __forceinline__ float4 lds128(const float* p) {
   return v;
 }
 
+#ifndef DINOX_EPI_WARPS
+#define DINOX_EPI_WARPS 8   // epilogue warps of the two row-math kernels (pass 1 / pass 2): 8 or 16
+#endif
+
 struct EpiStats {
   static constexpr bool kUsesTmaStore = false;
-  static constexpr int kEpiWarps = 8;
+  static constexpr int kEpiWarps = DINOX_EPI_WARPS;
+  static constexpr int kGroups = kEpiWarps / 4;          // column groups (each TMEM lane quarter has kGroups warps)
   static constexpr int kEpiSmemBytes = 2 * 256 * 4;
   struct Params {
     float scale2;
     const float* col2;   // (N) log2-unit column offsets, may be NULL
-    float2* partial;     // (M, 2*num_n_tiles)
+    float2* partial;     // (M, kGroups*num_n_tiles)
   };
-  struct State {};
+  struct State {
+    float col;   // this thread's column offset of the NEXT tile (prefetched while the current tile is processed)
+  };
   static __device__ __forceinline__ void finish(const Params&, const CoreParams&, int, int, State&) {}
   template <int BN>
   struct Impl {
     static_assert(BN == 256, "EpiStats is written for 256-wide tiles");
-    static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int acc_stage,
-                                                    int epi_warp, int lane, uint8_t* smem) {
-      float* buf = reinterpret_cast<float*>(smem) + acc_stage * 256;
-      const int i = epi_warp * 32 + lane;  // 0..255
+    static constexpr int kCols = BN / kGroups;           // columns per warp (128 or 64)
+    static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
+                                                 State& st) {
+      const int i = epi_warp * 32 + lane;
       const int col = tc.n_tile * BN + i;
-      buf[i] = (col < p.N) ? (e.col2 ? __ldg(e.col2 + col) : 0.f) : -INFINITY;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      st.col = (i < BN && col < p.N) ? (e.col2 ? __ldg(e.col2 + col) : 0.f) : -INFINITY;
+    }
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int acc_stage,
+                                                    int epi_warp, int lane, uint8_t* smem, State& st) {
+      float* buf = reinterpret_cast<float*>(smem) + acc_stage * 256;
+      const int i = epi_warp * 32 + lane;
+      if (i < BN) buf[i] = st.col;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
     }
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap*,
                                                 uint32_t tmem_acc, int acc_stage, int epi_warp, int lane, uint8_t* smem, State&) {
       const float* buf = reinterpret_cast<const float*>(smem) + acc_stage * 256;
       const int q = epi_quarter();
-      const int half = epi_warp >> 2;
+      const int grp = epi_warp >> 2;
       const int row = tc.m_tile * BM + q * 32 + lane;
-      const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
+      const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + grp * kCols;
       float m = -INFINITY, s = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < kCols / 64; ++c) {
         float v[2][32];
         sm100::tmem_ld32x2(taddr + c * 64, taddr + c * 64 + 32, v[0], v[1]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float* cb = buf + half * (BN / 2) + c * 64 + h * 32;
+          const float* cb = buf + grp * kCols + c * 64 + h * 32;
           float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -290,7 +311,7 @@ struct EpiStats {
           m = mn;
         }
       }
-      if (row < p.M) e.partial[(int64_t)row * (2 * p.num_n_tiles) + tc.n_tile * 2 + half] = make_float2(m, s);
+      if (row < p.M) e.partial[(int64_t)row * (kGroups * p.num_n_tiles) + tc.n_tile * kGroups + grp] = make_float2(m, s);
     }
   };
 };
@@ -328,10 +349,15 @@ __global__ void stats_merge_kernel(const float2* __restrict__ partial, int64_t r
 // =============================================================================================
 struct EpiGradT {
   static constexpr bool kUsesTmaStore = true;
-  static constexpr int kEpiWarps = 8;
-  static constexpr int kBufs = 2;
-  static constexpr int kStageBytes = kEpiWarps * kBufs * 4096;     // per-warp G staging (TMA store source)
-  static constexpr int kEpiSmemBytes = kStageBytes + 2 * 3 * 128 * 4;
+  static constexpr int kEpiWarps = DINOX_EPI_WARPS;
+  static constexpr int kGroups = kEpiWarps / 4;        // entry-column groups per TMEM lane quarter
+  static constexpr int kCols = 128 / kGroups;          // entries per warp and tile (64 or 32)
+  static constexpr int kRowBytes = kCols * 2;          // staging row: 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
+  static constexpr int kWarpBuf = 32 * kRowBytes;      // 4 KB or 2 KB per warp
+  // Shared memory buys pipeline depth here, so the epilogue keeps ONE staging buffer per warp and ONE
+  // copy of the per-entry constants, and pays for it with a second named barrier per tile.
+  static constexpr int kStageBytes = kEpiWarps * kWarpBuf;     // per-warp G staging (TMA store source)
+  static constexpr int kEpiSmemBytes = kStageBytes + 3 * 128 * 4;
   struct Params {
     float as2, at2, inv_tau_s;
     const float* cs2;       // (K)
@@ -341,42 +367,66 @@ struct EpiGradT {
     const float* lse2;      // (E) student LSE (log2) per entry
     const float* rb2;       // (E) teacher row bias (log2) per entry
     const float* cw;        // (E) entry weight (norm * group weight), 0 for padding
-    float* db2_partial;     // (2*num_n_tiles, M) or NULL
-    float* loss_partial;    // (gridDim.x * 8 * 2): per CTA, per epilogue warp, {entries < alt_from, >= alt_from}
+    float* db2_partial;     // (kGroups*num_n_tiles, M) or NULL
+    float* loss_partial;    // (gridDim.x * kEpiWarps * 2): per CTA and epilogue warp, {entries < alt_from, >= alt_from}
   };
   struct State {
     float loss_a = 0.f, loss_b = 0.f;
-    int flip = 0;
+    float nl, nr, cw;   // prefetched per-entry constants of the next tile (threads 0..127 of the epilogue)
+    float cs, ct;       // prefetched per-prototype offsets of the next tile (this thread's TMEM lane)
+    float cs_cur, ct_cur;   // ... of the tile being processed (latched by prologue)
   };
   static __device__ __forceinline__ void finish(const Params& e, const CoreParams&, int epi_warp, int lane, State& st) {
     const float a = warp_sum(st.loss_a), b = warp_sum(st.loss_b);
     const float sc = -DINOX_LN2 / e.inv_tau_s;   // the tiles accumulate (cw/tau_s) * q * u
     if (lane == 0) {
-      e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 0] = a * sc;
-      e.loss_partial[((int64_t)blockIdx.x * 8 + epi_warp) * 2 + 1] = b * sc;
+      e.loss_partial[((int64_t)blockIdx.x * kEpiWarps + epi_warp) * 2 + 0] = a * sc;
+      e.loss_partial[((int64_t)blockIdx.x * kEpiWarps + epi_warp) * 2 + 1] = b * sc;
       sm100::tma_store_wait_all<0>();
     }
   }
+  // this thread's staging row: 16-byte piece j lives at row*kRowBytes + ((j ^ swizzle(row)) << 4)
+  struct Stage {
+    uint32_t row, sw;
+    __device__ __forceinline__ void init(uint8_t* buf, int lane) {
+      row = sm100::smem_u32(buf) + lane * kRowBytes;
+      sw = kRowBytes == 128 ? ((lane & 7) << 4) : (((lane >> 1) & 3) << 4);
+    }
+    __device__ __forceinline__ void put(int piece, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + ((piece << 4) ^ sw)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+    }
+  };
   template <int BN>
   struct Impl {
-    static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int acc_stage,
-                                                    int epi_warp, int lane, uint8_t* smem) {
-      float* buf = reinterpret_cast<float*>(smem + kStageBytes) + acc_stage * 3 * 128;
-      const int i = epi_warp * 32 + lane;  // 0..255
+    static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
+                                                 State& st) {
+      const int i = epi_warp * 32 + lane;
       if (i < BN) {
         const int ent = tc.n_tile * BN + i;
         const bool ok = ent < p.N;
-        buf[i] = ok ? -__ldg(e.lse2 + ent) : 0.f;
-        buf[128 + i] = ok ? -__ldg(e.rb2 + ent) : 0.f;
-        buf[256 + i] = ok ? __ldg(e.cw + ent) * e.inv_tau_s : 0.f;
+        st.nl = ok ? -__ldg(e.lse2 + ent) : 0.f;
+        st.nr = ok ? -__ldg(e.rb2 + ent) : 0.f;
+        st.cw = ok ? __ldg(e.cw + ent) * e.inv_tau_s : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int k = tc.m_tile * BM + epi_quarter() * 32 + lane;
+      const bool alt = e.ct2_alt && tc.n_tile * BN >= e.alt_from;
+      st.cs = k < p.M ? __ldg(e.cs2 + k) : 0.f;
+      st.ct = k < p.M ? __ldg((alt ? e.ct2_alt : e.ct2) + k) : 0.f;
+    }
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int epi_warp, int lane,
+                                                    uint8_t* smem, State& st) {
+      float* buf = reinterpret_cast<float*>(smem + kStageBytes);
+      const int i = epi_warp * 32 + lane;
+      asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");   // every warp is done reading the previous constants
+      if (i < BN) { buf[i] = st.nl; buf[128 + i] = st.nr; buf[256 + i] = st.cw; }
+      st.cs_cur = st.cs; st.ct_cur = st.ct;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
     }
 
     // 16 entries of one prototype row: logits -> (p, q) -> gradient, loss and bias-gradient terms;
     // the bf16 gradients go to pieces 2*c16, 2*c16+1 of this thread's staging row
     static __device__ __forceinline__ void chunk16(const Params& e, const uint32_t (&sr)[16], const uint32_t (&tr)[16],
-                                                   const float* cb, float cs, float ct, const WarpStage& stg, int c16,
+                                                   const float* cb, float cs, float ct, const Stage& stg, int c16,
                                                    float& l0, float& l1, float& d0, float& d1) {
       uint32_t packed[8];
 #pragma unroll
@@ -407,54 +457,59 @@ struct EpiGradT {
                                                 uint32_t tmem_acc, int acc_stage, int epi_warp, int lane, uint8_t* smem,
                                                 State& st) {
       static_assert(BN == 128, "EpiGradT is written for 128-entry tiles");
-      const float* buf = reinterpret_cast<const float*>(smem + kStageBytes) + acc_stage * 3 * 128;
+      const float* buf = reinterpret_cast<const float*>(smem + kStageBytes);
       const int q = epi_quarter();
-      const int half = epi_warp >> 2;
+      const int grp = epi_warp >> 2;
       const int k0 = tc.m_tile * BM + q * 32;
       const int k = k0 + lane;   // prototype
       const bool kok = k < p.M;
       const bool alt = e.ct2_alt && tc.n_tile * BN >= e.alt_from;
-      const float* ctp = alt ? e.ct2_alt : e.ct2;
-      const float cs = kok ? __ldg(e.cs2 + k) : 0.f;
-      const float ct = kok ? __ldg(ctp + k) : 0.f;
-      const uint32_t ts = tmem_acc + ((uint32_t)(q * 32) << 16) + half * 64;
+      const float cs = st.cs_cur, ct = st.ct_cur;
+      const uint32_t ts = tmem_acc + ((uint32_t)(q * 32) << 16) + grp * kCols;
       const uint32_t tt = ts + BN;
-      const float* cb = buf + half * 64;
-      uint8_t* wbuf = smem + (epi_warp * kBufs + st.flip) * 4096;
-      WarpStage stg;
+      const float* cb = buf + grp * kCols;
+      uint8_t* wbuf = smem + epi_warp * kWarpBuf;
+      Stage stg;
       stg.init(wbuf, lane);
       float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
       uint32_t sa[16], ta[16], sb[16], tb[16];
       sm100::tmem_ld16_nowait(ts, sa);
       sm100::tmem_ld16_nowait(tt, ta);
-      // the staging buffer about to be refilled must no longer be read by the store issued 2 tiles ago
-      if (lane == 0) sm100::tma_store_wait_read<kBufs - 1>();
+      // the staging buffer about to be refilled must no longer be read by the previous tile's store
+      if (lane == 0) sm100::tma_store_wait_read<0>();
       __syncwarp();
       sm100::tmem_wait_ld();
       sm100::tmem_ld16_nowait(ts + 16, sb);
       sm100::tmem_ld16_nowait(tt + 16, tb);
+      sm100::pin16(sa); sm100::pin16(ta);
       chunk16(e, sa, ta, cb, cs, ct, stg, 0, l0, l1, d0, d1);
       sm100::tmem_wait_ld();
-      sm100::tmem_ld16_nowait(ts + 32, sa);
-      sm100::tmem_ld16_nowait(tt + 32, ta);
+      if (kCols == 64) {
+        sm100::tmem_ld16_nowait(ts + 32, sa);
+        sm100::tmem_ld16_nowait(tt + 32, ta);
+      }
+      sm100::pin16(sb); sm100::pin16(tb);
       chunk16(e, sb, tb, cb + 16, cs, ct, stg, 1, l0, l1, d0, d1);
-      sm100::tmem_wait_ld();
-      sm100::tmem_ld16_nowait(ts + 48, sb);
-      sm100::tmem_ld16_nowait(tt + 48, tb);
-      chunk16(e, sa, ta, cb + 32, cs, ct, stg, 2, l0, l1, d0, d1);
-      sm100::tmem_wait_ld();
-      chunk16(e, sb, tb, cb + 48, cs, ct, stg, 3, l0, l1, d0, d1);
-      // G tile rows [k0, k0+32) x entries [ent0, ent0+64) leave as one TMA store (clipped at K and E)
+      if (kCols == 64) {
+        sm100::tmem_wait_ld();
+        sm100::tmem_ld16_nowait(ts + 48, sb);
+        sm100::tmem_ld16_nowait(tt + 48, tb);
+        sm100::pin16(sa); sm100::pin16(ta);
+        chunk16(e, sa, ta, cb + 32, cs, ct, stg, 2, l0, l1, d0, d1);
+        sm100::tmem_wait_ld();
+        sm100::pin16(sb); sm100::pin16(tb);
+        chunk16(e, sb, tb, cb + 48, cs, ct, stg, 3, l0, l1, d0, d1);
+      }
+      // G tile rows [k0, k0+32) x entries [ent0, ent0+kCols) leave as one TMA store (clipped at K and E)
       sm100::fence_proxy_async_smem();
       __syncwarp();
-      const int ent0 = tc.n_tile * BN + half * 64;
+      const int ent0 = tc.n_tile * BN + grp * kCols;
       if (lane == 0 && k0 < p.M && ent0 < p.N) {
         sm100::tma_store_3d(tmC, wbuf, ent0, k0, 0);
         sm100::tma_store_commit();
       }
-      st.flip ^= 1;
       if (kok) {
-        if (e.db2_partial) e.db2_partial[(int64_t)(tc.n_tile * 2 + half) * p.M + k] = d0 + d1;
+        if (e.db2_partial) e.db2_partial[(int64_t)(tc.n_tile * kGroups + grp) * p.M + k] = d0 + d1;
         if (alt) st.loss_b += l0 + l1; else st.loss_a += l0 + l1;
       }
     }
@@ -485,7 +540,8 @@ struct EpiGramDiff {
   }
   template <int BN>
   struct Impl {
-    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*) {}
+    static __device__ __forceinline__ void fetch(const Params&, const CoreParams&, TileCoord, int, int, State&) {}
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int, int, uint8_t*, State&) {}
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap*,
                                                 uint32_t tmem_acc, int, int epi_warp, int lane, uint8_t*, State& st) {
       static_assert(BN == 128, "EpiGramDiff is written for 128-wide tiles");
@@ -565,8 +621,12 @@ struct EpiAdapter {
   static constexpr int kEpiSmemBytes = Epi::kEpiSmemBytes;
   using Params = typename Epi::Params;
   using State = typename Epi::State;
-  static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int a, int w, int l, uint8_t* s) {
-    Epi::template Impl<BN>::prologue(e, p, tc, a, w, l, s);
+  static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int w, int l, State& st) {
+    Epi::template Impl<BN>::fetch(e, p, tc, w, l, st);
+  }
+  static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int a, int w, int l,
+                                                  uint8_t* s, State& st) {
+    Epi::template Impl<BN>::prologue(e, p, tc, a, w, l, s, st);
   }
   static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap* tmC,
                                               uint32_t tm, int a, int w, int l, uint8_t* s, State& st) {
@@ -607,6 +667,7 @@ struct OutDesc {
   void* ptr = nullptr;
   int is_bf16 = 0;
   int64_t ld = 0, slab_stride = 0, slabs = 1;
+  int row_bytes = 128;   // staging row of the epilogue: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
 };
 
 static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int tile_rows, int64_t batches, const char* what) {
@@ -642,7 +703,7 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   tC = tA0;
   if (Epi::kUsesTmaStore) {
     DINOX_REQUIRE(od.ptr, DINOX_E_BADARG, "%s: output descriptor missing", name);
-    if ((rc = make_tmap_out_3d(&tC, od.ptr, od.is_bf16 != 0, od.slabs, M, N, od.ld, od.slab_stride, "C"))) return rc;
+    if ((rc = make_tmap_out_3d(&tC, od.ptr, od.is_bf16 != 0, od.slabs, M, N, od.ld, od.slab_stride, od.row_bytes, "C"))) return rc;
   }
   CoreParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -687,13 +748,19 @@ static int env_flag(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-// CTA-pair (cta_group::2) mode can be switched per process for A/B measurements: DINOX_PAIR=0|1
-static bool pair_enabled() {
+// CTA-pair (cta_group::2) mode per kernel family, DINOX_PAIR bit mask for A/B measurements:
+//   1 = plain store GEMMs (default on: dW2 / dH / layer 1 gain 10-20% from the halved B traffic)
+//   2 = pass 1 (head_stats), 4 = pass 2 (head_grad)   (default off: measured 5-13% slower)
+enum { kPairStore = 1, kPairStats = 2, kPairGrad = 4 };
+static bool pair_enabled(int family) {
   static int v = -1;
-  if (v < 0) v = env_flag("DINOX_PAIR", 0) != 0;
-  return v != 0;
+  if (v < 0) v = env_flag("DINOX_PAIR", kPairStore);
+  return (v & family) != 0;
 }
 
+#ifndef DINOX_EXP_NSPLIT256
+#define DINOX_EXP_NSPLIT256 1   // experiment knob: 2 issues the 256-wide tile as two N=128 MMAs (A read twice from smem)
+#endif
 // tile-shape dispatch of the plain GEMM: widest tile without N waste; clusters of 2 share the B tile
 struct StoreArgs {
   void* out;
@@ -709,14 +776,14 @@ template <class Epi>
 static int launch_store_t(int64_t M, int64_t N, const Operand& a, const Operand& b, int64_t K, int m_fastest,
                           const typename Epi::Params& ep, const OutDesc& od, cudaStream_t stream, int64_t batches,
                           int64_t splits) {
-  const bool cl2 = M > BM && pair_enabled();   // a single M tile has nobody to pair with
+  const bool cl2 = M > BM && pair_enabled(kPairStore);   // a single M tile has nobody to pair with
   if (N % 384 == 0) {
     return cl2 ? launch<384, 3, 1, 2, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<384,pair>", batches, splits)
                : launch<384, 3, 1, 1, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<384>", batches, splits);
   }
   if (N % 256 == 0 || N > 2048) {
     return cl2 ? launch<256, 1, 1, 2, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<256,pair>", batches, splits)
-               : launch<256, 1, 1, 1, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<256>", batches, splits);
+               : launch<256, DINOX_EXP_NSPLIT256, 1, 1, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<256>", batches, splits);
   }
   return cl2 ? launch<128, 1, 1, 2, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<128,pair>", batches, splits)
              : launch<128, 1, 1, 1, Epi>(a, b, nullptr, nullptr, M, N, K, m_fastest, ep, od, stream, "gemm_bf16<128>", batches, splits);
@@ -801,10 +868,30 @@ int dinox_gemm_splitk_plan(int64_t M, int64_t N, int64_t K) {
   return best;
 }
 
+/* diagnostics: how many CTA-pair clusters of the pass-1 kernel can be co-resident (74 = every SM) */
+int dinox_debug_max_active_clusters(int cluster_size) {
+  auto kern = cluster_size == 2 ? gemm_kernel<256, 1, 1, 2, EpiStats> : gemm_kernel<256, 1, 1, 1, EpiStats>;
+  constexpr int smem = smem_bytes<256, 2, EpiStats>() > smem_bytes<256, 1, EpiStats>() ? smem_bytes<256, 2, EpiStats>()
+                                                                                      : smem_bytes<256, 1, EpiStats>();
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148);
+  cfg.blockDim = dim3((2 + EpiStats::kEpiWarps) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -2; }
+  return n;
+}
+
 size_t dinox_head_stats_workspace_bytes(int64_t rows, int64_t K) {
   if (rows <= 0 || K <= 0) return 0;
   const int64_t n_tiles = (K + 255) / 256;
-  return (size_t)rows * 2 * n_tiles * sizeof(float2);
+  return (size_t)rows * EpiStats::kGroups * n_tiles * sizeof(float2);
 }
 
 int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D, int64_t ldh, int64_t ldw,
@@ -815,10 +902,10 @@ int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int
   if (rc) return rc;
   Operand a{H, rows, ldh, 0}, b{W2, K, ldw, 0};
   EpiStats::Params ep{inv_tau * DINOX_LOG2E, col2, reinterpret_cast<float2*>(workspace)};
-  rc = (rows > BM && pair_enabled()) ? launch<256, 1, 1, 2, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats<pair>")
+  rc = (rows > BM && pair_enabled(kPairStats)) ? launch<256, 1, 1, 2, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats<pair>")
                  : launch<256, 1, 1, 1, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats");
   if (rc) return rc;
-  const int n_part = 2 * (int)((K + 255) / 256);
+  const int n_part = EpiStats::kGroups * (int)((K + 255) / 256);
   stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows, n_part,
                                                                      lse_nat, lse2);
   return check_launch("stats_merge_kernel", stream);
@@ -826,8 +913,11 @@ int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int
 
 size_t dinox_head_grad_workspace_bytes(int64_t K, int64_t E) {
   if (K <= 0 || E <= 0) return 0;
-  return (size_t)(1024 * 8 * 2) * sizeof(float) + 256;  // per-CTA partials, grid <= 1024
+  return (size_t)(1024 * EpiGradT::kEpiWarps * 2) * sizeof(float) + 256;  // per-CTA partials, grid <= 1024
 }
+
+/* rows of the db2_partial buffer of dinox_head_grad: one per (128-entry tile, column group of the epilogue) */
+int64_t dinox_head_grad_db2_rows(int64_t E) { return E <= 0 ? 0 : EpiGradT::kGroups * ((E + 127) / 128); }
 
 int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const void* HtE, int64_t K, int64_t D,
                     int64_t E, int64_t ldw_s, int64_t ldw_t, int64_t ldh_s, int64_t ldh_t, float inv_tau_s,
@@ -849,14 +939,15 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
   ep.db2_partial = db2_partial; ep.loss_partial = reinterpret_cast<float*>(workspace);
   OutDesc od;
   od.ptr = Gt; od.is_bf16 = 1; od.ld = ldg; od.slab_stride = K * ldg; od.slabs = 1;
+  od.row_bytes = EpiGradT::kRowBytes;
   // entry tiles fastest: the 2 x (K-tile of W2) operands stay put while HsE/HtE (L2-resident) stream
-  const bool cl2 = K > BM && pair_enabled();
+  const bool cl2 = K > BM && pair_enabled(kPairGrad);
   rc = cl2 ? launch<128, 1, 2, 2, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, od, stream, "head_grad<pair>")
            : launch<128, 1, 2, 1, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, od, stream, "head_grad");
   if (rc) return rc;
   const int cl = cl2 ? 2 : 1;
   const int grid = launch_grid((((K + 127) / 128 + cl - 1) / cl) * ((E + 127) / 128), cl);
-  pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * 8, loss_out, loss_accumulate);
+  pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * EpiGradT::kEpiWarps, loss_out, loss_accumulate);
   return check_launch("pair_sum_kernel", stream);
 }
 

@@ -10,6 +10,16 @@
 #pragma once
 #include "sm100.cuh"
 
+#ifndef DINOX_EXP_NO_TMA
+#define DINOX_EXP_NO_TMA 0
+#endif
+#ifndef DINOX_EXP_NO_MMA
+#define DINOX_EXP_NO_MMA 0
+#endif
+#ifndef DINOX_EXP_NO_EPI
+#define DINOX_EXP_NO_EPI 0
+#endif
+
 namespace dinox {
 namespace gemm {
 
@@ -37,10 +47,14 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
   static constexpr int kBBytes = (BN / CL) * BK * 2;   // a CTA of a pair holds 1/CL of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = (EPI_SMEM + 1023) / 1024 * 1024;
+  static constexpr int kEpiBytes = (EPI_SMEM + 255) / 256 * 256;
   // 227 KB per CTA minus alignment slack (1 KB), control block (256 B) and the epilogue's staging area
   static constexpr int kBudget = 227 * 1024 - 1024 - 256 - kEpiBytes;
-  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+#ifndef DINOX_MAX_STAGES
+#define DINOX_MAX_STAGES 8
+#endif
+  static constexpr int kFit = kBudget / kStageBytes;
+  static constexpr int kStages = kFit > DINOX_MAX_STAGES ? DINOX_MAX_STAGES : kFit;
   static_assert(kStages >= 2, "tile too large for the smem pipeline");
   static constexpr int kPipeBytes = kStages * kStageBytes;
   static constexpr int kTotal = kPipeBytes + kEpiBytes + 256 + 1024;
@@ -98,6 +112,7 @@ struct SharedCtl {
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t tmem_empty_local[2];   // pair mode, non-leader CTA: its own epilogue warps report here
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -118,7 +133,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
 //                for both; each CTA's epilogue drains the 128 rows that live in its own TMEM.  This
 //                halves the B-operand bytes every SM pulls from L2 per FLOP - the K<=1024 GEMMs of
 //                the loss head are bound by L2->SMEM operand traffic, not by the tensor pipe.
-// `Epi` provides kEpiWarps, kEpiSmemBytes, Params, State, prologue(), tile(), finish().
+// `Epi` provides kEpiWarps, kEpiSmemBytes, Params, State, fetch(), prologue(), tile(), finish().
 // `tmC` is the output tensor map of epilogues that store through TMA (others ignore it).
 template <int BN, int NSPLIT, int NSUB, int CL, class Epi>
 __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Epi::Params& ep,
@@ -163,7 +178,10 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     for (int i = 0; i < kStages; ++i) { sm100::mbar_init(&ctl->full[i], 1); sm100::mbar_init(&ctl->empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&ctl->tmem_full[i], 1);
-      sm100::mbar_init(&ctl->tmem_empty[i], CL * Epi::kEpiWarps);   // pair: both CTAs' epilogues report to the leader
+      // pair: the leader's barrier takes its own epilogue warps plus ONE forwarded arrival for the peer
+      // CTA, whose epilogue warps report to their local barrier (see the forwarder in warp 1)
+      sm100::mbar_init(&ctl->tmem_empty[i], Epi::kEpiWarps + (kPair ? 1 : 0));
+      sm100::mbar_init(&ctl->tmem_empty_local[i], Epi::kEpiWarps);
     }
     sm100::fence_barrier_init();
   }
@@ -182,7 +200,11 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====
-    if (lane == 0) {
+    // The WHOLE warp walks the loop with warp-uniform state and one elected lane issues: inside a
+    // divergent `if (lane == 0)` region nvcc wraps every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST
+    // + BRA.U.ANY "waterfall" (~20 dependent instructions per issue), which made the single issuing
+    // thread - not the tensor pipe - the limiter of the 64-cycle N=128 MMAs.
+    {
       PipeState st;
       for (; walk.valid(); walk.next()) {
         const TileCoord tc = walk.coord(p, CL, crank);
@@ -194,16 +216,23 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
           const CUtensorMap* mb = sub ? tmB1 : tmB0;
           for (int kb = kb0; kb < kb1; ++kb) {
             sm100::mbar_wait(&ctl->empty[st.stage], st.phase ^ 1, 1);
+            if (sm100::elect_one()) {
             uint8_t* sa = pipe + st.stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
             uint64_t* full = &ctl->full[st.stage];
-            // pair: all bytes (both CTAs) are counted on the leader's barrier
-            const uint32_t full_addr = kPair ? sm100::mapa_u32(sm100::smem_u32(full), 0) : 0;
+            // pair: all bytes (both CTAs) are counted on the leader's barrier.  (Counting per CTA and
+            // forwarding "my half landed" with a release.cluster arrive was measured 2x slower: the
+            // cluster-scope release costs ~1.6k cycles per stage on the forwarding thread.)
+            constexpr bool kRemoteTx = kPair;
+#if DINOX_EXP_NO_TMA   // experiment: no operand loads at all, the MMAs re-read whatever is in smem
+            if (leader) sm100::mbar_arrive(full);
+#else
             if (leader) sm100::mbar_expect_tx(full, CL * L::kStageBytes);
+            const uint32_t full_addr = kRemoteTx ? sm100::mapa_u32(sm100::smem_u32(full), 0) : 0;
             const int k0 = kb * BK;
             const bool b3 = p.batches > 1;
             auto load = [&](uint8_t* dst, const CUtensorMap* tm, int c0, int c1) {
-              if (kPair) {
+              if (kRemoteTx) {
                 if (b3) sm100::tma_load_3d_pair(dst, tm, full_addr, c0, c1, tc.batch);
                 else sm100::tma_load_2d_pair(dst, tm, full_addr, c0, c1);
               } else {
@@ -231,14 +260,32 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
                   load(sb + (h * (kAtoms > 0 ? kAtoms : 1) + c) * (BK * 128), mb, r0 + c * 64, k0);
               }
             }
+#endif
+            }   // elected lane
+            __syncwarp();
             st.advance<kStages>();
           }
         }
       }
     }
   } else if (warp == 1) {
+    // ===================== pair, non-leader CTA: forward "accumulator stage drained" ==============
+    // One release.cluster arrive per tile from a thread with no memory traffic of its own; the
+    // epilogue warps only pay a CTA-local arrive.
+    if (kPair && !leader) {
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      for (; walk.valid(); walk.next()) {
+        sm100::mbar_wait(&ctl->tmem_empty_local[acc_stage], acc_phase, 7);
+        if (sm100::elect_one())
+          sm100::mbar_arrive_cluster(sm100::mapa_u32(sm100::smem_u32(&ctl->tmem_empty[acc_stage]), 0));
+        __syncwarp();
+        if (kAccStages == 2) { acc_stage ^= 1; if (acc_stage == 0) acc_phase ^= 1; }
+        else acc_phase ^= 1;
+      }
+    }
     // ===================== MMA issuer (one thread; pair: the leader CTA only) =====================
-    if (lane == 0 && leader) {
+    if (leader) {
       const uint32_t idesc = sm100::umma_idesc_bf16(BM * CL, BNI, p.a_mn_major, p.b_mn_major);
       // per-UMMA_K advance of the descriptor start address, and LBO per layout
       const uint32_t a_adv = p.a_mn_major ? (UMMA_K * 128) : (UMMA_K * 2);
@@ -262,6 +309,11 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             sm100::tc_fence_after();
             const uint32_t sa = sm100::smem_u32(pipe + st.stage * L::kStageBytes);
             const uint32_t sb = sa + L::kABytes;
+            if (sm100::elect_one()) {
+#if DINOX_EXP_NO_MMA   // experiment: operands stream through smem but nothing reads them
+            sm100::mbar_arrive(&ctl->empty[st.stage]);
+            if (kPair) sm100::mbar_arrive_cluster(sm100::mapa_u32(sm100::smem_u32(&ctl->empty[st.stage]), 1));
+#else
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = sm100::umma_smem_desc(sa + k * a_adv, a_lbo, 1024);
@@ -275,12 +327,18 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             // frees the smem slot (in both CTAs of a pair) when these MMAs retire
             if (kPair) sm100::umma_commit_pair(&ctl->empty[st.stage]);
             else sm100::umma_commit(&ctl->empty[st.stage]);
+#endif
+            }   // elected lane
+            __syncwarp();
             st.advance<kStages>();
           }
         }
         // accumulators complete -> epilogue (of both CTAs)
-        if (kPair) sm100::umma_commit_pair(&ctl->tmem_full[acc_stage]);
-        else sm100::umma_commit(&ctl->tmem_full[acc_stage]);
+        if (sm100::elect_one()) {
+          if (kPair) sm100::umma_commit_pair(&ctl->tmem_full[acc_stage]);
+          else sm100::umma_commit(&ctl->tmem_full[acc_stage]);
+        }
+        __syncwarp();
         if (kAccStages == 2) { acc_stage ^= 1; if (acc_stage == 0) acc_phase ^= 1; }
         else acc_phase ^= 1;
       }
@@ -291,20 +349,24 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     typename Epi::State state;
-    for (; walk.valid(); walk.next()) {
-      const TileCoord tc = walk.coord(p, CL, crank);
-      Epi::prologue(ep, p, tc, acc_stage, epi_warp, lane, epi_smem);
+    TileCoord tc = walk.coord(p, CL, crank);
+    if (walk.valid()) Epi::fetch(ep, p, tc, epi_warp, lane, state);   // per-tile constants: global -> registers
+    while (walk.valid()) {
+      Epi::prologue(ep, p, tc, acc_stage, epi_warp, lane, epi_smem, state);   // registers -> smem (+ barrier)
+      walk.next();
+      const TileCoord tn = walk.coord(p, CL, crank);
+      if (walk.valid()) Epi::fetch(ep, p, tn, epi_warp, lane, state);   // next tile's loads fly during this tile
       sm100::mbar_wait(&ctl->tmem_full[acc_stage], acc_phase, 4);
       sm100::tc_fence_after();
+#if !DINOX_EXP_NO_EPI   // experiment knob: skip the epilogue math, keep the barrier protocol
       Epi::tile(ep, p, tc, tmC, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
+#endif
       sm100::tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if (kPair) sm100::mbar_arrive_cluster(sm100::mapa_u32(sm100::smem_u32(&ctl->tmem_empty[acc_stage]), 0));
-        else sm100::mbar_arrive(&ctl->tmem_empty[acc_stage]);
-      }
+      if (lane == 0) sm100::mbar_arrive(leader ? &ctl->tmem_empty[acc_stage] : &ctl->tmem_empty_local[acc_stage]);
       if (kAccStages == 2) { acc_stage ^= 1; if (acc_stage == 0) acc_phase ^= 1; }
       else acc_phase ^= 1;
+      tc = tn;
     }
     Epi::finish(ep, p, epi_warp, lane, state);
   }

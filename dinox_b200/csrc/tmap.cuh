@@ -62,10 +62,10 @@ inline int make_tmap_bf16_3d(CUtensorMap* out, const void* base, int64_t batch, 
 }
 
 // Output tensor map for TMA-store epilogues: (batch, rows, cols) row-major fp32 or bf16, leading
-// dimension ld and batch stride bs in elements; box = 1 x 32 rows x 128 bytes, SWIZZLE_128B (one
+// dimension ld and batch stride bs in elements; box = 1 x 32 rows x row_bytes (128: SWIZZLE_128B, 64: SWIZZLE_64B) (one
 // epilogue warp's staging buffer).  Stores clip at the tensor bounds, so ragged tiles need no masks.
 inline int make_tmap_out_3d(CUtensorMap* out, const void* base, bool is_bf16, int64_t batch, int64_t rows,
-                            int64_t cols, int64_t ld, int64_t bs, const char* what) {
+                            int64_t cols, int64_t ld, int64_t bs, int row_bytes, const char* what) {
   PFN_encodeTiled enc = get_encode_fn();
   DINOX_REQUIRE(enc, DINOX_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int es = is_bf16 ? 2 : 4;
@@ -75,11 +75,13 @@ inline int make_tmap_out_3d(CUtensorMap* out, const void* base, bool is_bf16, in
   if (batch == 1 && bs < rows * ld) bs = rows * ld;
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)bs * es};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / es), 32u, 1u};
+  DINOX_REQUIRE(row_bytes == 128 || row_bytes == 64, DINOX_E_BADARG, "%s: staging rows are 64 or 128 bytes", what);
+  cuuint32_t box[3] = {(cuuint32_t)(row_bytes / es), 32u, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DINOX_REQUIRE(r == CUDA_SUCCESS, DINOX_E_CUDA, "%s: cuTensorMapEncodeTiled(out) failed with CUresult %d", what, (int)r);
   return DINOX_OK;
 }

@@ -240,8 +240,8 @@ def head_grad(w2s, w2t, hs_e, ht_e, inv_tau_s, inv_tau_t, cs2, ct2, ct2_alt, alt
     e_pad = (E + 127) // 128 * 128
     if gt is None:
         gt = torch.empty(K, e_pad, dtype=torch.bfloat16, device=w2s.device)
-    n_et = e_pad // 128
-    db2p = torch.empty(2 * n_et, K, dtype=torch.float32, device=w2s.device) if want_db2 else None
+    db2p = (torch.empty(int(_ext.lib().dinox_head_grad_db2_rows(E)), K, dtype=torch.float32, device=w2s.device)
+            if want_db2 else None)
     ws = torch.empty(int(_ext.lib().dinox_head_grad_workspace_bytes(K, E)), dtype=torch.uint8, device=w2s.device)
     _ext.call("dinox_head_grad", _p(w2s), _p(w2t), _p(hs_e), _p(ht_e), K, D, E, _rowmajor(w2s), _rowmajor(w2t),
               _rowmajor(hs_e), _rowmajor(ht_e), float(inv_tau_s), float(inv_tau_t), _p(cs2), _p(ct2), _p(ct2_alt),

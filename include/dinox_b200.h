@@ -144,6 +144,8 @@ DINOX_API int dinox_gemm_bf16_splitk(const void* A, const void* B, float* C_part
                                      int splits, int a_mn_major, int b_mn_major, float alpha,
                                      const float* alpha_dev, int m_fastest, dinox_stream_t stream);
 DINOX_API int dinox_gemm_splitk_plan(int64_t M, int64_t N, int64_t K);
+/* diagnostics: number of co-resident clusters of `cluster_size` CTAs for the pass-1 kernel */
+DINOX_API int dinox_debug_max_active_clusters(int cluster_size);
 
 /* ------------------------------------------------------------------------------------------
  * Fused pass 1: prototype logits (H . W2^T, bf16 operands, fp32 TMEM accumulators) with the
@@ -163,13 +165,15 @@ DINOX_API int dinox_head_stats(const void* H, const void* W2, int64_t rows, int6
  *   Gt[k,e]  = cw[e]*inv_tau_s*( softmax_s[e,k] - q_t[e,k] )          (bf16, (K, ldg) = dL/dlogits^T)
  *   loss[0..1] (+)= sum_e cw[e] * sum_k q_t[e,k] * (-ln softmax_s[e,k])  (two fp32 on device:
  *              [0] entries < alt_from (CLS pairs), [1] entries >= alt_from (iBOT), [1]=0 if no alt)
- *   db2_partial[(2*ceil(E/128)), K]  column partial sums of Gt (reduce with dinox_cols_sum), optional
+ *   db2_partial[dinox_head_grad_db2_rows(E), K]  column partial sums of Gt (reduce with dinox_cols_sum), optional
  * with softmax_s = 2^(S*inv_tau_s*log2e + cs2[k] - lse2[e]), q_t = 2^(T*inv_tau_t*log2e + ct2[k] - rb2[e]);
  * entries >= alt_from (multiple of 128) use ct2_alt (iBOT patch centre).  HsE/HtE: (E, D) bf16
  * gathered head activations of the entry's student / teacher row.  Cross-entropy of
  * scripts/phase5_big_run.py:703-717 and its autograd (grad of log_softmax) in one kernel.
  * ------------------------------------------------------------------------------------------ */
 DINOX_API size_t dinox_head_grad_workspace_bytes(int64_t K, int64_t E);
+/* rows of db2_partial: one per (128-entry tile, epilogue column group); db2_partial is (rows, K) fp32 */
+DINOX_API int64_t dinox_head_grad_db2_rows(int64_t E);
 DINOX_API int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const void* HtE,
                               int64_t K, int64_t D, int64_t E, int64_t ldw_s, int64_t ldw_t,
                               int64_t ldh_s, int64_t ldh_t, float inv_tau_s, float inv_tau_t,

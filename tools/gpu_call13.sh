@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for tag in "" st3 st2; do for pair in 0 1; do
+  DINOX_LIB_TAG=$tag DINOX_PAIR=$pair timeout 120 python tools/probe_time.py 2>&1 | tail -1
+done; done | tee gpurun_out/probe_time.log

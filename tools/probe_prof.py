@@ -20,6 +20,6 @@ for _ in range(nrep):
     _, r2 = ops.head_stats(ht, wt, 25.0, ct2, want_nat=False)
     gt, db2p = ops.head_grad(ws, wt, hs, ht, 10.0, 25.0, cs2, ct2, None, 0, l2.new_zeros(E) + l2.mean(), r2, cw, loss)
     ops.gemm_bf16(gt, hs, b_mn_major=True, out=w2grad, accumulate=True, m_fastest=False)
-    dh = ops.gemm_bf16(gt, ws, a_mn_major=True, b_mn_major=True)
+    dh = ops.gemm_bf16_splitk(gt, ws, a_mn_major=True, b_mn_major=True)
 torch.cuda.synchronize()
 print("ok", loss.tolist())
