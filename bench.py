@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "loss_head_crops_per_sec"
+_OUT = sys.stdout
 
 
 def _peaks():
@@ -153,7 +154,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -177,8 +178,23 @@ def run_ours(args):
     sh = synth.LossHeadShapes(**synth.CONFIGS[args.config])
     step = LossHeadStep(sh, dev, accum=args.accum, process_group=pg)
     g = synth.seeded_generator(2, rank)
-    host = {k: v.pin_memory() for k, v in synth.feature_batch(sh, g).items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    feats = synth.feature_batch(sh, g)
+
+    def blob_views(blob, like):
+        """typed views into one contiguous byte blob, 256-byte aligned segments, same keys/shapes as `like`"""
+        views, off = {}, 0
+        for k, v in like.items():
+            n = v.numel() * v.element_size()
+            views[k] = blob[off:off + n].view(v.dtype).view(v.shape)
+            off += (n + 255) // 256 * 256
+        return views
+
+    blob_bytes = sum((v.numel() * v.element_size() + 255) // 256 * 256 for v in feats.values())
+    host_blob = torch.empty(blob_bytes, dtype=torch.uint8).pin_memory()   # ONE pinned buffer -> ONE H2D copy per step
+    host = blob_views(host_blob, feats)
+    for k, v in feats.items():
+        host[k].copy_(v)
+    h2d_bytes = blob_bytes
 
     def to_leaves(f):
         return {k: (v.requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()}
@@ -223,7 +239,8 @@ def run_ours(args):
 
     # ---------------- leg 2: end to end from pinned host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    dev_blobs = [torch.empty(blob_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    bufs = [blob_views(b, feats) for b in dev_blobs]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
@@ -232,8 +249,7 @@ def run_ours(args):
         b = i & 1
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[b])
-            for k, v in host.items():
-                bufs[b][k].copy_(v, non_blocking=True)
+            dev_blobs[b].copy_(host_blob, non_blocking=True)
             ready[b].record(copy_stream)
 
     def e2e_loop(n):
@@ -314,9 +330,18 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "loss": loss_val,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) must not add lines to stdout: point fd 1 at stderr
+    for the run and hand back a file object on the real stdout for the single JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -330,6 +355,8 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global _OUT
+    _OUT = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -4,6 +4,7 @@
 // row gather-sum (dL/dh of entries -> rows), token L2-normalise forward/backward for Gram
 // anchoring (scripts/phase5_big_run.py:726).  128-bit accesses, one warp per row.
 #include "common.cuh"
+#include <type_traits>
 
 namespace dinox {
 
@@ -26,6 +27,54 @@ __global__ void gather_cast_kernel(const T* __restrict__ src, int64_t ld_src, co
   for (int c = lane * 2; c < D; c += 64) {
     float a = to_f32<T>(s[c]), b = to_f32<T>(s[c + 1]);
     *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(a, b);
+  }
+}
+
+// 16-byte vector flavour (D % 8 == 0, 16-byte aligned rows): each lane moves 8 elements per step,
+// all loads of a row are issued before the first store
+template <typename T>
+__global__ void gather_cast_vec_kernel(const T* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ idx,
+                                       int64_t rows, int D, __nv_bfloat16* __restrict__ dst, int64_t ld_dst) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int64_t sr = idx ? idx[r] : r;
+  __nv_bfloat16* d = dst + r * ld_dst;
+  constexpr int kMaxIter = 4;   // D <= 1024 per pass
+  for (int c0 = 0; c0 < D; c0 += 256 * kMaxIter) {
+    uint4 o[kMaxIter];
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int c = c0 + it * 256 + lane * 8;
+      o[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (c < D && sr >= 0) {
+        if (sizeof(T) == 4) {
+          const float4 v0 = ldg_stream_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + sr * ld_src + c));
+          const float4 v1 = ldg_stream_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + sr * ld_src + c + 4));
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v0.z, v0.w);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v1.x, v1.y), h3 = __floats2bfloat162_rn(v1.z, v1.w);
+          o[it] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                             *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        } else {
+          const uint4 v = ldg_stream_u4(reinterpret_cast<const uint4*>(src + sr * ld_src + c));
+          if (sizeof(T) == 2 && !std::is_same<T, __half>::value) {
+            o[it] = v;   // bf16 -> bf16
+          } else {
+            const __half2* hp = reinterpret_cast<const __half2*>(&v);
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hp[j]); h[j] = __floats2bfloat162_rn(f.x, f.y); }
+            o[it] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                               *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kMaxIter; ++it) {
+      const int c = c0 + it * 256 + lane * 8;
+      if (c < D) *reinterpret_cast<uint4*>(d + c) = o[it];
+    }
   }
 }
 
@@ -58,16 +107,17 @@ __global__ void gelu_fwd_kernel(const float* __restrict__ a, int64_t n4, __nv_bf
   reinterpret_cast<uint2*>(h)[i] = o;
 }
 
-// da[r, c] = bf16(dh[r,c] * scale * gelu'(a[r,c])); each thread owns 4 columns of a 64-row slab and
-// emits one partial column sum per slab (fixed order => deterministic db1)
+// da[r, c] = bf16(dh[r,c] * scale * gelu'(a[r,c])); each thread owns 4 columns of a kGeluSlab-row slab
+// and emits one partial column sum per slab (fixed order => deterministic db1)
+constexpr int kGeluSlab = 16;
 __global__ void gelu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ a, int64_t rows, int D,
                                 const float* __restrict__ scale_dev, __nv_bfloat16* __restrict__ da,
                                 float* __restrict__ colsum_partial /* (gridDim.y, D) */) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= D) return;
   const float sc = scale_dev ? *scale_dev : 1.f;
-  const int64_t r0 = (int64_t)blockIdx.y * 64;
-  const int64_t r1 = r0 + 64 < rows ? r0 + 64 : rows;
+  const int64_t r0 = (int64_t)blockIdx.y * kGeluSlab;
+  const int64_t r1 = r0 + kGeluSlab < rows ? r0 + kGeluSlab : rows;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   for (int64_t r = r0; r < r1; ++r) {
     const float4 g = *reinterpret_cast<const float4*>(dh + r * D + c);
@@ -105,6 +155,59 @@ __global__ void gemv_bf16_kernel(const __nv_bfloat16* __restrict__ W, int64_t ld
   }
   acc = warp_sum(acc);
   if (lane == 0) out[k] = acc * alpha + (bias ? bias[k] * beta : 0.f);
+}
+
+// nvec (<= 4) vectors against the same matrix in one pass over W: out[v][k] = alpha[v] * W[k,:].x[v] + beta*bias[k]
+struct GemvAlphas { float a[4]; };
+template <int NV>
+__global__ void gemv_bf16_multi_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, const float* __restrict__ X,
+                                       int64_t K, int D, GemvAlphas alphas, const float* __restrict__ bias, float beta,
+                                       float* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  const __nv_bfloat16* w = W + k * ldw;
+  float acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 u = ldg_stream_u4(reinterpret_cast<const uint4*>(w + c));
+    const float wv[8] = {__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                         __uint_as_float(u.y & 0xffff0000u), __uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u),
+                         __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u)};
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float4 x0 = *reinterpret_cast<const float4*>(X + (int64_t)v * D + c);
+      const float4 x1 = *reinterpret_cast<const float4*>(X + (int64_t)v * D + c + 4);
+      acc[v] = fmaf(wv[0], x0.x, acc[v]); acc[v] = fmaf(wv[1], x0.y, acc[v]);
+      acc[v] = fmaf(wv[2], x0.z, acc[v]); acc[v] = fmaf(wv[3], x0.w, acc[v]);
+      acc[v] = fmaf(wv[4], x1.x, acc[v]); acc[v] = fmaf(wv[5], x1.y, acc[v]);
+      acc[v] = fmaf(wv[6], x1.z, acc[v]); acc[v] = fmaf(wv[7], x1.w, acc[v]);
+    }
+  }
+  const float b = bias ? bias[k] * beta : 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float t = warp_sum(acc[v]);
+    if (lane == 0) out[(int64_t)v * K + k] = t * alphas.a[v] + b;
+  }
+}
+
+// dst[i] (+)= scale * sum_{s < slabs} src[s*slab_stride + i]   (fixed order; split-K partial slabs)
+__global__ void sum_slabs_kernel(const float* __restrict__ src, int slabs, int64_t slab_stride, int64_t n4,
+                                 const float* __restrict__ scale_dev, float scale, float* __restrict__ dst, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float sc = scale * (scale_dev ? *scale_dev : 1.f);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < slabs; ++s) {
+    const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(src + s * slab_stride) + i);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  float4 o = make_float4(a.x * sc, a.y * sc, a.z * sc, a.w * sc);
+  float4* d = reinterpret_cast<float4*>(dst) + i;
+  if (accumulate) { const float4 old = *d; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+  *d = o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -197,13 +300,18 @@ int dinox_gather_cast_bf16(const void* src, int src_dtype, int64_t ld_src, const
   DINOX_REQUIRE((reinterpret_cast<uintptr_t>(dst) % 4) == 0 && ld_dst % 2 == 0, DINOX_E_ALIGN, "gather_cast: dst misaligned");
   if (rows == 0) return DINOX_OK;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (src_dtype == DINOX_F32)
-    gather_cast_kernel<float><<<grid, 256, 0, stream>>>((const float*)src, ld_src, idx, rows, (int)D, (__nv_bfloat16*)dst, ld_dst);
-  else if (src_dtype == DINOX_BF16)
-    gather_cast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, ld_src, idx, rows, (int)D, (__nv_bfloat16*)dst, ld_dst);
-  else if (src_dtype == DINOX_F16)
-    gather_cast_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)src, ld_src, idx, rows, (int)D, (__nv_bfloat16*)dst, ld_dst);
+  const int es = src_dtype == DINOX_F32 ? 4 : 2;
+  const bool vec = D % 8 == 0 && aligned16(src) && aligned16(dst) && (ld_src * es) % 16 == 0 && (ld_dst * 2) % 16 == 0;
+#define DINOX_GC(T)                                                                                                \
+  do {                                                                                                             \
+    if (vec) gather_cast_vec_kernel<T><<<grid, 256, 0, stream>>>((const T*)src, ld_src, idx, rows, (int)D, (__nv_bfloat16*)dst, ld_dst); \
+    else gather_cast_kernel<T><<<grid, 256, 0, stream>>>((const T*)src, ld_src, idx, rows, (int)D, (__nv_bfloat16*)dst, ld_dst);         \
+  } while (0)
+  if (src_dtype == DINOX_F32) DINOX_GC(float);
+  else if (src_dtype == DINOX_BF16) DINOX_GC(__nv_bfloat16);
+  else if (src_dtype == DINOX_F16) DINOX_GC(__half);
   else { set_error("gather_cast: unknown dtype %d", src_dtype); return DINOX_E_BADARG; }
+#undef DINOX_GC
   return check_launch("gather_cast_kernel", stream);
 }
 
@@ -221,12 +329,14 @@ int dinox_gelu_fwd(const float* a, int64_t n, void* h_bf16, dinox_stream_t strea
   return check_launch("gelu_fwd_kernel", stream);
 }
 
-size_t dinox_gelu_bwd_workspace_bytes(int64_t rows, int64_t D) { return (size_t)((rows + 63) / 64) * D * sizeof(float); }
+size_t dinox_gelu_bwd_workspace_bytes(int64_t rows, int64_t D) {
+  return (size_t)((rows + kGeluSlab - 1) / kGeluSlab) * D * sizeof(float);
+}
 
 int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int64_t D, const float* scale_dev, void* da_bf16,
                    float* colsum_partial, dinox_stream_t stream) {
   DINOX_REQUIRE(dh && a && da_bf16 && rows > 0 && D > 0 && D % 4 == 0, DINOX_E_BADARG, "gelu_bwd: bad arguments");
-  dim3 grid((unsigned)((D / 4 + 127) / 128), (unsigned)((rows + 63) / 64));
+  dim3 grid((unsigned)((D / 4 + 127) / 128), (unsigned)((rows + kGeluSlab - 1) / kGeluSlab));
   gelu_bwd_kernel<<<grid, 128, 0, stream>>>(dh, a, rows, (int)D, scale_dev, (__nv_bfloat16*)da_bf16, colsum_partial);
   return check_launch("gelu_bwd_kernel", stream);
 }
@@ -237,6 +347,32 @@ int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64
   DINOX_REQUIRE(aligned16(W) && aligned16(x), DINOX_E_ALIGN, "gemv_bf16: misaligned");
   gemv_bf16_kernel<<<(unsigned)((K + 7) / 8), 256, 0, stream>>>((const __nv_bfloat16*)W, ldw, x, K, (int)D, alpha, bias, beta, out);
   return check_launch("gemv_bf16_kernel", stream);
+}
+
+int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
+                          const float* alphas_host, const float* bias, float beta, float* out, dinox_stream_t stream) {
+  DINOX_REQUIRE(W && X && out && alphas_host && K > 0 && D > 0 && D % 8 == 0 && ldw % 8 == 0 && nvec >= 1 && nvec <= 4,
+                DINOX_E_BADARG, "gemv_bf16_multi: bad arguments (D, ldw multiples of 8; 1..4 vectors)");
+  DINOX_REQUIRE(aligned16(W) && aligned16(X), DINOX_E_ALIGN, "gemv_bf16_multi: misaligned");
+  GemvAlphas al;
+  for (int v = 0; v < 4; ++v) al.a[v] = v < nvec ? alphas_host[v] : 0.f;
+  const unsigned grid = (unsigned)((K + 7) / 8);
+  const __nv_bfloat16* w = (const __nv_bfloat16*)W;
+  switch (nvec) {
+    case 1: gemv_bf16_multi_kernel<1><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, bias, beta, out); break;
+    case 2: gemv_bf16_multi_kernel<2><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, bias, beta, out); break;
+    case 3: gemv_bf16_multi_kernel<3><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, bias, beta, out); break;
+    default: gemv_bf16_multi_kernel<4><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, bias, beta, out); break;
+  }
+  return check_launch("gemv_bf16_multi_kernel", stream);
+}
+
+int dinox_sum_slabs(const float* src, int slabs, int64_t slab_stride, int64_t n, const float* scale_dev, float scale,
+                    float* dst, int accumulate, dinox_stream_t stream) {
+  DINOX_REQUIRE(src && dst && slabs >= 1 && n > 0 && n % 4 == 0 && slab_stride % 4 == 0 && aligned16(src) && aligned16(dst),
+                DINOX_E_BADARG, "sum_slabs: bad arguments (n, slab_stride multiples of 4; 16-byte aligned)");
+  sum_slabs_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(src, slabs, slab_stride, n / 4, scale_dev, scale, dst, accumulate);
+  return check_launch("sum_slabs_kernel", stream);
 }
 
 int dinox_gather_sum_rows(const float* src, int64_t ld_src, int slabs, int64_t slab_stride, const int64_t* ptr,

@@ -851,9 +851,11 @@ int dinox_gemm_splitk_plan(int64_t M, int64_t N, int64_t K) {
   // with few output tiles and a long reduction; 1 when the tile count already fills the machine
   if (M <= 0 || N <= 0 || K <= 0) return 1;
   const int64_t bn = (N % 384 == 0) ? 384 : ((N % 256 == 0 || N > 2048) ? 256 : 128);
-  const int64_t tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  // CTA pairs walk super tiles of two M tiles, one pair per two SMs
+  const bool pair = M > BM && pair_enabled(kPairStore);
+  const int64_t tiles = (((M + 127) / 128 + (pair ? 1 : 0)) / (pair ? 2 : 1)) * ((N + bn - 1) / bn);
   const int64_t kb = (K + 63) / 64;
-  const int sms = num_sms();
+  const int sms = num_sms() / (pair ? 2 : 1);
   if (tiles >= 3 * (int64_t)sms || kb < 16) return 1;
   int best = 1;
   double best_cost = 1e30;

@@ -162,9 +162,13 @@ constexpr int kColSumGroups = 16;
 
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(32 * kColSumGroups)
-cols_sum_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, float* __restrict__ out) {
+cols_sum_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, float* __restrict__ out, int64_t chunk) {
   __shared__ float red[kColSumGroups][32][4];
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  // blockIdx.y selects a chunk of rows; chunk sums land in row blockIdx.y of out (chunk >= rows: one chunk)
+  x += (int64_t)blockIdx.y * chunk * ld;
+  out += (int64_t)blockIdx.y * K;
+  rows = rows - (int64_t)blockIdx.y * chunk < chunk ? rows - (int64_t)blockIdx.y * chunk : chunk;
   const int64_t k = ((int64_t)blockIdx.x * 32 + cx) * 4;
   float a[4] = {0.f, 0.f, 0.f, 0.f};
   if (k < K) {
@@ -482,10 +486,26 @@ int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld
   const bool vec = vec_ok(x, dtype, K, ld);
   const unsigned grid = (unsigned)((K + 127) / 128);
   DISPATCH_T(dtype, T, {
-    if (vec) cols_sum_kernel<T, true><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out);
-    else cols_sum_kernel<T, false><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out);
+    if (vec) cols_sum_kernel<T, true><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out, rows);
+    else cols_sum_kernel<T, false><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out, rows);
   });
   return check_launch("cols_sum_kernel", stream);
+}
+
+int dinox_cols_sum_chunked(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, int64_t chunk,
+                           float* partial, dinox_stream_t stream) {
+  DINOX_REQUIRE(x && partial && rows > 0 && K > 0 && ld >= K && chunk > 0, DINOX_E_BADARG, "cols_sum_chunked: bad arguments");
+  int rc = require_sm100();
+  if (rc) return rc;
+  const int64_t nchunks = (rows + chunk - 1) / chunk;
+  DINOX_REQUIRE(nchunks <= 65535, DINOX_E_BADARG, "cols_sum_chunked: too many chunks");
+  const bool vec = vec_ok(x, dtype, K, ld);
+  const dim3 grid((unsigned)((K + 127) / 128), (unsigned)nchunks);
+  DISPATCH_T(dtype, T, {
+    if (vec) cols_sum_kernel<T, true><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, partial, chunk);
+    else cols_sum_kernel<T, false><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, partial, chunk);
+  });
+  return check_launch("cols_sum_kernel<chunked>", stream);
 }
 
 int dinox_center_ema(float* center, const float* colsum, float inv_rows, float m, int64_t K,

@@ -51,6 +51,15 @@ def allreduce_sum_(t: torch.Tensor, pg) -> torch.Tensor:
     return t
 
 
+def allreduce_sum_async(t: torch.Tensor, pg):
+    """SUM all-reduce that returns a work handle (None when single-process); the caller waits on it
+    right before the result is consumed, so the collective overlaps the kernels queued in between."""
+    if _world(pg) > 1:
+        import torch.distributed as dist
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group(pg), async_op=True)
+    return None
+
+
 def allreduce_lse(local_lse: torch.Tensor, pg, add: float = 0.0, _k=ops) -> torch.Tensor:
     """log-sum-exp all-reduce of per-rank LSE vectors: all_gather + one combine kernel.  Exact in
     the log domain (no common shift needed), one collective per Sinkhorn half-iteration."""
@@ -489,6 +498,16 @@ class _FusedHeadLoss(torch.autograd.Function):
         a_t = ops.gemm_bf16(xt, w1t, bias_n=t_head[0].bias.detach())
         ht = ops.gelu_fwd(a_t)
         del a_t
+        # ---- centre statistics: batch-mean teacher logits are W2t . mean(h_t) + b2t by
+        # linearity, so the data-parallel payload is the D-vector sum(h_t) (CLS and masked-patch rows
+        # in ONE all-reduce), launched now so that its latency hides behind the pass-1/pass-2 GEMMs
+        hsum = hsum_work = None
+        if update_center and teacher_mode == "center":
+            hsum = torch.empty(2 if Mm else 1, D, dtype=torch.float32, device=dev)
+            ops.cols_sum(ht[:Mt], out=hsum[0])
+            if Mm:
+                ops.cols_sum(ht[Mt:], out=hsum[1])   # every rank masks the same number of tokens (no host sync)
+            hsum_work = allreduce_sum_async(hsum, pg)
         # ---- pass 1: row statistics with logits kept on chip
         b2s, b2t = s_head[2].bias.detach(), t_head[2].bias.detach()
         cs2 = ops.axpb(b2s, inv_ts * LOG2E)
@@ -529,19 +548,16 @@ class _FusedHeadLoss(torch.autograd.Function):
         with ops.TIMER.region("head_grad"):
             gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
                                      lse2_e, rb2_e, cw, losses, want_db2=need_grad)
-        # ---- centre updates AFTER the loss (scripts/phase5_big_run.py:719): batch-mean logits are
-        # W2t . mean(h_t) + b2t by linearity -> a D-vector all-reduce instead of a K-vector one
-        if update_center and teacher_mode == "center":
+        # ---- centre updates AFTER the loss (scripts/phase5_big_run.py:719)
+        if hsum is not None:
             w = _world(pg)
-            hsum = ops.cols_sum(ht[:Mt])
-            allreduce_sum_(hsum, pg)
-            mean_logits = ops.gemv_bf16(w2t, hsum, 1.0 / (Mt * w), b2t, 1.0)
-            ops.center_ema_(loss_mod.center, mean_logits, 1, loss_mod.center_momentum)
+            if hsum_work is not None:
+                hsum_work.wait()
+            alphas = [1.0 / (Mt * w)] + ([1.0 / (Mm * w)] if Mm else [])
+            mean_logits = ops.gemv_bf16_multi(w2t, hsum, alphas, b2t, 1.0)    # one pass over W2t for both centres
+            ops.center_ema_(loss_mod.center, mean_logits[0], 1, loss_mod.center_momentum)
             if Mm:
-                hsum = ops.cols_sum(ht[Mt:])
-                allreduce_sum_(hsum, pg)  # every rank masks the same number of tokens (no host sync)
-                mean_logits = ops.gemv_bf16(w2t, hsum, 1.0 / (Mm * w), b2t, 1.0)
-                ops.center_ema_(center_patch, mean_logits, 1, patch_momentum)
+                ops.center_ema_(center_patch, mean_logits[1], 1, patch_momentum)
         if need_grad:
             ctx.save_for_backward(xs, a_s, hs_e, gt, db2p, w1s, w2s)
             ctx.plan, ctx.s_head = plan, s_head
@@ -572,8 +588,9 @@ class _FusedHeadLoss(torch.autograd.Function):
         da, part = ops.gelu_bwd(dh, a_s, scale_dev=up)
         db1 = ops.cols_sum(part)
         _accumulate_grad(s_head[0].bias, lambda out, acc: ops.axpby(db1, 1.0, out if acc else None, 1.0, out=out))
-        _accumulate_grad(s_head[0].weight, lambda out, acc: ops.gemm_bf16(
-            da, xs, a_mn_major=True, b_mn_major=True, out=out, accumulate=acc))
+        # dW1 = da^T x: 3x3 output tiles with a reduction over every row -> split-K, slabs summed in fixed order
+        dw1_parts = ops.gemm_bf16_splitk(da, xs, a_mn_major=True, b_mn_major=True)
+        _accumulate_grad(s_head[0].weight, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))
         dx = ops.gemm_bf16(da, w1s, b_mn_major=True)
         d_cls = dx[:plan.Ms].to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
         d_patch = dx[plan.Ms:].to(ctx.in_dtypes[1]) if (plan.Mm and ctx.needs_input_grad[1]) else None

@@ -118,11 +118,20 @@ def lse_combine(gathered: torch.Tensor, add: float = 0.0) -> torch.Tensor:
     return out
 
 
-def cols_sum(x: torch.Tensor) -> torch.Tensor:
+def cols_sum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk_cuda(x)
     ld = _rowmajor(x)
     rows, K = x.shape
-    out = torch.empty(K, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(K, dtype=torch.float32, device=x.device)
+    assert out.dtype == torch.float32 and out.numel() == K and out.is_contiguous()
+    if rows >= 1024 and K <= 8192:
+        # tall and skinny: K/128 CTAs would each walk every row - sum 64-row chunks first (fixed order)
+        chunk = 64
+        part = torch.empty((rows + chunk - 1) // chunk, K, dtype=torch.float32, device=x.device)
+        _ext.call("dinox_cols_sum_chunked", _p(x), DT[x.dtype], rows, K, ld, chunk, _p(part), _stream())
+        _ext.call("dinox_cols_sum", _p(part), DT[torch.float32], part.shape[0], K, K, _p(out), _stream())
+        return out
     _ext.call("dinox_cols_sum", _p(x), DT[x.dtype], rows, K, ld, _p(out), _stream())
     return out
 
@@ -330,7 +339,8 @@ def gelu_fwd(a: torch.Tensor) -> torch.Tensor:
 def gelu_bwd(dh: torch.Tensor, a: torch.Tensor, scale_dev: Optional[torch.Tensor] = None):
     rows, D = a.shape
     da = torch.empty(rows, D, dtype=torch.bfloat16, device=a.device)
-    part = torch.empty((rows + 63) // 64, D, dtype=torch.float32, device=a.device)
+    n_part = int(_ext.lib().dinox_gelu_bwd_workspace_bytes(rows, D)) // (4 * D)
+    part = torch.empty(n_part, D, dtype=torch.float32, device=a.device)
     _ext.call("dinox_gelu_bwd", _p(dh), _p(a), rows, D, _p(scale_dev), _p(da), _p(part), _stream())
     return da, part
 
@@ -340,6 +350,27 @@ def gemv_bf16(w: torch.Tensor, x: torch.Tensor, alpha: float = 1.0, bias: Option
     K, D = w.shape
     out = torch.empty(K, dtype=torch.float32, device=w.device)
     _ext.call("dinox_gemv_bf16", _p(w), _rowmajor(w), _p(x), K, D, float(alpha), _p(bias), float(beta), _p(out), _stream())
+    return out
+
+
+def gemv_bf16_multi(w: torch.Tensor, xs: torch.Tensor, alphas: Sequence[float], bias: Optional[torch.Tensor] = None,
+                    beta: float = 1.0) -> torch.Tensor:
+    """xs: (nvec, D) fp32 -> out (nvec, K): alphas[v] * W @ xs[v] + beta * bias, one pass over W."""
+    K, D = w.shape
+    nvec = xs.shape[0]
+    assert xs.is_contiguous() and xs.shape[1] == D and len(alphas) == nvec
+    out = torch.empty(nvec, K, dtype=torch.float32, device=w.device)
+    al = (ctypes.c_float * nvec)(*[float(a) for a in alphas])
+    _ext.call("dinox_gemv_bf16_multi", _p(w), _rowmajor(w), _p(xs), nvec, K, D, al, _p(bias), float(beta), _p(out), _stream())
+    return out
+
+
+def sum_slabs(parts: torch.Tensor, out: torch.Tensor, accumulate: bool = False, scale: float = 1.0,
+              scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out (+)= scale * parts.sum(0) for contiguous (S, ...) fp32 split-K slabs (fixed order)."""
+    assert parts.is_contiguous() and out.is_contiguous() and parts[0].numel() == out.numel()
+    _ext.call("dinox_sum_slabs", _p(parts), parts.shape[0], parts.stride(0), out.numel(), _p(scale_dev), float(scale),
+              _p(out), int(accumulate), _stream())
     return out
 
 

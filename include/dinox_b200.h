@@ -83,6 +83,10 @@ DINOX_API int dinox_lse_combine(const float* gathered, int world, int64_t K, flo
  * scripts/phase5_big_run.py:688) */
 DINOX_API int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld,
                              float* out, dinox_stream_t stream);
+/* partial[c, :] = column sums of rows [c*chunk, min((c+1)*chunk, rows)): first phase of a tall-skinny
+ * column sum (finish with dinox_cols_sum on the (ceil(rows/chunk), K) fp32 partial matrix) */
+DINOX_API int dinox_cols_sum_chunked(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, int64_t chunk,
+                                     float* partial, dinox_stream_t stream);
 /* a5: center <- center*m + (colsum*inv_rows)*(1-m)   (scripts/phase5_big_run.py:689) */
 DINOX_API int dinox_center_ema(float* center, const float* colsum, float inv_rows, float m,
                                int64_t K, dinox_stream_t stream);
@@ -234,6 +238,14 @@ DINOX_API int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int6
  * logits from the mean head activation, used for the centre update of the fused path (:686-690) */
 DINOX_API int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64_t D, float alpha,
                               const float* bias, float beta, float* out, dinox_stream_t stream);
+/* nvec (1..4) vectors X (nvec, D) against the same matrix in ONE pass over W: out (nvec, K),
+ * out[v][k] = alphas_host[v] * sum_d W[k,d] X[v,d] + beta * bias[k]  (CLS and iBOT centre means together) */
+DINOX_API int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
+                                    const float* alphas_host, const float* bias, float beta, float* out,
+                                    dinox_stream_t stream);
+/* dst[i] (+)= scale*(*scale_dev) * sum_{s<slabs} src[s*slab_stride + i]: fixed-order reduction of split-K slabs */
+DINOX_API int dinox_sum_slabs(const float* src, int slabs, int64_t slab_stride, int64_t n, const float* scale_dev,
+                              float scale, float* dst, int accumulate, dinox_stream_t stream);
 /* dst[r,:] (+)= scale*(*scale_dev) * sum_{i in [ptr[r],ptr[r+1])} sum_{s<slabs} src[s*slab_stride + ent[i]*ld_src,:]
  * (fp32; slabs > 1 sums the partial outputs of dinox_gemm_bf16_splitk in fixed order) */
 DINOX_API int dinox_gather_sum_rows(const float* src, int64_t ld_src, int slabs, int64_t slab_stride,
