@@ -307,22 +307,28 @@ def _ema_update(teacher: nn.Module, student: nn.Module, m: float) -> None:
 # =================================================================================================
 # a1 projection head as an nn.Sequential with the reference's parameter keys
 # =================================================================================================
-_BF16_CACHE: Dict[int, Tuple[int, int, int, torch.Tensor]] = {}
+_BF16_CACHE: Dict[int, Tuple] = {}
 _WEIGHT_EPOCH = [0]  # bumped by ema_update: raw-pointer kernels do not touch tensor version counters
 
 
 def bf16_weight(p: torch.Tensor) -> torch.Tensor:
     """bf16 copy of a weight, cached until the parameter is modified in place (autocast does the same
-    per forward).  Keyed on storage pointer + version counter."""
+    per forward).  An entry is valid only for the very same tensor object (weak reference: Python ids
+    and allocator blocks are both recycled), the same version counter, storage pointer and EMA epoch."""
+    import weakref
     key = id(p)
     ver = p._version
     hit = _BF16_CACHE.get(key)
-    if hit is not None and hit[0] == ver and hit[1] == p.data_ptr() and hit[2] == _WEIGHT_EPOCH[0]:
-        return hit[3]
+    if (hit is not None and hit[0]() is p and hit[1] == ver and hit[2] == p.data_ptr() and hit[3] == _WEIGHT_EPOCH[0]
+            and hit[4].shape == p.shape):
+        return hit[4]
     w = p.detach()
     out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
     ops.gather_cast_bf16(w.reshape(w.shape[0], -1), None, out.reshape(w.shape[0], -1))
-    _BF16_CACHE[key] = (ver, p.data_ptr(), _WEIGHT_EPOCH[0], out)
+    if len(_BF16_CACHE) > 64:   # drop entries whose parameter is gone
+        for k in [k for k, v in _BF16_CACHE.items() if v[0]() is None]:
+            del _BF16_CACHE[k]
+    _BF16_CACHE[key] = (weakref.ref(p), ver, p.data_ptr(), _WEIGHT_EPOCH[0], out)
     return out
 
 

@@ -464,3 +464,19 @@ def test_no_cpu_fallback(dx):
         dx.compute_gram_anchoring_loss(torch.zeros(1, 5, 8), torch.zeros(1, 5, 8))
     with pytest.raises(Exception):
         dx.ProjectionHead(8, 16)(torch.zeros(2, 8))
+
+
+def test_bf16_weight_cache_survives_recycled_ids_and_blocks(dx):
+    """The cached bf16 copies are keyed on the live parameter object: a freed parameter whose Python id
+    and allocator block are both reused by a different weight must not hit the stale entry."""
+    g = torch.Generator().manual_seed(5)
+    for i in range(40):
+        shape = (32 + 8 * (i % 5), 64)
+        w = torch.nn.Parameter(torch.randn(*shape, generator=g).to(DEV))
+        b = dx.bf16_weight(w)
+        assert b.shape == w.shape and torch.equal(b, w.detach().to(torch.bfloat16))
+        assert dx.bf16_weight(w) is b            # cache hit while the parameter is unchanged
+        with torch.no_grad():
+            w.mul_(2.0)                           # in-place update bumps the version counter
+        assert torch.equal(dx.bf16_weight(w), w.detach().to(torch.bfloat16))
+        del w, b

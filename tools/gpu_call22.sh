@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for tag in "" ctrl0; do for pair in 1 7; do
+  DINOX_LIB_TAG=$tag DINOX_PAIR=$pair timeout 120 python tools/probe_time.py 2>&1 | tail -1
+done; done | tee gpurun_out/probe_time.log
+bash tools/gpu_quick.sh
