@@ -235,6 +235,9 @@ __device__ __forceinline__ float4 lds128(const float* p) {
   return v;
 }
 
+#ifndef DINOX_EXP_EPI_MODE
+#define DINOX_EXP_EPI_MODE 0
+#endif
 #ifndef DINOX_EPI_WARPS
 #define DINOX_EPI_WARPS 8   // epilogue warps of the two row-math kernels (pass 1 / pass 2): 8 or 16
 #endif
@@ -243,36 +246,42 @@ struct EpiStats {
   static constexpr bool kUsesTmaStore = false;
   static constexpr int kEpiWarps = DINOX_EPI_WARPS;
   static constexpr int kGroups = kEpiWarps / 4;          // column groups (each TMEM lane quarter has kGroups warps)
-  static constexpr int kEpiSmemBytes = 2 * 256 * 4;
+  static constexpr int kColsW = 256 / kGroups;           // columns per warp (128 or 64)
+  // every warp keeps its own copy of the column offsets of its kColsW columns: no CTA-wide barrier per tile
+  static constexpr int kEpiSmemBytes = kEpiWarps * kColsW * 4;
   struct Params {
     float scale2;
     const float* col2;   // (N) log2-unit column offsets, may be NULL
     float2* partial;     // (M, kGroups*num_n_tiles)
   };
   struct State {
-    float col;   // this thread's column offset of the NEXT tile (prefetched while the current tile is processed)
+    float col[kColsW / 32];   // raw prefetched column offsets of the NEXT tile (this lane's columns of the warp's group)
   };
   static __device__ __forceinline__ void finish(const Params&, const CoreParams&, int, int, State&) {}
   template <int BN>
   struct Impl {
     static_assert(BN == 256, "EpiStats is written for 256-wide tiles");
-    static constexpr int kCols = BN / kGroups;           // columns per warp (128 or 64)
+    static constexpr int kCols = kColsW;
     static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
                                                  State& st) {
-      const int i = epi_warp * 32 + lane;
-      const int col = tc.n_tile * BN + i;
-      st.col = (i < BN && col < p.N) ? (e.col2 ? __ldg(e.col2 + col) : 0.f) : -INFINITY;
+      const int col0 = tc.n_tile * BN + (epi_warp >> 2) * kCols;
+#pragma unroll
+      for (int j = 0; j < kCols / 32; ++j) {
+        const int col = col0 + j * 32 + lane;
+        st.col[j] = (col < p.N) ? (e.col2 ? __ldg(e.col2 + col) : 0.f) : -INFINITY;
+      }
     }
-    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int acc_stage,
-                                                    int epi_warp, int lane, uint8_t* smem, State& st) {
-      float* buf = reinterpret_cast<float*>(smem) + acc_stage * 256;
-      const int i = epi_warp * 32 + lane;
-      if (i < BN) buf[i] = st.col;
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int epi_warp, int lane,
+                                                    uint8_t* smem, State& st) {
+      float* buf = reinterpret_cast<float*>(smem) + epi_warp * kCols;
+      __syncwarp();   // every lane is done with the previous tile's offsets
+#pragma unroll
+      for (int j = 0; j < kCols / 32; ++j) buf[j * 32 + lane] = st.col[j];
+      __syncwarp();
     }
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap*,
                                                 uint32_t tmem_acc, int acc_stage, int epi_warp, int lane, uint8_t* smem, State&) {
-      const float* buf = reinterpret_cast<const float*>(smem) + acc_stage * 256;
+      const float* buf = reinterpret_cast<const float*>(smem) + epi_warp * kCols;
       const int q = epi_quarter();
       const int grp = epi_warp >> 2;
       const int row = tc.m_tile * BM + q * 32 + lane;
@@ -284,7 +293,7 @@ struct EpiStats {
         sm100::tmem_ld32x2(taddr + c * 64, taddr + c * 64 + 32, v[0], v[1]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float* cb = buf + grp * kCols + c * 64 + h * 32;
+          const float* cb = buf + c * 64 + h * 32;
           float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -354,10 +363,13 @@ struct EpiGradT {
   static constexpr int kCols = 128 / kGroups;          // entries per warp and tile (64 or 32)
   static constexpr int kRowBytes = kCols * 2;          // staging row: 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
   static constexpr int kWarpBuf = 32 * kRowBytes;      // 4 KB or 2 KB per warp
-  // Shared memory buys pipeline depth here, so the epilogue keeps ONE staging buffer per warp and ONE
-  // copy of the per-entry constants, and pays for it with a second named barrier per tile.
-  static constexpr int kStageBytes = kEpiWarps * kWarpBuf;     // per-warp G staging (TMA store source)
-  static constexpr int kEpiSmemBytes = kStageBytes + 3 * 128 * 4;
+  static constexpr int kBufs = 2;                      // staging buffers per warp (TMA store source)
+  // Every epilogue warp is self-contained: its own staging buffers and its own copy of the per-entry
+  // constants of its kCols entries (each warp loads them itself: a few hundred redundant bytes per
+  // tile instead of two CTA-wide named barriers per tile that made every warp wait for the slowest).
+  static constexpr int kStageBytes = kEpiWarps * kBufs * kWarpBuf;
+  static constexpr int kConstFloats = 3 * kCols;       // per warp: -lse2 | -rb2 | cw/tau_s
+  static constexpr int kEpiSmemBytes = kStageBytes + kEpiWarps * kConstFloats * 4;
   struct Params {
     float as2, at2, inv_tau_s;
     const float* cs2;       // (K)
@@ -372,9 +384,12 @@ struct EpiGradT {
   };
   struct State {
     float loss_a = 0.f, loss_b = 0.f;
-    float nl, nr, cw;   // prefetched per-entry constants of the next tile (threads 0..127 of the epilogue)
-    float cs, ct;       // prefetched per-prototype offsets of the next tile (this thread's TMEM lane)
-    float cs_cur, ct_cur;   // ... of the tile being processed (latched by prologue)
+    // raw prefetched values of the NEXT tile (no arithmetic on them until prologue(): a dependent
+    // instruction right after the load would stall the warp for the whole global-memory latency)
+    float nl[kCols / 32], nr[kCols / 32], cw[kCols / 32];   // this lane's entries of the warp's column group
+    float cs, ct;            // per-prototype offsets of this thread's TMEM lane
+    float cs_cur, ct_cur;    // ... of the tile being processed (latched by prologue)
+    int flip = 0;
   };
   static __device__ __forceinline__ void finish(const Params& e, const CoreParams&, int epi_warp, int lane, State& st) {
     const float a = warp_sum(st.loss_a), b = warp_sum(st.loss_b);
@@ -400,27 +415,32 @@ struct EpiGradT {
   struct Impl {
     static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
                                                  State& st) {
-      const int i = epi_warp * 32 + lane;
-      if (i < BN) {
-        const int ent = tc.n_tile * BN + i;
+      const int ent0 = tc.n_tile * BN + (epi_warp >> 2) * kCols;
+#pragma unroll
+      for (int j = 0; j < kCols / 32; ++j) {
+        const int ent = ent0 + j * 32 + lane;
         const bool ok = ent < p.N;
-        st.nl = ok ? -__ldg(e.lse2 + ent) : 0.f;
-        st.nr = ok ? -__ldg(e.rb2 + ent) : 0.f;
-        st.cw = ok ? __ldg(e.cw + ent) * e.inv_tau_s : 0.f;
+        st.nl[j] = ok ? __ldg(e.lse2 + ent) : 0.f;
+        st.nr[j] = ok ? __ldg(e.rb2 + ent) : 0.f;
+        st.cw[j] = ok ? __ldg(e.cw + ent) : 0.f;
       }
       const int k = tc.m_tile * BM + epi_quarter() * 32 + lane;
       const bool alt = e.ct2_alt && tc.n_tile * BN >= e.alt_from;
       st.cs = k < p.M ? __ldg(e.cs2 + k) : 0.f;
       st.ct = k < p.M ? __ldg((alt ? e.ct2_alt : e.ct2) + k) : 0.f;
     }
-    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int epi_warp, int lane,
+    static __device__ __forceinline__ void prologue(const Params& e, const CoreParams&, TileCoord, int, int epi_warp, int lane,
                                                     uint8_t* smem, State& st) {
-      float* buf = reinterpret_cast<float*>(smem + kStageBytes);
-      const int i = epi_warp * 32 + lane;
-      asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory");   // every warp is done reading the previous constants
-      if (i < BN) { buf[i] = st.nl; buf[128 + i] = st.nr; buf[256 + i] = st.cw; }
+      float* buf = reinterpret_cast<float*>(smem + kStageBytes) + epi_warp * kConstFloats;
+      __syncwarp();   // every lane is done reading the previous tile's constants
+#pragma unroll
+      for (int j = 0; j < kCols / 32; ++j) {
+        buf[j * 32 + lane] = -st.nl[j];
+        buf[kCols + j * 32 + lane] = -st.nr[j];
+        buf[2 * kCols + j * 32 + lane] = st.cw[j] * e.inv_tau_s;
+      }
       st.cs_cur = st.cs; st.ct_cur = st.ct;
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      __syncwarp();
     }
 
     // 16 entries of one prototype row: logits -> (p, q) -> gradient, loss and bias-gradient terms;
@@ -429,9 +449,18 @@ struct EpiGradT {
                                                    const float* cb, float cs, float ct, const Stage& stg, int c16,
                                                    float& l0, float& l1, float& d0, float& d1) {
       uint32_t packed[8];
+#if DINOX_EXP_EPI_MODE == 1   // experiment: TMEM loads only, trivial math
+      {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a += __uint_as_float(sr[j]) + __uint_as_float(tr[j]);
+        l0 += a;
+        return;
+      }
+#endif
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 nl = lds128(cb + j), nr = lds128(cb + 128 + j), cw = lds128(cb + 256 + j);
+        const float4 nl = lds128(cb + j), nr = lds128(cb + kCols + j), cw = lds128(cb + 2 * kCols + j);
         const float nls[4] = {nl.x, nl.y, nl.z, nl.w}, nrs[4] = {nr.x, nr.y, nr.z, nr.w}, cws[4] = {cw.x, cw.y, cw.z, cw.w};
         float g[4];
 #pragma unroll
@@ -457,7 +486,7 @@ struct EpiGradT {
                                                 uint32_t tmem_acc, int acc_stage, int epi_warp, int lane, uint8_t* smem,
                                                 State& st) {
       static_assert(BN == 128, "EpiGradT is written for 128-entry tiles");
-      const float* buf = reinterpret_cast<const float*>(smem + kStageBytes);
+      const float* cb = reinterpret_cast<const float*>(smem + kStageBytes) + epi_warp * kConstFloats;
       const int q = epi_quarter();
       const int grp = epi_warp >> 2;
       const int k0 = tc.m_tile * BM + q * 32;
@@ -467,18 +496,29 @@ struct EpiGradT {
       const float cs = st.cs_cur, ct = st.ct_cur;
       const uint32_t ts = tmem_acc + ((uint32_t)(q * 32) << 16) + grp * kCols;
       const uint32_t tt = ts + BN;
-      const float* cb = buf + grp * kCols;
-      uint8_t* wbuf = smem + epi_warp * kWarpBuf;
+      uint8_t* wbuf = smem + (epi_warp * kBufs + st.flip) * kWarpBuf;
       Stage stg;
       stg.init(wbuf, lane);
       float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
       uint32_t sa[16], ta[16], sb[16], tb[16];
       sm100::tmem_ld16_nowait(ts, sa);
       sm100::tmem_ld16_nowait(tt, ta);
-      // the staging buffer about to be refilled must no longer be read by the previous tile's store
-      if (lane == 0) sm100::tma_store_wait_read<0>();
+      // the staging buffer about to be refilled must no longer be read by the store issued kBufs tiles ago
+      if (lane == 0) sm100::tma_store_wait_read<kBufs - 1>();
       __syncwarp();
       sm100::tmem_wait_ld();
+#if DINOX_EXP_EPI_MODE == 2   // experiment: math only (one TMEM load per tile, registers reused)
+      chunk16(e, sa, ta, cb, cs, ct, stg, 0, l0, l1, d0, d1);
+      sm100::pin16(sa); sm100::pin16(ta);
+      chunk16(e, sa, ta, cb + 16, cs, ct, stg, 1, l0, l1, d0, d1);
+      sm100::pin16(sa); sm100::pin16(ta);
+      chunk16(e, sa, ta, cb + 32, cs, ct, stg, 2, l0, l1, d0, d1);
+      sm100::pin16(sa); sm100::pin16(ta);
+      chunk16(e, sa, ta, cb + 48, cs, ct, stg, 3, l0, l1, d0, d1);
+      if (false) {
+#else
+      {
+#endif
       sm100::tmem_ld16_nowait(ts + 16, sb);
       sm100::tmem_ld16_nowait(tt + 16, tb);
       sm100::pin16(sa); sm100::pin16(ta);
@@ -500,14 +540,16 @@ struct EpiGradT {
         sm100::pin16(sb); sm100::pin16(tb);
         chunk16(e, sb, tb, cb + 48, cs, ct, stg, 3, l0, l1, d0, d1);
       }
+      }
       // G tile rows [k0, k0+32) x entries [ent0, ent0+kCols) leave as one TMA store (clipped at K and E)
       sm100::fence_proxy_async_smem();
       __syncwarp();
       const int ent0 = tc.n_tile * BN + grp * kCols;
-      if (lane == 0 && k0 < p.M && ent0 < p.N) {
-        sm100::tma_store_3d(tmC, wbuf, ent0, k0, 0);
-        sm100::tma_store_commit();
+      if (lane == 0) {
+        if (k0 < p.M && ent0 < p.N) sm100::tma_store_3d(tmC, wbuf, ent0, k0, 0);
+        sm100::tma_store_commit();   // always: wait_read<kBufs-1> counts groups
       }
+      st.flip ^= 1;
       if (kok) {
         if (e.db2_partial) e.db2_partial[(int64_t)(tc.n_tile * kGroups + grp) * p.M + k] = d0 + d1;
         if (alt) st.loss_b += l0 + l1; else st.loss_a += l0 + l1;

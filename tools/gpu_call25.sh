@@ -1,0 +1,6 @@
+#!/bin/bash
+export DINOX_LIB_TAG=math
+python tools/probe_prof.py 1 > gpurun_out/prof_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 2 -c 1 -o gpurun_out/prof_math \
+    python tools/probe_prof.py 1 > gpurun_out/prof_ncu.log 2>&1
+tail -2 gpurun_out/prof_plain.log; tail -2 gpurun_out/prof_ncu.log
