@@ -293,11 +293,22 @@ def run_ours(args):
         "gemm_dW2": 2.0 * D * K * rows_s, "gemm_dH": 2.0 * D * K * rows_s,
     }
     ach = alg_flops.get(dom, 0.0) / (kt[dom] * 1e-3) / 1e12
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        k = tj["kernels"].get(dom)
+        if k and args.config == "C2":
+            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
+            traffic_src = "profiles/r01_traffic.json (" + tj["source"] + ")"
+    except Exception:
+        pass
     peak_tf = peaks["tf_sustained"]
     step_alg_tf = sh.flops() / (ms_per_step * 1e-3) / 1e12
     roofline = {
         "kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": ach / peak_tf, "traffic": None, "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
+        "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
         "kernel_ms": kt[dom], "kernels_ms": kt,
         "step_algorithmic_tflops": step_alg_tf, "step_frac": step_alg_tf / peak_tf,
         "ema_gbs": (12.0 * step.n_params / (kt["ema_multi"] * 1e-3) / 1e9) if "ema_multi" in kt else None,
@@ -306,7 +317,7 @@ def run_ours(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, desc, _ = cpu_oracle_step_time(args.config, args.cpu_sample_batch, 2, 1, args.accum)
+        v, cores, desc, _ = cpu_oracle_step_time(args.config, args.cpu_sample_batch, args.cpu_steps, 2, args.accum)
         cpu_baseline = {"value": v, "unit": "crops/s", "cores": cores, "kind": "port", "sample": desc}
 
     line = {
@@ -353,6 +364,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--accum", type=int, default=4)
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=40, help="timed oracle steps of the cpu_baseline leg (~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     global _OUT
