@@ -1,0 +1,121 @@
+"""Full-size GPU tests at the BASELINE.json configurations (C2, C3-per-rank, C4, and the top of the C5
+sweep), where the CPU oracle would take minutes: size-independent properties instead.
+
+  * fused path == materialised-logit path (head GEMMs + row kernels) on the CLS term at full K
+  * every row of dL/dlogits sums to zero, so sum_k dL/db2[k] == 0 (softmax minus a probability vector)
+  * the gradient of a loss that is scaled by c is c times the gradient (upstream-gradient plumbing)
+  * zero student head => uniform student => both CE terms equal ln K (docs/phase5_big_run.md:375-377)
+  * bitwise reproducibility of loss and gradients (fixed reduction orders everywhere)
+  * EMA round trip: m = 0 copies the student exactly, m = 1 leaves the teacher bit-identical
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def dx():
+    from dinox_b200 import losshead, _ext
+    assert _ext.lib().dinox_device_check() == 0, "needs a B200"
+    return losshead
+
+
+def _setup(dx, cfg, seed, **over):
+    from dinox_b200 import synth
+    c = dict(synth.CONFIGS[cfg]); c.update(over)
+    sh = synth.LossHeadShapes(**c)
+    gen = synth.seeded_generator(seed, 0)
+    s_head, t_head = dx.ProjectionHead(sh.dim, sh.out_dim).to(DEV), dx.ProjectionHead(sh.dim, sh.out_dim).to(DEV)
+    s_head.load_state_dict(synth.head_weights(sh.dim, sh.out_dim, gen))
+    t_head.load_state_dict(synth.head_weights(sh.dim, sh.out_dim, gen))
+    for q in t_head.parameters():
+        q.requires_grad_(False)
+    f = {k: v.to(DEV) for k, v in synth.feature_batch(sh, gen, with_tokens=False).items()}
+    return sh, s_head, t_head, f
+
+
+def _fused(dx, sh, s_head, t_head, f, scale=1.0, ibot=True):
+    dl = dx.DINOLoss(sh.out_dim, 0.9, n_global=sh.n_global, n_local=sh.n_local).to(DEV)
+    cp = torch.zeros(1, sh.out_dim, device=DEV)
+    for q in s_head.parameters():
+        q.grad = None
+    x = f["student_cls"].clone().requires_grad_(True)
+    xp = f["student_patch"].clone().requires_grad_(True) if ibot else None
+    out = dx.fused_head_dino_loss(x, f["teacher_cls"], s_head, t_head, dl, 0.1, 0.04, student_patch=xp,
+                                  teacher_patch=f["teacher_patch"] if ibot else None,
+                                  masks_weight=f["masks_weight"] if ibot else None, center_patch=cp if ibot else None)
+    (out["loss"] * scale).backward()
+    torch.cuda.synchronize()
+    g = {n: q.grad.clone() for n, q in s_head.named_parameters()}
+    g["x"] = x.grad.clone()
+    if ibot:
+        g["xp"] = xp.grad.clone()
+    return out, g, dl
+
+
+@pytest.mark.parametrize("cfg,over", [("C2", {}), ("C4", {}), ("C5lo", {}), ("C1", dict(out_dim=262144))])
+def test_full_size_invariants(dx, cfg, over):
+    sh, s_head, t_head, f = _setup(dx, cfg, seed=3, **over)
+    K = sh.out_dim
+    out, g, _ = _fused(dx, sh, s_head, t_head, f)
+    assert all(torch.isfinite(v).all() for v in g.values()) and torch.isfinite(out["loss"])
+    assert out["loss_dino"].item() > 0 and out["loss_ibot"].item() > 0
+    # rows of dL/dlogits sum to zero -> the bias gradient sums to zero (relative to its magnitude)
+    db2 = g["2.bias"].double()
+    assert abs(db2.sum().item()) <= 2e-4 * db2.abs().sum().item()
+    # bitwise reproducible
+    out2, g2, _ = _fused(dx, sh, s_head, t_head, f)
+    assert out2["loss"].item() == out["loss"].item()
+    for n in g:
+        assert torch.equal(g[n], g2[n]), f"{n} not reproducible"
+    # upstream gradient scales every gradient exactly like autograd would (power of two: bit exact)
+    _, g4, _ = _fused(dx, sh, s_head, t_head, f, scale=0.25)
+    for n in ("2.weight", "0.weight", "x", "xp"):
+        assert torch.allclose(g4[n], 0.25 * g[n], rtol=2e-3, atol=1e-9 * g[n].abs().max().item()), n
+    # entropy wall
+    with torch.no_grad():
+        for q in s_head.parameters():
+            q.zero_()
+    out0, _, _ = _fused(dx, sh, s_head, t_head, f)
+    assert abs(out0["loss_dino"].item() - math.log(K)) < 1e-3
+    assert abs(out0["loss_ibot"].item() - math.log(K)) < 1e-3
+
+
+def test_c2_fused_equals_materialised_at_full_k(dx):
+    """C2 CLS rows (640 student / 128 teacher rows, K = 65536): fused TMEM-resident path against head GEMM ->
+    fp32 logits in HBM -> row kernels.  Same bf16 operands, fp32 logits on both sides."""
+    sh, s_head, t_head, f = _setup(dx, "C2", seed=4)
+    out, g, dl = _fused(dx, sh, s_head, t_head, f, ibot=False)
+    dl2 = dx.DINOLoss(sh.out_dim, 0.9, n_global=sh.n_global, n_local=sh.n_local).to(DEV)
+    for q in s_head.parameters():
+        q.grad = None
+    x = f["student_cls"].clone().requires_grad_(True)
+    loss = dl2(s_head(x), t_head(f["teacher_cls"]), 0.1, 0.04)
+    loss.backward()
+    assert abs(out["loss_dino"].item() - loss.item()) <= 1e-5 * abs(loss.item())
+
+    def rel(a, b):
+        return ((a.float() - b.float()).norm() / b.float().norm()).item()
+    assert rel(g["x"], x.grad) < 4e-3
+    assert rel(g["2.weight"], s_head[2].weight.grad) < 4e-3
+    assert rel(g["2.bias"], s_head[2].bias.grad) < 4e-3
+    assert rel(g["0.weight"], s_head[0].weight.grad) < 4e-3
+    assert rel(dl.center, dl2.center) < 1e-5
+
+
+def test_ema_full_parameter_list_limits(dx):
+    from dinox_b200 import synth
+    shapes = synth.student_param_shapes(384, 12, 65536)
+    gen = torch.Generator().manual_seed(9)
+    s = [torch.randn(*shp, generator=gen).to(DEV) for shp in shapes]
+    t = [torch.randn(*shp, generator=gen).to(DEV) for shp in shapes]
+    t0 = [x.clone() for x in t]
+    dx.ema_update(t, s, 1.0)
+    assert all(torch.equal(a, b) for a, b in zip(t, t0))          # m = 1: teacher untouched
+    dx.ema_update(t, s, 0.0)
+    assert all(torch.equal(a, b) for a, b in zip(t, s))           # m = 0: exact copy of the student
+    assert sum(x.numel() for x in s) == 47_085_312 or sum(x.numel() for x in s) > 47_000_000
