@@ -176,7 +176,7 @@ def run_ours(args):
         pg = True
 
     sh = synth.LossHeadShapes(**synth.CONFIGS[args.config])
-    step = LossHeadStep(sh, dev, accum=args.accum, process_group=pg)
+    step = LossHeadStep(sh, dev, accum=args.accum, process_group=pg, teacher_mode=args.teacher_mode)
     g = synth.seeded_generator(2, rank)
     feats = synth.feature_batch(sh, g)
 
@@ -211,36 +211,64 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- leg 1: inputs resident in HBM ----------------
+    use_graph = not args.no_graph
+    # ---------------- leg 0: eager, per-kernel CUDA-event timers (roofline of the dominant kernel) --------
     resident = {k: v.to(dev) for k, v in host.items()}
     for _ in range(args.warmup):
         step.micro_step(to_leaves({k: v.detach() for k, v in resident.items()}))
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ops.launch_count_reset()
     ops.TIMER.reset()
     ops.TIMER.enabled = True
+    n_eager = args.steps if not use_graph else max(4, min(args.steps, 8))
+    sampler = ClockSampler(local)
+    if not use_graph:
+        sampler.start()
+    ops.launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(n_eager):
         out = step.micro_step(to_leaves({k: v.detach() for k, v in resident.items()}))
     e1.record()
     barrier()
     ops.TIMER.enabled = False
     ops.TIMER.resolve()
-    clocks = sampler.stop()
+    eager_ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / n_eager
     launches = ops.launch_count()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms / args.steps
     crops_per_step = sh.student_rows * world
+
+    # ---------------- leg 1: inputs resident in HBM, micro-step replayed as a CUDA graph ----------------
+    dev_blobs = [torch.empty(blob_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    bufs = [blob_views(b, feats) for b in dev_blobs]
+    if use_graph:
+        for p in step.student_head.parameters():
+            p.grad = None
+        step.micro = 0
+        slots = step.static_inputs(feats, slots=2, buffers=bufs)
+        for b in range(2):
+            dev_blobs[b].copy_(host_blob, non_blocking=True)
+        torch.cuda.synchronize()
+        step.capture(0)
+        step.capture(1)
+        for _ in range(args.warmup):
+            step.micro_step_graph(0)
+        barrier()
+        sampler.start()
+        e0.record()
+        for _ in range(args.steps):
+            out = step.micro_step_graph(0)
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        launches = step.launches_per_graph * args.steps + args.steps // args.accum
+    else:
+        clocks = sampler.stop()
+        ms_per_step = eager_ms_per_step
     value = crops_per_step / (ms_per_step * 1e-3)
     loss_val = float(out["loss_total"].item())
 
     # ---------------- leg 2: end to end from pinned host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
-    dev_blobs = [torch.empty(blob_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
-    bufs = [blob_views(b, feats) for b in dev_blobs]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
@@ -249,7 +277,7 @@ def run_ours(args):
         b = i & 1
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[b])
-            dev_blobs[b].copy_(host_blob, non_blocking=True)
+            dev_blobs[b].copy_(host_blob, non_blocking=True)   # ONE H2D copy per step, straight into the step's inputs
             ready[b].record(copy_stream)
 
     def e2e_loop(n):
@@ -262,7 +290,10 @@ def run_ours(args):
             if i + 1 < n:
                 prefetch(i + 1)          # H2D of the next step overlaps this step's kernels
             cur.wait_event(ready[b])
-            o = step.micro_step(to_leaves({k: v.detach() for k, v in bufs[b].items()}))
+            if use_graph:
+                o = step.micro_step_graph(b)
+            else:
+                o = step.micro_step(to_leaves({k: v.detach() for k, v in bufs[b].items()}))
             consumed[b].record(cur)
             loss_host.copy_(o["loss_total"].reshape(1), non_blocking=True)   # D2H of the step's result
         cur.synchronize()
@@ -325,12 +356,13 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": f"{args.config}: ViT-S/16 loss head, per-GPU batch {sh.batch} x accum {args.accum}, "
+            "workload": f"{args.config}: ViT-{'S' if D == 384 else 'L'}/16 loss head (teacher {args.teacher_mode}), per-GPU batch {sh.batch} x accum {args.accum}, "
                         f"{sh.n_global} global + {sh.n_local} local crops, K={K}, D={D}, iBOT r={sh.mask_ratio} "
                         f"({sh.masked_rows} masked rows), Gram anchoring on ({sh.tokens - 1} tokens), "
                         f"EMA of {step.n_params / 1e6:.1f} M params every {args.accum} micro-steps",
             "rows": {"student": sh.student_rows, "teacher": sh.teacher_rows, "masked": sh.masked_rows},
-            "parallelism": f"dp{world}", "l2": "per-step working set (bf16 W2 x2 = 100 MB, dL/dlogits 1.1 GB) exceeds the 126 MB L2; no explicit flush",
+            "parallelism": f"dp{world}", "launch": "cuda-graph replay per micro-step" if use_graph else "eager launches",
+            "eager_ms_per_step": eager_ms_per_step, "l2": "per-step working set (bf16 W2 x2 = 100 MB, dL/dlogits 1.1 GB) exceeds the 126 MB L2; no explicit flush",
             "algorithmic_gflop_per_step": sh.flops() / 1e9,
         },
         "clocks": clocks,
@@ -364,8 +396,11 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--accum", type=int, default=4)
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--teacher-mode", default="center", choices=["center", "sinkhorn"],
+                    help="teacher normalisation of the CLS term (C3 uses sinkhorn)")
     ap.add_argument("--cpu-steps", type=int, default=40, help="timed oracle steps of the cpu_baseline leg (~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     global _OUT
     _OUT = _claim_stdout()

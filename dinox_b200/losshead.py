@@ -323,7 +323,10 @@ def bf16_weight(p: torch.Tensor) -> torch.Tensor:
             and hit[4].shape == p.shape):
         return hit[4]
     w = p.detach()
-    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    # refresh IN PLACE when the same parameter object is still alive: captured CUDA graphs hold the
+    # address of the bf16 copy, so a stale copy must be rewritten, not replaced
+    reuse = hit is not None and hit[0]() is p and hit[4].shape == p.shape and hit[4].device == p.device
+    out = hit[4] if reuse else torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
     ops.gather_cast_bf16(w.reshape(w.shape[0], -1), None, out.reshape(w.shape[0], -1))
     if len(_BF16_CACHE) > 64:   # drop entries whose parameter is gone
         for k in [k for k, v in _BF16_CACHE.items() if v[0]() is None]:
@@ -465,6 +468,9 @@ def _entry_plan(B, Vg, V, Mm, device) -> _EntryPlan:
 def _accumulate_grad(p: torch.Tensor, fn) -> None:
     """fn(out_tensor, accumulate: bool) writes/accumulates dL/dp straight into p.grad (fp32)."""
     if p.grad is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise _ext.DinoxError("graph capture needs pre-allocated .grad tensors on the head parameters "
+                                  "(LossHeadStep allocates and zeroes them)")
         p.grad = torch.empty_like(p, memory_format=torch.contiguous_format)
         fn(p.grad, False)
     else:

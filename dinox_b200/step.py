@@ -49,6 +49,8 @@ class LossHeadStep:
         self.teacher_params += list(self.teacher_head.parameters())
         self.n_params = sum(p.numel() for p in self.student_params)
         self.micro = 0
+        self._graphs: Dict[int, dict] = {}
+        self.launches_per_graph = 0
 
     def micro_step(self, f: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """f: student_cls, teacher_cls (+ student_tok, teacher_tok) (+ student_patch, teacher_patch,
@@ -71,3 +73,102 @@ class LossHeadStep:
             for p in self.student_head.parameters():
                 p.grad = None
         return out
+
+    # ---------------------------------------------------------------------------------------------
+    # CUDA-graph stepping: the ~60 launches of a micro-step (kernels of this library + the handful of
+    # scalar autograd ops of the step glue) are captured once per input slot and replayed, so the step
+    # is never bound by Python / launch latency (it is at the smaller per-GPU batches of C3 / C5).
+    # ---------------------------------------------------------------------------------------------
+    def _head_weights(self):
+        return [self.student_head[0].weight, self.student_head[2].weight,
+                self.teacher_head[0].weight, self.teacher_head[2].weight]
+
+    def static_inputs(self, like: Dict[str, torch.Tensor], slots: int = 1,
+                      buffers: Optional[List[Dict[str, torch.Tensor]]] = None) -> List[Dict[str, torch.Tensor]]:
+        """Device input buffers (one dict per slot) with the shapes / dtypes of `like`; the caller
+        fills them (H2D copies land here directly) and calls micro_step_graph(slot).  `buffers` lets the
+        caller supply the storage (e.g. typed views into one blob per slot: a single H2D copy per step)."""
+        out = []
+        for i in range(slots):
+            d = {}
+            for k, v in like.items():
+                t = buffers[i][k] if buffers is not None else torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                assert t.shape == v.shape and t.dtype == v.dtype and t.is_cuda
+                if k.startswith("student"):
+                    t.requires_grad_(True)
+                d[k] = t
+            out.append(d)
+        self._static = out
+        self._graphs = {}
+        return out
+
+    def _ensure_grads(self):
+        for p in self.student_head.parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+
+    def capture(self, slot: int = 0, warmup: int = 2) -> None:
+        """Capture forward + backward of one micro-step on the static inputs of `slot`."""
+        f = self._static[slot]
+        self._ensure_grads()
+        was_timing = ops.TIMER.enabled
+        ops.TIMER.enabled = False
+        # the warm-up passes must leave no trace: centres and accumulated head gradients are restored
+        saved = [self.dino_loss.center.clone(), self.center_patch.clone()] + [p.grad.clone() for p in self.student_head.parameters()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # warm-up on a side stream (PyTorch capture recipe)
+            for _ in range(warmup):
+                for k, v in f.items():
+                    if v.requires_grad:
+                        v.grad = None
+                self._fwd_bwd(f)
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():
+            self.dino_loss.center.copy_(saved[0])
+            self.center_patch.copy_(saved[1])
+            for p, g0 in zip(self.student_head.parameters(), saved[2:]):
+                p.grad.copy_(g0)
+        for k, v in f.items():
+            if v.requires_grad:
+                v.grad = None                    # backward allocates the input grads inside the capture
+        for w in self._head_weights():
+            losshead.bf16_weight(w)              # casts happen OUTSIDE the graph (refreshed in place later)
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g):
+            out = self._fwd_bwd(f)
+        self.launches_per_graph = ops.launch_count() - n0
+        self._graphs[slot] = dict(graph=g, out=out)
+        ops.TIMER.enabled = was_timing
+
+    def _fwd_bwd(self, f):
+        out = losshead.fused_head_dino_loss(
+            f["student_cls"], f["teacher_cls"], self.student_head, self.teacher_head, self.dino_loss,
+            self.student_temp, self.teacher_temp, student_patch=f.get("student_patch"),
+            teacher_patch=f.get("teacher_patch"), masks_weight=f.get("masks_weight"),
+            center_patch=self.center_patch if "student_patch" in f else None, ibot_weight=self.ibot_weight)
+        loss = out["loss"]
+        if "student_tok" in f:
+            out["loss_gram"] = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
+            loss = loss + self.gram_weight * out["loss_gram"]
+        out["loss_total"] = loss.detach()
+        (loss / self.accum).backward()
+        return out
+
+    def micro_step_graph(self, slot: int = 0) -> Dict[str, torch.Tensor]:
+        """Replay the captured micro-step on the current contents of the slot's static inputs.  Returns
+        the static output tensors (losses); input gradients are in `static_inputs[slot][k].grad`, head
+        gradients accumulate in the parameters' .grad (zeroed at the start of every accumulation window)."""
+        if slot not in self._graphs:
+            self.capture(slot)
+        if self.micro % self.accum == 0:
+            for p in self.student_head.parameters():
+                p.grad.zero_()
+        for w in self._head_weights():
+            losshead.bf16_weight(w)              # no-op unless a weight changed since the last cast
+        self._graphs[slot]["graph"].replay()
+        self.micro += 1
+        if self.micro % self.accum == 0:
+            losshead.ema_update(self.teacher_params, self.student_params, self.ema, plan_key=id(self))
+        return self._graphs[slot]["out"]

@@ -119,3 +119,37 @@ def test_ema_full_parameter_list_limits(dx):
     dx.ema_update(t, s, 0.0)
     assert all(torch.equal(a, b) for a, b in zip(t, s))           # m = 0: exact copy of the student
     assert sum(x.numel() for x in s) == 47_085_312 or sum(x.numel() for x in s) > 47_000_000
+
+
+def test_graph_replay_equals_eager(dx):
+    """LossHeadStep.micro_step_graph (captured CUDA graph, static inputs) against micro_step (eager):
+    same losses, same head gradients after an accumulation window, same teacher after the EMA, and
+    fresh input data is picked up on replay."""
+    from dinox_b200 import synth
+    from dinox_b200.step import LossHeadStep
+    sh = synth.LossHeadShapes(batch=4, dim=128, out_dim=2048, n_patches=36, n_global=2, n_local=2)
+    dev = torch.device("cuda", 0)
+    gen = synth.seeded_generator(11, 0)
+    batches = [synth.feature_batch(sh, gen) for _ in range(4)]
+    eager = LossHeadStep(sh, dev, accum=2, with_backbone_params=False)
+    graph = LossHeadStep(sh, dev, accum=2, with_backbone_params=False)
+    slot = graph.static_inputs(batches[0], slots=1)[0]
+    losses_e, losses_g = [], []
+    for i, f in enumerate(batches):
+        fe = {k: (v.to(dev).requires_grad_(True) if k.startswith("student") else v.to(dev)) for k, v in f.items()}
+        oe = eager.micro_step(fe)
+        with torch.no_grad():
+            for k, v in f.items():
+                slot[k].copy_(v)
+        og = graph.micro_step_graph(0)
+        torch.cuda.synchronize()
+        losses_e.append(oe["loss_total"].item()); losses_g.append(og["loss_total"].item())
+        assert torch.equal(fe["student_cls"].grad, slot["student_cls"].grad), f"step {i}: d student_cls"
+        assert torch.equal(fe["student_tok"].grad, slot["student_tok"].grad), f"step {i}: d student_tok"
+        if i % 2 == 0:   # mid-window: accumulated head gradients agree
+            for (n, a), (_, b) in zip(eager.student_head.named_parameters(), graph.student_head.named_parameters()):
+                assert torch.equal(a.grad, b.grad), f"step {i}: grad {n}"
+    assert losses_e == losses_g
+    for a, b in zip(eager.teacher_head.parameters(), graph.teacher_head.parameters()):
+        assert torch.equal(a, b)                      # two EMA updates happened on both
+    assert torch.equal(eager.dino_loss.center, graph.dino_loss.center)
