@@ -307,9 +307,20 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = crops_per_step / (e2e_ms * 1e-3)
 
-    if rank != 0:
+    def finish_rank():
+        """Multi-rank teardown without destroy_process_group(): with NCCL collectives captured in CUDA
+        graphs the communicator teardown was seen to hang; drop the graphs, synchronise every rank, exit hard."""
+        step._graphs.clear()
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stderr.flush()
+            _OUT.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish_rank()
         return
 
     # ---------------- roofline of the dominant kernel ----------------
@@ -374,8 +385,7 @@ def run_ours(args):
         "loss": loss_val,
     }
     print(json.dumps(line), file=_OUT, flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish_rank()
 
 
 def _claim_stdout():
