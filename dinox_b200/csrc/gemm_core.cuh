@@ -10,6 +10,13 @@
 #pragma once
 #include "sm100.cuh"
 
+// Pair mode, "accumulator stage drained" hand-off of the non-leader CTA: 0 = its epilogue warps arrive on
+// the leader's barrier directly with a relaxed remote arrive (TMEM reads have completed: nothing to
+// publish); 1 = they arrive on a local barrier and one forwarder thread does a release.cluster arrive
+// (formally conservative, ~1.6k cycles of extra latency per tile).
+#ifndef DINOX_PAIR_FORWARDER
+#define DINOX_PAIR_FORWARDER 0
+#endif
 #ifndef DINOX_EXP_NO_TMA
 #define DINOX_EXP_NO_TMA 0
 #endif
@@ -192,7 +199,11 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
       sm100::mbar_init(&ctl->tmem_full[i], 1);
       // pair: the leader's barrier takes its own epilogue warps plus ONE forwarded arrival for the peer
       // CTA, whose epilogue warps report to their local barrier (see the forwarder in warp 1)
+#if DINOX_PAIR_FORWARDER
       sm100::mbar_init(&ctl->tmem_empty[i], Epi::kEpiWarps + (kPair ? 1 : 0));
+#else
+      sm100::mbar_init(&ctl->tmem_empty[i], CL * Epi::kEpiWarps);   // both CTAs' epilogue warps arrive directly
+#endif
       sm100::mbar_init(&ctl->tmem_empty_local[i], Epi::kEpiWarps);
     }
     sm100::fence_barrier_init();
@@ -284,7 +295,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     // ===================== pair, non-leader CTA: forward "accumulator stage drained" ==============
     // One release.cluster arrive per tile from a thread with no memory traffic of its own; the
     // epilogue warps only pay a CTA-local arrive.
-    if (kPair && !leader) {
+    if (DINOX_PAIR_FORWARDER && kPair && !leader) {
       int acc_stage = 0;
       uint32_t acc_phase = 0;
       for (; walk.valid(); walk.next()) {
@@ -375,7 +386,14 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 #endif
       sm100::tc_fence_before();
       __syncwarp();
+#if DINOX_PAIR_FORWARDER
       if (lane == 0) sm100::mbar_arrive(leader ? &ctl->tmem_empty[acc_stage] : &ctl->tmem_empty_local[acc_stage]);
+#else
+      if (lane == 0) {
+        if (leader) sm100::mbar_arrive(&ctl->tmem_empty[acc_stage]);
+        else sm100::mbar_arrive_cluster_relaxed(sm100::mapa_u32(sm100::smem_u32(&ctl->tmem_empty[acc_stage]), 0));
+      }
+#endif
       if (kAccStages == 2) { acc_stage ^= 1; if (acc_stage == 0) acc_phase ^= 1; }
       else acc_phase ^= 1;
       tc = tn;

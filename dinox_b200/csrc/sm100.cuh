@@ -119,12 +119,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   return r;
 }
 // Remote arrive with release semantics at cluster scope.  It compiles to MEMBAR.ALL + ERRBAR + arrive
-// and so waits for every outstanding memory operation of the issuing thread: only a thread with
-// nothing in flight should call it (the pair-mode forwarder warp does).  A .relaxed remote arrive
-// straight from the epilogue warps was measured to race: the leader's next MMA overwrote TMEM
-// columns the peer CTA had not finished reading.
+// (~1.6k cycles, and it waits for every outstanding memory operation of the issuing thread).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Remote arrive WITHOUT release semantics, for hand-offs whose only shared state is TMEM: the reads
+// of the arriving warp have physically completed (tcgen05.wait::ld returned) before the arrive is
+// issued, so there is nothing in generic memory to publish.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // ---- clusters -------------------------------------------------------------------------------
