@@ -335,7 +335,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             if (sm100::elect_one()) {
 #if DINOX_EXP_NO_MMA   // experiment: operands stream through smem but nothing reads them
             sm100::mbar_arrive(&ctl->empty[st.stage]);
-            if (kPair) sm100::mbar_arrive_cluster(sm100::mapa_u32(sm100::smem_u32(&ctl->empty[st.stage]), 1));
+            if (kPair) sm100::mbar_arrive_cluster_relaxed(sm100::mapa_u32(sm100::smem_u32(&ctl->empty[st.stage]), 1));
 #else
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {

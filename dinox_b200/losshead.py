@@ -8,7 +8,7 @@ Drop-in names and signatures (reference: timlawrenz/DINO-X):
   DinoStudentTeacher(backbone, out_dim).head  zoo/arch.py:246-261 (state-dict keys head.{0,2}.*)
   _ema_update(teacher, student, m)            scripts/phase3_micro_run.py:152-155; inline loop at
                                               scripts/phase5_big_run.py:1798-1802
-  KoLeoLoss is out of scope.
+  KoLeoLoss()(student_out)                   scripts/phase5_big_run.py:742-773
 Extensions enter only through keyword arguments whose defaults reproduce the reference
 (n_global=2, n_local=0, teacher_mode="center", process_group=None) and through the fused entry
 point ``fused_head_dino_loss`` (projection head + multi-crop CE + iBOT in tcgen05 GEMM epilogues,
@@ -639,8 +639,34 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
     return {"loss": total, "loss_dino": losses[0], "loss_ibot": losses[1]}
 
 
-class KoLeoLoss(nn.Module):  # pragma: no cover - named for API completeness only
-    """Not part of the hot path (SURVEY 8f, next #1)."""
+class _KoLeo(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, eps):
+        loss, saved = ops.koleo_fwd(z.detach(), eps)
+        ctx.save_for_backward(z, *saved)
+        ctx.eps = eps
+        return loss
 
-    def forward(self, *a, **k):
-        raise _ext.DinoxError("KoLeoLoss is outside the B200 loss-head scope of this round (SURVEY 8f)")
+    @staticmethod
+    def backward(ctx, g):
+        z, inv, nn_idx, dist = ctx.saved_tensors
+        return ops.koleo_bwd(z.detach(), (inv, nn_idx, dist), ctx.eps, g), None
+
+
+class KoLeoLoss(nn.Module):
+    """Kozachenko-Leonenko entropy regulariser - drop-in for scripts/phase5_big_run.py:742-773
+    (`koleo_loss_fn(student_out)`, weight `--koleo-weight`, wired at :1764-1766).  The cosine Gram matrix
+    runs on the tcgen05 split-K GEMM and only ranks neighbours; nearest-neighbour distances are
+    recomputed exactly in fp32.  Up to 1024 rows; data parallel: local rows only (each rank regularises
+    its own crops, like the single-device reference does for its batch)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+
+    def forward(self, student_output: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+        if not student_output.is_cuda:
+            raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
+        if student_output.dim() != 2:
+            raise ValueError(f"expected (rows, K) head outputs, got {tuple(student_output.shape)}")
+        z = student_output if student_output.stride(1) == 1 else student_output.contiguous()
+        return _KoLeo.apply(z, float(eps))

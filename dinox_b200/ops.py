@@ -387,6 +387,42 @@ def gather_sum_rows(src: torch.Tensor, ptr: torch.Tensor, ent: torch.Tensor, row
     return out
 
 
+def koleo_fwd(z: torch.Tensor, eps: float):
+    """KoLeo forward on head outputs z (R, K) [fp32 | bf16 | fp16].  Returns (loss, saved) where
+    saved = (inv_norm, nn, dist) feeds koleo_bwd."""
+    _chk_cuda(z)
+    ld = _rowmajor(z)
+    R, K = z.shape
+    dev = z.device
+    ldb = (K + 7) // 8 * 8
+    zb = torch.empty(R, ldb, dtype=torch.bfloat16, device=dev)
+    inv = torch.empty(R, dtype=torch.float32, device=dev)
+    _ext.call("dinox_koleo_rownorm", _p(z), DT[z.dtype], R, K, ld, _p(inv), _p(zb), ldb, _stream())
+    zv = zb[:, :K]
+    parts = gemm_bf16_splitk(zv, zv)                       # cosine ranking only: (S, R, R) partial Gram slabs
+    gram = torch.empty(R, R, dtype=torch.float32, device=dev)
+    sum_slabs(parts, gram)
+    nc = int(_ext.lib().dinox_koleo_candidates())
+    cand = torch.empty(R, nc, dtype=torch.int32, device=dev)
+    d2 = torch.empty(R, nc, dtype=torch.float32, device=dev)
+    nn = torch.empty(R, dtype=torch.int32, device=dev)
+    dist = torch.empty(R, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    _ext.call("dinox_koleo_fwd", _p(z), DT[z.dtype], R, K, ld, _p(inv), _p(gram), R, float(eps), _p(cand), _p(d2), _p(nn),
+              _p(dist), _p(loss), _stream())
+    return loss, (inv, nn, dist)
+
+
+def koleo_bwd(z: torch.Tensor, saved, eps: float, upstream: torch.Tensor) -> torch.Tensor:
+    inv, nn, dist = saved
+    R, K = z.shape
+    dz = torch.empty(R, K, dtype=z.dtype, device=z.device)
+    up = upstream.to(torch.float32).reshape(1).contiguous()
+    _ext.call("dinox_koleo_bwd", _p(z), DT[z.dtype], R, K, _rowmajor(z), _p(inv), _p(nn), _p(dist), float(eps), _p(up),
+              _p(dz), K, _stream())
+    return dz
+
+
 def fill_(t: torch.Tensor, v: float = 0.0) -> torch.Tensor:
     assert t.dtype == torch.float32 and t.is_contiguous()
     _ext.call("dinox_fill_f32", _p(t), t.numel(), float(v), _stream())

@@ -19,9 +19,14 @@ class LossHeadStep:
     def __init__(self, shapes: synth.LossHeadShapes, device, seed_cfg: int = 2, rank: int = 0,
                  accum: int = 4, gram_weight: float = 1.0, ibot_weight: float = 1.0, ema: float = 0.996,
                  center_momentum: float = 0.9, student_temp: float = 0.1, teacher_temp: float = 0.04,
-                 teacher_mode: str = "center", process_group=None, with_backbone_params: bool = True):
+                 teacher_mode: str = "center", process_group=None, with_backbone_params: bool = True,
+                 koleo_weight: float = 0.0):
         self.shapes, self.device, self.accum = shapes, device, accum
         self.gram_weight, self.ibot_weight, self.ema = gram_weight, ibot_weight, ema
+        # KoLeo (scripts/phase5_big_run.py:1764-1766) is off by default: the benchmark metric is the
+        # north_star loss head; with a weight the global-view CLS logits are materialised for it
+        self.koleo_weight = koleo_weight
+        self.koleo = losshead.KoLeoLoss() if koleo_weight > 0.0 else None
         self.student_temp, self.teacher_temp = student_temp, teacher_temp
         g = synth.seeded_generator(seed_cfg, 0)  # identical replicas on every rank
         D, K = shapes.dim, shapes.out_dim
@@ -64,6 +69,7 @@ class LossHeadStep:
         if "student_tok" in f:
             out["loss_gram"] = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
             loss = loss + self.gram_weight * out["loss_gram"]
+        loss = self._add_koleo(f, out, loss)
         out["loss_total"] = loss.detach()
         (loss / self.accum).backward()
         self.micro += 1
@@ -152,9 +158,18 @@ class LossHeadStep:
         if "student_tok" in f:
             out["loss_gram"] = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
             loss = loss + self.gram_weight * out["loss_gram"]
+        loss = self._add_koleo(f, out, loss)
         out["loss_total"] = loss.detach()
         (loss / self.accum).backward()
         return out
+
+    def _add_koleo(self, f, out, loss):
+        if self.koleo is None:
+            return loss
+        n_glob = self.shapes.batch * self.shapes.n_global       # the reference feeds its 2B global-view rows
+        z = self.student_head(f["student_cls"][:n_glob])
+        out["loss_koleo"] = self.koleo(z)
+        return loss + self.koleo_weight * out["loss_koleo"]
 
     def micro_step_graph(self, slot: int = 0) -> Dict[str, torch.Tensor]:
         """Replay the captured micro-step on the current contents of the slot's static inputs.  Returns

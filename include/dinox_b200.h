@@ -254,6 +254,25 @@ DINOX_API int dinox_gather_sum_rows(const float* src, int64_t ld_src, int slabs,
                                     int accumulate, dinox_stream_t stream);
 DINOX_API int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a11 KoLeo regulariser on head outputs (scripts/phase5_big_run.py:742-773, wired at :1764-1766):
+ *   x = z / max(||z||, 1e-12);  d_i = min_{j != i} ||x_i - x_j||;  loss = -mean_i log(d_i + eps).
+ * dinox_koleo_rownorm: inv_norm[r] (and an optional bf16 copy of z for the ranking GEMM).
+ * The caller forms gram = z_bf16 z_bf16^T with dinox_gemm_bf16_splitk (+ dinox_sum_slabs); it only
+ * ranks neighbours.  dinox_koleo_fwd picks dinox_koleo_candidates() candidates per row, recomputes
+ * their distances exactly in fp32 from z, and reduces the loss; nn/dist feed dinox_koleo_bwd, which
+ * writes dL/dz (same dtype as z) = autograd of normalize -> cdist -> min -> log.  rows <= 1024.
+ * ------------------------------------------------------------------------------------------ */
+DINOX_API int dinox_koleo_candidates(void);
+DINOX_API int dinox_koleo_rownorm(const void* z, int dtype, int64_t rows, int64_t K, int64_t ld, float* inv_norm,
+                                  void* z_bf16, int64_t ldb, dinox_stream_t stream);
+DINOX_API int dinox_koleo_fwd(const void* z, int dtype, int64_t rows, int64_t K, int64_t ld, const float* inv_norm,
+                              const float* gram, int64_t ldg, float eps, int* cand, float* d2, int* nn, float* dist,
+                              float* loss, dinox_stream_t stream);
+DINOX_API int dinox_koleo_bwd(const void* z, int dtype, int64_t rows, int64_t K, int64_t ld, const float* inv_norm,
+                              const int* nn, const float* dist, float eps, const float* upstream, void* dz,
+                              int64_t ldd, dinox_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,5 +173,29 @@ def main():
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f))} bytes")
 
 
+def koleo_golden():
+    """KoLeoLoss of the reference (scripts/phase5_big_run.py:742-773) with its autograd gradient on
+    spread-out, clustered (near-duplicate rows: the cancellation-prone case) and wide-K inputs."""
+    sys.path[:0] = [REF, os.path.join(REF, "scripts")]
+    from phase5_big_run import KoLeoLoss
+    out = {}
+    for name, (r, k, seed, cluster) in {"small": (8, 128, 301, 0.0), "mid": (64, 1000, 302, 0.0),
+                                        "clustered": (48, 512, 303, 0.05), "wide": (16, 8192, 304, 0.0)}.items():
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(r, k, generator=g) * 3.0
+        if cluster:
+            x = x[: r // 4].repeat(4, 1) + cluster * torch.randn(r, k, generator=g)
+        xg = x.clone().requires_grad_(True)
+        loss = KoLeoLoss()(xg)
+        loss.backward()
+        out[f"{name}_x"], out[f"{name}_loss"], out[f"{name}_grad"] = _np(x), _np(loss), _np(xg.grad)
+    np.savez(os.path.join(OUT, "koleo.npz"), **out)
+    print("koleo.npz written")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "koleo":
+        koleo_golden()      # adds one file, leaves the other vectors untouched
+    else:
+        main()
+        koleo_golden()

@@ -198,3 +198,15 @@ def test_entropy_diagnostics_float64():
     ps = torch.softmax(s.double() / 0.1, -1)
     close(te, -(pt * torch.log(pt.clamp_min(1e-300))).sum(-1).mean().float(), rtol=1e-5)
     close(se, -(ps * torch.log(ps.clamp_min(1e-300))).sum(-1).mean().float(), rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["small", "mid", "clustered", "wide"])
+def test_koleo_loss_and_gradient(golden, name):
+    """a11 KoLeo (scripts/phase5_big_run.py:742-773): oracle restatement against the reference's own
+    loss and autograd gradient, including near-duplicate rows (small nearest-neighbour distances)."""
+    g = golden("koleo.npz")
+    x = T(g[f"{name}_x"]).clone().requires_grad_(True)
+    loss = O.koleo_loss(x)
+    loss.backward()
+    close(loss, g[f"{name}_loss"])
+    close(x.grad, g[f"{name}_grad"], rtol=1e-5, atol=1e-9)
