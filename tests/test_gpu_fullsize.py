@@ -153,3 +153,28 @@ def test_graph_replay_equals_eager(dx):
     for a, b in zip(eager.teacher_head.parameters(), graph.teacher_head.parameters()):
         assert torch.equal(a, b)                      # two EMA updates happened on both
     assert torch.equal(eager.dino_loss.center, graph.dino_loss.center)
+
+
+def test_step_with_koleo_term(dx):
+    """Step glue with the KoLeo term (scripts/phase5_big_run.py:1764-1766): the total is the weighted sum
+    of the parts, the KoLeo value equals the oracle on the same global-view logits, and it adds gradient."""
+    from dinox_b200 import synth
+    from dinox_b200.step import LossHeadStep
+    from oracle import losshead_oracle as O
+    sh = synth.LossHeadShapes(batch=4, dim=128, out_dim=2048, n_patches=36, n_global=2, n_local=2)
+    dev = torch.device("cuda", 0)
+    f = synth.feature_batch(sh, synth.seeded_generator(12, 0))
+    outs, grads = [], []
+    for w in (0.0, 0.1):
+        st = LossHeadStep(sh, dev, accum=1, with_backbone_params=False, koleo_weight=w)
+        fd = {k: (v.to(dev).requires_grad_(True) if k.startswith("student") else v.to(dev)) for k, v in f.items()}
+        out = st.micro_step(fd)
+        torch.cuda.synchronize()
+        outs.append({k: v.item() for k, v in out.items() if v.numel() == 1})
+        grads.append(fd["student_cls"].grad.clone())
+        if w:
+            z = st.student_head(fd["student_cls"][: sh.batch * sh.n_global].detach())
+            ref = O.koleo_loss(z.float().cpu())
+            assert abs(outs[-1]["loss_koleo"] - ref.item()) <= 1e-4 * abs(ref.item())
+    assert abs(outs[1]["loss_total"] - (outs[0]["loss_total"] + 0.1 * outs[1]["loss_koleo"])) <= 1e-5 * abs(outs[1]["loss_total"])
+    assert not torch.equal(grads[0], grads[1]) and torch.isfinite(grads[1]).all()
