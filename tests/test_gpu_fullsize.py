@@ -178,3 +178,32 @@ def test_step_with_koleo_term(dx):
             assert abs(outs[-1]["loss_koleo"] - ref.item()) <= 1e-4 * abs(ref.item())
     assert abs(outs[1]["loss_total"] - (outs[0]["loss_total"] + 0.1 * outs[1]["loss_koleo"])) <= 1e-5 * abs(outs[1]["loss_total"])
     assert not torch.equal(grads[0], grads[1]) and torch.isfinite(grads[1]).all()
+
+
+def test_strided_backbone_views_are_consumed_in_place(dx):
+    """SURVEY 8f #3 (caller-side staging): the reference slices the backbone output (`feats[:, 0]` CLS rows,
+    `feats[:, 1:]` tokens, scripts/phase5_big_run.py:1741-1747).  Those strided views go straight into the
+    kernels (row stride = T*D) and give bit-identical results to contiguous copies."""
+    from dinox_b200 import synth
+    gen = torch.Generator().manual_seed(31)
+    B, Vg, T_, D, K = 4, 2, 41, 128, 2048
+    feats_s = torch.randn(B * Vg, T_, D, generator=gen).to(DEV)
+    feats_t = torch.randn(B * Vg, T_, D, generator=gen).to(DEV)
+    sd = synth.head_weights(D, K, gen)
+    res = []
+    for contiguous in (False, True):
+        s_head, t_head = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+        s_head.load_state_dict(sd); t_head.load_state_dict(sd)
+        dl = dx.DINOLoss(K, 0.9).to(DEV)
+        fs = feats_s.clone().requires_grad_(True)
+        cls_s, cls_t = fs[:, 0], feats_t[:, 0]
+        assert not cls_s.is_contiguous()
+        if contiguous:
+            cls_s, cls_t = cls_s.contiguous(), cls_t.contiguous()
+        out = dx.fused_head_dino_loss(cls_s, cls_t, s_head, t_head, dl, 0.1, 0.04)
+        lg = dx.compute_gram_anchoring_loss(fs, feats_t)
+        (out["loss"] + lg).backward()
+        torch.cuda.synchronize()
+        res.append((out["loss"].item(), lg.item(), fs.grad.clone(), s_head[2].weight.grad.clone()))
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
