@@ -12,6 +12,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapFloatOOBfill);
 
 inline PFN_encodeTiled get_encode_fn() {
+  // cuTensorMapEncodeTiled is a DRIVER call: it fails with CUDA_ERROR_INVALID_CONTEXT on a thread that
+  // has not bound the primary context yet (an autograd worker whose first CUDA work is one of our
+  // launches, with every allocation served from PyTorch's cache).  A runtime call binds it.
+  static thread_local bool bound = false;
+  if (!bound) { cudaFree(nullptr); bound = true; }
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
