@@ -167,6 +167,11 @@ SIGNATURES = {
     "dinox_gather_sum_rows": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_f32,
                                       c_void_p, c_i64, c_int, c_void_p]),
     "dinox_fill_f32": (c_int, [c_void_p, c_i64, c_f32, c_void_p]),
+    "dinox_adamw_plan_create": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dinox_adamw_plan_destroy": (c_int, [c_void_p]),
+    "dinox_adamw_step": (c_int, [c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                 ctypes.c_double, ctypes.c_double, c_f32,
+                                 c_void_p, c_void_p]),
     "dinox_koleo_candidates": (c_int, []),
     "dinox_koleo_rownorm": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_void_p]),
     "dinox_koleo_fwd": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_f32, c_void_p, c_void_p,

@@ -273,6 +273,23 @@ DINOX_API int dinox_koleo_bwd(const void* z, int dtype, int64_t rows, int64_t K,
                               const int* nn, const float* dist, float eps, const float* upstream, void* dz,
                               int64_t ldd, dinox_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * multi-tensor AdamW step + global gradient norm, one launch for every tensor
+ * (fp32 params / grads / moments).  Replaces the optimizer step of scripts/phase5_big_run.py:1781-1796:
+ * the per-parameter `p.grad.norm(2).item()` loop (a host sync per tensor) and torch.optim.AdamW (:1621).
+ * Arithmetic of torch.optim.AdamW's single-tensor path; bias corrections 1 - beta^step are passed in
+ * (hyper-parameters are doubles like the python floats torch derives its scalars from).  grad_scale multiplies every gradient first (1/loss-scale; 1 for bf16 training).
+ * grad_norm_out: device scalar = || grad_scale * g ||_2 over all tensors (fixed reduction order).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dinox_adamw_plan dinox_adamw_plan;
+DINOX_API int dinox_adamw_plan_create(void* const* params, const void* const* grads, void* const* exp_avg,
+                                      void* const* exp_avg_sq, const int64_t* numel, int n_tensors,
+                                      dinox_adamw_plan** out);
+DINOX_API int dinox_adamw_plan_destroy(dinox_adamw_plan* plan);
+DINOX_API int dinox_adamw_step(const dinox_adamw_plan* plan, double lr, double beta1, double beta2, double eps,
+                               double weight_decay, double bias_correction1, double bias_correction2,
+                               float grad_scale, float* grad_norm_out, dinox_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

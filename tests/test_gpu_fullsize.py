@@ -207,3 +207,35 @@ def test_strided_backbone_views_are_consumed_in_place(dx):
         res.append((out["loss"].item(), lg.item(), fs.grad.clone(), s_head[2].weight.grad.clone()))
     assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
+
+
+def test_fused_adamw_matches_torch_adamw(dx):
+    """one-launch AdamW + gradient norm against torch.optim.AdamW (the reference's optimizer,
+    scripts/phase5_big_run.py:1621) over several steps on the reference's parameter-size mix: parameters
+    within 2 ulp-ish (rtol 2e-6), identical state_dict layout, gradient norm == the reference's python loop."""
+    import dinox_b200
+    gen = torch.Generator().manual_seed(41)
+    shapes = [(96,), (384, 96), (1, 197, 384), (1536, 384), (4099,), (7,), (2048, 384)]
+    p_ref = [torch.nn.Parameter(torch.randn(*s, generator=gen).to(DEV)) for s in shapes]
+    p_our = [torch.nn.Parameter(p.detach().clone()) for p in p_ref]
+    o_ref = torch.optim.AdamW(p_ref, lr=3e-4, weight_decay=0.04)
+    o_our = dinox_b200.FusedAdamW(p_our, lr=3e-4, weight_decay=0.04)
+    for step in range(5):
+        total = 0.0
+        for a, b in zip(p_ref, p_our):
+            g = torch.randn(a.shape, generator=gen).to(DEV) * (0.1 + step)
+            a.grad, b.grad = g.clone(), g.clone()
+            total += a.grad.norm(2).item() ** 2
+        o_ref.step(); o_our.step()
+        assert abs(o_our.last_grad_norm.item() - total ** 0.5) <= 1e-5 * total ** 0.5
+        for a, b in zip(p_ref, p_our):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-8), f"step {step}"
+    sd_r, sd_o = o_ref.state_dict(), o_our.state_dict()
+    assert sd_r["param_groups"][0].keys() == sd_o["param_groups"][0].keys()
+    for k in sd_r["state"]:
+        assert set(sd_r["state"][k].keys()) == set(sd_o["state"][k].keys())
+        assert float(sd_r["state"][k]["step"]) == float(sd_o["state"][k]["step"]) == 5.0
+        assert torch.allclose(sd_r["state"][k]["exp_avg"], sd_o["state"][k]["exp_avg"], rtol=2e-6, atol=1e-6)   # a few ulp at the gradient scale (m cancels to ~0 in places)
+        assert torch.allclose(sd_r["state"][k]["exp_avg_sq"], sd_o["state"][k]["exp_avg_sq"], rtol=2e-6, atol=1e-7)
+    o_ref2 = torch.optim.AdamW(p_ref, lr=3e-4, weight_decay=0.04)
+    o_ref2.load_state_dict(sd_o)            # a checkpoint written with the fused optimizer loads into torch's
