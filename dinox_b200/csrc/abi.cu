@@ -2,11 +2,13 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 
 namespace dinox {
 
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+// process-wide: backward kernels are launched from autograd worker threads
+static std::atomic<int64_t> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -75,6 +77,6 @@ extern "C" {
 int dinox_version(void) { return 100; }
 const char* dinox_last_error_string(void) { return dinox::g_err; }
 int dinox_device_check(void) { return dinox::require_sm100(); }
-int64_t dinox_launch_count(void) { return dinox::g_launches; }
-void dinox_launch_count_reset(void) { dinox::g_launches = 0; }
+int64_t dinox_launch_count(void) { return dinox::g_launches.load(); }
+void dinox_launch_count_reset(void) { dinox::g_launches.store(0); }
 }

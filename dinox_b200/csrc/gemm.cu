@@ -761,10 +761,13 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   auto kern = gemm_kernel<BN, NSPLIT, NSUB, CL, Epi>;
   constexpr int smem = smem_bytes<BN, CL, Epi>();
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in shared-memory size is a per-device function attribute
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     DINOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int64_t super = (int64_t)((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * (splits > 1 ? splits : batches);
   DINOX_REQUIRE(super < (1ll << 31), DINOX_E_BADARG, "%s: too many tiles", name);
