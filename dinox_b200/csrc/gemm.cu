@@ -242,6 +242,34 @@ __device__ __forceinline__ float4 lds128(const float* p) {
 #define DINOX_EPI_WARPS 8   // epilogue warps of the two row-math kernels (pass 1 / pass 2): 8 or 16
 #endif
 
+// ---- packed fp32 pairs (sm_100: add / mul / fma .f32x2 operate on two floats held in a 64-bit register) ----
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 struct EpiStats {
   static constexpr bool kUsesTmaStore = false;
   static constexpr int kEpiWarps = DINOX_EPI_WARPS;
@@ -368,7 +396,7 @@ struct EpiGradT {
   // constants of its kCols entries (each warp loads them itself: a few hundred redundant bytes per
   // tile instead of two CTA-wide named barriers per tile that made every warp wait for the slowest).
   static constexpr int kStageBytes = kEpiWarps * kBufs * kWarpBuf;
-  static constexpr int kConstFloats = 3 * kCols;       // per warp: -lse2 | -rb2 | cw/tau_s
+  static constexpr int kConstFloats = 4 * kCols;       // per warp: -lse2 | -rb2 | cw/tau_s | -cw/tau_s
   static constexpr int kEpiSmemBytes = kStageBytes + kEpiWarps * kConstFloats * 4;
   struct Params {
     float as2, at2, inv_tau_s;
@@ -438,45 +466,54 @@ struct EpiGradT {
         buf[j * 32 + lane] = -st.nl[j];
         buf[kCols + j * 32 + lane] = -st.nr[j];
         buf[2 * kCols + j * 32 + lane] = st.cw[j] * e.inv_tau_s;
+        buf[3 * kCols + j * 32 + lane] = -(st.cw[j] * e.inv_tau_s);
       }
       st.cs_cur = st.cs; st.ct_cur = st.ct;
       __syncwarp();
     }
 
     // 16 entries of one prototype row: logits -> (p, q) -> gradient, loss and bias-gradient terms;
-    // the bf16 gradients go to pieces 2*c16, 2*c16+1 of this thread's staging row
+    // the bf16 gradients go to pieces 2*c16, 2*c16+1 of this thread's staging row.
+    // The fp32 arithmetic runs on packed pairs (Blackwell fma/add/mul.f32x2: two IEEE operations per
+    // issued instruction - same results as the scalar form, ~40 % fewer issue slots):
+    //   u = S*as2 + nl + cs ; w = T*at2 + nr + ct ; p = 2^u ; q = 2^w
+    //   nq = (-cw)*q ; g = cw*p + nq ; loss_acc += nq*u (= -cw q u) ; db2_acc += g
     static __device__ __forceinline__ void chunk16(const Params& e, const uint32_t (&sr)[16], const uint32_t (&tr)[16],
                                                    const float* cb, float cs, float ct, const Stage& stg, int c16,
-                                                   float& l0, float& l1, float& d0, float& d1) {
+                                                   uint64_t& lacc, uint64_t& dacc) {
       uint32_t packed[8];
+      const uint64_t as2 = pack2(e.as2, e.as2), at2 = pack2(e.at2, e.at2), cs2 = pack2(cs, cs), ct2 = pack2(ct, ct);
 #if DINOX_EXP_EPI_MODE == 1   // experiment: TMEM loads only, trivial math
       {
         float a = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) a += __uint_as_float(sr[j]) + __uint_as_float(tr[j]);
-        l0 += a;
+        lacc = add2(lacc, pack2(a, 0.f));
         return;
       }
 #endif
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 nl = lds128(cb + j), nr = lds128(cb + kCols + j), cw = lds128(cb + 2 * kCols + j);
-        const float nls[4] = {nl.x, nl.y, nl.z, nl.w}, nrs[4] = {nr.x, nr.y, nr.z, nr.w}, cws[4] = {cw.x, cw.y, cw.z, cw.w};
-        float g[4];
+        const float4 nl = lds128(cb + j), nr = lds128(cb + kCols + j), cw = lds128(cb + 2 * kCols + j), ncw = lds128(cb + 3 * kCols + j);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float u = fmaf(__uint_as_float(sr[j + i]), e.as2, nls[i]) + cs;
-          const float w = fmaf(__uint_as_float(tr[j + i]), e.at2, nrs[i]) + ct;
-          const float pp = fast_ex2(u);
-          const float qq = fast_ex2(w);
-          const float cwq = cws[i] * qq;
-          g[i] = fmaf(cws[i], pp, -cwq);
-          if (i & 1) { l1 = fmaf(cwq, u, l1); d1 += g[i]; }
-          else { l0 = fmaf(cwq, u, l0); d0 += g[i]; }
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t s2 = pack2u(sr[j + 2 * h], sr[j + 2 * h + 1]), t2 = pack2u(tr[j + 2 * h], tr[j + 2 * h + 1]);
+          const uint64_t nl2 = h ? pack2(nl.z, nl.w) : pack2(nl.x, nl.y), nr2 = h ? pack2(nr.z, nr.w) : pack2(nr.x, nr.y);
+          const uint64_t c2 = h ? pack2(cw.z, cw.w) : pack2(cw.x, cw.y), n2 = h ? pack2(ncw.z, ncw.w) : pack2(ncw.x, ncw.y);
+          const uint64_t u2 = add2(fma2(s2, as2, nl2), cs2);
+          const uint64_t w2 = add2(fma2(t2, at2, nr2), ct2);
+          float ux, uy, wx, wy;
+          unpack2(u2, ux, uy); unpack2(w2, wx, wy);
+          const uint64_t pp = pack2(fast_ex2(ux), fast_ex2(uy)), qq = pack2(fast_ex2(wx), fast_ex2(wy));
+          const uint64_t nq = mul2(n2, qq);
+          const uint64_t g2 = fma2(c2, pp, nq);
+          lacc = fma2(nq, u2, lacc);
+          dacc = add2(dacc, g2);
+          float gx, gy;
+          unpack2(g2, gx, gy);
+          __nv_bfloat162 hh = __floats2bfloat162_rn(gx, gy);
+          packed[j / 2 + h] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(g[0], g[1]), h1 = __floats2bfloat162_rn(g[2], g[3]);
-        packed[j / 2] = *reinterpret_cast<uint32_t*>(&h0);
-        packed[j / 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
       }
       stg.put(2 * c16, packed[0], packed[1], packed[2], packed[3]);
       stg.put(2 * c16 + 1, packed[4], packed[5], packed[6], packed[7]);
@@ -499,7 +536,7 @@ struct EpiGradT {
       uint8_t* wbuf = smem + (epi_warp * kBufs + st.flip) * kWarpBuf;
       Stage stg;
       stg.init(wbuf, lane);
-      float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
+      uint64_t lacc = pack2(0.f, 0.f), dacc = pack2(0.f, 0.f);   // packed (even, odd) partial sums
       uint32_t sa[16], ta[16], sb[16], tb[16];
       sm100::tmem_ld16_nowait(ts, sa);
       sm100::tmem_ld16_nowait(tt, ta);
@@ -508,13 +545,13 @@ struct EpiGradT {
       __syncwarp();
       sm100::tmem_wait_ld();
 #if DINOX_EXP_EPI_MODE == 2   // experiment: math only (one TMEM load per tile, registers reused)
-      chunk16(e, sa, ta, cb, cs, ct, stg, 0, l0, l1, d0, d1);
+      chunk16(e, sa, ta, cb, cs, ct, stg, 0, lacc, dacc);
       sm100::pin16(sa); sm100::pin16(ta);
-      chunk16(e, sa, ta, cb + 16, cs, ct, stg, 1, l0, l1, d0, d1);
+      chunk16(e, sa, ta, cb + 16, cs, ct, stg, 1, lacc, dacc);
       sm100::pin16(sa); sm100::pin16(ta);
-      chunk16(e, sa, ta, cb + 32, cs, ct, stg, 2, l0, l1, d0, d1);
+      chunk16(e, sa, ta, cb + 32, cs, ct, stg, 2, lacc, dacc);
       sm100::pin16(sa); sm100::pin16(ta);
-      chunk16(e, sa, ta, cb + 48, cs, ct, stg, 3, l0, l1, d0, d1);
+      chunk16(e, sa, ta, cb + 48, cs, ct, stg, 3, lacc, dacc);
       if (false) {
 #else
       {
@@ -522,23 +559,23 @@ struct EpiGradT {
       sm100::tmem_ld16_nowait(ts + 16, sb);
       sm100::tmem_ld16_nowait(tt + 16, tb);
       sm100::pin16(sa); sm100::pin16(ta);
-      chunk16(e, sa, ta, cb, cs, ct, stg, 0, l0, l1, d0, d1);
+      chunk16(e, sa, ta, cb, cs, ct, stg, 0, lacc, dacc);
       sm100::tmem_wait_ld();
       if (kCols == 64) {
         sm100::tmem_ld16_nowait(ts + 32, sa);
         sm100::tmem_ld16_nowait(tt + 32, ta);
       }
       sm100::pin16(sb); sm100::pin16(tb);
-      chunk16(e, sb, tb, cb + 16, cs, ct, stg, 1, l0, l1, d0, d1);
+      chunk16(e, sb, tb, cb + 16, cs, ct, stg, 1, lacc, dacc);
       if (kCols == 64) {
         sm100::tmem_wait_ld();
         sm100::tmem_ld16_nowait(ts + 48, sb);
         sm100::tmem_ld16_nowait(tt + 48, tb);
         sm100::pin16(sa); sm100::pin16(ta);
-        chunk16(e, sa, ta, cb + 32, cs, ct, stg, 2, l0, l1, d0, d1);
+        chunk16(e, sa, ta, cb + 32, cs, ct, stg, 2, lacc, dacc);
         sm100::tmem_wait_ld();
         sm100::pin16(sb); sm100::pin16(tb);
-        chunk16(e, sb, tb, cb + 48, cs, ct, stg, 3, l0, l1, d0, d1);
+        chunk16(e, sb, tb, cb + 48, cs, ct, stg, 3, lacc, dacc);
       }
       }
       // G tile rows [k0, k0+32) x entries [ent0, ent0+kCols) leave as one TMA store (clipped at K and E)
@@ -551,8 +588,10 @@ struct EpiGradT {
       }
       st.flip ^= 1;
       if (kok) {
+        float l0, l1, d0, d1;
+        unpack2(lacc, l0, l1); unpack2(dacc, d0, d1);
         if (e.db2_partial) e.db2_partial[(int64_t)(tc.n_tile * kGroups + grp) * p.M + k] = d0 + d1;
-        if (alt) st.loss_b += l0 + l1; else st.loss_a += l0 + l1;
+        if (alt) st.loss_b -= l0 + l1; else st.loss_a -= l0 + l1;   // the accumulators hold -cw q u
       }
     }
   };
