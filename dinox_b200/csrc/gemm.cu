@@ -322,28 +322,33 @@ struct EpiStats {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const float* cb = buf + c * 64 + h * 32;
+          const uint64_t sc2 = pack2(e.scale2, e.scale2);
+          uint64_t u[16];          // 32 values as packed pairs
           float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = lds128(cb + j);
-            v[h][j] = fmaf(v[h][j], e.scale2, b4.x);
-            v[h][j + 1] = fmaf(v[h][j + 1], e.scale2, b4.y);
-            v[h][j + 2] = fmaf(v[h][j + 2], e.scale2, b4.z);
-            v[h][j + 3] = fmaf(v[h][j + 3], e.scale2, b4.w);
-            cm0 = fmaxf(cm0, fmaxf(v[h][j], v[h][j + 1]));
-            cm1 = fmaxf(cm1, fmaxf(v[h][j + 2], v[h][j + 3]));
+            u[j / 2] = fma2(pack2(v[h][j], v[h][j + 1]), sc2, pack2(b4.x, b4.y));
+            u[j / 2 + 1] = fma2(pack2(v[h][j + 2], v[h][j + 3]), sc2, pack2(b4.z, b4.w));
+            float x0, x1, x2, x3;
+            unpack2(u[j / 2], x0, x1); unpack2(u[j / 2 + 1], x2, x3);
+            cm0 = fmaxf(cm0, fmaxf(x0, x1));
+            cm1 = fmaxf(cm1, fmaxf(x2, x3));
           }
           const float mn = fmaxf(m, fmaxf(cm0, cm1));
           // a chunk that is entirely out of range keeps (m, s) untouched (mn may still be -inf)
           const float msafe = (mn == -INFINITY) ? 0.f : mn;
-          float a0 = s * fast_ex2(m - msafe), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          const uint64_t nm2 = pack2(-msafe, -msafe);
+          uint64_t acc0 = pack2(s * fast_ex2(m - msafe), 0.f), acc1 = pack2(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            a0 += fast_ex2(v[h][j] - msafe);
-            a1 += fast_ex2(v[h][j + 1] - msafe);
-            a2 += fast_ex2(v[h][j + 2] - msafe);
-            a3 += fast_ex2(v[h][j + 3] - msafe);
+          for (int j = 0; j < 16; j += 2) {
+            float x0, x1, x2, x3;
+            unpack2(add2(u[j], nm2), x0, x1); unpack2(add2(u[j + 1], nm2), x2, x3);
+            acc0 = add2(acc0, pack2(fast_ex2(x0), fast_ex2(x1)));
+            acc1 = add2(acc1, pack2(fast_ex2(x2), fast_ex2(x3)));
           }
+          float a0, a1, a2, a3;
+          unpack2(acc0, a0, a1); unpack2(acc1, a2, a3);
           s = (a0 + a1) + (a2 + a3);
           m = mn;
         }
