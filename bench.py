@@ -48,6 +48,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.power, self.power_limit = [], None
         self._halt = threading.Event()
         self.ok = False
         try:
@@ -56,6 +57,10 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:
+                self.power_limit = None
             self.ok = True
         except Exception:
             self.nv = None
@@ -74,6 +79,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -82,15 +91,21 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def stop(self):
         self._halt.set()
         if self.ok:
             self.join(timeout=2)
         med = statistics.median(self.samples) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        pmax = max(self.power) if self.power else None
+        reasons = set(self.reasons)
+        # the power-cap flag is momentary: a board drawing its enforced limit while the SM clock sits
+        # below max IS power capped even when no sample caught the flag
+        if pmax is not None and self.power_limit and pmax >= 0.9 * self.power_limit and med and self.max_mhz and med < self.max_mhz:
+            reasons.add("sw_power_cap")
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(self.samples),
+                "power_w_max": pmax, "power_limit_w": self.power_limit}
 
 
 # ---------------------------------------------------------------------------------------------------
