@@ -103,3 +103,54 @@ def test_synthetic_ct_crops_are_seeded_and_in_range():
     assert (s1[:, 0] >= 0.46).all() and (s1[:, 2] <= 5.0).all()
     g3 = synth.seeded_generator(1, 1)
     assert not torch.equal(synth.multicrop_batch(2, g3, 2, 2, 32, 16)[0][0], v1[0])
+
+
+def test_checkpoint_wire_format_matches_reference_modules():
+    """the payload of save_checkpoint (scripts/phase5_big_run.py:1104-1125) - student /
+    teacher state_dict, dino_loss state_dict, optimizer state_dict - has the same keys, shapes and dtypes
+    with the drop-in modules as with plain PyTorch modules of the reference's structure, and round-trips
+    through torch.save / load_state_dict(strict=True) in both directions.  (CPU only: no kernels run.)"""
+    import io
+    import torch
+    import torch.nn as nn
+    from dinox_b200 import losshead
+    from dinox_b200.optim import FusedAdamW
+
+    class Backbone(nn.Module):           # stand-in with the attribute the wrapper needs
+        def __init__(self, dim):
+            super().__init__()
+            self.dim = dim
+            self.proj = nn.Linear(dim, dim)
+
+    class RefStudentTeacher(nn.Module):  # structure of zoo/arch.py:246-261
+        def __init__(self, backbone, out_dim):
+            super().__init__()
+            self.backbone = backbone
+            self.head = nn.Sequential(nn.Linear(backbone.dim, backbone.dim), nn.GELU(), nn.Linear(backbone.dim, out_dim))
+
+    class RefDINOLoss(nn.Module):        # buffers of scripts/phase5_big_run.py:679-684
+        def __init__(self, out_dim):
+            super().__init__()
+            self.register_buffer("center", torch.zeros(1, out_dim))
+
+    D, K = 32, 96
+    ours, ref = losshead.DinoStudentTeacher(Backbone(D), K), RefStudentTeacher(Backbone(D), K)
+    sd_o, sd_r = ours.state_dict(), ref.state_dict()
+    assert list(sd_o.keys()) == list(sd_r.keys())
+    assert all(sd_o[k].shape == sd_r[k].shape and sd_o[k].dtype == sd_r[k].dtype for k in sd_o)
+    dl_o, dl_r = losshead.DINOLoss(K, 0.9), RefDINOLoss(K)
+    assert {k: (v.shape, v.dtype) for k, v in dl_o.state_dict().items()} == {k: (v.shape, v.dtype) for k, v in dl_r.state_dict().items()}
+    opt_o, opt_r = FusedAdamW(ours.parameters(), lr=1e-3, weight_decay=0.04), torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=0.04)
+    assert opt_o.state_dict()["param_groups"][0].keys() == opt_r.state_dict()["param_groups"][0].keys()
+    # round trip through the on-disk payload in both directions
+    buf = io.BytesIO()
+    torch.save({"step": 7, "student": sd_r, "teacher": sd_r, "opt": opt_r.state_dict(), "scaler": None,
+                "dino_loss": dl_r.state_dict()}, buf)
+    buf.seek(0)
+    payload = torch.load(buf, weights_only=False)
+    ours.load_state_dict(payload["student"], strict=True)
+    dl_o.load_state_dict(payload["dino_loss"], strict=True)
+    opt_o.load_state_dict(payload["opt"])
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    dl_r.load_state_dict(dl_o.state_dict(), strict=True)
+    assert all(torch.equal(a, b) for a, b in zip(ours.state_dict().values(), ref.state_dict().values()))
