@@ -77,3 +77,37 @@ def test_sass_uses_blackwell_tensor_path(built_lib):
     sass = subprocess.run([exe, "-sass", _ext.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
     assert not re.search(r"\bHMMA\b", sass)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/dinox_b200.h must be consumable by a C99 compiler (the drop-in boundary is a C ABI), and a C
+    program linked against libdinox_b200.so can call the host-only entry points without a GPU."""
+    import shutil
+    import subprocess
+    from dinox_b200 import _ext
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi_c.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "dinox_b200.h"\n'
+        "int main(void) {\n"
+        "  int v = dinox_version();\n"
+        "  int s = dinox_gemm_splitk_plan(384, 384, 8064);\n"
+        "  size_t ws = dinox_head_stats_workspace_bytes(8064, 65536);\n"
+        "  const char* e = dinox_last_error_string();\n"
+        '  printf("%d %d %zu %d\\n", v, s, ws, e != NULL);\n'
+        "  return !(v >= 100 && s >= 1 && ws > 0);\n}\n")
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if not os.path.exists(_ext.LIB_PATH):
+        pytest.skip("library not built")
+    exe = tmp_path / "abi_c"
+    libdir = os.path.dirname(_ext.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:libdinox_b200.so",
+                        f"-Wl,-rpath,{libdir}", "-Wl,--allow-shlib-undefined"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
