@@ -239,3 +239,37 @@ def test_fused_adamw_matches_torch_adamw(dx):
         assert torch.allclose(sd_r["state"][k]["exp_avg_sq"], sd_o["state"][k]["exp_avg_sq"], rtol=2e-6, atol=1e-7)
     o_ref2 = torch.optim.AdamW(p_ref, lr=3e-4, weight_decay=0.04)
     o_ref2.load_state_dict(sd_o)            # a checkpoint written with the fused optimizer loads into torch's
+
+
+def test_extreme_logits_and_non_finite_inputs(dx):
+    """Numerical guards of the fused path: (1) logits far outside exp() range (|z|/tau ~ 1e4) still give the
+    oracle's loss and finite gradients (everything is evaluated relative to the row LSE, in log2 units);
+    (2) a NaN in the inputs reaches the loss, so torch.autograd.detect_anomaly (:1216-1218) still fires."""
+    from dinox_b200 import synth
+    from oracle import losshead_oracle as O
+    gen = torch.Generator().manual_seed(55)
+    B, Vg, Vl, D, K = 4, 2, 2, 64, 1024
+    V = Vg + Vl
+    sd_s, sd_t = synth.head_weights(D, K, gen), synth.head_weights(D, K, gen)
+    for sd in (sd_s, sd_t):
+        sd["2.weight"] = sd["2.weight"] * 60.0          # logits ~ +-400 -> z/tau_t ~ 1e4
+    xs, xt = torch.randn(B * V, D, generator=gen), torch.randn(B * Vg, D, generator=gen)
+    sp = O.HeadParams(*[sd_s[k].clone().requires_grad_(True) for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    tp = O.HeadParams(*[sd_t[k].clone() for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    orc = O.LossHeadOracle(sp, tp, K, center_momentum=0.9, n_global=Vg, n_local=Vl, policy="bf16")
+    xo = xs.clone().requires_grad_(True)
+    ref = orc.step(xo, xt, 0.1, 0.04, accum=1)
+    s_head, t_head = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+    s_head.load_state_dict(sd_s); t_head.load_state_dict(sd_t)
+    dl = dx.DINOLoss(K, 0.9, n_global=Vg, n_local=Vl).to(DEV)
+    x = xs.to(DEV).requires_grad_(True)
+    out = dx.fused_head_dino_loss(x, xt.to(DEV), s_head, t_head, dl, 0.1, 0.04)
+    out["loss"].backward()
+    assert torch.isfinite(out["loss"]) and torch.isfinite(x.grad).all() and torch.isfinite(s_head[2].weight.grad).all()
+    assert abs(out["loss_dino"].item() - ref["loss_dino"].item()) <= 1e-3 * abs(ref["loss_dino"].item())
+    bad = xs.clone(); bad[3, 5] = float("nan")
+    dl2 = dx.DINOLoss(K, 0.9, n_global=Vg, n_local=Vl).to(DEV)
+    out2 = dx.fused_head_dino_loss(bad.to(DEV), xt.to(DEV), s_head, t_head, dl2, 0.1, 0.04)
+    assert not torch.isfinite(out2["loss"])
+    z = s_head(bad.to(DEV)[: B * Vg])
+    assert not torch.isfinite(dx.DINOLoss(K, 0.9).to(DEV)(z, t_head(xt.to(DEV)), 0.1, 0.04))
