@@ -55,14 +55,20 @@ struct CoreParams {
   int kb_per_split;
 };
 
-template <int BN, int CL, int EPI_SMEM>
+constexpr int kResKBlocks = 6;   // resident-A mode holds up to 6 k-blocks (K <= 384) of this CTA's 128 A rows
+
+// RESA: the A operand of sub-GEMM 0 stays resident in shared memory across consecutive tiles that share
+// the M tile (96 KB); stages of a single-GEMM kernel then carry B only.
+template <int BN, int CL, int EPI_SMEM, bool RESA = false, int NSUB = 1>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
   static constexpr int kBBytes = (BN / CL) * BK * 2;   // a CTA of a pair holds 1/CL of the B tile
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr bool kStageHasA = !(RESA && NSUB == 1);
+  static constexpr int kStageBytes = (kStageHasA ? kABytes : 0) + kBBytes;
+  static constexpr int kResBytes = RESA ? kResKBlocks * kABytes : 0;
   static constexpr int kEpiBytes = (EPI_SMEM + 255) / 256 * 256;
-  // 227 KB per CTA minus alignment slack (1 KB), control block (256 B) and the epilogue's staging area
-  static constexpr int kBudget = 227 * 1024 - 1024 - 256 - kEpiBytes;
+  // 227 KB per CTA minus alignment slack (1 KB), control block (256 B), the epilogue's staging area and resident A
+  static constexpr int kBudget = 227 * 1024 - 1024 - 256 - kEpiBytes - kResBytes;
 #ifndef DINOX_MAX_STAGES
 #define DINOX_MAX_STAGES 8
 #endif
@@ -70,7 +76,7 @@ struct SmemLayout {
   static constexpr int kStages = kFit > DINOX_MAX_STAGES ? DINOX_MAX_STAGES : kFit;
   static_assert(kStages >= 2, "tile too large for the smem pipeline");
   static constexpr int kPipeBytes = kStages * kStageBytes;
-  static constexpr int kTotal = kPipeBytes + kEpiBytes + 256 + 1024;
+  static constexpr int kTotal = kResBytes + kPipeBytes + kEpiBytes + 256 + 1024;
 };
 
 // Walks the tile indices cid, cid + ncl, cid + 2 ncl, ... of a persistent CTA without a division per
@@ -89,6 +95,15 @@ struct TileWalker {
     fast = first % nfast; int t = first / nfast; slow = t % nslow; outer = t / nslow;
     dfast = stride % nfast; t = stride / nfast; dslow = t % nslow; douter = t / nslow;
     remaining = first < total ? (total - first + stride - 1) / stride : 0;
+  }
+  // contiguous range [first, first + count) with unit stride (consecutive tiles share the slow digit)
+  __device__ __forceinline__ void init_range(const CoreParams& p, int num_m_super, int first, int count) {
+    m_fastest = p.m_fastest != 0;
+    nfast = m_fastest ? num_m_super : p.num_n_tiles;
+    nslow = m_fastest ? p.num_n_tiles : num_m_super;
+    fast = first % nfast; int t = first / nfast; slow = t % nslow; outer = t / nslow;
+    dfast = 1; dslow = 0; douter = 0;
+    remaining = count > 0 ? count : 0;
   }
   __device__ __forceinline__ bool valid() const { return remaining > 0; }
   __device__ __forceinline__ void next() {
@@ -126,6 +141,7 @@ struct SharedCtl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t tmem_empty_local[2];   // pair mode, non-leader CTA: its own epilogue warps report here
+  uint64_t a_full, a_empty;       // resident-A mode: "resident A tile landed" / "last MMA reading it retired"
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -148,12 +164,12 @@ __device__ __forceinline__ float fast_ex2(float x) {
 //                the loss head are bound by L2->SMEM operand traffic, not by the tensor pipe.
 // `Epi` provides kEpiWarps, kEpiSmemBytes, Params, State, fetch(), prologue(), tile(), finish().
 // `tmC` is the output tensor map of epilogues that store through TMA (others ignore it).
-template <int BN, int NSPLIT, int NSUB, int CL, class Epi>
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi, bool RESA = false>
 __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Epi::Params& ep,
                                           const CUtensorMap* tmA0, const CUtensorMap* tmB0,
                                           const CUtensorMap* tmA1, const CUtensorMap* tmB1,
                                           const CUtensorMap* tmC, uint8_t* smem_raw) {
-  using L = SmemLayout<BN, CL, Epi::kEpiSmemBytes>;
+  using L = SmemLayout<BN, CL, Epi::kEpiSmemBytes, RESA, NSUB>;
   constexpr int kStages = L::kStages;
   constexpr int BNI = BN / NSPLIT;                           // UMMA N
   constexpr int BNL = BNI / CL;                              // rows of one N sub-tile held by this CTA
@@ -169,9 +185,10 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 
   // 1024-B aligned carve-up (swizzle-128B atoms need it): [pipeline stages][epilogue staging][control]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* pipe = smem;
-  uint8_t* epi_smem = smem + L::kPipeBytes;
-  SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem + L::kPipeBytes + L::kEpiBytes);
+  uint8_t* res_a = smem;                       // resident A (RESA): kResKBlocks x 16 KB
+  uint8_t* pipe = smem + L::kResBytes;
+  uint8_t* epi_smem = pipe + L::kPipeBytes;
+  SharedCtl* ctl = reinterpret_cast<SharedCtl*>(pipe + L::kPipeBytes + L::kEpiBytes);
 
   const int warp_id = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -206,6 +223,8 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 #endif
       sm100::mbar_init(&ctl->tmem_empty_local[i], Epi::kEpiWarps);
     }
+    sm100::mbar_init(&ctl->a_full, 1);
+    sm100::mbar_init(&ctl->a_empty, 1);
     sm100::fence_barrier_init();
   }
   if (warp == 1) {
@@ -219,7 +238,13 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
   const uint32_t tmem_base = ctl->tmem_base;
 
   TileWalker walk;
-  walk.init(p, num_m_super, cid, ncl, num_super);
+  if (RESA) {   // contiguous chunk per cluster: consecutive tiles share the M tile whose A rows stay resident
+    const int per = (num_super + ncl - 1) / ncl;
+    const int first = cid * per;
+    walk.init_range(p, num_m_super, first, min(per, num_super - first));
+  } else {
+    walk.init(p, num_m_super, cid, ncl, num_super);
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====
@@ -229,19 +254,43 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     // thread - not the tensor pipe - the limiter of the 64-cycle N=128 MMAs.
     {
       PipeState st;
+      int res_m = -1, res_batch = -1;     // M tile whose A rows are resident (RESA)
+      uint32_t res_phase = 0;
       for (; walk.valid(); walk.next()) {
         const TileCoord tc = walk.coord(p, CL, crank);
         const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
         const int kb0 = tc.split * p.kb_per_split;
         const int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
+        if (RESA && (tc.m_tile != res_m || tc.batch != res_batch)) {
+          // (re)load the resident A rows of sub-GEMM 0: every k-block, once per M tile.  The previous
+          // resident tile must have been read by its last MMA (a_empty, committed by the MMA issuer).
+          sm100::mbar_wait(&ctl->a_empty, res_phase ^ 1, 8);
+          if (sm100::elect_one()) {
+            const uint32_t af = kPair ? sm100::mapa_u32(sm100::smem_u32(&ctl->a_full), 0) : 0;
+            if (leader) sm100::mbar_expect_tx(&ctl->a_full, CL * p.num_k_blocks * L::kABytes);
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+              uint8_t* dst = res_a + kb * L::kABytes;
+              if (kPair) {
+                if (p.batches > 1) sm100::tma_load_3d_pair(dst, tmA0, af, kb * BK, m0, tc.batch);
+                else sm100::tma_load_2d_pair(dst, tmA0, af, kb * BK, m0);
+              } else {
+                if (p.batches > 1) sm100::tma_load_3d(dst, tmA0, &ctl->a_full, kb * BK, m0, tc.batch);
+                else sm100::tma_load_2d(dst, tmA0, &ctl->a_full, kb * BK, m0);
+              }
+            }
+          }
+          __syncwarp();
+          res_m = tc.m_tile; res_batch = tc.batch; res_phase ^= 1;
+        }
         for (int sub = 0; sub < NSUB; ++sub) {
           const CUtensorMap* ma = sub ? tmA1 : tmA0;
           const CUtensorMap* mb = sub ? tmB1 : tmB0;
+          const bool load_a = !(RESA && sub == 0);
           for (int kb = kb0; kb < kb1; ++kb) {
             sm100::mbar_wait(&ctl->empty[st.stage], st.phase ^ 1, 1);
             if (sm100::elect_one()) {
             uint8_t* sa = pipe + st.stage * L::kStageBytes;
-            uint8_t* sb = sa + L::kABytes;
+            uint8_t* sb = sa + (L::kStageHasA ? L::kABytes : 0);
             uint64_t* full = &ctl->full[st.stage];
             // pair: all bytes (both CTAs) are counted on the leader's barrier.  (Counting per CTA and
             // forwarding "my half landed" with a release.cluster arrive was measured 2x slower: the
@@ -250,7 +299,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 #if DINOX_EXP_NO_TMA   // experiment: no operand loads at all, the MMAs re-read whatever is in smem
             if (leader) sm100::mbar_arrive(full);
 #else
-            if (leader) sm100::mbar_expect_tx(full, CL * L::kStageBytes);
+            if (leader) sm100::mbar_expect_tx(full, CL * (load_a ? L::kABytes + L::kBBytes : L::kBBytes));
             const uint32_t full_addr = kRemoteTx ? sm100::mapa_u32(sm100::smem_u32(full), 0) : 0;
             const int k0 = kb * BK;
             const bool b3 = p.batches > 1;
@@ -263,12 +312,14 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
                 else sm100::tma_load_2d(dst, tm, full, c0, c1);
               }
             };
-            // ---- A: this CTA's own 128 rows
-            if (!p.a_mn_major) {
-              load(sa, ma, k0, m0);
-            } else {
+            // ---- A: this CTA's own 128 rows (not for the sub-GEMM whose A is resident)
+            if (load_a) {
+              if (!p.a_mn_major) {
+                load(sa, ma, k0, m0);
+              } else {
 #pragma unroll
-              for (int c = 0; c < BM / 64; ++c) load(sa + c * (BK * 128), ma, m0 + c * 64, k0);
+                for (int c = 0; c < BM / 64; ++c) load(sa + c * (BK * 128), ma, m0 + c * 64, k0);
+              }
             }
             // ---- B: for every N sub-tile h, this CTA's BNL of its BNI rows
 #pragma unroll
@@ -319,10 +370,23 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
       PipeState st;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
+      int res_m = -1, res_batch = -1;
+      uint32_t res_phase = 0;
       for (; walk.valid(); walk.next()) {
         const TileCoord tc = walk.coord(p, CL, crank);
         const int kb0 = tc.split * p.kb_per_split;
         const int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
+        bool res_last = false;    // is this the last tile that reads the current resident A?
+        if (RESA) {
+          if (tc.m_tile != res_m || tc.batch != res_batch) {
+            sm100::mbar_wait(&ctl->a_full, res_phase, 9);
+            res_m = tc.m_tile; res_batch = tc.batch; res_phase ^= 1;
+          }
+          TileWalker nxt = walk;
+          nxt.next();
+          const TileCoord tn = nxt.coord(p, CL, crank);
+          res_last = !nxt.valid() || tn.m_tile != tc.m_tile || tn.batch != tc.batch;
+        }
         sm100::mbar_wait(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, 2);
         sm100::tc_fence_after();
         for (int sub = 0; sub < NSUB; ++sub) {
@@ -330,8 +394,9 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
           for (int kb = kb0; kb < kb1; ++kb) {
             sm100::mbar_wait(&ctl->full[st.stage], st.phase, 3);
             sm100::tc_fence_after();
-            const uint32_t sa = sm100::smem_u32(pipe + st.stage * L::kStageBytes);
-            const uint32_t sb = sa + L::kABytes;
+            const uint32_t stage_base = sm100::smem_u32(pipe + st.stage * L::kStageBytes);
+            const uint32_t sa = (RESA && sub == 0) ? sm100::smem_u32(res_a + kb * L::kABytes) : stage_base;
+            const uint32_t sb = stage_base + (L::kStageHasA ? L::kABytes : 0);
             if (sm100::elect_one()) {
 #if DINOX_EXP_NO_MMA   // experiment: operands stream through smem but nothing reads them
             sm100::mbar_arrive(&ctl->empty[st.stage]);
@@ -350,6 +415,11 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             // frees the smem slot (in both CTAs of a pair) when these MMAs retire
             if (kPair) sm100::umma_commit_pair(&ctl->empty[st.stage]);
             else sm100::umma_commit(&ctl->empty[st.stage]);
+            // ... and the resident A tile after the last MMA of the last tile that reads it
+            if (RESA && sub == 0 && res_last && kb == kb1 - 1) {
+              if (kPair) sm100::umma_commit_pair(&ctl->a_empty);
+              else sm100::umma_commit(&ctl->a_empty);
+            }
 #endif
             }   // elected lane
             __syncwarp();
@@ -411,9 +481,9 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
   }
 }
 
-template <int BN, int CL, class Epi>
+template <int BN, int CL, class Epi, bool RESA = false, int NSUB = 1>
 constexpr int smem_bytes() {
-  return SmemLayout<BN, CL, Epi::kEpiSmemBytes>::kTotal;
+  return SmemLayout<BN, CL, Epi::kEpiSmemBytes, RESA, NSUB>::kTotal;
 }
 
 // lane quarter of TMEM this warp may read (hardware: warp_id % 4), and which column half it owns
