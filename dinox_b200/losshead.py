@@ -18,7 +18,9 @@ Everything computes through libdinox_b200.so; CPU tensors raise (no fallback).
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -465,6 +467,24 @@ def _entry_plan(B, Vg, V, Mm, device) -> _EntryPlan:
     return p
 
 
+_SIDE_STREAMS: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
+
+
+def concurrency() -> int:
+    """DINOX_CONCURRENCY: 0 = one stream; 1 = Gram anchoring on a side stream (LossHeadStep);
+    2 (default) = also the teacher branch of the fused head loss."""
+    return int(os.environ.get("DINOX_CONCURRENCY", "2"))
+
+
+def _side_stream(device, which: int = 0) -> "torch.cuda.Stream":
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def _accumulate_grad(p: torch.Tensor, fn) -> None:
     """fn(out_tensor, accumulate: bool) writes/accumulates dL/dp straight into p.grad (fp32)."""
     if p.grad is None:
@@ -496,59 +516,74 @@ class _FusedHeadLoss(torch.autograd.Function):
         w1s, w2s = bf16_weight(s_head[0].weight), bf16_weight(s_head[2].weight)
         w1t, w2t = bf16_weight(t_head[0].weight), bf16_weight(t_head[2].weight)
 
-        # ---- stage inputs: [CLS rows | masked patch rows] as contiguous bf16
+        # Two branches that meet at pass 2.  The teacher branch (no gradient) is issued on a side stream
+        # so that its ~20 short kernels slot into the launch gaps and wave tails of the student branch;
+        # per-kernel timing (ops.TIMER) keeps everything on one stream.
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev) if (concurrency() >= 2 and not ops.TIMER.enabled) else None
+        if side is not None:
+            side.wait_stream(main)
+        # ---- teacher: stage inputs [CLS rows | masked patch rows] as bf16, layer 1, statistics
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            xt = torch.empty(Mt + Mm, D, dtype=torch.bfloat16, device=dev)
+            ops.gather_cast_bf16(teacher_cls.detach(), None, xt[:Mt])
+            if Mm:
+                ops.gather_cast_bf16(teacher_patch.detach(), None, xt[Mt:])
+            a_t = ops.gemm_bf16(xt, w1t, bias_n=t_head[0].bias.detach())   # layer 1 (zoo/arch.py:253-254)
+            ht = ops.gelu_fwd(a_t)
+            del a_t
+            # centre statistics: batch-mean teacher logits are W2t . mean(h_t) + b2t by
+            # linearity, so the data-parallel payload is the D-vector sum(h_t) (CLS and masked-patch rows
+            # in ONE all-reduce), launched now so that its latency hides behind the pass-1/pass-2 GEMMs
+            hsum = hsum_work = None
+            if update_center and teacher_mode == "center":
+                hsum = torch.empty(2 if Mm else 1, D, dtype=torch.float32, device=dev)
+                ops.cols_sum(ht[:Mt], out=hsum[0])
+                if Mm:
+                    ops.cols_sum(ht[Mt:], out=hsum[1])   # every rank masks the same number of tokens (no host sync)
+                hsum_work = allreduce_sum_async(hsum, pg)
+            # pass 1, teacher rows: row statistics with logits kept on chip
+            b2t = t_head[2].bias.detach()
+            center = loss_mod.center.reshape(-1)
+            rb2_t = torch.empty(Mt + Mm, dtype=torch.float32, device=dev)
+            if teacher_mode == "center":
+                ct2 = ops.axpby(b2t, inv_tt * LOG2E, center, -inv_tt * LOG2E)
+                with ops.TIMER.region("head_stats_teacher_cls"):
+                    ops.head_stats(ht[:Mt], w2t, inv_tt, ct2, want_nat=False, out_log2=rb2_t[:Mt])
+            else:  # Sinkhorn-Knopp on the (small) materialised CLS teacher logits
+                t_cls = ops.gemm_bf16(ht[:Mt], w2t, bias_n=b2t)
+                a_col, b_row = sinkhorn_knopp_biases(t_cls, teacher_temp, sk_iters, pg)
+                ct2 = ops.axpby(b2t, inv_tt * LOG2E, a_col, -LOG2E)
+                ops.axpb(b_row, LOG2E, out=rb2_t[:Mt])
+                del t_cls
+            ct2_patch = None
+            if Mm:
+                ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E)
+                with ops.TIMER.region("head_stats_teacher_patch"):
+                    ops.head_stats(ht[Mt:], w2t, inv_tt, ct2_patch, want_nat=False, out_log2=rb2_t[Mt:])
+            ht_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
+            ops.gather_cast_bf16(ht, plan.ent_t, ht_e)
+            rb2_e = ops.gather_f32(rb2_t, plan.ent_t)
+        # ---- student: the same on the current stream
         xs = torch.empty(Ms + Mm, D, dtype=torch.bfloat16, device=dev)
-        xt = torch.empty(Mt + Mm, D, dtype=torch.bfloat16, device=dev)
         ops.gather_cast_bf16(student_cls.detach(), None, xs[:Ms])
-        ops.gather_cast_bf16(teacher_cls.detach(), None, xt[:Mt])
         if Mm:
             ops.gather_cast_bf16(student_patch.detach(), None, xs[Ms:])
-            ops.gather_cast_bf16(teacher_patch.detach(), None, xt[Mt:])
-        # ---- layer 1 (zoo/arch.py:253-254)
         a_s = ops.gemm_bf16(xs, w1s, bias_n=s_head[0].bias.detach())
         hs = ops.gelu_fwd(a_s)
-        a_t = ops.gemm_bf16(xt, w1t, bias_n=t_head[0].bias.detach())
-        ht = ops.gelu_fwd(a_t)
-        del a_t
-        # ---- centre statistics: batch-mean teacher logits are W2t . mean(h_t) + b2t by
-        # linearity, so the data-parallel payload is the D-vector sum(h_t) (CLS and masked-patch rows
-        # in ONE all-reduce), launched now so that its latency hides behind the pass-1/pass-2 GEMMs
-        hsum = hsum_work = None
-        if update_center and teacher_mode == "center":
-            hsum = torch.empty(2 if Mm else 1, D, dtype=torch.float32, device=dev)
-            ops.cols_sum(ht[:Mt], out=hsum[0])
-            if Mm:
-                ops.cols_sum(ht[Mt:], out=hsum[1])   # every rank masks the same number of tokens (no host sync)
-            hsum_work = allreduce_sum_async(hsum, pg)
-        # ---- pass 1: row statistics with logits kept on chip
-        b2s, b2t = s_head[2].bias.detach(), t_head[2].bias.detach()
+        b2s = s_head[2].bias.detach()
         cs2 = ops.axpb(b2s, inv_ts * LOG2E)
         with ops.TIMER.region("head_stats_student"):
             _, lse2_s = ops.head_stats(hs, w2s, inv_ts, cs2, want_nat=False)
-        center = loss_mod.center.reshape(-1)
-        rb2_t = torch.empty(Mt + Mm, dtype=torch.float32, device=dev)
-        if teacher_mode == "center":
-            ct2 = ops.axpby(b2t, inv_tt * LOG2E, center, -inv_tt * LOG2E)
-            with ops.TIMER.region("head_stats_teacher_cls"):
-                ops.head_stats(ht[:Mt], w2t, inv_tt, ct2, want_nat=False, out_log2=rb2_t[:Mt])
-        else:  # Sinkhorn-Knopp on the (small) materialised CLS teacher logits
-            t_cls = ops.gemm_bf16(ht[:Mt], w2t, bias_n=b2t)
-            a_col, b_row = sinkhorn_knopp_biases(t_cls, teacher_temp, sk_iters, pg)
-            ct2 = ops.axpby(b2t, inv_tt * LOG2E, a_col, -LOG2E)
-            ops.axpb(b_row, LOG2E, out=rb2_t[:Mt])
-            del t_cls
-        ct2_patch = None
-        if Mm:
-            ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E)
-            with ops.TIMER.region("head_stats_teacher_patch"):
-                ops.head_stats(ht[Mt:], w2t, inv_tt, ct2_patch, want_nat=False, out_log2=rb2_t[Mt:])
         # ---- entries
         hs_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
-        ht_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
         ops.gather_cast_bf16(hs, plan.ent_s, hs_e)
-        ops.gather_cast_bf16(ht, plan.ent_t, ht_e)
         lse2_e = ops.gather_f32(lse2_s, plan.ent_s)
-        rb2_e = ops.gather_f32(rb2_t, plan.ent_t)
+        if side is not None:
+            # Everything the teacher branch allocated lives in the side stream's pool and is read by pass 2 on
+            # this stream: those blocks are only handed out again to side-stream work, and every side-stream
+            # region starts by waiting for this stream, i.e. after pass 2 has been queued.
+            main.wait_stream(side)
         cw = plan.cw_base
         if Mm:
             cw = plan.cw_base.clone()

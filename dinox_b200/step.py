@@ -6,6 +6,7 @@
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional
 
@@ -60,17 +61,7 @@ class LossHeadStep:
     def micro_step(self, f: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """f: student_cls, teacher_cls (+ student_tok, teacher_tok) (+ student_patch, teacher_patch,
         masks_weight); student tensors may require grad.  Returns the component losses."""
-        out = losshead.fused_head_dino_loss(
-            f["student_cls"], f["teacher_cls"], self.student_head, self.teacher_head, self.dino_loss,
-            self.student_temp, self.teacher_temp, student_patch=f.get("student_patch"),
-            teacher_patch=f.get("teacher_patch"), masks_weight=f.get("masks_weight"),
-            center_patch=self.center_patch if "student_patch" in f else None, ibot_weight=self.ibot_weight)
-        loss = out["loss"]
-        if "student_tok" in f:
-            out["loss_gram"] = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
-            loss = loss + self.gram_weight * out["loss_gram"]
-        loss = self._add_koleo(f, out, loss)
-        out["loss_total"] = loss.detach()
+        out, loss = self._losses(f)
         (loss / self.accum).backward()
         self.micro += 1
         if self.micro % self.accum == 0:
@@ -149,19 +140,35 @@ class LossHeadStep:
         ops.TIMER.enabled = was_timing
 
     def _fwd_bwd(self, f):
+        out, loss = self._losses(f)
+        (loss / self.accum).backward()
+        return out
+
+    def _losses(self, f):
+        """Forward of all loss terms.  Gram anchoring is independent of the head until the final sum: it is
+        issued first, on a side stream, and its small kernels (and, by autograd's stream rule, their
+        backward) run beside the head's GEMMs instead of between them."""
+        gram, side = None, None
+        if "student_tok" in f:
+            if losshead.concurrency() >= 1 and not ops.TIMER.enabled:
+                side = losshead._side_stream(self.device, 1)
+                side.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                gram = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
         out = losshead.fused_head_dino_loss(
             f["student_cls"], f["teacher_cls"], self.student_head, self.teacher_head, self.dino_loss,
             self.student_temp, self.teacher_temp, student_patch=f.get("student_patch"),
             teacher_patch=f.get("teacher_patch"), masks_weight=f.get("masks_weight"),
             center_patch=self.center_patch if "student_patch" in f else None, ibot_weight=self.ibot_weight)
         loss = out["loss"]
-        if "student_tok" in f:
-            out["loss_gram"] = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
-            loss = loss + self.gram_weight * out["loss_gram"]
+        if gram is not None:
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+            out["loss_gram"] = gram
+            loss = loss + self.gram_weight * gram
         loss = self._add_koleo(f, out, loss)
         out["loss_total"] = loss.detach()
-        (loss / self.accum).backward()
-        return out
+        return out, loss
 
     def _add_koleo(self, f, out, loss):
         if self.koleo is None:
