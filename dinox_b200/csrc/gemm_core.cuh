@@ -41,6 +41,11 @@ constexpr int UMMA_K = 16;
 #define DINOX_CTRL_WARPS_LAST 1
 #endif
 
+// A-operand collector reuse across the N sub-tiles of a 384-wide tile (see sm100::umma_bf16_collect)
+#ifndef DINOX_COLLECTOR
+#define DINOX_COLLECTOR 1
+#endif
+
 struct TileCoord {
   int m_tile, n_tile, batch, split;
 };
@@ -405,11 +410,22 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = sm100::umma_smem_desc(sa + k * a_adv, a_lbo, 1024);
+              const uint32_t acc = (uint32_t)((kb != kb0) | (k != 0));
+              if (NSPLIT == 3 && DINOX_COLLECTOR) {
+                // the three N sub-tiles multiply the same A slab: read it from shared memory once
+                const uint64_t db0 = sm100::umma_smem_desc(sb + k * b_adv, b_lbo, 1024);
+                const uint64_t db1 = sm100::umma_smem_desc(sb + b_split + k * b_adv, b_lbo, 1024);
+                const uint64_t db2 = sm100::umma_smem_desc(sb + 2 * b_split + k * b_adv, b_lbo, 1024);
+                sm100::umma_bf16_collect<1, kPair>(d_tmem, da, db0, idesc, acc);
+                sm100::umma_bf16_collect<2, kPair>(d_tmem + BNI, da, db1, idesc, acc);
+                sm100::umma_bf16_collect<3, kPair>(d_tmem + 2 * BNI, da, db2, idesc, acc);
+              } else {
 #pragma unroll
-              for (int h = 0; h < NSPLIT; ++h) {
-                const uint64_t db = sm100::umma_smem_desc(sb + h * b_split + k * b_adv, b_lbo, 1024);
-                if (kPair) sm100::umma_bf16_pair(d_tmem + h * BNI, da, db, idesc, (uint32_t)((kb != kb0) | (k != 0)));
-                else sm100::umma_bf16(d_tmem + h * BNI, da, db, idesc, (uint32_t)((kb != kb0) | (k != 0)));
+                for (int h = 0; h < NSPLIT; ++h) {
+                  const uint64_t db = sm100::umma_smem_desc(sb + h * b_split + k * b_adv, b_lbo, 1024);
+                  if (kPair) sm100::umma_bf16_pair(d_tmem + h * BNI, da, db, idesc, acc);
+                  else sm100::umma_bf16(d_tmem + h * BNI, da, db, idesc, acc);
+                }
               }
             }
             // frees the smem slot (in both CTAs of a pair) when these MMAs retire

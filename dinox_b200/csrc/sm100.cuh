@@ -201,6 +201,30 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// Same MMAs with a collector hint for the A operand: consecutive instructions that multiply the SAME A
+// slab by different B slabs (N sub-tiles of a wide tile) keep A in the tensor core's collector buffer
+// instead of re-reading it from shared memory.  kUse: 0 = none, 1 = fill (first), 2 = use, 3 = lastuse.
+// SASS: UTCHMMA gdesc[..].A_KEEP / .A_REUSE.A_KEEP / .A_REUSE
+template <int kUse, bool kPair>
+__device__ __forceinline__ void umma_bf16_collect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+#define DINOX_UMMA_C(CG, COLL)                                                                       \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                   \
+               "tcgen05.mma.cta_group::" CG ".kind::f16" COLL " [%0], %1, %2, %3, p;\n\t}"          \
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory")
+  if (kPair) {
+    if (kUse == 1) DINOX_UMMA_C("2", ".collector::a::fill");
+    else if (kUse == 2) DINOX_UMMA_C("2", ".collector::a::use");
+    else if (kUse == 3) DINOX_UMMA_C("2", ".collector::a::lastuse");
+    else DINOX_UMMA_C("2", "");
+  } else {
+    if (kUse == 1) DINOX_UMMA_C("1", ".collector::a::fill");
+    else if (kUse == 2) DINOX_UMMA_C("1", ".collector::a::use");
+    else if (kUse == 3) DINOX_UMMA_C("1", ".collector::a::lastuse");
+    else DINOX_UMMA_C("1", "");
+  }
+#undef DINOX_UMMA_C
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (one row per thread)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
