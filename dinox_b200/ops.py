@@ -441,6 +441,7 @@ class KernelTimer:
         self._pending = []
         self.totals = {}
         self.counts = {}
+        self.samples = {}
 
     class _Region:
         def __init__(self, timer, name):
@@ -466,10 +467,11 @@ class KernelTimer:
         for name, e0, e1 in self._pending:
             self.totals[name] = self.totals.get(name, 0.0) + e0.elapsed_time(e1)
             self.counts[name] = self.counts.get(name, 0) + 1
+            self.samples.setdefault(name, []).append(e0.elapsed_time(e1))
         self._pending = []
 
     def reset(self):
-        self._pending, self.totals, self.counts = [], {}, {}
+        self._pending, self.totals, self.counts, self.samples = [], {}, {}, {}
 
 
 TIMER = KernelTimer()
