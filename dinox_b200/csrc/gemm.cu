@@ -728,13 +728,13 @@ struct EpiAdapter {
   }
 };
 
-template <int BN, int NSPLIT, int NSUB, int CL, class Epi, bool RESA = false>
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi, int RES = kResNone>
 __global__ void __launch_bounds__((2 + Epi::kEpiWarps) * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
             const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
             const __grid_constant__ CUtensorMap tmC, const CoreParams p, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
-  gemm_body<BN, NSPLIT, NSUB, CL, EpiAdapter<BN, Epi>, RESA>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, &tmC, smem_raw);
+  gemm_body<BN, NSPLIT, NSUB, CL, EpiAdapter<BN, Epi>, RES>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, &tmC, smem_raw);
 }
 
 // number of CTAs for `tiles` super tiles of a CL-cluster kernel: one CTA per SM, whole clusters
@@ -770,7 +770,7 @@ static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int t
   return make_tmap_bf16_2d(tm, o.ptr, K, o.rows, o.ld, BK, what);  // box = 64 k-rows x 64 mn-elements
 }
 
-template <int BN, int NSPLIT, int NSUB, int CL, class Epi, bool RESA = false>
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi, int RES = kResNone>
 static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const Operand* b1, int64_t M, int64_t N,
                   int64_t K, int m_fastest, const typename Epi::Params& ep, const OutDesc& od, cudaStream_t stream,
                   const char* name, int64_t batches = 1, int64_t splits = 1) {
@@ -807,10 +807,12 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   p.kb_per_split = (int)((p.num_k_blocks + splits - 1) / splits);
   DINOX_REQUIRE(splits == 1 || (int64_t)p.kb_per_split * (splits - 1) < p.num_k_blocks, DINOX_E_BADARG,
                 "%s: %lld splits leave an empty K range", name, (long long)splits);
-  DINOX_REQUIRE(!RESA || (p.num_k_blocks <= kResKBlocks && !a0.mn_major && splits == 1), DINOX_E_UNSUPPORTED,
+  DINOX_REQUIRE(RES != kResA || (p.num_k_blocks <= kResKBlocks && !a0.mn_major && splits == 1), DINOX_E_UNSUPPORTED,
                 "%s: resident-A mode needs a K-major A operand with K <= %d", name, kResKBlocks * BK);
-  auto kern = gemm_kernel<BN, NSPLIT, NSUB, CL, Epi, RESA>;
-  constexpr int smem = smem_bytes<BN, CL, Epi, RESA, NSUB>();
+  DINOX_REQUIRE(RES != kResB || (p.num_k_blocks <= kResKBlocks && !b0.mn_major && splits == 1 && batches == 1),
+                DINOX_E_UNSUPPORTED, "%s: resident-B mode needs a K-major B operand with K <= %d", name, kResKBlocks * BK);
+  auto kern = gemm_kernel<BN, NSPLIT, NSUB, CL, Epi, RES>;
+  constexpr int smem = smem_bytes<BN, CL, Epi, RES, NSUB>();
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   // the opt-in shared-memory size is a per-device function attribute
   static bool attr_set[64] = {};
@@ -1012,8 +1014,8 @@ int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int
   EpiStats::Params ep{inv_tau * DINOX_LOG2E, col2, reinterpret_cast<float2*>(workspace)};
   const bool cl2 = rows > BM && pair_enabled(kPairStats);
   if (resa_enabled(kPairStats, D))   // prototype tiles fastest: the H rows of one M tile stay in shared memory
-    rc = cl2 ? launch<256, 1, 1, 2, EpiStats, true>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/0, ep, OutDesc{}, stream, "head_stats<pair,resA>")
-             : launch<256, 1, 1, 1, EpiStats, true>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/0, ep, OutDesc{}, stream, "head_stats<resA>");
+    rc = cl2 ? launch<256, 1, 1, 2, EpiStats, kResA>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/0, ep, OutDesc{}, stream, "head_stats<pair,resA>")
+             : launch<256, 1, 1, 1, EpiStats, kResA>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/0, ep, OutDesc{}, stream, "head_stats<resA>");
   else
     rc = cl2 ? launch<256, 1, 1, 2, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats<pair>")
              : launch<256, 1, 1, 1, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats");
@@ -1055,9 +1057,8 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
   od.row_bytes = EpiGradT::kRowBytes;
   // entry tiles fastest: the 2 x (K-tile of W2) operands stay put while HsE/HtE (L2-resident) stream
   const bool cl2 = K > BM && pair_enabled(kPairGrad);
-  if (resa_enabled(kPairGrad, D))
-    rc = cl2 ? launch<128, 1, 2, 2, EpiGradT, true>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, od, stream, "head_grad<pair,resA>")
-             : launch<128, 1, 2, 1, EpiGradT, true>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, od, stream, "head_grad<resA>");
+  if (cl2 && resa_enabled(kPairGrad, D))   // entries of an N tile resident (student + teacher), W2 tiles stream
+    rc = launch<128, 1, 2, 2, EpiGradT, kResB>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/1, ep, od, stream, "head_grad<pair,resB>");
   else
     rc = cl2 ? launch<128, 1, 2, 2, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, od, stream, "head_grad<pair>")
              : launch<128, 1, 2, 1, EpiGradT>(a0, b0, &a1, &b1, K, E, D, /*m_fastest=*/0, ep, od, stream, "head_grad");

@@ -62,17 +62,22 @@ struct CoreParams {
 
 constexpr int kResKBlocks = 6;   // resident-A mode holds up to 6 k-blocks (K <= 384) of this CTA's 128 A rows
 
-// RESA: the A operand of sub-GEMM 0 stays resident in shared memory across consecutive tiles that share
-// the M tile (96 KB); stages of a single-GEMM kernel then carry B only.
-template <int BN, int CL, int EPI_SMEM, bool RESA = false, int NSUB = 1>
+// Resident-operand modes (RES): an operand that consecutive tiles of a CTA share stays in shared memory
+// (all k-blocks, K <= 384) and only the other operand streams through the stage ring.
+//   kResA : A rows of sub-GEMM 0, tiles walked N-fastest in contiguous runs (pass 1: the H rows of an M tile)
+//   kResB : B rows of EVERY sub-GEMM, tiles walked in M-columns (pass 2: the entries of an N tile; a CTA of
+//           a pair holds 1/CL of them, so student + teacher fit: 2 x 6 x 8 KB)
+enum : int { kResNone = 0, kResA = 1, kResB = 2 };
+template <int BN, int CL, int EPI_SMEM, int RES = kResNone, int NSUB = 1>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
   static constexpr int kBBytes = (BN / CL) * BK * 2;   // a CTA of a pair holds 1/CL of the B tile
-  static constexpr bool kStageHasA = !(RESA && NSUB == 1);
-  static constexpr int kStageBytes = (kStageHasA ? kABytes : 0) + kBBytes;
-  static constexpr int kResBytes = RESA ? kResKBlocks * kABytes : 0;
+  static constexpr bool kStageHasA = !(RES == kResA && NSUB == 1);
+  static constexpr bool kStageHasB = RES != kResB;
+  static constexpr int kStageBytes = (kStageHasA ? kABytes : 0) + (kStageHasB ? kBBytes : 0);
+  static constexpr int kResBytes = RES == kResA ? kResKBlocks * kABytes : RES == kResB ? NSUB * kResKBlocks * kBBytes : 0;
   static constexpr int kEpiBytes = (EPI_SMEM + 255) / 256 * 256;
-  // 227 KB per CTA minus alignment slack (1 KB), control block (256 B), the epilogue's staging area and resident A
+  // 227 KB per CTA minus alignment slack (1 KB), control block (256 B), the epilogue's staging area and the resident operand
   static constexpr int kBudget = 227 * 1024 - 1024 - 256 - kEpiBytes - kResBytes;
 #ifndef DINOX_MAX_STAGES
 #define DINOX_MAX_STAGES 8
@@ -110,9 +115,44 @@ struct TileWalker {
     dfast = 1; dslow = 0; douter = 0;
     remaining = count > 0 ? count : 0;
   }
+  // Column schedule (resident B): every cluster sweeps the M tiles of ONE N tile at a time, all clusters in
+  // step (they read the same A tile at the same time -> it is fetched from HBM once).  Whole rounds of `ncl`
+  // columns first; of the `rem` left-over columns each goes to one cluster, which gives up its last `tail`
+  // M tiles to the ncl - rem otherwise idle clusters so that everybody finishes together.
+  bool columns = false;
+  int cm, cn, m_lo, m_hi, n_step, rem_a;          // current position / phase A (whole rounds) bookkeeping
+  int b_cm, b_cn, b_lo, b_hi, b_step;             // phase B (left-over columns) start state
+  __device__ __forceinline__ void init_columns(const CoreParams& p, int num_m, int cid, int ncl) {
+    columns = true;
+    const int num_n = p.num_n_tiles;
+    const int full = num_n / ncl, rem = num_n - full * ncl, n_base = full * ncl;
+    rem_a = full * num_m;
+    int count_b = 0;
+    b_cm = b_cn = b_lo = 0; b_hi = num_m; b_step = 0;
+    if (rem > 0) {
+      const int spares = ncl - rem;
+      const int tail = (int)(((long long)num_m * spares) / ncl);
+      if (cid < rem) {
+        b_cn = n_base + cid; b_cm = 0; b_lo = 0; b_hi = num_m; b_step = 0; count_b = num_m - tail;
+      } else if (tail > 0) {
+        const int total = rem * tail, per = (total + spares - 1) / spares, j0 = (cid - rem) * per;
+        count_b = min(per, total - j0);
+        if (count_b < 0) count_b = 0;
+        b_cn = n_base + j0 / tail; b_lo = num_m - tail; b_cm = b_lo + j0 % tail; b_hi = num_m; b_step = 1;
+      }
+    }
+    remaining = rem_a + count_b;
+    if (rem_a > 0) { cn = cid; cm = 0; m_lo = 0; m_hi = num_m; n_step = ncl; }
+    else { cn = b_cn; cm = b_cm; m_lo = b_lo; m_hi = b_hi; n_step = b_step; }
+  }
   __device__ __forceinline__ bool valid() const { return remaining > 0; }
   __device__ __forceinline__ void next() {
     --remaining;
+    if (columns) {
+      if (rem_a > 0 && --rem_a == 0) { cn = b_cn; cm = b_cm; m_lo = b_lo; m_hi = b_hi; n_step = b_step; return; }
+      if (++cm == m_hi) { cm = m_lo; cn += n_step; }
+      return;
+    }
     fast += dfast;
     int carry = 0;
     if (fast >= nfast) { fast -= nfast; carry = 1; }
@@ -124,6 +164,7 @@ struct TileWalker {
   // CL-wide super tile -> this CTA's tile
   __device__ __forceinline__ TileCoord coord(const CoreParams& p, int cl, int crank) const {
     TileCoord c;
+    if (columns) { c.m_tile = cm * cl + crank; c.n_tile = cn; c.batch = 0; c.split = 0; return c; }
     c.m_tile = (m_fastest ? fast : slow) * cl + crank;
     c.n_tile = m_fastest ? slow : fast;
     c.batch = p.splits > 1 ? 0 : outer;
@@ -146,7 +187,7 @@ struct SharedCtl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t tmem_empty_local[2];   // pair mode, non-leader CTA: its own epilogue warps report here
-  uint64_t a_full, a_empty;       // resident-A mode: "resident A tile landed" / "last MMA reading it retired"
+  uint64_t a_full, a_empty;       // resident operand: "tile landed" / "last MMA reading it retired"
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -169,12 +210,14 @@ __device__ __forceinline__ float fast_ex2(float x) {
 //                the loss head are bound by L2->SMEM operand traffic, not by the tensor pipe.
 // `Epi` provides kEpiWarps, kEpiSmemBytes, Params, State, fetch(), prologue(), tile(), finish().
 // `tmC` is the output tensor map of epilogues that store through TMA (others ignore it).
-template <int BN, int NSPLIT, int NSUB, int CL, class Epi, bool RESA = false>
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi, int RES = kResNone>
 __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Epi::Params& ep,
                                           const CUtensorMap* tmA0, const CUtensorMap* tmB0,
                                           const CUtensorMap* tmA1, const CUtensorMap* tmB1,
                                           const CUtensorMap* tmC, uint8_t* smem_raw) {
-  using L = SmemLayout<BN, CL, Epi::kEpiSmemBytes, RESA, NSUB>;
+  using L = SmemLayout<BN, CL, Epi::kEpiSmemBytes, RES, NSUB>;
+  constexpr bool RESA = (RES == kResA), RESB = (RES == kResB);
+  static_assert(!RESB || NSPLIT == 1, "resident B: one MMA per k-step");
   constexpr int kStages = L::kStages;
   constexpr int BNI = BN / NSPLIT;                           // UMMA N
   constexpr int BNL = BNI / CL;                              // rows of one N sub-tile held by this CTA
@@ -190,7 +233,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 
   // 1024-B aligned carve-up (swizzle-128B atoms need it): [pipeline stages][epilogue staging][control]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* res_a = smem;                       // resident A (RESA): kResKBlocks x 16 KB
+  uint8_t* res_a = smem;                       // resident operand: A k-blocks (kResA) or [sub][k-block] B slabs (kResB)
   uint8_t* pipe = smem + L::kResBytes;
   uint8_t* epi_smem = pipe + L::kPipeBytes;
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(pipe + L::kPipeBytes + L::kEpiBytes);
@@ -247,6 +290,8 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     const int per = (num_super + ncl - 1) / ncl;
     const int first = cid * per;
     walk.init_range(p, num_m_super, first, min(per, num_super - first));
+  } else if (RESB) {
+    walk.init_columns(p, num_m_super, cid, ncl);
   } else {
     walk.init(p, num_m_super, cid, ncl, num_super);
   }
@@ -287,6 +332,24 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
           __syncwarp();
           res_m = tc.m_tile; res_batch = tc.batch; res_phase ^= 1;
         }
+        if (RESB && tc.n_tile != res_m) {
+          // (re)load the resident B rows (this CTA's share of the N tile) of every sub-GEMM, all k-blocks
+          sm100::mbar_wait(&ctl->a_empty, res_phase ^ 1, 8);
+          if (sm100::elect_one()) {
+            const uint32_t af = kPair ? sm100::mapa_u32(sm100::smem_u32(&ctl->a_full), 0) : 0;
+            if (leader) sm100::mbar_expect_tx(&ctl->a_full, CL * NSUB * p.num_k_blocks * L::kBBytes);
+            for (int sub = 0; sub < NSUB; ++sub) {
+              const CUtensorMap* mb = sub ? tmB1 : tmB0;
+              for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                uint8_t* dst = res_a + (sub * kResKBlocks + kb) * L::kBBytes;
+                if (kPair) sm100::tma_load_2d_pair(dst, mb, af, kb * BK, n0 + crank * BNL);
+                else sm100::tma_load_2d(dst, mb, &ctl->a_full, kb * BK, n0 + crank * BNL);
+              }
+            }
+          }
+          __syncwarp();
+          res_m = tc.n_tile; res_phase ^= 1;
+        }
         for (int sub = 0; sub < NSUB; ++sub) {
           const CUtensorMap* ma = sub ? tmA1 : tmA0;
           const CUtensorMap* mb = sub ? tmB1 : tmB0;
@@ -304,7 +367,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 #if DINOX_EXP_NO_TMA   // experiment: no operand loads at all, the MMAs re-read whatever is in smem
             if (leader) sm100::mbar_arrive(full);
 #else
-            if (leader) sm100::mbar_expect_tx(full, CL * (load_a ? L::kABytes + L::kBBytes : L::kBBytes));
+            if (leader) sm100::mbar_expect_tx(full, CL * ((load_a ? L::kABytes : 0) + (RESB ? 0 : L::kBBytes)));
             const uint32_t full_addr = kRemoteTx ? sm100::mapa_u32(sm100::smem_u32(full), 0) : 0;
             const int k0 = kb * BK;
             const bool b3 = p.batches > 1;
@@ -328,7 +391,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             }
             // ---- B: for every N sub-tile h, this CTA's BNL of its BNI rows
 #pragma unroll
-            for (int h = 0; h < NSPLIT; ++h) {
+            for (int h = 0; h < (RESB ? 0 : NSPLIT); ++h) {
               const int r0 = n0 + h * BNI + crank * BNL;
               if (!p.b_mn_major) {
                 load(sb + h * (BNL * 128), mb, k0, r0);
@@ -392,6 +455,15 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
           const TileCoord tn = nxt.coord(p, CL, crank);
           res_last = !nxt.valid() || tn.m_tile != tc.m_tile || tn.batch != tc.batch;
         }
+        if (RESB) {
+          if (tc.n_tile != res_m) {
+            sm100::mbar_wait(&ctl->a_full, res_phase, 9);
+            res_m = tc.n_tile; res_phase ^= 1;
+          }
+          TileWalker nxt = walk;
+          nxt.next();
+          res_last = !nxt.valid() || nxt.coord(p, CL, crank).n_tile != tc.n_tile;
+        }
         sm100::mbar_wait(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, 2);
         sm100::tc_fence_after();
         for (int sub = 0; sub < NSUB; ++sub) {
@@ -401,7 +473,8 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             sm100::tc_fence_after();
             const uint32_t stage_base = sm100::smem_u32(pipe + st.stage * L::kStageBytes);
             const uint32_t sa = (RESA && sub == 0) ? sm100::smem_u32(res_a + kb * L::kABytes) : stage_base;
-            const uint32_t sb = stage_base + (L::kStageHasA ? L::kABytes : 0);
+            const uint32_t sb = RESB ? sm100::smem_u32(res_a + (sub * kResKBlocks + kb) * L::kBBytes)
+                                     : stage_base + (L::kStageHasA ? L::kABytes : 0);
             if (sm100::elect_one()) {
 #if DINOX_EXP_NO_MMA   // experiment: operands stream through smem but nothing reads them
             sm100::mbar_arrive(&ctl->empty[st.stage]);
@@ -432,7 +505,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             if (kPair) sm100::umma_commit_pair(&ctl->empty[st.stage]);
             else sm100::umma_commit(&ctl->empty[st.stage]);
             // ... and the resident A tile after the last MMA of the last tile that reads it
-            if (RESA && sub == 0 && res_last && kb == kb1 - 1) {
+            if (((RESA && sub == 0) || (RESB && sub == NSUB - 1)) && res_last && kb == kb1 - 1) {
               if (kPair) sm100::umma_commit_pair(&ctl->a_empty);
               else sm100::umma_commit(&ctl->a_empty);
             }
@@ -497,9 +570,9 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
   }
 }
 
-template <int BN, int CL, class Epi, bool RESA = false, int NSUB = 1>
+template <int BN, int CL, class Epi, int RES = kResNone, int NSUB = 1>
 constexpr int smem_bytes() {
-  return SmemLayout<BN, CL, Epi::kEpiSmemBytes, RESA, NSUB>::kTotal;
+  return SmemLayout<BN, CL, Epi::kEpiSmemBytes, RES, NSUB>::kTotal;
 }
 
 // lane quarter of TMEM this warp may read (hardware: warp_id % 4), and which column half it owns
