@@ -5,7 +5,7 @@ import torch
 from dinox_b200 import ops
 dev = "cuda"
 g = torch.Generator().manual_seed(4)
-E, K, D, rows = 8576, 65536, 384, 8064
+E, K, D, rows = 8576, 65536, int(os.environ.get("PROBE_D", "384")), 8064
 hs = torch.randn(E, D, generator=g).to(torch.bfloat16).to(dev)
 ht = torch.randn(E, D, generator=g).to(torch.bfloat16).to(dev)
 ws = (torch.randn(K, D, generator=g) / math.sqrt(D)).to(torch.bfloat16).to(dev)
@@ -25,5 +25,5 @@ def timeit(fn, n=5):
 t = {}
 t["stats"] = timeit(lambda: ops.head_stats(hs[:rows], ws, 10.0, cs2))
 t["grad"] = timeit(lambda: ops.head_grad(ws, wt, hs, ht, 10.0, 25.0, cs2, ct2, None, 0, lse_e, r2, cw, loss, gt=gt))
-print(os.environ.get("DINOX_LIB_TAG", "default"), "resa", os.environ.get("DINOX_RESA", "-"), "pair", os.environ.get("DINOX_PAIR", "-"),
+print("D", D, os.environ.get("DINOX_LIB_TAG", "default"), "resa", os.environ.get("DINOX_RESA", "-"), "pair", os.environ.get("DINOX_PAIR", "-"),
       " ".join(f"{k} {v:.3f}" for k, v in t.items()))
