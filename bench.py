@@ -111,7 +111,8 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------
 # CPU legs: the oracle (a port of the reference algorithm) timed on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_oracle_step_time(cfg_name: str, sample_batch: int, steps: int, warmup: int, accum: int):
+def cpu_oracle_step_time(cfg_name: str, sample_batch: int, steps: int, warmup: int, accum: int,
+                         patches_from_tokens: bool = True):
     """Times oracle.LossHeadOracle.step (+ amortised EMA of the full parameter list) on a
     `sample_batch`-image slice of the workload.  Returns (crops/s, cores, description)."""
     from dinox_b200 import synth
@@ -131,11 +132,14 @@ def cpu_oracle_step_time(cfg_name: str, sample_batch: int, steps: int, warmup: i
     shapes = synth.student_param_shapes(D, depth, K)[:-4]
     s_all = [torch.randn(s) * 0.02 for s in shapes] + [p.detach() for p in sp.tensors()]
     t_all = [torch.randn(s) * 0.02 for s in shapes] + [p.detach().clone() for p in tp.tensors()]
-    f = synth.feature_batch(sh, g)
+    f = synth.feature_batch(sh, g, patches_from_tokens=patches_from_tokens)
     times = []
     for i in range(warmup + steps):
         fs = {k: (v.clone().requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()}
         t0 = time.perf_counter()
+        if "patch_index" in fs:   # the iBOT rows are the masked rows of the token tensors (gathered inside the step)
+            fs["student_patch"] = fs["student_tok"].reshape(-1, D)[fs["patch_index"]]
+            fs["teacher_patch"] = fs["teacher_tok"].reshape(-1, D)[fs["patch_index"]]
         orc.step(fs["student_cls"], fs["teacher_cls"], 0.1, 0.04, student_tok=fs["student_tok"],
                  teacher_tok=fs["teacher_tok"], student_patch=fs.get("student_patch"),
                  teacher_patch=fs.get("teacher_patch"), masks_weight=fs.get("masks_weight"), accum=accum)
@@ -158,7 +162,7 @@ def run_reference(args):
     if rank != 0:
         return
     value, cores, desc, per_step = cpu_oracle_step_time(args.config, args.cpu_sample_batch, args.steps, args.warmup,
-                                                         args.accum)
+                                                         args.accum, args.patch_source == "tokens")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
@@ -193,7 +197,9 @@ def run_ours(args):
     sh = synth.LossHeadShapes(**synth.CONFIGS[args.config])
     step = LossHeadStep(sh, dev, accum=args.accum, process_group=pg, teacher_mode=args.teacher_mode)
     g = synth.seeded_generator(2, rank)
-    feats = synth.feature_batch(sh, g)
+    # iBOT rows: named by index inside the (crops, T, D) token tensors the backbone emits (default; the step
+    # gathers them on the device) or shipped as separately materialised rows (--patch-source rows)
+    feats = synth.feature_batch(sh, g, patches_from_tokens=(args.patch_source == "tokens"))
 
     def blob_views(blob, like):
         """typed views into one contiguous byte blob, 256-byte aligned segments, same keys/shapes as `like`"""
@@ -382,7 +388,8 @@ def run_ours(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, desc, _ = cpu_oracle_step_time(args.config, args.cpu_sample_batch, args.cpu_steps, 2, args.accum)
+        v, cores, desc, _ = cpu_oracle_step_time(args.config, args.cpu_sample_batch, args.cpu_steps, 2, args.accum,
+                                                 args.patch_source == "tokens")
         cpu_baseline = {"value": v, "unit": "crops/s", "cores": cores, "kind": "port", "sample": desc}
 
     line = {
@@ -392,7 +399,7 @@ def run_ours(args):
         "config": {
             "workload": f"{args.config}: ViT-{'S' if D == 384 else 'L'}/16 loss head (teacher {args.teacher_mode}), per-GPU batch {sh.batch} x accum {args.accum}, "
                         f"{sh.n_global} global + {sh.n_local} local crops, K={K}, D={D}, iBOT r={sh.mask_ratio} "
-                        f"({sh.masked_rows} masked rows), Gram anchoring on ({sh.tokens - 1} tokens), "
+                        f"({sh.masked_rows} masked rows, {'gathered from the token tensors by index' if args.patch_source == 'tokens' else 'materialised by the caller'}), Gram anchoring on ({sh.tokens - 1} tokens), "
                         f"EMA of {step.n_params / 1e6:.1f} M params every {args.accum} micro-steps",
             "rows": {"student": sh.student_rows, "teacher": sh.teacher_rows, "masked": sh.masked_rows},
             "parallelism": f"dp{world}", "launch": "cuda-graph replay per micro-step" if use_graph else "eager launches",
@@ -433,6 +440,9 @@ def main():
                     help="teacher normalisation of the CLS term (C3 uses sinkhorn)")
     ap.add_argument("--cpu-steps", type=int, default=40, help="timed oracle steps of the cpu_baseline leg (~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--patch-source", default="tokens", choices=["tokens", "rows"],
+                    help="iBOT rows: masked rows of the token tensors named by an index (gathered in the step), or rows "
+                         "materialised by the caller")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     global _OUT

@@ -85,6 +85,19 @@ __global__ void gather_f32_kernel(const float* __restrict__ src, const int64_t* 
   if (i < n) out[i] = idx[i] >= 0 ? src[idx[i]] : fill;
 }
 
+// dst[idx[r], :] = src[r, :] (fp32 rows, D % 4 == 0): one warp per row.  The backward of the in-kernel
+// token gather: masked positions are unique per crop, so rows never collide; idx < 0 is skipped.
+__global__ void scatter_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ idx,
+                                    int64_t rows, int D4, float* __restrict__ dst, int64_t ld_dst) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t t = idx[r];
+  if (t < 0) return;
+  const float4* s = reinterpret_cast<const float4*>(src + r * ld_src);
+  float4* d = reinterpret_cast<float4*>(dst + t * ld_dst);
+  for (int c = threadIdx.x & 31; c < D4; c += 32) d[c] = s[c];
+}
+
 // ---------------------------------------------------------------------------------------------
 // GELU (erf):  h = bf16(gelu(a));   backward: da = bf16(dh * gelu'(a)), colsum(da) for db1
 // ---------------------------------------------------------------------------------------------
@@ -320,6 +333,16 @@ int dinox_gather_f32(const float* src, const int64_t* idx, int64_t n, float fill
   if (n == 0) return DINOX_OK;
   gather_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, idx, n, fill, out);
   return check_launch("gather_f32_kernel", stream);
+}
+
+int dinox_scatter_rows_f32(const float* src, int64_t ld_src, const int64_t* idx, int64_t rows, int64_t D, float* dst,
+                           int64_t ld_dst, dinox_stream_t stream) {
+  DINOX_REQUIRE(src && idx && dst && rows >= 0 && D > 0 && D % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0,
+                DINOX_E_BADARG, "scatter_rows_f32: bad arguments (D, ld multiples of 4)");
+  DINOX_REQUIRE(aligned16(src) && aligned16(dst), DINOX_E_ALIGN, "scatter_rows_f32: misaligned");
+  if (rows == 0) return DINOX_OK;
+  scatter_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(src, ld_src, idx, rows, (int)(D / 4), dst, ld_dst);
+  return check_launch("scatter_rows_kernel", stream);
 }
 
 int dinox_gelu_fwd(const float* a, int64_t n, void* h_bf16, dinox_stream_t stream) {

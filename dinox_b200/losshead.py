@@ -500,7 +500,7 @@ def _accumulate_grad(p: torch.Tensor, fn) -> None:
 class _FusedHeadLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, student_cls, student_patch, teacher_cls, teacher_patch, masks_weight, s_head, t_head, loss_mod,
-                center_patch, cfg):
+                center_patch, cfg, patch_index=None):
         (student_temp, teacher_temp, Vg, n_local, ibot_weight, teacher_mode, sk_iters, pg, update_center,
          patch_momentum) = cfg
         dev = student_cls.device
@@ -510,7 +510,13 @@ class _FusedHeadLoss(torch.autograd.Function):
         B = Mt // Vg
         V = student_cls.shape[0] // B
         Ms = B * V
-        Mm = 0 if student_patch is None else student_patch.shape[0]
+        # iBOT rows: materialised (Mm, D) rows, or - with patch_index - gathered in the staging kernel straight
+        # from the backbone's token tensors (any (..., D) contiguous shape; patch_index = flat row numbers)
+        Mm = 0 if student_patch is None else (student_patch.shape[0] if patch_index is None else patch_index.numel())
+        sp2 = tp2 = None
+        if Mm:
+            sp2 = student_patch.detach() if patch_index is None else student_patch.detach().view(-1, D)
+            tp2 = teacher_patch.detach() if patch_index is None else teacher_patch.detach().view(-1, D)
         plan = _entry_plan(B, Vg, V, Mm, dev)
         inv_ts, inv_tt = 1.0 / student_temp, 1.0 / teacher_temp
         w1s, w2s = bf16_weight(s_head[0].weight), bf16_weight(s_head[2].weight)
@@ -528,7 +534,7 @@ class _FusedHeadLoss(torch.autograd.Function):
             xt = torch.empty(Mt + Mm, D, dtype=torch.bfloat16, device=dev)
             ops.gather_cast_bf16(teacher_cls.detach(), None, xt[:Mt])
             if Mm:
-                ops.gather_cast_bf16(teacher_patch.detach(), None, xt[Mt:])
+                ops.gather_cast_bf16(tp2, patch_index, xt[Mt:])
             a_t = ops.gemm_bf16(xt, w1t, bias_n=t_head[0].bias.detach())   # layer 1 (zoo/arch.py:253-254)
             ht = ops.gelu_fwd(a_t)
             del a_t
@@ -568,7 +574,7 @@ class _FusedHeadLoss(torch.autograd.Function):
         xs = torch.empty(Ms + Mm, D, dtype=torch.bfloat16, device=dev)
         ops.gather_cast_bf16(student_cls.detach(), None, xs[:Ms])
         if Mm:
-            ops.gather_cast_bf16(student_patch.detach(), None, xs[Ms:])
+            ops.gather_cast_bf16(sp2, patch_index, xs[Ms:])
         a_s = ops.gemm_bf16(xs, w1s, bias_n=s_head[0].bias.detach())
         hs = ops.gelu_fwd(a_s)
         b2s = s_head[2].bias.detach()
@@ -609,6 +615,8 @@ class _FusedHeadLoss(torch.autograd.Function):
             ctx.save_for_backward(xs, a_s, hs_e, gt, db2p, w1s, w2s)
             ctx.plan, ctx.s_head = plan, s_head
             ctx.in_dtypes = (student_cls.dtype, None if student_patch is None else student_patch.dtype)
+            ctx.patch_index = patch_index
+            ctx.patch_shape = None if student_patch is None else tuple(student_patch.shape)
         ctx.mark_non_differentiable(losses)
         total = losses.sum() if Mm else losses[0].clone()
         return total, losses
@@ -640,8 +648,15 @@ class _FusedHeadLoss(torch.autograd.Function):
         _accumulate_grad(s_head[0].weight, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))
         dx = ops.gemm_bf16(da, w1s, b_mn_major=True)
         d_cls = dx[:plan.Ms].to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
-        d_patch = dx[plan.Ms:].to(ctx.in_dtypes[1]) if (plan.Mm and ctx.needs_input_grad[1]) else None
-        return d_cls, d_patch, None, None, None, None, None, None, None, None
+        d_patch = None
+        if plan.Mm and ctx.needs_input_grad[1]:
+            if ctx.patch_index is None:
+                d_patch = dx[plan.Ms:].to(ctx.in_dtypes[1])
+            else:   # rows went in through an index: their gradients go back to those rows of the token tensor
+                d_tok = torch.zeros(ctx.patch_shape, dtype=torch.float32, device=dx.device)
+                ops.scatter_rows(dx[plan.Ms:], ctx.patch_index, d_tok.view(-1, D))
+                d_patch = d_tok.to(ctx.in_dtypes[1])
+        return d_cls, d_patch, None, None, None, None, None, None, None, None, None
 
 
 def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, student_head: nn.Sequential,
@@ -649,7 +664,7 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
                          *, student_patch: Optional[torch.Tensor] = None, teacher_patch: Optional[torch.Tensor] = None,
                          masks_weight: Optional[torch.Tensor] = None, center_patch: Optional[torch.Tensor] = None,
                          ibot_weight: float = 1.0, patch_center_momentum: Optional[float] = None,
-                         update_center: bool = True) -> Dict[str, torch.Tensor]:
+                         update_center: bool = True, patch_index: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """Projection head + multi-crop DINO CE (+ iBOT masked-patch CE) in one fused path.
 
     Equivalent to `dino_loss(student_head(student_cls), teacher_head(teacher_cls), ...)` of the reference
@@ -657,6 +672,10 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
     Gradients of the student head parameters are accumulated straight into their `.grad` during
     `backward()` (scaled by the upstream gradient, so `loss / accumulation_steps` and GradScaler work);
     gradients w.r.t. `student_cls` / `student_patch` flow through autograd.
+    With `patch_index` (int64, unique flat row numbers) `student_patch` / `teacher_patch` are the backbone's
+    token tensors themselves (contiguous (..., D), e.g. the (B*Vg, T, D) output that `feats[:, 1:]` slices,
+    scripts/phase5_big_run.py:1741-1747): the masked rows are gathered by the staging kernel and their
+    gradients scattered back, so the caller never materialises `tokens[mask]`.
     Returns {"loss": differentiable total, "loss_dino", "loss_ibot"}."""
     for t in (student_cls, teacher_cls):
         if not t.is_cuda:
@@ -665,12 +684,19 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
     if has_ibot:
         if teacher_patch is None or masks_weight is None or center_patch is None:
             raise ValueError("iBOT needs teacher_patch, masks_weight and center_patch")
+        if patch_index is not None:
+            if patch_index.dtype != torch.int64 or patch_index.dim() != 1 or not patch_index.is_cuda:
+                raise ValueError("patch_index: 1-D int64 CUDA tensor of flat token-row numbers expected")
+            if not (student_patch.is_contiguous() and teacher_patch.is_contiguous()):
+                raise ValueError("patch_index needs contiguous token tensors (pass the backbone output, not a slice)")
+            if masks_weight.numel() != patch_index.numel():
+                raise ValueError("masks_weight and patch_index must name the same rows")
     cfg = (student_temp, teacher_temp, dino_loss.n_global, dino_loss.n_local, ibot_weight, dino_loss.teacher_mode,
            dino_loss.sk_iterations, dino_loss.process_group, update_center,
            dino_loss.center_momentum if patch_center_momentum is None else patch_center_momentum)
     total, losses = _FusedHeadLoss.apply(student_cls, student_patch, teacher_cls.detach(),
                                          None if teacher_patch is None else teacher_patch.detach(), masks_weight,
-                                         student_head, teacher_head, dino_loss, center_patch, cfg)
+                                         student_head, teacher_head, dino_loss, center_patch, cfg, patch_index)
     return {"loss": total, "loss_dino": losses[0], "loss_ibot": losses[1]}
 
 

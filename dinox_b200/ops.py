@@ -330,6 +330,16 @@ def gather_f32(src: torch.Tensor, idx: torch.Tensor, fill: float = 0.0) -> torch
     return out
 
 
+def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[idx[r]] = src[r] (fp32 rows; unique idx; idx < 0 skipped).  dst rows not named by idx keep their value."""
+    _chk_cuda(src, dst, idx)
+    assert src.dim() == 2 and dst.dim() == 2 and src.dtype == dst.dtype == torch.float32 and idx.dtype == torch.int64
+    assert src.stride(1) == 1 and dst.stride(1) == 1 and idx.numel() == src.shape[0] and src.shape[1] == dst.shape[1]
+    _ext.call("dinox_scatter_rows_f32", _p(src), src.stride(0), _p(idx), src.shape[0], src.shape[1], _p(dst),
+              dst.stride(0), _stream())
+    return dst
+
+
 def gelu_fwd(a: torch.Tensor) -> torch.Tensor:
     h = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
     _ext.call("dinox_gelu_fwd", _p(a), a.numel(), _p(h), _stream())

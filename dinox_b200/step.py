@@ -155,11 +155,15 @@ class LossHeadStep:
                 side.wait_stream(torch.cuda.current_stream())
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
                 gram = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
+        # iBOT rows: materialised ("student_patch"/"teacher_patch") or named by "patch_index" inside the token tensors
+        by_index = "patch_index" in f
+        sp = f["student_tok"] if by_index else f.get("student_patch")
+        tp = f["teacher_tok"] if by_index else f.get("teacher_patch")
         out = losshead.fused_head_dino_loss(
             f["student_cls"], f["teacher_cls"], self.student_head, self.teacher_head, self.dino_loss,
-            self.student_temp, self.teacher_temp, student_patch=f.get("student_patch"),
-            teacher_patch=f.get("teacher_patch"), masks_weight=f.get("masks_weight"),
-            center_patch=self.center_patch if "student_patch" in f else None, ibot_weight=self.ibot_weight)
+            self.student_temp, self.teacher_temp, student_patch=sp, teacher_patch=tp,
+            masks_weight=f.get("masks_weight"), center_patch=self.center_patch if sp is not None else None,
+            ibot_weight=self.ibot_weight, patch_index=f.get("patch_index"))
         loss = out["loss"]
         if gram is not None:
             if side is not None:

@@ -157,8 +157,10 @@ def masked_positions(shapes: LossHeadShapes, g: torch.Generator) -> torch.Tensor
 
 
 def feature_batch(shapes: LossHeadShapes, g: torch.Generator, with_tokens: bool = True,
-                  with_ibot: bool = True) -> Dict[str, torch.Tensor]:
-    """Backbone outputs for one micro-step, fp32 on CPU (caller moves / casts them)."""
+                  with_ibot: bool = True, patches_from_tokens: bool = False) -> Dict[str, torch.Tensor]:
+    """Backbone outputs for one micro-step, fp32 on CPU (caller moves / casts them).
+    patches_from_tokens: the iBOT rows are not materialised; "patch_index" names them inside the (Mt, T, D)
+    token tensors (flat row = crop * T + 1 + masked position: CLS first, then patches, then registers)."""
     out: Dict[str, torch.Tensor] = {}
     D = shapes.dim
     out["student_cls"] = torch.randn(shapes.student_rows, D, generator=g)
@@ -166,7 +168,13 @@ def feature_batch(shapes: LossHeadShapes, g: torch.Generator, with_tokens: bool 
     if with_tokens:
         out["student_tok"] = torch.randn(shapes.teacher_rows, shapes.tokens, D, generator=g)
         out["teacher_tok"] = torch.randn(shapes.teacher_rows, shapes.tokens, D, generator=g)
-    if with_ibot and shapes.masked_rows > 0:
+    if with_ibot and shapes.masked_rows > 0 and patches_from_tokens:
+        assert with_tokens
+        pos = masked_positions(shapes, g)                                  # (Mt, n_masked)
+        crop = torch.arange(shapes.teacher_rows).unsqueeze(1)
+        out["patch_index"] = (crop * shapes.tokens + 1 + pos).reshape(-1).to(torch.int64)
+        out["masks_weight"] = torch.full((shapes.masked_rows,), 1.0 / shapes.masked_per_crop)
+    elif with_ibot and shapes.masked_rows > 0:
         out["student_patch"] = torch.randn(shapes.masked_rows, D, generator=g)
         out["teacher_patch"] = torch.randn(shapes.masked_rows, D, generator=g)
         out["masks_weight"] = torch.full((shapes.masked_rows,), 1.0 / shapes.masked_per_crop)

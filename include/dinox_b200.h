@@ -228,6 +228,10 @@ DINOX_API int dinox_gather_cast_bf16(const void* src, int src_dtype, int64_t ld_
                                      dinox_stream_t stream);
 DINOX_API int dinox_gather_f32(const float* src, const int64_t* idx, int64_t n, float fill, float* out,
                                dinox_stream_t stream);
+/* dst[idx[r], :] = src[r, :] for r < rows (fp32, D % 4 == 0, unique idx, idx < 0 skipped): the backward of
+ * gathering iBOT rows straight out of the backbone's token tensor (`feats[:, 1:][mask]`) */
+DINOX_API int dinox_scatter_rows_f32(const float* src, int64_t ld_src, const int64_t* idx, int64_t rows, int64_t D,
+                                     float* dst, int64_t ld_dst, dinox_stream_t stream);
 /* h = bf16(gelu_erf(a)), n elements */
 DINOX_API int dinox_gelu_fwd(const float* a, int64_t n, void* h_bf16, dinox_stream_t stream);
 /* da = bf16(dh * (*scale_dev) * gelu'(a)); colsum_partial (ceil(rows/64), D) partial column sums */

@@ -209,6 +209,45 @@ def test_strided_backbone_views_are_consumed_in_place(dx):
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
 
 
+def test_ibot_rows_gathered_from_token_tensors_by_index(dx):
+    """with `patch_index` the iBOT rows are read straight out of the backbone's (crops, T, D)
+    token tensors by the staging kernel and their gradients are scattered back - same losses and head
+    gradients (bit-exact) as materialising `tokens[mask]` first, and the token gradient is the scatter of
+    the row gradient (summed with the Gram gradient by autograd)."""
+    from dinox_b200 import synth
+    from dinox_b200.step import LossHeadStep
+    sh = synth.LossHeadShapes(batch=4, dim=128, out_dim=2048, n_patches=36)
+    f_idx = {k: v.to(DEV) for k, v in synth.feature_batch(sh, synth.seeded_generator(9, 0), patches_from_tokens=True).items()}
+    idx = f_idx["patch_index"]
+    assert idx.unique().numel() == idx.numel() == sh.masked_rows
+    f_rows = {k: v for k, v in f_idx.items() if k != "patch_index"}
+    res = []
+    for by_index in (True, False):
+        step = LossHeadStep(sh, DEV, accum=1, with_backbone_params=False)
+        tok = f_idx["student_tok"].clone().requires_grad_(True)
+        cls = f_idx["student_cls"].clone().requires_grad_(True)
+        f = dict(f_idx if by_index else f_rows, student_tok=tok, student_cls=cls)
+        if not by_index:
+            D = sh.dim
+            f["student_patch"] = tok.reshape(-1, D)[idx]                 # torch gather + its autograd scatter
+            f["teacher_patch"] = f_idx["teacher_tok"].reshape(-1, D)[idx]
+        out, loss = step._losses(f)
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((out["loss_dino"].item(), out["loss_ibot"].item(), out["loss_gram"].item(), tok.grad.clone(),
+                    cls.grad.clone(), step.student_head[2].weight.grad.clone(), step.center_patch.clone()))
+    a, b = res
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    assert torch.equal(a[4], b[4]) and torch.equal(a[5], b[5]) and torch.equal(a[6], b[6])
+    torch.testing.assert_close(a[3], b[3], rtol=0, atol=0)
+    # rows outside the mask (and every CLS row) carry the Gram gradient only
+    with pytest.raises(ValueError):
+        dx.fused_head_dino_loss(f_idx["student_cls"], f_idx["teacher_cls"], step.student_head, step.teacher_head,
+                                step.dino_loss, 0.1, 0.04, student_patch=f_idx["student_tok"][:, 1:],
+                                teacher_patch=f_idx["teacher_tok"][:, 1:], masks_weight=f_idx["masks_weight"],
+                                center_patch=step.center_patch, patch_index=idx)
+
+
 def test_fused_adamw_matches_torch_adamw(dx):
     """one-launch AdamW + gradient norm against torch.optim.AdamW (the reference's optimizer,
     scripts/phase5_big_run.py:1621) over several steps on the reference's parameter-size mix: parameters

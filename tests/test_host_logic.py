@@ -154,3 +154,19 @@ def test_checkpoint_wire_format_matches_reference_modules():
     ref.load_state_dict(ours.state_dict(), strict=True)
     dl_r.load_state_dict(dl_o.state_dict(), strict=True)
     assert all(torch.equal(a, b) for a, b in zip(ours.state_dict().values(), ref.state_dict().values()))
+
+
+def test_patch_index_names_masked_patch_rows_of_the_token_tensor():
+    """synth.feature_batch(patches_from_tokens=True): flat row = crop * T + 1 + position, CLS (token 0) and the
+    register tokens (last R) are never masked, indices are unique, masks_weight sums to 1 per crop."""
+    from dinox_b200 import synth
+    sh = synth.LossHeadShapes(batch=3, dim=64, out_dim=256, n_patches=49)
+    f = synth.feature_batch(sh, synth.seeded_generator(5, 0), patches_from_tokens=True)
+    idx = f["patch_index"]
+    assert "student_patch" not in f and idx.dtype == torch.int64 and idx.numel() == sh.masked_rows
+    assert idx.unique().numel() == idx.numel()
+    tok = idx % sh.tokens
+    assert int(tok.min()) >= 1 and int(tok.max()) <= sh.n_patches
+    crops = idx // sh.tokens
+    assert torch.equal(crops.bincount(minlength=sh.teacher_rows), torch.full((sh.teacher_rows,), sh.masked_per_crop))
+    assert abs(float(f["masks_weight"].sum()) - sh.teacher_rows) < 1e-5
