@@ -15,9 +15,9 @@ _LAZY = {
 
 
 def __getattr__(name):
-    if name == "FusedAdamW":
-        from .optim import FusedAdamW
-        return FusedAdamW
+    if name in ("FusedAdamW", "ShardedFusedAdamW"):
+        from . import optim
+        return getattr(optim, name)
     if name in _LAZY:
         from . import losshead
         return getattr(losshead, name)

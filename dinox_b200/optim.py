@@ -100,3 +100,143 @@ class FusedAdamW(torch.optim.AdamW):
                 _ext.lib().dinox_adamw_plan_destroy(h)
         except Exception:
             pass
+
+
+def shard_layout(shapes, world: int, min_numel: int = 1 << 20):
+    """Which parameters of a data-parallel replica set get a sharded optimizer state: those with at least
+    `min_numel` elements whose first dimension divides by `world` (the head's W2: 25-100 M parameters).
+    Returns [(sharded?, rows_per_rank or None)] per shape.  Pure host logic (tested on CPU)."""
+    out = []
+    for shp in shapes:
+        n = 1
+        for s in shp:
+            n *= int(s)
+        ok = world > 1 and len(shp) >= 1 and n >= min_numel and int(shp[0]) % world == 0
+        out.append((ok, int(shp[0]) // world if ok else None))
+    return out
+
+
+class ShardedFusedAdamW:
+    """Data-parallel optimizer step with the big tensors' AdamW state sharded over the ranks (SURVEY 8f next
+    #2, second half; the reference is single-device - scripts/phase5_big_run.py:1781-1796 - so this is the
+    data-parallel form of the same update):
+
+      large parameters (see `shard_layout`):  reduce-scatter(mean) of .grad -> each rank owns rows
+          [r*rows, (r+1)*rows) -> fused AdamW on that slice with ITS slice of exp_avg / exp_avg_sq ->
+          in-place all-gather of the updated rows.  Per GPU: moments and AdamW traffic / world, and the same
+          NVLink bytes as the all-reduce a DDP wrapper would issue (reduce-scatter + all-gather).
+      small parameters: all-reduce(mean) of .grad, replicated fused AdamW.
+
+    One launch per class (sharded / replicated) through `dinox_adamw_step`; `last_grad_norm` is the global
+    ||mean-gradient||_2 as a device scalar (the shard norms are all-reduced, no host sync).  Replicas stay
+    bit-identical: every rank applies the same arithmetic to the same reduced gradients.
+    `consolidated_state_dict()` returns torch.optim.AdamW's layout for checkpoints."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                 process_group=None, shard_min_numel: int = 1 << 20):
+        import torch.distributed as dist
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.pg = None if process_group in (None, True) else process_group
+        self.world = dist.get_world_size(self.pg) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(self.pg) if dist.is_initialized() else 0
+        for p in self.params:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise _ext.DinoxError("ShardedFusedAdamW needs contiguous fp32 CUDA parameters (no CPU fallback)")
+        self.layout = shard_layout([tuple(p.shape) for p in self.params], self.world, shard_min_numel)
+        self.step_count = 0
+        self.state = {}
+        for p, (sharded, rows) in zip(self.params, self.layout):
+            own = p.data[self.rank * rows:(self.rank + 1) * rows] if sharded else p.data
+            self.state[p] = dict(own=own, exp_avg=torch.zeros_like(own), exp_avg_sq=torch.zeros_like(own),
+                                 grad=torch.empty_like(own) if sharded else None)
+        self._plans = {}
+        self.last_grad_norm: Optional[torch.Tensor] = None
+
+    def _plan(self, key, items):
+        """items: [(param slice, grad, exp_avg, exp_avg_sq)]; rebuilt when a gradient tensor moved"""
+        gkey = tuple(g.data_ptr() for _, g, _, _ in items)
+        hit = self._plans.get(key)
+        if hit is not None and hit[0] == gkey:
+            return hit[1]
+        if hit is not None:
+            _ext.lib().dinox_adamw_plan_destroy(hit[1])
+        n = len(items)
+        col = lambda i: (ctypes.c_void_p * n)(*[it[i].data_ptr() for it in items])
+        ne = (ctypes.c_int64 * n)(*[it[0].numel() for it in items])
+        h = ctypes.c_void_p()
+        _ext.call("dinox_adamw_plan_create", col(0), col(1), col(2), col(3), ne, n, ctypes.byref(h))
+        self._plans[key] = (gkey, h)
+        return h
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0):
+        import torch.distributed as dist
+        live = [(p, lay) for p, lay in zip(self.params, self.layout) if p.grad is not None]
+        if not live:
+            return
+        sharded = [p for p, (s, _) in live if s]
+        repl = [p for p, (s, _) in live if not s]
+        works = []
+        if self.world > 1:
+            for p in sharded:   # mean over replicas, each rank receives its rows
+                works.append(dist.reduce_scatter_tensor(self.state[p]["grad"].view(-1), p.grad.view(-1),
+                                                        op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            for p in repl:
+                works.append(dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            for w in works:
+                w.wait()
+        self.step_count += 1
+        t = float(self.step_count)
+        b1, b2 = self.betas
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        sq = torch.zeros(2, dtype=torch.float32, device=self.params[0].device)
+        for slot, (key, ps) in enumerate((("sharded", sharded), ("replicated", repl))):
+            if not ps:
+                continue
+            use_shard_grad = key == "sharded" and self.world > 1
+            items = [(self.state[p]["own"], self.state[p]["grad"] if use_shard_grad else p.grad,
+                      self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) for p in ps]
+            h = self._plan(key, items)
+            _ext.call("dinox_adamw_step", h, float(self.lr), float(b1), float(b2), float(self.eps), float(self.weight_decay),
+                      1.0 - b1 ** t, 1.0 - b2 ** t, float(grad_scale), ctypes.c_void_p(sq[slot:].data_ptr()), stream)
+        sq.square_()
+        if self.world > 1:
+            if sharded:
+                dist.all_reduce(sq[0:1], group=self.pg)       # every rank holds 1/world of the rows
+            for p in sharded:                                 # in place: rank r's rows are already where they belong
+                dist.all_gather_into_tensor(p.data.view(-1), self.state[p]["own"].view(-1), group=self.pg)
+        self.last_grad_norm = sq.sum().sqrt()
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.zero_()
+
+    def consolidated_state_dict(self):
+        """torch.optim.AdamW-shaped state (full-size moments on every rank) for `save_checkpoint` (:1104-1125)."""
+        import torch.distributed as dist
+        state = {}
+        for i, (p, (s, _)) in enumerate(zip(self.params, self.layout)):
+            st = self.state[p]
+            if s and self.world > 1:
+                full = [torch.empty_like(p.data), torch.empty_like(p.data)]
+                for dst, src in zip(full, (st["exp_avg"], st["exp_avg_sq"])):
+                    dist.all_gather_into_tensor(dst.view(-1), src.contiguous().view(-1), group=self.pg)
+            else:
+                full = [st["exp_avg"].clone(), st["exp_avg_sq"].clone()]
+            state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": full[0], "exp_avg_sq": full[1]}
+        group = dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
+                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     decoupled_weight_decay=True, params=list(range(len(self.params))))
+        return {"state": state, "param_groups": [group]}
+
+    def __del__(self):
+        try:
+            for _, h in self._plans.values():
+                _ext.lib().dinox_adamw_plan_destroy(h)
+        except Exception:
+            pass

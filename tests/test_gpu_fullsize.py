@@ -280,6 +280,32 @@ def test_fused_adamw_matches_torch_adamw(dx):
     o_ref2.load_state_dict(sd_o)            # a checkpoint written with the fused optimizer loads into torch's
 
 
+def test_sharded_adamw_single_rank_equals_torch(dx):
+    """ShardedFusedAdamW without a process group (world 1: nothing sharded) is torch.optim.AdamW on the same
+    gradients; the sharded path itself runs under torchrun (tools/dist_sharded_adamw.py, profiles/)."""
+    from dinox_b200.optim import ShardedFusedAdamW
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(128, 128), (128,), (4096, 128), (4096,)]
+    init = [torch.randn(s, generator=gen) * 0.1 for s in shapes]
+    a = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    b = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    hp = dict(lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    oa, ob = ShardedFusedAdamW(a, **hp), torch.optim.AdamW(b, **hp)
+    for _ in range(4):
+        for p, q in zip(a, b):
+            g = torch.randn(p.shape, generator=gen).to(DEV) * 0.03
+            p.grad, q.grad = g.clone(), g.clone()
+        oa.step(); ob.step()
+        gn = torch.sqrt(sum((q.grad.double() ** 2).sum() for q in b))
+        assert abs(float(oa.last_grad_norm) - float(gn)) / float(gn) < 1e-5
+    for p, q in zip(a, b):
+        torch.testing.assert_close(p.data, q.data, rtol=2e-6, atol=1e-7)
+    sd, tsd = oa.consolidated_state_dict(), ob.state_dict()
+    for i in range(len(shapes)):
+        torch.testing.assert_close(sd["state"][i]["exp_avg_sq"], tsd["state"][i]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+    assert set(sd["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "params"}
+
+
 def test_extreme_logits_and_non_finite_inputs(dx):
     """Numerical guards of the fused path: (1) logits far outside exp() range (|z|/tau ~ 1e4) still give the
     oracle's loss and finite gradients (everything is evaluated relative to the row LSE, in log2 units);

@@ -170,3 +170,14 @@ def test_patch_index_names_masked_patch_rows_of_the_token_tensor():
     crops = idx // sh.tokens
     assert torch.equal(crops.bincount(minlength=sh.teacher_rows), torch.full((sh.teacher_rows,), sh.masked_per_crop))
     assert abs(float(f["masks_weight"].sum()) - sh.teacher_rows) < 1e-5
+
+
+def test_shard_layout_of_the_sharded_optimizer():
+    """SURVEY 8f #2 (second half): only tensors >= 1 Mi elements whose rows divide by the world size get a
+    sharded AdamW state (the head's W2); everything else stays replicated; world 1 shards nothing."""
+    from dinox_b200.optim import shard_layout
+    head = [(384, 384), (384,), (65536, 384), (65536,)]
+    assert shard_layout(head, 8) == [(False, None), (False, None), (True, 8192), (False, None)]
+    assert shard_layout(head, 1) == [(False, None)] * 4
+    assert shard_layout([(65537, 384)], 8) == [(False, None)]
+    assert shard_layout([(1024, 1024)], 4, min_numel=1 << 20) == [(True, 256)]
