@@ -472,7 +472,8 @@ _SIDE_STREAMS: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
 
 def concurrency() -> int:
     """DINOX_CONCURRENCY: 0 = one stream; 1 = Gram anchoring on a side stream (LossHeadStep);
-    2 (default) = also the teacher branch of the fused head loss."""
+    2 (default) = also the teacher branch of the fused head loss; 3 = also dW2/db2 beside the dH chain in the
+    backward and the centre GEMV inside the teacher branch."""
     return int(os.environ.get("DINOX_CONCURRENCY", "2"))
 
 
@@ -495,6 +496,21 @@ def _accumulate_grad(p: torch.Tensor, fn) -> None:
         fn(p.grad, False)
     else:
         fn(p.grad, True)
+
+
+def _update_centres(hsum, hsum_work, pg, Mt, Mm, w2t, b2t, loss_mod, center_patch, patch_momentum) -> None:
+    """Centre EMA of the fused path: mean teacher logits = W2t . mean(h_t) + b2t (one GEMV over W2t for the CLS
+    and the patch centre together) from the all-reduced activation sums."""
+    if hsum is None:
+        return
+    w = _world(pg)
+    if hsum_work is not None:
+        hsum_work.wait()
+    alphas = [1.0 / (Mt * w)] + ([1.0 / (Mm * w)] if Mm else [])
+    mean_logits = ops.gemv_bf16_multi(w2t, hsum, alphas, b2t, 1.0)
+    ops.center_ema_(loss_mod.center, mean_logits[0], 1, loss_mod.center_momentum)
+    if Mm:
+        ops.center_ema_(center_patch, mean_logits[1], 1, patch_momentum)
 
 
 class _FusedHeadLoss(torch.autograd.Function):
@@ -570,6 +586,12 @@ class _FusedHeadLoss(torch.autograd.Function):
             ht_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
             ops.gather_cast_bf16(ht, plan.ent_t, ht_e)
             rb2_e = ops.gather_f32(rb2_t, plan.ent_t)
+            if side is not None and concurrency() >= 3:
+                # centre updates here instead of after pass 2: ct2 / ct2_patch above already hold the OLD centres
+                # (scripts/phase5_big_run.py:719 - the loss sees the centre of the previous step), and the GEMV over
+                # W2t runs beside the student branch instead of after pass 2
+                _update_centres(hsum, hsum_work, pg, Mt, Mm, w2t, b2t, loss_mod, center_patch, patch_momentum)
+                hsum = None
         # ---- student: the same on the current stream
         xs = torch.empty(Ms + Mm, D, dtype=torch.bfloat16, device=dev)
         ops.gather_cast_bf16(student_cls.detach(), None, xs[:Ms])
@@ -602,15 +624,7 @@ class _FusedHeadLoss(torch.autograd.Function):
             gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
                                      lse2_e, rb2_e, cw, losses, want_db2=need_grad)
         # ---- centre updates AFTER the loss (scripts/phase5_big_run.py:719)
-        if hsum is not None:
-            w = _world(pg)
-            if hsum_work is not None:
-                hsum_work.wait()
-            alphas = [1.0 / (Mt * w)] + ([1.0 / (Mm * w)] if Mm else [])
-            mean_logits = ops.gemv_bf16_multi(w2t, hsum, alphas, b2t, 1.0)    # one pass over W2t for both centres
-            ops.center_ema_(loss_mod.center, mean_logits[0], 1, loss_mod.center_momentum)
-            if Mm:
-                ops.center_ema_(center_patch, mean_logits[1], 1, patch_momentum)
+        _update_centres(hsum, hsum_work, pg, Mt, Mm, w2t, b2t, loss_mod, center_patch, patch_momentum)
         if need_grad:
             ctx.save_for_backward(xs, a_s, hs_e, gt, db2p, w1s, w2s)
             ctx.plan, ctx.s_head = plan, s_head
@@ -628,13 +642,21 @@ class _FusedHeadLoss(torch.autograd.Function):
         up = g.to(torch.float32).reshape(1).contiguous()
         K, D = w2s.shape
         rows = plan.Ms + plan.Mm
-        # dW2 (K, D) += g * Gt . HsE   (A = Gt K-major over entries, B = HsE MN-major)
-        with ops.TIMER.region("gemm_dW2"):
-            _accumulate_grad(s_head[2].weight, lambda out, acc: ops.gemm_bf16(
-                gt, hs_e, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
-        db2 = ops.cols_sum(db2p)
-        _accumulate_grad(s_head[2].bias, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out,
-                                                                   alpha_dev=up))
+        # The layer-2 parameter gradients (dW2, db2) and the dH -> layer-1 chain only share their input G: at
+        # level 3 the former run on a side stream, so the CTAs of dH start on the SMs the last, partial wave of
+        # dW2 leaves idle (256 tile pairs on 74 CTA pairs = 3.46 waves).
+        main = torch.cuda.current_stream()
+        side = _side_stream(gt.device, 2) if (concurrency() >= 3 and not ops.TIMER.enabled) else None
+        if side is not None:
+            side.wait_stream(main)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            # dW2 (K, D) += g * Gt . HsE   (A = Gt K-major over entries, B = HsE MN-major)
+            with ops.TIMER.region("gemm_dW2"):
+                _accumulate_grad(s_head[2].weight, lambda out, acc: ops.gemm_bf16(
+                    gt, hs_e, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
+            db2 = ops.cols_sum(db2p)
+            _accumulate_grad(s_head[2].bias, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out,
+                                                                       alpha_dev=up))
         # dH per entry = G . W2  (A = Gt MN-major, B = W2 MN-major), then sum the entries of each row
         with ops.TIMER.region("gemm_dH"):
             dh_e = ops.gemm_bf16_splitk(gt, w2s, a_mn_major=True, b_mn_major=True, m_fastest=True)
@@ -647,6 +669,8 @@ class _FusedHeadLoss(torch.autograd.Function):
         dw1_parts = ops.gemm_bf16_splitk(da, xs, a_mn_major=True, b_mn_major=True)
         _accumulate_grad(s_head[0].weight, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))
         dx = ops.gemm_bf16(da, w1s, b_mn_major=True)
+        if side is not None:
+            main.wait_stream(side)
         d_cls = dx[:plan.Ms].to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
         d_patch = None
         if plan.Mm and ctx.needs_input_grad[1]:
