@@ -187,7 +187,7 @@ struct SharedCtl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t tmem_empty_local[2];   // pair mode, non-leader CTA: its own epilogue warps report here
-  uint64_t a_full, a_empty;       // resident operand: "tile landed" / "last MMA reading it retired"
+  uint64_t res_full, res_empty;       // resident operand: "tile landed" / "last MMA reading it retired"
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -233,7 +233,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 
   // 1024-B aligned carve-up (swizzle-128B atoms need it): [pipeline stages][epilogue staging][control]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* res_a = smem;                       // resident operand: A k-blocks (kResA) or [sub][k-block] B slabs (kResB)
+  uint8_t* res_buf = smem;                       // resident operand: A k-blocks (kResA) or [sub][k-block] B slabs (kResB)
   uint8_t* pipe = smem + L::kResBytes;
   uint8_t* epi_smem = pipe + L::kPipeBytes;
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(pipe + L::kPipeBytes + L::kEpiBytes);
@@ -271,8 +271,8 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
 #endif
       sm100::mbar_init(&ctl->tmem_empty_local[i], Epi::kEpiWarps);
     }
-    sm100::mbar_init(&ctl->a_full, 1);
-    sm100::mbar_init(&ctl->a_empty, 1);
+    sm100::mbar_init(&ctl->res_full, 1);
+    sm100::mbar_init(&ctl->res_empty, 1);
     sm100::fence_barrier_init();
   }
   if (warp == 1) {
@@ -304,51 +304,51 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     // thread - not the tensor pipe - the limiter of the 64-cycle N=128 MMAs.
     {
       PipeState st;
-      int res_m = -1, res_batch = -1;     // M tile whose A rows are resident (RESA)
+      int res_tile = -1, res_batch = -1;     // M tile (kResA) / N tile (kResB) whose rows are resident
       uint32_t res_phase = 0;
       for (; walk.valid(); walk.next()) {
         const TileCoord tc = walk.coord(p, CL, crank);
         const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
         const int kb0 = tc.split * p.kb_per_split;
         const int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
-        if (RESA && (tc.m_tile != res_m || tc.batch != res_batch)) {
+        if (RESA && (tc.m_tile != res_tile || tc.batch != res_batch)) {
           // (re)load the resident A rows of sub-GEMM 0: every k-block, once per M tile.  The previous
-          // resident tile must have been read by its last MMA (a_empty, committed by the MMA issuer).
-          sm100::mbar_wait(&ctl->a_empty, res_phase ^ 1, 8);
+          // resident tile must have been read by its last MMA (res_empty, committed by the MMA issuer).
+          sm100::mbar_wait(&ctl->res_empty, res_phase ^ 1, 8);
           if (sm100::elect_one()) {
-            const uint32_t af = kPair ? sm100::mapa_u32(sm100::smem_u32(&ctl->a_full), 0) : 0;
-            if (leader) sm100::mbar_expect_tx(&ctl->a_full, CL * p.num_k_blocks * L::kABytes);
+            const uint32_t af = kPair ? sm100::mapa_u32(sm100::smem_u32(&ctl->res_full), 0) : 0;
+            if (leader) sm100::mbar_expect_tx(&ctl->res_full, CL * p.num_k_blocks * L::kABytes);
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-              uint8_t* dst = res_a + kb * L::kABytes;
+              uint8_t* dst = res_buf + kb * L::kABytes;
               if (kPair) {
                 if (p.batches > 1) sm100::tma_load_3d_pair(dst, tmA0, af, kb * BK, m0, tc.batch);
                 else sm100::tma_load_2d_pair(dst, tmA0, af, kb * BK, m0);
               } else {
-                if (p.batches > 1) sm100::tma_load_3d(dst, tmA0, &ctl->a_full, kb * BK, m0, tc.batch);
-                else sm100::tma_load_2d(dst, tmA0, &ctl->a_full, kb * BK, m0);
+                if (p.batches > 1) sm100::tma_load_3d(dst, tmA0, &ctl->res_full, kb * BK, m0, tc.batch);
+                else sm100::tma_load_2d(dst, tmA0, &ctl->res_full, kb * BK, m0);
               }
             }
           }
           __syncwarp();
-          res_m = tc.m_tile; res_batch = tc.batch; res_phase ^= 1;
+          res_tile = tc.m_tile; res_batch = tc.batch; res_phase ^= 1;
         }
-        if (RESB && tc.n_tile != res_m) {
+        if (RESB && tc.n_tile != res_tile) {
           // (re)load the resident B rows (this CTA's share of the N tile) of every sub-GEMM, all k-blocks
-          sm100::mbar_wait(&ctl->a_empty, res_phase ^ 1, 8);
+          sm100::mbar_wait(&ctl->res_empty, res_phase ^ 1, 8);
           if (sm100::elect_one()) {
-            const uint32_t af = kPair ? sm100::mapa_u32(sm100::smem_u32(&ctl->a_full), 0) : 0;
-            if (leader) sm100::mbar_expect_tx(&ctl->a_full, CL * NSUB * p.num_k_blocks * L::kBBytes);
+            const uint32_t af = kPair ? sm100::mapa_u32(sm100::smem_u32(&ctl->res_full), 0) : 0;
+            if (leader) sm100::mbar_expect_tx(&ctl->res_full, CL * NSUB * p.num_k_blocks * L::kBBytes);
             for (int sub = 0; sub < NSUB; ++sub) {
               const CUtensorMap* mb = sub ? tmB1 : tmB0;
               for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                uint8_t* dst = res_a + (sub * kResKBlocks + kb) * L::kBBytes;
+                uint8_t* dst = res_buf + (sub * kResKBlocks + kb) * L::kBBytes;
                 if (kPair) sm100::tma_load_2d_pair(dst, mb, af, kb * BK, n0 + crank * BNL);
-                else sm100::tma_load_2d(dst, mb, &ctl->a_full, kb * BK, n0 + crank * BNL);
+                else sm100::tma_load_2d(dst, mb, &ctl->res_full, kb * BK, n0 + crank * BNL);
               }
             }
           }
           __syncwarp();
-          res_m = tc.n_tile; res_phase ^= 1;
+          res_tile = tc.n_tile; res_phase ^= 1;
         }
         for (int sub = 0; sub < NSUB; ++sub) {
           const CUtensorMap* ma = sub ? tmA1 : tmA0;
@@ -438,7 +438,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
       PipeState st;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      int res_m = -1, res_batch = -1;
+      int res_tile = -1, res_batch = -1;
       uint32_t res_phase = 0;
       for (; walk.valid(); walk.next()) {
         const TileCoord tc = walk.coord(p, CL, crank);
@@ -446,9 +446,9 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
         const int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
         bool res_last = false;    // is this the last tile that reads the current resident A?
         if (RESA) {
-          if (tc.m_tile != res_m || tc.batch != res_batch) {
-            sm100::mbar_wait(&ctl->a_full, res_phase, 9);
-            res_m = tc.m_tile; res_batch = tc.batch; res_phase ^= 1;
+          if (tc.m_tile != res_tile || tc.batch != res_batch) {
+            sm100::mbar_wait(&ctl->res_full, res_phase, 9);
+            res_tile = tc.m_tile; res_batch = tc.batch; res_phase ^= 1;
           }
           TileWalker nxt = walk;
           nxt.next();
@@ -456,9 +456,9 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
           res_last = !nxt.valid() || tn.m_tile != tc.m_tile || tn.batch != tc.batch;
         }
         if (RESB) {
-          if (tc.n_tile != res_m) {
-            sm100::mbar_wait(&ctl->a_full, res_phase, 9);
-            res_m = tc.n_tile; res_phase ^= 1;
+          if (tc.n_tile != res_tile) {
+            sm100::mbar_wait(&ctl->res_full, res_phase, 9);
+            res_tile = tc.n_tile; res_phase ^= 1;
           }
           TileWalker nxt = walk;
           nxt.next();
@@ -472,8 +472,8 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             sm100::mbar_wait(&ctl->full[st.stage], st.phase, 3);
             sm100::tc_fence_after();
             const uint32_t stage_base = sm100::smem_u32(pipe + st.stage * L::kStageBytes);
-            const uint32_t sa = (RESA && sub == 0) ? sm100::smem_u32(res_a + kb * L::kABytes) : stage_base;
-            const uint32_t sb = RESB ? sm100::smem_u32(res_a + (sub * kResKBlocks + kb) * L::kBBytes)
+            const uint32_t sa = (RESA && sub == 0) ? sm100::smem_u32(res_buf + kb * L::kABytes) : stage_base;
+            const uint32_t sb = RESB ? sm100::smem_u32(res_buf + (sub * kResKBlocks + kb) * L::kBBytes)
                                      : stage_base + (L::kStageHasA ? L::kABytes : 0);
             if (sm100::elect_one()) {
 #if DINOX_EXP_NO_MMA   // experiment: operands stream through smem but nothing reads them
@@ -506,8 +506,8 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
             else sm100::umma_commit(&ctl->empty[st.stage]);
             // ... and the resident A tile after the last MMA of the last tile that reads it
             if (((RESA && sub == 0) || (RESB && sub == NSUB - 1)) && res_last && kb == kb1 - 1) {
-              if (kPair) sm100::umma_commit_pair(&ctl->a_empty);
-              else sm100::umma_commit(&ctl->a_empty);
+              if (kPair) sm100::umma_commit_pair(&ctl->res_empty);
+              else sm100::umma_commit(&ctl->res_empty);
             }
 #endif
             }   // elected lane
