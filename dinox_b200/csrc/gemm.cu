@@ -737,6 +737,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
   gemm_body<BN, NSPLIT, NSUB, CL, EpiAdapter<BN, Epi>, RES>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, &tmC, smem_raw);
 }
 
+static int env_flag_early(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 // number of CTAs for `tiles` super tiles of a CL-cluster kernel: one CTA per SM, whole clusters
 static inline int launch_grid(int64_t super_tiles, int cl) {
   int64_t clusters = num_sms() / cl;
@@ -829,11 +834,17 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   cfg.blockDim = dim3((2 + Epi::kEpiWarps) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static const int pdl = env_flag_early("DINOX_PDL", 0);
+  if (pdl) {   // let the CTAs start their set-up while the previous kernel of the stream drains
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tA0, tB0, tA1, tB1, tC, p, ep);
   if (e != cudaSuccess) {
     set_error("%s: cudaLaunchKernelEx failed: %s", name, cudaGetErrorString(e));

@@ -284,6 +284,9 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
   if (kPair) sm100::cluster_sync();   // the peer's barriers / TMEM are set up before anyone signals them
   sm100::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  // barriers, TMEM and descriptor prefetch are set up: only now wait for the producer kernels of our inputs
+  // (the launch may have been programmatic, DINOX_PDL)
+  sm100::grid_dependency_wait();
 
   TileWalker walk;
   if (RESA) {   // contiguous chunk per cluster: consecutive tiles share the M tile whose A rows stay resident

@@ -66,6 +66,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start (and run its set-up) before the previous kernel in the stream has finished; it must not touch
+// anything that kernel wrote until this returns.  No-op for a normal launch.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
