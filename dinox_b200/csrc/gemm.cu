@@ -270,7 +270,11 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   return r;
 }
 
-struct EpiStats {
+// kRun: the kernel walks contiguous runs of N tiles per M tile (resident-A schedule), so every thread keeps the
+// running (max, sum) of its row across the tiles of a run and writes ONE partial per (row, cluster that touched
+// the row's M tile) instead of one per (row, 128 prototypes): 33 MB -> 0.5 MB of partials at C2.
+template <bool kRun>
+struct EpiStatsT {
   static constexpr bool kUsesTmaStore = false;
   static constexpr int kEpiWarps = DINOX_EPI_WARPS;
   static constexpr int kGroups = kEpiWarps / 4;          // column groups (each TMEM lane quarter has kGroups warps)
@@ -280,12 +284,26 @@ struct EpiStats {
   struct Params {
     float scale2;
     const float* col2;   // (N) log2-unit column offsets, may be NULL
-    float2* partial;     // (M, kGroups*num_n_tiles)
+    float2* partial;     // (M, kGroups*num_n_tiles); kRun: (M, kGroups*run_slots)
+    int cl, per, run_slots;   // kRun: cluster size, super tiles per cluster, partial slots per row
   };
   struct State {
     float col[kColsW / 32];   // raw prefetched column offsets of the NEXT tile (this lane's columns of the warp's group)
+    float run_m = -INFINITY, run_s = 0.f;   // kRun: statistics of this thread's row over the current run
+    int run_mtile = -1;
   };
-  static __device__ __forceinline__ void finish(const Params&, const CoreParams&, int, int, State&) {}
+  // slot of this cluster among the clusters whose contiguous chunk [c*per, (c+1)*per) meets the row's M tile
+  static __device__ __forceinline__ void flush(const Params& e, const CoreParams& p, int epi_warp, int lane, State& st) {
+    if (st.run_mtile < 0) return;
+    const int row = st.run_mtile * BM + epi_quarter() * 32 + lane;
+    const int c_lo = (int)(((int64_t)(st.run_mtile / e.cl) * p.num_n_tiles) / e.per);
+    const int slot = ((int)blockIdx.x / e.cl - c_lo) * kGroups + (epi_warp >> 2);
+    if (row < p.M) e.partial[(int64_t)row * (kGroups * e.run_slots) + slot] = make_float2(st.run_m, st.run_s);
+    st.run_m = -INFINITY; st.run_s = 0.f;
+  }
+  static __device__ __forceinline__ void finish(const Params& e, const CoreParams& p, int epi_warp, int lane, State& st) {
+    if (kRun) flush(e, p, epi_warp, lane, st);
+  }
   template <int BN>
   struct Impl {
     static_assert(BN == 256, "EpiStats is written for 256-wide tiles");
@@ -308,13 +326,17 @@ struct EpiStats {
       __syncwarp();
     }
     static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap*,
-                                                uint32_t tmem_acc, int acc_stage, int epi_warp, int lane, uint8_t* smem, State&) {
+                                                uint32_t tmem_acc, int acc_stage, int epi_warp, int lane, uint8_t* smem, State& st) {
       const float* buf = reinterpret_cast<const float*>(smem) + epi_warp * kCols;
       const int q = epi_quarter();
       const int grp = epi_warp >> 2;
       const int row = tc.m_tile * BM + q * 32 + lane;
       const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + grp * kCols;
-      float m = -INFINITY, s = 0.f;
+      if (kRun && tc.m_tile != st.run_mtile) {   // a new run: hand the finished one over
+        flush(e, p, epi_warp, lane, st);
+        st.run_mtile = tc.m_tile;
+      }
+      float m = kRun ? st.run_m : -INFINITY, s = kRun ? st.run_s : 0.f;
 #pragma unroll 1
       for (int c = 0; c < kCols / 64; ++c) {
         float v[2][32];
@@ -353,10 +375,13 @@ struct EpiStats {
           m = mn;
         }
       }
-      if (row < p.M) e.partial[(int64_t)row * (kGroups * p.num_n_tiles) + tc.n_tile * kGroups + grp] = make_float2(m, s);
+      if (kRun) { st.run_m = m; st.run_s = s; }
+      else if (row < p.M) e.partial[(int64_t)row * (kGroups * p.num_n_tiles) + tc.n_tile * kGroups + grp] = make_float2(m, s);
     }
   };
 };
+using EpiStats = EpiStatsT<false>;
+using EpiStatsRun = EpiStatsT<true>;
 
 __global__ void stats_merge_kernel(const float2* __restrict__ partial, int64_t rows, int n_part,
                                    float* __restrict__ lse_nat, float* __restrict__ lse2) {
@@ -369,6 +394,26 @@ __global__ void stats_merge_kernel(const float2* __restrict__ partial, int64_t r
     float2 v = partial[row * n_part + i];
     a = maxsum_merge(a, MaxSum{v.x, v.y});
   }
+  a = warp_maxsum(a);
+  if (lane == 0) {
+    const float l2 = a.m + log2f(a.s);
+    if (lse2) lse2[row] = l2;
+    if (lse_nat) lse_nat[row] = l2 * DINOX_LN2;
+  }
+}
+
+// run-mode partials: row r of M super tile mt has one slot per (cluster meeting mt, column group)
+__global__ void stats_merge_run_kernel(const float2* __restrict__ partial, int64_t rows, int groups, int run_slots,
+                                       int num_n, int per, int cl, float* __restrict__ lse_nat, float* __restrict__ lse2) {
+  // one warp per row (a single M tile spread over every CTA has > 100 slots)
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int64_t mt = row / (BM * cl);
+  const int c_lo = (int)((mt * num_n) / per), c_hi = (int)(((mt + 1) * num_n - 1) / per);
+  MaxSum a{-INFINITY, 0.f};
+  const float2* pr = partial + row * (int64_t)(groups * run_slots);
+  for (int i = lane; i < (c_hi - c_lo + 1) * groups; i += 32) a = maxsum_merge(a, MaxSum{pr[i].x, pr[i].y});
   a = warp_maxsum(a);
   if (lane == 0) {
     const float l2 = a.m + log2f(a.s);
@@ -1012,7 +1057,7 @@ int dinox_debug_max_active_clusters(int cluster_size) {
 size_t dinox_head_stats_workspace_bytes(int64_t rows, int64_t K) {
   if (rows <= 0 || K <= 0) return 0;
   const int64_t n_tiles = (K + 255) / 256;
-  return (size_t)rows * EpiStats::kGroups * n_tiles * sizeof(float2);
+  return (size_t)rows * EpiStats::kGroups * (n_tiles + 1) * sizeof(float2);   // + 1: run-mode slot bound
 }
 
 int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D, int64_t ldh, int64_t ldw,
@@ -1022,14 +1067,27 @@ int dinox_head_stats(const void* H, const void* W2, int64_t rows, int64_t K, int
   int rc = require_sm100();
   if (rc) return rc;
   Operand a{H, rows, ldh, 0}, b{W2, K, ldw, 0};
-  EpiStats::Params ep{inv_tau * DINOX_LOG2E, col2, reinterpret_cast<float2*>(workspace)};
+  EpiStats::Params ep{inv_tau * DINOX_LOG2E, col2, reinterpret_cast<float2*>(workspace), 1, 1, 1};
   const bool cl2 = rows > BM && pair_enabled(kPairStats);
-  if (resa_enabled(kPairStats, D))   // prototype tiles fastest: the H rows of one M tile stay in shared memory
-    rc = cl2 ? launch<256, 1, 1, 2, EpiStats, kResA>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/0, ep, OutDesc{}, stream, "head_stats<pair,resA>")
-             : launch<256, 1, 1, 1, EpiStats, kResA>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/0, ep, OutDesc{}, stream, "head_stats<resA>");
-  else
-    rc = cl2 ? launch<256, 1, 1, 2, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats<pair>")
-             : launch<256, 1, 1, 1, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats");
+  if (resa_enabled(kPairStats, D)) {
+    // prototype tiles fastest in contiguous runs: the H rows of one M tile stay in shared memory and the row
+    // statistics stay in registers over a run (one partial per row and cluster)
+    const int cl = cl2 ? 2 : 1;
+    const int64_t num_n = (K + 255) / 256, num_m_super = ((rows + BM - 1) / BM + cl - 1) / cl, super = num_m_super * num_n;
+    const int ncl = launch_grid(super, cl) / cl;
+    const int per = (int)((super + ncl - 1) / ncl);
+    const int run_slots = (int)((num_n + per - 1) / per) + 1;
+    // run_slots <= num_n + 1: inside the workspace dinox_head_stats_workspace_bytes() asks for
+    EpiStatsRun::Params er{ep.scale2, ep.col2, ep.partial, cl, per, run_slots};
+    rc = cl2 ? launch<256, 1, 1, 2, EpiStatsRun, kResA>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/0, er, OutDesc{}, stream, "head_stats<pair,resA>")
+             : launch<256, 1, 1, 1, EpiStatsRun, kResA>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/0, er, OutDesc{}, stream, "head_stats<resA>");
+    if (rc) return rc;
+    stats_merge_run_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(er.partial, rows, EpiStats::kGroups, run_slots, (int)num_n,
+                                                                               per, cl, lse_nat, lse2);
+    return check_launch("stats_merge_run_kernel", stream);
+  }
+  rc = cl2 ? launch<256, 1, 1, 2, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats<pair>")
+           : launch<256, 1, 1, 1, EpiStats>(a, b, nullptr, nullptr, rows, K, D, /*m_fastest=*/1, ep, OutDesc{}, stream, "head_stats");
   if (rc) return rc;
   const int n_part = EpiStats::kGroups * (int)((K + 255) / 256);
   stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows, n_part,

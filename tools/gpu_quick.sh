@@ -1,11 +1,18 @@
 #!/bin/bash
+# GPU suite + two default-length bench runs (no CPU leg)
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider -x 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
-python bench.py --steps 40 --warmup 4 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -2 gpurun_out/bench_quick.err
+timeout 900 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider -x 2>&1 | tail -4
+for i in 1 2; do
+  timeout 400 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/quick.json 2> gpurun_out/quick.err
+  python - <<'PY'
+import json
+d=json.load(open('gpurun_out/quick.json'))
+print('value',round(d['value']),'ms',round(d['ms_per_step'],4),'e2e',round(d['e2e']['value']),{k:round(v,3) for k,v in d['roofline']['kernels_ms'].items()},'launches',d['gpu_launches'])
+PY
+done
+DINOX_RESA=0 timeout 400 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/quick0.json 2> gpurun_out/quick0.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/bench_quick.json'))
-print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'clk',d['clocks'])
-print({k:round(v,4) for k,v in d['roofline']['kernels_ms'].items()})
-print('launches',d['gpu_launches'],'frac',d['roofline']['frac'],'step_frac',d['roofline']['step_frac'])
+d=json.load(open('gpurun_out/quick0.json'))
+print('RESA=0 value',round(d['value']),'ms',round(d['ms_per_step'],4))
 PY
