@@ -54,7 +54,7 @@ def test_version_and_error_string(built_lib):
     assert built_lib.dinox_version() >= 100
     assert isinstance(built_lib.dinox_last_error_string(), bytes)
     assert built_lib.dinox_ce_workspace_bytes(8, 1024) > 0
-    assert built_lib.dinox_head_stats_workspace_bytes(640, 65536) == 640 * 2 * 256 * 8
+    assert built_lib.dinox_head_stats_workspace_bytes(640, 65536) == 640 * 2 * (256 + 1) * 8   # (row, group, tile) partials + 1 run slot
 
 
 def test_no_hidden_cpu_path_in_package():
