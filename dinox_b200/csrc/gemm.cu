@@ -434,6 +434,9 @@ __global__ void stats_merge_run_kernel(const float2* __restrict__ partial, int64
 // staged in shared memory once per tile.  Issue budget per element: 2 FFMA + 2 FADD + 2 MUFU
 // (logits -> probs), FMUL + 2 FFMA + FADD (gradient, loss, bias grad), 1/2 F2FP, 3/4 LDS.128.
 // =============================================================================================
+#ifndef DINOX_G_EVICT_FIRST
+#define DINOX_G_EVICT_FIRST 0
+#endif
 struct EpiGradT {
   static constexpr bool kUsesTmaStore = true;
   static constexpr int kEpiWarps = DINOX_EPI_WARPS;
@@ -638,7 +641,11 @@ struct EpiGradT {
       __syncwarp();
       const int ent0 = tc.n_tile * BN + grp * kCols;
       if (lane == 0) {
+#if DINOX_G_EVICT_FIRST
+        if (k0 < p.M && ent0 < p.N) sm100::tma_store_3d_hint(tmC, wbuf, ent0, k0, 0, sm100::l2_policy_evict_first());
+#else
         if (k0 < p.M && ent0 < p.N) sm100::tma_store_3d(tmC, wbuf, ent0, k0, 0);
+#endif
         sm100::tma_store_commit();   // always: wait_read<kBufs-1> counts groups
       }
       if (kBufs > 1) st.flip ^= 1;
