@@ -248,6 +248,42 @@ def test_ibot_rows_gathered_from_token_tensors_by_index(dx):
                                 center_patch=step.center_patch, patch_index=idx)
 
 
+@pytest.mark.parametrize("dtype,mode", [(torch.bfloat16, "center"), (torch.float32, "sinkhorn")])
+def test_ibot_rows_by_index_low_precision_and_sinkhorn(dx, dtype, mode):
+    """`patch_index` with bf16 token tensors (autocast backbones) and with the Sinkhorn-Knopp CLS teacher: same
+    losses as materialised rows, token gradient in the tokens' dtype, zero outside the masked rows."""
+    from dinox_b200 import synth
+    gen = torch.Generator().manual_seed(21)
+    sh = synth.LossHeadShapes(batch=4, dim=128, out_dim=2048, n_patches=36)
+    f = {k: v.to(DEV) for k, v in synth.feature_batch(sh, synth.seeded_generator(11, 0), patches_from_tokens=True).items()}
+    idx, D, K = f["patch_index"], sh.dim, sh.out_dim
+    sd_s, sd_t = synth.head_weights(D, K, gen), synth.head_weights(D, K, gen)
+    res = []
+    for by_index in (True, False):
+        s_head, t_head = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+        s_head.load_state_dict(sd_s); t_head.load_state_dict(sd_t)
+        dl = dx.DINOLoss(K, 0.9, n_global=sh.n_global, n_local=sh.n_local, teacher_mode=mode).to(DEV)
+        cp = torch.zeros(1, K, device=DEV)
+        tok = f["student_tok"].to(dtype).clone().requires_grad_(True)   # a fresh leaf per variant
+        ttok = f["teacher_tok"].to(dtype)
+        kw = dict(masks_weight=f["masks_weight"], center_patch=cp)
+        if by_index:
+            out = dx.fused_head_dino_loss(f["student_cls"], f["teacher_cls"], s_head, t_head, dl, 0.1, 0.04,
+                                          student_patch=tok, teacher_patch=ttok, patch_index=idx, **kw)
+        else:
+            out = dx.fused_head_dino_loss(f["student_cls"], f["teacher_cls"], s_head, t_head, dl, 0.1, 0.04,
+                                          student_patch=tok.reshape(-1, D)[idx], teacher_patch=ttok.reshape(-1, D)[idx], **kw)
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        res.append((out["loss_dino"].item(), out["loss_ibot"].item(), tok.grad.clone(), s_head[2].weight.grad.clone()))
+    a, b = res
+    assert a[0] == b[0] and a[1] == b[1] and torch.equal(a[3], b[3])
+    assert a[2].dtype == dtype and torch.equal(a[2], b[2])
+    mask = torch.zeros(sh.teacher_rows * sh.tokens, dtype=torch.bool, device=DEV)
+    mask[idx] = True
+    assert float(a[2].reshape(-1, D)[~mask].abs().max()) == 0.0 and float(a[2].reshape(-1, D)[mask].abs().max()) > 0.0
+
+
 def test_fused_adamw_matches_torch_adamw(dx):
     """one-launch AdamW + gradient norm against torch.optim.AdamW (the reference's optimizer,
     scripts/phase5_big_run.py:1621) over several steps on the reference's parameter-size mix: parameters
