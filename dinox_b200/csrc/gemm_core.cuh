@@ -98,7 +98,7 @@ struct TileWalker {
   int nfast, nslow;
   int remaining;
   bool m_fastest;
-  __device__ __forceinline__ void init(const CoreParams& p, int num_m_super, int first, int stride, int total) {
+  __host__ __device__ __forceinline__ void init(const CoreParams& p, int num_m_super, int first, int stride, int total) {
     m_fastest = p.m_fastest != 0;
     nfast = m_fastest ? num_m_super : p.num_n_tiles;
     nslow = m_fastest ? p.num_n_tiles : num_m_super;
@@ -107,7 +107,7 @@ struct TileWalker {
     remaining = first < total ? (total - first + stride - 1) / stride : 0;
   }
   // contiguous range [first, first + count) with unit stride (consecutive tiles share the slow digit)
-  __device__ __forceinline__ void init_range(const CoreParams& p, int num_m_super, int first, int count) {
+  __host__ __device__ __forceinline__ void init_range(const CoreParams& p, int num_m_super, int first, int count) {
     m_fastest = p.m_fastest != 0;
     nfast = m_fastest ? num_m_super : p.num_n_tiles;
     nslow = m_fastest ? p.num_n_tiles : num_m_super;
@@ -122,7 +122,7 @@ struct TileWalker {
   bool columns = false;
   int cm, cn, m_lo, m_hi, n_step, rem_a;          // current position / phase A (whole rounds) bookkeeping
   int b_cm, b_cn, b_lo, b_hi, b_step;             // phase B (left-over columns) start state
-  __device__ __forceinline__ void init_columns(const CoreParams& p, int num_m, int cid, int ncl) {
+  __host__ __device__ __forceinline__ void init_columns(const CoreParams& p, int num_m, int cid, int ncl) {
     columns = true;
     const int num_n = p.num_n_tiles;
     const int full = num_n / ncl, rem = num_n - full * ncl, n_base = full * ncl;
@@ -136,7 +136,7 @@ struct TileWalker {
         b_cn = n_base + cid; b_cm = 0; b_lo = 0; b_hi = num_m; b_step = 0; count_b = num_m - tail;
       } else if (tail > 0) {
         const int total = rem * tail, per = (total + spares - 1) / spares, j0 = (cid - rem) * per;
-        count_b = min(per, total - j0);
+        count_b = per < total - j0 ? per : total - j0;
         if (count_b < 0) count_b = 0;
         b_cn = n_base + j0 / tail; b_lo = num_m - tail; b_cm = b_lo + j0 % tail; b_hi = num_m; b_step = 1;
       }
@@ -145,8 +145,8 @@ struct TileWalker {
     if (rem_a > 0) { cn = cid; cm = 0; m_lo = 0; m_hi = num_m; n_step = ncl; }
     else { cn = b_cn; cm = b_cm; m_lo = b_lo; m_hi = b_hi; n_step = b_step; }
   }
-  __device__ __forceinline__ bool valid() const { return remaining > 0; }
-  __device__ __forceinline__ void next() {
+  __host__ __device__ __forceinline__ bool valid() const { return remaining > 0; }
+  __host__ __device__ __forceinline__ void next() {
     --remaining;
     if (columns) {
       if (rem_a > 0 && --rem_a == 0) { cn = b_cn; cm = b_cm; m_lo = b_lo; m_hi = b_hi; n_step = b_step; return; }
@@ -162,7 +162,7 @@ struct TileWalker {
     outer += douter + carry;
   }
   // CL-wide super tile -> this CTA's tile
-  __device__ __forceinline__ TileCoord coord(const CoreParams& p, int cl, int crank) const {
+  __host__ __device__ __forceinline__ TileCoord coord(const CoreParams& p, int cl, int crank) const {
     TileCoord c;
     if (columns) { c.m_tile = cm * cl + crank; c.n_tile = cn; c.batch = 0; c.split = 0; return c; }
     c.m_tile = (m_fastest ? fast : slow) * cl + crank;
