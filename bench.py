@@ -157,18 +157,33 @@ def cpu_oracle_step_time(cfg_name: str, sample_batch: int, steps: int, warmup: i
     return sh.student_rows / per_step, cores, desc, per_step
 
 
+def workload_text(args, sh, n_params: float) -> str:
+    """The workload both arms run (BASELINE.json configs), in the same words."""
+    return (f"{args.config}: ViT-{'S' if sh.dim == 384 else 'L'}/16 loss head (teacher {args.teacher_mode}), per-GPU batch {sh.batch} x accum {args.accum}, "
+            f"{sh.n_global} global + {sh.n_local} local crops, K={sh.out_dim}, D={sh.dim}, iBOT r={sh.mask_ratio} "
+            f"({sh.masked_rows} masked rows, {'gathered from the token tensors by index' if args.patch_source == 'tokens' else 'materialised by the caller'}), "
+            f"Gram anchoring on ({sh.tokens - 1} tokens), EMA of {n_params / 1e6:.1f} M params every {args.accum} micro-steps")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from dinox_b200 import synth
     value, cores, desc, per_step = cpu_oracle_step_time(args.config, args.cpu_sample_batch, args.steps, args.warmup,
                                                          args.accum, args.patch_source == "tokens")
+    sh = synth.LossHeadShapes(**synth.CONFIGS[args.config])
+    depth = synth.BACKBONES.get(sh.dim, dict(depth=12))["depth"]
+    n_params = 0
+    for shp in synth.student_param_shapes(sh.dim, depth, sh.out_dim):
+        n_params += math.prod(shp)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: ViT-S/16 loss head, 2 global + 8 local crops, K=65536, iBOT r=0.3, "
-                               f"Gram on, accum {args.accum}; CPU sample batch {args.cpu_sample_batch}"},
+        "config": {"workload": workload_text(args, sh, n_params),
+                   "sample": f"each step runs a {args.cpu_sample_batch}-image slice of the per-GPU batch on {cores} host threads; "
+                             f"crops/s = slice crops / slice time"},
         "cpu_baseline": {"value": value, "unit": "crops/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -398,10 +413,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": f"{args.config}: ViT-{'S' if D == 384 else 'L'}/16 loss head (teacher {args.teacher_mode}), per-GPU batch {sh.batch} x accum {args.accum}, "
-                        f"{sh.n_global} global + {sh.n_local} local crops, K={K}, D={D}, iBOT r={sh.mask_ratio} "
-                        f"({sh.masked_rows} masked rows, {'gathered from the token tensors by index' if args.patch_source == 'tokens' else 'materialised by the caller'}), Gram anchoring on ({sh.tokens - 1} tokens), "
-                        f"EMA of {step.n_params / 1e6:.1f} M params every {args.accum} micro-steps",
+            "workload": workload_text(args, sh, step.n_params),
             "rows": {"student": sh.student_rows, "teacher": sh.teacher_rows, "masked": sh.masked_rows},
             "parallelism": f"dp{world}", "launch": "cuda-graph replay per micro-step" if use_graph else "eager launches",
             "eager_ms_per_step": eager_ms_per_step, "l2": "per-step working set (bf16 W2 x2 = 100 MB, dL/dlogits 1.1 GB) exceeds the 126 MB L2; no explicit flush",
