@@ -7,8 +7,7 @@ through ATen - if the library is missing or the device is not a B200 the call ra
 from __future__ import annotations
 
 import ctypes
-import math
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 

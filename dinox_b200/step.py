@@ -7,11 +7,9 @@
 from __future__ import annotations
 
 import contextlib
-import math
 from typing import Dict, List, Optional
 
 import torch
-import torch.nn as nn
 
 from . import losshead, ops, synth
 
