@@ -148,6 +148,14 @@ SIGNATURES = {
     "dinox_head_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                 c_f32, c_f32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_i64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dinox_head_teacher_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_head_teacher": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p, c_i64,
+                                   c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dinox_head_grad2_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_head_grad2_db2_rows": (c_i64, [c_i64]),
+    "dinox_head_grad2": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p,
+                                 c_void_p, c_int, c_void_p, c_void_p]),
     "dinox_gemm_bf16_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                         c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_f32, c_void_p, c_void_p]),
     "dinox_normalize_tokens": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -168,6 +176,8 @@ SIGNATURES = {
     "dinox_gather_sum_rows": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_f32,
                                       c_void_p, c_i64, c_int, c_void_p]),
     "dinox_fill_f32": (c_int, [c_void_p, c_i64, c_f32, c_void_p]),
+    "dinox_scalar_combine": (c_int, [c_void_p, c_void_p, c_int, c_f32, c_void_p, c_void_p, c_void_p]),
+    "dinox_scalar_fanout": (c_int, [c_void_p, c_void_p, c_int, c_f32, c_void_p, c_void_p]),
     "dinox_adamw_plan_create": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dinox_adamw_plan_destroy": (c_int, [c_void_p]),
     "dinox_adamw_step": (c_int, [c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,

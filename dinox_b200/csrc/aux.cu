@@ -304,6 +304,22 @@ __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
 
 }  // namespace dinox
 
+struct ScalarTerms {
+  const float* p[8];
+  float w[8];
+};
+__global__ void scalar_combine_kernel(ScalarTerms t, int n, float scale, float* __restrict__ out, float* __restrict__ out_unscaled) {
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < n; ++i) a += t.w[i] * *t.p[i];   // fixed order
+    out[0] = a * scale;
+    if (out_unscaled) out_unscaled[0] = a;
+  }
+}
+__global__ void scalar_fanout_kernel(const float* __restrict__ up, ScalarTerms t, int n, float scale, float* __restrict__ out) {
+  if ((int)threadIdx.x < n) out[threadIdx.x] = *up * scale * t.w[threadIdx.x];
+}
+
 extern "C" {
 using namespace dinox;
 
@@ -440,6 +456,26 @@ int dinox_normalize_tokens_bwd(const void* feats, int dtype, int64_t batch, int6
     normalize_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)feats, stride_b, stride_t, tokens, skip, (int)D, n_rows, dxn, inv_norm, scale_dev, scale, grad, gstride_b, gstride_t);
   else { set_error("normalize_tokens_bwd: dtype must be f32 or bf16"); return DINOX_E_BADARG; }
   return check_launch("normalize_bwd_kernel", stream);
+}
+
+/* step glue (scripts/phase5_big_run.py:1749-1772): loss = scale * sum_i w_i * term_i and, for the backward,
+ * the per-term upstream gradients g * scale * w_i - two launches instead of a dozen scalar framework ops */
+int dinox_scalar_combine(const float* const* terms, const float* weights, int n, float scale, float* out,
+                         float* out_unscaled, dinox_stream_t stream) {
+  DINOX_REQUIRE(terms && weights && out && n >= 1 && n <= 8, DINOX_E_BADARG, "scalar_combine: 1..8 terms");
+  ScalarTerms t;
+  for (int i = 0; i < 8; ++i) { t.p[i] = i < n ? terms[i] : nullptr; t.w[i] = i < n ? weights[i] : 0.f; }
+  for (int i = 0; i < n; ++i) DINOX_REQUIRE(t.p[i], DINOX_E_BADARG, "scalar_combine: null term");
+  scalar_combine_kernel<<<1, 32, 0, stream>>>(t, n, scale, out, out_unscaled);
+  return check_launch("scalar_combine_kernel", stream);
+}
+
+int dinox_scalar_fanout(const float* upstream, const float* weights, int n, float scale, float* out, dinox_stream_t stream) {
+  DINOX_REQUIRE(upstream && weights && out && n >= 1 && n <= 8, DINOX_E_BADARG, "scalar_fanout: 1..8 terms");
+  ScalarTerms t;
+  for (int i = 0; i < 8; ++i) { t.p[i] = nullptr; t.w[i] = i < n ? weights[i] : 0.f; }
+  scalar_fanout_kernel<<<1, 32, 0, stream>>>(upstream, t, n, scale, out);
+  return check_launch("scalar_fanout_kernel", stream);
 }
 
 int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream) {

@@ -423,6 +423,415 @@ __global__ void stats_merge_run_kernel(const float2* __restrict__ partial, int64
 }
 
 // =============================================================================================
+// Epilogue 2b (teacher, ONE pass over the prototypes): the row statistics of EpiStatsT PLUS the teacher
+// probabilities themselves, un-normalised, so that pass 2 never recomputes a teacher logit.
+// Each epilogue warp owns 32 rows x one 128-prototype GRANULE of the 256-wide tile:
+//   x[row,k]     = acc*scale2 + col2[k]                     (log2 units; col2 = (b2 - centre)/tau * log2e)
+//   gmax         = max over the granule of x                (sweep 1 over TMEM)
+//   qt[row,k]    = fp16( 2^(x - gmax) )  in (0, 1]          (sweep 2; swizzled staging + TMA store)
+//   ref[g][row]  = gmax                                      g = 2*n_tile + column group
+//   (m, s)      += online (max, sum 2^x) of the row          (fp32, from the unrounded exponentials)
+// Later  q[row,k] = qt[row,k] * 2^(ref[g][row] - rowbias2[row])  with rowbias2 = the row's log2 LSE (centre
+// teacher) or its Sinkhorn row offset.  Every value that matters for the row (within 14 binades of the row
+// maximum) is a NORMAL fp16 number relative to its own granule maximum (gmax <= row max), i.e. carries a
+// 2^-12 relative rounding; smaller ones fall into fp16 denormals with an absolute error below 2^-25 of a
+// probability.  (Storing the teacher LOGITS in 16 bits instead would cost 2^-9 * |x| ~ 10 % on q at
+// 1/tau_t = 25 - the reason pass 2 used to recompute them.)
+// scripts/phase5_big_run.py:703 (teacher softmax) with the statistics of :686-690 / the SK row sums.
+// =============================================================================================
+__device__ __forceinline__ uint32_t f16x2_bits(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <bool kRun>
+struct EpiTeachQT {
+  static constexpr bool kUsesTmaStore = true;
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kGroups = 2;                      // column groups per TMEM lane quarter
+  static constexpr int kColsW = 128;                     // one granule per warp and tile
+  // one staging buffer per warp (32 rows x 128 B) leaves five 16 KB operand stages beside the resident A rows;
+  // the wait for the previous store's read sits behind the math of the next 32 columns
+  static constexpr int kBufs = 1;
+  static constexpr int kStageBytes = kEpiWarps * kBufs * 4096;
+  static constexpr int kEpiSmemBytes = kStageBytes + kEpiWarps * kColsW * 4;
+  struct Params {
+    float scale2;
+    const float* col2;        // (N) log2-unit column offsets, may be NULL
+    const float* col2_alt;    // (N) offsets of the rows of M tiles >= alt_from_mtile (iBOT patch centre), may be NULL
+    int alt_from_mtile;
+    float2* partial;          // (M, kGroups*num_n_tiles); kRun: (M, kGroups*run_slots)
+    int cl, per, run_slots;
+    float* refs;              // (kGroups*num_n_tiles, ld_refs) granule maxima, log2 units
+    int64_t ld_refs;
+  };
+  struct State {
+    float col[kColsW / 32];
+    float run_m = -INFINITY, run_s = 0.f;
+    int run_mtile = -1;
+    int flip = 0;
+  };
+  static __device__ __forceinline__ void flush(const Params& e, const CoreParams& p, int epi_warp, int lane, State& st) {
+    if (st.run_mtile < 0) return;
+    const int row = st.run_mtile * BM + epi_quarter() * 32 + lane;
+    const int c_lo = (int)(((int64_t)(st.run_mtile / e.cl) * p.num_n_tiles) / e.per);
+    const int slot = ((int)blockIdx.x / e.cl - c_lo) * kGroups + (epi_warp >> 2);
+    if (row < p.M) e.partial[(int64_t)row * (kGroups * e.run_slots) + slot] = make_float2(st.run_m, st.run_s);
+    st.run_m = -INFINITY; st.run_s = 0.f;
+  }
+  static __device__ __forceinline__ void finish(const Params& e, const CoreParams& p, int epi_warp, int lane, State& st) {
+    if (kRun) flush(e, p, epi_warp, lane, st);
+    if (lane == 0) sm100::tma_store_wait_all<0>();
+  }
+  template <int BN>
+  struct Impl {
+    static_assert(BN == 256, "EpiTeachQ is written for 256-wide tiles");
+    static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
+                                                 State& st) {
+      const int col0 = tc.n_tile * BN + (epi_warp >> 2) * kColsW;
+      const float* c2 = (e.col2_alt && tc.m_tile >= e.alt_from_mtile) ? e.col2_alt : e.col2;
+#pragma unroll
+      for (int j = 0; j < kColsW / 32; ++j) {
+        const int col = col0 + j * 32 + lane;
+        st.col[j] = (col < p.N) ? (c2 ? __ldg(c2 + col) : 0.f) : -INFINITY;
+      }
+    }
+    static __device__ __forceinline__ void prologue(const Params&, const CoreParams&, TileCoord, int, int epi_warp, int lane,
+                                                    uint8_t* smem, State& st) {
+      float* buf = reinterpret_cast<float*>(smem + kStageBytes) + epi_warp * kColsW;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kColsW / 32; ++j) buf[j * 32 + lane] = st.col[j];
+      __syncwarp();
+    }
+    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap* tmC,
+                                                uint32_t tmem_acc, int, int epi_warp, int lane, uint8_t* smem, State& st) {
+      const float* buf = reinterpret_cast<const float*>(smem + kStageBytes) + epi_warp * kColsW;
+      const int q = epi_quarter();
+      const int grp = epi_warp >> 2;
+      const int row0 = tc.m_tile * BM + q * 32;
+      const int row = row0 + lane;
+      const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + grp * kColsW;
+      if (kRun && tc.m_tile != st.run_mtile) {
+        flush(e, p, epi_warp, lane, st);
+        st.run_mtile = tc.m_tile;
+      }
+      const uint64_t sc2 = pack2(e.scale2, e.scale2);
+      // ---- sweep 1: granule maximum of this thread's row
+      float gm = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kColsW / 64; ++c) {
+        float v[2][32];
+        sm100::tmem_ld32x2(taddr + c * 64, taddr + c * 64 + 32, v[0], v[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float* cb = buf + c * 64 + h * 32;
+          float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = lds128(cb + j);
+            float x0, x1, x2, x3;
+            unpack2(fma2(pack2(v[h][j], v[h][j + 1]), sc2, pack2(b4.x, b4.y)), x0, x1);
+            unpack2(fma2(pack2(v[h][j + 2], v[h][j + 3]), sc2, pack2(b4.z, b4.w)), x2, x3);
+            cm0 = fmaxf(cm0, fmaxf(x0, x1));
+            cm1 = fmaxf(cm1, fmaxf(x2, x3));
+          }
+          gm = fmaxf(gm, fmaxf(cm0, cm1));
+        }
+      }
+      const float gsafe = (gm == -INFINITY) ? 0.f : gm;   // a granule entirely beyond N: every exponential is 2^-inf = 0
+      const uint64_t ng2 = pack2(-gsafe, -gsafe);
+      // ---- sweep 2: exponentials -> row sum (fp32) and fp16 staging -> TMA store
+      uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
+      uint8_t* wbase = smem + epi_warp * (kBufs * 4096);
+      uint32_t ra[32], rb[32];
+      sm100::tmem_ld32_nowait(taddr, ra);
+      sm100::tmem_wait_ld();
+      WarpStage stg;
+      uint8_t* wbuf = wbase;
+#pragma unroll
+      for (int c = 0; c < kColsW / 32; ++c) {
+        uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+        uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+        if (c + 1 < kColsW / 32) sm100::tmem_ld32_nowait(taddr + (c + 1) * 32, nxt);
+        sm100::pin32(cur);
+        const float* cb = buf + c * 32;
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = lds128(cb + j);
+          float x0, x1, x2, x3;
+          unpack2(add2(fma2(pack2u(cur[j], cur[j + 1]), sc2, pack2(b4.x, b4.y)), ng2), x0, x1);
+          unpack2(add2(fma2(pack2u(cur[j + 2], cur[j + 3]), sc2, pack2(b4.z, b4.w)), ng2), x2, x3);
+          const float e0 = fast_ex2(x0), e1 = fast_ex2(x1), e2 = fast_ex2(x2), e3 = fast_ex2(x3);
+          acc0 = add2(acc0, pack2(e0, e1));
+          acc1 = add2(acc1, pack2(e2, e3));
+          packed[j / 2] = f16x2_bits(e0, e1);
+          packed[j / 2 + 1] = f16x2_bits(e2, e3);
+        }
+        if ((c & 1) == 0) {   // the staging buffer about to be refilled must no longer be read by the previous store
+          wbuf = wbase + st.flip * 4096;
+          if (lane == 0) sm100::tma_store_wait_read<kBufs - 1>();
+          __syncwarp();
+          stg.init(wbuf, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          stg.put((c & 1) * 4 + j, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        if (c & 1) {
+          sm100::fence_proxy_async_smem();
+          __syncwarp();
+          const int col0 = tc.n_tile * BN + grp * kColsW + (c >> 1) * 64;
+          if (lane == 0) {
+            // the map's column extent is the PADDED row length, so columns in [N, ld) receive the zeros computed
+            // for them (col2 = -inf) and pass 2 may read whole 256-byte row segments
+            if (row0 < p.M) sm100::tma_store_3d(tmC, wbuf, col0, row0, 0);
+            sm100::tma_store_commit();   // always: wait_read<kBufs-1> counts groups
+          }
+          if (kBufs > 1) st.flip ^= 1;
+        }
+        if (c + 1 < kColsW / 32) sm100::tmem_wait_ld();
+      }
+      float a0, a1, a2, a3;
+      unpack2(acc0, a0, a1); unpack2(acc1, a2, a3);
+      const float s_tile = (a0 + a1) + (a2 + a3);
+      float m = kRun ? st.run_m : -INFINITY, s = kRun ? st.run_s : 0.f;
+      const float mn = fmaxf(m, gm);
+      const float msafe = (mn == -INFINITY) ? 0.f : mn;
+      s = s * fast_ex2(m - msafe) + s_tile * fast_ex2(gsafe - msafe);
+      m = mn;
+      if (kRun) { st.run_m = m; st.run_s = s; }
+      else if (row < p.M) e.partial[(int64_t)row * (kGroups * p.num_n_tiles) + tc.n_tile * kGroups + grp] = make_float2(m, s);
+      if (row < p.M) e.refs[(int64_t)(tc.n_tile * kGroups + grp) * e.ld_refs + row] = gm;
+    }
+  };
+};
+
+// =============================================================================================
+// Epilogue 3b (pass 2, student logits only): TMEM lanes = entries e, columns = prototypes k.
+//   u      = S*as2 + cs2[k] - lse2[e]                 log2 of the student softmax prob, p = 2^u
+//   q'     = qt[trow[e],k] * cwt*2^(ref - rb2[e])     cwt = cw[e]/tau_s; the teacher prob from EpiTeachQ (fp16, HBM)
+//   G[e,k] = cwt*p - q'                               -> bf16, (E, ldg) entry-major
+//   loss  -= q' * u * ln2 * tau_s                     (-cw q ln p)
+//   db2[k] partial = sum of the bf16 G over the 32 entries of the warp (column sums of the staged tile)
+// One sub-GEMM, so the tile is 256 wide with double-buffered accumulators like pass 1 and the A rows of an M
+// tile can stay resident; the teacher probabilities arrive as 256-byte row segments straight from global
+// memory into registers (one 32-byte load per 16 prototypes, 4 chunks in flight per thread).
+// scripts/phase5_big_run.py:706-717 and its autograd (grad of log_softmax) in one kernel.
+// =============================================================================================
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// "minus infinity" that stays finite under 0 * x
+#define DINOX_NEG_HUGE (-1.0e30f)
+struct EpiGradR {
+  static constexpr bool kUsesTmaStore = true;
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kGroups = 2;
+  static constexpr int kColsW = 128;
+#ifndef DINOX_GRADR_STAGING_BUFS
+#define DINOX_GRADR_STAGING_BUFS 1
+#endif
+  static constexpr int kBufs = DINOX_GRADR_STAGING_BUFS;
+  static constexpr int kStageBytes = kEpiWarps * kBufs * 4096;
+  static constexpr int kEpiSmemBytes = kStageBytes + kEpiWarps * kColsW * 4;
+  struct Params {
+    float as2, inv_tau_s;
+    const float* cs2;        // (N) student column offsets, log2 units
+    const float* lse2;       // (M) student log2 LSE per entry
+    const float* cw;         // (M) entry weight, 0 for padding
+    const float* rb2;        // (M) teacher row offset (log2) per entry
+    const int* trow;         // (M) row of qt / refs holding the entry's teacher
+    const __half* qt;        // (teacher rows, ldq) un-normalised teacher probabilities
+    int64_t ldq;
+    const float* refs;       // (2*num_n_tiles, ld_refs)
+    int64_t ld_refs;
+    int alt_from;            // entries >= alt_from go to loss[1]
+    float* db2_partial;      // (ceil(M/32), N) or NULL
+    float* loss_partial;     // (gridDim.x * kEpiWarps * 2)
+  };
+  struct State {
+    float loss_a = 0.f, loss_b = 0.f;
+    float col[kColsW / 32];
+    // raw per-row values of the NEXT tile (no arithmetic until prologue)
+    float n_lse = 0.f, n_cw = 0.f, n_rb = 0.f;
+    int n_trow = 0, n_mtile = -1;
+    // the tile being processed
+    float nl = 0.f, cwt = 0.f, rb = 0.f, ref = 0.f;
+    const __half* qrow = nullptr;
+    int cur_mtile = -1, cur_trow = 0;
+    bool in_b = false;
+    uint32_t qb[4][8];       // teacher probabilities: 4 x 16 prototypes in flight
+    int flip = 0;
+  };
+  static __device__ __forceinline__ void finish(const Params& e, const CoreParams&, int epi_warp, int lane, State& st) {
+    const float a = warp_sum(st.loss_a), b = warp_sum(st.loss_b);
+    const float sc = -DINOX_LN2 / e.inv_tau_s;   // the tiles accumulate (cw/tau_s) * q * u
+    if (lane == 0) {
+      e.loss_partial[((int64_t)blockIdx.x * kEpiWarps + epi_warp) * 2 + 0] = a * sc;
+      e.loss_partial[((int64_t)blockIdx.x * kEpiWarps + epi_warp) * 2 + 1] = b * sc;
+      sm100::tma_store_wait_all<0>();
+    }
+  }
+  template <int BN>
+  struct Impl {
+    static_assert(BN == 256, "EpiGradR is written for 256-wide tiles");
+    static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
+                                                 State& st) {
+      const int grp = epi_warp >> 2;
+      const int col0 = tc.n_tile * BN + grp * kColsW;
+#pragma unroll
+      for (int j = 0; j < kColsW / 32; ++j) {
+        const int col = col0 + j * 32 + lane;
+        st.col[j] = (col < p.N) ? __ldg(e.cs2 + col) : DINOX_NEG_HUGE;
+      }
+      if (tc.m_tile != st.n_mtile) {   // a new row for this thread (once per run in the resident-A schedule)
+        const int row = tc.m_tile * BM + epi_quarter() * 32 + lane;
+        const bool ok = row < p.M;
+        st.n_lse = ok ? __ldg(e.lse2 + row) : 0.f;
+        st.n_cw = ok ? __ldg(e.cw + row) : 0.f;
+        st.n_rb = ok ? __ldg(e.rb2 + row) : 0.f;
+        st.n_trow = ok ? __ldg(e.trow + row) : 0;
+        st.n_mtile = tc.m_tile;
+      } else if (col0 < p.N) {
+        // same row, next granule: pull its 256 bytes of teacher probabilities towards L2 a whole tile ahead
+        const __half* nq = e.qt + (int64_t)st.n_trow * e.ldq + col0;
+        prefetch_l2(nq);
+        prefetch_l2(nq + 64);
+      }
+    }
+    static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int, int epi_warp, int lane,
+                                                    uint8_t* smem, State& st) {
+      float* buf = reinterpret_cast<float*>(smem + kStageBytes) + epi_warp * kColsW;
+      const int grp = epi_warp >> 2;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kColsW / 32; ++j) buf[j * 32 + lane] = st.col[j];
+      if (tc.m_tile != st.cur_mtile) {
+        const int row = tc.m_tile * BM + epi_quarter() * 32 + lane;
+        const bool live = st.n_cw != 0.f;
+        st.cwt = st.n_cw * e.inv_tau_s;
+        st.nl = live ? -st.n_lse : DINOX_NEG_HUGE;     // padding entries: p = 2^-huge = 0, and 0 * u stays finite
+        st.rb = st.n_rb;
+        st.cur_trow = st.n_trow;
+        st.in_b = row >= e.alt_from;
+        st.cur_mtile = tc.m_tile;
+      }
+      const int col0 = tc.n_tile * BN + grp * kColsW;
+      st.qrow = e.qt + (int64_t)st.cur_trow * e.ldq + col0;
+      st.ref = __ldg(e.refs + (int64_t)(tc.n_tile * kGroups + grp) * e.ld_refs + st.cur_trow);
+      // the first four 16-prototype chunks of teacher probabilities fly during the wait for the accumulators
+      // (col0 + 128 <= ldq: rows are padded to whole tiles)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ldg256(st.qrow + c * 16, st.qb[c]);
+      __syncwarp();
+    }
+
+    static __device__ __forceinline__ void tile(const Params& e, const CoreParams& p, TileCoord tc, const CUtensorMap* tmC,
+                                                uint32_t tmem_acc, int, int epi_warp, int lane, uint8_t* smem, State& st) {
+      const float* buf = reinterpret_cast<const float*>(smem + kStageBytes) + epi_warp * kColsW;
+      const int q = epi_quarter();
+      const int grp = epi_warp >> 2;
+      const int row0 = tc.m_tile * BM + q * 32;
+      const uint32_t ts = tmem_acc + ((uint32_t)(q * 32) << 16) + grp * kColsW;
+      // q' = qt * nsc with nsc = -(cw/tau_s) * 2^(ref - rb); dead entries (cw = 0) must not see 0 * inf
+      const float nsc = (st.cwt != 0.f) ? -(st.cwt * fast_ex2(st.ref - st.rb)) : 0.f;
+      const uint64_t as2 = pack2(e.as2, e.as2), nl2 = pack2(st.nl, st.nl), cw2 = pack2(st.cwt, st.cwt), nsc2 = pack2(nsc, nsc);
+      uint64_t lacc = pack2(0.f, 0.f);
+      uint8_t* wbase = smem + epi_warp * (kBufs * 4096);
+      uint8_t* wbuf = wbase;
+      WarpStage stg;
+      uint32_t sa[16], sb[16];
+      sm100::tmem_ld16_nowait(ts, sa);
+      sm100::tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < kColsW / 16; ++c) {
+        uint32_t (&cur)[16] = (c & 1) ? sb : sa;
+        uint32_t (&nxt)[16] = (c & 1) ? sa : sb;
+        if (c + 1 < kColsW / 16) sm100::tmem_ld16_nowait(ts + (c + 1) * 16, nxt);
+        sm100::pin16(cur);
+        uint32_t (&qv)[8] = st.qb[c & 3];
+        const float* cb = buf + c * 16;
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = lds128(cb + j);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t s2 = pack2u(cur[j + 2 * h], cur[j + 2 * h + 1]);
+            const uint64_t c2 = h ? pack2(b4.z, b4.w) : pack2(b4.x, b4.y);
+            const uint64_t u2 = add2(fma2(s2, as2, c2), nl2);
+            float ux, uy;
+            unpack2(u2, ux, uy);
+            const uint64_t pp = pack2(fast_ex2(ux), fast_ex2(uy));
+            const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qv[j / 2 + h]));
+            const uint64_t nq = mul2(pack2(qf.x, qf.y), nsc2);
+            const uint64_t g2 = fma2(cw2, pp, nq);
+            lacc = fma2(nq, u2, lacc);
+            float gx, gy;
+            unpack2(g2, gx, gy);
+            __nv_bfloat162 hh = __floats2bfloat162_rn(gx, gy);
+            packed[j / 2 + h] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+        }
+        if (c + 4 < kColsW / 16) ldg256(st.qrow + (c + 4) * 16, qv);   // refill the slot just consumed
+        if ((c & 3) == 0) {   // the staging buffer about to be refilled must no longer be read by the previous store
+          wbuf = wbase + st.flip * 4096;
+          if (lane == 0) sm100::tma_store_wait_read<kBufs - 1>();
+          __syncwarp();
+          stg.init(wbuf, lane);
+        }
+        stg.put((c & 3) * 2, packed[0], packed[1], packed[2], packed[3]);
+        stg.put((c & 3) * 2 + 1, packed[4], packed[5], packed[6], packed[7]);
+        if ((c & 3) == 3) {
+          sm100::fence_proxy_async_smem();
+          __syncwarp();
+          const int col0 = tc.n_tile * BN + grp * kColsW + (c >> 2) * 64;
+          if (lane == 0) {
+            if (row0 < p.M && col0 < p.N) sm100::tma_store_3d(tmC, wbuf, col0, row0, 0);
+            sm100::tma_store_commit();   // always: wait_read<kBufs-1> counts groups
+          }
+          if (e.db2_partial) {
+            // column sums of the staged 32 x 64 tile: lane l owns columns 2l, 2l+1; row r of the tile is one
+            // conflict-free 128-byte wavefront (16-byte piece j of row r lives at ((j ^ (r & 7)) << 4))
+            const uint32_t cbase = stg.base + (lane & 3) * 4;
+            const uint32_t piece = (uint32_t)lane >> 2;
+            uint64_t d2 = pack2(0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t v = lds32(cbase + r * 128 + ((piece ^ (uint32_t)(r & 7)) << 4));
+              d2 = add2(d2, pack2u(v << 16, v & 0xffff0000u));
+            }
+            const int col = col0 + 2 * lane;
+            if (row0 < p.M && col < p.N) {
+              float d0, d1;
+              unpack2(d2, d0, d1);
+              float* o = e.db2_partial + (int64_t)(row0 >> 5) * p.N + col;
+              if (col + 1 < p.N && (p.N & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(d0, d1);
+              else { o[0] = d0; if (col + 1 < p.N) o[1] = d1; }
+            }
+          }
+          if (kBufs > 1) st.flip ^= 1;
+        }
+        if (c + 1 < kColsW / 16) sm100::tmem_wait_ld();
+      }
+      float l0, l1;
+      unpack2(lacc, l0, l1);
+      if (st.in_b) st.loss_b -= l0 + l1; else st.loss_a -= l0 + l1;   // the accumulator holds -cwt q u
+    }
+  };
+};
+
+// =============================================================================================
 // Epilogue 3 (pass 2, "transposed"): TMEM lanes = prototypes k, columns = entries e.
 // Sub-GEMM 0 = student logits  S[k,e] = W2s[k,:] . Hs[e,:],  sub-GEMM 1 = teacher T[k,e].
 //   u = S*as2 - lse2[e] + cs2[k]            log2 of the student softmax prob,  p = 2^u
@@ -816,6 +1225,7 @@ struct OutDesc {
   int is_bf16 = 0;
   int64_t ld = 0, slab_stride = 0, slabs = 1;
   int row_bytes = 128;   // staging row of the epilogue: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  int64_t cols = 0;      // column extent of the map when it differs from N (padded rows), 0 = N
 };
 
 static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int tile_rows, int64_t batches, const char* what) {
@@ -851,7 +1261,7 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   tC = tA0;
   if (Epi::kUsesTmaStore) {
     DINOX_REQUIRE(od.ptr, DINOX_E_BADARG, "%s: output descriptor missing", name);
-    if ((rc = make_tmap_out_3d(&tC, od.ptr, od.is_bf16 != 0, od.slabs, M, N, od.ld, od.slab_stride, od.row_bytes, "C"))) return rc;
+    if ((rc = make_tmap_out_3d(&tC, od.ptr, od.is_bf16 != 0, od.slabs, M, od.cols ? od.cols : N, od.ld, od.slab_stride, od.row_bytes, "C"))) return rc;
   }
   CoreParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -1142,6 +1552,102 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
   const int cl = cl2 ? 2 : 1;
   const int grid = launch_grid((((K + 127) / 128 + cl - 1) / cl) * ((E + 127) / 128), cl);
   pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * EpiGradT::kEpiWarps, loss_out, loss_accumulate);
+  return check_launch("pair_sum_kernel", stream);
+}
+
+/* ---- teacher, one pass: statistics + un-normalised fp16 probabilities (see EpiTeachQT) ---- */
+size_t dinox_head_teacher_workspace_bytes(int64_t rows, int64_t K) { return dinox_head_stats_workspace_bytes(rows, K); }
+
+int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D, int64_t ldh, int64_t ldw,
+                       float inv_tau, const float* col2, const float* col2_alt, int64_t alt_from_row, void* qt,
+                       int64_t ldq, float* refs, int64_t ld_refs, float* lse_nat, float* lse2, void* workspace,
+                       dinox_stream_t stream) {
+  DINOX_REQUIRE(H && W2 && qt && refs && workspace, DINOX_E_BADARG, "head_teacher: null pointer");
+  DINOX_REQUIRE(rows > 0 && K > 0 && D > 0, DINOX_E_BADARG, "head_teacher: empty problem");
+  const int64_t num_n = (K + 255) / 256;
+  DINOX_REQUIRE(ldq >= num_n * 256 && aligned16(qt) && (ldq * 2) % 16 == 0, DINOX_E_ALIGN,
+                "head_teacher: qt rows must be padded to whole 256-prototype tiles (ldq >= %lld)", (long long)(num_n * 256));
+  DINOX_REQUIRE(ld_refs >= rows, DINOX_E_BADARG, "head_teacher: ld_refs < rows");
+  DINOX_REQUIRE(!col2_alt || alt_from_row % BM == 0, DINOX_E_BADARG, "head_teacher: alt_from_row must be a multiple of 128");
+  int rc = require_sm100();
+  if (rc) return rc;
+  Operand a{H, rows, ldh, 0}, b{W2, K, ldw, 0};
+  OutDesc od;
+  od.ptr = qt; od.is_bf16 = 1; od.ld = ldq; od.slab_stride = rows * ldq; od.slabs = 1; od.cols = num_n * 256;
+  const int alt_mtile = col2_alt ? (int)(alt_from_row / BM) : (1 << 30);
+  const bool cl2 = rows > BM && pair_enabled(kPairStats);
+  if (resa_enabled(kPairStats, D)) {
+    const int cl = cl2 ? 2 : 1;
+    const int64_t num_m_super = ((rows + BM - 1) / BM + cl - 1) / cl, super = num_m_super * num_n;
+    const int ncl = launch_grid(super, cl) / cl;
+    const int per = (int)((super + ncl - 1) / ncl);
+    const int run_slots = (int)((num_n + per - 1) / per) + 1;
+    EpiTeachQT<true>::Params er{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), cl, per,
+                                run_slots, refs, ld_refs};
+    rc = cl2 ? launch<256, 1, 1, 2, EpiTeachQT<true>, kResA>(a, b, nullptr, nullptr, rows, K, D, 0, er, od, stream, "head_teacher<pair,resA>")
+             : launch<256, 1, 1, 1, EpiTeachQT<true>, kResA>(a, b, nullptr, nullptr, rows, K, D, 0, er, od, stream, "head_teacher<resA>");
+    if (rc) return rc;
+    if (lse_nat || lse2) {
+      stats_merge_run_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(er.partial, rows, 2, run_slots, (int)num_n, per, cl,
+                                                                                 lse_nat, lse2);
+      return check_launch("stats_merge_run_kernel", stream);
+    }
+    return DINOX_OK;
+  }
+  EpiTeachQT<false>::Params ep{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), 1, 1, 1, refs, ld_refs};
+  rc = cl2 ? launch<256, 1, 1, 2, EpiTeachQT<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher<pair>")
+           : launch<256, 1, 1, 1, EpiTeachQT<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher");
+  if (rc) return rc;
+  if (lse_nat || lse2) {
+    stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows, 2 * (int)num_n,
+                                                                       lse_nat, lse2);
+    return check_launch("stats_merge_kernel", stream);
+  }
+  return DINOX_OK;
+}
+
+/* ---- pass 2, student logits only, teacher probabilities read back (see EpiGradR) ---- */
+size_t dinox_head_grad2_workspace_bytes(int64_t E, int64_t K) {
+  if (K <= 0 || E <= 0) return 0;
+  return (size_t)(1024 * EpiGradR::kEpiWarps * 2) * sizeof(float) + 256;   // per-CTA loss partials, grid <= 1024
+}
+int64_t dinox_head_grad2_db2_rows(int64_t E) { return E <= 0 ? 0 : (E + 31) / 32; }
+
+int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int64_t D, int64_t ldh, int64_t ldw,
+                     float inv_tau_s, const float* cs2, const float* lse2_e, const float* cw_e, const float* rb2_e,
+                     const int32_t* trow_e, const void* qt, int64_t ldq, const float* refs, int64_t ld_refs,
+                     int64_t alt_from, void* G, int64_t ldg, float* db2_partial, float* loss_out, int loss_accumulate,
+                     void* workspace, dinox_stream_t stream) {
+  DINOX_REQUIRE(HsE && W2s && cs2 && lse2_e && cw_e && rb2_e && trow_e && qt && refs && G && loss_out && workspace,
+                DINOX_E_BADARG, "head_grad2: null pointer");
+  DINOX_REQUIRE(E > 0 && K > 0 && D > 0, DINOX_E_BADARG, "head_grad2: empty problem");
+  const int64_t num_n = (K + 255) / 256;
+  DINOX_REQUIRE(ldq >= num_n * 256 && (ldq * 2) % 32 == 0 && (reinterpret_cast<uintptr_t>(qt) & 31u) == 0, DINOX_E_ALIGN,
+                "head_grad2: qt must be 32-byte aligned with rows padded to whole 256-prototype tiles");
+  DINOX_REQUIRE(ldg >= K && (ldg * 2) % 16 == 0 && aligned16(G), DINOX_E_ALIGN, "head_grad2: G / ldg misaligned");
+  int rc = require_sm100();
+  if (rc) return rc;
+  Operand a{HsE, E, ldh, 0}, b{W2s, K, ldw, 0};
+  EpiGradR::Params ep;
+  ep.as2 = inv_tau_s * DINOX_LOG2E; ep.inv_tau_s = inv_tau_s;
+  ep.cs2 = cs2; ep.lse2 = lse2_e; ep.cw = cw_e; ep.rb2 = rb2_e; ep.trow = trow_e;
+  ep.qt = reinterpret_cast<const __half*>(qt); ep.ldq = ldq; ep.refs = refs; ep.ld_refs = ld_refs;
+  ep.alt_from = (int)(alt_from < 0 ? 0 : (alt_from > (1ll << 30) ? (1ll << 30) : alt_from));
+  ep.db2_partial = db2_partial; ep.loss_partial = reinterpret_cast<float*>(workspace);
+  OutDesc od;
+  od.ptr = G; od.is_bf16 = 1; od.ld = ldg; od.slab_stride = E * ldg; od.slabs = 1;
+  const bool cl2 = E > BM && pair_enabled(kPairGrad);
+  const int cl = cl2 ? 2 : 1;
+  if (resa_enabled(kPairStats, D))   // the entries of an M tile resident, prototype tiles walked in one contiguous run
+    rc = cl2 ? launch<256, 1, 1, 2, EpiGradR, kResA>(a, b, nullptr, nullptr, E, K, D, 0, ep, od, stream, "head_grad2<pair,resA>")
+             : launch<256, 1, 1, 1, EpiGradR, kResA>(a, b, nullptr, nullptr, E, K, D, 0, ep, od, stream, "head_grad2<resA>");
+  else
+    rc = cl2 ? launch<256, 1, 1, 2, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair>")
+             : launch<256, 1, 1, 1, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2");
+  if (rc) return rc;
+  const int grid = launch_grid((((E + BM - 1) / BM + cl - 1) / cl) * num_n, cl);
+  pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * EpiGradR::kEpiWarps, loss_out,
+                                          loss_accumulate);
   return check_launch("pair_sum_kernel", stream);
 }
 

@@ -310,25 +310,50 @@ def _ema_update(teacher: nn.Module, student: nn.Module, m: float) -> None:
 # a1 projection head as an nn.Sequential with the reference's parameter keys
 # =================================================================================================
 _BF16_CACHE: Dict[int, Tuple] = {}
-_WEIGHT_EPOCH = [0]  # bumped by ema_update: raw-pointer kernels do not touch tensor version counters
+_WEIGHT_EPOCH = [0]  # bumped by every dinox kernel that writes parameters through raw pointers
+_WEIGHT_CACHE_MODE = ["always"]
+
+
+def set_weight_cache(mode: str) -> str:
+    """How the bf16 operand copies of the head weights are kept:
+
+    "always"  (default) - re-cast from the fp32 master on every forward, exactly like CUDA autocast does.  Safe
+              for ANY way of updating parameters, including the reference's own EMA loop
+              `p_t.data.mul_(m).add_(p_s.data, alpha=1-m)` (scripts/phase5_big_run.py:1800-1802), which does
+              not bump `p._version`.
+    "tracked" - reuse the copy until the parameter's version counter / storage changes or a dinox kernel that
+              writes parameters (`ema_update`, `FusedAdamW.step`, `ShardedFusedAdamW.step`) bumps the weight
+              epoch.  For loops that update parameters ONLY through autograd-visible in-place ops or those
+              dinox entry points (`LossHeadStep` does); call `invalidate_weight_cache()` after anything else.
+    Returns the previous mode."""
+    if mode not in ("always", "tracked"):
+        raise ValueError(f"weight cache mode {mode!r}: expected 'always' or 'tracked'")
+    prev = _WEIGHT_CACHE_MODE[0]
+    _WEIGHT_CACHE_MODE[0] = mode
+    return prev
+
+
+def invalidate_weight_cache() -> None:
+    """Forces a re-cast of every cached bf16 weight copy at its next use (copies are rewritten in place, so
+    captured CUDA graphs keep valid addresses)."""
+    _WEIGHT_EPOCH[0] += 1
 
 
 def bf16_weight(p: torch.Tensor) -> torch.Tensor:
-    """bf16 copy of a weight, cached until the parameter is modified in place (autocast does the same
-    per forward).  An entry is valid only for the very same tensor object (weak reference: Python ids
-    and allocator blocks are both recycled), the same version counter, storage pointer and EMA epoch."""
+    """bf16 copy of a weight.  In "tracked" mode an entry is valid only for the very same tensor object (weak
+    reference: Python ids and allocator blocks are both recycled), the same version counter, storage pointer
+    and weight epoch; in "always" mode it is rewritten on every call.  The copy of a live parameter is always
+    refreshed IN PLACE: captured CUDA graphs hold its address."""
     import weakref
     key = id(p)
     ver = p._version
     hit = _BF16_CACHE.get(key)
-    if (hit is not None and hit[0]() is p and hit[1] == ver and hit[2] == p.data_ptr() and hit[3] == _WEIGHT_EPOCH[0]
-            and hit[4].shape == p.shape):
+    same = hit is not None and hit[0]() is p and hit[4].shape == p.shape and hit[4].device == p.device
+    if (same and _WEIGHT_CACHE_MODE[0] == "tracked" and hit[1] == ver and hit[2] == p.data_ptr()
+            and hit[3] == _WEIGHT_EPOCH[0]):
         return hit[4]
     w = p.detach()
-    # refresh IN PLACE when the same parameter object is still alive: captured CUDA graphs hold the
-    # address of the bf16 copy, so a stale copy must be rewritten, not replaced
-    reuse = hit is not None and hit[0]() is p and hit[4].shape == p.shape and hit[4].device == p.device
-    out = hit[4] if reuse else torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    out = hit[4] if same else torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
     ops.gather_cast_bf16(w.reshape(w.shape[0], -1), None, out.reshape(w.shape[0], -1))
     if len(_BF16_CACHE) > 64:   # drop entries whose parameter is gone
         for k in [k for k, v in _BF16_CACHE.items() if v[0]() is None]:
@@ -453,6 +478,13 @@ class _EntryPlan:
         self.csr_ptr, self.csr_ent = t(ptr, torch.int64), t(ent, torch.int64)
         self.cw_base = t(cw, torch.float32)
         self.Ms, self.Mt, self.Mm, self.B, self.V, self.Vg = Ms, Mt, Mm, B, V, Vg
+        # read-back path: the teacher rows are laid out [CLS rows | zero rows up to a multiple of 128 | masked
+        # patch rows] so that one teacher launch can switch its column offsets (centre / patch centre) per M tile
+        self.Mt_pad = (Mt + 127) // 128 * 128 if Mm else Mt
+        etp = [(r if r < Mt else r - Mt + self.Mt_pad) if r >= 0 else -1 for r in et]
+        self.ent_t_pad = t(etp, torch.int64)                           # -1 = padding entry
+        self.trow = t([max(r, 0) for r in etp], torch.int32)           # row of qt / refs (padding -> row 0, weight 0)
+        self.cls_rows_pad = t(list(range(Mt)) + [-1] * (self.Mt_pad - Mt), torch.int64)
 
 
 _PLANS: Dict[Tuple, _EntryPlan] = {}
@@ -486,6 +518,16 @@ def _side_stream(device, which: int = 0) -> "torch.cuda.Stream":
     return st
 
 
+def pass2_mode() -> str:
+    """DINOX_PASS2: "readback" (default) - the teacher runs ONE pass that also writes its un-normalised fp16
+    probabilities (dinox_head_teacher) and pass 2 recomputes only the student logits (dinox_head_grad2);
+    "recompute" - round-1 path: teacher statistics pass + both logit tiles recomputed side by side in pass 2."""
+    m = os.environ.get("DINOX_PASS2", "readback")
+    if m not in ("readback", "recompute"):
+        raise ValueError(f"DINOX_PASS2={m!r}: expected readback or recompute")
+    return m
+
+
 def _accumulate_grad(p: torch.Tensor, fn) -> None:
     """fn(out_tensor, accumulate: bool) writes/accumulates dL/dp straight into p.grad (fp32)."""
     if p.grad is None:
@@ -498,30 +540,54 @@ def _accumulate_grad(p: torch.Tensor, fn) -> None:
         fn(p.grad, True)
 
 
-def _update_centres(hsum, hsum_work, pg, Mt, Mm, w2t, b2t, loss_mod, center_patch, patch_momentum) -> None:
+def _update_centres(hsum, hsum_work, pg, Mt, Mm, w2t, b2t, loss_mod, center_patch, patch_momentum, cls: bool) -> None:
     """Centre EMA of the fused path: mean teacher logits = W2t . mean(h_t) + b2t (one GEMV over W2t for the CLS
-    and the patch centre together) from the all-reduced activation sums."""
+    and the patch centre together) from the all-reduced activation sums.  hsum rows: [CLS (if cls)] [patch (if Mm)]."""
     if hsum is None:
         return
     w = _world(pg)
     if hsum_work is not None:
         hsum_work.wait()
-    alphas = [1.0 / (Mt * w)] + ([1.0 / (Mm * w)] if Mm else [])
+    alphas = ([1.0 / (Mt * w)] if cls else []) + ([1.0 / (Mm * w)] if Mm else [])
     mean_logits = ops.gemv_bf16_multi(w2t, hsum, alphas, b2t, 1.0)
-    ops.center_ema_(loss_mod.center, mean_logits[0], 1, loss_mod.center_momentum)
+    i = 0
+    if cls:
+        ops.center_ema_(loss_mod.center, mean_logits[0], 1, loss_mod.center_momentum)
+        i = 1
     if Mm:
-        ops.center_ema_(center_patch, mean_logits[1], 1, patch_momentum)
+        ops.center_ema_(center_patch, mean_logits[i], 1, patch_momentum)
+
+
+_MM_CHECKED: Dict[Tuple, bool] = {}
+
+
+def _check_equal_masked_rows(Mm: int, pg, device) -> None:
+    """The patch-centre mean divides the all-reduced activation sum by Mm * world: every rank must mask the same
+    number of tokens.  Verified once per (count, group) with one tiny all-gather, never inside a graph capture."""
+    w = _world(pg)
+    key = (Mm, id(pg) if pg is not True else 0, w)
+    if w == 1 or key in _MM_CHECKED or torch.cuda.is_current_stream_capturing():
+        return
+    import torch.distributed as dist
+    mine = torch.tensor([Mm], dtype=torch.int64, device=device)
+    allm = [torch.empty_like(mine) for _ in range(w)]
+    dist.all_gather(allm, mine, group=_group(pg))
+    counts = [int(x.item()) for x in allm]
+    if any(c != Mm for c in counts):
+        raise ValueError(f"fused_head_dino_loss: ranks mask different numbers of patch tokens {counts}; the patch "
+                         "centre assumes equal counts (pad the masks or use equal mask ratios per rank)")
+    _MM_CHECKED[key] = True
 
 
 class _FusedHeadLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, student_cls, student_patch, teacher_cls, teacher_patch, masks_weight, s_head, t_head, loss_mod,
-                center_patch, cfg, patch_index=None):
+    def forward(ctx, student_cls, student_patch, w1, b1, w2, b2, teacher_cls, teacher_patch, masks_weight, t_head,
+                loss_mod, center_patch, cfg, patch_index=None, params_in_place=None):
         (student_temp, teacher_temp, Vg, n_local, ibot_weight, teacher_mode, sk_iters, pg, update_center,
-         patch_momentum) = cfg
+         patch_momentum, grads_in_place) = cfg
         dev = student_cls.device
         D = student_cls.shape[1]
-        K = s_head[2].weight.shape[0]
+        K = w2.shape[0]
         Mt = teacher_cls.shape[0]
         B = Mt // Vg
         V = student_cls.shape[0] // B
@@ -533,24 +599,32 @@ class _FusedHeadLoss(torch.autograd.Function):
         if Mm:
             sp2 = student_patch.detach() if patch_index is None else student_patch.detach().view(-1, D)
             tp2 = teacher_patch.detach() if patch_index is None else teacher_patch.detach().view(-1, D)
+            _check_equal_masked_rows(Mm, pg, dev)
         plan = _entry_plan(B, Vg, V, Mm, dev)
+        readback = pass2_mode() == "readback"
+        Mt_pad = plan.Mt_pad if readback else Mt        # row of the first masked patch in the teacher matrices
         inv_ts, inv_tt = 1.0 / student_temp, 1.0 / teacher_temp
-        w1s, w2s = bf16_weight(s_head[0].weight), bf16_weight(s_head[2].weight)
+        w1s, w2s = bf16_weight(w1), bf16_weight(w2)
         w1t, w2t = bf16_weight(t_head[0].weight), bf16_weight(t_head[2].weight)
+        centre_cls = update_center and teacher_mode == "center"
+        # the patch centre is the only collapse protection of the iBOT targets in BOTH teacher modes (the CLS
+        # Sinkhorn-Knopp normalisation does not touch the patch rows), so it is updated whenever there are patch rows
+        centre_patch = update_center and Mm > 0
 
         # Two branches that meet at pass 2.  The teacher branch (no gradient) is issued on a side stream
-        # so that its ~20 short kernels slot into the launch gaps and wave tails of the student branch;
+        # so that its short kernels slot into the launch gaps and wave tails of the student branch;
         # per-kernel timing (ops.TIMER) keeps everything on one stream.
         main = torch.cuda.current_stream()
         side = _side_stream(dev) if (concurrency() >= 2 and not ops.TIMER.enabled) else None
         if side is not None:
             side.wait_stream(main)
-        # ---- teacher: stage inputs [CLS rows | masked patch rows] as bf16, layer 1, statistics
+        qt = refs = ht_e = None
+        # ---- teacher: stage inputs [CLS rows | (zero rows) | masked patch rows] as bf16, layer 1, statistics
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            xt = torch.empty(Mt + Mm, D, dtype=torch.bfloat16, device=dev)
-            ops.gather_cast_bf16(teacher_cls.detach(), None, xt[:Mt])
+            xt = torch.empty(Mt_pad + Mm, D, dtype=torch.bfloat16, device=dev)
+            ops.gather_cast_bf16(teacher_cls.detach(), plan.cls_rows_pad if Mt_pad != Mt else None, xt[:Mt_pad])
             if Mm:
-                ops.gather_cast_bf16(tp2, patch_index, xt[Mt:])
+                ops.gather_cast_bf16(tp2, patch_index, xt[Mt_pad:])
             a_t = ops.gemm_bf16(xt, w1t, bias_n=t_head[0].bias.detach())   # layer 1 (zoo/arch.py:253-254)
             ht = ops.gelu_fwd(a_t)
             del a_t
@@ -558,55 +632,64 @@ class _FusedHeadLoss(torch.autograd.Function):
             # linearity, so the data-parallel payload is the D-vector sum(h_t) (CLS and masked-patch rows
             # in ONE all-reduce), launched now so that its latency hides behind the pass-1/pass-2 GEMMs
             hsum = hsum_work = None
-            if update_center and teacher_mode == "center":
-                hsum = torch.empty(2 if Mm else 1, D, dtype=torch.float32, device=dev)
-                ops.cols_sum(ht[:Mt], out=hsum[0])
-                if Mm:
-                    ops.cols_sum(ht[Mt:], out=hsum[1])   # every rank masks the same number of tokens (no host sync)
+            if centre_cls or centre_patch:
+                hsum = torch.empty(int(centre_cls) + int(centre_patch), D, dtype=torch.float32, device=dev)
+                if centre_cls:
+                    ops.cols_sum(ht[:Mt], out=hsum[0])
+                if centre_patch:
+                    ops.cols_sum(ht[Mt_pad:], out=hsum[int(centre_cls)])
                 hsum_work = allreduce_sum_async(hsum, pg)
-            # pass 1, teacher rows: row statistics with logits kept on chip
             b2t = t_head[2].bias.detach()
             center = loss_mod.center.reshape(-1)
-            rb2_t = torch.empty(Mt + Mm, dtype=torch.float32, device=dev)
+            rb2_t = torch.empty(Mt_pad + Mm, dtype=torch.float32, device=dev)
+            b_row = None
             if teacher_mode == "center":
                 ct2 = ops.axpby(b2t, inv_tt * LOG2E, center, -inv_tt * LOG2E)
-                with ops.TIMER.region("head_stats_teacher_cls"):
-                    ops.head_stats(ht[:Mt], w2t, inv_tt, ct2, want_nat=False, out_log2=rb2_t[:Mt])
             else:  # Sinkhorn-Knopp on the (small) materialised CLS teacher logits
                 t_cls = ops.gemm_bf16(ht[:Mt], w2t, bias_n=b2t)
                 a_col, b_row = sinkhorn_knopp_biases(t_cls, teacher_temp, sk_iters, pg)
                 ct2 = ops.axpby(b2t, inv_tt * LOG2E, a_col, -LOG2E)
-                ops.axpb(b_row, LOG2E, out=rb2_t[:Mt])
                 del t_cls
-            ct2_patch = None
-            if Mm:
-                ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E)
-                with ops.TIMER.region("head_stats_teacher_patch"):
-                    ops.head_stats(ht[Mt:], w2t, inv_tt, ct2_patch, want_nat=False, out_log2=rb2_t[Mt:])
-            ht_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
-            ops.gather_cast_bf16(ht, plan.ent_t, ht_e)
-            rb2_e = ops.gather_f32(rb2_t, plan.ent_t)
+            ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E) if Mm else None
+            if readback:
+                # ONE pass over the teacher rows: statistics + un-normalised fp16 probabilities
+                with ops.TIMER.region("head_teacher"):
+                    qt, refs, _ = ops.head_teacher(ht, w2t, inv_tt, ct2, ct2_patch, Mt_pad, out_log2=rb2_t)
+            else:
+                if teacher_mode == "center":
+                    with ops.TIMER.region("head_stats_teacher_cls"):
+                        ops.head_stats(ht[:Mt], w2t, inv_tt, ct2, want_nat=False, out_log2=rb2_t[:Mt])
+                if Mm:
+                    with ops.TIMER.region("head_stats_teacher_patch"):
+                        ops.head_stats(ht[Mt:], w2t, inv_tt, ct2_patch, want_nat=False, out_log2=rb2_t[Mt:])
+                ht_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
+                ops.gather_cast_bf16(ht, plan.ent_t, ht_e)
+            if b_row is not None:   # Sinkhorn rows are normalised by their own offset, not by the row LSE
+                ops.axpb(b_row, LOG2E, out=rb2_t[:Mt])
+            # padding entries: a huge offset makes their probabilities exactly 0 (0 * inf would poison the sums)
+            rb2_e = ops.gather_f32(rb2_t, plan.ent_t_pad if readback else plan.ent_t, fill=1.0e30)
             if side is not None and concurrency() >= 3:
                 # centre updates here instead of after pass 2: ct2 / ct2_patch above already hold the OLD centres
                 # (scripts/phase5_big_run.py:719 - the loss sees the centre of the previous step), and the GEMV over
                 # W2t runs beside the student branch instead of after pass 2
-                _update_centres(hsum, hsum_work, pg, Mt, Mm, w2t, b2t, loss_mod, center_patch, patch_momentum)
+                _update_centres(hsum, hsum_work, pg, Mt, Mm if centre_patch else 0, w2t, b2t, loss_mod, center_patch,
+                                patch_momentum, centre_cls)
                 hsum = None
         # ---- student: the same on the current stream
         xs = torch.empty(Ms + Mm, D, dtype=torch.bfloat16, device=dev)
         ops.gather_cast_bf16(student_cls.detach(), None, xs[:Ms])
         if Mm:
             ops.gather_cast_bf16(sp2, patch_index, xs[Ms:])
-        a_s = ops.gemm_bf16(xs, w1s, bias_n=s_head[0].bias.detach())
+        a_s = ops.gemm_bf16(xs, w1s, bias_n=b1.detach())
         hs = ops.gelu_fwd(a_s)
-        b2s = s_head[2].bias.detach()
+        b2s = b2.detach()
         cs2 = ops.axpb(b2s, inv_ts * LOG2E)
         with ops.TIMER.region("head_stats_student"):
             _, lse2_s = ops.head_stats(hs, w2s, inv_ts, cs2, want_nat=False)
         # ---- entries
         hs_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
         ops.gather_cast_bf16(hs, plan.ent_s, hs_e)
-        lse2_e = ops.gather_f32(lse2_s, plan.ent_s)
+        lse2_e = ops.gather_f32(lse2_s, plan.ent_s, fill=1.0e30)
         if side is not None:
             # Everything the teacher branch allocated lives in the side stream's pool and is read by pass 2 on
             # this stream: those blocks are only handed out again to side-stream work, and every side-stream
@@ -618,56 +701,78 @@ class _FusedHeadLoss(torch.autograd.Function):
             ops.axpb(masks_weight.detach().float().contiguous(), ibot_weight / Mt,
                      0.0, out=cw[plan.e_cls_pad:plan.e_cls_pad + Mm])
         # ---- pass 2
-        losses = torch.zeros(2, dtype=torch.float32, device=dev)
-        need_grad = any(ctx.needs_input_grad[:2]) or s_head[2].weight.requires_grad
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad[:6]) or (params_in_place is not None and
+                                                      any(p.requires_grad for p in params_in_place))
         with ops.TIMER.region("head_grad"):
-            gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
-                                     lse2_e, rb2_e, cw, losses, want_db2=need_grad)
+            if readback:
+                gt, db2p = ops.head_grad2(hs_e, w2s, inv_ts, cs2, lse2_e, cw, rb2_e, plan.trow, qt, refs, plan.e_cls_pad,
+                                          losses, want_db2=need_grad)
+            else:
+                gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
+                                         lse2_e, rb2_e, cw, losses, want_db2=need_grad)
         # ---- centre updates AFTER the loss (scripts/phase5_big_run.py:719)
-        _update_centres(hsum, hsum_work, pg, Mt, Mm, w2t, b2t, loss_mod, center_patch, patch_momentum)
+        _update_centres(hsum, hsum_work, pg, Mt, Mm if centre_patch else 0, w2t, b2t, loss_mod, center_patch,
+                        patch_momentum, centre_cls)
         if need_grad:
             ctx.save_for_backward(xs, a_s, hs_e, gt, db2p, w1s, w2s)
-            ctx.plan, ctx.s_head = plan, s_head
+            ctx.plan = plan
+            ctx.params = params_in_place if params_in_place is not None else (w1, b1, w2, b2)
+            ctx.readback, ctx.grads_in_place = readback, grads_in_place
             ctx.in_dtypes = (student_cls.dtype, None if student_patch is None else student_patch.dtype)
             ctx.patch_index = patch_index
             ctx.patch_shape = None if student_patch is None else tuple(student_patch.shape)
         ctx.mark_non_differentiable(losses)
-        total = losses.sum() if Mm else losses[0].clone()
+        total = ops.scalar_combine([losses[0], losses[1]], [1.0, 1.0])
         return total, losses
 
     @staticmethod
     def backward(ctx, g, _g_losses):
         xs, a_s, hs_e, gt, db2p, w1s, w2s = ctx.saved_tensors
-        plan, s_head = ctx.plan, ctx.s_head
+        plan = ctx.plan
+        w1, b1, w2, b2 = ctx.params
+        in_place = ctx.grads_in_place
         up = g.to(torch.float32).reshape(1).contiguous()
         K, D = w2s.shape
         rows = plan.Ms + plan.Mm
+        dev = gt.device
+        outs = {}
+
+        def emit(name, p, fn):
+            """dL/dp: accumulated straight into p.grad (in-place mode) or returned to autograd"""
+            if in_place:
+                _accumulate_grad(p, fn)
+            else:
+                o = torch.empty_like(p, memory_format=torch.contiguous_format)
+                fn(o, False)
+                outs[name] = o
+
         # The layer-2 parameter gradients (dW2, db2) and the dH -> layer-1 chain only share their input G: at
         # level 3 the former run on a side stream, so the CTAs of dH start on the SMs the last, partial wave of
         # dW2 leaves idle (256 tile pairs on 74 CTA pairs = 3.46 waves).
         main = torch.cuda.current_stream()
-        side = _side_stream(gt.device, 2) if (concurrency() >= 3 and not ops.TIMER.enabled) else None
+        side = _side_stream(dev, 2) if (concurrency() >= 3 and not ops.TIMER.enabled) else None
         if side is not None:
             side.wait_stream(main)
+        rb = ctx.readback   # G is (E, K) entry-major on the read-back path, Gt (K, E) prototype-major otherwise
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            # dW2 (K, D) += g * Gt . HsE   (A = Gt K-major over entries, B = HsE MN-major)
+            # dW2 (K, D) += g * G^T . HsE   (A = G with the prototypes as M; B = HsE MN-major)
             with ops.TIMER.region("gemm_dW2"):
-                _accumulate_grad(s_head[2].weight, lambda out, acc: ops.gemm_bf16(
-                    gt, hs_e, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
+                emit("w2", w2, lambda out, acc: ops.gemm_bf16(
+                    gt, hs_e, a_mn_major=rb, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
             db2 = ops.cols_sum(db2p)
-            _accumulate_grad(s_head[2].bias, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out,
-                                                                       alpha_dev=up))
-        # dH per entry = G . W2  (A = Gt MN-major, B = W2 MN-major), then sum the entries of each row
+            emit("b2", b2, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out, alpha_dev=up))
+        # dH per entry = G . W2  (B = W2 MN-major), then sum the entries of each row
         with ops.TIMER.region("gemm_dH"):
-            dh_e = ops.gemm_bf16_splitk(gt, w2s, a_mn_major=True, b_mn_major=True, m_fastest=True)
-        dh = torch.empty(rows, D, dtype=torch.float32, device=gt.device)
+            dh_e = ops.gemm_bf16_splitk(gt, w2s, a_mn_major=not rb, b_mn_major=True, m_fastest=True)
+        dh = torch.empty(rows, D, dtype=torch.float32, device=dev)
         ops.gather_sum_rows(dh_e, plan.csr_ptr, plan.csr_ent, rows, dh)
         da, part = ops.gelu_bwd(dh, a_s, scale_dev=up)
         db1 = ops.cols_sum(part)
-        _accumulate_grad(s_head[0].bias, lambda out, acc: ops.axpby(db1, 1.0, out if acc else None, 1.0, out=out))
+        emit("b1", b1, lambda out, acc: ops.axpby(db1, 1.0, out if acc else None, 1.0, out=out))
         # dW1 = da^T x: 3x3 output tiles with a reduction over every row -> split-K, slabs summed in fixed order
         dw1_parts = ops.gemm_bf16_splitk(da, xs, a_mn_major=True, b_mn_major=True)
-        _accumulate_grad(s_head[0].weight, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))
+        emit("w1", w1, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))
         dx = ops.gemm_bf16(da, w1s, b_mn_major=True)
         if side is not None:
             main.wait_stream(side)
@@ -677,10 +782,12 @@ class _FusedHeadLoss(torch.autograd.Function):
             if ctx.patch_index is None:
                 d_patch = dx[plan.Ms:].to(ctx.in_dtypes[1])
             else:   # rows went in through an index: their gradients go back to those rows of the token tensor
-                d_tok = torch.zeros(ctx.patch_shape, dtype=torch.float32, device=dx.device)
+                d_tok = torch.empty(ctx.patch_shape, dtype=torch.float32, device=dx.device)
+                ops.fill_(d_tok.view(-1), 0.0)
                 ops.scatter_rows(dx[plan.Ms:], ctx.patch_index, d_tok.view(-1, D))
                 d_patch = d_tok.to(ctx.in_dtypes[1])
-        return d_cls, d_patch, None, None, None, None, None, None, None, None, None
+        return (d_cls, d_patch, outs.get("w1"), outs.get("b1"), outs.get("w2"), outs.get("b2"),
+                None, None, None, None, None, None, None, None, None)
 
 
 def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, student_head: nn.Sequential,
@@ -688,14 +795,18 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
                          *, student_patch: Optional[torch.Tensor] = None, teacher_patch: Optional[torch.Tensor] = None,
                          masks_weight: Optional[torch.Tensor] = None, center_patch: Optional[torch.Tensor] = None,
                          ibot_weight: float = 1.0, patch_center_momentum: Optional[float] = None,
-                         update_center: bool = True, patch_index: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                         update_center: bool = True, patch_index: Optional[torch.Tensor] = None,
+                         grads_in_place: bool = False) -> Dict[str, torch.Tensor]:
     """Projection head + multi-crop DINO CE (+ iBOT masked-patch CE) in one fused path.
 
     Equivalent to `dino_loss(student_head(student_cls), teacher_head(teacher_cls), ...)` of the reference
     loop (scripts/phase5_big_run.py:1746-1754) but the (rows x K) logits exist only in TMEM.
-    Gradients of the student head parameters are accumulated straight into their `.grad` during
-    `backward()` (scaled by the upstream gradient, so `loss / accumulation_steps` and GradScaler work);
-    gradients w.r.t. `student_cls` / `student_patch` flow through autograd.
+    Gradients flow through autograd to `student_cls` / `student_patch` AND to the four student head
+    parameters (AccumulateGrad hooks, DDP reducers and `torch.autograd.grad` all see them).
+    `grads_in_place=True` is the opt-in fast path of a single-process accumulation loop: the head gradients
+    are reduce-added straight into the parameters' `.grad` by the GEMM epilogues (no (K, D) temporary, no
+    AccumulateGrad pass; scaled by the upstream gradient, so `loss / accumulation_steps` and GradScaler work),
+    invisible to autograd hooks.
     With `patch_index` (int64, unique flat row numbers) `student_patch` / `teacher_patch` are the backbone's
     token tensors themselves (contiguous (..., D), e.g. the (B*Vg, T, D) output that `feats[:, 1:]` slices,
     scripts/phase5_big_run.py:1741-1747): the masked rows are gathered by the staging kernel and their
@@ -717,11 +828,44 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
                 raise ValueError("masks_weight and patch_index must name the same rows")
     cfg = (student_temp, teacher_temp, dino_loss.n_global, dino_loss.n_local, ibot_weight, dino_loss.teacher_mode,
            dino_loss.sk_iterations, dino_loss.process_group, update_center,
-           dino_loss.center_momentum if patch_center_momentum is None else patch_center_momentum)
-    total, losses = _FusedHeadLoss.apply(student_cls, student_patch, teacher_cls.detach(),
-                                         None if teacher_patch is None else teacher_patch.detach(), masks_weight,
-                                         student_head, teacher_head, dino_loss, center_patch, cfg, patch_index)
+           dino_loss.center_momentum if patch_center_momentum is None else patch_center_momentum, bool(grads_in_place))
+    params = (student_head[0].weight, student_head[0].bias, student_head[2].weight, student_head[2].bias)
+    # in-place mode: the parameters enter detached (no AccumulateGrad node takes part in the backward - theirs would
+    # tie a captured backward to whatever stream first created them) and the real ones ride along to receive .grad
+    ins = tuple(p.detach() for p in params) if grads_in_place else params
+    total, losses = _FusedHeadLoss.apply(student_cls, student_patch, *ins,
+                                         teacher_cls.detach(), None if teacher_patch is None else teacher_patch.detach(),
+                                         masks_weight, teacher_head, dino_loss, center_patch, cfg, patch_index,
+                                         params if grads_in_place else None)
     return {"loss": total, "loss_dino": losses[0], "loss_ibot": losses[1]}
+
+
+class _CombineLosses(torch.autograd.Function):
+    """loss = scale * sum_i w_i * term_i in one launch (and one for the backward fan-out) instead of the
+    mul/add/div chain of scripts/phase5_big_run.py:1749-1772; also returns the unscaled sum for logging."""
+
+    @staticmethod
+    def forward(ctx, weights, scale, *terms):
+        ctx.weights, ctx.scale = tuple(float(w) for w in weights), float(scale)
+        ts = [t.detach().reshape(()) for t in terms]
+        total = torch.empty((), dtype=torch.float32, device=ts[0].device)
+        scaled = ops.scalar_combine(ts, ctx.weights, ctx.scale, out_unscaled=total)
+        ctx.mark_non_differentiable(total)
+        return scaled, total
+
+    @staticmethod
+    def backward(ctx, g, _g_total):
+        fan = ops.scalar_fanout(g.reshape(1), ctx.weights, ctx.scale)
+        return (None, None) + tuple(fan[i] for i in range(len(ctx.weights)))
+
+
+def combine_losses(terms: Sequence[torch.Tensor], weights: Sequence[float], scale: float = 1.0):
+    """(scale * sum_i weights[i] * terms[i]  [differentiable], the unscaled sum [detached]) for 0-dim fp32 CUDA
+    loss terms - the step glue `loss = L_dino + w_g * L_gram (+ ...); loss / accum`."""
+    for t in terms:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.numel() == 1):
+            raise ValueError("combine_losses: 0-dim fp32 CUDA tensors expected")
+    return _CombineLosses.apply(tuple(weights), scale, *terms)
 
 
 class _KoLeo(torch.autograd.Function):

@@ -258,6 +258,55 @@ def head_grad(w2s, w2t, hs_e, ht_e, inv_tau_s, inv_tau_t, cs2, ct2, ct2_alt, alt
     return gt, db2p
 
 
+def teacher_buffers(rows: int, K: int, device):
+    """(qt, refs) of dinox_head_teacher: fp16 probabilities with rows padded to whole 256-prototype tiles,
+    and the per-(128-prototype granule, row) maxima."""
+    n_tiles = (K + 255) // 256
+    qt = torch.empty(rows, n_tiles * 256, dtype=torch.float16, device=device)
+    refs = torch.empty(2 * n_tiles, rows, dtype=torch.float32, device=device)
+    return qt, refs
+
+
+def head_teacher(h: torch.Tensor, w2: torch.Tensor, inv_tau: float, col2: Optional[torch.Tensor],
+                 col2_alt: Optional[torch.Tensor] = None, alt_from_row: int = 0,
+                 qt: Optional[torch.Tensor] = None, refs: Optional[torch.Tensor] = None,
+                 out_log2: Optional[torch.Tensor] = None):
+    """Teacher in one pass: returns (qt (rows, K_pad) fp16, refs (2*ceil(K/256), rows) fp32, lse2 (rows))
+    with softmax(h @ w2^T * inv_tau + col2/log2e)[i, k] = qt[i, k] * 2^(refs[k // 128, i] - lse2[i])."""
+    _chk_cuda(h, w2, col2, col2_alt)
+    rows, D = h.shape
+    K = w2.shape[0]
+    if qt is None or refs is None:
+        qt, refs = teacher_buffers(rows, K, h.device)
+    l2 = out_log2 if out_log2 is not None else torch.empty(rows, dtype=torch.float32, device=h.device)
+    ws = torch.empty(int(_ext.lib().dinox_head_teacher_workspace_bytes(rows, K)), dtype=torch.uint8, device=h.device)
+    _ext.call("dinox_head_teacher", _p(h), _p(w2), rows, K, D, _rowmajor(h), _rowmajor(w2), float(inv_tau), _p(col2),
+              _p(col2_alt), int(alt_from_row), _p(qt), qt.stride(0), _p(refs), refs.stride(0), None, _p(l2), _p(ws),
+              _stream())
+    return qt, refs, l2
+
+
+def head_grad2(hs_e: torch.Tensor, w2s: torch.Tensor, inv_tau_s: float, cs2: torch.Tensor, lse2_e: torch.Tensor,
+               cw_e: torch.Tensor, rb2_e: torch.Tensor, trow_e: torch.Tensor, qt: torch.Tensor, refs: torch.Tensor,
+               alt_from: int, loss_out: torch.Tensor, loss_accumulate: bool = False, want_db2: bool = True,
+               g: Optional[torch.Tensor] = None):
+    """Pass 2 (student logits recomputed, teacher probabilities read back).  loss_out: 2 fp32 ([0] entries <
+    alt_from, [1] the rest).  Returns (G (E, K) bf16 = dL/dlogits per entry, db2_partial or None)."""
+    assert loss_out.numel() >= 2 and trow_e.dtype == torch.int32 and qt.dtype == torch.float16
+    _chk_cuda(hs_e, w2s, qt, refs)
+    E, D = hs_e.shape
+    K = w2s.shape[0]
+    if g is None:   # rows padded to 16 bytes (TMA store pitch); the view hides the padding
+        g = torch.empty(E, (K + 7) // 8 * 8, dtype=torch.bfloat16, device=w2s.device)[:, :K]
+    db2p = (torch.empty(int(_ext.lib().dinox_head_grad2_db2_rows(E)), K, dtype=torch.float32, device=w2s.device)
+            if want_db2 else None)
+    ws = torch.empty(int(_ext.lib().dinox_head_grad2_workspace_bytes(E, K)), dtype=torch.uint8, device=w2s.device)
+    _ext.call("dinox_head_grad2", _p(hs_e), _p(w2s), E, K, D, _rowmajor(hs_e), _rowmajor(w2s), float(inv_tau_s), _p(cs2),
+              _p(lse2_e), _p(cw_e), _p(rb2_e), _p(trow_e), _p(qt), qt.stride(0), _p(refs), refs.stride(0), int(alt_from),
+              _p(g), _rowmajor(g), _p(db2p), _p(loss_out), int(loss_accumulate), _p(ws), _stream())
+    return g, db2p
+
+
 def axpby(x: torch.Tensor, alpha: float, y: Optional[torch.Tensor], beta: float,
           out: Optional[torch.Tensor] = None, alpha_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     out = torch.empty_like(x) if out is None else out
@@ -430,6 +479,31 @@ def koleo_bwd(z: torch.Tensor, saved, eps: float, upstream: torch.Tensor) -> tor
     _ext.call("dinox_koleo_bwd", _p(z), DT[z.dtype], R, K, _rowmajor(z), _p(inv), _p(nn), _p(dist), float(eps), _p(up),
               _p(dz), K, _stream())
     return dz
+
+
+def scalar_combine(terms: Sequence[torch.Tensor], weights: Sequence[float], scale: float = 1.0,
+                   out: Optional[torch.Tensor] = None, out_unscaled: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """0-dim fp32 tensor scale * sum_i weights[i] * terms[i] (device scalars, one launch, fixed order);
+    `out_unscaled` (optional) receives the sum without `scale`."""
+    n = len(terms)
+    assert 1 <= n <= 8 and len(weights) == n
+    for t in terms:
+        assert t.dtype == torch.float32 and t.numel() == 1 and t.is_cuda
+    out = torch.empty((), dtype=torch.float32, device=terms[0].device) if out is None else out
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in terms])
+    w = (ctypes.c_float * n)(*[float(x) for x in weights])
+    _ext.call("dinox_scalar_combine", ptrs, w, n, float(scale), _p(out), _p(out_unscaled), _stream())
+    return out
+
+
+def scalar_fanout(upstream: torch.Tensor, weights: Sequence[float], scale: float = 1.0) -> torch.Tensor:
+    """(n,) fp32: upstream * scale * weights[i] - the per-term gradients of scalar_combine."""
+    n = len(weights)
+    up = upstream if (upstream.dtype == torch.float32 and upstream.is_contiguous()) else upstream.float().contiguous()
+    out = torch.empty(n, dtype=torch.float32, device=up.device)
+    w = (ctypes.c_float * n)(*[float(x) for x in weights])
+    _ext.call("dinox_scalar_fanout", _p(up), w, n, float(scale), _p(out), _stream())
+    return out
 
 
 def fill_(t: torch.Tensor, v: float = 0.0) -> torch.Tensor:

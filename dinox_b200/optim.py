@@ -14,7 +14,7 @@ from typing import Optional
 
 import torch
 
-from . import _ext
+from . import _ext, losshead
 
 
 class FusedAdamW(torch.optim.AdamW):
@@ -84,6 +84,9 @@ class FusedAdamW(torch.optim.AdamW):
                       ctypes.c_void_p(norm.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
             torch._foreach_add_([self.state[p]["step"] for p in ps], 1.0)
             norms.append(norm)
+        # the kernel wrote the parameters through raw pointers: tensor version counters did not move, so cached
+        # bf16 operand copies of the head weights (losshead.bf16_weight, "tracked" mode) must be told
+        losshead.invalidate_weight_cache()
         if norms:
             self.last_grad_norm = norms[0] if len(norms) == 1 else torch.stack(norms).square().sum().sqrt()
         return loss
@@ -136,7 +139,9 @@ class ShardedFusedAdamW:
                  process_group=None, shard_min_numel: int = 1 << 20):
         import torch.distributed as dist
         self.params = [p for p in params]
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        # torch.optim-style single parameter group: the reference loop writes `param_groups[i]['lr']` every step
+        # (scripts/phase5_big_run.py:1699); lr / betas / eps / weight_decay are read from it at step time
+        self.param_groups = [dict(params=self.params, lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)]
         self.pg = None if process_group in (None, True) else process_group
         self.world = dist.get_world_size(self.pg) if dist.is_initialized() else 1
         self.rank = dist.get_rank(self.pg) if dist.is_initialized() else 0
@@ -188,7 +193,9 @@ class ShardedFusedAdamW:
                 w.wait()
         self.step_count += 1
         t = float(self.step_count)
-        b1, b2 = self.betas
+        grp = self.param_groups[0]
+        lr, eps, wd = grp["lr"], grp["eps"], grp["weight_decay"]
+        b1, b2 = grp["betas"]
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         sq = torch.zeros(2, dtype=torch.float32, device=self.params[0].device)
         for slot, (key, ps) in enumerate((("sharded", sharded), ("replicated", repl))):
@@ -198,7 +205,7 @@ class ShardedFusedAdamW:
             items = [(self.state[p]["own"], self.state[p]["grad"] if use_shard_grad else p.grad,
                       self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) for p in ps]
             h = self._plan(key, items)
-            _ext.call("dinox_adamw_step", h, float(self.lr), float(b1), float(b2), float(self.eps), float(self.weight_decay),
+            _ext.call("dinox_adamw_step", h, float(lr), float(b1), float(b2), float(eps), float(wd),
                       1.0 - b1 ** t, 1.0 - b2 ** t, float(grad_scale), ctypes.c_void_p(sq[slot:].data_ptr()), stream)
         sq.square_()
         if self.world > 1:
@@ -207,6 +214,14 @@ class ShardedFusedAdamW:
             for p in sharded:                                 # in place: rank r's rows are already where they belong
                 dist.all_gather_into_tensor(p.data.view(-1), self.state[p]["own"].view(-1), group=self.pg)
         self.last_grad_norm = sq.sum().sqrt()
+        losshead.invalidate_weight_cache()   # parameters were written through raw pointers / p.data
+
+    # lr, betas, eps, weight_decay: views of the parameter group, so `opt.lr = x` and `param_groups[0]['lr'] = x` agree
+    lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
+    betas = property(lambda self: self.param_groups[0]["betas"])
+    eps = property(lambda self: self.param_groups[0]["eps"])
+    weight_decay = property(lambda self: self.param_groups[0]["weight_decay"],
+                            lambda self, v: self.param_groups[0].__setitem__("weight_decay", v))
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
@@ -233,6 +248,42 @@ class ShardedFusedAdamW:
                      maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
                      decoupled_weight_decay=True, params=list(range(len(self.params))))
         return {"state": state, "param_groups": [group]}
+
+    def state_dict(self):
+        """torch.optim.AdamW's layout (`opt.state_dict()` of the reference checkpoint, :1119); collective: every
+        rank must call it (the sharded moments are all-gathered)."""
+        return self.consolidated_state_dict()
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """Inverse of `state_dict()` (resume, scripts/phase5_big_run.py:1168): accepts torch.optim.AdamW's layout
+        with full-size moments - written by this class, by FusedAdamW or by torch.optim.AdamW - and keeps only the
+        rows this rank owns.  Hyper-parameters of the stored group replace the current ones."""
+        groups = state_dict["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.params):
+            raise ValueError(f"optimizer state holds {len(order)} parameters, this optimizer {len(self.params)}")
+        steps = set()
+        for pos, idx in enumerate(order):
+            p, (sharded, rows) = self.params[pos], self.layout[pos]
+            src = state_dict["state"].get(idx)
+            st = self.state[p]
+            if src is None:      # a parameter that never received a gradient
+                st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+                continue
+            for k in ("exp_avg", "exp_avg_sq"):
+                full = src[k].to(device=p.device, dtype=torch.float32)
+                if tuple(full.shape) != tuple(p.shape):
+                    raise ValueError(f"{k} of parameter {pos}: shape {tuple(full.shape)} != {tuple(p.shape)}")
+                st[k].copy_(full[self.rank * rows:(self.rank + 1) * rows] if sharded else full)
+            steps.add(float(src["step"]))
+        if len(steps) > 1:
+            raise ValueError(f"ShardedFusedAdamW keeps one step count; the state holds {sorted(steps)}")
+        self.step_count = int(steps.pop()) if steps else 0
+        g0 = groups[0]
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in g0:
+                self.param_groups[0][k] = tuple(g0[k]) if k == "betas" else g0[k]
 
     def __del__(self):
         try:

@@ -52,6 +52,9 @@ class LossHeadStep:
         self.student_params += list(self.student_head.parameters())
         self.teacher_params += list(self.teacher_head.parameters())
         self.n_params = sum(p.numel() for p in self.student_params)
+        # this loop updates parameters only through dinox entry points (ema_update bumps the weight epoch), so the
+        # bf16 operand copies of the head weights are re-cast only when a weight changed
+        losshead.set_weight_cache("tracked")
         self.micro = 0
         self._graphs: Dict[int, dict] = {}
         self.launches_per_graph = 0
@@ -59,8 +62,8 @@ class LossHeadStep:
     def micro_step(self, f: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """f: student_cls, teacher_cls (+ student_tok, teacher_tok) (+ student_patch, teacher_patch,
         masks_weight); student tensors may require grad.  Returns the component losses."""
-        out, loss = self._losses(f)
-        (loss / self.accum).backward()
+        out, loss = self._losses(f)      # already divided by accum
+        loss.backward()
         self.micro += 1
         if self.micro % self.accum == 0:
             # the optimizer step belongs to the host loop (scripts/phase5_big_run.py:1794-1796); then EMA
@@ -139,7 +142,7 @@ class LossHeadStep:
 
     def _fwd_bwd(self, f):
         out, loss = self._losses(f)
-        (loss / self.accum).backward()
+        loss.backward()
         return out
 
     def _losses(self, f):
@@ -161,24 +164,24 @@ class LossHeadStep:
             f["student_cls"], f["teacher_cls"], self.student_head, self.teacher_head, self.dino_loss,
             self.student_temp, self.teacher_temp, student_patch=sp, teacher_patch=tp,
             masks_weight=f.get("masks_weight"), center_patch=self.center_patch if sp is not None else None,
-            ibot_weight=self.ibot_weight, patch_index=f.get("patch_index"))
-        loss = out["loss"]
+            ibot_weight=self.ibot_weight, patch_index=f.get("patch_index"), grads_in_place=True)
+        terms, weights = [out["loss"]], [1.0]
         if gram is not None:
             if side is not None:
                 torch.cuda.current_stream().wait_stream(side)
             out["loss_gram"] = gram
-            loss = loss + self.gram_weight * gram
-        loss = self._add_koleo(f, out, loss)
-        out["loss_total"] = loss.detach()
-        return out, loss
-
-    def _add_koleo(self, f, out, loss):
-        if self.koleo is None:
-            return loss
-        n_glob = self.shapes.batch * self.shapes.n_global       # the reference feeds its 2B global-view rows
-        z = self.student_head(f["student_cls"][:n_glob])
-        out["loss_koleo"] = self.koleo(z)
-        return loss + self.koleo_weight * out["loss_koleo"]
+            terms.append(gram)
+            weights.append(self.gram_weight)
+        if self.koleo is not None:
+            n_glob = self.shapes.batch * self.shapes.n_global       # the reference feeds its 2B global-view rows
+            z = self.student_head(f["student_cls"][:n_glob])
+            out["loss_koleo"] = self.koleo(z)
+            terms.append(out["loss_koleo"])
+            weights.append(self.koleo_weight)
+        # loss = (L_dino + L_ibot + w_g L_gram + w_k L_koleo) / accum  (scripts/phase5_big_run.py:1749-1769), one launch
+        scaled, total = losshead.combine_losses(terms, weights, 1.0 / self.accum)
+        out["loss_total"] = total
+        return out, scaled
 
     def micro_step_graph(self, slot: int = 0) -> Dict[str, torch.Tensor]:
         """Replay the captured micro-step on the current contents of the slot's static inputs.  Returns

@@ -187,6 +187,44 @@ DINOX_API int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE,
                               float* loss_out, int loss_accumulate, void* workspace,
                               dinox_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Teacher in ONE pass (default fused path): the statistics of dinox_head_stats PLUS the teacher
+ * probabilities themselves in un-normalised 16-bit form, so that pass 2 never recomputes a teacher
+ * logit.  For x[i,k] = (H.W2^T)[i,k]*inv_tau*log2e + col2[k] and every 128-prototype granule g:
+ *   refs[g][i] = max_{k in g} x[i,k]                       (log2 units; (2*ceil(K/256), ld_refs) fp32)
+ *   qt[i,k]    = fp16( 2^(x[i,k] - refs[g(k)][i]) )        ((rows, ldq) fp16, ldq >= 256*ceil(K/256);
+ *                                                            columns in [K, ldq) are written as 0)
+ *   lse2[i]    = log2 sum_k 2^x[i,k]  (and/or the natural-log lse_nat), from the unrounded values
+ * so softmax((t - c)/tau_t)[i,k] = qt[i,k] * 2^(refs[g][i] - lse2[i])  (scripts/phase5_big_run.py:703).
+ * Rows of M tiles at or beyond alt_from_row (multiple of 128) use col2_alt (iBOT patch centre); NULL = none.
+ * ------------------------------------------------------------------------------------------ */
+DINOX_API size_t dinox_head_teacher_workspace_bytes(int64_t rows, int64_t K);
+DINOX_API int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D,
+                                 int64_t ldh, int64_t ldw, float inv_tau, const float* col2,
+                                 const float* col2_alt, int64_t alt_from_row, void* qt, int64_t ldq,
+                                 float* refs, int64_t ld_refs, float* lse_nat, float* lse2,
+                                 void* workspace, dinox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pass 2 on top of dinox_head_teacher: for E entries (student row gathered into HsE, teacher row
+ * trow_e[e] of qt/refs) recompute only the STUDENT logit tile in TMEM and emit
+ *   G[e,k]   = cw[e]*inv_tau_s*( softmax_s[e,k] - q_t[e,k] )            (bf16, (E, ldg) = dL/dlogits)
+ *   loss[0..1] (+)= sum_e cw[e] * sum_k q_t[e,k] * (-ln softmax_s[e,k])   ([0]: e < alt_from, [1]: the rest)
+ *   db2_partial[dinox_head_grad2_db2_rows(E), K]  column sums of G per 32 entries (reduce with dinox_cols_sum)
+ * with softmax_s = 2^(S*inv_tau_s*log2e + cs2[k] - lse2_e[e]) and
+ *      q_t       = qt[trow_e[e],k] * 2^(refs[g(k)][trow_e[e]] - rb2_e[e]).
+ * Cross-entropy of scripts/phase5_big_run.py:706-717 and its autograd in one kernel.
+ * ------------------------------------------------------------------------------------------ */
+DINOX_API size_t dinox_head_grad2_workspace_bytes(int64_t E, int64_t K);
+DINOX_API int64_t dinox_head_grad2_db2_rows(int64_t E);
+DINOX_API int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int64_t D,
+                               int64_t ldh, int64_t ldw, float inv_tau_s, const float* cs2,
+                               const float* lse2_e, const float* cw_e, const float* rb2_e,
+                               const int32_t* trow_e, const void* qt, int64_t ldq, const float* refs,
+                               int64_t ld_refs, int64_t alt_from, void* G, int64_t ldg,
+                               float* db2_partial, float* loss_out, int loss_accumulate,
+                               void* workspace, dinox_stream_t stream);
+
 /* batched variant: `batches` independent problems, element strides between problems.  Used for the
  * per-image Gram backward  dXn[b] = alpha * Delta[b] @ Xn[b]  (autograd of torch.bmm,
  * scripts/phase5_big_run.py:727). */
@@ -257,6 +295,14 @@ DINOX_API int dinox_gather_sum_rows(const float* src, int64_t ld_src, int slabs,
                                     const float* scale_dev, float scale, float* dst, int64_t ld_dst,
                                     int accumulate, dinox_stream_t stream);
 DINOX_API int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream);
+/* a9 step glue (scripts/phase5_big_run.py:1749-1772, `loss = L_dino + w_g*L_gram (+ w_k*L_koleo); loss /= accum`):
+ *   out[0] = scale * sum_{i<n} weights[i] * terms[i][0]      (n <= 8 device scalars, fixed order)
+ *   out_unscaled[0] = the same sum without `scale` (optional, NULL to skip; the logged loss)
+ * and for its backward  out[i] = upstream[0] * scale * weights[i].  `terms` / `weights` are HOST arrays. */
+DINOX_API int dinox_scalar_combine(const float* const* terms, const float* weights, int n, float scale,
+                                   float* out, float* out_unscaled, dinox_stream_t stream);
+DINOX_API int dinox_scalar_fanout(const float* upstream, const float* weights, int n, float scale,
+                                  float* out, dinox_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a11 KoLeo regulariser on head outputs (scripts/phase5_big_run.py:742-773, wired at :1764-1766):
