@@ -192,6 +192,55 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+# HBM-bound kernels of the materialised-logit path (DINOLoss drop-in, Sinkhorn-Knopp, centre EMA): achieved GB/s
+# ---------------------------------------------------------------------------------------------------
+def hbm_kernel_table(dev, sh, hbm_peak: float, reps: int = 20):
+    """CUDA-event medians of the row / column reduction kernels at this config's logit shapes, each launched on
+    a cold L2 (a 512 MB buffer is rewritten between calls), with their ALGORITHMIC bytes (every logit read once
+    per pass, fp32) -> GB/s and fraction of the measured HBM copy bandwidth.  Shapes at C2: student 640 x 65536,
+    teacher 128 x 65536 - the small ones are launch-latency bound and say so."""
+    from dinox_b200 import losshead, ops
+    K, Ms, Mt, B = sh.out_dim, sh.student_rows, sh.teacher_rows, sh.batch
+    g = torch.Generator(device="cpu").manual_seed(7)
+    s = torch.randn(Ms, K, generator=g).to(dev)
+    t = torch.randn(Mt, K, generator=g).to(dev)
+    center = torch.zeros(K, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    colb = ops.axpb(center, 25.0)
+    rowb = ops.rows_lse(t, 25.0, colb)
+    lse_s = ops.rows_lse(s, 10.0)
+    V, Vg = sh.views, sh.n_global
+    norm = 1.0 / ((Vg * V - Vg) * B)
+    up = torch.ones((), device=dev)
+    colsum = ops.cols_sum(t)
+    cases = {
+        "rows_lse_student": (lambda: ops.rows_lse(s, 10.0), 4.0 * Ms * K),
+        "rows_lse_teacher": (lambda: ops.rows_lse(t, 25.0, colb), 4.0 * Mt * K + 4.0 * K),
+        "cols_lse_teacher": (lambda: ops.cols_lse(t, 25.0, rowb), 4.0 * Mt * K + 4.0 * K),
+        "cols_sum_teacher": (lambda: ops.cols_sum(t), 4.0 * Mt * K + 4.0 * K),
+        "ce_fwd": (lambda: ops.ce_fwd(s, t, B, V, Vg, 10.0, 25.0, colb, rowb, lse_s, None, norm, True), 4.0 * (Ms + Mt) * K),
+        "ce_bwd": (lambda: ops.ce_bwd(s, t, B, V, Vg, 10.0, 25.0, colb, rowb, lse_s, None, norm, True, up),
+                   4.0 * (2 * Ms + Mt) * K),
+        "center_ema": (lambda: ops.center_ema_(center, colsum, Mt, 0.9), 12.0 * K),
+        "sinkhorn_3it": (lambda: losshead.sinkhorn_knopp_biases(t, 0.04, 3, None), 6.0 * 4.0 * Mt * K),
+    }
+    out = {}
+    for name, (fn, nbytes) in cases.items():
+        fn()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)                      # evict the logits from L2 (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(statistics.median(ts))
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -258,10 +307,13 @@ def run_ours(args):
         step.micro_step(to_leaves({k: v.detach() for k, v in resident.items()}))
     barrier()
     ops.TIMER.reset()
-    n_eager = args.steps if not use_graph else max(4, min(args.steps, 8))
+    n_eager = args.steps if not use_graph else max(20, min(args.steps, 24))   # >= 20 calls per kernel, >= 5 EMA launches
     sampler = ClockSampler(local)
+    eager_sampler = ClockSampler(local)
     if not use_graph:
         sampler.start()
+    else:
+        eager_sampler.start()
     ops.launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -269,6 +321,7 @@ def run_ours(args):
         out = step.micro_step(to_leaves({k: v.detach() for k, v in resident.items()}))
     e1.record()
     barrier()
+    eager_clocks = eager_sampler.stop() if use_graph else None
     ops.TIMER.enabled = False
     ops.TIMER.resolve()
     eager_ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / n_eager
@@ -305,6 +358,23 @@ def run_ours(args):
         ms_per_step = eager_ms_per_step
     value = crops_per_step / (ms_per_step * 1e-3)
     loss_val = float(out["loss_total"].item())
+
+    # ---------------- leg 1b: the same replay for >= sustained_s seconds (power-limited steady state) -------------
+    sustained = None
+    if use_graph and args.sustained_s > 0:
+        n_sus = max(args.steps, int(math.ceil(args.sustained_s * 1e3 / ms_per_step)))
+        sus_sampler = ClockSampler(local)
+        barrier()
+        sus_sampler.start()
+        e0.record()
+        for _ in range(n_sus):
+            step.micro_step_graph(0)
+        e1.record()
+        barrier()
+        sus_clocks = sus_sampler.stop()
+        sus_ms = max_over_ranks(e0.elapsed_time(e1)) / n_sus
+        sustained = {"ms_per_step": sus_ms, "value": crops_per_step / (sus_ms * 1e-3), "steps": n_sus,
+                     "seconds": sus_ms * n_sus * 1e-3, "clocks": sus_clocks}
 
     # ---------------- leg 2: end to end from pinned host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -366,41 +436,80 @@ def run_ours(args):
     peaks = _peaks()
     D, K = sh.dim, sh.out_dim
     rows_s, rows_t = sh.student_rows + sh.masked_rows, sh.teacher_rows + sh.masked_rows
-    # per-kernel time = median over the calls of the eager leg (one slow call - a first-time allocation,
-    # a host hiccup between the two events - must not read as kernel time)
+    e_pad = (sh.batch * (sh.n_global * sh.views - sh.n_global) + 127) // 128 * 128 + (sh.masked_rows + 127) // 128 * 128
+    # per-kernel time = median over the calls of the eager leg (>= 20 calls; one slow call - a first-time
+    # allocation, a host hiccup between the two events - must not read as kernel time)
     kt = {k: float(statistics.median(v)) for k, v in ops.TIMER.samples.items()}
+    kn = {k: len(v) for k, v in ops.TIMER.samples.items()}
     if os.environ.get("DINOX_BENCH_DEBUG"):
         for k, v in ops.TIMER.samples.items():
             print(f"[timer] {k:26s}", " ".join(f"{x:.3f}" for x in v), file=sys.stderr)
-    dom = max(kt, key=kt.get)
+    from dinox_b200 import losshead as _lh
+    readback = _lh.pass2_mode() == "readback"
+    # ALGORITHMIC FLOPs per launch: the forward logits each kernel is charged with.  Recompute work is
+    # not credited: the statistics passes of the student (recomputed in pass 2) count 0.
     alg_flops = {
-        "head_grad": 2.0 * D * K * (rows_s + rows_t),          # student + teacher logit tiles (forward logits)
-        "head_stats_student": 0.0, "head_stats_teacher_cls": 0.0, "head_stats_teacher_patch": 0.0,  # recompute
+        # read-back path: pass 2 forms the student logits of every entry once (the teacher's come from head_teacher)
+        "head_grad": 2.0 * D * K * (rows_s if readback else rows_s + rows_t),
+        "head_teacher": 2.0 * D * K * rows_t,
+        "head_stats_student": 0.0, "head_stats_teacher_cls": 0.0, "head_stats_teacher_patch": 0.0,
         "gemm_dW2": 2.0 * D * K * rows_s, "gemm_dH": 2.0 * D * K * rows_s,
     }
+    # ALGORITHMIC HBM bytes per launch of the kernels that stream a rows x K object
+    alg_bytes = {
+        "head_teacher": 2.0 * rows_t * K + 2.0 * K * D,                     # fp16 probabilities out + W2t in
+        "head_grad": (2.0 * rows_t * K if readback else 0.0) + 2.0 * e_pad * K + 2.0 * K * D,   # q in, G out, W2s in
+        "gemm_dW2": 2.0 * e_pad * K + 8.0 * K * D, "gemm_dH": 2.0 * e_pad * K + 2.0 * K * D,
+        "ema_multi": 12.0 * step.n_params,
+    }
+    gemm_like = [k for k in kt if alg_flops.get(k, 0.0) > 0.0]
+    dom = max(gemm_like or kt, key=kt.get)
     ach = alg_flops.get(dom, 0.0) / (kt[dom] * 1e-3) / 1e12
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    # Which measured peak applies: the per-kernel leg is a few tens of milliseconds.  If its own clock record shows the
+    # SM clock at (or within 2 % of) the maximum, the chip was in the burst regime -> burst cuBLAS peak; a clock that
+    # sagged under the power cap -> sustained peak.  Both fractions are printed.
+    ck = eager_clocks if eager_clocks is not None else clocks
+    at_max = bool(ck and ck.get("sm_mhz") and ck.get("sm_max_mhz") and ck["sm_mhz"] >= 0.98 * ck["sm_max_mhz"])
+    peak_tf = peaks["tf_burst"] if at_max else peaks["tf_sustained"]
+    peak_choice = ("burst" if at_max else "sustained") + f" (median SM clock {ck.get('sm_mhz') if ck else None} MHz of " \
+        f"{ck.get('sm_max_mhz') if ck else None} during the per-kernel leg)"
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this round
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tj = json.load(f)
         k = tj["kernels"].get(dom)
-        if k and args.config == "C2":
+        if k and args.config == "C2" and tj.get("pass2_mode") == _lh.pass2_mode():
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
-            traffic_src = "profiles/r01_traffic.json (" + tj["source"] + ")"
+            traffic_src = "profiles/r02_traffic.json (" + tj["source"] + ")"
     except Exception:
         pass
-    peak_tf = peaks["tf_sustained"]
     step_alg_tf = sh.flops() / (ms_per_step * 1e-3) / 1e12
+    step_peak = peaks["tf_burst"] if (clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.98 * clocks["sm_max_mhz"]) else peaks["tf_sustained"]
+    kernels_gbs = {k: alg_bytes[k] / (kt[k] * 1e-3) / 1e9 for k in kt if k in alg_bytes}
     roofline = {
         "kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
-        "kernel_ms": kt[dom], "kernels_ms": kt, "kernel_ms_stat": "median over the calls of the eager leg",
+        "frac": ach / peak_tf, "frac_of_burst": ach / peaks["tf_burst"], "frac_of_sustained": ach / peaks["tf_sustained"],
+        "peak_choice": peak_choice, "peaks": {"bf16_burst": peaks["tf_burst"], "bf16_sustained": peaks["tf_sustained"],
+                                              "hbm_gbs": peaks["hbm"], "source": peaks["src"]},
+        "traffic": traffic, "traffic_source": traffic_src,
+        "kernel_ms": kt[dom], "kernels_ms": kt, "kernels_calls": kn,
+        "kernel_ms_stat": f"median over the {kn[dom]} calls of the eager leg",
         "kernels_ms_mean": {k: sum(v) / len(v) for k, v in ops.TIMER.samples.items()},
-        "step_algorithmic_tflops": step_alg_tf, "step_frac": step_alg_tf / peak_tf,
-        "ema_gbs": (12.0 * step.n_params / (kt["ema_multi"] * 1e-3) / 1e9) if "ema_multi" in kt else None,
-        "hbm_peak_gbs": peaks["hbm"],
+        "kernels_tflops": {k: alg_flops[k] / (kt[k] * 1e-3) / 1e12 for k in kt if alg_flops.get(k, 0.0) > 0.0},
+        "kernels_hbm_gbs": kernels_gbs,
+        "kernels_hbm_frac": {k: v / peaks["hbm"] for k, v in kernels_gbs.items()},
+        "step_algorithmic_tflops": step_alg_tf, "step_frac": step_alg_tf / step_peak,
+        "step_frac_of_burst": step_alg_tf / peaks["tf_burst"], "step_frac_of_sustained": step_alg_tf / peaks["tf_sustained"],
+        "ema_gbs": kernels_gbs.get("ema_multi"), "hbm_peak_gbs": peaks["hbm"],
+        "eager_leg_clocks": eager_clocks,
     }
+    if sustained is not None:
+        sus_tf = sh.flops() / (sustained["ms_per_step"] * 1e-3) / 1e12
+        sustained["step_algorithmic_tflops"] = sus_tf
+        sustained["step_frac_of_sustained_peak"] = sus_tf / peaks["tf_sustained"]
+    if world == 1 and not args.no_hbm_table:
+        roofline["hbm_kernels"] = hbm_kernel_table(dev, sh, peaks["hbm"])
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -424,6 +533,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": roofline,
+        "sustained": sustained,
         "cpu_baseline": cpu_baseline,
         "loss": loss_val,
     }
@@ -457,6 +567,9 @@ def main():
                     help="iBOT rows: masked rows of the token tensors named by an index (gathered in the step), or rows "
                          "materialised by the caller")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--sustained-s", type=float, default=2.0,
+                    help="length of the extra graph-replay leg that reports the power-limited steady state (0 = skip)")
+    ap.add_argument("--no-hbm-table", action="store_true", help="skip the GB/s table of the HBM-bound reduction kernels")
     args = ap.parse_args()
     global _OUT
     _OUT = _claim_stdout()

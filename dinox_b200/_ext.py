@@ -149,6 +149,7 @@ SIGNATURES = {
                                 c_f32, c_f32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_i64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dinox_head_teacher_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_head_teacher_granules_per_tile": (c_int, []),
     "dinox_head_teacher": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p, c_i64,
                                    c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dinox_head_grad2_workspace_bytes": (c_size, [c_i64, c_i64]),
@@ -170,8 +171,8 @@ SIGNATURES = {
     "dinox_gelu_bwd_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_gelu_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dinox_gemv_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_f32, c_void_p, c_f32, c_void_p, c_void_p]),
-    "dinox_gemv_bf16_multi": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_f32, c_void_p,
-                                      c_void_p]),
+    "dinox_gemv_bf16_multi": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_f32,
+                                      c_void_p, c_void_p]),
     "dinox_sum_slabs": (c_int, [c_void_p, c_int, c_i64, c_i64, c_void_p, c_f32, c_void_p, c_int, c_void_p]),
     "dinox_gather_sum_rows": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_f32,
                                       c_void_p, c_i64, c_int, c_void_p]),

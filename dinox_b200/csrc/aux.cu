@@ -174,8 +174,8 @@ __global__ void gemv_bf16_kernel(const __nv_bfloat16* __restrict__ W, int64_t ld
 struct GemvAlphas { float a[4]; };
 template <int NV>
 __global__ void gemv_bf16_multi_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, const float* __restrict__ X,
-                                       int64_t K, int D, GemvAlphas alphas, const float* __restrict__ bias, float beta,
-                                       float* __restrict__ out) {
+                                       int64_t K, int D, GemvAlphas alphas, const float* __restrict__ divisors,
+                                       const float* __restrict__ bias, float beta, float* __restrict__ out) {
   const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (k >= K) return;
@@ -202,7 +202,7 @@ __global__ void gemv_bf16_multi_kernel(const __nv_bfloat16* __restrict__ W, int6
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const float t = warp_sum(acc[v]);
-    if (lane == 0) out[(int64_t)v * K + k] = t * alphas.a[v] + b;
+    if (lane == 0) out[(int64_t)v * K + k] = t * (divisors ? alphas.a[v] / divisors[v] : alphas.a[v]) + b;
   }
 }
 
@@ -389,7 +389,8 @@ int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64
 }
 
 int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
-                          const float* alphas_host, const float* bias, float beta, float* out, dinox_stream_t stream) {
+                          const float* alphas_host, const float* divisors_dev, const float* bias, float beta, float* out,
+                          dinox_stream_t stream) {
   DINOX_REQUIRE(W && X && out && alphas_host && K > 0 && D > 0 && D % 8 == 0 && ldw % 8 == 0 && nvec >= 1 && nvec <= 4,
                 DINOX_E_BADARG, "gemv_bf16_multi: bad arguments (D, ldw multiples of 8; 1..4 vectors)");
   DINOX_REQUIRE(aligned16(W) && aligned16(X), DINOX_E_ALIGN, "gemv_bf16_multi: misaligned");
@@ -398,10 +399,10 @@ int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, 
   const unsigned grid = (unsigned)((K + 7) / 8);
   const __nv_bfloat16* w = (const __nv_bfloat16*)W;
   switch (nvec) {
-    case 1: gemv_bf16_multi_kernel<1><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, bias, beta, out); break;
-    case 2: gemv_bf16_multi_kernel<2><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, bias, beta, out); break;
-    case 3: gemv_bf16_multi_kernel<3><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, bias, beta, out); break;
-    default: gemv_bf16_multi_kernel<4><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, bias, beta, out); break;
+    case 1: gemv_bf16_multi_kernel<1><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;
+    case 2: gemv_bf16_multi_kernel<2><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;
+    case 3: gemv_bf16_multi_kernel<3><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;
+    default: gemv_bf16_multi_kernel<4><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;
   }
   return check_launch("gemv_bf16_multi_kernel", stream);
 }

@@ -444,12 +444,15 @@ __device__ __forceinline__ uint32_t f16x2_bits(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <bool kRun>
+#ifndef DINOX_RB_EPI_WARPS
+#define DINOX_RB_EPI_WARPS 8   // epilogue warps of the two read-back kernels (teacher pass / pass 2): 8 or 16 (16: register cap 96, 3 operand stages - measured slower)
+#endif
+template <bool kRun, int W>
 struct EpiTeachQT {
   static constexpr bool kUsesTmaStore = true;
-  static constexpr int kEpiWarps = 8;
-  static constexpr int kGroups = 2;                      // column groups per TMEM lane quarter
-  static constexpr int kColsW = 128;                     // one granule per warp and tile
+  static constexpr int kEpiWarps = W;                    // 8 or 16
+  static constexpr int kGroups = W / 4;                  // column groups per TMEM lane quarter
+  static constexpr int kColsW = 256 / kGroups;           // one granule (128 or 64 prototypes) per warp and tile
   // one staging buffer per warp (32 rows x 128 B) leaves five 16 KB operand stages beside the resident A rows;
   // the wait for the previous store's read sits behind the math of the next 32 columns
   static constexpr int kBufs = 1;
@@ -485,7 +488,7 @@ struct EpiTeachQT {
   }
   template <int BN>
   struct Impl {
-    static_assert(BN == 256, "EpiTeachQ is written for 256-wide tiles");
+    static_assert(BN == 256 && (W == 8 || W == 16), "EpiTeachQ is written for 256-wide tiles and 8 or 16 epilogue warps");
     static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
                                                  State& st) {
       const int col0 = tc.n_tile * BN + (epi_warp >> 2) * kColsW;
@@ -520,24 +523,21 @@ struct EpiTeachQT {
       // ---- sweep 1: granule maximum of this thread's row
       float gm = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < kColsW / 64; ++c) {
-        float v[2][32];
-        sm100::tmem_ld32x2(taddr + c * 64, taddr + c * 64 + 32, v[0], v[1]);
+      for (int c = 0; c < kColsW / 32; ++c) {
+        float v[32];
+        sm100::tmem_ld32(taddr + c * 32, v);
+        const float* cb = buf + c * 32;
+        float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float* cb = buf + c * 64 + h * 32;
-          float cm0 = -INFINITY, cm1 = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = lds128(cb + j);
-            float x0, x1, x2, x3;
-            unpack2(fma2(pack2(v[h][j], v[h][j + 1]), sc2, pack2(b4.x, b4.y)), x0, x1);
-            unpack2(fma2(pack2(v[h][j + 2], v[h][j + 3]), sc2, pack2(b4.z, b4.w)), x2, x3);
-            cm0 = fmaxf(cm0, fmaxf(x0, x1));
-            cm1 = fmaxf(cm1, fmaxf(x2, x3));
-          }
-          gm = fmaxf(gm, fmaxf(cm0, cm1));
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = lds128(cb + j);
+          float x0, x1, x2, x3;
+          unpack2(fma2(pack2(v[j], v[j + 1]), sc2, pack2(b4.x, b4.y)), x0, x1);
+          unpack2(fma2(pack2(v[j + 2], v[j + 3]), sc2, pack2(b4.z, b4.w)), x2, x3);
+          cm0 = fmaxf(cm0, fmaxf(x0, x1));
+          cm1 = fmaxf(cm1, fmaxf(x2, x3));
         }
+        gm = fmaxf(gm, fmaxf(cm0, cm1));
       }
       const float gsafe = (gm == -INFINITY) ? 0.f : gm;   // a granule entirely beyond N: every exponential is 2^-inf = 0
       const uint64_t ng2 = pack2(-gsafe, -gsafe);
@@ -585,7 +585,11 @@ struct EpiTeachQT {
           if (lane == 0) {
             // the map's column extent is the PADDED row length, so columns in [N, ld) receive the zeros computed
             // for them (col2 = -inf) and pass 2 may read whole 256-byte row segments
+#if DINOX_STREAM_EVICT_FIRST
+            if (row0 < p.M) sm100::tma_store_3d_hint(tmC, wbuf, col0, row0, 0, sm100::l2_policy_evict_first());
+#else
             if (row0 < p.M) sm100::tma_store_3d(tmC, wbuf, col0, row0, 0);
+#endif
             sm100::tma_store_commit();   // always: wait_read<kBufs-1> counts groups
           }
           if (kBufs > 1) st.flip ^= 1;
@@ -624,6 +628,16 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "l"(p));
 }
+// ... with an L2 eviction-priority hint: streams that are read exactly once must not displace the W2 tiles that
+// every M tile re-reads from L2
+__device__ __forceinline__ void ldg256_hint(const void* p, uint32_t (&r)[8], uint64_t pol) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p), "l"(pol));
+}
+#ifndef DINOX_STREAM_EVICT_FIRST
+#define DINOX_STREAM_EVICT_FIRST 1
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
@@ -633,11 +647,14 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 
 // "minus infinity" that stays finite under 0 * x
 #define DINOX_NEG_HUGE (-1.0e30f)
-struct EpiGradR {
+template <int W>
+struct EpiGradRT {
   static constexpr bool kUsesTmaStore = true;
-  static constexpr int kEpiWarps = 8;
-  static constexpr int kGroups = 2;
-  static constexpr int kColsW = 128;
+  static constexpr int kEpiWarps = W;                    // 8: 2 x 128 columns per TMEM lane quarter; 16: 4 x 64
+  static constexpr int kGroups = W / 4;
+  static constexpr int kColsW = 256 / kGroups;
+  static constexpr int kChunks = kColsW / 16;
+  static constexpr int kSlots = 4;                       // 16-prototype chunks of teacher probabilities in flight
 #ifndef DINOX_GRADR_STAGING_BUFS
 #define DINOX_GRADR_STAGING_BUFS 1
 #endif
@@ -653,24 +670,29 @@ struct EpiGradR {
     const int* trow;         // (M) row of qt / refs holding the entry's teacher
     const __half* qt;        // (teacher rows, ldq) un-normalised teacher probabilities
     int64_t ldq;
-    const float* refs;       // (2*num_n_tiles, ld_refs)
+    const float* refs;       // (kGroups*num_n_tiles, ld_refs)
     int64_t ld_refs;
     int alt_from;            // entries >= alt_from go to loss[1]
+    int run_rows;            // 1: contiguous prototype runs per M tile (consecutive tiles of a CTA share the row)
     float* db2_partial;      // (ceil(M/32), N) or NULL
     float* loss_partial;     // (gridDim.x * kEpiWarps * 2)
   };
   struct State {
     float loss_a = 0.f, loss_b = 0.f;
     float col[kColsW / 32];
-    // raw per-row values of the NEXT tile (no arithmetic until prologue)
+    // raw per-row values of the NEXT tile (loaded by fetch(); no arithmetic on them until prologue)
     float n_lse = 0.f, n_cw = 0.f, n_rb = 0.f;
-    int n_trow = 0, n_mtile = -1;
+    int n_trow = 0, n_mtile = -1, n_ntile = 0;
     // the tile being processed
-    float nl = 0.f, cwt = 0.f, rb = 0.f, ref = 0.f;
-    const __half* qrow = nullptr;
+    float nl = 0.f, cwt = 0.f, rb = 0.f;
     int cur_mtile = -1, cur_trow = 0;
     bool in_b = false;
-    uint32_t qb[4][8];       // teacher probabilities: 4 x 16 prototypes in flight
+    // teacher probabilities of the tile about to be processed: kSlots x 16 prototypes.  tile() refills the slots it
+    // has drained with the first chunks of the NEXT tile (its row is known from fetch()), so that their global-memory
+    // latency hides behind the rest of this tile instead of standing between two tiles
+    uint32_t qb[kSlots][8];
+    float ref_ahead = 0.f;   // granule maximum of the tile about to be processed
+    bool ahead = false;      // qb / ref_ahead already hold the next tile's values
     int flip = 0;
   };
   static __device__ __forceinline__ void finish(const Params& e, const CoreParams&, int epi_warp, int lane, State& st) {
@@ -684,7 +706,18 @@ struct EpiGradR {
   }
   template <int BN>
   struct Impl {
-    static_assert(BN == 256, "EpiGradR is written for 256-wide tiles");
+    static_assert(BN == 256 && (W == 8 || W == 16), "EpiGradR is written for 256-wide tiles and 8 or 16 epilogue warps");
+    static __device__ __forceinline__ void ldq(const __half* p, uint32_t (&r)[8], uint64_t pol) {
+#if DINOX_STREAM_EVICT_FIRST
+      ldg256_hint(p, r, pol);
+#else
+      ldg256(p, r);
+#endif
+    }
+    // first prototype of the granule this warp owns in tile n_tile, clamped into the padded row (ldq >= 256 * tiles)
+    static __device__ __forceinline__ const __half* granule(const Params& e, int trow, int n_tile, int grp) {
+      return e.qt + (int64_t)trow * e.ldq + (n_tile * BN + grp * kColsW);
+    }
     static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
                                                  State& st) {
       const int grp = epi_warp >> 2;
@@ -702,12 +735,8 @@ struct EpiGradR {
         st.n_rb = ok ? __ldg(e.rb2 + row) : 0.f;
         st.n_trow = ok ? __ldg(e.trow + row) : 0;
         st.n_mtile = tc.m_tile;
-      } else if (col0 < p.N) {
-        // same row, next granule: pull its 256 bytes of teacher probabilities towards L2 a whole tile ahead
-        const __half* nq = e.qt + (int64_t)st.n_trow * e.ldq + col0;
-        prefetch_l2(nq);
-        prefetch_l2(nq + 64);
       }
+      st.n_ntile = tc.n_tile;
     }
     static __device__ __forceinline__ void prologue(const Params& e, const CoreParams& p, TileCoord tc, int, int epi_warp, int lane,
                                                     uint8_t* smem, State& st) {
@@ -726,13 +755,13 @@ struct EpiGradR {
         st.in_b = row >= e.alt_from;
         st.cur_mtile = tc.m_tile;
       }
-      const int col0 = tc.n_tile * BN + grp * kColsW;
-      st.qrow = e.qt + (int64_t)st.cur_trow * e.ldq + col0;
-      st.ref = __ldg(e.refs + (int64_t)(tc.n_tile * kGroups + grp) * e.ld_refs + st.cur_trow);
-      // the first four 16-prototype chunks of teacher probabilities fly during the wait for the accumulators
-      // (col0 + 128 <= ldq: rows are padded to whole tiles)
+      if (!st.ahead) {   // first tile of this CTA: nobody fetched ahead (n_* describe THIS tile: fetch() ran for it)
+        const uint64_t pol = sm100::l2_policy_evict_first();
+        const __half* qrow = granule(e, st.n_trow, tc.n_tile, grp);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) ldg256(st.qrow + c * 16, st.qb[c]);
+        for (int c = 0; c < (kSlots < kChunks ? kSlots : kChunks); ++c) ldq(qrow + c * 16, st.qb[c], pol);
+        st.ref_ahead = __ldg(e.refs + (int64_t)(tc.n_tile * kGroups + grp) * e.ld_refs + st.n_trow);
+      }
       __syncwarp();
     }
 
@@ -742,9 +771,24 @@ struct EpiGradR {
       const int q = epi_quarter();
       const int grp = epi_warp >> 2;
       const int row0 = tc.m_tile * BM + q * 32;
+      const uint64_t pol = sm100::l2_policy_evict_first();
       const uint32_t ts = tmem_acc + ((uint32_t)(q * 32) << 16) + grp * kColsW;
+      // By now fetch() has run for the next tile (if there is one): n_trow / n_mtile / n_ntile name it.  Without a next
+      // tile they still name this one - the look-ahead loads below then re-read valid memory and are never used.
+      const __half* qrow = granule(e, st.cur_trow, tc.n_tile, grp);
+      const __half* qnext = granule(e, st.n_trow, st.n_ntile, grp);
       // q' = qt * nsc with nsc = -(cw/tau_s) * 2^(ref - rb); dead entries (cw = 0) must not see 0 * inf
-      const float nsc = (st.cwt != 0.f) ? -(st.cwt * fast_ex2(st.ref - st.rb)) : 0.f;
+      const float nsc = (st.cwt != 0.f) ? -(st.cwt * fast_ex2(st.ref_ahead - st.rb)) : 0.f;
+      // ... and the next tile's granule maximum starts its trip now: a whole tile of lead
+      st.ref_ahead = __ldg(e.refs + (int64_t)(st.n_ntile * kGroups + grp) * e.ld_refs + st.n_trow);
+      if (e.run_rows && st.n_mtile == tc.m_tile) {
+        // contiguous-run schedule: the tile after next continues this thread's row -> pull its granule towards L2
+        const int col2 = (st.n_ntile + 1) * BN + grp * kColsW;
+        if (col2 < p.N) {
+          prefetch_l2(qnext + BN);
+          if (kColsW > 64) prefetch_l2(qnext + BN + 64);
+        }
+      }
       const uint64_t as2 = pack2(e.as2, e.as2), nl2 = pack2(st.nl, st.nl), cw2 = pack2(st.cwt, st.cwt), nsc2 = pack2(nsc, nsc);
       uint64_t lacc = pack2(0.f, 0.f);
       uint8_t* wbase = smem + epi_warp * (kBufs * 4096);
@@ -754,12 +798,12 @@ struct EpiGradR {
       sm100::tmem_ld16_nowait(ts, sa);
       sm100::tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < kColsW / 16; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
         uint32_t (&cur)[16] = (c & 1) ? sb : sa;
         uint32_t (&nxt)[16] = (c & 1) ? sa : sb;
-        if (c + 1 < kColsW / 16) sm100::tmem_ld16_nowait(ts + (c + 1) * 16, nxt);
+        if (c + 1 < kChunks) sm100::tmem_ld16_nowait(ts + (c + 1) * 16, nxt);
         sm100::pin16(cur);
-        uint32_t (&qv)[8] = st.qb[c & 3];
+        uint32_t (&qv)[8] = st.qb[c % kSlots];
         const float* cb = buf + c * 16;
         uint32_t packed[8];
 #pragma unroll
@@ -783,7 +827,10 @@ struct EpiGradR {
             packed[j / 2 + h] = *reinterpret_cast<uint32_t*>(&hh);
           }
         }
-        if (c + 4 < kColsW / 16) ldg256(st.qrow + (c + 4) * 16, qv);   // refill the slot just consumed
+        // refill the slot just drained: with a later chunk of this tile, or - once those are all in flight - with
+        // chunk c + kSlots - kChunks of the next tile
+        if (c + kSlots < kChunks) ldq(qrow + (c + kSlots) * 16, qv, pol);
+        else ldq(qnext + (c + kSlots - kChunks) * 16, qv, pol);
         if ((c & 3) == 0) {   // the staging buffer about to be refilled must no longer be read by the previous store
           wbuf = wbase + st.flip * 4096;
           if (lane == 0) sm100::tma_store_wait_read<kBufs - 1>();
@@ -797,7 +844,11 @@ struct EpiGradR {
           __syncwarp();
           const int col0 = tc.n_tile * BN + grp * kColsW + (c >> 2) * 64;
           if (lane == 0) {
+#if DINOX_STREAM_EVICT_FIRST
+            if (row0 < p.M && col0 < p.N) sm100::tma_store_3d_hint(tmC, wbuf, col0, row0, 0, pol);
+#else
             if (row0 < p.M && col0 < p.N) sm100::tma_store_3d(tmC, wbuf, col0, row0, 0);
+#endif
             sm100::tma_store_commit();   // always: wait_read<kBufs-1> counts groups
           }
           if (e.db2_partial) {
@@ -822,14 +873,17 @@ struct EpiGradR {
           }
           if (kBufs > 1) st.flip ^= 1;
         }
-        if (c + 1 < kColsW / 16) sm100::tmem_wait_ld();
+        if (c + 1 < kChunks) sm100::tmem_wait_ld();
       }
+      st.ahead = true;
       float l0, l1;
       unpack2(lacc, l0, l1);
       if (st.in_b) st.loss_b -= l0 + l1; else st.loss_a -= l0 + l1;   // the accumulator holds -cwt q u
     }
   };
 };
+using EpiGradR = EpiGradRT<DINOX_RB_EPI_WARPS>;
+template <bool kRun> using EpiTeachQ = EpiTeachQT<kRun, DINOX_RB_EPI_WARPS>;
 
 // =============================================================================================
 // Epilogue 3 (pass 2, "transposed"): TMEM lanes = prototypes k, columns = entries e.
@@ -1339,6 +1393,18 @@ static bool resa_enabled(int family, int64_t K) {
   return (v & family) != 0 && K <= kResKBlocks * BK;
 }
 
+// Schedule of the two read-back kernels (DINOX_RB_SCHED bit mask: 1 = teacher pass, 2 = pass 2): bit set = W2 tile
+// resident + column sweep over the M tiles; clear = rows of an M tile resident + contiguous prototype runs (the pass-1
+// schedule).  Measured at C2 (ms): teacher 0.355 (columns) / 0.384 (runs); pass 2 0.654 (columns) / 0.589 (runs).
+#ifndef DINOX_RB_SCHED_DEFAULT
+#define DINOX_RB_SCHED_DEFAULT 1
+#endif
+static bool readback_cols(int which, int64_t K) {
+  static int v = -1;
+  if (v < 0) v = env_flag("DINOX_RB_SCHED", DINOX_RB_SCHED_DEFAULT);
+  return (v & which) != 0 && K <= kResKBlocks * BK;
+}
+
 #ifndef DINOX_EXP_NSPLIT256
 #define DINOX_EXP_NSPLIT256 1   // experiment knob: 2 issues the 256-wide tile as two N=128 MMAs (A read twice from smem)
 #endif
@@ -1556,7 +1622,12 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
 }
 
 /* ---- teacher, one pass: statistics + un-normalised fp16 probabilities (see EpiTeachQT) ---- */
-size_t dinox_head_teacher_workspace_bytes(int64_t rows, int64_t K) { return dinox_head_stats_workspace_bytes(rows, K); }
+size_t dinox_head_teacher_workspace_bytes(int64_t rows, int64_t K) {
+  if (rows <= 0 || K <= 0) return 0;
+  return (size_t)rows * EpiTeachQ<false>::kGroups * ((K + 255) / 256 + 1) * sizeof(float2);   // + 1: run-mode slot bound
+}
+/* granules (rows of `refs`) per 256-prototype tile: 128 / 64 prototypes per granule with 8 / 16 epilogue warps */
+int dinox_head_teacher_granules_per_tile(void) { return EpiTeachQ<false>::kGroups; }
 
 int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D, int64_t ldh, int64_t ldw,
                        float inv_tau, const float* col2, const float* col2_alt, int64_t alt_from_row, void* qt,
@@ -1576,31 +1647,43 @@ int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, i
   od.ptr = qt; od.is_bf16 = 1; od.ld = ldq; od.slab_stride = rows * ldq; od.slabs = 1; od.cols = num_n * 256;
   const int alt_mtile = col2_alt ? (int)(alt_from_row / BM) : (1 << 30);
   const bool cl2 = rows > BM && pair_enabled(kPairStats);
-  if (resa_enabled(kPairStats, D)) {
-    const int cl = cl2 ? 2 : 1;
+  if (cl2 && readback_cols(1, D)) {
+    // W2 tile resident (a CTA of a pair holds half of it: 96 KB), every cluster sweeps the M tiles of its prototype tile in step with the others: W2 is read
+    // from HBM exactly once per launch (the probability stream would evict it from L2 between two M-tile runs)
+    EpiTeachQ<false>::Params ep{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), 1, 1, 1, refs, ld_refs};
+    rc = launch<256, 1, 1, 2, EpiTeachQ<false>, kResB>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher<pair,resB>");
+    if (rc) return rc;
+    if (lse_nat || lse2) {
+      stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows,
+                                                                         EpiTeachQ<false>::kGroups * (int)num_n, lse_nat, lse2);
+      return check_launch("stats_merge_kernel", stream);
+    }
+    return DINOX_OK;
+  }
+  if (cl2 && resa_enabled(kPairStats, D)) {   // (a lone CTA has no room for a resident operand beside the staging buffers)
+    const int cl = 2;
     const int64_t num_m_super = ((rows + BM - 1) / BM + cl - 1) / cl, super = num_m_super * num_n;
     const int ncl = launch_grid(super, cl) / cl;
     const int per = (int)((super + ncl - 1) / ncl);
     const int run_slots = (int)((num_n + per - 1) / per) + 1;
-    EpiTeachQT<true>::Params er{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), cl, per,
+    EpiTeachQ<true>::Params er{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), cl, per,
                                 run_slots, refs, ld_refs};
-    rc = cl2 ? launch<256, 1, 1, 2, EpiTeachQT<true>, kResA>(a, b, nullptr, nullptr, rows, K, D, 0, er, od, stream, "head_teacher<pair,resA>")
-             : launch<256, 1, 1, 1, EpiTeachQT<true>, kResA>(a, b, nullptr, nullptr, rows, K, D, 0, er, od, stream, "head_teacher<resA>");
+    rc = launch<256, 1, 1, 2, EpiTeachQ<true>, kResA>(a, b, nullptr, nullptr, rows, K, D, 0, er, od, stream, "head_teacher<pair,resA>");
     if (rc) return rc;
     if (lse_nat || lse2) {
-      stats_merge_run_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(er.partial, rows, 2, run_slots, (int)num_n, per, cl,
-                                                                                 lse_nat, lse2);
+      stats_merge_run_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(er.partial, rows, EpiTeachQ<true>::kGroups, run_slots,
+                                                                                 (int)num_n, per, cl, lse_nat, lse2);
       return check_launch("stats_merge_run_kernel", stream);
     }
     return DINOX_OK;
   }
-  EpiTeachQT<false>::Params ep{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), 1, 1, 1, refs, ld_refs};
-  rc = cl2 ? launch<256, 1, 1, 2, EpiTeachQT<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher<pair>")
-           : launch<256, 1, 1, 1, EpiTeachQT<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher");
+  EpiTeachQ<false>::Params ep{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), 1, 1, 1, refs, ld_refs};
+  rc = cl2 ? launch<256, 1, 1, 2, EpiTeachQ<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher<pair>")
+           : launch<256, 1, 1, 1, EpiTeachQ<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher");
   if (rc) return rc;
   if (lse_nat || lse2) {
-    stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows, 2 * (int)num_n,
-                                                                       lse_nat, lse2);
+    stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows,
+                                                                       EpiTeachQ<false>::kGroups * (int)num_n, lse_nat, lse2);
     return check_launch("stats_merge_kernel", stream);
   }
   return DINOX_OK;
@@ -1638,9 +1721,11 @@ int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int
   od.ptr = G; od.is_bf16 = 1; od.ld = ldg; od.slab_stride = E * ldg; od.slabs = 1;
   const bool cl2 = E > BM && pair_enabled(kPairGrad);
   const int cl = cl2 ? 2 : 1;
-  if (resa_enabled(kPairStats, D))   // the entries of an M tile resident, prototype tiles walked in one contiguous run
-    rc = cl2 ? launch<256, 1, 1, 2, EpiGradR, kResA>(a, b, nullptr, nullptr, E, K, D, 0, ep, od, stream, "head_grad2<pair,resA>")
-             : launch<256, 1, 1, 1, EpiGradR, kResA>(a, b, nullptr, nullptr, E, K, D, 0, ep, od, stream, "head_grad2<resA>");
+  ep.run_rows = (cl2 && !readback_cols(2, D) && resa_enabled(kPairStats, D)) ? 1 : 0;
+  if (cl2 && readback_cols(2, D))   // W2 tile resident, clusters sweep the entry tiles in step (W2 read from HBM once)
+    rc = launch<256, 1, 1, 2, EpiGradR, kResB>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair,resB>");
+  else if (cl2 && resa_enabled(kPairStats, D))   // the entries of an M tile resident, prototype tiles walked in one contiguous run
+    rc = launch<256, 1, 1, 2, EpiGradR, kResA>(a, b, nullptr, nullptr, E, K, D, 0, ep, od, stream, "head_grad2<pair,resA>");
   else
     rc = cl2 ? launch<256, 1, 1, 2, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair>")
              : launch<256, 1, 1, 1, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2");

@@ -485,6 +485,7 @@ class _EntryPlan:
         self.ent_t_pad = t(etp, torch.int64)                           # -1 = padding entry
         self.trow = t([max(r, 0) for r in etp], torch.int32)           # row of qt / refs (padding -> row 0, weight 0)
         self.cls_rows_pad = t(list(range(Mt)) + [-1] * (self.Mt_pad - Mt), torch.int64)
+        self.row_counts = t([float(Mt), float(Mm), 0.0, 0.0], torch.float32)   # teacher CLS rows, masked patch rows
 
 
 _PLANS: Dict[Tuple, _EntryPlan] = {}
@@ -540,43 +541,23 @@ def _accumulate_grad(p: torch.Tensor, fn) -> None:
         fn(p.grad, True)
 
 
-def _update_centres(hsum, hsum_work, pg, Mt, Mm, w2t, b2t, loss_mod, center_patch, patch_momentum, cls: bool) -> None:
+def _update_centres(stats, work, w2t, b2t, loss_mod, center_patch, patch_momentum, cls: bool, patch: bool) -> None:
     """Centre EMA of the fused path: mean teacher logits = W2t . mean(h_t) + b2t (one GEMV over W2t for the CLS
-    and the patch centre together) from the all-reduced activation sums.  hsum rows: [CLS (if cls)] [patch (if Mm)]."""
-    if hsum is None:
+    and the patch centre together).  `stats` = (hsum (n, D), counts (n,)): the all-reduced activation sums and row
+    counts of [CLS rows (if cls)] [masked patch rows (if patch)] - the division by the GLOBAL count happens on the
+    device, so ranks may mask different numbers of tokens."""
+    if stats is None:
         return
-    w = _world(pg)
-    if hsum_work is not None:
-        hsum_work.wait()
-    alphas = ([1.0 / (Mt * w)] if cls else []) + ([1.0 / (Mm * w)] if Mm else [])
-    mean_logits = ops.gemv_bf16_multi(w2t, hsum, alphas, b2t, 1.0)
+    hsum, counts = stats
+    if work is not None:
+        work.wait()
+    mean_logits = ops.gemv_bf16_multi(w2t, hsum, [1.0] * hsum.shape[0], b2t, 1.0, divisors=counts)
     i = 0
     if cls:
         ops.center_ema_(loss_mod.center, mean_logits[0], 1, loss_mod.center_momentum)
         i = 1
-    if Mm:
+    if patch:
         ops.center_ema_(center_patch, mean_logits[i], 1, patch_momentum)
-
-
-_MM_CHECKED: Dict[Tuple, bool] = {}
-
-
-def _check_equal_masked_rows(Mm: int, pg, device) -> None:
-    """The patch-centre mean divides the all-reduced activation sum by Mm * world: every rank must mask the same
-    number of tokens.  Verified once per (count, group) with one tiny all-gather, never inside a graph capture."""
-    w = _world(pg)
-    key = (Mm, id(pg) if pg is not True else 0, w)
-    if w == 1 or key in _MM_CHECKED or torch.cuda.is_current_stream_capturing():
-        return
-    import torch.distributed as dist
-    mine = torch.tensor([Mm], dtype=torch.int64, device=device)
-    allm = [torch.empty_like(mine) for _ in range(w)]
-    dist.all_gather(allm, mine, group=_group(pg))
-    counts = [int(x.item()) for x in allm]
-    if any(c != Mm for c in counts):
-        raise ValueError(f"fused_head_dino_loss: ranks mask different numbers of patch tokens {counts}; the patch "
-                         "centre assumes equal counts (pad the masks or use equal mask ratios per rank)")
-    _MM_CHECKED[key] = True
 
 
 class _FusedHeadLoss(torch.autograd.Function):
@@ -599,7 +580,6 @@ class _FusedHeadLoss(torch.autograd.Function):
         if Mm:
             sp2 = student_patch.detach() if patch_index is None else student_patch.detach().view(-1, D)
             tp2 = teacher_patch.detach() if patch_index is None else teacher_patch.detach().view(-1, D)
-            _check_equal_masked_rows(Mm, pg, dev)
         plan = _entry_plan(B, Vg, V, Mm, dev)
         readback = pass2_mode() == "readback"
         Mt_pad = plan.Mt_pad if readback else Mt        # row of the first masked patch in the teacher matrices
@@ -631,14 +611,21 @@ class _FusedHeadLoss(torch.autograd.Function):
             # centre statistics: batch-mean teacher logits are W2t . mean(h_t) + b2t by
             # linearity, so the data-parallel payload is the D-vector sum(h_t) (CLS and masked-patch rows
             # in ONE all-reduce), launched now so that its latency hides behind the pass-1/pass-2 GEMMs
-            hsum = hsum_work = None
+            stats = hsum_work = None
             if centre_cls or centre_patch:
-                hsum = torch.empty(int(centre_cls) + int(centre_patch), D, dtype=torch.float32, device=dev)
+                nv = int(centre_cls) + int(centre_patch)
+                # [nv x D activation sums | nv row counts] in one buffer = ONE all-reduce; the counts make the mean
+                # exact when ranks hold different numbers of rows (masked tokens)
+                sbuf = torch.empty(nv * D + 4, dtype=torch.float32, device=dev)
+                hsum, counts = sbuf[:nv * D].view(nv, D), sbuf[nv * D:nv * D + nv]
                 if centre_cls:
                     ops.cols_sum(ht[:Mt], out=hsum[0])
                 if centre_patch:
                     ops.cols_sum(ht[Mt_pad:], out=hsum[int(centre_cls)])
-                hsum_work = allreduce_sum_async(hsum, pg)
+                i0 = 0 if centre_cls else 1
+                ops.axpb(plan.row_counts[i0:i0 + nv], 1.0, 0.0, out=counts)
+                hsum_work = allreduce_sum_async(sbuf, pg)
+                stats = (hsum, counts)
             b2t = t_head[2].bias.detach()
             center = loss_mod.center.reshape(-1)
             rb2_t = torch.empty(Mt_pad + Mm, dtype=torch.float32, device=dev)
@@ -672,9 +659,8 @@ class _FusedHeadLoss(torch.autograd.Function):
                 # centre updates here instead of after pass 2: ct2 / ct2_patch above already hold the OLD centres
                 # (scripts/phase5_big_run.py:719 - the loss sees the centre of the previous step), and the GEMV over
                 # W2t runs beside the student branch instead of after pass 2
-                _update_centres(hsum, hsum_work, pg, Mt, Mm if centre_patch else 0, w2t, b2t, loss_mod, center_patch,
-                                patch_momentum, centre_cls)
-                hsum = None
+                _update_centres(stats, hsum_work, w2t, b2t, loss_mod, center_patch, patch_momentum, centre_cls, centre_patch)
+                stats = None
         # ---- student: the same on the current stream
         xs = torch.empty(Ms + Mm, D, dtype=torch.bfloat16, device=dev)
         ops.gather_cast_bf16(student_cls.detach(), None, xs[:Ms])
@@ -712,8 +698,7 @@ class _FusedHeadLoss(torch.autograd.Function):
                 gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
                                          lse2_e, rb2_e, cw, losses, want_db2=need_grad)
         # ---- centre updates AFTER the loss (scripts/phase5_big_run.py:719)
-        _update_centres(hsum, hsum_work, pg, Mt, Mm if centre_patch else 0, w2t, b2t, loss_mod, center_patch,
-                        patch_momentum, centre_cls)
+        _update_centres(stats, hsum_work, w2t, b2t, loss_mod, center_patch, patch_momentum, centre_cls, centre_patch)
         if need_grad:
             ctx.save_for_backward(xs, a_s, hs_e, gt, db2p, w1s, w2s)
             ctx.plan = plan
@@ -838,6 +823,38 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
                                          masks_weight, teacher_head, dino_loss, center_patch, cfg, patch_index,
                                          params if grads_in_place else None)
     return {"loss": total, "loss_dino": losses[0], "loss_ibot": losses[1]}
+
+
+class FusedLossHead(nn.Module):
+    """The fused path as ONE module, so that wrappers which hook `forward` see it - in particular
+    `torch.nn.parallel.DistributedDataParallel(FusedLossHead(...))`: DDP arms its gradient reducer in `forward`,
+    and the head gradients reach it through autograd (default `grads_in_place=False`), i.e. the head's dW1/db1/
+    dW2/db2 are all-reduced like every other parameter (gradient all-reduce is the host's DDP job).
+
+    Holds the student head (trainable), the teacher head (frozen; update it with `_ema_update`), the DINOLoss
+    state (`center`) and the iBOT patch centre.  `forward` returns the differentiable total (tensor) - DDP wants
+    a tensor output - and keeps the component losses in `last`."""
+
+    def __init__(self, student_head: nn.Sequential, teacher_head: nn.Sequential, dino_loss: DINOLoss,
+                 ibot_weight: float = 1.0, grads_in_place: bool = False) -> None:
+        super().__init__()
+        self.student_head, self.teacher_head, self.dino_loss = student_head, teacher_head, dino_loss
+        for p in self.teacher_head.parameters():
+            p.requires_grad_(False)
+        self.register_buffer("center_patch", torch.zeros_like(dino_loss.center))
+        self.ibot_weight, self.grads_in_place = ibot_weight, grads_in_place
+        self.last: Dict[str, torch.Tensor] = {}
+
+    def forward(self, student_cls, teacher_cls, student_temp: float, teacher_temp: float, student_patch=None,
+                teacher_patch=None, masks_weight=None, patch_index=None) -> torch.Tensor:
+        out = fused_head_dino_loss(student_cls, teacher_cls, self.student_head, self.teacher_head, self.dino_loss,
+                                   student_temp, teacher_temp, student_patch=student_patch, teacher_patch=teacher_patch,
+                                   masks_weight=masks_weight,
+                                   center_patch=self.center_patch if student_patch is not None else None,
+                                   ibot_weight=self.ibot_weight, patch_index=patch_index,
+                                   grads_in_place=self.grads_in_place)
+        self.last = {k: v.detach() for k, v in out.items()}
+        return out["loss"]
 
 
 class _CombineLosses(torch.autograd.Function):

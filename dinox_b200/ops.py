@@ -258,12 +258,17 @@ def head_grad(w2s, w2t, hs_e, ht_e, inv_tau_s, inv_tau_t, cs2, ct2, ct2_alt, alt
     return gt, db2p
 
 
+def teacher_granules_per_tile() -> int:
+    """granules (prototype groups sharing one reference exponent) per 256-prototype tile: 2 or 4"""
+    return int(_ext.lib().dinox_head_teacher_granules_per_tile())
+
+
 def teacher_buffers(rows: int, K: int, device):
     """(qt, refs) of dinox_head_teacher: fp16 probabilities with rows padded to whole 256-prototype tiles,
     and the per-(128-prototype granule, row) maxima."""
     n_tiles = (K + 255) // 256
     qt = torch.empty(rows, n_tiles * 256, dtype=torch.float16, device=device)
-    refs = torch.empty(2 * n_tiles, rows, dtype=torch.float32, device=device)
+    refs = torch.empty(teacher_granules_per_tile() * n_tiles, rows, dtype=torch.float32, device=device)
     return qt, refs
 
 
@@ -271,8 +276,9 @@ def head_teacher(h: torch.Tensor, w2: torch.Tensor, inv_tau: float, col2: Option
                  col2_alt: Optional[torch.Tensor] = None, alt_from_row: int = 0,
                  qt: Optional[torch.Tensor] = None, refs: Optional[torch.Tensor] = None,
                  out_log2: Optional[torch.Tensor] = None):
-    """Teacher in one pass: returns (qt (rows, K_pad) fp16, refs (2*ceil(K/256), rows) fp32, lse2 (rows))
-    with softmax(h @ w2^T * inv_tau + col2/log2e)[i, k] = qt[i, k] * 2^(refs[k // 128, i] - lse2[i])."""
+    """Teacher in one pass: returns (qt (rows, K_pad) fp16, refs (granules, rows) fp32, lse2 (rows)) with
+    softmax(h @ w2^T * inv_tau + col2/log2e)[i, k] = qt[i, k] * 2^(refs[k // gw, i] - lse2[i]),
+    gw = 256 // teacher_granules_per_tile() prototypes per granule."""
     _chk_cuda(h, w2, col2, col2_alt)
     rows, D = h.shape
     K = w2.shape[0]
@@ -412,14 +418,17 @@ def gemv_bf16(w: torch.Tensor, x: torch.Tensor, alpha: float = 1.0, bias: Option
 
 
 def gemv_bf16_multi(w: torch.Tensor, xs: torch.Tensor, alphas: Sequence[float], bias: Optional[torch.Tensor] = None,
-                    beta: float = 1.0) -> torch.Tensor:
-    """xs: (nvec, D) fp32 -> out (nvec, K): alphas[v] * W @ xs[v] + beta * bias, one pass over W."""
+                    beta: float = 1.0, divisors: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """xs: (nvec, D) fp32 -> out (nvec, K): alphas[v] / divisors[v] * W @ xs[v] + beta * bias, one pass over W
+    (divisors: optional (nvec,) fp32 DEVICE tensor)."""
     K, D = w.shape
     nvec = xs.shape[0]
     assert xs.is_contiguous() and xs.shape[1] == D and len(alphas) == nvec
+    assert divisors is None or (divisors.dtype == torch.float32 and divisors.numel() == nvec and divisors.is_contiguous())
     out = torch.empty(nvec, K, dtype=torch.float32, device=w.device)
     al = (ctypes.c_float * nvec)(*[float(a) for a in alphas])
-    _ext.call("dinox_gemv_bf16_multi", _p(w), _rowmajor(w), _p(xs), nvec, K, D, al, _p(bias), float(beta), _p(out), _stream())
+    _ext.call("dinox_gemv_bf16_multi", _p(w), _rowmajor(w), _p(xs), nvec, K, D, al, _p(divisors), _p(bias), float(beta),
+              _p(out), _stream())
     return out
 
 

@@ -190,8 +190,9 @@ DINOX_API int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE,
 /* ------------------------------------------------------------------------------------------
  * Teacher in ONE pass (default fused path): the statistics of dinox_head_stats PLUS the teacher
  * probabilities themselves in un-normalised 16-bit form, so that pass 2 never recomputes a teacher
- * logit.  For x[i,k] = (H.W2^T)[i,k]*inv_tau*log2e + col2[k] and every 128-prototype granule g:
- *   refs[g][i] = max_{k in g} x[i,k]                       (log2 units; (2*ceil(K/256), ld_refs) fp32)
+ * logit.  For x[i,k] = (H.W2^T)[i,k]*inv_tau*log2e + col2[k] and every granule g of 128 or 64 prototypes
+ * (dinox_head_teacher_granules_per_tile()):
+ *   refs[g][i] = max_{k in g} x[i,k]                       (log2 units; (granules, ld_refs) fp32)
  *   qt[i,k]    = fp16( 2^(x[i,k] - refs[g(k)][i]) )        ((rows, ldq) fp16, ldq >= 256*ceil(K/256);
  *                                                            columns in [K, ldq) are written as 0)
  *   lse2[i]    = log2 sum_k 2^x[i,k]  (and/or the natural-log lse_nat), from the unrounded values
@@ -199,6 +200,9 @@ DINOX_API int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE,
  * Rows of M tiles at or beyond alt_from_row (multiple of 128) use col2_alt (iBOT patch centre); NULL = none.
  * ------------------------------------------------------------------------------------------ */
 DINOX_API size_t dinox_head_teacher_workspace_bytes(int64_t rows, int64_t K);
+/* granules per 256-prototype tile (2: 128 prototypes each, or 4: 64 each - a build constant); refs has
+ * granules_per_tile * ceil(K/256) rows and granule g(k) = k / (256 / granules_per_tile) */
+DINOX_API int dinox_head_teacher_granules_per_tile(void);
 DINOX_API int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D,
                                  int64_t ldh, int64_t ldw, float inv_tau, const float* col2,
                                  const float* col2_alt, int64_t alt_from_row, void* qt, int64_t ldq,
@@ -281,10 +285,11 @@ DINOX_API int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int6
 DINOX_API int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64_t D, float alpha,
                               const float* bias, float beta, float* out, dinox_stream_t stream);
 /* nvec (1..4) vectors X (nvec, D) against the same matrix in ONE pass over W: out (nvec, K),
- * out[v][k] = alphas_host[v] * sum_d W[k,d] X[v,d] + beta * bias[k]  (CLS and iBOT centre means together) */
+ * out[v][k] = alphas_host[v] / divisors_dev[v] * sum_d W[k,d] X[v,d] + beta * bias[k]  (CLS and iBOT centre means
+ * together; divisors_dev = optional DEVICE vector, e.g. the all-reduced row counts, NULL = 1) */
 DINOX_API int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
-                                    const float* alphas_host, const float* bias, float beta, float* out,
-                                    dinox_stream_t stream);
+                                    const float* alphas_host, const float* divisors_dev, const float* bias,
+                                    float beta, float* out, dinox_stream_t stream);
 /* dst[i] (+)= scale*(*scale_dev) * sum_{s<slabs} src[s*slab_stride + i]: fixed-order reduction of split-K slabs */
 DINOX_API int dinox_sum_slabs(const float* src, int slabs, int64_t slab_stride, int64_t n, const float* scale_dev,
                               float scale, float* dst, int accumulate, dinox_stream_t stream);

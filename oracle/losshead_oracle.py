@@ -283,7 +283,11 @@ class LossHeadOracle:
     def __init__(self, student: HeadParams, teacher: HeadParams, out_dim: int,
                  center_momentum: float = 0.999, n_global: int = 2, n_local: int = 0,
                  teacher_mode: str = "center", sk_iters: int = 3, gram_weight: float = 1.0,
-                 ibot_weight: float = 1.0, policy: str = "fp32"):
+                 ibot_weight: float = 1.0, policy: str = "fp32", patch_teacher_mode: Optional[str] = None):
+        # patch_teacher_mode: normalisation of the iBOT (masked-patch) teacher rows; None = same as teacher_mode.
+        # "center" with teacher_mode="sinkhorn" is what the CUDA path implements: Sinkhorn-Knopp on the CLS rows,
+        # softmax-centring with the patch centre (kept updated) on the patch rows.
+        self.patch_teacher_mode = patch_teacher_mode or teacher_mode
         self.student, self.teacher = student, teacher
         self.center = torch.zeros(1, out_dim)
         self.center_patch = torch.zeros(1, out_dim)
@@ -310,7 +314,7 @@ class LossHeadOracle:
                 tp_out = head_forward(teacher_patch, self.teacher, self.policy)
             n_images = teacher_cls.shape[0]
             loss_ibot = ibot_patch_loss(sp_out, tp_out, self.center_patch, student_temp, teacher_temp,
-                                        masks_weight, n_images, self.teacher_mode, self.sk_iters)
+                                        masks_weight, n_images, self.patch_teacher_mode, self.sk_iters)
             loss = loss + self.ibot_weight * loss_ibot
             out["loss_ibot"] = loss_ibot.detach()
         if student_tok is not None:
@@ -319,10 +323,11 @@ class LossHeadOracle:
             out["loss_gram"] = loss_gram.detach()
         out["loss"] = loss.detach()
         (loss / accum).backward()
-        if update_center and self.teacher_mode == "center":
+        if update_center:
             with torch.no_grad():
-                self.center = center_update(self.center, t_out, self.center_momentum)
-                if student_patch is not None:
+                if self.teacher_mode == "center":
+                    self.center = center_update(self.center, t_out, self.center_momentum)
+                if student_patch is not None and self.patch_teacher_mode == "center":
                     self.center_patch = center_update(self.center_patch, tp_out, self.center_momentum)
         return out
 
