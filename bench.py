@@ -296,6 +296,35 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def per_rank(ms: float):
+        """[ms of every rank] (the same list on every rank)"""
+        if world == 1:
+            return [ms]
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
+
+    def replay_leg(st, feats_like, steps, warmup):
+        """graph-replay timing of another configuration (inputs resident): ms per micro-step, max over ranks"""
+        slots = st.static_inputs(feats_like, slots=1)
+        for k, v in feats_like.items():
+            slots[0][k].detach().copy_(v)
+        st.capture(0)
+        for _ in range(warmup):
+            st.micro_step_graph(0)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            st.micro_step_graph(0)
+        b.record()
+        barrier()
+        mine = a.elapsed_time(b) / steps
+        ranks = per_rank(mine)
+        st._graphs.clear()
+        return max(ranks), ranks
+
     use_graph = not args.no_graph
     # ---------------- leg 0: eager, per-kernel CUDA-event timers (roofline of the dominant kernel) --------
     resident = {k: v.to(dev) for k, v in host.items()}
@@ -351,11 +380,13 @@ def run_ours(args):
         e1.record()
         barrier()
         clocks = sampler.stop()
-        ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        rank_ms = [x / args.steps for x in per_rank(e0.elapsed_time(e1))]
+        ms_per_step = max(rank_ms)
         launches = step.launches_per_graph * args.steps + args.steps // args.accum
     else:
         clocks = sampler.stop()
         ms_per_step = eager_ms_per_step
+        rank_ms = [ms_per_step]
     value = crops_per_step / (ms_per_step * 1e-3)
     loss_val = float(out["loss_total"].item())
 
@@ -416,17 +447,53 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = crops_per_step / (e2e_ms * 1e-3)
 
-    def finish_rank():
-        """Multi-rank teardown without destroy_process_group(): with NCCL collectives captured in CUDA
-        graphs the communicator teardown was seen to hang; drop the graphs, synchronise every rank, exit hard."""
+    # ---------------- extra: the other multi-GPU configurations of BASELINE.json at this N ----------------
+    # C3 (global batch 256 over 8 GPUs = 32 per GPU, Sinkhorn-Knopp CLS teacher: three all-gathered LSE exchanges per
+    # step) and C4 (ViT-L/16, D = 1024, 32 per GPU), per-GPU shapes fixed like the headline (weak scaling).  For C3 the
+    # same shapes are replayed WITHOUT the process group as well: the difference is what the collectives cost.
+    extra = None
+    if use_graph and not args.no_extra and args.config == "C2":
+        extra = {}
         step._graphs.clear()
+        for name, cfgname, mode in (("C3", "C3", "sinkhorn"), ("C4", "C4", "center")):
+            shx = synth.LossHeadShapes(**synth.CONFIGS[cfgname])
+            fx = {k: v.to(dev) for k, v in synth.feature_batch(shx, synth.seeded_generator(3, rank), patches_from_tokens=True).items()}
+            stx = LossHeadStep(shx, dev, accum=args.accum, process_group=pg, teacher_mode=mode)
+            ms_x, ranks_x = replay_leg(stx, fx, args.extra_steps, args.warmup)
+            rec = {"workload": f"{cfgname} per-GPU shapes: batch {shx.batch}, D={shx.dim}, K={shx.out_dim}, teacher {mode}, "
+                               f"{shx.masked_rows} masked rows, accum {args.accum}, EMA of {stx.n_params / 1e6:.1f} M params",
+                   "ms_per_step": ms_x, "value": shx.student_rows * world / (ms_x * 1e-3), "unit": "crops/s",
+                   "per_rank_ms": {"min": min(ranks_x), "median": statistics.median(ranks_x), "max": max(ranks_x)},
+                   "steps": args.extra_steps}
+            if world > 1 and name == "C3":
+                del stx
+                st0 = LossHeadStep(shx, dev, accum=args.accum, process_group=None, teacher_mode=mode)
+                ms_0, _ = replay_leg(st0, fx, args.extra_steps, args.warmup)
+                rec["ms_per_step_without_collectives"] = ms_0
+                rec["exposed_collective_ms"] = ms_x - ms_0
+                stx = st0
+            extra[name] = rec
+            del stx, fx
+            torch.cuda.empty_cache()
+
+    def finish_rank():
+        """Teardown: every captured graph (they hold NCCL kernels of the communicator) is destroyed and the device
+        idle on EVERY rank before the process group goes away; a watchdog turns a hung communicator teardown into a
+        clean exit instead of a stuck job."""
+        import gc
+        step._graphs.clear()
+        gc.collect()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
             sys.stderr.flush()
             _OUT.flush()
-            os._exit(0)
+            guard = threading.Timer(30.0, lambda: os._exit(0))
+            guard.daemon = True
+            guard.start()
+            dist.destroy_process_group()
+            guard.cancel()
 
     if rank != 0:
         finish_rank()
@@ -487,9 +554,18 @@ def run_ours(args):
     step_alg_tf = sh.flops() / (ms_per_step * 1e-3) / 1e12
     step_peak = peaks["tf_burst"] if (clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.98 * clocks["sm_max_mhz"]) else peaks["tf_sustained"]
     kernels_gbs = {k: alg_bytes[k] / (kt[k] * 1e-3) / 1e9 for k in kt if k in alg_bytes}
+    # The roofline that binds the dominant kernel: tensor pipe (algorithmic FLOPs / measured cuBLAS peak) or HBM
+    # (algorithmic bytes / measured copy bandwidth), whichever fraction is larger; both are printed.
+    frac_tensor = ach / peak_tf
+    frac_hbm = kernels_gbs.get(dom, 0.0) / peaks["hbm"]
+    hbm_bound = frac_hbm > frac_tensor
     roofline = {
-        "kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": ach / peak_tf, "frac_of_burst": ach / peaks["tf_burst"], "frac_of_sustained": ach / peaks["tf_sustained"],
+        "kernel": dom, "bound": "hbm" if hbm_bound else "tensor",
+        "achieved": kernels_gbs[dom] if hbm_bound else ach, "peak": peaks["hbm"] if hbm_bound else peak_tf,
+        "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": frac_hbm if hbm_bound else frac_tensor,
+        "frac_tensor": frac_tensor, "frac_hbm": frac_hbm, "achieved_tflops": ach, "achieved_gbs": kernels_gbs.get(dom),
+        "algorithmic_flops_per_launch": alg_flops.get(dom), "algorithmic_bytes_per_launch": alg_bytes.get(dom),
+        "frac_of_burst": ach / peaks["tf_burst"], "frac_of_sustained": ach / peaks["tf_sustained"],
         "peak_choice": peak_choice, "peaks": {"bf16_burst": peaks["tf_burst"], "bf16_sustained": peaks["tf_sustained"],
                                               "hbm_gbs": peaks["hbm"], "source": peaks["src"]},
         "traffic": traffic, "traffic_source": traffic_src,
@@ -534,6 +610,8 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": roofline,
         "sustained": sustained,
+        "per_rank_ms": {"min": min(rank_ms), "median": statistics.median(rank_ms), "max": max(rank_ms)},
+        "extra": extra,
         "cpu_baseline": cpu_baseline,
         "loss": loss_val,
     }
@@ -570,6 +648,8 @@ def main():
     ap.add_argument("--sustained-s", type=float, default=2.0,
                     help="length of the extra graph-replay leg that reports the power-limited steady state (0 = skip)")
     ap.add_argument("--no-hbm-table", action="store_true", help="skip the GB/s table of the HBM-bound reduction kernels")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 legs of the `extra` block")
+    ap.add_argument("--extra-steps", type=int, default=24, help="timed micro-steps of each `extra` leg")
     args = ap.parse_args()
     global _OUT
     _OUT = _claim_stdout()

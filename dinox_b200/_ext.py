@@ -167,6 +167,8 @@ SIGNATURES = {
     "dinox_gather_cast_bf16": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p]),
     "dinox_gather_f32": (c_int, [c_void_p, c_void_p, c_i64, c_f32, c_void_p, c_void_p]),
     "dinox_scatter_rows_f32": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p]),
+    "dinox_gather_rows_f32": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p]),
+    "dinox_scatter_add_rows_f32": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p]),
     "dinox_gelu_fwd": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
     "dinox_gelu_bwd_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_gelu_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -98,6 +98,36 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, int64_t ld_sr
   for (int c = threadIdx.x & 31; c < D4; c += 32) d[c] = s[c];
 }
 
+// out[r, :] = float(src[idx[r], :]) (idx < 0 -> zero row): materialises index-named rows in fp32
+template <typename T>
+__global__ void gather_rows_f32_kernel(const T* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ idx,
+                                       int64_t rows, int D, float* __restrict__ out, int64_t ld_out) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t t = idx ? idx[r] : r;
+  float* o = out + r * ld_out;
+  if (t < 0) { for (int c = threadIdx.x & 31; c < D; c += 32) o[c] = 0.f; return; }
+  const T* x = src + t * ld_src;
+  for (int c = threadIdx.x & 31; c < D; c += 32) o[c] = to_f32<T>(x[c]);
+}
+
+// dst[idx[r], :] += src[r, :] (unique idx, so no two rows collide: a plain read-modify-write is race free)
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ idx,
+                                        int64_t rows, int D4, float* __restrict__ dst, int64_t ld_dst) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t t = idx[r];
+  if (t < 0) return;
+  const float4* s = reinterpret_cast<const float4*>(src + r * ld_src);
+  float4* d = reinterpret_cast<float4*>(dst + t * ld_dst);
+  for (int c = threadIdx.x & 31; c < D4; c += 32) {
+    float4 a = d[c];
+    const float4 b = s[c];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    d[c] = a;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // GELU (erf):  h = bf16(gelu(a));   backward: da = bf16(dh * gelu'(a)), colsum(da) for db1
 // ---------------------------------------------------------------------------------------------
@@ -172,37 +202,56 @@ __global__ void gemv_bf16_kernel(const __nv_bfloat16* __restrict__ W, int64_t ld
 
 // nvec (<= 4) vectors against the same matrix in one pass over W: out[v][k] = alpha[v] * W[k,:].x[v] + beta*bias[k]
 struct GemvAlphas { float a[4]; };
+constexpr int kGemvRows = 4;
 template <int NV>
 __global__ void gemv_bf16_multi_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, const float* __restrict__ X,
                                        int64_t K, int D, GemvAlphas alphas, const float* __restrict__ divisors,
                                        const float* __restrict__ bias, float beta, float* __restrict__ out) {
-  const int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (k >= K) return;
-  const __nv_bfloat16* w = W + k * ldw;
-  float acc[NV];
+  // each warp owns kGemvRows consecutive rows and loads them together: one row of D = 384 is only 1.5 16-byte loads
+  // per lane, which left the kernel latency bound at 1.7 TB/s
+  const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kGemvRows;
+  if (k0 >= K) return;
+  float acc[kGemvRows][NV];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+  for (int r = 0; r < kGemvRows; ++r)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[r][v] = 0.f;
   for (int c = lane * 8; c < D; c += 256) {
-    const uint4 u = ldg_stream_u4(reinterpret_cast<const uint4*>(w + c));
-    const float wv[8] = {__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
-                         __uint_as_float(u.y & 0xffff0000u), __uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u),
-                         __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u)};
+    uint4 u[kGemvRows];
+#pragma unroll
+    for (int r = 0; r < kGemvRows; ++r)
+      u[r] = (k0 + r < K) ? ldg_stream_u4(reinterpret_cast<const uint4*>(W + (k0 + r) * ldw + c)) : make_uint4(0, 0, 0, 0);
+    float4 x0[NV], x1[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const float4 x0 = *reinterpret_cast<const float4*>(X + (int64_t)v * D + c);
-      const float4 x1 = *reinterpret_cast<const float4*>(X + (int64_t)v * D + c + 4);
-      acc[v] = fmaf(wv[0], x0.x, acc[v]); acc[v] = fmaf(wv[1], x0.y, acc[v]);
-      acc[v] = fmaf(wv[2], x0.z, acc[v]); acc[v] = fmaf(wv[3], x0.w, acc[v]);
-      acc[v] = fmaf(wv[4], x1.x, acc[v]); acc[v] = fmaf(wv[5], x1.y, acc[v]);
-      acc[v] = fmaf(wv[6], x1.z, acc[v]); acc[v] = fmaf(wv[7], x1.w, acc[v]);
+      x0[v] = *reinterpret_cast<const float4*>(X + (int64_t)v * D + c);
+      x1[v] = *reinterpret_cast<const float4*>(X + (int64_t)v * D + c + 4);
+    }
+#pragma unroll
+    for (int r = 0; r < kGemvRows; ++r) {
+      const float wv[8] = {__uint_as_float(u[r].x << 16), __uint_as_float(u[r].x & 0xffff0000u), __uint_as_float(u[r].y << 16),
+                           __uint_as_float(u[r].y & 0xffff0000u), __uint_as_float(u[r].z << 16), __uint_as_float(u[r].z & 0xffff0000u),
+                           __uint_as_float(u[r].w << 16), __uint_as_float(u[r].w & 0xffff0000u)};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float a = acc[r][v];
+        a = fmaf(wv[0], x0[v].x, a); a = fmaf(wv[1], x0[v].y, a); a = fmaf(wv[2], x0[v].z, a); a = fmaf(wv[3], x0[v].w, a);
+        a = fmaf(wv[4], x1[v].x, a); a = fmaf(wv[5], x1[v].y, a); a = fmaf(wv[6], x1[v].z, a); a = fmaf(wv[7], x1[v].w, a);
+        acc[r][v] = a;
+      }
     }
   }
-  const float b = bias ? bias[k] * beta : 0.f;
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    const float t = warp_sum(acc[v]);
-    if (lane == 0) out[(int64_t)v * K + k] = t * (divisors ? alphas.a[v] / divisors[v] : alphas.a[v]) + b;
+  for (int r = 0; r < kGemvRows; ++r) {
+    const int64_t k = k0 + r;
+    if (k >= K) break;
+    const float b = bias ? bias[k] * beta : 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float t = warp_sum(acc[r][v]);
+      if (lane == 0) out[(int64_t)v * K + k] = t * (divisors ? alphas.a[v] / divisors[v] : alphas.a[v]) + b;
+    }
   }
 }
 
@@ -295,6 +344,10 @@ __global__ void normalize_bwd_kernel(const T* __restrict__ feats, int64_t stride
   dot = warp_sum(dot);
   float* o = grad + b * gstride_b + (t + skip) * gstride_t;
   for (int c = lane; c < D; c += 32) o[c] = (g[c] - to_f32<T>(x[c]) * inv * dot) * inv * sc;
+  if (t < skip) {   // the skipped leading tokens (CLS) receive no gradient: row t of the image is written as zeros
+    float* z = grad + b * gstride_b + t * gstride_t;
+    for (int c = lane; c < D; c += 32) z[c] = 0.f;
+  }
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
@@ -361,6 +414,28 @@ int dinox_scatter_rows_f32(const float* src, int64_t ld_src, const int64_t* idx,
   return check_launch("scatter_rows_kernel", stream);
 }
 
+int dinox_gather_rows_f32(const void* src, int dtype, int64_t ld_src, const int64_t* idx, int64_t rows, int64_t D,
+                          float* out, int64_t ld_out, dinox_stream_t stream) {
+  DINOX_REQUIRE(src && out && rows >= 0 && D > 0, DINOX_E_BADARG, "gather_rows_f32: bad arguments");
+  if (rows == 0) return DINOX_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dtype == DINOX_F32) gather_rows_f32_kernel<float><<<grid, 256, 0, stream>>>((const float*)src, ld_src, idx, rows, (int)D, out, ld_out);
+  else if (dtype == DINOX_BF16) gather_rows_f32_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, ld_src, idx, rows, (int)D, out, ld_out);
+  else if (dtype == DINOX_F16) gather_rows_f32_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)src, ld_src, idx, rows, (int)D, out, ld_out);
+  else { set_error("gather_rows_f32: dtype must be f32, bf16 or f16"); return DINOX_E_BADARG; }
+  return check_launch("gather_rows_f32_kernel", stream);
+}
+
+int dinox_scatter_add_rows_f32(const float* src, int64_t ld_src, const int64_t* idx, int64_t rows, int64_t D, float* dst,
+                               int64_t ld_dst, dinox_stream_t stream) {
+  DINOX_REQUIRE(src && idx && dst && rows >= 0 && D > 0 && D % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0,
+                DINOX_E_BADARG, "scatter_add_rows_f32: bad arguments (D, ld multiples of 4)");
+  DINOX_REQUIRE(aligned16(src) && aligned16(dst), DINOX_E_ALIGN, "scatter_add_rows_f32: misaligned");
+  if (rows == 0) return DINOX_OK;
+  scatter_add_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(src, ld_src, idx, rows, (int)(D / 4), dst, ld_dst);
+  return check_launch("scatter_add_rows_kernel", stream);
+}
+
 int dinox_gelu_fwd(const float* a, int64_t n, void* h_bf16, dinox_stream_t stream) {
   DINOX_REQUIRE(a && h_bf16 && n > 0 && n % 4 == 0, DINOX_E_BADARG, "gelu_fwd: n must be a positive multiple of 4");
   DINOX_REQUIRE(aligned16(a) && (reinterpret_cast<uintptr_t>(h_bf16) % 8) == 0, DINOX_E_ALIGN, "gelu_fwd: misaligned");
@@ -396,7 +471,7 @@ int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, 
   DINOX_REQUIRE(aligned16(W) && aligned16(X), DINOX_E_ALIGN, "gemv_bf16_multi: misaligned");
   GemvAlphas al;
   for (int v = 0; v < 4; ++v) al.a[v] = v < nvec ? alphas_host[v] : 0.f;
-  const unsigned grid = (unsigned)((K + 7) / 8);
+  const unsigned grid = (unsigned)((K + 8 * kGemvRows - 1) / (8 * kGemvRows));
   const __nv_bfloat16* w = (const __nv_bfloat16*)W;
   switch (nvec) {
     case 1: gemv_bf16_multi_kernel<1><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;

@@ -674,6 +674,7 @@ struct EpiGradRT {
     int64_t ld_refs;
     int alt_from;            // entries >= alt_from go to loss[1]
     int run_rows;            // 1: contiguous prototype runs per M tile (consecutive tiles of a CTA share the row)
+    int m_step;              // > 0: column sweep, consecutive tiles of a CTA are m_step M tiles apart
     float* db2_partial;      // (ceil(M/32), N) or NULL
     float* loss_partial;     // (gridDim.x * kEpiWarps * 2)
   };
@@ -683,6 +684,7 @@ struct EpiGradRT {
     // raw per-row values of the NEXT tile (loaded by fetch(); no arithmetic on them until prologue)
     float n_lse = 0.f, n_cw = 0.f, n_rb = 0.f;
     int n_trow = 0, n_mtile = -1, n_ntile = 0;
+    int n2_trow = 0, n2_mtile = -1;   // column sweep: teacher row of the tile after the next one
     // the tile being processed
     float nl = 0.f, cwt = 0.f, rb = 0.f;
     int cur_mtile = -1, cur_trow = 0;
@@ -735,6 +737,19 @@ struct EpiGradRT {
         st.n_rb = ok ? __ldg(e.rb2 + row) : 0.f;
         st.n_trow = ok ? __ldg(e.trow + row) : 0;
         st.n_mtile = tc.m_tile;
+        if (e.m_step > 0) {
+          // column sweep: the row changes with every tile.  The teacher row of THIS tile was looked up one fetch ago
+          // (n2_*): pull its granule of probabilities towards L2 now, a whole tile before the register loads ask
+          // for it, and look up the row of the tile after this one.
+          if (st.n2_mtile == tc.m_tile) {
+            const __half* nq = granule(e, st.n2_trow, tc.n_tile, grp);
+            prefetch_l2(nq);
+            if (kColsW > 64) prefetch_l2(nq + 64);
+          }
+          const int row2 = row + e.m_step * BM;
+          st.n2_mtile = tc.m_tile + e.m_step;
+          st.n2_trow = row2 < p.M ? __ldg(e.trow + row2) : 0;
+        }
       }
       st.n_ntile = tc.n_tile;
     }
@@ -1397,7 +1412,7 @@ static bool resa_enabled(int family, int64_t K) {
 // resident + column sweep over the M tiles; clear = rows of an M tile resident + contiguous prototype runs (the pass-1
 // schedule).  Measured at C2 (ms): teacher 0.355 (columns) / 0.384 (runs); pass 2 0.654 (columns) / 0.589 (runs).
 #ifndef DINOX_RB_SCHED_DEFAULT
-#define DINOX_RB_SCHED_DEFAULT 1
+#define DINOX_RB_SCHED_DEFAULT 3
 #endif
 static bool readback_cols(int which, int64_t K) {
   static int v = -1;
@@ -1722,6 +1737,7 @@ int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int
   const bool cl2 = E > BM && pair_enabled(kPairGrad);
   const int cl = cl2 ? 2 : 1;
   ep.run_rows = (cl2 && !readback_cols(2, D) && resa_enabled(kPairStats, D)) ? 1 : 0;
+  ep.m_step = (cl2 && readback_cols(2, D)) ? 2 : 0;
   if (cl2 && readback_cols(2, D))   // W2 tile resident, clusters sweep the entry tiles in step (W2 read from HBM once)
     rc = launch<256, 1, 1, 2, EpiGradR, kResB>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair,resB>");
   else if (cl2 && resa_enabled(kPairStats, D))   // the entries of an M tile resident, prototype tiles walked in one contiguous run

@@ -262,8 +262,8 @@ class _GramAnchor(torch.autograd.Function):
         dv = delta[:, :, :T - 1]
         # dL/dXn = (dG + dG^T) Xn = (4/n) * Delta @ Xn   (Delta symmetric)
         dxn = ops.gemm_bf16_batched(dv, xs, b_mn_major=True, alpha=4.0 / ctx.n)
+        # the CLS row receives no gradient (the reference slices feats[:, 1:]): the kernel writes it as zeros
         grad = torch.empty(Bt, T, D, dtype=torch.float32, device=g.device)
-        grad[:, 0].zero_()  # CLS row receives no gradient (the reference slices feats[:, 1:])
         up = g.to(torch.float32).reshape(1).contiguous()
         ops.normalize_tokens_bwd(student_feats, dxn, inv_s, grad, skip=1, scale_dev=up)
         return grad.to(student_feats.dtype), None
@@ -563,7 +563,7 @@ def _update_centres(stats, work, w2t, b2t, loss_mod, center_patch, patch_momentu
 class _FusedHeadLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, student_cls, student_patch, w1, b1, w2, b2, teacher_cls, teacher_patch, masks_weight, t_head,
-                loss_mod, center_patch, cfg, patch_index=None, params_in_place=None):
+                loss_mod, center_patch, cfg, patch_index=None, params_in_place=None, teacher_index=None):
         (student_temp, teacher_temp, Vg, n_local, ibot_weight, teacher_mode, sk_iters, pg, update_center,
          patch_momentum, grads_in_place) = cfg
         dev = student_cls.device
@@ -579,7 +579,9 @@ class _FusedHeadLoss(torch.autograd.Function):
         sp2 = tp2 = None
         if Mm:
             sp2 = student_patch.detach() if patch_index is None else student_patch.detach().view(-1, D)
-            tp2 = teacher_patch.detach() if patch_index is None else teacher_patch.detach().view(-1, D)
+            if teacher_index is None:
+                teacher_index = patch_index
+            tp2 = teacher_patch.detach() if teacher_index is None else teacher_patch.detach().view(-1, D)
         plan = _entry_plan(B, Vg, V, Mm, dev)
         readback = pass2_mode() == "readback"
         Mt_pad = plan.Mt_pad if readback else Mt        # row of the first masked patch in the teacher matrices
@@ -604,7 +606,7 @@ class _FusedHeadLoss(torch.autograd.Function):
             xt = torch.empty(Mt_pad + Mm, D, dtype=torch.bfloat16, device=dev)
             ops.gather_cast_bf16(teacher_cls.detach(), plan.cls_rows_pad if Mt_pad != Mt else None, xt[:Mt_pad])
             if Mm:
-                ops.gather_cast_bf16(tp2, patch_index, xt[Mt_pad:])
+                ops.gather_cast_bf16(tp2, teacher_index, xt[Mt_pad:])
             a_t = ops.gemm_bf16(xt, w1t, bias_n=t_head[0].bias.detach())   # layer 1 (zoo/arch.py:253-254)
             ht = ops.gelu_fwd(a_t)
             del a_t
@@ -772,7 +774,7 @@ class _FusedHeadLoss(torch.autograd.Function):
                 ops.scatter_rows(dx[plan.Ms:], ctx.patch_index, d_tok.view(-1, D))
                 d_patch = d_tok.to(ctx.in_dtypes[1])
         return (d_cls, d_patch, outs.get("w1"), outs.get("b1"), outs.get("w2"), outs.get("b2"),
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None)
 
 
 def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, student_head: nn.Sequential,
@@ -781,7 +783,8 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
                          masks_weight: Optional[torch.Tensor] = None, center_patch: Optional[torch.Tensor] = None,
                          ibot_weight: float = 1.0, patch_center_momentum: Optional[float] = None,
                          update_center: bool = True, patch_index: Optional[torch.Tensor] = None,
-                         grads_in_place: bool = False) -> Dict[str, torch.Tensor]:
+                         grads_in_place: bool = False,
+                         teacher_patch_index: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """Projection head + multi-crop DINO CE (+ iBOT masked-patch CE) in one fused path.
 
     Equivalent to `dino_loss(student_head(student_cls), teacher_head(teacher_cls), ...)` of the reference
@@ -796,6 +799,9 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
     token tensors themselves (contiguous (..., D), e.g. the (B*Vg, T, D) output that `feats[:, 1:]` slices,
     scripts/phase5_big_run.py:1741-1747): the masked rows are gathered by the staging kernel and their
     gradients scattered back, so the caller never materialises `tokens[mask]`.
+    `teacher_patch_index` names the rows of the TEACHER token tensor only (`student_patch` then holds materialised
+    (Mm, D) rows): what `token_fork` + `LossHeadStep` use so that the iBOT gradient is added into the Gram-anchoring
+    gradient of the same token tensor instead of travelling as a second dense tensor.
     Returns {"loss": differentiable total, "loss_dino", "loss_ibot"}."""
     for t in (student_cls, teacher_cls):
         if not t.is_cuda:
@@ -811,6 +817,14 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
                 raise ValueError("patch_index needs contiguous token tensors (pass the backbone output, not a slice)")
             if masks_weight.numel() != patch_index.numel():
                 raise ValueError("masks_weight and patch_index must name the same rows")
+        if teacher_patch_index is not None:
+            if patch_index is not None:
+                raise ValueError("give either patch_index (both token tensors) or teacher_patch_index (teacher only)")
+            ti = teacher_patch_index
+            if ti.dtype != torch.int64 or ti.dim() != 1 or not ti.is_cuda or ti.numel() != student_patch.shape[0]:
+                raise ValueError("teacher_patch_index: 1-D int64 CUDA tensor with one entry per student_patch row expected")
+            if not teacher_patch.is_contiguous():
+                raise ValueError("teacher_patch_index needs a contiguous teacher token tensor")
     cfg = (student_temp, teacher_temp, dino_loss.n_global, dino_loss.n_local, ibot_weight, dino_loss.teacher_mode,
            dino_loss.sk_iterations, dino_loss.process_group, update_center,
            dino_loss.center_momentum if patch_center_momentum is None else patch_center_momentum, bool(grads_in_place))
@@ -821,8 +835,46 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
     total, losses = _FusedHeadLoss.apply(student_cls, student_patch, *ins,
                                          teacher_cls.detach(), None if teacher_patch is None else teacher_patch.detach(),
                                          masks_weight, teacher_head, dino_loss, center_patch, cfg, patch_index,
-                                         params if grads_in_place else None)
+                                         params if grads_in_place else None, teacher_patch_index)
     return {"loss": total, "loss_dino": losses[0], "loss_ibot": losses[1]}
+
+
+class _TokenFork(torch.autograd.Function):
+    """One token tensor feeding two loss terms: returns (the tensor itself for Gram anchoring, the masked rows as a
+    materialised (Mm, D) fp32 matrix for the iBOT term).  Backward: the dense gradient that arrives for the first
+    output (Gram anchoring owns it) receives the row gradients of the second by an in-place scatter-add - no
+    zero-filled dense tensor for the rows, no framework add of two dense tensors."""
+
+    @staticmethod
+    def forward(ctx, tokens, index):
+        D = tokens.shape[-1]
+        flat = tokens.detach().reshape(-1, D)
+        rows = torch.empty(index.numel(), D, dtype=torch.float32, device=tokens.device)
+        ops.gather_rows_f32(flat, index, rows)
+        ctx.save_for_backward(index)
+        ctx.shape, ctx.dtype = tuple(tokens.shape), tokens.dtype
+        return tokens.view_as(tokens), rows
+
+    @staticmethod
+    def backward(ctx, g_tokens, g_rows):
+        (index,) = ctx.saved_tensors
+        D = ctx.shape[-1]
+        if g_tokens is None:
+            g_tokens = torch.empty(ctx.shape, dtype=torch.float32, device=index.device)
+            ops.fill_(g_tokens.view(-1), 0.0)
+        elif not (g_tokens.dtype == torch.float32 and g_tokens.is_contiguous()):
+            g_tokens = g_tokens.float().contiguous()
+        if g_rows is not None:
+            ops.scatter_add_rows(g_rows.float().contiguous(), index, g_tokens.view(-1, D))
+        return g_tokens.to(ctx.dtype), None
+
+
+def token_fork(tokens: torch.Tensor, index: torch.Tensor):
+    """(tokens, tokens.reshape(-1, D)[index] as fp32 rows) with a backward that adds the row gradients into the
+    dense gradient of the first output in place.  `index`: unique flat row numbers (int64, CUDA)."""
+    if not (tokens.is_cuda and tokens.is_contiguous()):
+        raise ValueError("token_fork: contiguous CUDA token tensor expected")
+    return _TokenFork.apply(tokens, index)
 
 
 class FusedLossHead(nn.Module):

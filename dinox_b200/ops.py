@@ -394,6 +394,25 @@ def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> tor
     return dst
 
 
+def gather_rows_f32(src: torch.Tensor, idx: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """out[r] = float(src[idx[r]]) (idx None: identity; idx < 0: zero row); src rows may be strided."""
+    _chk_cuda(src, out)
+    assert src.dim() == 2 and src.stride(1) == 1 and out.stride(1) == 1 and out.dtype == torch.float32
+    _ext.call("dinox_gather_rows_f32", _p(src), DT[src.dtype], src.stride(0), _p(idx), out.shape[0], src.shape[1], _p(out),
+              out.stride(0), _stream())
+    return out
+
+
+def scatter_add_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[idx[r]] += src[r] (fp32 rows; unique idx; idx < 0 skipped), in place."""
+    _chk_cuda(src, dst, idx)
+    assert src.dim() == 2 and dst.dim() == 2 and src.dtype == dst.dtype == torch.float32 and idx.dtype == torch.int64
+    assert src.stride(1) == 1 and dst.stride(1) == 1 and idx.numel() == src.shape[0] and src.shape[1] == dst.shape[1]
+    _ext.call("dinox_scatter_add_rows_f32", _p(src), src.stride(0), _p(idx), src.shape[0], src.shape[1], _p(dst),
+              dst.stride(0), _stream())
+    return dst
+
+
 def gelu_fwd(a: torch.Tensor) -> torch.Tensor:
     h = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
     _ext.call("dinox_gelu_fwd", _p(a), a.numel(), _p(h), _stream())

@@ -149,22 +149,30 @@ class LossHeadStep:
         """Forward of all loss terms.  Gram anchoring is independent of the head until the final sum: it is
         issued first, on a side stream, and its small kernels (and, by autograd's stream rule, their
         backward) run beside the head's GEMMs instead of between them."""
-        gram, side = None, None
+        gram, side, stok, rows = None, None, None, None
         if "student_tok" in f:
+            stok = f["student_tok"]
+            if "patch_index" in f and stok.requires_grad:
+                stok, rows = losshead.token_fork(stok, f["patch_index"])
             if losshead.concurrency() >= 1 and not ops.TIMER.enabled:
                 side = losshead._side_stream(self.device, 1)
                 side.wait_stream(torch.cuda.current_stream())
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-                gram = losshead.compute_gram_anchoring_loss(f["student_tok"], f["teacher_tok"])
+                gram = losshead.compute_gram_anchoring_loss(stok, f["teacher_tok"])
         # iBOT rows: materialised ("student_patch"/"teacher_patch") or named by "patch_index" inside the token tensors
         by_index = "patch_index" in f
         sp = f["student_tok"] if by_index else f.get("student_patch")
         tp = f["teacher_tok"] if by_index else f.get("teacher_patch")
+        idx, t_idx = f.get("patch_index"), None
+        if by_index and rows is not None:
+            # the token tensor feeds Gram anchoring AND (its masked rows) the iBOT term: the fork hands the rows to the
+            # head as a matrix and adds their gradient into the Gram gradient in place (see losshead.token_fork)
+            sp, idx, t_idx = rows, None, f["patch_index"]
         out = losshead.fused_head_dino_loss(
             f["student_cls"], f["teacher_cls"], self.student_head, self.teacher_head, self.dino_loss,
             self.student_temp, self.teacher_temp, student_patch=sp, teacher_patch=tp,
             masks_weight=f.get("masks_weight"), center_patch=self.center_patch if sp is not None else None,
-            ibot_weight=self.ibot_weight, patch_index=f.get("patch_index"), grads_in_place=True)
+            ibot_weight=self.ibot_weight, patch_index=idx, teacher_patch_index=t_idx, grads_in_place=True)
         terms, weights = [out["loss"]], [1.0]
         if gram is not None:
             if side is not None:

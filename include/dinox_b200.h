@@ -299,6 +299,13 @@ DINOX_API int dinox_gather_sum_rows(const float* src, int64_t ld_src, int slabs,
                                     const int64_t* ptr, const int64_t* ent, int64_t rows, int64_t D,
                                     const float* scale_dev, float scale, float* dst, int64_t ld_dst,
                                     int accumulate, dinox_stream_t stream);
+/* out[r,:] = float(src[idx[r],:]) (idx NULL: identity, idx < 0: zero row): index-named token rows as fp32 rows */
+DINOX_API int dinox_gather_rows_f32(const void* src, int dtype, int64_t ld_src, const int64_t* idx, int64_t rows,
+                                    int64_t D, float* out, int64_t ld_out, dinox_stream_t stream);
+/* dst[idx[r],:] += src[r,:] (fp32 rows, unique idx, idx < 0 skipped): adds the gradients of index-gathered rows
+ * into a gradient tensor that already holds another term (Gram anchoring + iBOT on the same token tensor) */
+DINOX_API int dinox_scatter_add_rows_f32(const float* src, int64_t ld_src, const int64_t* idx, int64_t rows,
+                                         int64_t D, float* dst, int64_t ld_dst, dinox_stream_t stream);
 DINOX_API int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream);
 /* a9 step glue (scripts/phase5_big_run.py:1749-1772, `loss = L_dino + w_g*L_gram (+ w_k*L_koleo); loss /= accum`):
  *   out[0] = scale * sum_{i<n} weights[i] * terms[i][0]      (n <= 8 device scalars, fixed order)
