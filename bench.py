@@ -157,6 +157,104 @@ def cpu_oracle_step_time(cfg_name: str, sample_batch: int, steps: int, warmup: i
     return sh.student_rows / per_step, cores, desc, per_step
 
 
+def torch_eager_gpu_step_time(cfg_name: str, dev, steps: int, warmup: int, accum: int):
+    """The same-box comparator: the reference algorithm as plain PyTorch eager ops on THIS GPU
+    under torch.autocast(bf16) - the oracle's code executed on CUDA, i.e. what scripts/phase5_big_run.py --amp would
+    launch for this workload (cuBLAS GEMMs + ATen softmax / reductions, logits materialised) - with the reference's
+    per-tensor EMA loop.  Full configuration, inputs resident.  Returns (crops/s, ms per micro-step)."""
+    from dinox_b200 import synth
+    from oracle import losshead_oracle as O
+    sh = synth.LossHeadShapes(**synth.CONFIGS[cfg_name])
+    g = synth.seeded_generator(2, 0)
+    D, K = sh.dim, sh.out_dim
+    sw, tw = synth.head_weights(D, K, g), synth.head_weights(D, K, g)
+    keys = ("0.weight", "0.bias", "2.weight", "2.bias")
+    sp = O.HeadParams(*[sw[k].to(dev).requires_grad_(True) for k in keys])
+    tp = O.HeadParams(*[tw[k].to(dev) for k in keys])
+    orc = O.LossHeadOracle(sp, tp, K, center_momentum=0.9, n_global=sh.n_global, n_local=sh.n_local, policy="fp32")
+    orc.center, orc.center_patch = orc.center.to(dev), orc.center_patch.to(dev)
+    depth = synth.BACKBONES.get(D, dict(depth=12))["depth"]
+    shapes = synth.student_param_shapes(D, depth, K)[:-4]
+    s_all = [torch.randn(s, device=dev) * 0.02 for s in shapes] + [p.detach() for p in sp.tensors()]
+    t_all = [torch.randn(s, device=dev) * 0.02 for s in shapes] + [p.detach().clone() for p in tp.tensors()]
+    f = {k: v.to(dev) for k, v in synth.feature_batch(sh, g, patches_from_tokens=True).items()}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        fs = {k: (v.clone().requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            sp_rows = fs["student_tok"].reshape(-1, D)[fs["patch_index"]]
+            tp_rows = fs["teacher_tok"].reshape(-1, D)[fs["patch_index"]]
+            orc.step(fs["student_cls"], fs["teacher_cls"], 0.1, 0.04, student_tok=fs["student_tok"],
+                     teacher_tok=fs["teacher_tok"], student_patch=sp_rows, teacher_patch=tp_rows,
+                     masks_weight=fs["masks_weight"], accum=accum)
+        if (i + 1) % accum == 0:
+            orc.ema(s_all, t_all, 0.996)
+            for p in sp.tensors():
+                p.grad = None
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del orc, sp, tp, s_all, t_all, f
+    torch.cuda.empty_cache()
+    return sh.student_rows / (ms * 1e-3), ms
+
+
+def reference_verbatim_cpu(batch: int, steps: int, warmup: int, K: int = 65536, D: int = 384, tokens: int = 201):
+    """The reference's OWN classes (imported from /root/reference when that tree exists - it does in the build
+    container, not on the GPU box) on the host cores: head forward for student and teacher, DINOLoss, Gram anchoring,
+    backward, and the inline EMA loop of scripts/phase5_big_run.py:1798-1802 over the head parameters, on the
+    2-global-view subset the reference can run (no local crops, no iBOT).  Returns None when the tree is absent."""
+    ref_root = os.environ.get("DINOX_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(ref_root, "scripts")):
+        return None
+    import importlib
+    for pth in (ref_root, os.path.join(ref_root, "scripts")):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    try:
+        big = importlib.import_module("phase5_big_run")
+    except Exception as exc:   # missing optional dependency of the reference script
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+    from dinox_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = synth.seeded_generator(2, 0)
+    mk = lambda: torch.nn.Sequential(torch.nn.Linear(D, D), torch.nn.GELU(), torch.nn.Linear(D, K))   # zoo/arch.py:252-256
+    s_head, t_head = mk(), mk()
+    s_head.load_state_dict(synth.head_weights(D, K, g))
+    t_head.load_state_dict(synth.head_weights(D, K, g))
+    for p in t_head.parameters():
+        p.requires_grad_(False)
+    loss_fn = big.DINOLoss(K, 0.9)
+    sf = torch.randn(2 * batch, tokens, D, generator=g)
+    tf = torch.randn(2 * batch, tokens, D, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        x = sf.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        student_out = s_head(x[:, 0])
+        with torch.no_grad():
+            teacher_out = t_head(tf[:, 0])
+        loss = loss_fn(student_out, teacher_out, 0.1, 0.04) + 1.0 * big.compute_gram_anchoring_loss(x, tf)
+        loss.backward()
+        with torch.no_grad():
+            for p_s, p_t in zip(s_head.parameters(), t_head.parameters()):
+                p_t.data.mul_(0.996).add_(p_s.data, alpha=1 - 0.996)
+        for p in s_head.parameters():
+            p.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per = statistics.median(times)
+    return {"value": 2 * batch / per, "unit": "crops/s", "ms_per_step": per * 1e3, "cores": cores, "kind": "reference",
+            "sample": f"reference classes verbatim (DINOLoss, compute_gram_anchoring_loss, nn.Sequential head, inline EMA of the head) "
+                      f"on the 2-global-view subset: batch {batch} -> {2 * batch} crops, K={K}, D={D}, {tokens} tokens, fp32, "
+                      f"median of {steps} steps after {warmup} warm-up"}
+
+
 def workload_text(args, sh, n_params: float) -> str:
     """The workload both arms run (BASELINE.json configs), in the same words."""
     return (f"{args.config}: ViT-{'S' if sh.dim == 384 else 'L'}/16 loss head (teacher {args.teacher_mode}), per-GPU batch {sh.batch} x accum {args.accum}, "
@@ -177,6 +275,15 @@ def run_reference(args):
     n_params = 0
     for shp in synth.student_param_shapes(sh.dim, depth, sh.out_dim):
         n_params += math.prod(shp)
+    verbatim = None
+    if not args.no_reference_verbatim:
+        v8 = reference_verbatim_cpu(args.cpu_sample_batch, 3, 1, K=sh.out_dim, D=sh.dim, tokens=sh.tokens)
+        if v8 is not None and "value" in v8:
+            verbatim = {"slice": v8, "full_batch": reference_verbatim_cpu(sh.batch, 2, 1, K=sh.out_dim, D=sh.dim, tokens=sh.tokens)}
+        else:
+            verbatim = v8 or {"unavailable": "the reference tree (/root/reference) is not present on this host: the reference "
+                                             "is a Python package that cannot travel to the GPU box; see "
+                                             "profiles/r02_cpu_reference_verbatim.json for the run in the build container"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
@@ -184,9 +291,11 @@ def run_reference(args):
         "config": {"workload": workload_text(args, sh, n_params),
                    "sample": f"each step runs a {args.cpu_sample_batch}-image slice of the per-GPU batch on {cores} host threads; "
                              f"crops/s = slice crops / slice time"},
-        "cpu_baseline": {"value": value, "unit": "crops/s", "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "crops/s", "cores": cores, "kind": "port", "sample": desc,
+                         "processes": 1, "note": "ONE CPU process on this host's cores at every --gpus N"},
         "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_verbatim": verbatim,
     }
     print(json.dumps(line), file=_OUT, flush=True)
 
@@ -587,6 +696,20 @@ def run_ours(args):
     if world == 1 and not args.no_hbm_table:
         roofline["hbm_kernels"] = hbm_kernel_table(dev, sh, peaks["hbm"])
 
+    torch_eager = None
+    if world == 1 and not args.no_torch_eager:
+        try:
+            step._graphs.clear()
+            torch.cuda.empty_cache()
+            v, ms = torch_eager_gpu_step_time(args.config, dev, 8, 3, args.accum)
+            torch_eager = {"value": v, "unit": "crops/s", "ms_per_step": ms,
+                           "what": "the reference algorithm (oracle code) as PyTorch eager ops on this GPU under "
+                                   "torch.autocast(bf16): cuBLAS + ATen, logits materialised, per-tensor EMA loop; same "
+                                   "workload, inputs resident, 8 steps after 3 warm-up",
+                           "speedup_of_this_repo": value / v}
+        except Exception as exc:   # e.g. out of memory on a shared GPU: the comparator is optional
+            torch_eager = {"unavailable": f"{type(exc).__name__}: {str(exc)[:200]}"}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         v, cores, desc, _ = cpu_oracle_step_time(args.config, args.cpu_sample_batch, args.cpu_steps, 2, args.accum,
@@ -612,6 +735,7 @@ def run_ours(args):
         "sustained": sustained,
         "per_rank_ms": {"min": min(rank_ms), "median": statistics.median(rank_ms), "max": max(rank_ms)},
         "extra": extra,
+        "torch_eager_b200": torch_eager,
         "cpu_baseline": cpu_baseline,
         "loss": loss_val,
     }
@@ -649,6 +773,9 @@ def main():
                     help="length of the extra graph-replay leg that reports the power-limited steady state (0 = skip)")
     ap.add_argument("--no-hbm-table", action="store_true", help="skip the GB/s table of the HBM-bound reduction kernels")
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 legs of the `extra` block")
+    ap.add_argument("--no-torch-eager", action="store_true", help="skip the PyTorch-eager-on-this-GPU comparator leg")
+    ap.add_argument("--no-reference-verbatim", action="store_true",
+                    help="--impl reference: skip timing the reference's own classes (only possible where /root/reference exists)")
     ap.add_argument("--extra-steps", type=int, default=24, help="timed micro-steps of each `extra` leg")
     args = ap.parse_args()
     global _OUT

@@ -1258,13 +1258,20 @@ struct EpiAdapter {
   }
 };
 
-template <int BN, int NSPLIT, int NSUB, int CL, class Epi, int RES = kResNone>
+// NOUT output tensor maps (1 everywhere except the reduce-scatter GEMM: one map per data-parallel rank's shard)
+constexpr int kMaxOwners = 8;
+template <int NOUT>
+struct alignas(64) OutMaps {
+  CUtensorMap m[NOUT];
+};
+
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi, int RES = kResNone, int NOUT = 1>
 __global__ void __launch_bounds__((2 + Epi::kEpiWarps) * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
             const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-            const __grid_constant__ CUtensorMap tmC, const CoreParams p, const typename Epi::Params ep) {
+            const __grid_constant__ OutMaps<NOUT> tmC, const CoreParams p, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
-  gemm_body<BN, NSPLIT, NSUB, CL, EpiAdapter<BN, Epi>, RES>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, &tmC, smem_raw);
+  gemm_body<BN, NSPLIT, NSUB, CL, EpiAdapter<BN, Epi>, RES>(p, ep, &tmA0, &tmB0, &tmA1, &tmB1, &tmC.m[0], smem_raw);
 }
 
 static int env_flag_early(const char* name, int dflt) {
@@ -1295,6 +1302,10 @@ struct OutDesc {
   int64_t ld = 0, slab_stride = 0, slabs = 1;
   int row_bytes = 128;   // staging row of the epilogue: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   int64_t cols = 0;      // column extent of the map when it differs from N (padded rows), 0 = N
+  // sharded output (reduce-scatter GEMM): owners > 0 buffers of rows_per_owner rows each; ptr is ignored
+  int owners = 0;
+  int64_t rows_per_owner = 0;
+  void* owner_ptr[8] = {};
 };
 
 static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int tile_rows, int64_t batches, const char* what) {
@@ -1306,7 +1317,7 @@ static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int t
   return make_tmap_bf16_2d(tm, o.ptr, K, o.rows, o.ld, BK, what);  // box = 64 k-rows x 64 mn-elements
 }
 
-template <int BN, int NSPLIT, int NSUB, int CL, class Epi, int RES = kResNone>
+template <int BN, int NSPLIT, int NSUB, int CL, class Epi, int RES = kResNone, int NOUT = 1>
 static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const Operand* b1, int64_t M, int64_t N,
                   int64_t K, int m_fastest, const typename Epi::Params& ep, const OutDesc& od, cudaStream_t stream,
                   const char* name, int64_t batches = 1, int64_t splits = 1) {
@@ -1316,7 +1327,8 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   DINOX_REQUIRE(splits >= 1 && (splits == 1 || batches == 1), DINOX_E_BADARG, "%s: split-K cannot be batched", name);
   DINOX_REQUIRE(!(b0.mn_major && ((BN / NSPLIT / CL) % 64) != 0), DINOX_E_UNSUPPORTED,
                 "%s: MN-major B needs 64-element atoms per CTA at this tile shape", name);
-  CUtensorMap tA0, tB0, tA1, tB1, tC;
+  CUtensorMap tA0, tB0, tA1, tB1;
+  OutMaps<NOUT> tC;
   int rc;
   if ((rc = make_operand_tmap(&tA0, a0, K, BM, batches, "A"))) return rc;
   if ((rc = make_operand_tmap(&tB0, b0, K, BN / NSPLIT / CL, batches, "B"))) return rc;   // one box per (N sub-tile, CTA)
@@ -1327,10 +1339,19 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
     if ((rc = make_operand_tmap(&tA1, *a1, K, BM, batches, "A1"))) return rc;
     if ((rc = make_operand_tmap(&tB1, *b1, K, BN / NSPLIT / CL, batches, "B1"))) return rc;
   }
-  tC = tA0;
-  if (Epi::kUsesTmaStore) {
+  for (int i = 0; i < NOUT; ++i) tC.m[i] = tA0;
+  if (NOUT > 1) {
+    DINOX_REQUIRE(Epi::kUsesTmaStore && od.owners >= 1 && od.owners <= NOUT && od.rows_per_owner > 0 &&
+                      od.rows_per_owner % BM == 0 && od.rows_per_owner * od.owners >= M && splits == 1 && batches == 1,
+                  DINOX_E_BADARG, "%s: sharded output needs 1..%d owners with a multiple of %d rows each", name, NOUT, BM);
+    for (int i = 0; i < od.owners; ++i) {
+      DINOX_REQUIRE(od.owner_ptr[i], DINOX_E_BADARG, "%s: null shard pointer", name);
+      if ((rc = make_tmap_out_3d(&tC.m[i], od.owner_ptr[i], od.is_bf16 != 0, 1, od.rows_per_owner, N, od.ld,
+                                 od.rows_per_owner * od.ld, od.row_bytes, "C shard"))) return rc;
+    }
+  } else if (Epi::kUsesTmaStore) {
     DINOX_REQUIRE(od.ptr, DINOX_E_BADARG, "%s: output descriptor missing", name);
-    if ((rc = make_tmap_out_3d(&tC, od.ptr, od.is_bf16 != 0, od.slabs, M, od.cols ? od.cols : N, od.ld, od.slab_stride, od.row_bytes, "C"))) return rc;
+    if ((rc = make_tmap_out_3d(&tC.m[0], od.ptr, od.is_bf16 != 0, od.slabs, M, od.cols ? od.cols : N, od.ld, od.slab_stride, od.row_bytes, "C"))) return rc;
   }
   CoreParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -1341,13 +1362,14 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   p.batches = (int)batches;
   p.splits = (int)splits;
   p.kb_per_split = (int)((p.num_k_blocks + splits - 1) / splits);
+  p.rows_per_owner = NOUT > 1 ? (int)od.rows_per_owner : 0;
   DINOX_REQUIRE(splits == 1 || (int64_t)p.kb_per_split * (splits - 1) < p.num_k_blocks, DINOX_E_BADARG,
                 "%s: %lld splits leave an empty K range", name, (long long)splits);
   DINOX_REQUIRE(RES != kResA || (p.num_k_blocks <= kResKBlocks && !a0.mn_major && splits == 1), DINOX_E_UNSUPPORTED,
                 "%s: resident-A mode needs a K-major A operand with K <= %d", name, kResKBlocks * BK);
   DINOX_REQUIRE(RES != kResB || (p.num_k_blocks <= kResKBlocks && !b0.mn_major && splits == 1 && batches == 1),
                 DINOX_E_UNSUPPORTED, "%s: resident-B mode needs a K-major B operand with K <= %d", name, kResKBlocks * BK);
-  auto kern = gemm_kernel<BN, NSPLIT, NSUB, CL, Epi, RES>;
+  auto kern = gemm_kernel<BN, NSPLIT, NSUB, CL, Epi, RES, NOUT>;
   constexpr int smem = smem_bytes<BN, CL, Epi, RES, NSUB>();
   static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
   // the opt-in shared-memory size is a per-device function attribute
@@ -1506,6 +1528,38 @@ int dinox_gemm_bf16_splitk(const void* A, const void* B, float* C_partials, int6
   Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
   StoreArgs sa{C_partials, ldc, 0, 0, alpha, alpha_dev, nullptr, split_stride};
   return launch_store(M, N, a, b, K, m_fastest, sa, stream, 1, splits);
+}
+
+/* C = alpha * A @ B^T with the ROWS of C sharded over `owners` buffers: tile rows [o*rows_per_owner, ...) are
+ * reduce-added (cp.reduce.async.bulk.tensor .add.f32, performed in the owner's L2) into shard_ptrs[o], which may be
+ * peer-mapped memory of another GPU (NVLink).  Every data-parallel rank launching this with the same shard table
+ * performs the reduce-scatter of dW2 inside the GEMM epilogue, tile by tile, instead of a collective afterwards. */
+int dinox_gemm_bf16_reduce_scatter(const void* A, const void* B, float* const* shard_ptrs, int owners,
+                                   int64_t rows_per_owner, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                   int64_t ldc, int a_mn_major, int b_mn_major, float alpha, const float* alpha_dev,
+                                   dinox_stream_t stream) {
+  DINOX_REQUIRE(A && B && shard_ptrs && owners >= 1 && owners <= kMaxOwners, DINOX_E_BADARG,
+                "gemm_bf16_reduce_scatter: 1..%d shards", kMaxOwners);
+  DINOX_REQUIRE(rows_per_owner > 0 && rows_per_owner % BM == 0 && rows_per_owner * owners >= M, DINOX_E_BADARG,
+                "gemm_bf16_reduce_scatter: rows_per_owner must be a multiple of %d covering M", BM);
+  DINOX_REQUIRE(ldc >= N && (ldc * 4) % 16 == 0, DINOX_E_ALIGN, "gemm_bf16_reduce_scatter: ldc misaligned");
+  DINOX_REQUIRE(M > BM, DINOX_E_UNSUPPORTED, "gemm_bf16_reduce_scatter: needs more than one M tile");
+  int rc = require_sm100();
+  if (rc) return rc;
+  Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
+  EpiStore::Params ep{0, 1, alpha, alpha_dev, nullptr};
+  OutDesc od;
+  od.is_bf16 = 0; od.ld = ldc; od.owners = owners; od.rows_per_owner = rows_per_owner;
+  for (int i = 0; i < owners; ++i) {
+    DINOX_REQUIRE(shard_ptrs[i] && aligned16(shard_ptrs[i]), DINOX_E_ALIGN, "gemm_bf16_reduce_scatter: shard %d null or misaligned", i);
+    od.owner_ptr[i] = shard_ptrs[i];
+  }
+  if (N % 384 == 0)
+    return launch<384, 3, 1, 2, EpiStore, kResNone, kMaxOwners>(a, b, nullptr, nullptr, M, N, K, 0, ep, od, stream, "gemm_bf16_rs<384,pair>");
+  if (N % 256 == 0)
+    return launch<256, 1, 1, 2, EpiStore, kResNone, kMaxOwners>(a, b, nullptr, nullptr, M, N, K, 0, ep, od, stream, "gemm_bf16_rs<256,pair>");
+  set_error("gemm_bf16_reduce_scatter: N must be a multiple of 256 or 384 (got %lld)", (long long)N);
+  return DINOX_E_UNSUPPORTED;
 }
 
 int dinox_gemm_splitk_plan(int64_t M, int64_t N, int64_t K) {

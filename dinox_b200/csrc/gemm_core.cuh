@@ -58,6 +58,9 @@ struct CoreParams {
   int batches;                 // > 1: independent problems along a third tensor-map dimension
   int splits;                  // > 1: split-K, split s reduces k-blocks [s*kb_per_split, ...) into output slab s
   int kb_per_split;
+  int rows_per_owner;          // > 0: the output rows are sharded over several buffers (one tensor map each, e.g. the
+                               // peer-mapped gradient shards of the data-parallel ranks): M tile t goes to map
+                               // t*BM / rows_per_owner at local row t*BM % rows_per_owner.  Multiple of BM.  0 = one map.
 };
 
 constexpr int kResKBlocks = 6;   // resident-A mode holds up to 6 k-blocks (K <= 384) of this CTA's 128 A rows
@@ -544,7 +547,17 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
       sm100::mbar_wait(&ctl->tmem_full[acc_stage], acc_phase, 4);
       sm100::tc_fence_after();
 #if !DINOX_EXP_NO_EPI   // experiment knob: skip the epilogue math, keep the barrier protocol
-      Epi::tile(ep, p, tc, tmC, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
+      {
+        // sharded output: pick the owner's tensor map and address the tile by its row inside that shard
+        const CUtensorMap* tmCt = tmC;
+        TileCoord tce = tc;
+        if (p.rows_per_owner > 0) {
+          const int owner = (tc.m_tile * BM) / p.rows_per_owner;
+          tmCt = tmC + owner;
+          tce.m_tile = tc.m_tile - owner * (p.rows_per_owner / BM);
+        }
+        Epi::tile(ep, p, tce, tmCt, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
+      }
 #endif
       sm100::tc_fence_before();
       __syncwarp();

@@ -565,7 +565,7 @@ class _FusedHeadLoss(torch.autograd.Function):
     def forward(ctx, student_cls, student_patch, w1, b1, w2, b2, teacher_cls, teacher_patch, masks_weight, t_head,
                 loss_mod, center_patch, cfg, patch_index=None, params_in_place=None, teacher_index=None):
         (student_temp, teacher_temp, Vg, n_local, ibot_weight, teacher_mode, sk_iters, pg, update_center,
-         patch_momentum, grads_in_place) = cfg
+         patch_momentum, grads_in_place, w2_sink) = cfg
         dev = student_cls.device
         D = student_cls.shape[1]
         K = w2.shape[0]
@@ -705,7 +705,7 @@ class _FusedHeadLoss(torch.autograd.Function):
             ctx.save_for_backward(xs, a_s, hs_e, gt, db2p, w1s, w2s)
             ctx.plan = plan
             ctx.params = params_in_place if params_in_place is not None else (w1, b1, w2, b2)
-            ctx.readback, ctx.grads_in_place = readback, grads_in_place
+            ctx.readback, ctx.grads_in_place, ctx.w2_sink = readback, grads_in_place, w2_sink
             ctx.in_dtypes = (student_cls.dtype, None if student_patch is None else student_patch.dtype)
             ctx.patch_index = patch_index
             ctx.patch_shape = None if student_patch is None else tuple(student_patch.shape)
@@ -745,8 +745,15 @@ class _FusedHeadLoss(torch.autograd.Function):
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             # dW2 (K, D) += g * G^T . HsE   (A = G with the prototypes as M; B = HsE MN-major)
             with ops.TIMER.region("gemm_dW2"):
-                emit("w2", w2, lambda out, acc: ops.gemm_bf16(
-                    gt, hs_e, a_mn_major=rb, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
+                sink = ctx.w2_sink
+                if sink is not None:
+                    # data parallel: every output tile is reduce-added into the OWNER rank's peer-mapped gradient shard
+                    # (mean over ranks) - GEMM and reduce-scatter in one kernel, no (K, D) gradient on this rank
+                    ops.gemm_bf16_reduce_scatter(gt, hs_e, sink.ptrs, sink.rows, sink.cols, a_mn_major=rb, b_mn_major=True,
+                                                 alpha=1.0 / sink.world, alpha_dev=up)
+                else:
+                    emit("w2", w2, lambda out, acc: ops.gemm_bf16(
+                        gt, hs_e, a_mn_major=rb, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
             db2 = ops.cols_sum(db2p)
             emit("b2", b2, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out, alpha_dev=up))
         # dH per entry = G . W2  (B = W2 MN-major), then sum the entries of each row
@@ -784,7 +791,8 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
                          ibot_weight: float = 1.0, patch_center_momentum: Optional[float] = None,
                          update_center: bool = True, patch_index: Optional[torch.Tensor] = None,
                          grads_in_place: bool = False,
-                         teacher_patch_index: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                         teacher_patch_index: Optional[torch.Tensor] = None,
+                         w2_grad_shards=None) -> Dict[str, torch.Tensor]:
     """Projection head + multi-crop DINO CE (+ iBOT masked-patch CE) in one fused path.
 
     Equivalent to `dino_loss(student_head(student_cls), teacher_head(teacher_cls), ...)` of the reference
@@ -799,6 +807,9 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
     token tensors themselves (contiguous (..., D), e.g. the (B*Vg, T, D) output that `feats[:, 1:]` slices,
     scripts/phase5_big_run.py:1741-1747): the masked rows are gathered by the staging kernel and their
     gradients scattered back, so the caller never materialises `tokens[mask]`.
+    `w2_grad_shards` (an `optim.PeerGradShards` of `student_head[2].weight`, data parallel only): dW2 is not
+    written to `.grad` / returned; the backward GEMM reduce-adds its tiles into the owner ranks' peer-mapped shards
+    (fused GEMM + reduce-scatter over NVLink), to be consumed by `ShardedFusedAdamW(grad_shards=...)`.
     `teacher_patch_index` names the rows of the TEACHER token tensor only (`student_patch` then holds materialised
     (Mm, D) rows): what `token_fork` + `LossHeadStep` use so that the iBOT gradient is added into the Gram-anchoring
     gradient of the same token tensor instead of travelling as a second dense tensor.
@@ -827,7 +838,8 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
                 raise ValueError("teacher_patch_index needs a contiguous teacher token tensor")
     cfg = (student_temp, teacher_temp, dino_loss.n_global, dino_loss.n_local, ibot_weight, dino_loss.teacher_mode,
            dino_loss.sk_iterations, dino_loss.process_group, update_center,
-           dino_loss.center_momentum if patch_center_momentum is None else patch_center_momentum, bool(grads_in_place))
+           dino_loss.center_momentum if patch_center_momentum is None else patch_center_momentum, bool(grads_in_place),
+           w2_grad_shards)
     params = (student_head[0].weight, student_head[0].bias, student_head[2].weight, student_head[2].bias)
     # in-place mode: the parameters enter detached (no AccumulateGrad node takes part in the backward - theirs would
     # tie a captured backward to whatever stream first created them) and the real ones ride along to receive .grad

@@ -197,6 +197,24 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_m
     return out
 
 
+def gemm_bf16_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shard_ptrs: Sequence[int], rows_per_owner: int, ldc: int,
+                             *, a_mn_major: bool = False, b_mn_major: bool = False, alpha: float = 1.0,
+                             alpha_dev: Optional[torch.Tensor] = None) -> None:
+    """alpha * A @ B^T reduce-added, tile by tile, into the row shards named by `shard_ptrs` (device addresses, one
+    per data-parallel rank, possibly peer-mapped): the reduce-scatter happens in the GEMM epilogue."""
+    _chk_cuda(a, b, alpha_dev)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise _ext.DinoxError("gemm_bf16_reduce_scatter needs bf16 operands")
+    M, Ka = (a.shape[1], a.shape[0]) if a_mn_major else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn_major else b.shape
+    if Ka != Kb:
+        raise _ext.DinoxError(f"gemm_bf16_reduce_scatter: reduction dims differ ({Ka} vs {Kb})")
+    n = len(shard_ptrs)
+    ptrs = (ctypes.c_void_p * n)(*[int(p) for p in shard_ptrs])
+    _ext.call("dinox_gemm_bf16_reduce_scatter", _p(a), _p(b), ptrs, n, int(rows_per_owner), M, N, Ka, _rowmajor(a),
+              _rowmajor(b), int(ldc), int(a_mn_major), int(b_mn_major), float(alpha), _p(alpha_dev), _stream())
+
+
 def gemm_splitk_plan(M: int, N: int, K: int) -> int:
     return int(_ext.lib().dinox_gemm_splitk_plan(M, N, K))
 

@@ -119,6 +119,40 @@ def shard_layout(shapes, world: int, min_numel: int = 1 << 20):
     return out
 
 
+class PeerGradShards:
+    """Row shards of one large gradient (the head's dW2) in SYMMETRIC memory: rank r owns rows
+    [r*rows, (r+1)*rows) as an fp32 accumulator that every rank has mapped into its address space
+    (torch.distributed._symmetric_memory: CUDA VMM handles exchanged once, NVLink / NVSwitch peer access).
+    The backward GEMM of every rank reduce-adds each of its output tiles straight into the owner's accumulator
+    (`dinox_gemm_bf16_reduce_scatter`): the gradient reduce-scatter of a data-parallel step happens inside the
+    GEMM epilogue, tile by tile, and the full (K, D) gradient is never materialised on any rank.
+
+    Protocol (all ranks): accumulate over the micro-steps of a window -> any collective (ShardedFusedAdamW issues
+    one) orders every rank's last kernel before the owner reads -> owner applies its optimizer slice and zeroes the
+    accumulator -> the parameter all-gather orders the zeroing before the next window's adds."""
+
+    def __init__(self, param: torch.Tensor, process_group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.pg = None if process_group in (None, True) else process_group
+        grp = self.pg if self.pg is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(grp), dist.get_rank(grp)
+        K, D = param.shape
+        if K % (128 * self.world) or self.world > 8:
+            raise ValueError(f"PeerGradShards: {K} rows do not split into {self.world} shards of whole 128-row tiles (<= 8 ranks)")
+        self.rows, self.cols = K // self.world, D
+        self.acc = symm.empty(self.rows, D, dtype=torch.float32, device=param.device)
+        self.acc.zero_()
+        self._hdl = symm.rendezvous(self.acc, grp.group_name)
+        self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+
+    def zero_(self) -> None:
+        from . import ops
+        ops.fill_(self.acc.view(-1), 0.0)
+
+
 class ShardedFusedAdamW:
     """Data-parallel optimizer step with the big tensors' AdamW state sharded over the ranks (SURVEY 8f next
     #2, second half; the reference is single-device - scripts/phase5_big_run.py:1781-1796 - so this is the
@@ -136,7 +170,7 @@ class ShardedFusedAdamW:
     `consolidated_state_dict()` returns torch.optim.AdamW's layout for checkpoints."""
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 process_group=None, shard_min_numel: int = 1 << 20):
+                 process_group=None, shard_min_numel: int = 1 << 20, grad_shards=None):
         import torch.distributed as dist
         self.params = [p for p in params]
         # torch.optim-style single parameter group: the reference loop writes `param_groups[i]['lr']` every step
@@ -157,6 +191,14 @@ class ShardedFusedAdamW:
                                  grad=torch.empty_like(own) if sharded else None)
         self._plans = {}
         self.last_grad_norm: Optional[torch.Tensor] = None
+        # {parameter: PeerGradShards}: gradients that arrive already reduce-scattered (mean over ranks) in the
+        # owner's peer-mapped accumulator, written by the fused GEMM + reduce-scatter of the backward pass
+        self.grad_shards = dict(grad_shards or {})
+        for p, sh in self.grad_shards.items():
+            lay = self.layout[[id(q) for q in self.params].index(id(p))]
+            if not lay[0] or lay[1] != sh.rows:
+                raise ValueError("grad_shards: the parameter is not sharded by this optimizer with the same row split")
+        self._token = torch.zeros(1, device=self.params[0].device) if self.grad_shards else None
 
     def _plan(self, key, items):
         """items: [(param slice, grad, exp_avg, exp_avg_sq)]; rebuilt when a gradient tensor moved"""
@@ -177,14 +219,19 @@ class ShardedFusedAdamW:
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0):
         import torch.distributed as dist
-        live = [(p, lay) for p, lay in zip(self.params, self.layout) if p.grad is not None]
+        fused = [p for p in self.params if p in self.grad_shards]
+        live = [(p, lay) for p, lay in zip(self.params, self.layout) if p.grad is not None or p in self.grad_shards]
         if not live:
             return
         sharded = [p for p, (s, _) in live if s]
         repl = [p for p, (s, _) in live if not s]
         works = []
         if self.world > 1:
+            if fused:   # every rank's reduce-scatter GEMMs are complete once this (4-byte) collective is
+                dist.all_reduce(self._token, group=self.pg)
             for p in sharded:   # mean over replicas, each rank receives its rows
+                if p in self.grad_shards:
+                    continue
                 works.append(dist.reduce_scatter_tensor(self.state[p]["grad"].view(-1), p.grad.view(-1),
                                                         op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
             for p in repl:
@@ -202,11 +249,14 @@ class ShardedFusedAdamW:
             if not ps:
                 continue
             use_shard_grad = key == "sharded" and self.world > 1
-            items = [(self.state[p]["own"], self.state[p]["grad"] if use_shard_grad else p.grad,
+            items = [(self.state[p]["own"],
+                      self.grad_shards[p].acc if p in self.grad_shards else (self.state[p]["grad"] if use_shard_grad else p.grad),
                       self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) for p in ps]
             h = self._plan(key, items)
             _ext.call("dinox_adamw_step", h, float(lr), float(b1), float(b2), float(eps), float(wd),
                       1.0 - b1 ** t, 1.0 - b2 ** t, float(grad_scale), ctypes.c_void_p(sq[slot:].data_ptr()), stream)
+        for p in fused:   # consumed: ready for the next accumulation window (the all-gather below orders this
+            self.grad_shards[p].zero_()   # before any rank's next adds)
         sq.square_()
         if self.world > 1:
             if sharded:

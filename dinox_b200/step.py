@@ -55,6 +55,8 @@ class LossHeadStep:
         # this loop updates parameters only through dinox entry points (ema_update bumps the weight epoch), so the
         # bf16 operand copies of the head weights are re-cast only when a weight changed
         losshead.set_weight_cache("tracked")
+        # data parallel: an optim.PeerGradShards of student_head[2].weight turns the dW2 GEMM into GEMM + reduce-scatter
+        self.w2_grad_shards = None
         self.micro = 0
         self._graphs: Dict[int, dict] = {}
         self.launches_per_graph = 0
@@ -172,7 +174,8 @@ class LossHeadStep:
             f["student_cls"], f["teacher_cls"], self.student_head, self.teacher_head, self.dino_loss,
             self.student_temp, self.teacher_temp, student_patch=sp, teacher_patch=tp,
             masks_weight=f.get("masks_weight"), center_patch=self.center_patch if sp is not None else None,
-            ibot_weight=self.ibot_weight, patch_index=idx, teacher_patch_index=t_idx, grads_in_place=True)
+            ibot_weight=self.ibot_weight, patch_index=idx, teacher_patch_index=t_idx, grads_in_place=True,
+            w2_grad_shards=self.w2_grad_shards)
         terms, weights = [out["loss"]], [1.0]
         if gram is not None:
             if side is not None:

@@ -148,6 +148,17 @@ DINOX_API int dinox_gemm_bf16_splitk(const void* A, const void* B, float* C_part
                                      int splits, int a_mn_major, int b_mn_major, float alpha,
                                      const float* alpha_dev, int m_fastest, dinox_stream_t stream);
 DINOX_API int dinox_gemm_splitk_plan(int64_t M, int64_t N, int64_t K);
+/* GEMM fused with the reduce-scatter of its output rows over the data-parallel ranks (the gradient
+ * reduction of dW2 that follows `loss.backward()` at scripts/phase5_big_run.py:1772-1796 in a DDP run of the loop):
+ * C = alpha*(*alpha_dev) * A @ B^T is never stored locally; the tile rows [o*rows_per_owner, (o+1)*rows_per_owner)
+ * are reduce-ADDED into shard_ptrs[o] ((rows_per_owner, ldc) fp32), which may be memory of a PEER GPU mapped into
+ * this process (CUDA IPC / symmetric memory over NVLink).  `shard_ptrs` is a HOST array of `owners` (<= 8) device
+ * pointers; rows_per_owner is a multiple of 128.  Every rank calls it with the same table: afterwards (once all
+ * ranks' kernels have completed - order them with any collective) shard o holds the sum over ranks of its rows. */
+DINOX_API int dinox_gemm_bf16_reduce_scatter(const void* A, const void* B, float* const* shard_ptrs, int owners,
+                                             int64_t rows_per_owner, int64_t M, int64_t N, int64_t K, int64_t lda,
+                                             int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, float alpha,
+                                             const float* alpha_dev, dinox_stream_t stream);
 /* diagnostics: number of co-resident clusters of `cluster_size` CTAs for the pass-1 kernel */
 DINOX_API int dinox_debug_max_active_clusters(int cluster_size);
 
