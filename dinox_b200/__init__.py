@@ -11,7 +11,7 @@ _LAZY = {
     "DINOLoss", "DinoStudentTeacher", "compute_gram_matrix", "compute_gram_anchoring_loss",
     "ema_update", "_ema_update", "fused_head_dino_loss", "LossHead", "entropy_diagnostics",
     "sinkhorn_knopp_teacher", "KoLeoLoss", "FusedLossHead", "ProjectionHead", "combine_losses",
-    "set_weight_cache", "invalidate_weight_cache",
+    "set_weight_cache", "invalidate_weight_cache", "set_contraction_precision", "token_fork",
 }
 
 

@@ -183,6 +183,13 @@ SIGNATURES = {
     "dinox_fill_f32": (c_int, [c_void_p, c_i64, c_f32, c_void_p]),
     "dinox_scalar_combine": (c_int, [c_void_p, c_void_p, c_int, c_f32, c_void_p, c_void_p, c_void_p]),
     "dinox_scalar_fanout": (c_int, [c_void_p, c_void_p, c_int, c_f32, c_void_p, c_void_p]),
+    "dinox_split_bf16": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_void_p]),
+    "dinox_gelu_fwd_f32": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
+    "dinox_gelu_bwd_f32_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_gelu_bwd_f32": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dinox_normalize_tokens_f32": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "dinox_sqdiff_workspace_bytes": (c_size, []),
+    "dinox_sqdiff_f32": (c_int, [c_void_p, c_void_p, c_i64, c_f32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dinox_adamw_plan_create": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dinox_adamw_plan_destroy": (c_int, [c_void_p]),
     "dinox_adamw_step": (c_int, [c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,

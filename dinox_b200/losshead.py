@@ -237,7 +237,7 @@ def compute_gram_matrix(feats: torch.Tensor) -> torch.Tensor:
     """Gram matrix of L2-normalised tokens, (B, N, D) -> (B, N, N)  (scripts/phase5_big_run.py:723-728)."""
     if not feats.is_cuda:
         raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
-    return _GramMatrix.apply(feats)
+    return _GramMatrixFp32.apply(feats) if _fp32_mode() else _GramMatrix.apply(feats)
 
 
 class _GramAnchor(torch.autograd.Function):
@@ -276,7 +276,8 @@ def compute_gram_anchoring_loss(student_feats: torch.Tensor, teacher_feats: torc
         raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
     if student_feats.shape != teacher_feats.shape or student_feats.dim() != 3:
         raise ValueError("student/teacher feats must both be (B, T, D)")
-    return _GramAnchor.apply(student_feats, teacher_feats.detach())
+    fn = _GramAnchorFp32 if _fp32_mode() else _GramAnchor
+    return fn.apply(student_feats, teacher_feats.detach())
 
 
 # =================================================================================================
@@ -369,6 +370,145 @@ def _to_bf16_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# -------------------------------------------------------------------------------------------------
+# Contraction precision of the drop-in modules
+# -------------------------------------------------------------------------------------------------
+_PRECISION = ["auto"]
+
+
+def set_contraction_precision(mode: str) -> str:
+    """Precision of the dense contractions behind `ProjectionHead`, `compute_gram_matrix` and
+    `compute_gram_anchoring_loss`:
+
+    "auto" (default) - what the reference does on the same call: inside `torch.autocast` (its `--amp` flag) bf16
+             tensor-core operands with fp32 accumulation; OUTSIDE autocast (the reference's default,
+             scripts/phase5_big_run.py:1322) fp32-faithful products - three bf16 GEMMs on hi/lo operand splits, ~16
+             mantissa bits per product (see csrc/precise.cu).
+    "bf16" - always bf16 operands (fastest; what `fused_head_dino_loss` always uses).
+    "fp32" - always the fp32-faithful products.
+    Returns the previous mode."""
+    if mode not in ("auto", "bf16", "fp32"):
+        raise ValueError(f"contraction precision {mode!r}: expected 'auto', 'bf16' or 'fp32'")
+    prev = _PRECISION[0]
+    _PRECISION[0] = mode
+    return prev
+
+
+@contextlib.contextmanager
+def contraction_precision(mode: str):
+    """`with contraction_precision("bf16"): ...` - scoped form of set_contraction_precision."""
+    prev = set_contraction_precision(mode)
+    try:
+        yield
+    finally:
+        _PRECISION[0] = prev
+
+
+def _fp32_mode() -> bool:
+    m = _PRECISION[0]
+    return m == "fp32" or (m == "auto" and not torch.is_autocast_enabled())
+
+
+_SPLIT_CACHE: Dict[int, Tuple] = {}
+
+
+def split_weight(p: torch.Tensor):
+    """(hi, lo) bf16 split of a weight, cached like `bf16_weight` (same invalidation rules, "tracked" mode only)."""
+    import weakref
+    key = id(p)
+    hit = _SPLIT_CACHE.get(key)
+    if (hit is not None and hit[0]() is p and _WEIGHT_CACHE_MODE[0] == "tracked" and hit[1] == p._version
+            and hit[2] == p.data_ptr() and hit[3] == _WEIGHT_EPOCH[0]):
+        return hit[4]
+    pair = ops.split_bf16(p.detach())
+    if len(_SPLIT_CACHE) > 64:
+        for k in [k for k, v in _SPLIT_CACHE.items() if v[0]() is None]:
+            del _SPLIT_CACHE[k]
+    _SPLIT_CACHE[key] = (weakref.ref(p), p._version, p.data_ptr(), _WEIGHT_EPOCH[0], pair)
+    return pair
+
+
+class _HeadFnFp32(torch.autograd.Function):
+    """The projection head in the fp32-faithful mode: every contraction (2 forward, 4 backward) is a three-GEMM
+    product of hi/lo splits; GELU and the bias sums stay in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        xs = ops.split_bf16(x.detach())
+        w1s, w2s = split_weight(w1), split_weight(w2)
+        a = ops.gemm3(xs, w1s, bias_n=b1.detach())
+        hs = ops.split_bf16(ops.gelu_fwd_f32(a))
+        z = ops.gemm3(hs, w2s, bias_n=b2.detach())
+        ctx.save_for_backward(a, *xs, *hs, *w1s, *w2s)
+        ctx.in_dtype = x.dtype
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        a, xh, xl, hh, hl, w1h, w1l, w2h, w2l = ctx.saved_tensors
+        dzf = dz if (dz.dtype == torch.float32 and dz.stride(-1) == 1) else dz.float().contiguous()
+        dzs = ops.split_bf16(dzf)
+        db2 = ops.cols_sum(dzf)
+        dw2 = ops.gemm3(dzs, (hh, hl), a_mn_major=True, b_mn_major=True)          # dz^T h   (K, D)
+        dh = ops.gemm3(dzs, (w2h, w2l), b_mn_major=True)                          # dz W2    (rows, D)
+        da, part = ops.gelu_bwd_f32(dh, a)
+        db1 = ops.cols_sum(part)
+        das = ops.split_bf16(da)
+        dw1 = ops.gemm3(das, (xh, xl), a_mn_major=True, b_mn_major=True)          # da^T x   (D, D)
+        dx = ops.gemm3(das, (w1h, w1l), b_mn_major=True)                          # da W1    (rows, D)
+        return dx.to(ctx.in_dtype), dw1, db1, dw2, db2
+
+
+class _GramMatrixFp32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats):
+        xn, inv = ops.normalize_tokens_f32(feats, skip=0)
+        xs = ops.split_bf16(xn)
+        gram = ops.gemm3_batched(xs, xs)
+        ctx.save_for_backward(feats, *xs, inv)
+        return gram
+
+    @staticmethod
+    def backward(ctx, dg):
+        feats, xh, xl, inv = ctx.saved_tensors
+        Bt, T, D = feats.shape
+        dgs = ops.split_bf16(dg.float().contiguous())
+        dxn = ops.gemm3_batched(dgs, (xh, xl), b_mn_major=True)                                   # dG   @ Xn
+        dxn2 = ops.gemm3_batched(dgs, (xh, xl), a_mn_major=True, b_mn_major=True)                 # dG^T @ Xn
+        ops.axpby(dxn, 1.0, dxn2, 1.0, out=dxn)
+        grad = torch.empty(Bt, T, D, dtype=torch.float32, device=dg.device)
+        ops.normalize_tokens_bwd(feats, dxn, inv, grad, skip=0)
+        return grad.to(feats.dtype)
+
+
+class _GramAnchorFp32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student_feats, teacher_feats):
+        Bt, T, D = student_feats.shape
+        xs_f, inv_s = ops.normalize_tokens_f32(student_feats, skip=1)
+        xt_f, _ = ops.normalize_tokens_f32(teacher_feats, skip=1)
+        xs, xt = ops.split_bf16(xs_f), ops.split_bf16(xt_f)
+        gs, gt = ops.gemm3_batched(xs, xs), ops.gemm3_batched(xt, xt)
+        n = Bt * (T - 1) * (T - 1)
+        need_grad = student_feats.requires_grad
+        loss, delta = ops.sqdiff(gs, gt, 1.0 / n, want_delta=need_grad)
+        if need_grad:
+            ctx.save_for_backward(student_feats, *xs, inv_s, delta)
+            ctx.n = n
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        student_feats, xh, xl, inv_s, delta = ctx.saved_tensors
+        Bt, T, D = student_feats.shape
+        # dL/dXn = (dG + dG^T) Xn = (4/n) * Delta @ Xn   (Delta symmetric)
+        dxn = ops.gemm3_batched(ops.split_bf16(delta), (xh, xl), b_mn_major=True, alpha=4.0 / ctx.n)
+        grad = torch.empty(Bt, T, D, dtype=torch.float32, device=g.device)
+        up = g.to(torch.float32).reshape(1).contiguous()
+        ops.normalize_tokens_bwd(student_feats, dxn, inv_s, grad, skip=1, scale_dev=up)
+        return grad.to(student_feats.dtype), None
+
+
 class _HeadFn(torch.autograd.Function):
     """logits = W2 . gelu(W1 . x + b1) + b2 with bf16 tensor-core operands / fp32 accumulation, and
     the matching backward GEMMs (operands taken in place through MN-major descriptors)."""
@@ -410,6 +550,9 @@ class ProjectionHead(nn.Sequential):
             raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
+        if _fp32_mode():
+            z = _HeadFnFp32.apply(x2, self[0].weight, self[0].bias, self[2].weight, self[2].bias)
+            return z.reshape(*lead, z.shape[-1])
         out_dtype = torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
         z = _HeadFn.apply(x2, self[0].weight, self[0].bias, self[2].weight, self[2].bias, out_dtype)
         return z.reshape(*lead, z.shape[-1])

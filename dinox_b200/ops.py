@@ -190,7 +190,8 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_m
     if out is None:
         if accumulate:
             raise _ext.DinoxError("accumulate=True needs an output tensor")
-        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+        q = 16 // torch.empty((), dtype=out_dtype).element_size()      # 16-byte row pitch for the TMA store
+        out = torch.empty(M, (N + q - 1) // q * q, dtype=out_dtype, device=a.device)[:, :N]
     _ext.call("dinox_gemm_bf16", _p(a), _p(b), _p(out), M, N, Ka, _rowmajor(a), _rowmajor(b), _rowmajor(out),
               int(a_mn_major), int(b_mn_major), DT[out.dtype], int(accumulate), float(alpha), _p(alpha_dev),
               _p(bias_n), int(m_fastest), _stream())
@@ -550,6 +551,85 @@ def scalar_fanout(upstream: torch.Tensor, weights: Sequence[float], scale: float
     w = (ctypes.c_float * n)(*[float(x) for x in weights])
     _ext.call("dinox_scalar_fanout", _p(up), w, n, float(scale), _p(out), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32-faithful contraction mode: hi/lo bf16 splits and three-GEMM products
+# ------------------------------------------------------------------------------------------------
+def split_bf16(x: torch.Tensor):
+    """(hi, lo) bf16 with x ~= hi + lo to ~16 mantissa bits.  x: (rows, cols) or (batch, rows, cols) with unit stride
+    in the last dimension (any float dtype).  The outputs have a 16-byte row pitch (the TMA maps of the GEMMs need it)
+    and are returned as views of shape x.shape."""
+    _chk_cuda(x)
+    cols = x.shape[-1]
+    x2 = x.reshape(-1, cols)
+    if x2.stride(1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < cols):
+        x2 = x2.contiguous()
+    ldd = (cols + 7) // 8 * 8
+    hi = torch.empty(x2.shape[0], ldd, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x2.shape[0], ldd, dtype=torch.bfloat16, device=x.device)
+    _ext.call("dinox_split_bf16", _p(x2), DT[x2.dtype], x2.shape[0], cols, x2.stride(0) if x2.shape[0] > 1 else cols,
+              _p(hi), _p(lo), ldd, _stream())
+    lead = tuple(x.shape[:-1])
+    view = lambda t: t.view(*lead, ldd)[..., :cols]
+    return view(hi), view(lo)
+
+
+def gemm3(a, b, *, a_mn_major=False, b_mn_major=False, out=None, accumulate=False, alpha=1.0, alpha_dev=None, bias_n=None):
+    """fp32-grade C (+)= alpha * A @ B^T from hi/lo splits a = (a_hi, a_lo), b = (b_hi, b_lo): three tensor-core GEMMs
+    (hi.hi + hi.lo + lo.hi) accumulated in fp32."""
+    (ah, al), (bh, bl) = a, b
+    kw = dict(a_mn_major=a_mn_major, b_mn_major=b_mn_major, alpha=alpha, alpha_dev=alpha_dev)
+    out = gemm_bf16(ah, bh, out=out, accumulate=accumulate, bias_n=bias_n, **kw)
+    gemm_bf16(ah, bl, out=out, accumulate=True, **kw)
+    gemm_bf16(al, bh, out=out, accumulate=True, **kw)
+    return out
+
+
+def gemm3_batched(a, b, *, a_mn_major=False, b_mn_major=False, alpha=1.0, alpha_dev=None):
+    (ah, al), (bh, bl) = a, b
+    kw = dict(a_mn_major=a_mn_major, b_mn_major=b_mn_major, alpha=alpha, alpha_dev=alpha_dev)
+    out = gemm_bf16_batched(ah, bh, **kw)
+    gemm_bf16_batched(ah, bl, out=out, accumulate=True, **kw)
+    gemm_bf16_batched(al, bh, out=out, accumulate=True, **kw)
+    return out
+
+
+def gelu_fwd_f32(a: torch.Tensor) -> torch.Tensor:
+    h = torch.empty_like(a)
+    _ext.call("dinox_gelu_fwd_f32", _p(a), a.numel(), _p(h), _stream())
+    return h
+
+
+def gelu_bwd_f32(dh: torch.Tensor, a: torch.Tensor, scale_dev: Optional[torch.Tensor] = None):
+    rows, D = a.shape
+    da = torch.empty(rows, D, dtype=torch.float32, device=a.device)
+    n_part = int(_ext.lib().dinox_gelu_bwd_f32_workspace_bytes(rows, D)) // (4 * D)
+    part = torch.empty(n_part, D, dtype=torch.float32, device=a.device)
+    _ext.call("dinox_gelu_bwd_f32", _p(dh), _p(a), rows, D, _p(scale_dev), _p(da), _p(part), _stream())
+    return da, part
+
+
+def normalize_tokens_f32(feats: torch.Tensor, skip: int = 1):
+    _chk_cuda(feats)
+    Bt, T, D = feats.shape
+    if feats.stride(2) != 1:
+        feats = feats.contiguous()
+    xn = torch.empty(Bt, T - skip, D, dtype=torch.float32, device=feats.device)
+    inv = torch.empty(Bt, T - skip, dtype=torch.float32, device=feats.device)
+    _ext.call("dinox_normalize_tokens_f32", _p(feats), DT[feats.dtype], Bt, T, D, feats.stride(0), feats.stride(1), skip,
+              _p(xn), _p(inv), _stream())
+    return xn, inv
+
+
+def sqdiff(a: torch.Tensor, b: torch.Tensor, scale: float, want_delta: bool = True):
+    """(scale * sum (a - b)^2, a - b) for contiguous fp32 tensors of one shape."""
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype == torch.float32
+    delta = torch.empty_like(a) if want_delta else None
+    loss = torch.empty((), dtype=torch.float32, device=a.device)
+    ws = torch.empty(int(_ext.lib().dinox_sqdiff_workspace_bytes()), dtype=torch.uint8, device=a.device)
+    _ext.call("dinox_sqdiff_f32", _p(a), _p(b), a.numel(), float(scale), _p(delta), _p(loss), _p(ws), _stream())
+    return loss, delta
 
 
 def fill_(t: torch.Tensor, v: float = 0.0) -> torch.Tensor:

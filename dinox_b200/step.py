@@ -148,6 +148,12 @@ class LossHeadStep:
         return out
 
     def _losses(self, f):
+        # this step is the bf16 tensor-core configuration of the benchmark (BASELINE.json: bf16 operands, fp32
+        # accumulation) whatever the global contraction precision of the drop-in modules is
+        with losshead.contraction_precision("bf16"):
+            return self._losses_bf16(f)
+
+    def _losses_bf16(self, f):
         """Forward of all loss terms.  Gram anchoring is independent of the head until the final sum: it is
         issued first, on a side stream, and its small kernels (and, by autograd's stream rule, their
         backward) run beside the head's GEMMs instead of between them."""

@@ -328,6 +328,29 @@ DINOX_API int dinox_scalar_fanout(const float* upstream, const float* weights, i
                                   float* out, dinox_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32-faithful contraction mode.  The reference without `--amp` (its default, scripts/phase5_big_run.py:1322)
+ * runs nn.Linear (zoo/arch.py:252-256) and torch.bmm (:727) in true fp32.  The drop-in reproduces that on the bf16
+ * tensor pipe by evaluating every contraction as three GEMMs on hi/lo bf16 splits of the fp32 operands
+ * (A_hi.B_hi + A_hi.B_lo + A_lo.B_hi, fp32 accumulation; ~16 mantissa bits per product).  These are the
+ * element-wise helpers of that mode; the GEMMs themselves are dinox_gemm_bf16[_batched] with accumulate = 1.
+ * ------------------------------------------------------------------------------------------ */
+/* hi = bf16(x), lo = bf16(x - hi) for a (rows, cols) matrix with row pitch ld_src; outputs have pitch ld_dst */
+DINOX_API int dinox_split_bf16(const void* src, int dtype, int64_t rows, int64_t cols, int64_t ld_src, void* hi,
+                               void* lo, int64_t ld_dst, dinox_stream_t stream);
+DINOX_API int dinox_gelu_fwd_f32(const float* a, int64_t n, float* h, dinox_stream_t stream);
+DINOX_API size_t dinox_gelu_bwd_f32_workspace_bytes(int64_t rows, int64_t D);
+/* da = dh * (*scale_dev) * gelu'(a) in fp32; colsum_partial (workspace) holds per-16-row-slab column sums */
+DINOX_API int dinox_gelu_bwd_f32(const float* dh, const float* a, int64_t rows, int64_t D, const float* scale_dev,
+                                 float* da, float* colsum_partial, dinox_stream_t stream);
+DINOX_API int dinox_normalize_tokens_f32(const void* feats, int dtype, int64_t batch, int64_t tokens_total, int64_t D,
+                                         int64_t stride_b, int64_t stride_t, int skip, float* xn, float* inv_norm,
+                                         dinox_stream_t stream);
+DINOX_API size_t dinox_sqdiff_workspace_bytes(void);
+/* loss_out = scale * sum (a - b)^2 over n elements (fixed order), delta = a - b (optional)  - F.mse_loss, :738 */
+DINOX_API int dinox_sqdiff_f32(const float* a, const float* b, int64_t n, float scale, float* delta, float* loss_out,
+                               void* workspace, dinox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * a11 KoLeo regulariser on head outputs (scripts/phase5_big_run.py:742-773, wired at :1764-1766):
  *   x = z / max(||z||, 1e-12);  d_i = min_{j != i} ||x_i - x_j||;  loss = -mean_i log(d_i + eps).
  * dinox_koleo_rownorm: inv_norm[r] (and an optional bf16 copy of z for the ranking GEMM).

@@ -35,3 +35,18 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
     return load
+
+
+@pytest.fixture(autouse=True)
+def _bf16_contractions_by_default(request):
+    """GPU tests written against the bf16-operand policy (the oracle's policy="bf16") pin it; the fp32-faithful
+    mode that the drop-ins select outside torch.autocast has its own tests (tests/test_gpu_fp32_mode.py), which
+    set the precision themselves."""
+    import torch
+    if "gpu" not in request.keywords or not torch.cuda.is_available():
+        yield
+        return
+    from dinox_b200 import losshead
+    prev = losshead.set_contraction_precision("bf16")
+    yield
+    losshead.set_contraction_precision(prev)

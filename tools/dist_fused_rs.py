@@ -39,11 +39,19 @@ def make(fused: bool):
     return st, opt, head
 
 
-def window(st, opt, seed):
-    """one accumulation window on this rank's crops: ACC micro-steps (fwd + bwd), optimizer step"""
+def batches(seed):
+    """this rank's ACC micro-batches of a window, resident on the device"""
+    out = []
     for m in range(ACC):
         f = synth.feature_batch(sh, synth.seeded_generator(seed * 10 + m, rank), patches_from_tokens=True)
-        fd = {k: (v.to(dev).requires_grad_(True) if k.startswith("student") else v.to(dev)) for k, v in f.items()}
+        out.append({k: v.to(dev) for k, v in f.items()})
+    return out
+
+
+def window(st, opt, feats):
+    """one accumulation window on this rank's crops: ACC micro-steps (fwd + bwd), optimizer step"""
+    for f in feats:
+        fd = {k: (v.detach().requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()}
         out, loss = st._losses(fd)
         loss.backward()
     opt.step()
@@ -81,8 +89,9 @@ dist.barrier()
 
 # ---- 2. optimizer over two windows
 for w in range(2):
-    window(st_a, opt_a, 20 + w)
-    window(st_b, opt_b, 20 + w)
+    fb = batches(20 + w)
+    window(st_a, opt_a, fb)
+    window(st_b, opt_b, fb)
 torch.cuda.synchronize()
 errs = [rel(b, a) for a, b in zip(head_a, head_b)]
 t = torch.tensor(errs, device=dev)
@@ -101,13 +110,16 @@ if rank == 0:
 
 # ---- 3. timing of a window
 if timing:
-    def timed(st, opt, reps=6):
-        window(st, opt, 40)
+    fb = batches(40)
+
+    def timed(st, opt, reps=8):
+        window(st, opt, fb)
+        window(st, opt, fb)
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for r in range(reps):
-            window(st, opt, 41 + r)
+            window(st, opt, fb)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
