@@ -743,6 +743,90 @@ def run_ours(args):
     finish_rank()
 
 
+def run_sweep(args):
+    """BASELINE.json configs[4] (C5): K in {8192, 65536, 262144} x N in {196, 576, 1024} at batch 64 per GPU, ViT-S/16
+    features, full step (multi-crop CE + iBOT + Gram + EMA/accum).  One JSON line with a `sweep` table: ms per
+    micro-step (graph replay, max over ranks), crops/s, algorithmic TFLOP/s, and the per-kernel medians of a short
+    eager leg with their fraction of the applicable measured peak."""
+    import torch.distributed as dist
+    from dinox_b200 import ops, synth
+    from dinox_b200.step import LossHeadStep
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = True
+    peaks = _peaks()
+    rows = []
+    for K in synth.C5_SWEEP_K:
+        for N in synth.C5_SWEEP_N:
+            sh = synth.LossHeadShapes(batch=64, dim=384, out_dim=K, n_patches=N)
+            st = LossHeadStep(sh, dev, accum=args.accum, process_group=pg)
+            f = {k: v.to(dev) for k, v in synth.feature_batch(sh, synth.seeded_generator(5, rank), patches_from_tokens=True).items()}
+            ops.TIMER.enabled = True
+            for _ in range(2):
+                st.micro_step({k: (v.detach().requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()})
+            torch.cuda.synchronize()
+            ops.TIMER.reset()
+            for _ in range(8):
+                st.micro_step({k: (v.detach().requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()})
+            torch.cuda.synchronize()
+            ops.TIMER.enabled = False
+            ops.TIMER.resolve()
+            kt = {k: float(statistics.median(v)) for k, v in ops.TIMER.samples.items()}
+            for p in st.student_head.parameters():
+                p.grad = None
+            st.micro = 0
+            slots = st.static_inputs(f, slots=1)
+            for k, v in f.items():
+                slots[0][k].detach().copy_(v)
+            st.capture(0)
+            for _ in range(3):
+                st.micro_step_graph(0)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = args.sweep_steps
+            e0.record()
+            for _ in range(n):
+                st.micro_step_graph(0)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            D = sh.dim
+            rs, rt = sh.student_rows + sh.masked_rows, sh.teacher_rows + sh.masked_rows
+            gram_flops = 2.0 * 2 * sh.teacher_rows * (sh.tokens - 1) ** 2 * D      # student + teacher Gram tiles
+            fl = {"head_teacher": 2.0 * D * K * rt, "head_stats_student": 2.0 * D * K * rs, "head_grad": 2.0 * D * K * rs,
+                  "gemm_dW2": 2.0 * D * K * rs, "gemm_dH": 2.0 * D * K * rs, "gram_diff": gram_flops}
+            rows.append({"K": K, "N": N, "tokens": sh.tokens - 1, "masked_rows": sh.masked_rows, "ms_per_step": ms,
+                         "crops_per_s": sh.student_rows * world / (ms * 1e-3),
+                         "algorithmic_tflops": sh.flops() / (ms * 1e-3) / 1e12,
+                         "frac_of_burst_peak": sh.flops() / (ms * 1e-3) / 1e12 / peaks["tf_burst"],
+                         "kernels_ms": kt,
+                         "kernels_executed_tflops": {k: fl[k] / (kt[k] * 1e-3) / 1e12 for k in kt if k in fl},
+                         "kernels_frac_of_burst_peak": {k: fl[k] / (kt[k] * 1e-3) / 1e12 / peaks["tf_burst"] for k in kt if k in fl}})
+            st._graphs.clear()
+            del st, f, slots
+            torch.cuda.empty_cache()
+    if rank == 0:
+        line = {"metric": METRIC, "unit": "crops/s", "n_gpus": world, "config": {"workload": "C5 sweep: ViT-S/16 loss head, batch 64 per GPU, "
+                "K x N grid, 2 global + 8 local crops, iBOT r=0.3, Gram on, accum %d" % args.accum}, "scaling": "weak",
+                "dtype": "bf16", "data": "synthetic", "peaks": peaks, "sweep": rows}
+        print(json.dumps(line), file=_OUT, flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def _claim_stdout():
     """Libraries (NCCL prints its version banner) must not add lines to stdout: point fd 1 at stderr
     for the run and hand back a file object on the real stdout for the single JSON line."""
@@ -772,6 +856,8 @@ def main():
     ap.add_argument("--sustained-s", type=float, default=2.0,
                     help="length of the extra graph-replay leg that reports the power-limited steady state (0 = skip)")
     ap.add_argument("--no-hbm-table", action="store_true", help="skip the GB/s table of the HBM-bound reduction kernels")
+    ap.add_argument("--sweep", action="store_true", help="run the C5 sweep grid (K x N) instead of the headline workload")
+    ap.add_argument("--sweep-steps", type=int, default=12)
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 legs of the `extra` block")
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the PyTorch-eager-on-this-GPU comparator leg")
     ap.add_argument("--no-reference-verbatim", action="store_true",
@@ -782,6 +868,10 @@ def main():
     _OUT = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.sweep:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --sweep: no CUDA device")
+        run_sweep(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device - the dinox_b200 path has no CPU fallback "

@@ -125,34 +125,59 @@ rows_lse_kernel(const T* __restrict__ x, int64_t K, int64_t ld, float scale2 /* 
 // ---------------------------------------------------------------------------------------------
 // column passes: each thread owns 4 adjacent columns and walks all rows
 // ---------------------------------------------------------------------------------------------
-constexpr int kColThreads = 128;
+constexpr int kColGroups = 16;   // row groups per block: 32 column-threads (4 columns each) x 16 row groups
 
+// Block = 32 column-threads x kColGroups row groups.  Every row group walks its rows (stride kColGroups, two loads
+// in flight) with a private online (max, sum 2^x) per column; the groups are merged through shared memory in a
+// fixed order.  (One thread walking all rows of its columns serially was latency bound at 0.5 TB/s.)
 template <typename T, bool kVec>
-__global__ void __launch_bounds__(kColThreads)
+__global__ void __launch_bounds__(32 * kColGroups)
 cols_lse_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, float scale2,
                 const float* __restrict__ rowbias, float* __restrict__ out) {
-  const int64_t k = ((int64_t)blockIdx.x * kColThreads + threadIdx.x) * 4;
-  if (k >= K) return;
+  __shared__ float sm[kColGroups][32][4], ss[kColGroups][32][4];
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int64_t k = ((int64_t)blockIdx.x * 32 + cx) * 4;
   float m[4], s[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) { m[j] = -INFINITY; s[j] = 0.f; }
-  for (int64_t i = 0; i < rows; ++i) {
-    float v[4];
-    load4<T, kVec>(x + i * ld, k, K, v, 0.f);
-    const float rb = rowbias ? rowbias[i] * DINOX_LOG2E : 0.f;
+  auto fold = [&](const float (&v)[4], float rb) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float u = fmaf(v[j], scale2, -rb);
-      float mn = fmaxf(m[j], u);
+      const float u = fmaf(v[j], scale2, -rb);
+      const float mn = fmaxf(m[j], u);
       if (mn != -INFINITY) {
         s[j] = s[j] * exp2f(m[j] - mn) + exp2f(u - mn);
         m[j] = mn;
       }
     }
+  };
+  if (k < K) {
+    int64_t i = gy;
+    for (; i + kColGroups < rows; i += 2 * kColGroups) {
+      float v0[4], v1[4];
+      load4<T, kVec>(x + i * ld, k, K, v0, 0.f);
+      load4<T, kVec>(x + (i + kColGroups) * ld, k, K, v1, 0.f);
+      const float r0 = rowbias ? rowbias[i] * DINOX_LOG2E : 0.f, r1 = rowbias ? rowbias[i + kColGroups] * DINOX_LOG2E : 0.f;
+      fold(v0, r0);
+      fold(v1, r1);
+    }
+    for (; i < rows; i += kColGroups) {
+      float v0[4];
+      load4<T, kVec>(x + i * ld, k, K, v0, 0.f);
+      fold(v0, rowbias ? rowbias[i] * DINOX_LOG2E : 0.f);
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (k + j < K) out[k + j] = DINOX_LN2 * (m[j] + log2f(s[j]));
+  for (int j = 0; j < 4; ++j) { sm[gy][cx][j] = m[j]; ss[gy][cx][j] = s[j]; }
+  __syncthreads();
+  if (gy == 0 && k < K) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      MaxSum a{-INFINITY, 0.f};
+      for (int g = 0; g < kColGroups; ++g) a = maxsum_merge(a, MaxSum{sm[g][cx][j], ss[g][cx][j]});   // fixed order
+      if (k + j < K) out[k + j] = DINOX_LN2 * (a.m + log2f(a.s));
+    }
+  }
 }
 
 // column sums: block = 32 column-threads (4 columns each) x kRowGroups row groups; the row groups
@@ -287,17 +312,25 @@ ce_fwd_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, Ce
     }
     float stot[4] = {0.f, 0.f, 0.f, 0.f};
     float sown[kMaxGlobalViews][4];
-    for (int v = 0; v < a.V; ++v) {
-      float s[4];
-      load4<TS, kVec>(student + (v * a.groups + g) * a.ld_s, k, k1, s, 0.f);
+    // student views: the teacher-paired (global) ones are kept, all are summed; four row loads in flight
+    for (int v0 = 0; v0 < a.V; v0 += 4) {
+      float s[4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) stot[j] += s[j];
+      for (int u = 0; u < 4; ++u) {
+        if (v0 + u < a.V) load4<TS, kVec>(student + ((v0 + u) * a.groups + g) * a.ld_s, k, k1, s[u], 0.f);
+        else { s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.f; }
+      }
 #pragma unroll
-      for (int q = 0; q < kMaxGlobalViews; ++q)
-        if (q == v) {
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) sown[q][j] = s[j];
-        }
+        for (int j = 0; j < 4; ++j) stot[j] += s[u][j];
+#pragma unroll
+        for (int q = 0; q < kMaxGlobalViews; ++q)
+          if (q == v0 + u) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sown[q][j] = s[u][j];
+          }
+      }
     }
 #pragma unroll
     for (int q = 0; q < kMaxGlobalViews; ++q) {
@@ -462,11 +495,11 @@ int dinox_cols_lse(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld
   int rc = require_sm100();
   if (rc) return rc;
   const bool vec = vec_ok(x, dtype, K, ld);
-  const unsigned grid = (unsigned)((K + kColThreads * 4 - 1) / (kColThreads * 4));
+  const unsigned grid = (unsigned)((K + 127) / 128);
   const float s2 = inv_tau * DINOX_LOG2E;
   DISPATCH_T(dtype, T, {
-    if (vec) cols_lse_kernel<T, true><<<grid, kColThreads, 0, stream>>>((const T*)x, rows, K, ld, s2, rowbias, out);
-    else cols_lse_kernel<T, false><<<grid, kColThreads, 0, stream>>>((const T*)x, rows, K, ld, s2, rowbias, out);
+    if (vec) cols_lse_kernel<T, true><<<grid, 32 * kColGroups, 0, stream>>>((const T*)x, rows, K, ld, s2, rowbias, out);
+    else cols_lse_kernel<T, false><<<grid, 32 * kColGroups, 0, stream>>>((const T*)x, rows, K, ld, s2, rowbias, out);
   });
   return check_launch("cols_lse_kernel", stream);
 }

@@ -188,7 +188,12 @@ CONFIGS = {
     "C3": dict(batch=32, dim=384, out_dim=65536, n_patches=196),
     "C4": dict(batch=32, dim=1024, out_dim=65536, n_patches=196),
     "C5lo": dict(batch=64, dim=384, out_dim=8192, n_patches=196),
+    "C5": dict(batch=64, dim=384, out_dim=65536, n_patches=196),      # centre of the C5 sweep grid (bench.py --sweep)
+    "C5hi": dict(batch=64, dim=384, out_dim=262144, n_patches=1024),  # top corner: K = 262144, 512x512 crops at patch 16
 }
+# BASELINE.json configs[4]: the C5 sweep K in [8192, 262144] x N in [196, 1024]
+C5_SWEEP_K = (8192, 65536, 262144)
+C5_SWEEP_N = (196, 576, 1024)
 
 
 def student_param_shapes(dim: int, depth: int, out_dim: int, patch: int = 16, img: int = 224,
