@@ -148,12 +148,19 @@ class DINOLoss(nn.Module):
     """
 
     def __init__(self, out_dim: int, center_momentum: float = 0.999, *, n_global: int = 2, n_local: int = 0,
-                 teacher_mode: str = "center", sk_iterations: int = 3, process_group=None) -> None:
+                 teacher_mode: str = "center", sk_iterations: int = 3, process_group=None,
+                 patch_teacher_mode: Optional[str] = None) -> None:
         super().__init__()
         self.center_momentum = center_momentum
         self.register_buffer("center", torch.zeros(1, out_dim))
         self.n_global, self.n_local = n_global, n_local
         self.teacher_mode, self.sk_iterations = teacher_mode, sk_iterations
+        # iBOT (masked-patch) teacher rows of the fused path: "center" (default: softmax-centred with the patch
+        # centre, which is kept updated in both CLS modes) or "sinkhorn" (DINOv2: Sinkhorn-Knopp over the masked
+        # patches of the global batch as well - their teacher logits are materialised for the three iterations)
+        self.patch_teacher_mode = patch_teacher_mode or "center"
+        if self.patch_teacher_mode not in ("center", "sinkhorn"):
+            raise ValueError(f"unknown patch_teacher_mode {patch_teacher_mode!r}")
         self.process_group = process_group
 
     @torch.no_grad()
@@ -708,7 +715,7 @@ class _FusedHeadLoss(torch.autograd.Function):
     def forward(ctx, student_cls, student_patch, w1, b1, w2, b2, teacher_cls, teacher_patch, masks_weight, t_head,
                 loss_mod, center_patch, cfg, patch_index=None, params_in_place=None, teacher_index=None):
         (student_temp, teacher_temp, Vg, n_local, ibot_weight, teacher_mode, sk_iters, pg, update_center,
-         patch_momentum, grads_in_place, w2_sink) = cfg
+         patch_momentum, grads_in_place, w2_sink, patch_mode) = cfg
         dev = student_cls.device
         D = student_cls.shape[1]
         K = w2.shape[0]
@@ -734,7 +741,7 @@ class _FusedHeadLoss(torch.autograd.Function):
         centre_cls = update_center and teacher_mode == "center"
         # the patch centre is the only collapse protection of the iBOT targets in BOTH teacher modes (the CLS
         # Sinkhorn-Knopp normalisation does not touch the patch rows), so it is updated whenever there are patch rows
-        centre_patch = update_center and Mm > 0
+        centre_patch = update_center and Mm > 0 and patch_mode == "center"
 
         # Two branches that meet at pass 2.  The teacher branch (no gradient) is issued on a side stream
         # so that its short kernels slot into the launch gaps and wave tails of the student branch;
@@ -782,7 +789,17 @@ class _FusedHeadLoss(torch.autograd.Function):
                 a_col, b_row = sinkhorn_knopp_biases(t_cls, teacher_temp, sk_iters, pg)
                 ct2 = ops.axpby(b2t, inv_tt * LOG2E, a_col, -LOG2E)
                 del t_cls
-            ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E) if Mm else None
+            b_row_patch = None
+            if Mm and patch_mode == "sinkhorn":
+                # Sinkhorn-Knopp over the masked patches (DINOv2): the iterations need the whole (Mm, K) logit matrix
+                # three times over, so it is materialised once (fp32) for them; the resulting per-prototype offsets go
+                # into the teacher pass as its column offsets and the per-token offsets replace the row LSE
+                t_patch = ops.gemm_bf16(ht[Mt_pad:], w2t, bias_n=b2t)
+                a_col_p, b_row_patch = sinkhorn_knopp_biases(t_patch, teacher_temp, sk_iters, pg)
+                ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, a_col_p, -LOG2E)
+                del t_patch
+            else:
+                ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E) if Mm else None
             if readback:
                 # ONE pass over the teacher rows: statistics + un-normalised fp16 probabilities
                 with ops.TIMER.region("head_teacher"):
@@ -798,6 +815,8 @@ class _FusedHeadLoss(torch.autograd.Function):
                 ops.gather_cast_bf16(ht, plan.ent_t, ht_e)
             if b_row is not None:   # Sinkhorn rows are normalised by their own offset, not by the row LSE
                 ops.axpb(b_row, LOG2E, out=rb2_t[:Mt])
+            if b_row_patch is not None:
+                ops.axpb(b_row_patch, LOG2E, out=rb2_t[Mt_pad:])
             # padding entries: a huge offset makes their probabilities exactly 0 (0 * inf would poison the sums)
             rb2_e = ops.gather_f32(rb2_t, plan.ent_t_pad if readback else plan.ent_t, fill=1.0e30)
             if side is not None and concurrency() >= 3:
@@ -982,7 +1001,7 @@ def fused_head_dino_loss(student_cls: torch.Tensor, teacher_cls: torch.Tensor, s
     cfg = (student_temp, teacher_temp, dino_loss.n_global, dino_loss.n_local, ibot_weight, dino_loss.teacher_mode,
            dino_loss.sk_iterations, dino_loss.process_group, update_center,
            dino_loss.center_momentum if patch_center_momentum is None else patch_center_momentum, bool(grads_in_place),
-           w2_grad_shards)
+           w2_grad_shards, dino_loss.patch_teacher_mode)
     params = (student_head[0].weight, student_head[0].bias, student_head[2].weight, student_head[2].bias)
     # in-place mode: the parameters enter detached (no AccumulateGrad node takes part in the backward - theirs would
     # tie a captured backward to whatever stream first created them) and the real ones ride along to receive .grad

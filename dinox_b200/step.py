@@ -19,7 +19,7 @@ class LossHeadStep:
                  accum: int = 4, gram_weight: float = 1.0, ibot_weight: float = 1.0, ema: float = 0.996,
                  center_momentum: float = 0.9, student_temp: float = 0.1, teacher_temp: float = 0.04,
                  teacher_mode: str = "center", process_group=None, with_backbone_params: bool = True,
-                 koleo_weight: float = 0.0):
+                 koleo_weight: float = 0.0, patch_teacher_mode: Optional[str] = None):
         self.shapes, self.device, self.accum = shapes, device, accum
         self.gram_weight, self.ibot_weight, self.ema = gram_weight, ibot_weight, ema
         # KoLeo (scripts/phase5_big_run.py:1764-1766) is off by default: the benchmark metric is the
@@ -38,7 +38,8 @@ class LossHeadStep:
         for p in self.teacher_head.parameters():
             p.requires_grad_(False)
         self.dino_loss = losshead.DINOLoss(K, center_momentum, n_global=shapes.n_global, n_local=shapes.n_local,
-                                           teacher_mode=teacher_mode, process_group=process_group).to(device)
+                                           teacher_mode=teacher_mode, process_group=process_group,
+                                           patch_teacher_mode=patch_teacher_mode).to(device)
         self.center_patch = torch.zeros(1, K, device=device)
         # every other student/teacher parameter (backbone, scale-embed): random stand-ins with the
         # reference's shapes so that the EMA walks the real 161 / 305 tensor list

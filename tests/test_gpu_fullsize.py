@@ -385,14 +385,17 @@ def test_extreme_logits_and_non_finite_inputs(dx):
 # against the pure-fp32 oracle (the reference without --amp): losses 2e-3, gradients 1.5e-2 - the
 # operand rounding of the bf16 tensor-core path, see profiles/r02_tolerance_table.txt.
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", ["center", "sinkhorn"])
+@pytest.mark.parametrize("mode", ["center", "sinkhorn", "sinkhorn+patches"])
 def test_c1_full_size_step_vs_oracle(dx, mode):
+    patch_mode = "sinkhorn" if mode.endswith("+patches") else "center"   # Sinkhorn-Knopp on the masked patch rows too
+    mode = mode.split("+")[0]
     from dinox_b200 import synth
     from dinox_b200.step import LossHeadStep
     from oracle import losshead_oracle as O
     sh = synth.LossHeadShapes(**synth.CONFIGS["C1"])
     assert (sh.student_rows, sh.teacher_rows, sh.masked_rows, sh.out_dim) == (80, 16, 928, 65536)
-    st = LossHeadStep(sh, DEV, accum=1, with_backbone_params=False, teacher_mode=mode, center_momentum=0.9)
+    st = LossHeadStep(sh, DEV, accum=1, with_backbone_params=False, teacher_mode=mode, center_momentum=0.9,
+                      patch_teacher_mode=patch_mode)
     g = synth.seeded_generator(1, 0)
     f = synth.feature_batch(sh, g)
     c0 = torch.randn(1, sh.out_dim, generator=g) * 0.05
@@ -412,7 +415,7 @@ def test_c1_full_size_step_vs_oracle(dx, mode):
         sp = O.HeadParams(*[p.clone().requires_grad_(True) for p in sd_s])
         tp = O.HeadParams(*[p.clone() for p in sd_t])
         orc = O.LossHeadOracle(sp, tp, sh.out_dim, center_momentum=0.9, n_global=sh.n_global, n_local=sh.n_local,
-                               teacher_mode=mode, policy=policy, patch_teacher_mode="center")
+                               teacher_mode=mode, policy=policy, patch_teacher_mode=patch_mode)
         orc.center, orc.center_patch = c0.clone(), cp0.clone()
         fo = {k: (v.clone().requires_grad_(True) if k.startswith("student") else v) for k, v in f.items()}
         ref = orc.step(fo["student_cls"], fo["teacher_cls"], 0.1, 0.04, student_tok=fo["student_tok"],
@@ -438,4 +441,4 @@ def test_c1_full_size_step_vs_oracle(dx, mode):
             lim = t["gram"] if k == "loss_gram" else t["loss"] if k.startswith("loss") else t["center"] if k.startswith("center") else t["grad"]
             assert v <= lim, f"{mode}/{policy}: {k} relative error {v:.3e} > {lim:.1e}"
     for policy, errs in report:
-        print(f"[C1 {mode} vs oracle({policy})] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+        print(f"[C1 {mode}/{patch_mode} patches vs oracle({policy})] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))

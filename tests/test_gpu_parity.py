@@ -337,6 +337,42 @@ def test_fused_sinkhorn_vs_oracle(dx):
     assert_close(s_head[2].weight.grad, sp.w2.grad, 4e-3, "dW2")
 
 
+@pytest.mark.parametrize("K", [512, 4099])
+def test_fused_sinkhorn_on_patch_rows_vs_oracle(dx, K):
+    """DINOv2 form: Sinkhorn-Knopp on the CLS rows AND on the masked patch rows (patch_teacher_mode="sinkhorn");
+    the oracle's default for teacher_mode="sinkhorn".  The patch centre is then not used and not updated."""
+    from dinox_b200 import synth
+    gen = torch.Generator().manual_seed(31)
+    B, Vg, Vl, D, n_mask = 8, 2, 2, 64, 6
+    V, Mm = Vg + Vl, B * Vg * n_mask
+    s_sd, t_sd = synth.head_weights(D, K, gen), synth.head_weights(D, K, gen)
+    feats = dict(student_cls=torch.randn(B * V, D, generator=gen), teacher_cls=torch.randn(B * Vg, D, generator=gen),
+                 student_patch=torch.randn(Mm, D, generator=gen), teacher_patch=torch.randn(Mm, D, generator=gen),
+                 masks_weight=torch.full((Mm,), 1.0 / n_mask))
+    sp = O.HeadParams(*[s_sd[k].clone().requires_grad_(True) for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    tp = O.HeadParams(*[t_sd[k].clone() for k in ("0.weight", "0.bias", "2.weight", "2.bias")])
+    orc = O.LossHeadOracle(sp, tp, K, n_global=Vg, n_local=Vl, teacher_mode="sinkhorn", policy="bf16")
+    of = {k: (v.clone().requires_grad_(True) if k.startswith("student") else v) for k, v in feats.items()}
+    ref = orc.step(of["student_cls"], of["teacher_cls"], 0.1, 0.04, student_patch=of["student_patch"],
+                   teacher_patch=of["teacher_patch"], masks_weight=of["masks_weight"])
+    s_head, t_head = dx.ProjectionHead(D, K).to(DEV), dx.ProjectionHead(D, K).to(DEV)
+    s_head.load_state_dict(s_sd); t_head.load_state_dict(t_sd)
+    dl = dx.DINOLoss(K, 0.9, n_global=Vg, n_local=Vl, teacher_mode="sinkhorn", patch_teacher_mode="sinkhorn").to(DEV)
+    cpatch = torch.zeros(1, K, device=DEV)
+    df = {k: (v.to(DEV).requires_grad_(True) if k.startswith("student") else v.to(DEV)) for k, v in feats.items()}
+    out = dx.fused_head_dino_loss(df["student_cls"], df["teacher_cls"], s_head, t_head, dl, 0.1, 0.04,
+                                  student_patch=df["student_patch"], teacher_patch=df["teacher_patch"],
+                                  masks_weight=df["masks_weight"], center_patch=cpatch)
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    assert abs(out["loss_dino"].item() - ref["loss_dino"].item()) <= 1e-3 * abs(ref["loss_dino"].item())
+    assert abs(out["loss_ibot"].item() - ref["loss_ibot"].item()) <= 1e-3 * abs(ref["loss_ibot"].item())
+    assert_close(df["student_cls"].grad, of["student_cls"].grad, 4e-3, "d student_cls")
+    assert_close(df["student_patch"].grad, of["student_patch"].grad, 4e-3, "d student_patch")
+    assert_close(s_head[2].weight.grad, sp.w2.grad, 4e-3, "dW2")
+    assert cpatch.abs().max().item() == 0.0 and dl.center.abs().max().item() == 0.0
+
+
 def test_fused_equals_materialised_path(dx):
     """Degenerate-case identity on the GPU: fused kernels == head GEMMs + DINOLoss row kernels
     (same bf16 operands, logits kept fp32 on both sides)."""
