@@ -140,7 +140,7 @@ SIGNATURES = {
                                        c_int, c_int, c_int, c_f32, c_void_p, c_int, c_void_p]),
     "dinox_gemm_splitk_plan": (c_int, [c_i64, c_i64, c_i64]),
     "dinox_gemm_bf16_reduce_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
-                                               c_i64, c_int, c_int, c_f32, c_void_p, c_void_p]),
+                                               c_i64, c_int, c_int, c_f32, c_void_p, c_void_p, c_i64, c_f32, c_void_p]),
     "dinox_debug_max_active_clusters": (c_int, [c_int]),
     "dinox_head_stats_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_head_stats": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p,

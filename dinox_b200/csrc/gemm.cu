@@ -33,6 +33,11 @@ struct EpiStore {
     float alpha;
     const float* alpha_dev;  // optional device scalar multiplied into alpha
     const float* bias_n;     // optional per-column bias
+    // optional fp32 addend (M, ld_add) in PROBLEM row coordinates, scaled by add_scale: the locally accumulated
+    // gradient of the earlier micro-steps that leaves with this GEMM's tile (reduce-scatter variant)
+    const float* add_src = nullptr;
+    int64_t ld_add = 0;
+    float add_scale = 0.f;
   };
   struct State {
     int flip = 0;
@@ -67,6 +72,22 @@ struct EpiStore {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) * alpha;
+        if (e.add_src) {
+          const int64_t grow = (int64_t)tc.row_shift + row0 + lane;     // this thread's row of the whole problem
+          if (grow < (int64_t)p.M + tc.row_shift && grow < p.M && col0 + 32 <= p.N) {
+            const float4* src = reinterpret_cast<const float4*>(e.add_src + grow * e.ld_add + col0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a4 = __ldg(src + j / 4);
+              v[j] = fmaf(a4.x, e.add_scale, v[j]); v[j + 1] = fmaf(a4.y, e.add_scale, v[j + 1]);
+              v[j + 2] = fmaf(a4.z, e.add_scale, v[j + 2]); v[j + 3] = fmaf(a4.w, e.add_scale, v[j + 3]);
+            }
+          } else if (grow < p.M) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] = fmaf(__ldg(e.add_src + grow * e.ld_add + col0 + j), e.add_scale, v[j]);
+          }
+        }
         if (e.bias_n) {
           if (col0 + 32 <= p.N) {
 #pragma unroll
@@ -1537,7 +1558,7 @@ int dinox_gemm_bf16_splitk(const void* A, const void* B, float* C_partials, int6
 int dinox_gemm_bf16_reduce_scatter(const void* A, const void* B, float* const* shard_ptrs, int owners,
                                    int64_t rows_per_owner, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                    int64_t ldc, int a_mn_major, int b_mn_major, float alpha, const float* alpha_dev,
-                                   dinox_stream_t stream) {
+                                   const float* add_local, int64_t ld_local, float add_scale, dinox_stream_t stream) {
   DINOX_REQUIRE(A && B && shard_ptrs && owners >= 1 && owners <= kMaxOwners, DINOX_E_BADARG,
                 "gemm_bf16_reduce_scatter: 1..%d shards", kMaxOwners);
   DINOX_REQUIRE(rows_per_owner > 0 && rows_per_owner % BM == 0 && rows_per_owner * owners >= M, DINOX_E_BADARG,
@@ -1547,7 +1568,10 @@ int dinox_gemm_bf16_reduce_scatter(const void* A, const void* B, float* const* s
   int rc = require_sm100();
   if (rc) return rc;
   Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
+  DINOX_REQUIRE(!add_local || (ld_local >= N && ld_local % 4 == 0 && aligned16(add_local)), DINOX_E_ALIGN,
+                "gemm_bf16_reduce_scatter: add_local / ld_local misaligned");
   EpiStore::Params ep{0, 1, alpha, alpha_dev, nullptr};
+  ep.add_src = add_local; ep.ld_add = ld_local; ep.add_scale = add_scale;
   OutDesc od;
   od.is_bf16 = 0; od.ld = ldc; od.owners = owners; od.rows_per_owner = rows_per_owner;
   for (int i = 0; i < owners; ++i) {

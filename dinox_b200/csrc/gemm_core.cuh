@@ -48,6 +48,7 @@ constexpr int UMMA_K = 16;
 
 struct TileCoord {
   int m_tile, n_tile, batch, split;
+  int row_shift = 0;   // sharded output only: rows of the problem that precede the owner's shard (m_tile is shard-local)
 };
 
 struct CoreParams {
@@ -555,6 +556,7 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
           const int owner = (tc.m_tile * BM) / p.rows_per_owner;
           tmCt = tmC + owner;
           tce.m_tile = tc.m_tile - owner * (p.rows_per_owner / BM);
+          tce.row_shift = owner * p.rows_per_owner;
         }
         Epi::tile(ep, p, tce, tmCt, tmem_base + acc_stage * kAccCols, acc_stage, epi_warp, lane, epi_smem, state);
       }

@@ -699,7 +699,9 @@ def _update_centres(stats, work, w2t, b2t, loss_mod, center_patch, patch_momentu
     if stats is None:
         return
     hsum, counts = stats
-    if work is not None:
+    if isinstance(work, tuple):       # ("late", buffer): the all-reduce was deferred to this point
+        allreduce_sum_(work[1], loss_mod.process_group)
+    elif work is not None:
         work.wait()
     mean_logits = ops.gemv_bf16_multi(w2t, hsum, [1.0] * hsum.shape[0], b2t, 1.0, divisors=counts)
     i = 0
@@ -776,7 +778,12 @@ class _FusedHeadLoss(torch.autograd.Function):
                     ops.cols_sum(ht[Mt_pad:], out=hsum[int(centre_cls)])
                 i0 = 0 if centre_cls else 1
                 ops.axpb(plan.row_counts[i0:i0 + nv], 1.0, 0.0, out=counts)
-                hsum_work = allreduce_sum_async(sbuf, pg)
+                # DINOX_CENTER_AR=late issues the all-reduce only where its result is needed (after pass 2) instead of
+                # here, next to the teacher pass (A/B knob: does the NCCL kernel disturb the persistent GEMMs?)
+                if os.environ.get("DINOX_CENTER_AR", "early") == "late":
+                    hsum_work = ("late", sbuf)
+                else:
+                    hsum_work = allreduce_sum_async(sbuf, pg)
                 stats = (hsum, counts)
             b2t = t_head[2].bias.detach()
             center = loss_mod.center.reshape(-1)
@@ -908,11 +915,17 @@ class _FusedHeadLoss(torch.autograd.Function):
             # dW2 (K, D) += g * G^T . HsE   (A = G with the prototypes as M; B = HsE MN-major)
             with ops.TIMER.region("gemm_dW2"):
                 sink = ctx.w2_sink
-                if sink is not None:
-                    # data parallel: every output tile is reduce-added into the OWNER rank's peer-mapped gradient shard
-                    # (mean over ranks) - GEMM and reduce-scatter in one kernel, no (K, D) gradient on this rank
+                if sink is not None and sink.flush:
+                    # data parallel, LAST micro-step of the accumulation window: every output tile - plus the gradient
+                    # accumulated locally over the earlier micro-steps - is reduce-added into the OWNER rank's
+                    # peer-mapped shard (mean over ranks): GEMM and reduce-scatter in one kernel, one gradient per
+                    # window over NVLink
+                    local = w2.grad
                     ops.gemm_bf16_reduce_scatter(gt, hs_e, sink.ptrs, sink.rows, sink.cols, a_mn_major=rb, b_mn_major=True,
-                                                 alpha=1.0 / sink.world, alpha_dev=up)
+                                                 alpha=1.0 / sink.world, alpha_dev=up, add_local=local,
+                                                 add_scale=1.0 / sink.world)
+                    if local is not None:
+                        w2.grad = None    # shipped: the owner's shard holds it now
                 else:
                     emit("w2", w2, lambda out, acc: ops.gemm_bf16(
                         gt, hs_e, a_mn_major=rb, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))

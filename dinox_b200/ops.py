@@ -200,9 +200,11 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_m
 
 def gemm_bf16_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shard_ptrs: Sequence[int], rows_per_owner: int, ldc: int,
                              *, a_mn_major: bool = False, b_mn_major: bool = False, alpha: float = 1.0,
-                             alpha_dev: Optional[torch.Tensor] = None) -> None:
+                             alpha_dev: Optional[torch.Tensor] = None, add_local: Optional[torch.Tensor] = None,
+                             add_scale: float = 1.0) -> None:
     """alpha * A @ B^T reduce-added, tile by tile, into the row shards named by `shard_ptrs` (device addresses, one
-    per data-parallel rank, possibly peer-mapped): the reduce-scatter happens in the GEMM epilogue."""
+    per data-parallel rank, possibly peer-mapped): the reduce-scatter happens in the GEMM epilogue.  `add_local`
+    ((M, N) fp32, times add_scale) rides along: the gradient accumulated locally over the earlier micro-steps."""
     _chk_cuda(a, b, alpha_dev)
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
         raise _ext.DinoxError("gemm_bf16_reduce_scatter needs bf16 operands")
@@ -212,8 +214,11 @@ def gemm_bf16_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shard_ptrs: Seque
         raise _ext.DinoxError(f"gemm_bf16_reduce_scatter: reduction dims differ ({Ka} vs {Kb})")
     n = len(shard_ptrs)
     ptrs = (ctypes.c_void_p * n)(*[int(p) for p in shard_ptrs])
+    if add_local is not None:
+        assert add_local.dtype == torch.float32 and tuple(add_local.shape) == (M, N) and add_local.stride(1) == 1
     _ext.call("dinox_gemm_bf16_reduce_scatter", _p(a), _p(b), ptrs, n, int(rows_per_owner), M, N, Ka, _rowmajor(a),
-              _rowmajor(b), int(ldc), int(a_mn_major), int(b_mn_major), float(alpha), _p(alpha_dev), _stream())
+              _rowmajor(b), int(ldc), int(a_mn_major), int(b_mn_major), float(alpha), _p(alpha_dev), _p(add_local),
+              0 if add_local is None else _rowmajor(add_local), float(add_scale), _stream())
 
 
 def gemm_splitk_plan(M: int, N: int, K: int) -> int:

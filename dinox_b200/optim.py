@@ -145,6 +145,9 @@ class PeerGradShards:
         self.acc.zero_()
         self._hdl = symm.rendezvous(self.acc, grp.group_name)
         self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        # the backward pass ships the gradient only when `flush` is set (the caller sets it for the LAST micro-step
+        # of an accumulation window; earlier micro-steps accumulate into .grad locally, and their sum rides along)
+        self.flush = True
         torch.cuda.synchronize()
         dist.barrier(group=self.pg)
 

@@ -154,11 +154,15 @@ DINOX_API int dinox_gemm_splitk_plan(int64_t M, int64_t N, int64_t K);
  * are reduce-ADDED into shard_ptrs[o] ((rows_per_owner, ldc) fp32), which may be memory of a PEER GPU mapped into
  * this process (CUDA IPC / symmetric memory over NVLink).  `shard_ptrs` is a HOST array of `owners` (<= 8) device
  * pointers; rows_per_owner is a multiple of 128.  Every rank calls it with the same table: afterwards (once all
- * ranks' kernels have completed - order them with any collective) shard o holds the sum over ranks of its rows. */
+ * ranks' kernels have completed - order them with any collective) shard o holds the sum over ranks of its rows.
+ * add_local (optional, (M, ld_local) fp32, scaled by add_scale) is added to every tile before it leaves: the
+ * gradient accumulated LOCALLY over the earlier micro-steps of a window travels with the last micro-step's GEMM,
+ * so the NVLink traffic is one gradient per window, not one per micro-step. */
 DINOX_API int dinox_gemm_bf16_reduce_scatter(const void* A, const void* B, float* const* shard_ptrs, int owners,
                                              int64_t rows_per_owner, int64_t M, int64_t N, int64_t K, int64_t lda,
                                              int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, float alpha,
-                                             const float* alpha_dev, dinox_stream_t stream);
+                                             const float* alpha_dev, const float* add_local, int64_t ld_local,
+                                             float add_scale, dinox_stream_t stream);
 /* diagnostics: number of co-resident clusters of `cluster_size` CTAs for the pass-1 kernel */
 DINOX_API int dinox_debug_max_active_clusters(int cluster_size);
 
