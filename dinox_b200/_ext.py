@@ -123,6 +123,7 @@ SIGNATURES = {
     "dinox_cols_lse": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p, c_void_p]),
     "dinox_lse_combine": (c_int, [c_void_p, c_int, c_i64, c_f32, c_void_p, c_void_p]),
     "dinox_cols_sum": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
+    "dinox_cols_sum_axpy": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p, c_int, c_void_p]),
     "dinox_cols_sum_chunked": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "dinox_center_ema": (c_int, [c_void_p, c_void_p, c_f32, c_f32, c_i64, c_void_p]),
     "dinox_axpb": (c_int, [c_void_p, c_f32, c_f32, c_void_p, c_i64, c_void_p]),
@@ -177,6 +178,8 @@ SIGNATURES = {
     "dinox_gemv_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_f32, c_void_p, c_f32, c_void_p, c_void_p]),
     "dinox_gemv_bf16_multi": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_f32,
                                       c_void_p, c_void_p]),
+    "dinox_gemv_bf16_multi_ema": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_f32,
+                                          c_void_p, c_void_p, c_void_p]),
     "dinox_sum_slabs": (c_int, [c_void_p, c_int, c_i64, c_i64, c_void_p, c_f32, c_void_p, c_int, c_void_p]),
     "dinox_gather_sum_rows": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_f32,
                                       c_void_p, c_i64, c_int, c_void_p]),

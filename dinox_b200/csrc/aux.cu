@@ -202,11 +202,13 @@ __global__ void gemv_bf16_kernel(const __nv_bfloat16* __restrict__ W, int64_t ld
 
 // nvec (<= 4) vectors against the same matrix in one pass over W: out[v][k] = alpha[v] * W[k,:].x[v] + beta*bias[k]
 struct GemvAlphas { float a[4]; };
+// optional in-place EMA of the result into a target vector: target[k] = m * target[k] + (1 - m) * value
+struct GemvEma { float* target[4]; float m[4]; };
 constexpr int kGemvRows = 4;
 template <int NV>
 __global__ void gemv_bf16_multi_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, const float* __restrict__ X,
                                        int64_t K, int D, GemvAlphas alphas, const float* __restrict__ divisors,
-                                       const float* __restrict__ bias, float beta, float* __restrict__ out) {
+                                       const float* __restrict__ bias, float beta, float* __restrict__ out, GemvEma ema) {
   const int lane = threadIdx.x & 31;
   // each warp owns kGemvRows consecutive rows and loads them together: one row of D = 384 is only 1.5 16-byte loads
   // per lane, which left the kernel latency bound at 1.7 TB/s
@@ -250,7 +252,11 @@ __global__ void gemv_bf16_multi_kernel(const __nv_bfloat16* __restrict__ W, int6
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const float t = warp_sum(acc[r][v]);
-      if (lane == 0) out[(int64_t)v * K + k] = t * (divisors ? alphas.a[v] / divisors[v] : alphas.a[v]) + b;
+      if (lane == 0) {
+        const float val = t * (divisors ? alphas.a[v] / divisors[v] : alphas.a[v]) + b;
+        if (out) out[(int64_t)v * K + k] = val;
+        if (ema.target[v]) ema.target[v][k] = ema.target[v][k] * ema.m[v] + val * (1.f - ema.m[v]);   // :686-690 op order
+      }
     }
   }
 }
@@ -463,10 +469,35 @@ int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64
   return check_launch("gemv_bf16_kernel", stream);
 }
 
+static int gemv_multi_impl(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
+                           const float* alphas_host, const float* divisors_dev, const float* bias, float beta, float* out,
+                           const GemvEma& ema, dinox_stream_t stream);
+
 int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
                           const float* alphas_host, const float* divisors_dev, const float* bias, float beta, float* out,
                           dinox_stream_t stream) {
-  DINOX_REQUIRE(W && X && out && alphas_host && K > 0 && D > 0 && D % 8 == 0 && ldw % 8 == 0 && nvec >= 1 && nvec <= 4,
+  DINOX_REQUIRE(out, DINOX_E_BADARG, "gemv_bf16_multi: null output");
+  GemvEma ema = {};
+  return gemv_multi_impl(W, ldw, X, nvec, K, D, alphas_host, divisors_dev, bias, beta, out, ema, stream);
+}
+
+int dinox_gemv_bf16_multi_ema(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
+                              const float* alphas_host, const float* divisors_dev, const float* bias, float beta,
+                              float* const* targets, const float* momenta_host, dinox_stream_t stream) {
+  DINOX_REQUIRE(targets && momenta_host && nvec >= 1 && nvec <= 4, DINOX_E_BADARG, "gemv_bf16_multi_ema: bad arguments");
+  GemvEma ema = {};
+  for (int v = 0; v < nvec; ++v) {
+    DINOX_REQUIRE(targets[v], DINOX_E_BADARG, "gemv_bf16_multi_ema: null target");
+    ema.target[v] = targets[v];
+    ema.m[v] = momenta_host[v];
+  }
+  return gemv_multi_impl(W, ldw, X, nvec, K, D, alphas_host, divisors_dev, bias, beta, nullptr, ema, stream);
+}
+
+static int gemv_multi_impl(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
+                           const float* alphas_host, const float* divisors_dev, const float* bias, float beta, float* out,
+                           const GemvEma& ema, dinox_stream_t stream) {
+  DINOX_REQUIRE(W && X && alphas_host && K > 0 && D > 0 && D % 8 == 0 && ldw % 8 == 0 && nvec >= 1 && nvec <= 4,
                 DINOX_E_BADARG, "gemv_bf16_multi: bad arguments (D, ldw multiples of 8; 1..4 vectors)");
   DINOX_REQUIRE(aligned16(W) && aligned16(X), DINOX_E_ALIGN, "gemv_bf16_multi: misaligned");
   GemvAlphas al;
@@ -474,10 +505,10 @@ int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, 
   const unsigned grid = (unsigned)((K + 8 * kGemvRows - 1) / (8 * kGemvRows));
   const __nv_bfloat16* w = (const __nv_bfloat16*)W;
   switch (nvec) {
-    case 1: gemv_bf16_multi_kernel<1><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;
-    case 2: gemv_bf16_multi_kernel<2><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;
-    case 3: gemv_bf16_multi_kernel<3><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;
-    default: gemv_bf16_multi_kernel<4><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out); break;
+    case 1: gemv_bf16_multi_kernel<1><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out, ema); break;
+    case 2: gemv_bf16_multi_kernel<2><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out, ema); break;
+    case 3: gemv_bf16_multi_kernel<3><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out, ema); break;
+    default: gemv_bf16_multi_kernel<4><<<grid, 256, 0, stream>>>(w, ldw, X, K, (int)D, al, divisors_dev, bias, beta, out, ema); break;
   }
   return check_launch("gemv_bf16_multi_kernel", stream);
 }

@@ -1231,7 +1231,7 @@ struct EpiGramDiff {
 
 // per-CTA loss partials of pass 2, interleaved {a, b}: out[0] (+)= sum a, out[1] (+)= sum b (fixed order)
 __global__ void __launch_bounds__(1024) pair_sum_kernel(const float* __restrict__ x, int64_t n_pairs,
-                                                         float* __restrict__ out, int accumulate) {
+                                                         float* __restrict__ out, int accumulate, int write_total = 0) {
   __shared__ float red[64];
   float a = 0.f, b = 0.f;
   for (int64_t i = threadIdx.x; i < n_pairs; i += 1024) { a += x[2 * i]; b += x[2 * i + 1]; }
@@ -1240,6 +1240,7 @@ __global__ void __launch_bounds__(1024) pair_sum_kernel(const float* __restrict_
   if (threadIdx.x == 0) {
     out[0] = a + (accumulate ? out[0] : 0.f);
     out[1] = b + (accumulate ? out[1] : 0.f);
+    if (write_total) out[2] = out[0] + out[1];
   }
 }
 
@@ -1826,7 +1827,7 @@ int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int
   if (rc) return rc;
   const int grid = launch_grid((((E + BM - 1) / BM + cl - 1) / cl) * num_n, cl);
   pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * EpiGradR::kEpiWarps, loss_out,
-                                          loss_accumulate);
+                                          loss_accumulate, /*write_total=*/1);
   return check_launch("pair_sum_kernel", stream);
 }
 

@@ -10,7 +10,7 @@
 #include "common.cuh"
 
 namespace dinox {
-constexpr int kKoleoCand = 4;      // candidates per row whose distance is recomputed exactly
+constexpr int kKoleoCand = 8;      // candidates per row whose distance is recomputed exactly (bf16 ranking noise: the true nearest neighbour of a near-duplicate cluster must be among them)
 constexpr int kKoleoMaxRows = 1024;
 
 template <typename T>

@@ -187,7 +187,8 @@ constexpr int kColSumGroups = 16;
 
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(32 * kColSumGroups)
-cols_sum_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, float* __restrict__ out, int64_t chunk) {
+cols_sum_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, float* __restrict__ out, int64_t chunk,
+                float scale = 1.f, const float* __restrict__ scale_dev = nullptr, int accumulate = 0) {
   __shared__ float red[kColSumGroups][32][4];
   const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
   // blockIdx.y selects a chunk of rows; chunk sums land in row blockIdx.y of out (chunk >= rows: one chunk)
@@ -223,7 +224,10 @@ cols_sum_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, fl
       float t = 0.f;
 #pragma unroll
       for (int g = 0; g < kColSumGroups; ++g) t += red[g][cx][j];
-      if (k + j < K) out[k + j] = t;
+      if (k + j < K) {
+        const float v = t * (scale * (scale_dev ? *scale_dev : 1.f));
+        out[k + j] = accumulate ? out[k + j] + v : v;
+      }
     }
   }
 }
@@ -521,6 +525,20 @@ int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld
   DISPATCH_T(dtype, T, {
     if (vec) cols_sum_kernel<T, true><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out, rows);
     else cols_sum_kernel<T, false><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out, rows);
+  });
+  return check_launch("cols_sum_kernel", stream);
+}
+
+int dinox_cols_sum_axpy(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, float scale, const float* scale_dev,
+                        float* out, int accumulate, dinox_stream_t stream) {
+  DINOX_REQUIRE(x && out && rows > 0 && K > 0 && ld >= K, DINOX_E_BADARG, "cols_sum_axpy: bad arguments");
+  int rc = require_sm100();
+  if (rc) return rc;
+  const bool vec = vec_ok(x, dtype, K, ld);
+  const unsigned grid = (unsigned)((K + 127) / 128);
+  DISPATCH_T(dtype, T, {
+    if (vec) cols_sum_kernel<T, true><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out, rows, scale, scale_dev, accumulate);
+    else cols_sum_kernel<T, false><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out, rows, scale, scale_dev, accumulate);
   });
   return check_launch("cols_sum_kernel", stream);
 }

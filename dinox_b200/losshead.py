@@ -703,13 +703,10 @@ def _update_centres(stats, work, w2t, b2t, loss_mod, center_patch, patch_momentu
         allreduce_sum_(work[1], loss_mod.process_group)
     elif work is not None:
         work.wait()
-    mean_logits = ops.gemv_bf16_multi(w2t, hsum, [1.0] * hsum.shape[0], b2t, 1.0, divisors=counts)
-    i = 0
-    if cls:
-        ops.center_ema_(loss_mod.center, mean_logits[0], 1, loss_mod.center_momentum)
-        i = 1
-    if patch:
-        ops.center_ema_(center_patch, mean_logits[i], 1, patch_momentum)
+    targets = ([loss_mod.center.view(-1)] if cls else []) + ([center_patch.view(-1)] if patch else [])
+    momenta = ([loss_mod.center_momentum] if cls else []) + ([patch_momentum] if patch else [])
+    # mean logits and both centre EMAs in ONE pass over W2t (scripts/phase5_big_run.py:686-690)
+    ops.gemv_bf16_multi_ema_(w2t, hsum, [1.0] * hsum.shape[0], b2t, targets, momenta, divisors=counts)
 
 
 class _FusedHeadLoss(torch.autograd.Function):
@@ -858,7 +855,8 @@ class _FusedHeadLoss(torch.autograd.Function):
             ops.axpb(masks_weight.detach().float().contiguous(), ibot_weight / Mt,
                      0.0, out=cw[plan.e_cls_pad:plan.e_cls_pad + Mm])
         # ---- pass 2
-        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        lbuf = torch.empty(4, dtype=torch.float32, device=dev)     # [L_dino, L_ibot, total, -]
+        losses = lbuf[:3]
         need_grad = any(ctx.needs_input_grad[:6]) or (params_in_place is not None and
                                                       any(p.requires_grad for p in params_in_place))
         with ops.TIMER.region("head_grad"):
@@ -878,8 +876,12 @@ class _FusedHeadLoss(torch.autograd.Function):
             ctx.in_dtypes = (student_cls.dtype, None if student_patch is None else student_patch.dtype)
             ctx.patch_index = patch_index
             ctx.patch_shape = None if student_patch is None else tuple(student_patch.shape)
+        if readback:
+            total = lbuf[2]                      # written by pass 2 itself
+        else:
+            total = ops.scalar_combine([lbuf[0], lbuf[1]], [1.0, 1.0])
+        losses = lbuf[:2]
         ctx.mark_non_differentiable(losses)
-        total = ops.scalar_combine([losses[0], losses[1]], [1.0, 1.0])
         return total, losses
 
     @staticmethod
@@ -929,16 +931,14 @@ class _FusedHeadLoss(torch.autograd.Function):
                 else:
                     emit("w2", w2, lambda out, acc: ops.gemm_bf16(
                         gt, hs_e, a_mn_major=rb, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
-            db2 = ops.cols_sum(db2p)
-            emit("b2", b2, lambda out, acc: ops.axpby(db2, 1.0, out if acc else None, 1.0, out=out, alpha_dev=up))
+            emit("b2", b2, lambda out, acc: ops.cols_sum_axpy_(db2p, out, acc, scale_dev=up))
         # dH per entry = G . W2  (B = W2 MN-major), then sum the entries of each row
         with ops.TIMER.region("gemm_dH"):
             dh_e = ops.gemm_bf16_splitk(gt, w2s, a_mn_major=not rb, b_mn_major=True, m_fastest=True)
         dh = torch.empty(rows, D, dtype=torch.float32, device=dev)
         ops.gather_sum_rows(dh_e, plan.csr_ptr, plan.csr_ent, rows, dh)
         da, part = ops.gelu_bwd(dh, a_s, scale_dev=up)
-        db1 = ops.cols_sum(part)
-        emit("b1", b1, lambda out, acc: ops.axpby(db1, 1.0, out if acc else None, 1.0, out=out))
+        emit("b1", b1, lambda out, acc: ops.cols_sum_axpy_(part, out, acc))
         # dW1 = da^T x: 3x3 output tiles with a reduction over every row -> split-K, slabs summed in fixed order
         dw1_parts = ops.gemm_bf16_splitk(da, xs, a_mn_major=True, b_mn_major=True)
         emit("w1", w1, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))

@@ -135,6 +135,17 @@ def cols_sum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tenso
     return out
 
 
+def cols_sum_axpy_(x: torch.Tensor, out: torch.Tensor, accumulate: bool, scale: float = 1.0,
+                   scale_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out (+)= scale * scale_dev * x.sum(0) in one launch (fixed summation order)."""
+    _chk_cuda(x, out)
+    rows, K = x.shape
+    assert out.dtype == torch.float32 and out.numel() == K and out.is_contiguous()
+    _ext.call("dinox_cols_sum_axpy", _p(x), DT[x.dtype], rows, K, _rowmajor(x), float(scale), _p(scale_dev), _p(out),
+              int(accumulate), _stream())
+    return out
+
+
 def center_ema_(center: torch.Tensor, colsum: torch.Tensor, global_rows: int, momentum: float) -> None:
     _chk_cuda(center, colsum)
     K = center.numel()
@@ -320,9 +331,9 @@ def head_grad2(hs_e: torch.Tensor, w2s: torch.Tensor, inv_tau_s: float, cs2: tor
                cw_e: torch.Tensor, rb2_e: torch.Tensor, trow_e: torch.Tensor, qt: torch.Tensor, refs: torch.Tensor,
                alt_from: int, loss_out: torch.Tensor, loss_accumulate: bool = False, want_db2: bool = True,
                g: Optional[torch.Tensor] = None):
-    """Pass 2 (student logits recomputed, teacher probabilities read back).  loss_out: 2 fp32 ([0] entries <
-    alt_from, [1] the rest).  Returns (G (E, K) bf16 = dL/dlogits per entry, db2_partial or None)."""
-    assert loss_out.numel() >= 2 and trow_e.dtype == torch.int32 and qt.dtype == torch.float16
+    """Pass 2 (student logits recomputed, teacher probabilities read back).  loss_out: 3 fp32 ([0] entries <
+    alt_from, [1] the rest, [2] their sum).  Returns (G (E, K) bf16 = dL/dlogits per entry, db2_partial or None)."""
+    assert loss_out.numel() >= 3 and trow_e.dtype == torch.int32 and qt.dtype == torch.float16
     _chk_cuda(hs_e, w2s, qt, refs)
     E, D = hs_e.shape
     K = w2s.shape[0]
@@ -473,6 +484,23 @@ def gemv_bf16_multi(w: torch.Tensor, xs: torch.Tensor, alphas: Sequence[float], 
     _ext.call("dinox_gemv_bf16_multi", _p(w), _rowmajor(w), _p(xs), nvec, K, D, al, _p(divisors), _p(bias), float(beta),
               _p(out), _stream())
     return out
+
+
+def gemv_bf16_multi_ema_(w: torch.Tensor, xs: torch.Tensor, alphas: Sequence[float], bias: Optional[torch.Tensor],
+                         targets: Sequence[torch.Tensor], momenta: Sequence[float],
+                         divisors: Optional[torch.Tensor] = None) -> None:
+    """targets[v] <- m_v * targets[v] + (1 - m_v) * (alphas[v] / divisors[v] * W @ xs[v] + bias), in place, one pass
+    over W: the centre / patch-centre update of the fused path."""
+    K, D = w.shape
+    nvec = xs.shape[0]
+    assert xs.is_contiguous() and xs.shape[1] == D and len(alphas) == nvec == len(targets) == len(momenta)
+    for t in targets:
+        assert t.dtype == torch.float32 and t.numel() == K and t.is_contiguous()
+    al = (ctypes.c_float * nvec)(*[float(a) for a in alphas])
+    mo = (ctypes.c_float * nvec)(*[float(m) for m in momenta])
+    tg = (ctypes.c_void_p * nvec)(*[t.data_ptr() for t in targets])
+    _ext.call("dinox_gemv_bf16_multi_ema", _p(w), _rowmajor(w), _p(xs), nvec, K, D, al, _p(divisors), _p(bias), 1.0, tg, mo,
+              _stream())
 
 
 def sum_slabs(parts: torch.Tensor, out: torch.Tensor, accumulate: bool = False, scale: float = 1.0,

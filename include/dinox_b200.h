@@ -83,6 +83,10 @@ DINOX_API int dinox_lse_combine(const float* gathered, int world, int64_t K, flo
  * scripts/phase5_big_run.py:688) */
 DINOX_API int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld,
                              float* out, dinox_stream_t stream);
+/* out[k] (+)= scale*(*scale_dev) * column sum (accumulate != 0: +=): the bias gradients db1 / db2 summed from their
+ * partial rows straight into `.grad` (autograd's Linear backward `grad_output.sum(0)`, zoo/arch.py:252-256) */
+DINOX_API int dinox_cols_sum_axpy(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, float scale,
+                                  const float* scale_dev, float* out, int accumulate, dinox_stream_t stream);
 /* partial[c, :] = column sums of rows [c*chunk, min((c+1)*chunk, rows)): first phase of a tall-skinny
  * column sum (finish with dinox_cols_sum on the (ceil(rows/chunk), K) fp32 partial matrix) */
 DINOX_API int dinox_cols_sum_chunked(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, int64_t chunk,
@@ -229,6 +233,7 @@ DINOX_API int dinox_head_teacher(const void* H, const void* W2, int64_t rows, in
  * trow_e[e] of qt/refs) recompute only the STUDENT logit tile in TMEM and emit
  *   G[e,k]   = cw[e]*inv_tau_s*( softmax_s[e,k] - q_t[e,k] )            (bf16, (E, ldg) = dL/dlogits)
  *   loss[0..1] (+)= sum_e cw[e] * sum_k q_t[e,k] * (-ln softmax_s[e,k])   ([0]: e < alt_from, [1]: the rest)
+ *   loss[2]     = loss[0] + loss[1]                                      (loss_out holds THREE fp32)
  *   db2_partial[dinox_head_grad2_db2_rows(E), K]  column sums of G per 32 entries (reduce with dinox_cols_sum)
  * with softmax_s = 2^(S*inv_tau_s*log2e + cs2[k] - lse2_e[e]) and
  *      q_t       = qt[trow_e[e],k] * 2^(refs[g(k)][trow_e[e]] - rb2_e[e]).
@@ -305,6 +310,13 @@ DINOX_API int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_
 DINOX_API int dinox_gemv_bf16_multi(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
                                     const float* alphas_host, const float* divisors_dev, const float* bias,
                                     float beta, float* out, dinox_stream_t stream);
+/* the same GEMV with the centre EMA folded in (scripts/phase5_big_run.py:686-690): instead of storing the nvec result
+ * vectors, targets[v][k] = momenta[v]*targets[v][k] + (1-momenta[v])*value[v][k] in place (HOST arrays of nvec
+ * device pointers / momenta) - one launch for "mean teacher logits -> centre and patch-centre update" */
+DINOX_API int dinox_gemv_bf16_multi_ema(const void* W, int64_t ldw, const float* X, int nvec, int64_t K, int64_t D,
+                                        const float* alphas_host, const float* divisors_dev, const float* bias,
+                                        float beta, float* const* targets, const float* momenta_host,
+                                        dinox_stream_t stream);
 /* dst[i] (+)= scale*(*scale_dev) * sum_{s<slabs} src[s*slab_stride + i]: fixed-order reduction of split-K slabs */
 DINOX_API int dinox_sum_slabs(const float* src, int slabs, int64_t slab_stride, int64_t n, const float* scale_dev,
                               float scale, float* dst, int accumulate, dinox_stream_t stream);

@@ -181,3 +181,38 @@ def test_shard_layout_of_the_sharded_optimizer():
     assert shard_layout(head, 1) == [(False, None)] * 4
     assert shard_layout([(65537, 384)], 8) == [(False, None)]
     assert shard_layout([(1024, 1024)], 4, min_numel=1 << 20) == [(True, 256)]
+
+
+def test_entry_plan_padded_teacher_layout_of_the_readback_path():
+    """Teacher rows of the read-back path: [CLS rows | zero rows to a multiple of 128 | masked patch rows]; `trow`
+    names each entry's teacher row in that layout, padding entries point at row 0 with weight 0."""
+    B, Vg, V, Mm = 5, 2, 4, 9
+    plan = losshead._EntryPlan(B, Vg, V, Mm, "cpu")
+    Mt = B * Vg
+    assert plan.Mt_pad == 128 and plan.cls_rows_pad.tolist() == list(range(Mt)) + [-1] * (128 - Mt)
+    et, etp, trow = plan.ent_t.tolist(), plan.ent_t_pad.tolist(), plan.trow.tolist()
+    for e, (a, b, c) in enumerate(zip(et, etp, trow)):
+        if a < 0:
+            assert b == -1 and c == 0 and plan.cw_base[e] == 0.0
+        elif a < Mt:
+            assert b == a == c
+        else:
+            assert b == a - Mt + plan.Mt_pad == c
+    assert plan.row_counts.tolist()[:2] == [float(Mt), float(Mm)]
+    # without iBOT rows there is nothing to pad
+    assert losshead._EntryPlan(B, Vg, V, 0, "cpu").Mt_pad == Mt
+
+
+def test_precision_and_cache_switches_validate_their_arguments():
+    prev = losshead.set_contraction_precision("fp32")
+    assert losshead.set_contraction_precision(prev) == "fp32"
+    with pytest.raises(ValueError):
+        losshead.set_contraction_precision("tf32")
+    with losshead.contraction_precision("bf16"):
+        assert not losshead._fp32_mode()
+    prev = losshead.set_weight_cache("tracked")
+    assert losshead.set_weight_cache(prev) == "tracked"
+    with pytest.raises(ValueError):
+        losshead.set_weight_cache("sometimes")
+    with pytest.raises(ValueError):
+        losshead.DINOLoss(64, patch_teacher_mode="mean")

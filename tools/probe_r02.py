@@ -17,7 +17,7 @@ wt = (torch.randn(K, D, generator=g) / math.sqrt(D)).to(torch.bfloat16).to(dev)
 cs2 = torch.zeros(K, device=dev); ct2 = torch.zeros(K, device=dev)
 cw = torch.full((E,), 1.0 / E, device=dev)
 trow = (torch.arange(E, device=dev) % rows_t).to(torch.int32)
-loss = torch.zeros(2, device=dev)
+loss = torch.zeros(4, device=dev)
 w2grad = torch.zeros(K, D, device=dev)
 qt, refs = ops.teacher_buffers(rows_t, K, dev)
 rb2_t = torch.empty(rows_t, device=dev)
