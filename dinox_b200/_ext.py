@@ -183,6 +183,8 @@ SIGNATURES = {
     "dinox_sum_slabs": (c_int, [c_void_p, c_int, c_i64, c_i64, c_void_p, c_f32, c_void_p, c_int, c_void_p]),
     "dinox_gather_sum_rows": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_f32,
                                       c_void_p, c_i64, c_int, c_void_p]),
+    "dinox_head_offsets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_f32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "dinox_entry_weights": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_f32, c_void_p, c_void_p]),
     "dinox_fill_f32": (c_int, [c_void_p, c_i64, c_f32, c_void_p]),
     "dinox_scalar_combine": (c_int, [c_void_p, c_void_p, c_int, c_f32, c_void_p, c_void_p, c_void_p]),
     "dinox_scalar_fanout": (c_int, [c_void_p, c_void_p, c_int, c_f32, c_void_p, c_void_p]),

@@ -363,6 +363,26 @@ __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
 
 }  // namespace dinox
 
+// per-prototype offsets of the fused passes in log2 units, one launch: cs2 = b2s * as2; ct2 = (b2t - c) * at2;
+// ct2p = (b2t - cp) * at2 (optional)
+__global__ void head_offsets_kernel(const float* __restrict__ b2s, const float* __restrict__ b2t, const float* __restrict__ c,
+                                    const float* __restrict__ cp, float as2, float at2, float* __restrict__ cs2,
+                                    float* __restrict__ ct2, float* __restrict__ ct2p, int64_t K) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float bt = b2t[k];
+  cs2[k] = b2s[k] * as2;
+  ct2[k] = (bt - c[k]) * at2;
+  if (ct2p) ct2p[k] = (bt - cp[k]) * at2;
+}
+// entry weights: out = base, except out[off + i] = mw[i] * scale for i < n (the iBOT entries' mask weights)
+__global__ void entry_weights_kernel(const float* __restrict__ base, int64_t total, const float* __restrict__ mw, int64_t off,
+                                     int64_t n, float scale, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  out[i] = (i >= off && i < off + n) ? mw[i - off] * scale : base[i];
+}
+
 struct ScalarTerms {
   const float* p[8];
   float w[8];
@@ -583,6 +603,25 @@ int dinox_scalar_fanout(const float* upstream, const float* weights, int n, floa
   for (int i = 0; i < 8; ++i) { t.p[i] = nullptr; t.w[i] = i < n ? weights[i] : 0.f; }
   scalar_fanout_kernel<<<1, 32, 0, stream>>>(upstream, t, n, scale, out);
   return check_launch("scalar_fanout_kernel", stream);
+}
+
+int dinox_head_offsets(const float* b2_student, const float* b2_teacher, const float* center, const float* center_patch,
+                       float inv_tau_s, float inv_tau_t, float* cs2, float* ct2, float* ct2_patch, int64_t K,
+                       dinox_stream_t stream) {
+  DINOX_REQUIRE(b2_student && b2_teacher && center && cs2 && ct2 && K > 0 && (!ct2_patch || center_patch), DINOX_E_BADARG,
+                "head_offsets: bad arguments");
+  head_offsets_kernel<<<(unsigned)((K + 255) / 256), 256, 0, stream>>>(b2_student, b2_teacher, center, center_patch,
+                                                                      inv_tau_s * DINOX_LOG2E, inv_tau_t * DINOX_LOG2E, cs2, ct2,
+                                                                      ct2_patch, K);
+  return check_launch("head_offsets_kernel", stream);
+}
+
+int dinox_entry_weights(const float* base, int64_t total, const float* mask_weights, int64_t offset, int64_t n, float scale,
+                        float* out, dinox_stream_t stream) {
+  DINOX_REQUIRE(base && out && total > 0 && n >= 0 && offset >= 0 && offset + n <= total && (n == 0 || mask_weights),
+                DINOX_E_BADARG, "entry_weights: bad arguments");
+  entry_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(base, total, mask_weights, offset, n, scale, out);
+  return check_launch("entry_weights_kernel", stream);
 }
 
 int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream) {

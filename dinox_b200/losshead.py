@@ -747,6 +747,12 @@ class _FusedHeadLoss(torch.autograd.Function):
         # per-kernel timing (ops.TIMER) keeps everything on one stream.
         main = torch.cuda.current_stream()
         side = _side_stream(dev) if (concurrency() >= 2 and not ops.TIMER.enabled) else None
+        # per-prototype offsets of both branches in one launch, before the streams fork (the centre teacher of the CLS
+        # rows and the centred patch teacher; Sinkhorn modes build theirs from the iteration results below)
+        pre = None
+        if teacher_mode == "center" and (not Mm or patch_mode == "center"):
+            pre = ops.head_offsets(b2.detach(), t_head[2].bias.detach(), loss_mod.center.reshape(-1),
+                                   center_patch.reshape(-1) if Mm else None, inv_ts, inv_tt)
         if side is not None:
             side.wait_stream(main)
         qt = refs = ht_e = None
@@ -786,7 +792,9 @@ class _FusedHeadLoss(torch.autograd.Function):
             center = loss_mod.center.reshape(-1)
             rb2_t = torch.empty(Mt_pad + Mm, dtype=torch.float32, device=dev)
             b_row = None
-            if teacher_mode == "center":
+            if pre is not None:
+                ct2 = pre[1]
+            elif teacher_mode == "center":
                 ct2 = ops.axpby(b2t, inv_tt * LOG2E, center, -inv_tt * LOG2E)
             else:  # Sinkhorn-Knopp on the (small) materialised CLS teacher logits
                 t_cls = ops.gemm_bf16(ht[:Mt], w2t, bias_n=b2t)
@@ -802,6 +810,8 @@ class _FusedHeadLoss(torch.autograd.Function):
                 a_col_p, b_row_patch = sinkhorn_knopp_biases(t_patch, teacher_temp, sk_iters, pg)
                 ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, a_col_p, -LOG2E)
                 del t_patch
+            elif pre is not None:
+                ct2_patch = pre[2]
             else:
                 ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E) if Mm else None
             if readback:
@@ -837,7 +847,7 @@ class _FusedHeadLoss(torch.autograd.Function):
         a_s = ops.gemm_bf16(xs, w1s, bias_n=b1.detach())
         hs = ops.gelu_fwd(a_s)
         b2s = b2.detach()
-        cs2 = ops.axpb(b2s, inv_ts * LOG2E)
+        cs2 = pre[0] if pre is not None else ops.axpb(b2s, inv_ts * LOG2E)
         with ops.TIMER.region("head_stats_student"):
             _, lse2_s = ops.head_stats(hs, w2s, inv_ts, cs2, want_nat=False)
         # ---- entries
@@ -851,9 +861,9 @@ class _FusedHeadLoss(torch.autograd.Function):
             main.wait_stream(side)
         cw = plan.cw_base
         if Mm:
-            cw = plan.cw_base.clone()
-            ops.axpb(masks_weight.detach().float().contiguous(), ibot_weight / Mt,
-                     0.0, out=cw[plan.e_cls_pad:plan.e_cls_pad + Mm])
+            mw = masks_weight.detach()
+            mw = mw if (mw.dtype == torch.float32 and mw.is_contiguous()) else mw.float().contiguous()
+            cw = ops.entry_weights(plan.cw_base, mw, plan.e_cls_pad, ibot_weight / Mt)
         # ---- pass 2
         lbuf = torch.empty(4, dtype=torch.float32, device=dev)     # [L_dino, L_ibot, total, -]
         losses = lbuf[:3]

@@ -665,6 +665,23 @@ def sqdiff(a: torch.Tensor, b: torch.Tensor, scale: float, want_delta: bool = Tr
     return loss, delta
 
 
+def head_offsets(b2s: torch.Tensor, b2t: torch.Tensor, center: torch.Tensor, center_patch: Optional[torch.Tensor],
+                 inv_tau_s: float, inv_tau_t: float):
+    """(cs2, ct2, ct2_patch | None): per-prototype log2-unit offsets of the fused passes, one launch."""
+    K = b2s.numel()
+    buf = torch.empty(3 if center_patch is not None else 2, K, dtype=torch.float32, device=b2s.device)
+    _ext.call("dinox_head_offsets", _p(b2s), _p(b2t), _p(center), _p(center_patch), float(inv_tau_s), float(inv_tau_t),
+              _p(buf[0]), _p(buf[1]), _p(buf[2]) if center_patch is not None else None, K, _stream())
+    return buf[0], buf[1], (buf[2] if center_patch is not None else None)
+
+
+def entry_weights(base: torch.Tensor, mask_weights: torch.Tensor, offset: int, scale: float) -> torch.Tensor:
+    out = torch.empty_like(base)
+    _ext.call("dinox_entry_weights", _p(base), base.numel(), _p(mask_weights), int(offset), mask_weights.numel(), float(scale),
+              _p(out), _stream())
+    return out
+
+
 def fill_(t: torch.Tensor, v: float = 0.0) -> torch.Tensor:
     assert t.dtype == torch.float32 and t.is_contiguous()
     _ext.call("dinox_fill_f32", _p(t), t.numel(), float(v), _stream())

@@ -333,6 +333,16 @@ DINOX_API int dinox_gather_rows_f32(const void* src, int dtype, int64_t ld_src, 
  * into a gradient tensor that already holds another term (Gram anchoring + iBOT on the same token tensor) */
 DINOX_API int dinox_scatter_add_rows_f32(const float* src, int64_t ld_src, const int64_t* idx, int64_t rows,
                                          int64_t D, float* dst, int64_t ld_dst, dinox_stream_t stream);
+/* per-prototype offsets of the fused passes (log2 units) in one launch: cs2 = b2_student/tau_s*log2e,
+ * ct2 = (b2_teacher - center)/tau_t*log2e, ct2_patch = (b2_teacher - center_patch)/tau_t*log2e (optional) -
+ * the bias add of zoo/arch.py:256 and the centring of scripts/phase5_big_run.py:703 folded into the epilogues */
+DINOX_API int dinox_head_offsets(const float* b2_student, const float* b2_teacher, const float* center,
+                                 const float* center_patch, float inv_tau_s, float inv_tau_t, float* cs2,
+                                 float* ct2, float* ct2_patch, int64_t K, dinox_stream_t stream);
+/* entry weights of pass 2: out = base (the CLS pair weights, 0 for padding) with out[offset + i] = mask_weights[i]*scale
+ * for the n iBOT entries */
+DINOX_API int dinox_entry_weights(const float* base, int64_t total, const float* mask_weights, int64_t offset,
+                                  int64_t n, float scale, float* out, dinox_stream_t stream);
 DINOX_API int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream);
 /* a9 step glue (scripts/phase5_big_run.py:1749-1772, `loss = L_dino + w_g*L_gram (+ w_k*L_koleo); loss /= accum`):
  *   out[0] = scale * sum_{i<n} weights[i] * terms[i][0]      (n <= 8 device scalars, fixed order)
