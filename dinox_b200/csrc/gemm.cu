@@ -668,6 +668,9 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 
 // "minus infinity" that stays finite under 0 * x
 #define DINOX_NEG_HUGE (-1.0e30f)
+#ifndef DINOX_EXP_G2
+#define DINOX_EXP_G2 0
+#endif
 template <int W>
 struct EpiGradRT {
   static constexpr bool kUsesTmaStore = true;
@@ -731,6 +734,9 @@ struct EpiGradRT {
   struct Impl {
     static_assert(BN == 256 && (W == 8 || W == 16), "EpiGradR is written for 256-wide tiles and 8 or 16 epilogue warps");
     static __device__ __forceinline__ void ldq(const __half* p, uint32_t (&r)[8], uint64_t pol) {
+#if DINOX_EXP_G2 & 1   // experiment: no teacher-probability loads
+      return;
+#endif
 #if DINOX_STREAM_EVICT_FIRST
       ldg256_hint(p, r, pol);
 #else
@@ -825,8 +831,11 @@ struct EpiGradRT {
           if (kColsW > 64) prefetch_l2(qnext + BN + 64);
         }
       }
-      const uint64_t as2 = pack2(e.as2, e.as2), nl2 = pack2(st.nl, st.nl), cw2 = pack2(st.cwt, st.cwt), nsc2 = pack2(nsc, nsc);
-      uint64_t lacc = pack2(0.f, 0.f);
+      // packed fp32 pairs through the sm_100 float2 intrinsics (FFMA2 / FADD2 / FMUL2): the register allocator pairs
+      // the values itself - hand-packed 64-bit asm operands cost ~5 IMAD.MOV per pair in this loop
+      const float2 as2 = make_float2(e.as2, e.as2), nl2 = make_float2(st.nl, st.nl), cw2 = make_float2(st.cwt, st.cwt),
+                   nsc2 = make_float2(nsc, nsc);
+      float2 lacc = make_float2(0.f, 0.f);
       uint8_t* wbase = smem + epi_warp * (kBufs * 4096);
       uint8_t* wbuf = wbase;
       WarpStage stg;
@@ -847,19 +856,15 @@ struct EpiGradRT {
           const float4 b4 = lds128(cb + j);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint64_t s2 = pack2u(cur[j + 2 * h], cur[j + 2 * h + 1]);
-            const uint64_t c2 = h ? pack2(b4.z, b4.w) : pack2(b4.x, b4.y);
-            const uint64_t u2 = add2(fma2(s2, as2, c2), nl2);
-            float ux, uy;
-            unpack2(u2, ux, uy);
-            const uint64_t pp = pack2(fast_ex2(ux), fast_ex2(uy));
+            const float2 s2 = make_float2(__uint_as_float(cur[j + 2 * h]), __uint_as_float(cur[j + 2 * h + 1]));
+            const float2 c2 = h ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y);
+            const float2 u2 = __fadd2_rn(__ffma2_rn(s2, as2, c2), nl2);
+            const float2 pp = make_float2(fast_ex2(u2.x), fast_ex2(u2.y));
             const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qv[j / 2 + h]));
-            const uint64_t nq = mul2(pack2(qf.x, qf.y), nsc2);
-            const uint64_t g2 = fma2(cw2, pp, nq);
-            lacc = fma2(nq, u2, lacc);
-            float gx, gy;
-            unpack2(g2, gx, gy);
-            __nv_bfloat162 hh = __floats2bfloat162_rn(gx, gy);
+            const float2 nq = __fmul2_rn(qf, nsc2);
+            const float2 g2 = __ffma2_rn(cw2, pp, nq);
+            lacc = __ffma2_rn(nq, u2, lacc);
+            __nv_bfloat162 hh = __floats2bfloat162_rn(g2.x, g2.y);
             packed[j / 2 + h] = *reinterpret_cast<uint32_t*>(&hh);
           }
         }
@@ -880,28 +885,29 @@ struct EpiGradRT {
           __syncwarp();
           const int col0 = tc.n_tile * BN + grp * kColsW + (c >> 2) * 64;
           if (lane == 0) {
-#if DINOX_STREAM_EVICT_FIRST
+#if DINOX_EXP_G2 & 2   // experiment: G is staged but never stored
+            if (false) {}
+#elif DINOX_STREAM_EVICT_FIRST
             if (row0 < p.M && col0 < p.N) sm100::tma_store_3d_hint(tmC, wbuf, col0, row0, 0, pol);
 #else
             if (row0 < p.M && col0 < p.N) sm100::tma_store_3d(tmC, wbuf, col0, row0, 0);
 #endif
             sm100::tma_store_commit();   // always: wait_read<kBufs-1> counts groups
           }
-          if (e.db2_partial) {
+          if (e.db2_partial && !(DINOX_EXP_G2 & 4)) {
             // column sums of the staged 32 x 64 tile: lane l owns columns 2l, 2l+1; row r of the tile is one
             // conflict-free 128-byte wavefront (16-byte piece j of row r lives at ((j ^ (r & 7)) << 4))
             const uint32_t cbase = stg.base + (lane & 3) * 4;
             const uint32_t piece = (uint32_t)lane >> 2;
-            uint64_t d2 = pack2(0.f, 0.f);
+            float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
               const uint32_t v = lds32(cbase + r * 128 + ((piece ^ (uint32_t)(r & 7)) << 4));
-              d2 = add2(d2, pack2u(v << 16, v & 0xffff0000u));
+              d2 = __fadd2_rn(d2, make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)));
             }
             const int col = col0 + 2 * lane;
             if (row0 < p.M && col < p.N) {
-              float d0, d1;
-              unpack2(d2, d0, d1);
+              const float d0 = d2.x, d1 = d2.y;
               float* o = e.db2_partial + (int64_t)(row0 >> 5) * p.N + col;
               if (col + 1 < p.N && (p.N & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(d0, d1);
               else { o[0] = d0; if (col + 1 < p.N) o[1] = d1; }
@@ -912,9 +918,7 @@ struct EpiGradRT {
         if (c + 1 < kChunks) sm100::tmem_wait_ld();
       }
       st.ahead = true;
-      float l0, l1;
-      unpack2(lacc, l0, l1);
-      if (st.in_b) st.loss_b -= l0 + l1; else st.loss_a -= l0 + l1;   // the accumulator holds -cwt q u
+      if (st.in_b) st.loss_b -= lacc.x + lacc.y; else st.loss_a -= lacc.x + lacc.y;   // the accumulator holds -cwt q u
     }
   };
 };
