@@ -143,3 +143,33 @@ def test_sharded_adamw_optimizer_protocol(dx):
     topt.step()
     for q, r in zip(opt2.params, ref):
         assert rel(q, r) < 1e-6
+
+
+def test_head_gradients_are_visible_to_autograd(dx):
+    """Default fused path: dW1/db1/dW2/db2 are autograd gradients of the head parameters (torch.autograd.grad and
+    parameter hooks see them); grads_in_place=True writes the same values straight into .grad instead."""
+    B, D, K = 8, 64, 1024
+    s_head, t_head, gen = _heads(dx, D, K, 7)
+    xs, xt = torch.randn(2 * B, D, generator=gen).to(DEV), torch.randn(2 * B, D, generator=gen).to(DEV)
+    seen = []
+    hook = s_head[2].weight.register_hook(lambda g: seen.append(g.detach().clone()))
+    x = xs.clone().requires_grad_(True)
+    dl = dx.DINOLoss(K, 0.9).to(DEV)
+    loss = dx.fused_head_dino_loss(x, xt, s_head, t_head, dl, 0.1, 0.04, update_center=False)["loss"]
+    grads = torch.autograd.grad(loss, [x] + list(s_head.parameters()))
+    hook.remove()
+    assert len(seen) == 1 and torch.equal(seen[0], grads[3])
+    assert all(p.grad is None for p in s_head.parameters())        # autograd.grad does not touch .grad
+    # the nn.Module form and the in-place fast path give the same numbers
+    mod = dx.FusedLossHead(s_head, t_head, dx.DINOLoss(K, 0.9).to(DEV)).to(DEV)
+    x2 = xs.clone().requires_grad_(True)
+    mod(x2, xt, 0.1, 0.04).backward()
+    for p, g in zip(s_head.parameters(), grads[1:]):
+        assert torch.equal(p.grad, g)
+        p.grad = None
+    x3 = xs.clone().requires_grad_(True)
+    dx.fused_head_dino_loss(x3, xt, s_head, t_head, dx.DINOLoss(K, 0.9).to(DEV), 0.1, 0.04, update_center=False,
+                            grads_in_place=True)["loss"].backward()
+    for p, g in zip(s_head.parameters(), grads[1:]):
+        assert rel(p.grad, g) < 1e-6
+    assert torch.equal(x3.grad, grads[0]) and torch.equal(x2.grad, grads[0])
