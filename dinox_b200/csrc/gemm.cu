@@ -476,7 +476,10 @@ struct EpiTeachQT {
   static constexpr int kColsW = 256 / kGroups;           // one granule (128 or 64 prototypes) per warp and tile
   // one staging buffer per warp (32 rows x 128 B) leaves five 16 KB operand stages beside the resident A rows;
   // the wait for the previous store's read sits behind the math of the next 32 columns
-  static constexpr int kBufs = 1;
+#ifndef DINOX_TEACHQ_STAGING_BUFS
+#define DINOX_TEACHQ_STAGING_BUFS 1
+#endif
+  static constexpr int kBufs = DINOX_TEACHQ_STAGING_BUFS;
   static constexpr int kStageBytes = kEpiWarps * kBufs * 4096;
   static constexpr int kEpiSmemBytes = kStageBytes + kEpiWarps * kColsW * 4;
   struct Params {
@@ -678,7 +681,10 @@ struct EpiGradRT {
   static constexpr int kGroups = W / 4;
   static constexpr int kColsW = 256 / kGroups;
   static constexpr int kChunks = kColsW / 16;
-  static constexpr int kSlots = 4;                       // 16-prototype chunks of teacher probabilities in flight
+#ifndef DINOX_GRADR_SLOTS
+#define DINOX_GRADR_SLOTS 4
+#endif
+  static constexpr int kSlots = DINOX_GRADR_SLOTS;       // 16-prototype chunks of teacher probabilities in flight
 #ifndef DINOX_GRADR_STAGING_BUFS
 #define DINOX_GRADR_STAGING_BUFS 1
 #endif
