@@ -158,8 +158,8 @@ SIGNATURES = {
     "dinox_head_grad2_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_head_grad2_db2_rows": (c_i64, [c_i64]),
     "dinox_head_grad2": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p,
-                                 c_void_p, c_int, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64,
+                                 c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "dinox_gemm_bf16_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                         c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_f32, c_void_p, c_void_p]),
     "dinox_normalize_tokens": (c_int, [c_void_p, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -167,6 +167,17 @@ SIGNATURES = {
                                            c_void_p, c_f32, c_void_p, c_i64, c_i64, c_void_p]),
     "dinox_gram_diff_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_gram_diff": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_f32, c_void_p, c_void_p, c_void_p]),
+    "dinox_gemm_bf16_balanced_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_gemm_bf16_balanced": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
+                                         c_int, c_f32, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dinox_gather_cast_bf16_2": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_i64,
+                                         c_void_p, c_i64, c_void_p]),
+    "dinox_gelu_bwd_gather": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "dinox_segment_cols_sum_chunks": (c_i64, [c_i64, c_i64]),
+    "dinox_segment_cols_sum_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "dinox_segment_cols_sum": (c_int, [c_void_p, c_int, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p]),
     "dinox_gather_cast_bf16": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p]),
     "dinox_gather_f32": (c_int, [c_void_p, c_void_p, c_i64, c_f32, c_void_p, c_void_p]),
     "dinox_scatter_rows_f32": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p]),

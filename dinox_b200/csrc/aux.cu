@@ -78,6 +78,54 @@ __global__ void gather_cast_vec_kernel(const T* __restrict__ src, int64_t ld_src
   }
 }
 
+// Two sources into one destination in ONE launch: rows [0, rows0) come from segment 0, rows [rows0, rows0 + rows1) from
+// segment 1 (the staging of [CLS rows | masked-patch rows] of one branch of the fused head).  16-byte vector rows only.
+struct GatherSeg {
+  const void* src;
+  int64_t ld_src;
+  const int64_t* idx;
+  int64_t rows;
+};
+template <typename T>
+__global__ void gather_cast2_kernel(GatherSeg s0, GatherSeg s1, int D, __nv_bfloat16* __restrict__ dst, int64_t ld_dst) {
+  int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= s0.rows + s1.rows) return;
+  __nv_bfloat16* d = dst + r * ld_dst;
+  const bool second = r >= s0.rows;
+  const GatherSeg& sg = second ? s1 : s0;
+  if (second) r -= s0.rows;
+  const int64_t sr = sg.idx ? sg.idx[r] : r;
+  const T* src = reinterpret_cast<const T*>(sg.src);
+  for (int c = lane * 8; c < D; c += 256) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (sr >= 0) {
+      if (sizeof(T) == 4) {
+        const float* sp = reinterpret_cast<const float*>(src) + sr * sg.ld_src + c;
+        const float4 v0 = ldg_stream_f4(reinterpret_cast<const float4*>(sp));
+        const float4 v1 = ldg_stream_f4(reinterpret_cast<const float4*>(sp + 4));
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v0.z, v0.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v1.x, v1.y), h3 = __floats2bfloat162_rn(v1.z, v1.w);
+        o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+      } else {
+        const uint4 v = ldg_stream_u4(reinterpret_cast<const uint4*>(src + sr * sg.ld_src + c));
+        if (!std::is_same<T, __half>::value) {
+          o = v;
+        } else {
+          const __half2* hp = reinterpret_cast<const __half2*>(&v);
+          __nv_bfloat162 h[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(hp[j]); h[j] = __floats2bfloat162_rn(f.x, f.y); }
+          o = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                         *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(d + c) = o;
+  }
+}
+
 // out[r] = src[idx[r]] (fp32 scalars; idx < 0 -> fill)
 __global__ void gather_f32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t n,
                                   float fill, float* __restrict__ out) {
@@ -165,6 +213,44 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dh, const float* __res
   for (int64_t r = r0; r < r1; ++r) {
     const float4 g = *reinterpret_cast<const float4*>(dh + r * D + c);
     const float4 x = *reinterpret_cast<const float4*>(a + r * D + c);
+    const float d0 = g.x * sc * gelu_grad_f(x.x), d1 = g.y * sc * gelu_grad_f(x.y);
+    const float d2 = g.z * sc * gelu_grad_f(x.z), d3 = g.w * sc * gelu_grad_f(x.w);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(d0, d1), hi = __floats2bfloat162_rn(d2, d3);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(da + r * D + c) = o;
+    s0 += d0; s1 += d1; s2 += d2; s3 += d3;
+  }
+  if (colsum_partial) *reinterpret_cast<float4*>(colsum_partial + (int64_t)blockIdx.y * D + c) = make_float4(s0, s1, s2, s3);
+}
+
+// The same with dh[r, :] = sum_{i in [ptr[r], ptr[r+1])} sum_{s < slabs} src[s*slab_stride + ent[i]*ld_src, :] formed on
+// the fly (entries outer, split-K slabs inner: the order of gather_sum_kernel, so the two routes agree bit for bit):
+// the per-row dL/dh of the fused head never exists in memory.
+__global__ void gelu_bwd_gather_kernel(const float* __restrict__ src, int64_t ld_src, int slabs, int64_t slab_stride,
+                                       const int64_t* __restrict__ ptr, const int64_t* __restrict__ ent,
+                                       const float* __restrict__ a, int64_t rows, int D, const float* __restrict__ scale_dev,
+                                       __nv_bfloat16* __restrict__ da, float* __restrict__ colsum_partial) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= D) return;
+  const float sc = scale_dev ? *scale_dev : 1.f;
+  const int64_t r0 = (int64_t)blockIdx.y * kGeluSlab;
+  const int64_t r1 = r0 + kGeluSlab < rows ? r0 + kGeluSlab : rows;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int64_t i0 = ptr[r0];
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t i1 = ptr[r + 1];
+    const float4 x = *reinterpret_cast<const float4*>(a + r * D + c);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = i0; i < i1; ++i) {
+      const float* base = src + ent[i] * ld_src + c;
+      for (int sl = 0; sl < slabs; ++sl) {
+        const float4 v = ldg_stream_f4(reinterpret_cast<const float4*>(base + sl * slab_stride));
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      }
+    }
+    i0 = i1;
     const float d0 = g.x * sc * gelu_grad_f(x.x), d1 = g.y * sc * gelu_grad_f(x.y);
     const float d2 = g.z * sc * gelu_grad_f(x.z), d3 = g.w * sc * gelu_grad_f(x.w);
     __nv_bfloat162 lo = __floats2bfloat162_rn(d0, d1), hi = __floats2bfloat162_rn(d2, d3);
@@ -423,6 +509,25 @@ int dinox_gather_cast_bf16(const void* src, int src_dtype, int64_t ld_src, const
   return check_launch("gather_cast_kernel", stream);
 }
 
+int dinox_gather_cast_bf16_2(const void* src0, int64_t ld_src0, const int64_t* idx0, int64_t rows0, const void* src1,
+                             int64_t ld_src1, const int64_t* idx1, int64_t rows1, int src_dtype, int64_t D, void* dst,
+                             int64_t ld_dst, dinox_stream_t stream) {
+  DINOX_REQUIRE(src0 && src1 && dst && rows0 >= 0 && rows1 >= 0 && D > 0 && ld_dst >= D, DINOX_E_BADARG,
+                "gather_cast_2: bad arguments");
+  const int es = src_dtype == DINOX_F32 ? 4 : 2;
+  DINOX_REQUIRE(D % 8 == 0 && aligned16(src0) && aligned16(src1) && aligned16(dst) && (ld_src0 * es) % 16 == 0 &&
+                    (ld_src1 * es) % 16 == 0 && (ld_dst * 2) % 16 == 0,
+                DINOX_E_ALIGN, "gather_cast_2: rows must be 16-byte vectors (use dinox_gather_cast_bf16 per segment otherwise)");
+  if (rows0 + rows1 == 0) return DINOX_OK;
+  const unsigned grid = (unsigned)((rows0 + rows1 + 7) / 8);
+  const GatherSeg s0{src0, ld_src0, idx0, rows0}, s1{src1, ld_src1, idx1, rows1};
+  if (src_dtype == DINOX_F32) gather_cast2_kernel<float><<<grid, 256, 0, stream>>>(s0, s1, (int)D, (__nv_bfloat16*)dst, ld_dst);
+  else if (src_dtype == DINOX_BF16) gather_cast2_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(s0, s1, (int)D, (__nv_bfloat16*)dst, ld_dst);
+  else if (src_dtype == DINOX_F16) gather_cast2_kernel<__half><<<grid, 256, 0, stream>>>(s0, s1, (int)D, (__nv_bfloat16*)dst, ld_dst);
+  else { set_error("gather_cast_2: unknown dtype %d", src_dtype); return DINOX_E_BADARG; }
+  return check_launch("gather_cast2_kernel", stream);
+}
+
 int dinox_gather_f32(const float* src, const int64_t* idx, int64_t n, float fill, float* out, dinox_stream_t stream) {
   DINOX_REQUIRE(src && idx && out && n >= 0, DINOX_E_BADARG, "gather_f32: bad arguments");
   if (n == 0) return DINOX_OK;
@@ -479,6 +584,18 @@ int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int64_t D, con
   dim3 grid((unsigned)((D / 4 + 127) / 128), (unsigned)((rows + kGeluSlab - 1) / kGeluSlab));
   gelu_bwd_kernel<<<grid, 128, 0, stream>>>(dh, a, rows, (int)D, scale_dev, (__nv_bfloat16*)da_bf16, colsum_partial);
   return check_launch("gelu_bwd_kernel", stream);
+}
+
+int dinox_gelu_bwd_gather(const float* src, int64_t ld_src, int slabs, int64_t slab_stride, const int64_t* ptr,
+                          const int64_t* ent, const float* a, int64_t rows, int64_t D, const float* scale_dev, void* da_bf16,
+                          float* colsum_partial, dinox_stream_t stream) {
+  DINOX_REQUIRE(src && ptr && ent && a && da_bf16 && rows > 0 && D > 0 && D % 4 == 0 && slabs >= 1 && ld_src % 4 == 0 &&
+                    slab_stride % 4 == 0 && aligned16(src),
+                DINOX_E_BADARG, "gelu_bwd_gather: bad arguments");
+  dim3 grid((unsigned)((D / 4 + 127) / 128), (unsigned)((rows + kGeluSlab - 1) / kGeluSlab));
+  gelu_bwd_gather_kernel<<<grid, 128, 0, stream>>>(src, ld_src, slabs, slab_stride, ptr, ent, a, rows, (int)D, scale_dev,
+                                                   (__nv_bfloat16*)da_bf16, colsum_partial);
+  return check_launch("gelu_bwd_gather_kernel", stream);
 }
 
 int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64_t D, float alpha, const float* bias,

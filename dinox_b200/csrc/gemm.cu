@@ -38,6 +38,10 @@ struct EpiStore {
     const float* add_src = nullptr;
     int64_t ld_add = 0;
     float add_scale = 0.f;
+    // ordered split (CoreParams::os_*): one counter per (tile, TMEM lane quarter), zero between launches.  Part j of a
+    // tile waits for the counter to read j, adds its contribution (part 0: store / accumulate as configured, parts
+    // > 0: always reduce-add) and publishes j + 1 (the last part: 0) once its bulk stores have completed.
+    uint32_t* order_flags = nullptr;
   };
   struct State {
     int flip = 0;
@@ -59,8 +63,17 @@ struct EpiStore {
       const int slab = tc.batch + tc.split;
       uint8_t* wbase = smem + epi_warp * (kBufs * 4096);
       constexpr int kChunks = BN / 32;           // 32-column TMEM chunks
+      // (the phantom second tile of a ragged last CTA pair stores nothing and owns no counters)
+      const bool ordered = tc.kparts > 1 && tc.m_tile < p.num_m_tiles;
+      const bool accumulate = e.accumulate || (ordered && tc.kpart > 0);
+      const bool first_part = tc.kpart == 0;     // bias / addend enter once
+      uint32_t* flag = ordered ? e.order_flags + ((int64_t)tc.n_tile * p.num_m_tiles + tc.m_tile) * 4 + q : nullptr;
       uint32_t ra[32], rb[32];
       sm100::tmem_ld32_nowait(taddr, ra);
+      if (ordered && tc.kpart > 0) {             // my predecessor's rows are in memory before my first reduce-add
+        if (lane == 0) sm100::flag_wait(flag, (uint32_t)tc.kpart);
+        __syncwarp();
+      }
       sm100::tmem_wait_ld();
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
@@ -72,7 +85,7 @@ struct EpiStore {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(cur[j]) * alpha;
-        if (e.add_src) {
+        if (e.add_src && first_part) {
           const int64_t grow = (int64_t)tc.row_shift + row0 + lane;     // this thread's row of the whole problem
           if (grow < (int64_t)p.M + tc.row_shift && grow < p.M && col0 + 32 <= p.N) {
             const float4* src = reinterpret_cast<const float4*>(e.add_src + grow * e.ld_add + col0);
@@ -88,7 +101,7 @@ struct EpiStore {
               if (col0 + j < p.N) v[j] = fmaf(__ldg(e.add_src + grow * e.ld_add + col0 + j), e.add_scale, v[j]);
           }
         }
-        if (e.bias_n) {
+        if (e.bias_n && first_part) {
           if (col0 + 32 <= p.N) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -144,7 +157,7 @@ struct EpiStore {
           __syncwarp();
           if (lane == 0) {
             if (row0 < p.M && col0 < p.N) {
-              if (e.accumulate) sm100::tma_reduce_add_3d(tmC, wbuf, col0, row0, slab);
+              if (accumulate) sm100::tma_reduce_add_3d(tmC, wbuf, col0, row0, slab);
               else sm100::tma_store_3d(tmC, wbuf, col0, row0, slab);
             }
             sm100::tma_store_commit();   // always: see the bf16 branch
@@ -152,6 +165,14 @@ struct EpiStore {
           st.flip ^= 1;
         }
         if (c + 1 < kChunks) sm100::tmem_wait_ld();
+      }
+      if (ordered) {   // hand the tile's rows of this lane quarter to the next part
+        if (lane == 0) {
+          sm100::tma_store_wait_all<0>();        // completed, not merely read out of the staging buffers
+          __threadfence();
+          sm100::flag_release(flag, tc.kpart + 1 == tc.kparts ? 0u : (uint32_t)(tc.kpart + 1));
+        }
+        __syncwarp();
       }
     }
   };
@@ -698,6 +719,8 @@ struct EpiGradRT {
     const float* cw;         // (M) entry weight, 0 for padding
     const float* rb2;        // (M) teacher row offset (log2) per entry
     const int* trow;         // (M) row of qt / refs holding the entry's teacher
+    const int* srow;         // NULL: lse2 / rb2 are per ENTRY.  Else (M) student row of the entry (-1 = padding) and
+                             // lse2 is indexed by student row, rb2 by teacher row (trow): no per-entry gathers upstream
     const __half* qt;        // (teacher rows, ldq) un-normalised teacher probabilities
     int64_t ldq;
     const float* refs;       // (kGroups*num_n_tiles, ld_refs)
@@ -707,6 +730,11 @@ struct EpiGradRT {
     int m_step;              // > 0: column sweep, consecutive tiles of a CTA are m_step M tiles apart
     float* db2_partial;      // (ceil(M/32), N) or NULL
     float* loss_partial;     // (gridDim.x * kEpiWarps * 2)
+    // ticket != NULL: the epilogue warp that finishes LAST adds up all loss partials itself (fixed order) and writes
+    // loss_out[0..2]; the counter returns to 0 for the next launch.  NULL: a pair_sum launch follows.
+    unsigned* ticket = nullptr;
+    float* loss_out = nullptr;
+    int loss_accumulate = 0;
   };
   struct State {
     float loss_a = 0.f, loss_b = 0.f;
@@ -734,6 +762,30 @@ struct EpiGradRT {
       e.loss_partial[((int64_t)blockIdx.x * kEpiWarps + epi_warp) * 2 + 0] = a * sc;
       e.loss_partial[((int64_t)blockIdx.x * kEpiWarps + epi_warp) * 2 + 1] = b * sc;
       sm100::tma_store_wait_all<0>();
+    }
+    if (e.ticket) {
+      const unsigned n = gridDim.x * kEpiWarps;
+      unsigned t = 0;
+      if (lane == 0) {
+        __threadfence();                       // the partials above are visible before the ticket is
+        t = atomicAdd(e.ticket, 1u);
+      }
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t == n - 1) {                        // every other warp of the grid has published its partials
+        __threadfence();
+        float s0 = 0.f, s1 = 0.f;
+        for (unsigned i = lane; i < n; i += 32) {
+          s0 += __ldcg(e.loss_partial + 2 * i);
+          s1 += __ldcg(e.loss_partial + 2 * i + 1);
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        if (lane == 0) {
+          const float o0 = s0 + (e.loss_accumulate ? e.loss_out[0] : 0.f), o1 = s1 + (e.loss_accumulate ? e.loss_out[1] : 0.f);
+          e.loss_out[0] = o0; e.loss_out[1] = o1; e.loss_out[2] = o0 + o1;
+          *e.ticket = 0u;
+        }
+      }
     }
   }
   template <int BN>
@@ -765,10 +817,16 @@ struct EpiGradRT {
       if (tc.m_tile != st.n_mtile) {   // a new row for this thread (once per run in the resident-A schedule)
         const int row = tc.m_tile * BM + epi_quarter() * 32 + lane;
         const bool ok = row < p.M;
-        st.n_lse = ok ? __ldg(e.lse2 + row) : 0.f;
         st.n_cw = ok ? __ldg(e.cw + row) : 0.f;
-        st.n_rb = ok ? __ldg(e.rb2 + row) : 0.f;
         st.n_trow = ok ? __ldg(e.trow + row) : 0;
+        if (e.srow) {   // row statistics live per student / teacher ROW; dead entries (cw = 0) never use them
+          const int sr = ok ? __ldg(e.srow + row) : -1;
+          st.n_lse = sr >= 0 ? __ldg(e.lse2 + sr) : 0.f;
+          st.n_rb = ok ? __ldg(e.rb2 + st.n_trow) : 0.f;
+        } else {
+          st.n_lse = ok ? __ldg(e.lse2 + row) : 0.f;
+          st.n_rb = ok ? __ldg(e.rb2 + row) : 0.f;
+        }
         st.n_mtile = tc.m_tile;
         if (e.m_step > 0) {
           // column sweep: the row changes with every tile.  The teacher row of THIS tile was looked up one fetch ago
@@ -1328,6 +1386,35 @@ struct Operand {
 };
 
 // output of the TMA-store epilogues: (slabs, M, N) with leading dimension ld and slab stride
+// Ordered split for a GEMM of `tiles` super tiles on `ncl` clusters with `kblocks` k-blocks per tile: which tiles are cut
+// (from `first` on) into how many parts.  Cost model in units of one whole tile: waves of equal items; every extra part
+// of a tile costs one more epilogue pass over the output (`kPartCost`).  Returns parts = 0 when nothing beats whole tiles.
+struct OrderedSplit { int first = 0, parts = 0; };
+static OrderedSplit plan_ordered_split(int64_t tiles, int64_t ncl, int64_t kblocks) {
+  OrderedSplit best;
+  if (tiles <= 0 || ncl <= 1 || tiles % ncl == 0) return best;
+  constexpr double kPartCost = 0.004;
+  // parts of one tile that land in the same round run side by side and their epilogues hand over one after the
+  // other: an item must be long (>= 32 k-blocks of MMA work) next to an epilogue pass for that chain to stay hidden
+  constexpr int kMinKb = 32, kMaxParts = 16;
+  double best_cost = (double)((tiles + ncl - 1) / ncl);
+  const int64_t full = tiles / ncl * ncl, left = tiles - full;
+  for (int variant = 0; variant < 2; ++variant) {
+    // 0: only the tiles of the last, partial wave are cut; 1: every tile is cut
+    const int64_t first = variant == 0 ? full : 0, cut = tiles - first;
+    if (variant == 0 && full == 0) continue;
+    for (int parts = 2; parts <= kMaxParts; ++parts) {
+      if ((kblocks + parts - 1) / parts < kMinKb) break;
+      if (((kblocks + parts - 1) / parts) * (parts - 1) >= kblocks) continue;   // an empty last part
+      const double waves = (double)((cut * parts + ncl - 1) / ncl) / parts;
+      const double cost = (double)(first / ncl) + waves + kPartCost * parts * ((double)cut / tiles);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best.first = (int)first; best.parts = parts; }
+    }
+  }
+  (void)left;
+  return best;
+}
+
 struct OutDesc {
   void* ptr = nullptr;
   int is_bf16 = 0;
@@ -1338,6 +1425,9 @@ struct OutDesc {
   int owners = 0;
   int64_t rows_per_owner = 0;
   void* owner_ptr[8] = {};
+  // ordered split allowed (plain fp32 TMA-store GEMMs): the zeroed counters the epilogue's order_flags point to hold
+  // at least order_flag_count entries (4 per 128-row tile of the output)
+  int64_t order_flag_count = 0;
 };
 
 static int make_operand_tmap(CUtensorMap* tm, const Operand& o, int64_t K, int tile_rows, int64_t batches, const char* what) {
@@ -1395,6 +1485,15 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
   p.splits = (int)splits;
   p.kb_per_split = (int)((p.num_k_blocks + splits - 1) / splits);
   p.rows_per_owner = NOUT > 1 ? (int)od.rows_per_owner : 0;
+  int64_t os_items = 0;
+  if (od.order_flag_count > 0 && splits == 1 && batches == 1 && RES == kResNone && NOUT == 1 && NSUB == 1) {
+    const int64_t tiles = (int64_t)((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles;
+    const OrderedSplit os = plan_ordered_split(tiles, num_sms() / CL, p.num_k_blocks);
+    if (os.parts >= 2 && (int64_t)p.num_m_tiles * p.num_n_tiles * 4 <= od.order_flag_count) {
+      p.os_first = os.first; p.os_parts = os.parts; p.os_kb = (p.num_k_blocks + os.parts - 1) / os.parts;
+      os_items = os.first + (tiles - os.first) * os.parts;
+    }
+  }
   DINOX_REQUIRE(splits == 1 || (int64_t)p.kb_per_split * (splits - 1) < p.num_k_blocks, DINOX_E_BADARG,
                 "%s: %lld splits leave an empty K range", name, (long long)splits);
   DINOX_REQUIRE(RES != kResA || (p.num_k_blocks <= kResKBlocks && !a0.mn_major && splits == 1), DINOX_E_UNSUPPORTED,
@@ -1412,7 +1511,8 @@ static int launch(const Operand& a0, const Operand& b0, const Operand* a1, const
     DINOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const int64_t super = (int64_t)((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * (splits > 1 ? splits : batches);
+  const int64_t super = os_items > 0 ? os_items
+                                    : (int64_t)((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * (splits > 1 ? splits : batches);
   DINOX_REQUIRE(super < (1ll << 31), DINOX_E_BADARG, "%s: too many tiles", name);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)launch_grid(super, CL));
@@ -1486,6 +1586,8 @@ struct StoreArgs {
   const float* alpha_dev;
   const float* bias_n;
   int64_t slab_stride;   // output elements between batches / splits
+  uint32_t* order_flags = nullptr;   // ordered split allowed: zeroed counters, order_flag_count of them
+  int64_t order_flag_count = 0;
 };
 
 template <class Epi>
@@ -1518,6 +1620,10 @@ static int launch_store(int64_t M, int64_t N, const Operand& a, const Operand& b
   OutDesc od;
   od.ptr = sa.out; od.is_bf16 = sa.out_bf16; od.ld = sa.ldo; od.slab_stride = sa.slab_stride;
   od.slabs = splits > 1 ? splits : batches;
+  if (sa.order_flags && !sa.out_bf16 && splits == 1 && batches == 1) {
+    ep.order_flags = sa.order_flags;
+    od.order_flag_count = sa.order_flag_count;
+  }
   return launch_store_t<EpiStore>(M, N, a, b, K, m_fastest, ep, od, stream, batches, splits);
 }
 
@@ -1545,6 +1651,28 @@ int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N,
   if (rc) return rc;
   Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
   StoreArgs sa{C, ldc, out_dtype == DINOX_BF16, accumulate, alpha, alpha_dev, bias_n, 0};
+  return launch_store(M, N, a, b, K, m_fastest, sa, stream, 1, 1);
+}
+
+/* fp32 GEMM whose tile count does not fill whole waves of the persistent grid: the tiles of the partial wave (or all
+ * tiles when there are fewer tiles than clusters) are cut along K into parts that accumulate into C in a FIXED order
+ * (part j waits for part j - 1 of its tile through the counters in `flags`), see CoreParams::os_*. */
+size_t dinox_gemm_bf16_balanced_workspace_bytes(int64_t M, int64_t N) {
+  if (M <= 0 || N <= 0) return 0;
+  return (size_t)((M + BM - 1) / BM) * ((N + 127) / 128) * 4 * sizeof(uint32_t);
+}
+
+int dinox_gemm_bf16_balanced(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                             int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int accumulate, float alpha,
+                             const float* alpha_dev, const float* bias_n, int m_fastest, void* flags,
+                             dinox_stream_t stream) {
+  int rc = gemm_common_checks(A, B, C, N, ldc, DINOX_F32, "gemm_bf16_balanced");
+  if (rc) return rc;
+  DINOX_REQUIRE(flags && (reinterpret_cast<uintptr_t>(flags) & 3u) == 0, DINOX_E_BADARG, "gemm_bf16_balanced: flags missing");
+  Operand a{A, M, lda, a_mn_major ? 1 : 0}, b{B, N, ldb, b_mn_major ? 1 : 0};
+  StoreArgs sa{C, ldc, 0, accumulate, alpha, alpha_dev, bias_n, 0};
+  sa.order_flags = reinterpret_cast<uint32_t*>(flags);
+  sa.order_flag_count = (int64_t)(dinox_gemm_bf16_balanced_workspace_bytes(M, N) / sizeof(uint32_t));
   return launch_store(M, N, a, b, K, m_fastest, sa, stream, 1, 1);
 }
 
@@ -1802,9 +1930,9 @@ int64_t dinox_head_grad2_db2_rows(int64_t E) { return E <= 0 ? 0 : (E + 31) / 32
 
 int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int64_t D, int64_t ldh, int64_t ldw,
                      float inv_tau_s, const float* cs2, const float* lse2_e, const float* cw_e, const float* rb2_e,
-                     const int32_t* trow_e, const void* qt, int64_t ldq, const float* refs, int64_t ld_refs,
-                     int64_t alt_from, void* G, int64_t ldg, float* db2_partial, float* loss_out, int loss_accumulate,
-                     void* workspace, dinox_stream_t stream) {
+                     const int32_t* trow_e, const int32_t* srow_e, const void* qt, int64_t ldq, const float* refs,
+                     int64_t ld_refs, int64_t alt_from, void* G, int64_t ldg, float* db2_partial, float* loss_out,
+                     int loss_accumulate, void* workspace, uint32_t* ticket, dinox_stream_t stream) {
   DINOX_REQUIRE(HsE && W2s && cs2 && lse2_e && cw_e && rb2_e && trow_e && qt && refs && G && loss_out && workspace,
                 DINOX_E_BADARG, "head_grad2: null pointer");
   DINOX_REQUIRE(E > 0 && K > 0 && D > 0, DINOX_E_BADARG, "head_grad2: empty problem");
@@ -1817,7 +1945,8 @@ int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int
   Operand a{HsE, E, ldh, 0}, b{W2s, K, ldw, 0};
   EpiGradR::Params ep;
   ep.as2 = inv_tau_s * DINOX_LOG2E; ep.inv_tau_s = inv_tau_s;
-  ep.cs2 = cs2; ep.lse2 = lse2_e; ep.cw = cw_e; ep.rb2 = rb2_e; ep.trow = trow_e;
+  ep.cs2 = cs2; ep.lse2 = lse2_e; ep.cw = cw_e; ep.rb2 = rb2_e; ep.trow = trow_e; ep.srow = srow_e;
+  ep.ticket = ticket; ep.loss_out = loss_out; ep.loss_accumulate = loss_accumulate;
   ep.qt = reinterpret_cast<const __half*>(qt); ep.ldq = ldq; ep.refs = refs; ep.ld_refs = ld_refs;
   ep.alt_from = (int)(alt_from < 0 ? 0 : (alt_from > (1ll << 30) ? (1ll << 30) : alt_from));
   ep.db2_partial = db2_partial; ep.loss_partial = reinterpret_cast<float*>(workspace);
@@ -1834,7 +1963,7 @@ int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int
   else
     rc = cl2 ? launch<256, 1, 1, 2, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair>")
              : launch<256, 1, 1, 1, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2");
-  if (rc) return rc;
+  if (rc || ticket) return rc;
   const int grid = launch_grid((((E + BM - 1) / BM + cl - 1) / cl) * num_n, cl);
   pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * EpiGradR::kEpiWarps, loss_out,
                                           loss_accumulate, /*write_total=*/1);

@@ -49,6 +49,7 @@ constexpr int UMMA_K = 16;
 struct TileCoord {
   int m_tile, n_tile, batch, split;
   int row_shift = 0;   // sharded output only: rows of the problem that precede the owner's shard (m_tile is shard-local)
+  int kpart = 0, kparts = 1;   // ordered split: this item reduces part kpart of kparts of the K range into the SAME output
 };
 
 struct CoreParams {
@@ -59,6 +60,13 @@ struct CoreParams {
   int batches;                 // > 1: independent problems along a third tensor-map dimension
   int splits;                  // > 1: split-K, split s reduces k-blocks [s*kb_per_split, ...) into output slab s
   int kb_per_split;
+  // Ordered split (os_parts >= 2; splits == batches == 1): super tiles [0, os_first) are whole items; each of the
+  // remaining ones is cut into os_parts K ranges of os_kb k-blocks that accumulate into the same output IN PART ORDER
+  // (the epilogue of part j waits for part j - 1 of its tile, see EpiStore), so the result does not depend on timing.
+  // Items are numbered whole tiles first, then part-major: every item only depends on items with a smaller number,
+  // which the round-robin walk has already started - no deadlock on a resident (persistent) grid.  Used to fill
+  // the last, partial wave of a GEMM whose tile count is not a multiple of the cluster count.
+  int os_first = 0, os_parts = 0, os_kb = 0;
   int rows_per_owner;          // > 0: the output rows are sharded over several buffers (one tensor map each, e.g. the
                                // peer-mapped gradient shards of the data-parallel ranks): M tile t goes to map
                                // t*BM / rows_per_owner at local row t*BM % rows_per_owner.  Multiple of BM.  0 = one map.
@@ -149,9 +157,25 @@ struct TileWalker {
     if (rem_a > 0) { cn = cid; cm = 0; m_lo = 0; m_hi = num_m; n_step = ncl; }
     else { cn = b_cn; cm = b_cm; m_lo = b_lo; m_hi = b_hi; n_step = b_step; }
   }
+  // Ordered split (CoreParams::os_*): item index o_i walks cid, cid + ncl, ...; a division per item is nothing
+  // next to the >= 10 us an item of these GEMMs takes.
+  bool ordered = false;
+  int o_i = 0, o_stride = 0, o_first = 0, o_left = 1, o_parts = 1;
+  __host__ __device__ __forceinline__ void init_ordered(const CoreParams& p, int num_m_super, int cid, int ncl) {
+    ordered = true;
+    m_fastest = p.m_fastest != 0;
+    nfast = m_fastest ? num_m_super : p.num_n_tiles;
+    nslow = m_fastest ? p.num_n_tiles : num_m_super;
+    const int tiles = num_m_super * p.num_n_tiles;
+    o_first = p.os_first; o_left = tiles - p.os_first > 0 ? tiles - p.os_first : 1; o_parts = p.os_parts;
+    const int total = p.os_first + (tiles - p.os_first) * p.os_parts;
+    o_i = cid; o_stride = ncl;
+    remaining = cid < total ? (total - cid + ncl - 1) / ncl : 0;
+  }
   __host__ __device__ __forceinline__ bool valid() const { return remaining > 0; }
   __host__ __device__ __forceinline__ void next() {
     --remaining;
+    if (ordered) { o_i += o_stride; return; }
     if (columns) {
       if (rem_a > 0 && --rem_a == 0) { cn = b_cn; cm = b_cm; m_lo = b_lo; m_hi = b_hi; n_step = b_step; return; }
       if (++cm == m_hi) { cm = m_lo; cn += n_step; }
@@ -168,6 +192,18 @@ struct TileWalker {
   // CL-wide super tile -> this CTA's tile
   __host__ __device__ __forceinline__ TileCoord coord(const CoreParams& p, int cl, int crank) const {
     TileCoord c;
+    if (ordered) {
+      int t = o_i;
+      if (o_i >= o_first) {
+        const int j = o_i - o_first;
+        c.kpart = j / o_left; c.kparts = o_parts; t = o_first + j - c.kpart * o_left;
+      }
+      const int s_ = t / nfast, f_ = t - s_ * nfast;
+      c.m_tile = (m_fastest ? f_ : s_) * cl + crank;
+      c.n_tile = m_fastest ? s_ : f_;
+      c.batch = 0; c.split = 0;
+      return c;
+    }
     if (columns) { c.m_tile = cm * cl + crank; c.n_tile = cn; c.batch = 0; c.split = 0; return c; }
     c.m_tile = (m_fastest ? fast : slow) * cl + crank;
     c.n_tile = m_fastest ? slow : fast;
@@ -299,6 +335,8 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
     walk.init_range(p, num_m_super, first, min(per, num_super - first));
   } else if (RESB) {
     walk.init_columns(p, num_m_super, cid, ncl);
+  } else if (p.os_parts > 1) {
+    walk.init_ordered(p, num_m_super, cid, ncl);
   } else {
     walk.init(p, num_m_super, cid, ncl, num_super);
   }
@@ -316,8 +354,9 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
       for (; walk.valid(); walk.next()) {
         const TileCoord tc = walk.coord(p, CL, crank);
         const int m0 = tc.m_tile * BM, n0 = tc.n_tile * BN;
-        const int kb0 = tc.split * p.kb_per_split;
-        const int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
+        int kb0 = tc.split * p.kb_per_split;
+        int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
+        if (tc.kparts > 1) { kb0 = tc.kpart * p.os_kb; kb1 = min(kb0 + p.os_kb, p.num_k_blocks); }
         if (RESA && (tc.m_tile != res_tile || tc.batch != res_batch)) {
           // (re)load the resident A rows of sub-GEMM 0: every k-block, once per M tile.  The previous
           // resident tile must have been read by its last MMA (res_empty, committed by the MMA issuer).
@@ -449,8 +488,9 @@ __device__ __forceinline__ void gemm_body(const CoreParams& p, const typename Ep
       uint32_t res_phase = 0;
       for (; walk.valid(); walk.next()) {
         const TileCoord tc = walk.coord(p, CL, crank);
-        const int kb0 = tc.split * p.kb_per_split;
-        const int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
+        int kb0 = tc.split * p.kb_per_split;
+        int kb1 = p.splits > 1 ? min(kb0 + p.kb_per_split, p.num_k_blocks) : p.num_k_blocks;
+        if (tc.kparts > 1) { kb0 = tc.kpart * p.os_kb; kb1 = min(kb0 + p.os_kb, p.num_k_blocks); }
         bool res_last = false;    // is this the last tile that reads the current resident A?
         if (RESA) {
           if (tc.m_tile != res_tile || tc.batch != res_batch) {

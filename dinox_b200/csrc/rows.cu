@@ -232,6 +232,86 @@ cols_sum_kernel(const T* __restrict__ x, int64_t rows, int64_t K, int64_t ld, fl
   }
 }
 
+// Column sums of up to two row ranges of one matrix in ONE launch (the centre statistics of the fused head: sum of the
+// teacher activations over the CLS rows and over the masked-patch rows).  Blocks sum 64-row chunks into a scratch
+// slab; the LAST block of a (segment, column block) - found with a ticket counter - adds the chunk sums in chunk
+// order, so the result does not depend on which block that is.  The ticket returns to 0: graph replays and
+// later launches may reuse it without a memset.  Block (0, 0, seg) also copies the segment's row count.
+struct SumSegs {
+  int64_t begin[2], end[2];
+};
+constexpr int kSegChunk = 64;
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(32 * kColSumGroups)
+segment_cols_sum_kernel(const T* __restrict__ x, int64_t K, int64_t ld, SumSegs sg, float* __restrict__ out /* (nseg, K) */,
+                        const float* __restrict__ counts_in, float* __restrict__ counts_out,
+                        float* __restrict__ scratch /* (nseg, gridDim.y, K) */, unsigned* __restrict__ tickets) {
+  __shared__ float red[kColSumGroups][32][4];
+  __shared__ int is_last;
+  const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+  const int seg = blockIdx.z;
+  const int64_t k = ((int64_t)blockIdx.x * 32 + cx) * 4;
+  const int64_t r0 = sg.begin[seg] + (int64_t)blockIdx.y * kSegChunk;
+  const int64_t r1 = r0 + kSegChunk < sg.end[seg] ? r0 + kSegChunk : sg.end[seg];
+  const int nchunks = (int)((sg.end[seg] - sg.begin[seg] + kSegChunk - 1) / kSegChunk);
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < K) {
+    for (int64_t i = r0 + gy; i < r1; i += kColSumGroups) {   // 64 rows / 16 groups: 4 independent loads per thread
+      float v[4];
+      load4<T, kVec>(x + i * ld, k, K, v, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[gy][cx][j] = a[j];
+  __syncthreads();
+  float* mine = scratch + ((int64_t)seg * gridDim.y + blockIdx.y) * K;
+  if (gy == 0 && k < K && (int)blockIdx.y < nchunks) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < kColSumGroups; ++g) t += red[g][cx][j];
+      if (k + j < K) mine[k + j] = t;
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && counts_out) counts_out[seg] = counts_in[seg];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* tk = tickets + seg * gridDim.x + blockIdx.x;
+    const unsigned t = atomicAdd(tk, 1u);
+    is_last = (t == gridDim.y - 1);
+    if (is_last) *tk = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < K) {
+    const float* base = scratch + (int64_t)seg * gridDim.y * K;
+    for (int c = gy; c < nchunks; c += kColSumGroups) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k + j < K) b[j] += __ldcg(base + (int64_t)c * K + k + j);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[gy][cx][j] = b[j];
+  __syncthreads();
+  if (gy == 0 && k < K) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < kColSumGroups; ++g) t += red[g][cx][j];
+      if (k + j < K) out[(int64_t)seg * K + k + j] = t;
+    }
+  }
+}
+
 __global__ void lse_combine_kernel(const float* __restrict__ g, int world, int64_t K, float add,
                                    float* __restrict__ out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -527,6 +607,45 @@ int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld
     else cols_sum_kernel<T, false><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, rows, K, ld, out, rows);
   });
   return check_launch("cols_sum_kernel", stream);
+}
+
+int64_t dinox_segment_cols_sum_chunks(int64_t rows0, int64_t rows1) {
+  const int64_t m = rows0 > rows1 ? rows0 : rows1;
+  return m > 0 ? (m + kSegChunk - 1) / kSegChunk : 1;
+}
+
+size_t dinox_segment_cols_sum_workspace_bytes(int64_t rows0, int64_t rows1, int64_t K) {
+  // [tickets: 2 * ceil(K/128) unsigned, rounded up to 256 B | scratch (2, chunks, K) fp32]
+  const size_t tk = ((size_t)(2 * ((K + 127) / 128)) * sizeof(unsigned) + 255) / 256 * 256;
+  return tk + (size_t)2 * dinox_segment_cols_sum_chunks(rows0, rows1) * K * sizeof(float);
+}
+
+int dinox_segment_cols_sum(const void* x, int dtype, int64_t K, int64_t ld, int nseg, const int64_t* seg_begin,
+                           const int64_t* seg_end, float* out, const float* counts_in, float* counts_out, void* workspace,
+                           dinox_stream_t stream) {
+  DINOX_REQUIRE(x && out && workspace && seg_begin && seg_end && (nseg == 1 || nseg == 2) && K > 0 && ld >= K &&
+                    (!counts_out || counts_in),
+                DINOX_E_BADARG, "segment_cols_sum: bad arguments");
+  int rc = require_sm100();
+  if (rc) return rc;
+  SumSegs sg{};
+  for (int i = 0; i < nseg; ++i) {
+    DINOX_REQUIRE(seg_begin[i] >= 0 && seg_end[i] >= seg_begin[i], DINOX_E_BADARG, "segment_cols_sum: bad segment");
+    sg.begin[i] = seg_begin[i];
+    sg.end[i] = seg_end[i];
+  }
+  const int64_t chunks = dinox_segment_cols_sum_chunks(sg.end[0] - sg.begin[0], nseg > 1 ? sg.end[1] - sg.begin[1] : 0);
+  DINOX_REQUIRE(chunks <= 65535, DINOX_E_BADARG, "segment_cols_sum: too many rows");
+  const size_t tk = ((size_t)(2 * ((K + 127) / 128)) * sizeof(unsigned) + 255) / 256 * 256;
+  unsigned* tickets = reinterpret_cast<unsigned*>(workspace);
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + tk);
+  const bool vec = vec_ok(x, dtype, K, ld);
+  const dim3 grid((unsigned)((K + 127) / 128), (unsigned)chunks, (unsigned)nseg);
+  DISPATCH_T(dtype, T, {
+    if (vec) segment_cols_sum_kernel<T, true><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, K, ld, sg, out, counts_in, counts_out, scratch, tickets);
+    else segment_cols_sum_kernel<T, false><<<grid, 32 * kColSumGroups, 0, stream>>>((const T*)x, K, ld, sg, out, counts_in, counts_out, scratch, tickets);
+  });
+  return check_launch("segment_cols_sum_kernel", stream);
 }
 
 int dinox_cols_sum_axpy(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, float scale, const float* scale_dev,

@@ -346,6 +346,28 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const vo
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// ---- cross-CTA ordering of output accumulation (ordered split, gemm_core.cuh): release / acquire on a global flag
+__device__ __forceinline__ void flag_release(uint32_t* flag, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t flag_acquire(const uint32_t* flag) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  return v;
+}
+// bounded like the mbarrier waits: a protocol bug is a trap, not a hung box
+__device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t want) {
+  const uint64_t t0 = globaltimer_ns();
+  while (flag_acquire(flag) != want) {
+    __nanosleep(64);
+    if (globaltimer_ns() - t0 > 4000000000ull) {
+      printf("dinox: flag wait timed out (block %d, want %u)\n", (int)blockIdx.x, want);
+      __trap();
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");   // the reduce-adds that follow go through the async proxy
+}
+
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's committed bulk groups still READ their smem source
 template <int N>

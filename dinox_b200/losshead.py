@@ -634,6 +634,7 @@ class _EntryPlan:
         etp = [(r if r < Mt else r - Mt + self.Mt_pad) if r >= 0 else -1 for r in et]
         self.ent_t_pad = t(etp, torch.int64)                           # -1 = padding entry
         self.trow = t([max(r, 0) for r in etp], torch.int32)           # row of qt / refs (padding -> row 0, weight 0)
+        self.srow = t(es, torch.int32)                                 # student row of the entry (-1 = padding)
         self.cls_rows_pad = t(list(range(Mt)) + [-1] * (self.Mt_pad - Mt), torch.int64)
         self.row_counts = t([float(Mt), float(Mm), 0.0, 0.0], torch.float32)   # teacher CLS rows, masked patch rows
 
@@ -759,9 +760,11 @@ class _FusedHeadLoss(torch.autograd.Function):
         # ---- teacher: stage inputs [CLS rows | (zero rows) | masked patch rows] as bf16, layer 1, statistics
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             xt = torch.empty(Mt_pad + Mm, D, dtype=torch.bfloat16, device=dev)
-            ops.gather_cast_bf16(teacher_cls.detach(), plan.cls_rows_pad if Mt_pad != Mt else None, xt[:Mt_pad])
-            if Mm:
-                ops.gather_cast_bf16(tp2, teacher_index, xt[Mt_pad:])
+            cls_idx = plan.cls_rows_pad if Mt_pad != Mt else None
+            if Mm:   # [CLS rows | zero rows | masked patch rows] staged by one launch
+                ops.gather_cast_bf16_2(teacher_cls.detach(), cls_idx, Mt_pad, tp2, teacher_index, xt)
+            else:
+                ops.gather_cast_bf16(teacher_cls.detach(), cls_idx, xt)
             a_t = ops.gemm_bf16(xt, w1t, bias_n=t_head[0].bias.detach())   # layer 1 (zoo/arch.py:253-254)
             ht = ops.gelu_fwd(a_t)
             del a_t
@@ -775,12 +778,10 @@ class _FusedHeadLoss(torch.autograd.Function):
                 # exact when ranks hold different numbers of rows (masked tokens)
                 sbuf = torch.empty(nv * D + 4, dtype=torch.float32, device=dev)
                 hsum, counts = sbuf[:nv * D].view(nv, D), sbuf[nv * D:nv * D + nv]
-                if centre_cls:
-                    ops.cols_sum(ht[:Mt], out=hsum[0])
-                if centre_patch:
-                    ops.cols_sum(ht[Mt_pad:], out=hsum[int(centre_cls)])
                 i0 = 0 if centre_cls else 1
-                ops.axpb(plan.row_counts[i0:i0 + nv], 1.0, 0.0, out=counts)
+                segs = ([(0, Mt)] if centre_cls else []) + ([(Mt_pad, Mt_pad + Mm)] if centre_patch else [])
+                # activation sums of both row ranges and their row counts in one launch
+                ops.segment_cols_sum(ht, segs, hsum, plan.row_counts[i0:i0 + nv], counts)
                 # DINOX_CENTER_AR=late issues the all-reduce only where its result is needed (after pass 2) instead of
                 # here, next to the teacher pass (A/B knob: does the NCCL kernel disturb the persistent GEMMs?)
                 if os.environ.get("DINOX_CENTER_AR", "early") == "late":
@@ -831,8 +832,10 @@ class _FusedHeadLoss(torch.autograd.Function):
                 ops.axpb(b_row, LOG2E, out=rb2_t[:Mt])
             if b_row_patch is not None:
                 ops.axpb(b_row_patch, LOG2E, out=rb2_t[Mt_pad:])
-            # padding entries: a huge offset makes their probabilities exactly 0 (0 * inf would poison the sums)
-            rb2_e = ops.gather_f32(rb2_t, plan.ent_t_pad if readback else plan.ent_t, fill=1.0e30)
+            # read-back pass 2 looks the row statistics up itself (entry -> row tables of the plan; entries of weight 0
+            # are dead).  Round-1 pass 2 takes them per entry: a huge offset makes the padding entries'
+            # probabilities exactly 0 (0 * inf would poison the sums)
+            rb2_e = rb2_t if readback else ops.gather_f32(rb2_t, plan.ent_t, fill=1.0e30)
             if side is not None and concurrency() >= 3:
                 # centre updates here instead of after pass 2: ct2 / ct2_patch above already hold the OLD centres
                 # (scripts/phase5_big_run.py:719 - the loss sees the centre of the previous step), and the GEMV over
@@ -841,9 +844,10 @@ class _FusedHeadLoss(torch.autograd.Function):
                 stats = None
         # ---- student: the same on the current stream
         xs = torch.empty(Ms + Mm, D, dtype=torch.bfloat16, device=dev)
-        ops.gather_cast_bf16(student_cls.detach(), None, xs[:Ms])
         if Mm:
-            ops.gather_cast_bf16(sp2, patch_index, xs[Ms:])
+            ops.gather_cast_bf16_2(student_cls.detach(), None, Ms, sp2, patch_index, xs)
+        else:
+            ops.gather_cast_bf16(student_cls.detach(), None, xs)
         a_s = ops.gemm_bf16(xs, w1s, bias_n=b1.detach())
         hs = ops.gelu_fwd(a_s)
         b2s = b2.detach()
@@ -853,7 +857,7 @@ class _FusedHeadLoss(torch.autograd.Function):
         # ---- entries
         hs_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
         ops.gather_cast_bf16(hs, plan.ent_s, hs_e)
-        lse2_e = ops.gather_f32(lse2_s, plan.ent_s, fill=1.0e30)
+        lse2_e = lse2_s if readback else ops.gather_f32(lse2_s, plan.ent_s, fill=1.0e30)
         if side is not None:
             # Everything the teacher branch allocated lives in the side stream's pool and is read by pass 2 on
             # this stream: those blocks are only handed out again to side-stream work, and every side-stream
@@ -872,7 +876,7 @@ class _FusedHeadLoss(torch.autograd.Function):
         with ops.TIMER.region("head_grad"):
             if readback:
                 gt, db2p = ops.head_grad2(hs_e, w2s, inv_ts, cs2, lse2_e, cw, rb2_e, plan.trow, qt, refs, plan.e_cls_pad,
-                                          losses, want_db2=need_grad)
+                                          losses, want_db2=need_grad, srow_e=plan.srow)
             else:
                 gt, db2p = ops.head_grad(w2s, w2t, hs_e, ht_e, inv_ts, inv_tt, cs2, ct2, ct2_patch, plan.e_cls_pad,
                                          lse2_e, rb2_e, cw, losses, want_db2=need_grad)
@@ -892,10 +896,13 @@ class _FusedHeadLoss(torch.autograd.Function):
             total = ops.scalar_combine([lbuf[0], lbuf[1]], [1.0, 1.0])
         losses = lbuf[:2]
         ctx.mark_non_differentiable(losses)
+        ctx.set_materialize_grads(False)     # no zero-filled gradient for the (non-differentiable) loss pair
         return total, losses
 
     @staticmethod
     def backward(ctx, g, _g_losses):
+        if g is None:
+            return (None,) * 16
         xs, a_s, hs_e, gt, db2p, w1s, w2s = ctx.saved_tensors
         plan = ctx.plan
         w1, b1, w2, b2 = ctx.params
@@ -923,6 +930,11 @@ class _FusedHeadLoss(torch.autograd.Function):
         if side is not None:
             side.wait_stream(main)
         rb = ctx.readback   # G is (E, K) entry-major on the read-back path, Gt (K, E) prototype-major otherwise
+        # DINOX_BALANCED (bit mask, default 0): 1 = dW2, 2 = dH on the balanced schedule (dinox_gemm_bf16_balanced).
+        # Measured at C2: dW2 alone 0.335 -> 0.318 ms, dH 0.296 -> 0.308 ms, but the micro-step does not get shorter
+        # (2.322 vs 2.337 ms, 3 interleaved runs each): inside the step the idle SMs of dW2's last wave are already
+        # taken by the side-stream kernels (centre GEMV, Gram backward) - profiles/README.md.
+        balanced = int(os.environ.get("DINOX_BALANCED", "0"))
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             # dW2 (K, D) += g * G^T . HsE   (A = G with the prototypes as M; B = HsE MN-major)
             with ops.TIMER.region("gemm_dW2"):
@@ -938,16 +950,23 @@ class _FusedHeadLoss(torch.autograd.Function):
                                                  add_scale=1.0 / sink.world)
                     if local is not None:
                         w2.grad = None    # shipped: the owner's shard holds it now
+                elif balanced & 1:
+                    # 256 tile pairs on 74 CTA pairs: the 34 tiles of the last wave are cut in two along the entries
+                    emit("w2", w2, lambda out, acc: ops.gemm_bf16_balanced(
+                        gt, hs_e, tag="dW2", a_mn_major=rb, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up,
+                        m_fastest=False))
                 else:
                     emit("w2", w2, lambda out, acc: ops.gemm_bf16(
                         gt, hs_e, a_mn_major=rb, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
             emit("b2", b2, lambda out, acc: ops.cols_sum_axpy_(db2p, out, acc, scale_dev=up))
         # dH per entry = G . W2  (B = W2 MN-major), then sum the entries of each row
         with ops.TIMER.region("gemm_dH"):
-            dh_e = ops.gemm_bf16_splitk(gt, w2s, a_mn_major=not rb, b_mn_major=True, m_fastest=True)
-        dh = torch.empty(rows, D, dtype=torch.float32, device=dev)
-        ops.gather_sum_rows(dh_e, plan.csr_ptr, plan.csr_ent, rows, dh)
-        da, part = ops.gelu_bwd(dh, a_s, scale_dev=up)
+            if balanced & 2:   # fewer tiles than CTA pairs: every tile cut along the prototypes, accumulated in place
+                dh_e = ops.gemm_bf16_balanced(gt, w2s, tag="dH", a_mn_major=not rb, b_mn_major=True, m_fastest=True)
+            else:
+                dh_e = ops.gemm_bf16_splitk(gt, w2s, a_mn_major=not rb, b_mn_major=True, m_fastest=True)
+        # dL/dh of a row = sum of its entries' rows (and of the split-K slabs), formed inside the GELU backward
+        da, part = ops.gelu_bwd_gather(dh_e, plan.csr_ptr, plan.csr_ent, a_s, scale_dev=up)
         emit("b1", b1, lambda out, acc: ops.cols_sum_axpy_(part, out, acc))
         # dW1 = da^T x: 3x3 output tiles with a reduction over every row -> split-K, slabs summed in fixed order
         dw1_parts = ops.gemm_bf16_splitk(da, xs, a_mn_major=True, b_mn_major=True)
@@ -1050,12 +1069,15 @@ class _TokenFork(torch.autograd.Function):
         ops.gather_rows_f32(flat, index, rows)
         ctx.save_for_backward(index)
         ctx.shape, ctx.dtype = tuple(tokens.shape), tokens.dtype
+        ctx.set_materialize_grads(False)
         return tokens.view_as(tokens), rows
 
     @staticmethod
     def backward(ctx, g_tokens, g_rows):
         (index,) = ctx.saved_tensors
         D = ctx.shape[-1]
+        if g_tokens is None and g_rows is None:
+            return None, None
         if g_tokens is None:
             g_tokens = torch.empty(ctx.shape, dtype=torch.float32, device=index.device)
             ops.fill_(g_tokens.view(-1), 0.0)
@@ -1117,10 +1139,13 @@ class _CombineLosses(torch.autograd.Function):
         total = torch.empty((), dtype=torch.float32, device=ts[0].device)
         scaled = ops.scalar_combine(ts, ctx.weights, ctx.scale, out_unscaled=total)
         ctx.mark_non_differentiable(total)
+        ctx.set_materialize_grads(False)
         return scaled, total
 
     @staticmethod
     def backward(ctx, g, _g_total):
+        if g is None:
+            return (None, None) + (None,) * len(ctx.weights)
         fan = ops.scalar_fanout(g.reshape(1), ctx.weights, ctx.scale)
         return (None, None) + tuple(fan[i] for i in range(len(ctx.weights)))
 

@@ -7,7 +7,7 @@ through ATen - if the library is missing or the device is not a B200 the call ra
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Sequence
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -209,6 +209,31 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_m
     return out
 
 
+def gemm_bf16_balanced(a: torch.Tensor, b: torch.Tensor, *, tag: str, a_mn_major: bool = False, b_mn_major: bool = False,
+                       out: Optional[torch.Tensor] = None, accumulate: bool = False, alpha: float = 1.0,
+                       alpha_dev: Optional[torch.Tensor] = None, bias_n: Optional[torch.Tensor] = None,
+                       m_fastest: bool = True) -> torch.Tensor:
+    """gemm_bf16 with fp32 output and the balanced schedule (tiles of a partial wave cut along K, parts accumulated
+    in a fixed order).  `tag` names the call site: its ordering counters live in a persistent zeroed workspace."""
+    _chk_cuda(a, b, out, bias_n, alpha_dev)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise _ext.DinoxError("gemm_bf16_balanced needs bf16 operands")
+    M, Ka = (a.shape[1], a.shape[0]) if a_mn_major else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn_major else b.shape
+    if Ka != Kb:
+        raise _ext.DinoxError(f"gemm_bf16_balanced: reduction dims differ ({Ka} vs {Kb})")
+    if out is None:
+        if accumulate:
+            raise _ext.DinoxError("accumulate=True needs an output tensor")
+        out = torch.empty(M, (N + 3) // 4 * 4, dtype=torch.float32, device=a.device)[:, :N]
+    assert out.dtype == torch.float32
+    flags = zeroed_workspace("gemm_balanced:" + tag, int(_ext.lib().dinox_gemm_bf16_balanced_workspace_bytes(M, N)), a.device)
+    _ext.call("dinox_gemm_bf16_balanced", _p(a), _p(b), _p(out), M, N, Ka, _rowmajor(a), _rowmajor(b), _rowmajor(out),
+              int(a_mn_major), int(b_mn_major), int(accumulate), float(alpha), _p(alpha_dev), _p(bias_n), int(m_fastest),
+              _p(flags), _stream())
+    return out
+
+
 def gemm_bf16_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shard_ptrs: Sequence[int], rows_per_owner: int, ldc: int,
                              *, a_mn_major: bool = False, b_mn_major: bool = False, alpha: float = 1.0,
                              alpha_dev: Optional[torch.Tensor] = None, add_local: Optional[torch.Tensor] = None,
@@ -327,13 +352,35 @@ def head_teacher(h: torch.Tensor, w2: torch.Tensor, inv_tau: float, col2: Option
     return qt, refs, l2
 
 
+_ZEROED: dict = {}
+
+
+def zeroed_workspace(tag: str, nbytes: int, device) -> torch.Tensor:
+    """Persistent uint8 workspace for the kernels that keep a ticket counter in it (zero before the first launch, left
+    zero by every launch).  One per (tag, size, device): launches of one tag must be stream-ordered (they are - each
+    tag belongs to one call site of the step); concurrent users pass their own tag."""
+    dev = torch.device(device)
+    key = (tag, int(nbytes), dev.index if dev.index is not None else torch.cuda.current_device())
+    t = _ZEROED.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            # allocated from the capturing graph's pool the block would be recycled between replays: make it once, eagerly
+            raise _ext.DinoxError(f"workspace {tag!r} must exist before graph capture (run one eager warm-up step first)")
+        t = _ZEROED[key] = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)
+    return t
+
+
 def head_grad2(hs_e: torch.Tensor, w2s: torch.Tensor, inv_tau_s: float, cs2: torch.Tensor, lse2_e: torch.Tensor,
                cw_e: torch.Tensor, rb2_e: torch.Tensor, trow_e: torch.Tensor, qt: torch.Tensor, refs: torch.Tensor,
                alt_from: int, loss_out: torch.Tensor, loss_accumulate: bool = False, want_db2: bool = True,
-               g: Optional[torch.Tensor] = None):
+               g: Optional[torch.Tensor] = None, srow_e: Optional[torch.Tensor] = None, fused_loss_sum: bool = True):
     """Pass 2 (student logits recomputed, teacher probabilities read back).  loss_out: 3 fp32 ([0] entries <
-    alt_from, [1] the rest, [2] their sum).  Returns (G (E, K) bf16 = dL/dlogits per entry, db2_partial or None)."""
+    alt_from, [1] the rest, [2] their sum).  Returns (G (E, K) bf16 = dL/dlogits per entry, db2_partial or None).
+    srow_e (int32 student row per entry, -1 = padding): lse2_e is then the per-ROW student LSE and rb2_e the per-ROW
+    teacher offset (indexed through srow_e / trow_e inside the kernel).  fused_loss_sum: the kernel adds up its own
+    loss partials (ticket counter) instead of a follow-up launch."""
     assert loss_out.numel() >= 3 and trow_e.dtype == torch.int32 and qt.dtype == torch.float16
+    assert srow_e is None or (srow_e.dtype == torch.int32 and srow_e.numel() == trow_e.numel())
     _chk_cuda(hs_e, w2s, qt, refs)
     E, D = hs_e.shape
     K = w2s.shape[0]
@@ -342,9 +389,10 @@ def head_grad2(hs_e: torch.Tensor, w2s: torch.Tensor, inv_tau_s: float, cs2: tor
     db2p = (torch.empty(int(_ext.lib().dinox_head_grad2_db2_rows(E)), K, dtype=torch.float32, device=w2s.device)
             if want_db2 else None)
     ws = torch.empty(int(_ext.lib().dinox_head_grad2_workspace_bytes(E, K)), dtype=torch.uint8, device=w2s.device)
+    ticket = zeroed_workspace("head_grad2", 256, w2s.device) if fused_loss_sum else None
     _ext.call("dinox_head_grad2", _p(hs_e), _p(w2s), E, K, D, _rowmajor(hs_e), _rowmajor(w2s), float(inv_tau_s), _p(cs2),
-              _p(lse2_e), _p(cw_e), _p(rb2_e), _p(trow_e), _p(qt), qt.stride(0), _p(refs), refs.stride(0), int(alt_from),
-              _p(g), _rowmajor(g), _p(db2p), _p(loss_out), int(loss_accumulate), _p(ws), _stream())
+              _p(lse2_e), _p(cw_e), _p(rb2_e), _p(trow_e), _p(srow_e), _p(qt), qt.stride(0), _p(refs), refs.stride(0),
+              int(alt_from), _p(g), _rowmajor(g), _p(db2p), _p(loss_out), int(loss_accumulate), _p(ws), _p(ticket), _stream())
     return g, db2p
 
 
@@ -413,6 +461,45 @@ def gather_cast_bf16(src: torch.Tensor, idx: Optional[torch.Tensor], out: torch.
     return out
 
 
+def gather_cast_bf16_2(src0: torch.Tensor, idx0: Optional[torch.Tensor], rows0: int, src1: torch.Tensor,
+                       idx1: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """out[:rows0] = bf16(src0[idx0]), out[rows0:] = bf16(src1[idx1]) in one launch when both sources are 16-byte
+    vector rows of one dtype; two launches otherwise.  idx None: identity; idx < 0: zero row."""
+    _chk_cuda(src0, src1, out)
+    rows1 = out.shape[0] - rows0
+    D = out.shape[1]
+    es = src0.element_size()
+    fits = (src0.dtype == src1.dtype and D % 8 == 0 and src0.stride(1) == 1 and src1.stride(1) == 1 and out.stride(1) == 1
+            and all(t.data_ptr() % 16 == 0 for t in (src0, src1, out))
+            and (src0.stride(0) * es) % 16 == 0 and (src1.stride(0) * es) % 16 == 0 and (out.stride(0) * 2) % 16 == 0)
+    if not fits or rows0 == 0 or rows1 == 0:
+        if rows0:
+            gather_cast_bf16(src0, idx0, out[:rows0])
+        if rows1:
+            gather_cast_bf16(src1, idx1, out[rows0:])
+        return out
+    _ext.call("dinox_gather_cast_bf16_2", _p(src0), src0.stride(0), _p(idx0), rows0, _p(src1), src1.stride(0), _p(idx1),
+              rows1, DT[src0.dtype], D, _p(out), out.stride(0), _stream())
+    return out
+
+
+def segment_cols_sum(x: torch.Tensor, segments: Sequence[Tuple[int, int]], out: torch.Tensor,
+                     counts_in: Optional[torch.Tensor] = None, counts_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = x[b_i:e_i].sum(0) for one or two row ranges in ONE launch (fixed summation order); counts_out[i] =
+    counts_in[i] rides along.  The payload of the centre statistics all-reduce."""
+    _chk_cuda(x, out)
+    n = len(segments)
+    assert n in (1, 2) and x.dim() == 2 and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n * x.shape[1]
+    K, ld = x.shape[1], _rowmajor(x)
+    r = [e - b for b, e in segments] + [0]
+    ws = zeroed_workspace("segment_cols_sum", int(_ext.lib().dinox_segment_cols_sum_workspace_bytes(r[0], r[1], K)), x.device)
+    begin = (ctypes.c_int64 * n)(*[int(b) for b, _ in segments])
+    end = (ctypes.c_int64 * n)(*[int(e) for _, e in segments])
+    _ext.call("dinox_segment_cols_sum", _p(x), DT[x.dtype], K, ld, n, begin, end, _p(out), _p(counts_in), _p(counts_out),
+              _p(ws), _stream())
+    return out
+
+
 def gather_f32(src: torch.Tensor, idx: torch.Tensor, fill: float = 0.0) -> torch.Tensor:
     out = torch.empty(idx.numel(), dtype=torch.float32, device=src.device)
     _ext.call("dinox_gather_f32", _p(src), _p(idx), idx.numel(), float(fill), _p(out), _stream())
@@ -460,6 +547,24 @@ def gelu_bwd(dh: torch.Tensor, a: torch.Tensor, scale_dev: Optional[torch.Tensor
     n_part = int(_ext.lib().dinox_gelu_bwd_workspace_bytes(rows, D)) // (4 * D)
     part = torch.empty(n_part, D, dtype=torch.float32, device=a.device)
     _ext.call("dinox_gelu_bwd", _p(dh), _p(a), rows, D, _p(scale_dev), _p(da), _p(part), _stream())
+    return da, part
+
+
+def gelu_bwd_gather(src: torch.Tensor, ptr: torch.Tensor, ent: torch.Tensor, a: torch.Tensor,
+                    scale_dev: Optional[torch.Tensor] = None):
+    """gelu_bwd on dh[r] = sum of the rows ent[ptr[r]:ptr[r+1]] of src ((E, D) fp32 or (S, E, D) split-K slabs, summed
+    too) without materialising dh: gather_sum_rows + gelu_bwd in one launch, same summation order."""
+    rows, D = a.shape
+    if src.dim() == 3:
+        slabs, slab_stride, ld = src.shape[0], src.stride(0), src.stride(1)
+        assert src.stride(2) == 1
+    else:
+        slabs, slab_stride, ld = 1, 0, _rowmajor(src)
+    da = torch.empty(rows, D, dtype=torch.bfloat16, device=a.device)
+    n_part = int(_ext.lib().dinox_gelu_bwd_workspace_bytes(rows, D)) // (4 * D)
+    part = torch.empty(n_part, D, dtype=torch.float32, device=a.device)
+    _ext.call("dinox_gelu_bwd_gather", _p(src), ld, slabs, slab_stride, _p(ptr), _p(ent), _p(a), rows, D, _p(scale_dev),
+              _p(da), _p(part), _stream())
     return da, part
 
 

@@ -41,6 +41,7 @@ class LossHeadStep:
                                            teacher_mode=teacher_mode, process_group=process_group,
                                            patch_teacher_mode=patch_teacher_mode).to(device)
         self.center_patch = torch.zeros(1, K, device=device)
+        self._unit = torch.ones((), dtype=torch.float32, device=device)
         # every other student/teacher parameter (backbone, scale-embed): random stand-ins with the
         # reference's shapes so that the EMA walks the real 161 / 305 tensor list
         self.student_params: List[torch.Tensor] = []
@@ -145,7 +146,7 @@ class LossHeadStep:
 
     def _fwd_bwd(self, f):
         out, loss = self._losses(f)
-        loss.backward()
+        loss.backward(self._unit)      # a resident 1.0: no ones_like fill per step
         return out
 
     def _losses(self, f):

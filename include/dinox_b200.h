@@ -85,6 +85,18 @@ DINOX_API int dinox_cols_sum(const void* x, int dtype, int64_t rows, int64_t K, 
                              float* out, dinox_stream_t stream);
 /* out[k] (+)= scale*(*scale_dev) * column sum (accumulate != 0: +=): the bias gradients db1 / db2 summed from their
  * partial rows straight into `.grad` (autograd's Linear backward `grad_output.sum(0)`, zoo/arch.py:252-256) */
+/* column sums of one or two row ranges [seg_begin[i], seg_end[i]) of x in ONE launch -> out (nseg, K); optionally
+ * counts_out[i] = counts_in[i] rides along (the [activation sums | row counts] all-reduce payload of the centre
+ * update, scripts/phase5_big_run.py:686-690).  64-row chunk sums are combined in chunk order by the block that
+ * finishes last (ticket counter), so the result is run-to-run identical.  `workspace`
+ * (dinox_segment_cols_sum_workspace_bytes) must be ZERO before its first use; every launch leaves its ticket area
+ * zero again.  Not to be shared by launches that may run concurrently. */
+DINOX_API int64_t dinox_segment_cols_sum_chunks(int64_t rows0, int64_t rows1);
+DINOX_API size_t dinox_segment_cols_sum_workspace_bytes(int64_t rows0, int64_t rows1, int64_t K);
+DINOX_API int dinox_segment_cols_sum(const void* x, int dtype, int64_t K, int64_t ld, int nseg,
+                                     const int64_t* seg_begin, const int64_t* seg_end, float* out,
+                                     const float* counts_in, float* counts_out, void* workspace,
+                                     dinox_stream_t stream);
 DINOX_API int dinox_cols_sum_axpy(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld, float scale,
                                   const float* scale_dev, float* out, int accumulate, dinox_stream_t stream);
 /* partial[c, :] = column sums of rows [c*chunk, min((c+1)*chunk, rows)): first phase of a tall-skinny
@@ -141,6 +153,18 @@ DINOX_API int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, 
                               int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major,
                               int out_dtype, int accumulate, float alpha, const float* alpha_dev,
                               const float* bias_n, int m_fastest, dinox_stream_t stream);
+
+/* The same (fp32 output) with a balanced schedule: when the tile count does not fill whole waves of the persistent
+ * grid (dW2: 256 tile pairs on 74 CTA pairs = 3.46 waves; dH: 32 on 74), the tiles of the partial wave - or all
+ * tiles when there are fewer tiles than clusters - are cut along K into parts that other clusters compute at the same
+ * time.  The parts of a tile accumulate into C in a FIXED order (part j waits for part j-1 through the counters in
+ * `flags`), so the result is run-to-run identical.  `flags` (dinox_gemm_bf16_balanced_workspace_bytes): zero before
+ * the first launch, left zero by every launch; not to be shared by launches that may overlap. */
+DINOX_API size_t dinox_gemm_bf16_balanced_workspace_bytes(int64_t M, int64_t N);
+DINOX_API int dinox_gemm_bf16_balanced(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K,
+                                       int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major,
+                                       int accumulate, float alpha, const float* alpha_dev, const float* bias_n,
+                                       int m_fastest, void* flags, dinox_stream_t stream);
 
 /* Split-K flavour for GEMMs with few output tiles and a long reduction (dH = G . W2: 67 tiles,
  * K = 65536): split s reduces its share of K into the fp32 slab C_partials + s*split_stride;
@@ -237,6 +261,10 @@ DINOX_API int dinox_head_teacher(const void* H, const void* W2, int64_t rows, in
  *   db2_partial[dinox_head_grad2_db2_rows(E), K]  column sums of G per 32 entries (reduce with dinox_cols_sum)
  * with softmax_s = 2^(S*inv_tau_s*log2e + cs2[k] - lse2_e[e]) and
  *      q_t       = qt[trow_e[e],k] * 2^(refs[g(k)][trow_e[e]] - rb2_e[e]).
+ * srow_e != NULL: the row statistics are NOT gathered per entry - lse2_e is indexed by the entry's student row
+ * srow_e[e] (-1 = padding entry) and rb2_e by its teacher row trow_e[e]; entries with cw_e[e] == 0 are dead.
+ * ticket != NULL (one uint32, zero before the first launch, left zero by every launch): the kernel itself adds up
+ * the per-warp loss partials in a fixed order (the warp that finishes last does it) instead of a follow-up launch.
  * Cross-entropy of scripts/phase5_big_run.py:706-717 and its autograd in one kernel.
  * ------------------------------------------------------------------------------------------ */
 DINOX_API size_t dinox_head_grad2_workspace_bytes(int64_t E, int64_t K);
@@ -244,10 +272,10 @@ DINOX_API int64_t dinox_head_grad2_db2_rows(int64_t E);
 DINOX_API int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int64_t D,
                                int64_t ldh, int64_t ldw, float inv_tau_s, const float* cs2,
                                const float* lse2_e, const float* cw_e, const float* rb2_e,
-                               const int32_t* trow_e, const void* qt, int64_t ldq, const float* refs,
-                               int64_t ld_refs, int64_t alt_from, void* G, int64_t ldg,
+                               const int32_t* trow_e, const int32_t* srow_e, const void* qt, int64_t ldq,
+                               const float* refs, int64_t ld_refs, int64_t alt_from, void* G, int64_t ldg,
                                float* db2_partial, float* loss_out, int loss_accumulate,
-                               void* workspace, dinox_stream_t stream);
+                               void* workspace, uint32_t* ticket, dinox_stream_t stream);
 
 /* batched variant: `batches` independent problems, element strides between problems.  Used for the
  * per-image Gram backward  dXn[b] = alpha * Delta[b] @ Xn[b]  (autograd of torch.bmm,
@@ -288,6 +316,12 @@ DINOX_API int dinox_gram_diff(const void* xn_s, const void* xn_t, int64_t batche
 DINOX_API int dinox_gather_cast_bf16(const void* src, int src_dtype, int64_t ld_src, const int64_t* idx,
                                      int64_t rows, int64_t D, void* dst, int64_t ld_dst,
                                      dinox_stream_t stream);
+/* two sources into one destination in one launch: dst rows [0, rows0) from (src0, idx0), rows [rows0, rows0 + rows1)
+ * from (src1, idx1) - the [CLS rows | masked-patch rows] staging of one branch (:1746-1747).  Rows must be 16-byte
+ * vectors (D % 8 == 0, aligned pitches); both sources share src_dtype. */
+DINOX_API int dinox_gather_cast_bf16_2(const void* src0, int64_t ld_src0, const int64_t* idx0, int64_t rows0,
+                                       const void* src1, int64_t ld_src1, const int64_t* idx1, int64_t rows1,
+                                       int src_dtype, int64_t D, void* dst, int64_t ld_dst, dinox_stream_t stream);
 DINOX_API int dinox_gather_f32(const float* src, const int64_t* idx, int64_t n, float fill, float* out,
                                dinox_stream_t stream);
 /* dst[idx[r], :] = src[r, :] for r < rows (fp32, D % 4 == 0, unique idx, idx < 0 skipped): the backward of
@@ -300,6 +334,13 @@ DINOX_API int dinox_gelu_fwd(const float* a, int64_t n, void* h_bf16, dinox_stre
 DINOX_API size_t dinox_gelu_bwd_workspace_bytes(int64_t rows, int64_t D);
 DINOX_API int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int64_t D, const float* scale_dev,
                              void* da_bf16, float* colsum_partial, dinox_stream_t stream);
+/* the same with dh[r,:] = sum over the row's entries i in [ptr[r], ptr[r+1]) and the split-K slabs s of
+ * src[s*slab_stride + ent[i]*ld_src, :] formed on the fly (dinox_gather_sum_rows + dinox_gelu_bwd in one launch,
+ * identical summation order) */
+DINOX_API int dinox_gelu_bwd_gather(const float* src, int64_t ld_src, int slabs, int64_t slab_stride,
+                                    const int64_t* ptr, const int64_t* ent, const float* a, int64_t rows, int64_t D,
+                                    const float* scale_dev, void* da_bf16, float* colsum_partial,
+                                    dinox_stream_t stream);
 /* out[k] = alpha * sum_d W[k,d] x[d] + beta * bias[k]   (W bf16 (K,D), x fp32): batch-mean teacher
  * logits from the mean head activation, used for the centre update of the fused path (:686-690) */
 DINOX_API int dinox_gemv_bf16(const void* W, int64_t ldw, const float* x, int64_t K, int64_t D, float alpha,

@@ -1,0 +1,239 @@
+"""GPU tests of the merged launches of the micro-step (round 2 launch diet) through the C ABI.
+
+Each merged kernel is compared with the launches it replaces.  Where the summation order is the same by
+construction (two-segment staging, GELU backward over gathered entry rows, row statistics looked up by pass 2
+itself) the results must be BIT-identical; where it differs (64-row chunk sums combined by the last block, loss
+partials added by the last warp) they agree to fp32 rounding and are identical from launch to launch.
+The last test pins the launch count of the captured micro-step."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dinox_b200 import ops, _ext
+    assert _ext.lib().dinox_device_check() == 0, "needs a B200"
+    return ops
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows0,rows1,D", [(80, 928, 384), (128, 7552, 384), (16, 33, 1024), (5, 0, 384), (0, 7, 384),
+                                            (24, 40, 100)])
+def test_two_segment_staging_equals_two_launches(ops, dtype, rows0, rows1, D):
+    g = torch.Generator().manual_seed(3)
+    cls = torch.randn(max(rows0, 1) + 3, D, generator=g).to(dtype).to(DEV)
+    tok = torch.randn(4 * max(rows1, 1) + 9, D, generator=g).to(dtype).to(DEV)        # the token tensor the rows are named in
+    idx0 = torch.randperm(cls.shape[0], generator=g)[:rows0].to(DEV)
+    if rows0 > 2:
+        idx0[1] = -1                                                                  # a padding row -> zeros
+    idx1 = torch.randperm(tok.shape[0], generator=g)[:rows1].to(DEV)
+    for i0 in (idx0, None):
+        n0 = rows0 if i0 is not None else min(rows0, cls.shape[0])
+        a = torch.full((n0 + rows1, D), 7.0, dtype=torch.bfloat16, device=DEV)
+        b = a.clone()
+        ops.gather_cast_bf16_2(cls, i0, n0, tok, idx1, a)
+        if n0:
+            ops.gather_cast_bf16(cls, i0, b[:n0])
+        if rows1:
+            ops.gather_cast_bf16(tok, idx1, b[n0:])
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+        if i0 is not None and rows0 > 2:
+            assert (a[1] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("segs,K", [([(0, 128), (128, 7680)], 384), ([(0, 16), (128, 1056)], 384), ([(3, 70)], 1000),
+                                     ([(0, 0), (5, 300)], 1024), ([(0, 130), (130, 131)], 100)])
+def test_segment_column_sums(ops, dtype, segs, K):
+    g = torch.Generator().manual_seed(4)
+    rows = max(e for _, e in segs) + 5
+    x = torch.randn(rows, K, generator=g).to(dtype).to(DEV)
+    n = len(segs)
+    counts_in = torch.tensor([float(e - b) for b, e in segs], device=DEV)
+    outs = []
+    for _ in range(3):                     # the ticket counters must be back at zero after every launch
+        out = torch.full((n, K), float("nan"), device=DEV)
+        counts = torch.full((n,), -1.0, device=DEV)
+        ops.segment_cols_sum(x, segs, out, counts_in, counts)
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(counts, counts_in)
+    for i, (b, e) in enumerate(segs):
+        ref = x[b:e].double().sum(0)
+        assert (outs[0][i].double() - ref).abs().max().item() <= 1e-5 * max(1.0, math.sqrt(e - b))
+        if e > b:
+            assert rel(outs[0][i], ops.cols_sum(x[b:e])) < 1e-6
+
+
+@pytest.mark.parametrize("rows,E,D,slabs", [(1008, 1216, 384, 2), (100, 64, 384, 1), (37, 200, 1024, 3)])
+def test_gelu_backward_over_gathered_entry_rows(ops, rows, E, D, slabs):
+    g = torch.Generator().manual_seed(5)
+    src = torch.randn(slabs, E, D, generator=g).to(DEV)
+    # CSR: every row owns 0..4 entries
+    n_per = torch.randint(0, 5, (rows,), generator=g)
+    ptr = torch.zeros(rows + 1, dtype=torch.int64)
+    ptr[1:] = n_per.cumsum(0)
+    ent = torch.randint(0, E, (int(ptr[-1]),), generator=g)
+    a = torch.randn(rows, D, generator=g).to(DEV)
+    up = torch.tensor([0.25], device=DEV)
+    ptr, ent = ptr.to(DEV), ent.to(DEV)
+    src_in = src if slabs > 1 else src[0]
+    dh = torch.empty(rows, D, device=DEV)
+    ops.gather_sum_rows(src_in, ptr, ent, rows, dh)
+    da0, part0 = ops.gelu_bwd(dh, a, scale_dev=up)
+    da1, part1 = ops.gelu_bwd_gather(src_in, ptr, ent, a, scale_dev=up)
+    torch.cuda.synchronize()
+    assert torch.equal(da0, da1) and torch.equal(part0, part1)
+    # and against torch: dh * gelu'(a)
+    a64 = a.double().requires_grad_(True)
+    torch.nn.functional.gelu(a64).backward(dh.double() * 0.25)
+    assert rel(da1, a64.grad) < 4e-3
+
+
+def test_pass2_row_statistics_by_index_and_fused_loss_sum(ops):
+    """head_grad2 with (srow, trow) lookups of per-ROW statistics == per-entry gathered statistics (bit-identical G and
+    db2); the loss added up by the last warp agrees with the follow-up pair_sum launch to fp32 rounding and is the
+    same on every launch."""
+    try:
+        from tests.test_gpu_readback import _grad2_case
+    except ImportError:
+        from test_gpu_readback import _grad2_case
+    E, K, D, Tr, Sr = 640, 8192, 384, 96, 300
+    hs_rows, ht, ws, wt, cs, ct, cw, trow = _grad2_case(Sr, K, D, Tr, 21)
+    g = torch.Generator().manual_seed(22)
+    srow = torch.randint(0, Sr, (E,), generator=g)
+    trow = torch.randint(0, Tr, (E,), generator=g)
+    cw = torch.rand(E, generator=g) / E
+    srow[-50:] = -1                      # padding entries
+    cw[-50:] = 0
+    d = lambda t: t.to(DEV)
+    inv_ts, inv_tt = 10.0, 25.0
+    qt, refs, rb2_t = ops.head_teacher(d(ht), d(wt), inv_tt, d(ct))
+    _, lse2_s = ops.head_stats(d(hs_rows), d(ws), inv_ts, d(cs), want_nat=False)
+    hs_e = torch.zeros(E, D, dtype=torch.bfloat16, device=DEV)
+    ops.gather_cast_bf16(d(hs_rows), d(srow), hs_e)
+    lse2_e = ops.gather_f32(lse2_s, d(srow), fill=1.0e30)
+    rb2_e = rb2_t[d(trow)].contiguous()
+    rb2_e[-50:] = 1.0e30
+    t32, s32 = d(trow).to(torch.int32), d(srow).to(torch.int32)
+    l0 = torch.empty(3, device=DEV)
+    G0, db0 = ops.head_grad2(hs_e, d(ws), inv_ts, d(cs), lse2_e, d(cw), rb2_e, t32, qt, refs, 256, l0, fused_loss_sum=False)
+    res = []
+    for _ in range(3):
+        l1 = torch.full((3,), float("nan"), device=DEV)
+        G1, db1 = ops.head_grad2(hs_e, d(ws), inv_ts, d(cs), lse2_s, d(cw), rb2_t, t32, qt, refs, 256, l1, srow_e=s32)
+        res.append((G1, db1, l1))
+    torch.cuda.synchronize()
+    for G1, db1, l1 in res:
+        assert torch.equal(G0, G1) and torch.equal(db0, db1)
+        assert torch.equal(l1, res[0][2])
+        assert l1[2].item() == (l1[0] + l1[1]).item()
+        assert torch.allclose(l1, l0, rtol=2e-6, atol=0)
+    assert (G0[-50:] == 0).all()
+    # accumulate mode of the fused sum
+    l2 = res[0][2].clone()
+    ops.head_grad2(hs_e, d(ws), inv_ts, d(cs), lse2_s, d(cw), rb2_t, t32, qt, refs, 256, l2, loss_accumulate=True, srow_e=s32)
+    torch.cuda.synchronize()
+    assert torch.allclose(l2[:2], 2 * res[0][2][:2], rtol=1e-6)
+
+
+def test_micro_step_launch_count():
+    """The captured micro-step (fused head + iBOT rows named by index + Gram anchoring, centre teacher) is <= 38
+    launches of this library and its forward/backward glue issues no framework fill kernels."""
+    from dinox_b200 import synth
+    from dinox_b200.step import LossHeadStep
+    shapes = synth.LossHeadShapes(**synth.CONFIGS["C1"])
+    step = LossHeadStep(shapes, DEV, accum=2, with_backbone_params=False)
+    g = synth.seeded_generator(1)
+    feats = synth.feature_batch(shapes, g, patches_from_tokens=True)
+    slot = step.static_inputs(feats, slots=1)[0]
+    with torch.no_grad():
+        for k, v in feats.items():
+            slot[k].copy_(v)
+    step.capture(0)
+    assert step.launches_per_graph <= 38, step.launches_per_graph
+    out = step.micro_step_graph(0)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v).all() for v in out.values())
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,acc,bias", [
+    (27648, 384, 4096, True, True, True, False),       # dW2-like: 108 tile pairs on 74 CTA pairs -> the last 34 cut in two
+    (27648, 384, 4096, True, True, False, False),     # ... into a fresh output: part 0 stores, part 1 reduce-adds
+    (8192, 384, 16384, False, True, False, False),    # dH-like: 32 tile pairs -> every tile cut along K, many parts
+    (8192, 384, 16384, False, True, False, True),     # a bias enters exactly once
+    (4000, 256, 4096, False, False, True, False),     # ragged M, 256-wide tiles
+    (18944, 384, 1024, False, False, False, False),   # 74 tile pairs: whole waves, nothing to cut (== plain GEMM)
+    (128, 384, 8192, False, True, False, False),      # a single M tile (no CTA pair): 1 tile on 148 CTAs
+])
+def test_balanced_gemm_ordered_split(ops, M, N, K, a_mn, b_mn, acc, bias):
+    """dinox_gemm_bf16_balanced: same result as the plain GEMM up to the fp32 summation split, against torch fp64 on
+    the same bf16 operands, and BIT-identical from launch to launch (the parts of a tile are accumulated in a fixed
+    order through the flag counters, which return to zero)."""
+    g = torch.Generator().manual_seed(7)
+    a = (torch.randn((K, M) if a_mn else (M, K), generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    b = (torch.randn((K, N) if b_mn else (N, K), generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    c0 = torch.randn(M, N, generator=g).to(DEV) if acc else None
+    bias_n = torch.randn(N, generator=g).to(DEV) if bias else None
+    up = torch.tensor([0.5], device=DEV)
+    tag = f"test{M}x{N}x{K}"
+
+    def run(fn, **kw):
+        out = c0.clone() if acc else torch.full((M, N), float("nan"), device=DEV)
+        fn(a, b, a_mn_major=a_mn, b_mn_major=b_mn, out=out, accumulate=acc, alpha=2.0, alpha_dev=up, bias_n=bias_n, **kw)
+        return out
+    plain = run(ops.gemm_bf16)
+    outs = [run(ops.gemm_bf16_balanced, tag=tag) for _ in range(3)]
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    A = (a.t() if a_mn else a).double()
+    B = (b.t() if b_mn else b).double()
+    ref = A @ B.t()
+    if bias:
+        ref = ref + bias_n.double()[None, :]
+    if acc:
+        ref = ref + c0.double()
+    assert torch.isfinite(outs[0]).all()
+    # the tensor core's fp32 accumulation over K = 16384 is itself ~8e-6 from fp64 (both schedules); cutting K moves it
+    assert rel(outs[0], ref) < 2e-5
+    assert rel(outs[0], plain) < 3e-5
+    if M == 18944:
+        assert torch.equal(outs[0], plain)
+    # the counters are back at zero
+    from dinox_b200 import ops as _o
+    flags = [v for k, v in _o._ZEROED.items() if k[0] == "gemm_balanced:" + tag]
+    assert flags and all(int(f.view(torch.int32).abs().sum()) == 0 for f in flags)
+
+
+def test_micro_step_gradients_with_balanced_backward(monkeypatch):
+    """DINOX_BALANCED=3 (dW2 and dH on the balanced schedule) gives the gradients of the default schedule up to the
+    fp32 summation split of the K ranges."""
+    from dinox_b200 import synth
+    from dinox_b200.step import LossHeadStep
+    shapes = synth.LossHeadShapes(**synth.CONFIGS["C1"])
+    feats = synth.feature_batch(shapes, synth.seeded_generator(1), patches_from_tokens=True)
+    res = {}
+    for mode in ("0", "3"):
+        monkeypatch.setenv("DINOX_BALANCED", mode)
+        step = LossHeadStep(shapes, DEV, accum=1, with_backbone_params=False)
+        f = {k: (v.to(DEV).requires_grad_(True) if k.startswith("student") else v.to(DEV)) for k, v in feats.items()}
+        out, loss = step._losses(f)
+        loss.backward()
+        torch.cuda.synchronize()
+        res[mode] = ([p.grad.clone() for p in step.student_head.parameters()] + [f["student_cls"].grad, f["student_tok"].grad],
+                     {k: v.item() for k, v in out.items()})
+    assert res["0"][1] == res["3"][1]
+    for a, b in zip(res["0"][0], res["3"][0]):
+        assert rel(b, a) < 2e-5
