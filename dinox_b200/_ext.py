@@ -115,6 +115,10 @@ SIGNATURES = {
     "dinox_device_check": (c_int, []),
     "dinox_launch_count": (c_i64, []),
     "dinox_launch_count_reset": (None, []),
+    "dinox_trace_begin": (c_int, [c_void_p, c_int]),
+    "dinox_trace_end": (c_int, []),
+    "dinox_trace_name": (ctypes.c_char_p, [c_int]),
+    "dinox_trace_stream": (ctypes.c_uint64, [c_int]),
     "dinox_ema_plan_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dinox_ema_plan_destroy": (c_int, [c_void_p]),
     "dinox_ema_plan_numel": (c_i64, [c_void_p]),

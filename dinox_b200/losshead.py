@@ -736,7 +736,10 @@ class _FusedHeadLoss(torch.autograd.Function):
         readback = pass2_mode() == "readback"
         Mt_pad = plan.Mt_pad if readback else Mt        # row of the first masked patch in the teacher matrices
         inv_ts, inv_tt = 1.0 / student_temp, 1.0 / teacher_temp
-        w1s, w2s = bf16_weight(w1), bf16_weight(w2)
+        # the bf16 copies are cached per PARAMETER object: in in-place mode w1 / w2 are fresh detached views on every
+        # call (a cache miss = a 150 MB cast of W2 inside every step), the real parameters ride in params_in_place
+        pw1, pw2 = (params_in_place[0], params_in_place[2]) if params_in_place is not None else (w1, w2)
+        w1s, w2s = bf16_weight(pw1), bf16_weight(pw2)
         w1t, w2t = bf16_weight(t_head[0].weight), bf16_weight(t_head[2].weight)
         centre_cls = update_center and teacher_mode == "center"
         # the patch centre is the only collapse protection of the iBOT targets in BOTH teacher modes (the CLS
@@ -815,6 +818,16 @@ class _FusedHeadLoss(torch.autograd.Function):
                 ct2_patch = pre[2]
             else:
                 ct2_patch = ops.axpby(b2t, inv_tt * LOG2E, center_patch.reshape(-1), -inv_tt * LOG2E) if Mm else None
+            # The centre EMA (a 50 MB GEMV over W2t) only needs the activation sums: from here on - the offsets above hold
+            # copies of the OLD centres, scripts/phase5_big_run.py:719 - it runs on its own stream beside the three big
+            # passes and is joined after pass 2 (it used to sit between pass 2 and the backward: 36 us of the step)
+            centre_stream = None
+            if side is not None and stats is not None and concurrency() < 3:
+                centre_stream = _side_stream(dev, 3)
+                centre_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(centre_stream):
+                    _update_centres(stats, hsum_work, w2t, b2t, loss_mod, center_patch, patch_momentum, centre_cls, centre_patch)
+                stats = None
             if readback:
                 # ONE pass over the teacher rows: statistics + un-normalised fp16 probabilities
                 with ops.TIMER.region("head_teacher"):
@@ -882,6 +895,8 @@ class _FusedHeadLoss(torch.autograd.Function):
                                          lse2_e, rb2_e, cw, losses, want_db2=need_grad)
         # ---- centre updates AFTER the loss (scripts/phase5_big_run.py:719)
         _update_centres(stats, hsum_work, w2t, b2t, loss_mod, center_patch, patch_momentum, centre_cls, centre_patch)
+        if centre_stream is not None:
+            main.wait_stream(centre_stream)
         if need_grad:
             ctx.save_for_backward(xs, a_s, hs_e, gt, db2p, w1s, w2s)
             ctx.plan = plan
@@ -967,11 +982,18 @@ class _FusedHeadLoss(torch.autograd.Function):
                 dh_e = ops.gemm_bf16_splitk(gt, w2s, a_mn_major=not rb, b_mn_major=True, m_fastest=True)
         # dL/dh of a row = sum of its entries' rows (and of the split-K slabs), formed inside the GELU backward
         da, part = ops.gelu_bwd_gather(dh_e, plan.csr_ptr, plan.csr_ent, a_s, scale_dev=up)
-        emit("b1", b1, lambda out, acc: ops.cols_sum_axpy_(part, out, acc))
-        # dW1 = da^T x: 3x3 output tiles with a reduction over every row -> split-K, slabs summed in fixed order
-        dw1_parts = ops.gemm_bf16_splitk(da, xs, a_mn_major=True, b_mn_major=True)
-        emit("w1", w1, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))
+        # the layer-1 parameter gradients (db1, dW1) and dL/dx only share da: two short chains side by side
+        side1 = _side_stream(dev, 4) if (concurrency() >= 2 and not ops.TIMER.enabled) else None
+        if side1 is not None:
+            side1.wait_stream(main)
+        with (torch.cuda.stream(side1) if side1 is not None else contextlib.nullcontext()):
+            emit("b1", b1, lambda out, acc: ops.cols_sum_axpy_(part, out, acc))
+            # dW1 = da^T x: 3x3 output tiles with a reduction over every row -> split-K, slabs summed in fixed order
+            dw1_parts = ops.gemm_bf16_splitk(da, xs, a_mn_major=True, b_mn_major=True)
+            emit("w1", w1, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))
         dx = ops.gemm_bf16(da, w1s, b_mn_major=True)
+        if side1 is not None:
+            main.wait_stream(side1)
         if side is not None:
             main.wait_stream(side)
         d_cls = dx[:plan.Ms].to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None

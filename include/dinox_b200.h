@@ -45,6 +45,14 @@ DINOX_API int dinox_device_check(void);
 /* number of kernels this library has launched on the calling thread since the last reset */
 DINOX_API int64_t dinox_launch_count(void);
 DINOX_API void dinox_launch_count_reset(void);
+/* Launch trace (diagnostics, tools/trace_step.py): between trace_begin and trace_end every launch of this library is
+ * followed, on its stream, by a one-thread kernel that writes %globaltimer (ns) into device_slots[i], i = launch
+ * order; captured into a CUDA graph the stamps are rewritten by every replay.  trace_end returns the number of
+ * launches recorded; trace_name / trace_stream describe slot i. */
+DINOX_API int dinox_trace_begin(uint64_t* device_slots, int capacity);
+DINOX_API int dinox_trace_end(void);
+DINOX_API const char* dinox_trace_name(int i);
+DINOX_API uint64_t dinox_trace_stream(int i);
 
 /* ------------------------------------------------------------------------------------------
  * a8  EMA teacher update.  Replaces the per-tensor loop
@@ -330,7 +338,7 @@ DINOX_API int dinox_scatter_rows_f32(const float* src, int64_t ld_src, const int
                                      float* dst, int64_t ld_dst, dinox_stream_t stream);
 /* h = bf16(gelu_erf(a)), n elements */
 DINOX_API int dinox_gelu_fwd(const float* a, int64_t n, void* h_bf16, dinox_stream_t stream);
-/* da = bf16(dh * (*scale_dev) * gelu'(a)); colsum_partial (ceil(rows/64), D) partial column sums */
+/* da = bf16(dh * (*scale_dev) * gelu'(a)); colsum_partial (dinox_gelu_bwd_workspace_bytes / (4 D) rows, D): partial column sums of da per slab of rows */
 DINOX_API size_t dinox_gelu_bwd_workspace_bytes(int64_t rows, int64_t D);
 DINOX_API int dinox_gelu_bwd(const float* dh, const float* a, int64_t rows, int64_t D, const float* scale_dev,
                              void* da_bf16, float* colsum_partial, dinox_stream_t stream);
