@@ -451,6 +451,16 @@ __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+// 16-byte stores, 4 per thread (the 100 MB gradient of W2 at the start of an accumulation window)
+__global__ void fill_f32x4_kernel(float4* __restrict__ p, int64_t n4, float v) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
+  const float4 x = make_float4(v, v, v, v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t i = i0 + (int64_t)j * blockDim.x;
+    if (i < n4) p[i] = x;
+  }
+}
 
 }  // namespace dinox
 
@@ -749,7 +759,12 @@ int dinox_entry_weights(const float* base, int64_t total, const float* mask_weig
 int dinox_fill_f32(float* p, int64_t n, float v, dinox_stream_t stream) {
   DINOX_REQUIRE(p && n >= 0, DINOX_E_BADARG, "fill_f32: bad arguments");
   if (n == 0) return DINOX_OK;
-  fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, n, v);
+  if (aligned16(p) && n % 4 == 0 && n >= 4096) {
+    const int64_t n4 = n / 4;
+    fill_f32x4_kernel<<<(unsigned)((n4 + 1023) / 1024), 256, 0, stream>>>(reinterpret_cast<float4*>(p), n4, v);
+  } else {
+    fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, n, v);
+  }
   return check_launch("fill_f32_kernel", stream);
 }
 

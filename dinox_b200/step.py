@@ -210,7 +210,7 @@ class LossHeadStep:
             self.capture(slot)
         if self.micro % self.accum == 0:
             for p in self.student_head.parameters():
-                p.grad.zero_()
+                ops.fill_(p.grad.view(-1), 0.0)
         for w in self._head_weights():
             losshead.bf16_weight(w)              # no-op unless a weight changed since the last cast
         self._graphs[slot]["graph"].replay()

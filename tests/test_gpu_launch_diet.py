@@ -237,3 +237,37 @@ def test_micro_step_gradients_with_balanced_backward(monkeypatch):
     assert res["0"][1] == res["3"][1]
     for a, b in zip(res["0"][0], res["3"][0]):
         assert rel(b, a) < 2e-5
+
+
+@pytest.mark.parametrize("n", [1, 5, 4096, 4100, 384 * 65536 + 384])
+def test_fill(ops, n):
+    buf = torch.full((n + 8,), 3.0, device=DEV)
+    ops.fill_(buf[4:4 + n], -1.5)            # 16-byte aligned start (4 floats in), any length
+    ops.fill_(buf[:1], 7.0)
+    torch.cuda.synchronize()
+    assert (buf[4:4 + n] == -1.5).all() and buf[0] == 7.0 and (buf[1:4] == 3.0).all() and (buf[4 + n:] == 3.0).all()
+
+
+@pytest.mark.parametrize("in_place", [True, False])
+def test_weight_copies_are_cached_across_calls(in_place):
+    """Second call of the fused loss with unchanged parameters issues no cast of the head weights (in in-place mode the
+    parameters enter the autograd function as fresh detached views: the cache must key on the parameters themselves)."""
+    from dinox_b200 import losshead, ops as O, synth
+    prev = losshead.set_weight_cache("tracked")
+    try:
+        sh = synth.LossHeadShapes(batch=4, dim=128, out_dim=2048, n_patches=16)
+        g = synth.seeded_generator(3)
+        s_head, t_head = losshead.ProjectionHead(sh.dim, sh.out_dim).to(DEV), losshead.ProjectionHead(sh.dim, sh.out_dim).to(DEV)
+        dl = losshead.DINOLoss(sh.out_dim, 0.9, n_global=2, n_local=8).to(DEV)
+        f = {k: v.to(DEV) for k, v in synth.feature_batch(sh, g, with_tokens=False, with_ibot=False).items()}
+        counts = []
+        for _ in range(3):
+            cls = f["student_cls"].clone().requires_grad_(True)
+            n0 = O.launch_count()
+            out = losshead.fused_head_dino_loss(cls, f["teacher_cls"], s_head, t_head, dl, 0.1, 0.04, grads_in_place=in_place)
+            out["loss"].backward()
+            counts.append(O.launch_count() - n0)
+        torch.cuda.synchronize()
+        assert counts[1] == counts[2] and counts[0] >= counts[1] + 4, counts     # 4 weight casts on the first call only
+    finally:
+        losshead.set_weight_cache(prev)
