@@ -157,6 +157,7 @@ SIGNATURES = {
                                 c_void_p, c_i64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dinox_head_teacher_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_head_teacher_granules_per_tile": (c_int, []),
+    "dinox_head_teacher_tile_cols": (c_int, []),
     "dinox_head_teacher": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_void_p, c_void_p, c_i64,
                                    c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dinox_head_grad2_workspace_bytes": (c_size, [c_i64, c_i64]),

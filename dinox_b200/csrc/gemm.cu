@@ -487,14 +487,23 @@ __device__ __forceinline__ uint32_t f16x2_bits(float lo, float hi) {
 }
 
 #ifndef DINOX_RB_EPI_WARPS
-#define DINOX_RB_EPI_WARPS 8   // epilogue warps of the two read-back kernels (teacher pass / pass 2): 8 or 16 (16: register cap 96, 3 operand stages - measured slower)
+#define DINOX_RB_EPI_WARPS 8   // epilogue warps of the two read-back kernels (teacher pass / pass 2): 8, 12 or 16 (16: register cap 96, 3 operand stages - measured slower)
 #endif
+// Tile width (prototypes) of the two read-back kernels: 256 with 8 or 16 epilogue warps (granules of 128 / 64
+// prototypes), 192 with 12 (three granules of 64: three epilogue warps per scheduler instead of two)
+#ifndef DINOX_RB_TILE
+#define DINOX_RB_TILE 256
+#endif
+constexpr int kRbTile = DINOX_RB_TILE;
+static_assert((DINOX_RB_TILE == 256 && (DINOX_RB_EPI_WARPS == 8 || DINOX_RB_EPI_WARPS == 16)) ||
+                  (DINOX_RB_TILE == 192 && DINOX_RB_EPI_WARPS == 12),
+              "read-back kernels: 256-wide tiles with 8 / 16 epilogue warps or 192-wide tiles with 12");
 template <bool kRun, int W>
 struct EpiTeachQT {
   static constexpr bool kUsesTmaStore = true;
-  static constexpr int kEpiWarps = W;                    // 8 or 16
+  static constexpr int kEpiWarps = W;                    // 8, 12 or 16
   static constexpr int kGroups = W / 4;                  // column groups per TMEM lane quarter
-  static constexpr int kColsW = 256 / kGroups;           // one granule (128 or 64 prototypes) per warp and tile
+  static constexpr int kColsW = kRbTile / kGroups;       // one granule (128 or 64 prototypes) per warp and tile
   // one staging buffer per warp (32 rows x 128 B) leaves five 16 KB operand stages beside the resident A rows;
   // the wait for the previous store's read sits behind the math of the next 32 columns
 #ifndef DINOX_TEACHQ_STAGING_BUFS
@@ -533,7 +542,7 @@ struct EpiTeachQT {
   }
   template <int BN>
   struct Impl {
-    static_assert(BN == 256 && (W == 8 || W == 16), "EpiTeachQ is written for 256-wide tiles and 8 or 16 epilogue warps");
+    static_assert(BN == kRbTile && kColsW % 64 == 0, "EpiTeachQ: tile width / epilogue warp count mismatch");
     static __device__ __forceinline__ void fetch(const Params& e, const CoreParams& p, TileCoord tc, int epi_warp, int lane,
                                                  State& st) {
       const int col0 = tc.n_tile * BN + (epi_warp >> 2) * kColsW;
@@ -698,9 +707,9 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 template <int W>
 struct EpiGradRT {
   static constexpr bool kUsesTmaStore = true;
-  static constexpr int kEpiWarps = W;                    // 8: 2 x 128 columns per TMEM lane quarter; 16: 4 x 64
+  static constexpr int kEpiWarps = W;                    // 8: 2 x 128 columns per TMEM lane quarter; 16: 4 x 64; 12: 3 x 64 (192-wide tile)
   static constexpr int kGroups = W / 4;
-  static constexpr int kColsW = 256 / kGroups;
+  static constexpr int kColsW = kRbTile / kGroups;
   static constexpr int kChunks = kColsW / 16;
 #ifndef DINOX_GRADR_SLOTS
 #define DINOX_GRADR_SLOTS 4
@@ -790,7 +799,7 @@ struct EpiGradRT {
   }
   template <int BN>
   struct Impl {
-    static_assert(BN == 256 && (W == 8 || W == 16), "EpiGradR is written for 256-wide tiles and 8 or 16 epilogue warps");
+    static_assert(BN == kRbTile && kColsW % 64 == 0, "EpiGradR: tile width / epilogue warp count mismatch");
     static __device__ __forceinline__ void ldq(const __half* p, uint32_t (&r)[8], uint64_t pol) {
 #if DINOX_EXP_G2 & 1   // experiment: no teacher-probability loads
       return;
@@ -1856,10 +1865,12 @@ int dinox_head_grad(const void* W2s, const void* W2t, const void* HsE, const voi
 /* ---- teacher, one pass: statistics + un-normalised fp16 probabilities (see EpiTeachQT) ---- */
 size_t dinox_head_teacher_workspace_bytes(int64_t rows, int64_t K) {
   if (rows <= 0 || K <= 0) return 0;
-  return (size_t)rows * EpiTeachQ<false>::kGroups * ((K + 255) / 256 + 1) * sizeof(float2);   // + 1: run-mode slot bound
+  return (size_t)rows * EpiTeachQ<false>::kGroups * ((K + kRbTile - 1) / kRbTile + 1) * sizeof(float2);   // + 1: run-mode slot bound
 }
 /* granules (rows of `refs`) per 256-prototype tile: 128 / 64 prototypes per granule with 8 / 16 epilogue warps */
 int dinox_head_teacher_granules_per_tile(void) { return EpiTeachQ<false>::kGroups; }
+/* prototypes per tile of the read-back pair: rows of qt are padded to a multiple of it */
+int dinox_head_teacher_tile_cols(void) { return kRbTile; }
 
 int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D, int64_t ldh, int64_t ldw,
                        float inv_tau, const float* col2, const float* col2_alt, int64_t alt_from_row, void* qt,
@@ -1867,23 +1878,23 @@ int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, i
                        dinox_stream_t stream) {
   DINOX_REQUIRE(H && W2 && qt && refs && workspace, DINOX_E_BADARG, "head_teacher: null pointer");
   DINOX_REQUIRE(rows > 0 && K > 0 && D > 0, DINOX_E_BADARG, "head_teacher: empty problem");
-  const int64_t num_n = (K + 255) / 256;
-  DINOX_REQUIRE(ldq >= num_n * 256 && aligned16(qt) && (ldq * 2) % 16 == 0, DINOX_E_ALIGN,
-                "head_teacher: qt rows must be padded to whole 256-prototype tiles (ldq >= %lld)", (long long)(num_n * 256));
+  const int64_t num_n = (K + kRbTile - 1) / kRbTile;
+  DINOX_REQUIRE(ldq >= num_n * kRbTile && aligned16(qt) && (ldq * 2) % 16 == 0, DINOX_E_ALIGN,
+                "head_teacher: qt rows must be padded to whole prototype tiles (ldq >= %lld)", (long long)(num_n * kRbTile));
   DINOX_REQUIRE(ld_refs >= rows, DINOX_E_BADARG, "head_teacher: ld_refs < rows");
   DINOX_REQUIRE(!col2_alt || alt_from_row % BM == 0, DINOX_E_BADARG, "head_teacher: alt_from_row must be a multiple of 128");
   int rc = require_sm100();
   if (rc) return rc;
   Operand a{H, rows, ldh, 0}, b{W2, K, ldw, 0};
   OutDesc od;
-  od.ptr = qt; od.is_bf16 = 1; od.ld = ldq; od.slab_stride = rows * ldq; od.slabs = 1; od.cols = num_n * 256;
+  od.ptr = qt; od.is_bf16 = 1; od.ld = ldq; od.slab_stride = rows * ldq; od.slabs = 1; od.cols = num_n * kRbTile;
   const int alt_mtile = col2_alt ? (int)(alt_from_row / BM) : (1 << 30);
   const bool cl2 = rows > BM && pair_enabled(kPairStats);
   if (cl2 && readback_cols(1, D)) {
     // W2 tile resident (a CTA of a pair holds half of it: 96 KB), every cluster sweeps the M tiles of its prototype tile in step with the others: W2 is read
     // from HBM exactly once per launch (the probability stream would evict it from L2 between two M-tile runs)
     EpiTeachQ<false>::Params ep{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), 1, 1, 1, refs, ld_refs};
-    rc = launch<256, 1, 1, 2, EpiTeachQ<false>, kResB>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher<pair,resB>");
+    rc = launch<kRbTile, 1, 1, 2, EpiTeachQ<false>, kResB>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher<pair,resB>");
     if (rc) return rc;
     if (lse_nat || lse2) {
       stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows,
@@ -1900,7 +1911,7 @@ int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, i
     const int run_slots = (int)((num_n + per - 1) / per) + 1;
     EpiTeachQ<true>::Params er{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), cl, per,
                                 run_slots, refs, ld_refs};
-    rc = launch<256, 1, 1, 2, EpiTeachQ<true>, kResA>(a, b, nullptr, nullptr, rows, K, D, 0, er, od, stream, "head_teacher<pair,resA>");
+    rc = launch<kRbTile, 1, 1, 2, EpiTeachQ<true>, kResA>(a, b, nullptr, nullptr, rows, K, D, 0, er, od, stream, "head_teacher<pair,resA>");
     if (rc) return rc;
     if (lse_nat || lse2) {
       stats_merge_run_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(er.partial, rows, EpiTeachQ<true>::kGroups, run_slots,
@@ -1910,8 +1921,8 @@ int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, i
     return DINOX_OK;
   }
   EpiTeachQ<false>::Params ep{inv_tau * DINOX_LOG2E, col2, col2_alt, alt_mtile, reinterpret_cast<float2*>(workspace), 1, 1, 1, refs, ld_refs};
-  rc = cl2 ? launch<256, 1, 1, 2, EpiTeachQ<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher<pair>")
-           : launch<256, 1, 1, 1, EpiTeachQ<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher");
+  rc = cl2 ? launch<kRbTile, 1, 1, 2, EpiTeachQ<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher<pair>")
+           : launch<kRbTile, 1, 1, 1, EpiTeachQ<false>>(a, b, nullptr, nullptr, rows, K, D, 1, ep, od, stream, "head_teacher");
   if (rc) return rc;
   if (lse_nat || lse2) {
     stats_merge_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const float2*>(workspace), rows,
@@ -1936,9 +1947,9 @@ int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int
   DINOX_REQUIRE(HsE && W2s && cs2 && lse2_e && cw_e && rb2_e && trow_e && qt && refs && G && loss_out && workspace,
                 DINOX_E_BADARG, "head_grad2: null pointer");
   DINOX_REQUIRE(E > 0 && K > 0 && D > 0, DINOX_E_BADARG, "head_grad2: empty problem");
-  const int64_t num_n = (K + 255) / 256;
-  DINOX_REQUIRE(ldq >= num_n * 256 && (ldq * 2) % 32 == 0 && (reinterpret_cast<uintptr_t>(qt) & 31u) == 0, DINOX_E_ALIGN,
-                "head_grad2: qt must be 32-byte aligned with rows padded to whole 256-prototype tiles");
+  const int64_t num_n = (K + kRbTile - 1) / kRbTile;
+  DINOX_REQUIRE(ldq >= num_n * kRbTile && (ldq * 2) % 32 == 0 && (reinterpret_cast<uintptr_t>(qt) & 31u) == 0, DINOX_E_ALIGN,
+                "head_grad2: qt must be 32-byte aligned with rows padded to whole prototype tiles");
   DINOX_REQUIRE(ldg >= K && (ldg * 2) % 16 == 0 && aligned16(G), DINOX_E_ALIGN, "head_grad2: G / ldg misaligned");
   int rc = require_sm100();
   if (rc) return rc;
@@ -1957,12 +1968,12 @@ int dinox_head_grad2(const void* HsE, const void* W2s, int64_t E, int64_t K, int
   ep.run_rows = (cl2 && !readback_cols(2, D) && resa_enabled(kPairStats, D)) ? 1 : 0;
   ep.m_step = (cl2 && readback_cols(2, D)) ? 2 : 0;
   if (cl2 && readback_cols(2, D))   // W2 tile resident, clusters sweep the entry tiles in step (W2 read from HBM once)
-    rc = launch<256, 1, 1, 2, EpiGradR, kResB>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair,resB>");
+    rc = launch<kRbTile, 1, 1, 2, EpiGradR, kResB>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair,resB>");
   else if (cl2 && resa_enabled(kPairStats, D))   // the entries of an M tile resident, prototype tiles walked in one contiguous run
-    rc = launch<256, 1, 1, 2, EpiGradR, kResA>(a, b, nullptr, nullptr, E, K, D, 0, ep, od, stream, "head_grad2<pair,resA>");
+    rc = launch<kRbTile, 1, 1, 2, EpiGradR, kResA>(a, b, nullptr, nullptr, E, K, D, 0, ep, od, stream, "head_grad2<pair,resA>");
   else
-    rc = cl2 ? launch<256, 1, 1, 2, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair>")
-             : launch<256, 1, 1, 1, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2");
+    rc = cl2 ? launch<kRbTile, 1, 1, 2, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2<pair>")
+             : launch<kRbTile, 1, 1, 1, EpiGradR>(a, b, nullptr, nullptr, E, K, D, 1, ep, od, stream, "head_grad2");
   if (rc || ticket) return rc;
   const int grid = launch_grid((((E + BM - 1) / BM + cl - 1) / cl) * num_n, cl);
   pair_sum_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float*>(workspace), (int64_t)grid * EpiGradR::kEpiWarps, loss_out,

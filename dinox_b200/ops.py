@@ -319,15 +319,21 @@ def head_grad(w2s, w2t, hs_e, ht_e, inv_tau_s, inv_tau_t, cs2, ct2, ct2_alt, alt
 
 
 def teacher_granules_per_tile() -> int:
-    """granules (prototype groups sharing one reference exponent) per 256-prototype tile: 2 or 4"""
+    """granules (prototype groups sharing one reference exponent) per prototype tile: 2, 3 or 4"""
     return int(_ext.lib().dinox_head_teacher_granules_per_tile())
 
 
+def teacher_tile_cols() -> int:
+    """prototypes per tile of the read-back pair (256, or 192 in the 12-epilogue-warp build)"""
+    return int(_ext.lib().dinox_head_teacher_tile_cols())
+
+
 def teacher_buffers(rows: int, K: int, device):
-    """(qt, refs) of dinox_head_teacher: fp16 probabilities with rows padded to whole 256-prototype tiles,
-    and the per-(128-prototype granule, row) maxima."""
-    n_tiles = (K + 255) // 256
-    qt = torch.empty(rows, n_tiles * 256, dtype=torch.float16, device=device)
+    """(qt, refs) of dinox_head_teacher: fp16 probabilities with rows padded to whole prototype tiles,
+    and the per-(granule, row) maxima."""
+    tile = teacher_tile_cols()
+    n_tiles = (K + tile - 1) // tile
+    qt = torch.empty(rows, n_tiles * tile, dtype=torch.float16, device=device)
     refs = torch.empty(teacher_granules_per_tile() * n_tiles, rows, dtype=torch.float32, device=device)
     return qt, refs
 
@@ -338,7 +344,7 @@ def head_teacher(h: torch.Tensor, w2: torch.Tensor, inv_tau: float, col2: Option
                  out_log2: Optional[torch.Tensor] = None):
     """Teacher in one pass: returns (qt (rows, K_pad) fp16, refs (granules, rows) fp32, lse2 (rows)) with
     softmax(h @ w2^T * inv_tau + col2/log2e)[i, k] = qt[i, k] * 2^(refs[k // gw, i] - lse2[i]),
-    gw = 256 // teacher_granules_per_tile() prototypes per granule."""
+    gw = teacher_tile_cols() // teacher_granules_per_tile() prototypes per granule."""
     _chk_cuda(h, w2, col2, col2_alt)
     rows, D = h.shape
     K = w2.shape[0]

@@ -254,6 +254,9 @@ DINOX_API size_t dinox_head_teacher_workspace_bytes(int64_t rows, int64_t K);
 /* granules per 256-prototype tile (2: 128 prototypes each, or 4: 64 each - a build constant); refs has
  * granules_per_tile * ceil(K/256) rows and granule g(k) = k / (256 / granules_per_tile) */
 DINOX_API int dinox_head_teacher_granules_per_tile(void);
+/* prototypes per tile of the read-back pair (256; 192 in the 12-epilogue-warp build): qt rows are padded to a multiple
+ * of it, and wherever this header says ceil(K/256) for qt / refs it means ceil(K / tile_cols) */
+DINOX_API int dinox_head_teacher_tile_cols(void);
 DINOX_API int dinox_head_teacher(const void* H, const void* W2, int64_t rows, int64_t K, int64_t D,
                                  int64_t ldh, int64_t ldw, float inv_tau, const float* col2,
                                  const float* col2_alt, int64_t alt_from_row, void* qt, int64_t ldq,

@@ -61,9 +61,9 @@ def test_head_teacher_probabilities_and_statistics(ops, rows, K, D, alt_from, sp
     qt, refs, lse2 = ops.head_teacher(h.to(DEV), w.to(DEV), inv_tau, col.to(DEV),
                                       None if col_alt is None else col_alt.to(DEV), alt_from or 0)
     torch.cuda.synchronize()
-    gpt = ops.teacher_granules_per_tile()
-    gw = 256 // gpt                                                   # prototypes per granule
-    assert qt.shape == (rows, (K + 255) // 256 * 256) and refs.shape == (gpt * ((K + 255) // 256), rows)
+    gpt, tile = ops.teacher_granules_per_tile(), ops.teacher_tile_cols()
+    gw = tile // gpt                                                  # prototypes per granule
+    assert qt.shape == (rows, (K + tile - 1) // tile * tile) and refs.shape == (gpt * ((K + tile - 1) // tile), rows)
     assert torch.isfinite(qt.float()).all()
     assert (qt[:, K:] == 0).all(), "padding prototypes must be written as zeros"
     assert rel(lse2, lse2_ref) < 1e-5
