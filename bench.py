@@ -518,8 +518,10 @@ def run_ours(args):
 
     # ---------------- leg 2: end to end from pinned host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    read_back = [torch.cuda.Event() for _ in range(2)]
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def prefetch(i):
@@ -533,19 +535,27 @@ def run_ours(args):
         cur = torch.cuda.current_stream()
         for b in range(2):
             consumed[b].record(cur)
+            read_back[b].record(cur)
         prefetch(0)
         for i in range(n):
             b = i & 1
             if i + 1 < n:
                 prefetch(i + 1)          # H2D of the next step overlaps this step's kernels
             cur.wait_event(ready[b])
+            cur.wait_event(read_back[b])   # the slot's static outputs were read back (two steps ago) before they are rewritten
             if use_graph:
                 o = step.micro_step_graph(b)
             else:
                 o = step.micro_step(to_leaves({k: v.detach() for k, v in bufs[b].items()}))
             consumed[b].record(cur)
-            loss_host.copy_(o["loss_total"].reshape(1), non_blocking=True)   # D2H of the step's result
+            # D2H of the step's result, every step, on its own stream: a copy queued between two graph launches on the
+            # compute stream would put its launch latency on the critical path of every step
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(consumed[b])
+                loss_host.copy_(o["loss_total"].reshape(1), non_blocking=True)
+                read_back[b].record(d2h_stream)
         cur.synchronize()
+        d2h_stream.synchronize()
 
     e2e_loop(max(args.warmup, 2))
     barrier()

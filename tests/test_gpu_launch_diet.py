@@ -271,3 +271,34 @@ def test_weight_copies_are_cached_across_calls(in_place):
         assert counts[1] == counts[2] and counts[0] >= counts[1] + 4, counts     # 4 weight casts on the first call only
     finally:
         losshead.set_weight_cache(prev)
+
+
+def test_launch_trace_records_names_streams_and_ordered_stamps(ops):
+    """dinox_trace_begin/end: every launch between them is followed by a %globaltimer stamp on its stream."""
+    import ctypes
+    from dinox_b200 import _ext
+    lib = _ext.lib()
+    slots = torch.zeros(64, dtype=torch.int64, device=DEV)
+    x = torch.randn(1 << 20, device=DEV)
+    _ext.check(lib.dinox_trace_begin(ctypes.c_void_p(slots.data_ptr()), 64), "trace_begin")
+    try:
+        ops.fill_(x, 1.0)
+        ops.axpb(x, 2.0, 1.0, out=x)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.fill_(x[:4096], 0.0)
+    finally:
+        n = lib.dinox_trace_end()
+    torch.cuda.synchronize()
+    assert n == 3
+    names = [lib.dinox_trace_name(i).decode() for i in range(n)]
+    assert names[0].startswith("fill") and names[2].startswith("fill") and "axpb" in names[1]
+    st = [int(lib.dinox_trace_stream(i)) for i in range(n)]
+    assert st[0] == st[1] and st[2] == side.cuda_stream
+    t = slots[:n].tolist()
+    assert 0 < t[0] <= t[1] <= t[2]
+    # tracing is off again: nothing is recorded, nothing is stamped
+    ops.fill_(x, 3.0)
+    torch.cuda.synchronize()
+    assert lib.dinox_trace_end() == 3 and int(slots[3]) == 0
