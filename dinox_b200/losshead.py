@@ -950,6 +950,13 @@ class _FusedHeadLoss(torch.autograd.Function):
         # (2.322 vs 2.337 ms, 3 interleaved runs each): inside the step the idle SMs of dW2's last wave are already
         # taken by the side-stream kernels (centre GEMV, Gram backward) - profiles/README.md.
         balanced = int(os.environ.get("DINOX_BALANCED", "0"))
+        # the bias gradients and dW1 never feed another kernel of this backward: they run on a side stream beside the
+        # dW2 -> dH -> dL/dx chain (db2's 70 MB column sum used to stand between dW2 and dH)
+        side1 = _side_stream(dev, 4) if (concurrency() >= 2 and not ops.TIMER.enabled) else None
+        if side1 is not None:
+            side1.wait_stream(main)
+            with torch.cuda.stream(side1):
+                emit("b2", b2, lambda out, acc: ops.cols_sum_axpy_(db2p, out, acc, scale_dev=up))
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             # dW2 (K, D) += g * G^T . HsE   (A = G with the prototypes as M; B = HsE MN-major)
             with ops.TIMER.region("gemm_dW2"):
@@ -973,7 +980,8 @@ class _FusedHeadLoss(torch.autograd.Function):
                 else:
                     emit("w2", w2, lambda out, acc: ops.gemm_bf16(
                         gt, hs_e, a_mn_major=rb, b_mn_major=True, out=out, accumulate=acc, alpha_dev=up, m_fastest=False))
-            emit("b2", b2, lambda out, acc: ops.cols_sum_axpy_(db2p, out, acc, scale_dev=up))
+            if side1 is None:
+                emit("b2", b2, lambda out, acc: ops.cols_sum_axpy_(db2p, out, acc, scale_dev=up))
         # dH per entry = G . W2  (B = W2 MN-major), then sum the entries of each row
         with ops.TIMER.region("gemm_dH"):
             if balanced & 2:   # fewer tiles than CTA pairs: every tile cut along the prototypes, accumulated in place
@@ -983,7 +991,6 @@ class _FusedHeadLoss(torch.autograd.Function):
         # dL/dh of a row = sum of its entries' rows (and of the split-K slabs), formed inside the GELU backward
         da, part = ops.gelu_bwd_gather(dh_e, plan.csr_ptr, plan.csr_ent, a_s, scale_dev=up)
         # the layer-1 parameter gradients (db1, dW1) and dL/dx only share da: two short chains side by side
-        side1 = _side_stream(dev, 4) if (concurrency() >= 2 and not ops.TIMER.enabled) else None
         if side1 is not None:
             side1.wait_stream(main)
         with (torch.cuda.stream(side1) if side1 is not None else contextlib.nullcontext()):
