@@ -150,8 +150,8 @@ def test_pass2_row_statistics_by_index_and_fused_loss_sum(ops):
 
 
 def test_micro_step_launch_count():
-    """The captured micro-step (fused head + iBOT rows named by index + Gram anchoring, centre teacher) is <= 38
-    launches of this library and its forward/backward glue issues no framework fill kernels."""
+    """The captured micro-step (fused head + iBOT rows named by index + Gram anchoring, centre teacher) is <= 36
+    launches of this library (34 measured) with the default pass pair."""
     from dinox_b200 import synth
     from dinox_b200.step import LossHeadStep
     shapes = synth.LossHeadShapes(**synth.CONFIGS["C1"])
@@ -163,7 +163,11 @@ def test_micro_step_launch_count():
         for k, v in feats.items():
             slot[k].copy_(v)
     step.capture(0)
-    assert step.launches_per_graph <= 38, step.launches_per_graph
+    from dinox_b200 import losshead
+    # 34 with the default read-back pass pair; the round-1 pair (DINOX_PASS2=recompute) has two statistics launches on
+    # the teacher side, a per-entry gather of the teacher activations and the per-entry gathers of the row statistics
+    limit = 36 if losshead.pass2_mode() == "readback" else 44
+    assert step.launches_per_graph <= limit, step.launches_per_graph
     out = step.micro_step_graph(0)
     torch.cuda.synchronize()
     assert all(torch.isfinite(v).all() for v in out.values())
