@@ -661,12 +661,24 @@ def concurrency() -> int:
     return int(os.environ.get("DINOX_CONCURRENCY", "2"))
 
 
+def stream_priorities() -> bool:
+    """DINOX_STREAM_PRIO (default 1): the streams of the critical chain (teacher branch, backward side chains, the
+    capture stream of LossHeadStep) get a higher CUDA priority than the Gram-anchoring and centre-update streams, so
+    that pending blocks of the chain are dispatched first when SMs free up."""
+    return os.environ.get("DINOX_STREAM_PRIO", "1") != "0"
+
+
+# which: 0 teacher branch, 1 Gram anchoring, 2 dW2/db2 at concurrency level 3, 3 centre update, 4 parameter-gradient chain
+_LOW_PRIORITY_STREAMS = (1, 3)
+
+
 def _side_stream(device, which: int = 0) -> "torch.cuda.Stream":
     dev = torch.device(device)
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
     st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+        prio = -1 if (stream_priorities() and which not in _LOW_PRIORITY_STREAMS) else 0
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=prio)
     return st
 
 

@@ -138,7 +138,10 @@ class LossHeadStep:
             losshead.bf16_weight(w)              # casts happen OUTSIDE the graph (refreshed in place later)
         g = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
-        with torch.cuda.graph(g):
+        # the main chain of the step is captured on a high-priority stream (kernel nodes keep the priority of the stream
+        # they were captured on): its blocks are dispatched ahead of the Gram / centre side work when SMs free up
+        cap_stream = torch.cuda.Stream(device=self.device, priority=-1) if losshead.stream_priorities() else None
+        with torch.cuda.graph(g, stream=cap_stream):
             out = self._fwd_bwd(f)
         self.launches_per_graph = ops.launch_count() - n0
         self._graphs[slot] = dict(graph=g, out=out)
