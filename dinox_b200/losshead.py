@@ -668,7 +668,8 @@ def stream_priorities() -> bool:
     return os.environ.get("DINOX_STREAM_PRIO", "1") != "0"
 
 
-# which: 0 teacher branch, 1 Gram anchoring, 2 dW2/db2 at concurrency level 3, 3 centre update, 4 parameter-gradient chain
+# which: 0 teacher branch, 1 Gram anchoring, 2 dW2/db2 at concurrency level 3, 3 centre update, 4 / 6 parameter-gradient
+# chains of the backward, 5 entry staging beside pass 1
 _LOW_PRIORITY_STREAMS = (1, 3)
 
 
@@ -877,22 +878,29 @@ class _FusedHeadLoss(torch.autograd.Function):
         hs = ops.gelu_fwd(a_s)
         b2s = b2.detach()
         cs2 = pre[0] if pre is not None else ops.axpb(b2s, inv_ts * LOG2E)
+        # ---- entries: the student activations per entry and the entry weights only need the GELU output - they are
+        # staged beside pass 1 (own stream; these small kernels fit on the SMs next to its CTAs) instead of between the
+        # teacher pass and pass 2
+        aux = _side_stream(dev, 5) if side is not None else None
+        if aux is not None:
+            aux.wait_stream(main)
+        with (torch.cuda.stream(aux) if aux is not None else contextlib.nullcontext()):
+            hs_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
+            ops.gather_cast_bf16(hs, plan.ent_s, hs_e)
+            cw = plan.cw_base
+            if Mm:
+                mw = masks_weight.detach()
+                mw = mw if (mw.dtype == torch.float32 and mw.is_contiguous()) else mw.float().contiguous()
+                cw = ops.entry_weights(plan.cw_base, mw, plan.e_cls_pad, ibot_weight / Mt)
         with ops.TIMER.region("head_stats_student"):
             _, lse2_s = ops.head_stats(hs, w2s, inv_ts, cs2, want_nat=False)
-        # ---- entries
-        hs_e = torch.empty(plan.e_pad, D, dtype=torch.bfloat16, device=dev)
-        ops.gather_cast_bf16(hs, plan.ent_s, hs_e)
         lse2_e = lse2_s if readback else ops.gather_f32(lse2_s, plan.ent_s, fill=1.0e30)
         if side is not None:
-            # Everything the teacher branch allocated lives in the side stream's pool and is read by pass 2 on
+            # Everything the side branches allocated lives in their streams' pools and is read by pass 2 on
             # this stream: those blocks are only handed out again to side-stream work, and every side-stream
             # region starts by waiting for this stream, i.e. after pass 2 has been queued.
             main.wait_stream(side)
-        cw = plan.cw_base
-        if Mm:
-            mw = masks_weight.detach()
-            mw = mw if (mw.dtype == torch.float32 and mw.is_contiguous()) else mw.float().contiguous()
-            cw = ops.entry_weights(plan.cw_base, mw, plan.e_cls_pad, ibot_weight / Mt)
+            main.wait_stream(aux)
         # ---- pass 2
         lbuf = torch.empty(4, dtype=torch.float32, device=dev)     # [L_dino, L_ibot, total, -]
         losses = lbuf[:3]
@@ -1005,14 +1013,19 @@ class _FusedHeadLoss(torch.autograd.Function):
         # the layer-1 parameter gradients (db1, dW1) and dL/dx only share da: two short chains side by side
         if side1 is not None:
             side1.wait_stream(main)
-        with (torch.cuda.stream(side1) if side1 is not None else contextlib.nullcontext()):
+        side2 = _side_stream(dev, 6) if side1 is not None else None
+        if side2 is not None:
+            side2.wait_stream(main)
+        with (torch.cuda.stream(side2) if side2 is not None else contextlib.nullcontext()):
             emit("b1", b1, lambda out, acc: ops.cols_sum_axpy_(part, out, acc))
+        with (torch.cuda.stream(side1) if side1 is not None else contextlib.nullcontext()):
             # dW1 = da^T x: 3x3 output tiles with a reduction over every row -> split-K, slabs summed in fixed order
             dw1_parts = ops.gemm_bf16_splitk(da, xs, a_mn_major=True, b_mn_major=True)
             emit("w1", w1, lambda out, acc: ops.sum_slabs(dw1_parts, out, accumulate=acc))
         dx = ops.gemm_bf16(da, w1s, b_mn_major=True)
         if side1 is not None:
             main.wait_stream(side1)
+            main.wait_stream(side2)
         if side is not None:
             main.wait_stream(side)
         d_cls = dx[:plan.Ms].to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None

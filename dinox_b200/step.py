@@ -7,6 +7,7 @@
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -42,6 +43,7 @@ class LossHeadStep:
                                            patch_teacher_mode=patch_teacher_mode).to(device)
         self.center_patch = torch.zeros(1, K, device=device)
         self._unit = torch.ones((), dtype=torch.float32, device=device)
+        self._seeds: Dict[float, torch.Tensor] = {}
         # every other student/teacher parameter (backbone, scale-embed): random stand-ins with the
         # reference's shapes so that the EMA walks the real 161 / 305 tensor list
         self.student_params: List[torch.Tensor] = []
@@ -148,20 +150,58 @@ class LossHeadStep:
         ops.TIMER.enabled = was_timing
 
     def _fwd_bwd(self, f):
-        out, loss = self._losses(f)
-        loss.backward(self._unit)      # a resident 1.0: no ones_like fill per step
+        """Forward + backward of one micro-step.  The loss terms are NOT summed inside the autograd graph: the gradient of
+        the total with respect to term i is the constant w_i / accum, so every term's backward is seeded with that
+        constant (torch.autograd.backward on the list of terms) and the head's backward - the critical chain - starts
+        right behind pass 2 instead of behind the side branches (Gram anchoring's forward used to gate it through the
+        sum).  The total, for reporting, is formed on the side stream once its last term is there."""
+        with losshead.contraction_precision("bf16"):
+            out, terms, weights, side = self._loss_terms(f)
+        main = torch.cuda.current_stream()
+        if side is not None and os.environ.get("DINOX_DECOUPLED", "1") == "0":   # A/B knob: the sum inside the graph
+            main.wait_stream(side)
+            side = None
+        if side is None:
+            scaled, total = losshead.combine_losses(terms, weights, 1.0 / self.accum)
+            out["loss_total"] = total
+            scaled.backward(self._unit)      # a resident 1.0: no ones_like fill per step
+            return out
+        side.wait_stream(main)               # the head's loss values (pass 2) are on the main stream
+        with torch.cuda.stream(side):
+            total = torch.empty((), dtype=torch.float32, device=self.device)
+            ops.scalar_combine([t.detach().reshape(()) for t in terms], weights, 1.0 / self.accum, out_unscaled=total)
+            out["loss_total"] = total
+        seeds = [self._seed(w) for w in weights]
+        torch.autograd.backward(terms, seeds)
+        main.wait_stream(side)               # Gram forward / backward and the total are part of this step
         return out
+
+    def _seed(self, w: float) -> torch.Tensor:
+        """d(total / accum) / d(term) = w / accum as a resident device scalar, rounded like the fan-out kernel of
+        combine_losses rounds it (fp32: (1 * 1/accum) * w), so both routes give the same gradients bit for bit."""
+        t = self._seeds.get(w)
+        if t is None:
+            import numpy as np
+            v = np.float32(np.float32(1.0) * np.float32(1.0 / self.accum)) * np.float32(w)
+            t = self._seeds[w] = torch.full((), float(v), dtype=torch.float32, device=self.device)
+        return t
 
     def _losses(self, f):
         # this step is the bf16 tensor-core configuration of the benchmark (BASELINE.json: bf16 operands, fp32
         # accumulation) whatever the global contraction precision of the drop-in modules is
         with losshead.contraction_precision("bf16"):
-            return self._losses_bf16(f)
+            out, terms, weights, side = self._loss_terms(f)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        # loss = (L_dino + L_ibot + w_g L_gram + w_k L_koleo) / accum  (scripts/phase5_big_run.py:1749-1769), one launch
+        scaled, total = losshead.combine_losses(terms, weights, 1.0 / self.accum)
+        out["loss_total"] = total
+        return out, scaled
 
-    def _losses_bf16(self, f):
-        """Forward of all loss terms.  Gram anchoring is independent of the head until the final sum: it is
-        issued first, on a side stream, and its small kernels (and, by autograd's stream rule, their
-        backward) run beside the head's GEMMs instead of between them."""
+    def _loss_terms(self, f):
+        """Forward of all loss terms -> (outputs, terms, weights, side stream of the Gram term or None).  Gram anchoring
+        is independent of the head: it is issued first, on a side stream, and its small kernels (and, by autograd's
+        stream rule, their backward) run beside the head's GEMMs instead of between them."""
         gram, side, stok, rows = None, None, None, None
         if "student_tok" in f:
             stok = f["student_tok"]
@@ -189,8 +229,6 @@ class LossHeadStep:
             w2_grad_shards=self.w2_grad_shards)
         terms, weights = [out["loss"]], [1.0]
         if gram is not None:
-            if side is not None:
-                torch.cuda.current_stream().wait_stream(side)
             out["loss_gram"] = gram
             terms.append(gram)
             weights.append(self.gram_weight)
@@ -200,10 +238,7 @@ class LossHeadStep:
             out["loss_koleo"] = self.koleo(z)
             terms.append(out["loss_koleo"])
             weights.append(self.koleo_weight)
-        # loss = (L_dino + L_ibot + w_g L_gram + w_k L_koleo) / accum  (scripts/phase5_big_run.py:1749-1769), one launch
-        scaled, total = losshead.combine_losses(terms, weights, 1.0 / self.accum)
-        out["loss_total"] = total
-        return out, scaled
+        return out, terms, weights, side
 
     def micro_step_graph(self, slot: int = 0) -> Dict[str, torch.Tensor]:
         """Replay the captured micro-step on the current contents of the slot's static inputs.  Returns
