@@ -173,6 +173,8 @@ SIGNATURES = {
     "dinox_gram_diff_workspace_bytes": (c_size, [c_i64, c_i64]),
     "dinox_gram_diff": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_i64, c_f32, c_void_p, c_void_p, c_void_p]),
     "dinox_gemm_bf16_balanced_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "dinox_plan_ordered_split": (c_int, [c_i64, c_i64, c_i64, c_void_p, c_void_p]),
+    "dinox_debug_walk_ordered": (c_i64, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_i64]),
     "dinox_gemm_bf16_balanced": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
                                          c_int, c_f32, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "dinox_gather_cast_bf16_2": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int, c_i64,

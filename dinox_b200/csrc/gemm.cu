@@ -1663,6 +1663,39 @@ int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, int64_t N,
   return launch_store(M, N, a, b, K, m_fastest, sa, stream, 1, 1);
 }
 
+/* host-side views of the balanced schedule (no GPU needed; tests/test_host_logic.py): the plan for a tile / cluster /
+ * k-block count, and the item list every cluster walks (TileWalker::init_ordered) */
+int dinox_plan_ordered_split(int64_t tiles, int64_t clusters, int64_t kblocks, int* first, int* parts) {
+  DINOX_REQUIRE(first && parts, DINOX_E_BADARG, "plan_ordered_split: null pointer");
+  const OrderedSplit os = plan_ordered_split(tiles, clusters, kblocks);
+  *first = os.first;
+  *parts = os.parts;
+  return DINOX_OK;
+}
+
+int64_t dinox_debug_walk_ordered(int num_m_super, int num_n_tiles, int m_fastest, int os_first, int os_parts, int clusters,
+                                 int cl, int32_t* out /* (cap, 6): item, cluster, m_tile of CTA 0, n_tile, kpart, kparts */,
+                                 int64_t cap) {
+  if (!out || num_m_super <= 0 || num_n_tiles <= 0 || clusters <= 0 || cl <= 0 || os_parts < 2) return -1;
+  CoreParams p{};
+  p.num_m_tiles = num_m_super * cl; p.num_n_tiles = num_n_tiles; p.m_fastest = m_fastest;
+  p.batches = 1; p.splits = 1; p.os_first = os_first; p.os_parts = os_parts;
+  int64_t n = 0;
+  for (int cid = 0; cid < clusters; ++cid) {
+    TileWalker w;
+    w.init_ordered(p, num_m_super, cid, clusters);
+    for (; w.valid(); w.next()) {
+      const TileCoord tc = w.coord(p, cl, 0);
+      if (n < cap) {
+        int32_t* o = out + n * 6;
+        o[0] = w.o_i; o[1] = cid; o[2] = tc.m_tile; o[3] = tc.n_tile; o[4] = tc.kpart; o[5] = tc.kparts;
+      }
+      ++n;
+    }
+  }
+  return n;
+}
+
 /* fp32 GEMM whose tile count does not fill whole waves of the persistent grid: the tiles of the partial wave (or all
  * tiles when there are fewer tiles than clusters) are cut along K into parts that accumulate into C in a FIXED order
  * (part j waits for part j - 1 of its tile through the counters in `flags`), see CoreParams::os_*. */

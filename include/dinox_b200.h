@@ -169,6 +169,12 @@ DINOX_API int dinox_gemm_bf16(const void* A, const void* B, void* C, int64_t M, 
  * `flags`), so the result is run-to-run identical.  `flags` (dinox_gemm_bf16_balanced_workspace_bytes): zero before
  * the first launch, left zero by every launch; not to be shared by launches that may overlap. */
 DINOX_API size_t dinox_gemm_bf16_balanced_workspace_bytes(int64_t M, int64_t N);
+/* host-side views of that schedule (no GPU): the plan - tiles from `first` on are cut into `parts` K ranges, parts = 0:
+ * whole tiles only - and the (item, cluster, m_tile, n_tile, kpart, kparts) list the clusters walk; returns the
+ * number of items (out receives the first `cap`) or -1 */
+DINOX_API int dinox_plan_ordered_split(int64_t tiles, int64_t clusters, int64_t kblocks, int* first, int* parts);
+DINOX_API int64_t dinox_debug_walk_ordered(int num_m_super, int num_n_tiles, int m_fastest, int os_first,
+                                           int os_parts, int clusters, int cl, int32_t* out, int64_t cap);
 DINOX_API int dinox_gemm_bf16_balanced(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K,
                                        int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major,
                                        int accumulate, float alpha, const float* alpha_dev, const float* bias_n,

@@ -216,3 +216,71 @@ def test_precision_and_cache_switches_validate_their_arguments():
         losshead.set_weight_cache("sometimes")
     with pytest.raises(ValueError):
         losshead.DINOLoss(64, patch_teacher_mode="mean")
+
+
+def test_balanced_schedule_plan_and_item_walk():
+    """Host side of dinox_gemm_bf16_balanced (no GPU): the plan for the step's two big backward GEMMs, and for a range
+    of tile / cluster counts the item list the clusters walk - every whole tile once, every part of every cut tile
+    once, and the predecessor of a part (same tile, part - 1) always has a LOWER item number (what makes the ordered
+    accumulation deadlock free on a resident grid) and lives in the same or an earlier round."""
+    import ctypes
+    import numpy as np
+    from dinox_b200 import _ext
+    lib = _ext.lib()
+
+    def plan(tiles, clusters, kblocks):
+        first, parts = ctypes.c_int(-1), ctypes.c_int(-1)
+        assert lib.dinox_plan_ordered_split(tiles, clusters, kblocks, ctypes.byref(first), ctypes.byref(parts)) == 0
+        return first.value, parts.value
+
+    # dW2 at C2: 256 tile pairs, 74 CTA pairs, E = 8192 entries = 128 k-blocks -> the 34 tiles of the last wave in two
+    assert plan(256, 74, 128) == (222, 2)
+    # dH at C2: 32 tile pairs, K = 65536 prototypes = 1024 k-blocks -> every tile in 9 parts (288 items = 3.9 rounds)
+    assert plan(32, 74, 1024) == (0, 9)
+    assert plan(74, 74, 64)[1] == 0 and plan(148, 74, 64)[1] == 0          # whole waves: nothing to cut
+    assert plan(75, 74, 16)[1] == 0                                          # parts would be shorter than 32 k-blocks
+
+    for num_m, num_n, m_fastest, clusters, kblocks in [(256, 1, 0, 74, 128), (32, 1, 1, 74, 1024), (12, 3, 1, 74, 256),
+                                                       (100, 2, 0, 148, 96), (5, 1, 1, 7, 640), (1, 1, 1, 148, 128)]:
+        tiles = num_m * num_n
+        first, parts = plan(tiles, clusters, kblocks)
+        if parts < 2:
+            continue
+        total = first + (tiles - first) * parts
+        out = np.full((total + 8, 6), -7, dtype=np.int32)
+        n = lib.dinox_debug_walk_ordered(num_m, num_n, m_fastest, first, parts, clusters, 2,
+                                         out.ctypes.data_as(ctypes.c_void_p), out.shape[0])
+        assert n == total
+        items = out[:n]
+        assert sorted(items[:, 0].tolist()) == list(range(total))            # every item number exactly once
+        assert (items[:, 1] == items[:, 0] % clusters).all()                 # round-robin over the clusters
+        seen = {}
+        for item, cid, m_tile, n_tile, kpart, kparts in items.tolist():
+            assert m_tile % 2 == 0 and 0 <= m_tile // 2 < num_m and 0 <= n_tile < num_n
+            key = (m_tile, n_tile)
+            seen.setdefault(key, {})[kpart] = (item, kparts)
+        assert len(seen) == tiles
+        n_whole = 0
+        for key, ps in seen.items():
+            kparts = next(iter(ps.values()))[1]
+            assert sorted(ps) == list(range(kparts)) and all(v[1] == kparts for v in ps.values())
+            n_whole += kparts == 1
+            for j in range(1, kparts):
+                assert ps[j - 1][0] < ps[j][0]                               # predecessor has a lower item number
+                assert ps[j - 1][0] // clusters <= ps[j][0] // clusters      # ... same or earlier round
+        assert n_whole == first
+
+
+def test_loss_term_seeds_round_like_the_fanout_kernel():
+    """LossHeadStep seeds term i's backward with fp32((1 * 1/accum) * w_i) - the arithmetic of the scalar_fanout kernel of
+    combine_losses - so the decoupled and the summed backward agree bit for bit."""
+    import numpy as np
+    from dinox_b200.step import LossHeadStep
+    st = LossHeadStep.__new__(LossHeadStep)
+    st._seeds, st.device = {}, "cpu"
+    for accum in (1, 2, 3, 4, 7):
+        st.accum = accum
+        st._seeds.clear()
+        for w in (1.0, 0.5, 0.1, 3.0):
+            v = np.float32(np.float32(1.0) * np.float32(1.0 / accum)) * np.float32(w)
+            assert st._seed(w).item() == float(v)
