@@ -328,6 +328,8 @@ def hbm_kernel_table(dev, sh, hbm_peak: float, reps: int = 20):
         "cols_lse_teacher": (lambda: ops.cols_lse(t, 25.0, rowb), 4.0 * Mt * K + 4.0 * K),
         "cols_sum_teacher": (lambda: ops.cols_sum(t), 4.0 * Mt * K + 4.0 * K),
         "ce_fwd": (lambda: ops.ce_fwd(s, t, B, V, Vg, 10.0, 25.0, colb, rowb, lse_s, None, norm, True), 4.0 * (Ms + Mt) * K),
+        "ce_fwd_onepass": (lambda: ops.ce_fwd_onepass(s, t, B, V, Vg, 10.0, 25.0, colb, None, norm, True),
+                           4.0 * (Ms + Mt) * K),
         "ce_bwd": (lambda: ops.ce_bwd(s, t, B, V, Vg, 10.0, 25.0, colb, rowb, lse_s, None, norm, True, up),
                    4.0 * (2 * Ms + Mt) * K),
         "center_ema": (lambda: ops.center_ema_(center, colsum, Mt, 0.9), 12.0 * K),

@@ -136,6 +136,11 @@ SIGNATURES = {
     "dinox_ce_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_int, c_int, c_i64, c_i64, c_i64,
                              c_f32, c_f32, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_int,
                              c_void_p, c_void_p, c_void_p]),
+    "dinox_ce_onepass_max_views": (c_int, []),
+    "dinox_ce_onepass_workspace_bytes": (c_size, [c_i64, c_int, c_int, c_i64]),
+    "dinox_ce_fwd_onepass": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_int, c_int, c_i64, c_i64, c_i64,
+                                     c_f32, c_f32, c_void_p, c_void_p, c_f32, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dinox_ce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_int, c_int, c_i64, c_i64, c_i64,
                              c_f32, c_f32, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_int,
                              c_void_p, c_void_p, c_i64, c_void_p]),

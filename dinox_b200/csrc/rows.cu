@@ -76,32 +76,40 @@ __device__ __forceinline__ void loadf4(const float* p, int64_t k, int64_t K, flo
 // ---------------------------------------------------------------------------------------------
 // rows_lse: one CTA per row.  lse[i] = ln sum_k exp(u[i,k]),  entropy[i] = lse - sum_k p_k u_k
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool kVec>
-__global__ void __launch_bounds__(kRowThreads)
+// kThreads = 512 while all rows fit in one wave of 4 CTAs per SM, else 256 (8 CTAs per SM: 640 rows at 512 threads
+// were 1.08 waves - the second wave ran on 48 CTAs).  Two 16-byte loads per thread in flight.
+template <typename T, bool kVec, int kThreads>
+__global__ void __launch_bounds__(kThreads)
 rows_lse_kernel(const T* __restrict__ x, int64_t K, int64_t ld, float scale2 /* inv_tau*log2e */,
                 const float* __restrict__ colbias, float* __restrict__ lse, float* __restrict__ entropy) {
   __shared__ float red[64];
   const T* row = x + (int64_t)blockIdx.x * ld;
   float m = -INFINITY, s = 0.f, e = 0.f;
   const bool want_ent = entropy != nullptr;
-  for (int64_t k = (int64_t)threadIdx.x * 4; k < K; k += (int64_t)kRowThreads * 4) {
-    float v[4], cb[4];
-    load4<T, kVec>(row, k, K, v, 0.f);
-    loadf4<kVec>(colbias, k, K, cb, 0.f);
-    float u[4];
+  for (int64_t k = (int64_t)threadIdx.x * 4; k < K; k += (int64_t)kThreads * 8) {
+    const int64_t kb = k + (int64_t)kThreads * 4;
+    const bool hb = kb < K;
+    float va[4], vb[4], ca[4], cb[4];
+    load4<T, kVec>(row, k, K, va, 0.f);
+    if (hb) load4<T, kVec>(row, kb, K, vb, 0.f);
+    loadf4<kVec>(colbias, k, K, ca, 0.f);
+    if (hb) loadf4<kVec>(colbias, kb, K, cb, 0.f);
+    float u[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      u[j] = fmaf(v[j], scale2, -cb[j] * DINOX_LOG2E);
+      u[j] = fmaf(va[j], scale2, -ca[j] * DINOX_LOG2E);
       if (!kVec && k + j >= K) u[j] = -INFINITY;
+      u[4 + j] = hb ? fmaf(vb[j], scale2, -cb[j] * DINOX_LOG2E) : -INFINITY;
+      if (!kVec && kb + j >= K) u[4 + j] = -INFINITY;
     }
-    float mv = fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3]));
+    float mv = fmaxf(fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3])), fmaxf(fmaxf(u[4], u[5]), fmaxf(u[6], u[7])));
     float mn = fmaxf(m, mv);
     if (mn == -INFINITY) continue;
     float r = exp2f(m - mn);  // m == -inf -> 0
     s *= r;
     e *= r;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       float p = exp2f(u[j] - mn);
       s += p;
       if (want_ent) e += (u[j] == -INFINITY) ? 0.f : p * u[j];
@@ -110,10 +118,10 @@ rows_lse_kernel(const T* __restrict__ x, int64_t K, int64_t ld, float scale2 /* 
   }
   // block combine
   MaxSum ms{m, s};
-  MaxSum tot = block_maxsum<kRowThreads>(ms, red);
+  MaxSum tot = block_maxsum<kThreads>(ms, red);
   if (want_ent) {
     float escaled = (m == -INFINITY) ? 0.f : e * exp2f(m - tot.m);
-    float etot = block_sum<kRowThreads>(escaled, red);
+    float etot = block_sum<kThreads>(escaled, red);
     if (threadIdx.x == 0) {
       float l2 = tot.m + log2f(tot.s);
       entropy[blockIdx.x] = DINOX_LN2 * (l2 - etot / tot.s);
@@ -349,6 +357,9 @@ __global__ void axpby_kernel(const float* __restrict__ x, float alpha, const flo
 // cross-entropy forward / backward over groups x K-splits
 // ---------------------------------------------------------------------------------------------
 constexpr int kCeThreads = 256;
+// resident CTAs per SM the kernels are compiled for (register caps 85 / 64 / 128): the K-split is chosen against
+// these so that the grid fills whole waves
+constexpr int kCeFwdCtasPerSm = 3, kCeBwdCtasPerSm = 4, kOnePassCtasPerSm = 2;
 
 struct CeArgs {
   int64_t groups, K, ld_s, ld_t, ld_g;
@@ -362,7 +373,7 @@ struct CeArgs {
 };
 
 template <typename TS, typename TT, bool kVec>
-__global__ void __launch_bounds__(kCeThreads)
+__global__ void __launch_bounds__(kCeThreads, kCeFwdCtasPerSm)
 ce_fwd_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, CeArgs a,
               float* __restrict__ partial /* [groups][ksplit][Vg][2] */) {
   __shared__ float red[64];
@@ -465,8 +476,212 @@ ce_finalize_kernel(const float* __restrict__ partial, CeArgs a, float inv_tau_s,
   if (threadIdx.x == 0) *loss_out = tot * a.norm;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cross-entropy forward in ONE pass over the logits (softmax-centred teacher): the student LSEs, the teacher
+// LSEs and the cross terms sum_k 2^(u_t[k]) * s[k] are all accumulated online (running maximum + rescale) while
+// every logit is read exactly once - DINOLoss.forward (scripts/phase5_big_run.py:703-717) without the separate
+// softmax / log_softmax passes.  The LSEs come out as by-products for the backward kernel.
+//   partial[g][split][ q < Vg : (m, z, c) | v < V : (m, s) ]   all in log2 units, merged in split order
+// ---------------------------------------------------------------------------------------------
+constexpr int kOnePassMaxViews = 12;
+
+// (max, sum, cross) of one row across the warp: rescale to the common maximum, then plain sums
+__device__ __forceinline__ void warp_merge3(float& m, float& z, float& c) {
+  const float M = warp_max(m);
+  const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
+  z = warp_sum(z * sc);
+  c = warp_sum(c * sc);
+  m = M;
+}
+
+template <typename TS, typename TT, bool kVec, int kMaxV>
+__global__ void __launch_bounds__(kCeThreads, kMaxV <= 4 ? kCeFwdCtasPerSm : kOnePassCtasPerSm)
+ce_fwd_onepass_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, CeArgs a,
+                      float* __restrict__ partial /* [groups][ksplit][3 Vg + 2 V] */) {
+  static_assert(kMaxV % 4 == 0 && kMaxV >= kMaxGlobalViews, "views are walked four at a time");
+  constexpr int kWarps = kCeThreads / 32;
+  constexpr int kVals = 3 * kMaxGlobalViews + 2 * kMaxV;
+  __shared__ float red[kWarps][kVals];
+  const int64_t g = blockIdx.x;
+  const int split = blockIdx.y;
+  const int64_t per = ((a.K + a.ksplit - 1) / a.ksplit + 3) & ~int64_t(3);
+  const int64_t k0 = split * per, k1 = (k0 + per < a.K) ? k0 + per : a.K;
+  float tm[kMaxGlobalViews], tz[kMaxGlobalViews], tc[kMaxGlobalViews];
+#pragma unroll
+  for (int q = 0; q < kMaxGlobalViews; ++q) { tm[q] = -INFINITY; tz[q] = 0.f; tc[q] = 0.f; }
+  float sm[kMaxV], ss[kMaxV];
+#pragma unroll
+  for (int v = 0; v < kMaxV; ++v) { sm[v] = -INFINITY; ss[v] = 0.f; }
+
+  for (int64_t k = k0 + (int64_t)threadIdx.x * 4; k < k1; k += (int64_t)kCeThreads * 4) {
+    float cb[4];
+    loadf4<kVec>(a.colbias_t, k, k1, cb, 0.f);
+    float tu[kMaxGlobalViews][4];
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) {
+        float t[4];
+        load4<TT, kVec>(teacher + (q * a.groups + g) * a.ld_t, k, k1, t, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          tu[q][j] = (!kVec && k + j >= k1) ? -INFINITY : fmaf(t[j], a.t2, -cb[j] * DINOX_LOG2E);
+      }
+    }
+    float stot[4] = {0.f, 0.f, 0.f, 0.f};
+    float sown[kMaxGlobalViews][4];
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) { sown[q][0] = sown[q][1] = sown[q][2] = sown[q][3] = 0.f; }
+#pragma unroll
+    for (int v0 = 0; v0 < kMaxV; v0 += 4) {
+      float s[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {   // four row loads in flight
+        if (v0 + u < a.V) load4<TS, kVec>(student + ((v0 + u) * a.groups + g) * a.ld_s, k, k1, s[u], 0.f);
+        else { s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.f; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u;
+        if (v < a.V) {
+          float x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            stot[j] += s[u][j];
+            x[j] = (!kVec && k + j >= k1) ? -INFINITY : s[u][j] * a.s2;
+          }
+          if (v < kMaxGlobalViews) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sown[v < kMaxGlobalViews ? v : 0][j] = s[u][j];
+          }
+          const float mn = fmaxf(sm[v], fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
+          if (mn != -INFINITY) {
+            float acc = ss[v] * exp2f(sm[v] - mn);   // first chunk: 0 * 2^-inf = 0
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc += exp2f(x[j] - mn);
+            ss[v] = acc;
+            sm[v] = mn;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) {
+        const float mn = fmaxf(tm[q], fmaxf(fmaxf(tu[q][0], tu[q][1]), fmaxf(tu[q][2], tu[q][3])));
+        if (mn != -INFINITY) {
+          const float r = exp2f(tm[q] - mn);
+          float z = tz[q] * r, c = tc[q] * r;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float other = a.exclude_same ? (stot[j] - sown[q][j]) : stot[j];
+            const float p = exp2f(tu[q][j] - mn);
+            z += p;
+            c = fmaf(p, other, c);
+          }
+          tz[q] = z; tc[q] = c; tm[q] = mn;
+        }
+      }
+    }
+  }
+  // block merge: warp shuffles, then one thread per row walks the warps in order
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < kMaxGlobalViews; ++q) {
+    if (q < a.Vg) {
+      warp_merge3(tm[q], tz[q], tc[q]);
+      if (lane == 0) { red[w][3 * q] = tm[q]; red[w][3 * q + 1] = tz[q]; red[w][3 * q + 2] = tc[q]; }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < kMaxV; ++v) {
+    if (v < a.V) {
+      float dummy = 0.f;
+      warp_merge3(sm[v], ss[v], dummy);
+      if (lane == 0) { red[w][3 * kMaxGlobalViews + 2 * v] = sm[v]; red[w][3 * kMaxGlobalViews + 2 * v + 1] = ss[v]; }
+    }
+  }
+  __syncthreads();
+  float* out = partial + ((int64_t)g * a.ksplit + split) * (3 * a.Vg + 2 * a.V);
+  const int t = threadIdx.x;
+  if (t < a.Vg) {
+    float M = -INFINITY;
+    for (int i = 0; i < kWarps; ++i) M = fmaxf(M, red[i][3 * t]);
+    float z = 0.f, c = 0.f;
+    for (int i = 0; i < kWarps; ++i) {
+      const float m = red[i][3 * t];
+      const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
+      z += red[i][3 * t + 1] * sc;
+      c += red[i][3 * t + 2] * sc;
+    }
+    out[3 * t] = M; out[3 * t + 1] = z; out[3 * t + 2] = c;
+  } else if (t >= 32 && t < 32 + a.V) {
+    const int v = t - 32;
+    float M = -INFINITY;
+    for (int i = 0; i < kWarps; ++i) M = fmaxf(M, red[i][3 * kMaxGlobalViews + 2 * v]);
+    float s = 0.f;
+    for (int i = 0; i < kWarps; ++i) {
+      const float m = red[i][3 * kMaxGlobalViews + 2 * v];
+      s += red[i][3 * kMaxGlobalViews + 2 * v + 1] * ((m == -INFINITY) ? 0.f : exp2f(m - M));
+    }
+    out[3 * a.Vg + 2 * v] = M; out[3 * a.Vg + 2 * v + 1] = s;
+  }
+}
+
+// one CTA: merges the K-splits of every group in split order, writes the natural-log LSEs of all rows (the backward
+// kernel's inputs) and the loss; fixed summation order => deterministic
+__global__ void __launch_bounds__(1024)
+ce_onepass_finalize_kernel(const float* __restrict__ partial, CeArgs a, float inv_tau_s, float* __restrict__ loss_out,
+                           float* __restrict__ lse_s_out, float* __restrict__ rowbias_t_out) {
+  __shared__ float red[64];
+  const int stride = 3 * a.Vg + 2 * a.V;
+  float acc = 0.f;
+  for (int64_t g = threadIdx.x; g < a.groups; g += 1024) {
+    const float* pg = partial + g * a.ksplit * stride;
+    float lse_tot = 0.f, lse_own[kMaxGlobalViews];
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) lse_own[q] = 0.f;
+    for (int v = 0; v < a.V; ++v) {
+      float M = -INFINITY;
+      for (int sp = 0; sp < a.ksplit; ++sp) M = fmaxf(M, pg[sp * stride + 3 * a.Vg + 2 * v]);
+      float s = 0.f;
+      for (int sp = 0; sp < a.ksplit; ++sp) {
+        const float m = pg[sp * stride + 3 * a.Vg + 2 * v];
+        s += pg[sp * stride + 3 * a.Vg + 2 * v + 1] * ((m == -INFINITY) ? 0.f : exp2f(m - M));
+      }
+      const float lse = DINOX_LN2 * (M + log2f(s));
+      lse_s_out[v * a.groups + g] = lse;
+      lse_tot += lse;
+#pragma unroll
+      for (int q = 0; q < kMaxGlobalViews; ++q)
+        if (q == v) lse_own[q] = lse;
+    }
+    float lg = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) {
+        float M = -INFINITY;
+        for (int sp = 0; sp < a.ksplit; ++sp) M = fmaxf(M, pg[sp * stride + 3 * q]);
+        float z = 0.f, c = 0.f;
+        for (int sp = 0; sp < a.ksplit; ++sp) {
+          const float m = pg[sp * stride + 3 * q];
+          const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
+          z += pg[sp * stride + 3 * q + 1] * sc;
+          c += pg[sp * stride + 3 * q + 2] * sc;
+        }
+        rowbias_t_out[q * a.groups + g] = DINOX_LN2 * (M + log2f(z));
+        // sum over the pairs of this teacher view of [ lse_v - (1/tau_s) sum_k q[k] s_v[k] ], q = 2^(u - M) / z
+        const float lse_sum = a.exclude_same ? lse_tot - lse_own[q] : lse_tot;
+        lg += lse_sum - (c / z) * inv_tau_s;
+      }
+    }
+    acc += lg * (a.group_w ? a.group_w[g] : 1.f);
+  }
+  const float tot = block_sum<1024>(acc, red);
+  if (threadIdx.x == 0) *loss_out = tot * a.norm;
+}
+
 template <typename TS, typename TT, bool kVec>
-__global__ void __launch_bounds__(kCeThreads)
+__global__ void __launch_bounds__(kCeThreads, kCeBwdCtasPerSm)
 ce_bwd_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, CeArgs a,
               const float* __restrict__ upstream, TS* __restrict__ grad) {
   const int64_t g = blockIdx.x;
@@ -497,28 +712,43 @@ ce_bwd_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, Ce
         }
       }
     }
-    for (int v = 0; v < a.V; ++v) {
-      float s[4], o[4];
-      const int64_t r = v * a.groups + g;
-      load4<TS, kVec>(student + r * a.ld_s, k, k1, s, 0.f);
-      const float lse2 = a.lse_s[r] * DINOX_LOG2E;
-      const bool own = a.exclude_same && v < a.Vg;
-      const float nq = (float)(a.Vg - (own ? 1 : 0));
+    for (int v0 = 0; v0 < a.V; v0 += 4) {   // four student rows in flight per thread
+      float s4[4][4], lse2[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float p = exp2f(fmaf(s[j], a.s2, -lse2));
-        float target = qtot[j];
-#pragma unroll
-        for (int q = 0; q < kMaxGlobalViews; ++q)
-          if (own && q == v) target -= qv[q][j];
-        o[j] = w * (nq * p - target);
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = (v0 + u) * a.groups + g;
+        if (v0 + u < a.V) {
+          load4<TS, kVec>(student + r * a.ld_s, k, k1, s4[u], 0.f);
+          lse2[u] = a.lse_s[r] * DINOX_LOG2E;
+        } else {
+          s4[u][0] = s4[u][1] = s4[u][2] = s4[u][3] = 0.f;
+          lse2[u] = 0.f;
+        }
       }
-      if (kVec) {
-        Vec4<TS>::store(grad + r * a.ld_g + k, o);
-      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (k + j < k1) grad[r * a.ld_g + k + j] = from_f32<TS>(o[j]);
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u;
+        if (v >= a.V) break;
+        const int64_t r = v * a.groups + g;
+        const bool own = a.exclude_same && v < a.Vg;
+        const float nq = (float)(a.Vg - (own ? 1 : 0));
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float p = exp2f(fmaf(s4[u][j], a.s2, -lse2[u]));
+          float target = qtot[j];
+#pragma unroll
+          for (int q = 0; q < kMaxGlobalViews; ++q)
+            if (own && q == v) target -= qv[q][j];
+          o[j] = w * (nq * p - target);
+        }
+        if (kVec) {
+          Vec4<TS>::store(grad + r * a.ld_g + k, o);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (k + j < k1) grad[r * a.ld_g + k + j] = from_f32<TS>(o[j]);
+        }
       }
     }
   }
@@ -533,15 +763,24 @@ static inline bool vec_ok(const void* p, int dtype, int64_t K, int64_t ld) {
 }
 static inline bool fvec_ok(const float* p) { return p == nullptr || aligned16(p); }
 
-static int pick_ksplit(int64_t groups, int64_t K) {
-  int target = 2 * num_sms();
-  int64_t ks = (target + groups - 1) / groups;
+// K-split of the (groups x splits) grids: the smallest split count whose grid fills whole waves of the resident CTAs
+// best (at most 4 waves; each split keeps >= 1024 prototypes).  A fixed "2 CTAs per SM" target left 3/4 of the
+// machine's threads unused (ce_fwd 2.3 TB/s, ce_bwd 2.9 TB/s at the C2 shapes); a fixed 8 per SM ran 2.05 waves.
+static int pick_ksplit(int64_t groups, int64_t K, int ctas_per_sm) {
+  const int64_t resident = (int64_t)num_sms() * ctas_per_sm;
   int64_t maxs = K / 1024;
   if (maxs < 1) maxs = 1;
-  if (ks > maxs) ks = maxs;
-  if (ks < 1) ks = 1;
-  if (ks > 64) ks = 64;
-  return (int)ks;
+  if (maxs > 64) maxs = 64;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int64_t ks = 1; ks <= maxs; ++ks) {
+    const int64_t total = groups * ks;
+    const int64_t waves = (total + resident - 1) / resident;
+    if (waves > 4 && ks > 1) break;
+    const double eff = (double)total / (double)(waves * resident);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = (int)ks; }
+  }
+  return best;
 }
 
 #define DISPATCH_T(dtype, T, ...)                                  \
@@ -566,9 +805,15 @@ int dinox_rows_lse(const void* x, int dtype, int64_t rows, int64_t K, int64_t ld
   DINOX_REQUIRE(rows < (1ll << 31), DINOX_E_BADARG, "rows_lse: too many rows");
   const bool vec = vec_ok(x, dtype, K, ld) && fvec_ok(colbias);
   const float s2 = inv_tau * DINOX_LOG2E;
+  const bool one_wave = rows * kRowThreads <= (int64_t)num_sms() * 2048;
   DISPATCH_T(dtype, T, {
-    if (vec) rows_lse_kernel<T, true><<<(unsigned)rows, kRowThreads, 0, stream>>>((const T*)x, K, ld, s2, colbias, lse, entropy);
-    else rows_lse_kernel<T, false><<<(unsigned)rows, kRowThreads, 0, stream>>>((const T*)x, K, ld, s2, colbias, lse, entropy);
+    if (one_wave) {
+      if (vec) rows_lse_kernel<T, true, kRowThreads><<<(unsigned)rows, kRowThreads, 0, stream>>>((const T*)x, K, ld, s2, colbias, lse, entropy);
+      else rows_lse_kernel<T, false, kRowThreads><<<(unsigned)rows, kRowThreads, 0, stream>>>((const T*)x, K, ld, s2, colbias, lse, entropy);
+    } else {
+      if (vec) rows_lse_kernel<T, true, 256><<<(unsigned)rows, 256, 0, stream>>>((const T*)x, K, ld, s2, colbias, lse, entropy);
+      else rows_lse_kernel<T, false, 256><<<(unsigned)rows, 256, 0, stream>>>((const T*)x, K, ld, s2, colbias, lse, entropy);
+    }
   });
   return check_launch("rows_lse_kernel", stream);
 }
@@ -708,7 +953,7 @@ size_t dinox_ce_workspace_bytes(int64_t groups, int64_t K) {
 static int ce_args(CeArgs& a, const void* student, const void* teacher, int64_t groups, int V, int Vg,
                    int64_t K, int64_t ld_s, int64_t ld_t, float inv_tau_s, float inv_tau_t,
                    const float* colbias_t, const float* rowbias_t, const float* lse_s,
-                   const float* group_w, float norm, int exclude_same) {
+                   const float* group_w, float norm, int exclude_same, int ctas_per_sm) {
   DINOX_REQUIRE(student && teacher && rowbias_t && lse_s, DINOX_E_BADARG, "ce: null pointer");
   DINOX_REQUIRE(groups > 0 && K > 0 && V >= 1 && Vg >= 1 && Vg <= kMaxGlobalViews && Vg <= V,
                 DINOX_E_BADARG, "ce: need groups>0, K>0, 1<=Vg<=%d, Vg<=V (got groups=%lld V=%d Vg=%d)",
@@ -717,7 +962,7 @@ static int ce_args(CeArgs& a, const void* student, const void* teacher, int64_t 
   DINOX_REQUIRE(groups < (1ll << 31), DINOX_E_BADARG, "ce: too many groups");
   a.groups = groups; a.K = K; a.ld_s = ld_s; a.ld_t = ld_t; a.ld_g = ld_s;
   a.V = V; a.Vg = Vg; a.exclude_same = exclude_same ? 1 : 0;
-  a.ksplit = pick_ksplit(groups, K);
+  a.ksplit = pick_ksplit(groups, K, ctas_per_sm);
   a.s2 = inv_tau_s * DINOX_LOG2E; a.t2 = inv_tau_t * DINOX_LOG2E;
   a.colbias_t = colbias_t; a.rowbias_t = rowbias_t; a.lse_s = lse_s; a.group_w = group_w; a.norm = norm;
   return require_sm100();
@@ -730,7 +975,7 @@ int dinox_ce_fwd(const void* student, int s_dtype, const void* teacher, int t_dt
                  dinox_stream_t stream) {
   CeArgs a;
   int rc = ce_args(a, student, teacher, groups, V, Vg, K, ld_s, ld_t, inv_tau_s, inv_tau_t, colbias_t,
-                   rowbias_t, lse_s, group_w, norm, exclude_same);
+                   rowbias_t, lse_s, group_w, norm, exclude_same, kCeFwdCtasPerSm);
   if (rc) return rc;
   DINOX_REQUIRE(loss_out && workspace, DINOX_E_BADARG, "ce_fwd: null output/workspace");
   const bool vec = vec_ok(student, s_dtype, K, ld_s) && vec_ok(teacher, t_dtype, K, ld_t) && fvec_ok(colbias_t);
@@ -746,6 +991,42 @@ int dinox_ce_fwd(const void* student, int s_dtype, const void* teacher, int t_dt
   return check_launch("ce_finalize_kernel", stream);
 }
 
+int dinox_ce_onepass_max_views(void) { return kOnePassMaxViews; }
+
+size_t dinox_ce_onepass_workspace_bytes(int64_t groups, int V, int Vg, int64_t K) {
+  if (groups <= 0 || K <= 0 || V < 1 || Vg < 1) return 0;
+  return (size_t)groups * 64 * (size_t)(3 * Vg + 2 * V) * sizeof(float);
+}
+
+int dinox_ce_fwd_onepass(const void* student, int s_dtype, const void* teacher, int t_dtype, int64_t groups,
+                         int V, int Vg, int64_t K, int64_t ld_s, int64_t ld_t, float inv_tau_s, float inv_tau_t,
+                         const float* colbias_t, const float* group_w, float norm, int exclude_same,
+                         float* loss_out, float* lse_s_out, float* rowbias_t_out, void* workspace,
+                         dinox_stream_t stream) {
+  CeArgs a;
+  DINOX_REQUIRE(lse_s_out && rowbias_t_out, DINOX_E_BADARG, "ce_fwd_onepass: null LSE outputs");
+  int rc = ce_args(a, student, teacher, groups, V, Vg, K, ld_s, ld_t, inv_tau_s, inv_tau_t, colbias_t,
+                   rowbias_t_out, lse_s_out, group_w, norm, exclude_same, V <= 4 ? kCeFwdCtasPerSm : kOnePassCtasPerSm);
+  if (rc) return rc;
+  DINOX_REQUIRE(V <= kOnePassMaxViews, DINOX_E_BADARG, "ce_fwd_onepass: V=%d views > %d (use dinox_rows_lse + dinox_ce_fwd)",
+                V, kOnePassMaxViews);
+  DINOX_REQUIRE(loss_out && workspace, DINOX_E_BADARG, "ce_fwd_onepass: null output/workspace");
+  const bool vec = vec_ok(student, s_dtype, K, ld_s) && vec_ok(teacher, t_dtype, K, ld_t) && fvec_ok(colbias_t);
+  dim3 grid((unsigned)groups, (unsigned)a.ksplit);
+  float* partial = (float*)workspace;
+#define DINOX_ONEPASS_LAUNCH(MAXV)                                                                                          \
+  DISPATCH_T(s_dtype, TS, DISPATCH_T(t_dtype, TT, {                                                                         \
+    if (vec) ce_fwd_onepass_kernel<TS, TT, true, MAXV><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, partial); \
+    else ce_fwd_onepass_kernel<TS, TT, false, MAXV><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, partial);    \
+  }))
+  if (V <= 4) { DINOX_ONEPASS_LAUNCH(4); } else { DINOX_ONEPASS_LAUNCH(kOnePassMaxViews); }
+#undef DINOX_ONEPASS_LAUNCH
+  rc = check_launch("ce_fwd_onepass_kernel", stream);
+  if (rc) return rc;
+  ce_onepass_finalize_kernel<<<1, 1024, 0, stream>>>(partial, a, inv_tau_s, loss_out, lse_s_out, rowbias_t_out);
+  return check_launch("ce_onepass_finalize_kernel", stream);
+}
+
 int dinox_ce_bwd(const void* student, int s_dtype, const void* teacher, int t_dtype, int64_t groups,
                  int V, int Vg, int64_t K, int64_t ld_s, int64_t ld_t, float inv_tau_s, float inv_tau_t,
                  const float* colbias_t, const float* rowbias_t, const float* lse_s,
@@ -753,7 +1034,7 @@ int dinox_ce_bwd(const void* student, int s_dtype, const void* teacher, int t_dt
                  int64_t ld_g, dinox_stream_t stream) {
   CeArgs a;
   int rc = ce_args(a, student, teacher, groups, V, Vg, K, ld_s, ld_t, inv_tau_s, inv_tau_t, colbias_t,
-                   rowbias_t, lse_s, group_w, norm, exclude_same);
+                   rowbias_t, lse_s, group_w, norm, exclude_same, kCeBwdCtasPerSm);
   if (rc) return rc;
   DINOX_REQUIRE(upstream && grad && ld_g >= K, DINOX_E_BADARG, "ce_bwd: null upstream/grad or ld_g < K");
   a.ld_g = ld_g;

@@ -130,6 +130,42 @@ class _RowCE(torch.autograd.Function):
         return (grad,) + (None,) * 12
 
 
+class _RowCEOnePass(torch.autograd.Function):
+    """Softmax-centred teacher: loss, student LSEs and teacher LSEs from ONE pass over the logits
+    (`dinox_ce_fwd_onepass`); the backward is the same kernel as `_RowCE`."""
+
+    @staticmethod
+    def forward(ctx, student, teacher, colbias_t, group_w, groups, V, Vg, inv_ts, inv_tt, norm, exclude_same):
+        loss, lse_s, rowbias_t = ops.ce_fwd_onepass(student, teacher, groups, V, Vg, inv_ts, inv_tt, colbias_t,
+                                                    group_w, norm, exclude_same)
+        ctx.save_for_backward(student, teacher, colbias_t, rowbias_t, lse_s, group_w)
+        ctx.cfg = (groups, V, Vg, inv_ts, inv_tt, norm, exclude_same)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        student, teacher, colbias_t, rowbias_t, lse_s, group_w = ctx.saved_tensors
+        groups, V, Vg, inv_ts, inv_tt, norm, exclude_same = ctx.cfg
+        grad = ops.ce_bwd(student, teacher, groups, V, Vg, inv_ts, inv_tt, colbias_t, rowbias_t, lse_s, group_w,
+                          norm, exclude_same, g)
+        return (grad,) + (None,) * 10
+
+
+# DINOLoss.forward on materialised logits with the softmax-centred teacher: "onepass" (default) reads every logit once
+# in the forward (dinox_ce_fwd_onepass); "passes" is the three-pass form (teacher LSE, student LSE, cross-entropy)
+# that the Sinkhorn-Knopp teacher and V > 12 views always take.  DINOX_CE_FORWARD overrides at import.
+_CE_FORWARD = [os.environ.get("DINOX_CE_FORWARD", "onepass")]
+
+
+def set_ce_forward(mode: str) -> str:
+    """Selects the forward of `DINOLoss` on materialised logits ("onepass" or "passes"); returns the previous mode."""
+    if mode not in ("onepass", "passes"):
+        raise ValueError(f"ce forward mode {mode!r}: expected 'onepass' or 'passes'")
+    prev = _CE_FORWARD[0]
+    _CE_FORWARD[0] = mode
+    return prev
+
+
 def _as_rows(t: torch.Tensor) -> torch.Tensor:
     if not t.is_cuda:
         raise _ext.DinoxError("dinox_b200: CUDA tensors required (no CPU fallback)")
@@ -193,12 +229,18 @@ class DINOLoss(nn.Module):
         V = s.shape[0] // B
         if self.n_local and V != Vg + self.n_local:
             raise ValueError(f"student rows imply {V} views, expected {Vg + self.n_local}")
-        with torch.no_grad():
-            colbias, rowbias = self.teacher_biases(t, teacher_temp)
-            lse_s = ops.rows_lse(s.detach(), 1.0 / student_temp)
         n_terms = Vg * V - Vg
-        loss = _RowCE.apply(s, t, colbias, rowbias, lse_s, None, B, V, Vg, 1.0 / student_temp, 1.0 / teacher_temp,
-                            1.0 / (n_terms * B), True)
+        if self.teacher_mode == "center" and _CE_FORWARD[0] == "onepass" and V <= ops.ce_onepass_max_views():
+            with torch.no_grad():
+                colbias = ops.axpb(self.center.reshape(-1), 1.0 / teacher_temp)
+            loss = _RowCEOnePass.apply(s, t, colbias, None, B, V, Vg, 1.0 / student_temp, 1.0 / teacher_temp,
+                                       1.0 / (n_terms * B), True)
+        else:
+            with torch.no_grad():
+                colbias, rowbias = self.teacher_biases(t, teacher_temp)
+                lse_s = ops.rows_lse(s.detach(), 1.0 / student_temp)
+            loss = _RowCE.apply(s, t, colbias, rowbias, lse_s, None, B, V, Vg, 1.0 / student_temp, 1.0 / teacher_temp,
+                                1.0 / (n_terms * B), True)
         if self.teacher_mode == "center":
             self.update_center(t)
         return loss

@@ -170,6 +170,27 @@ def ce_fwd(student, teacher, groups: int, V: int, Vg: int, inv_tau_s: float, inv
     return loss
 
 
+def ce_onepass_max_views() -> int:
+    return int(_ext.lib().dinox_ce_onepass_max_views())
+
+
+def ce_fwd_onepass(student, teacher, groups: int, V: int, Vg: int, inv_tau_s: float, inv_tau_t: float,
+                   colbias_t, group_w, norm: float, exclude_same: bool):
+    """Cross-entropy forward with a softmax-centred teacher in ONE pass over the logits.  Returns
+    (loss, lse_s (V*groups), rowbias_t (Vg*groups)); the two LSE vectors are what `ce_bwd` needs."""
+    _chk_cuda(student, teacher, colbias_t, group_w)
+    K = student.shape[1]
+    dev = student.device
+    ws = torch.empty(int(_ext.lib().dinox_ce_onepass_workspace_bytes(groups, V, Vg, K)), dtype=torch.uint8, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    lse_s = torch.empty(V * groups, dtype=torch.float32, device=dev)
+    rowbias_t = torch.empty(Vg * groups, dtype=torch.float32, device=dev)
+    _ext.call("dinox_ce_fwd_onepass", _p(student), DT[student.dtype], _p(teacher), DT[teacher.dtype], groups, V, Vg, K,
+              _rowmajor(student), _rowmajor(teacher), float(inv_tau_s), float(inv_tau_t), _p(colbias_t), _p(group_w),
+              float(norm), int(exclude_same), _p(loss), _p(lse_s), _p(rowbias_t), _p(ws), _stream())
+    return loss, lse_s, rowbias_t
+
+
 def ce_bwd(student, teacher, groups: int, V: int, Vg: int, inv_tau_s: float, inv_tau_t: float,
            colbias_t, rowbias_t, lse_s, group_w, norm: float, exclude_same: bool,
            upstream: torch.Tensor) -> torch.Tensor:

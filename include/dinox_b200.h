@@ -139,6 +139,21 @@ DINOX_API int dinox_ce_fwd(const void* student, int s_dtype, const void* teacher
                            const float* rowbias_t, const float* lse_s, const float* group_w,
                            float norm, int exclude_same, float* loss_out, void* workspace,
                            dinox_stream_t stream);
+/* The same loss with a softmax-centred teacher, every logit read ONCE: softmax((t - c)/tau_t) and
+ * log_softmax(s/tau_s) of scripts/phase5_big_run.py:703-706 are never formed - the row LSEs and the cross terms
+ * sum_k exp(ut[k]) s[k] are accumulated online (running maximum + rescale) in the pass that reads the logits,
+ * merged over K-splits in a fixed order.  By-products for dinox_ce_bwd: lse_s_out (V*groups) = ln sum_k exp(us),
+ * rowbias_t_out (Vg*groups) = ln sum_k exp(t*inv_tau_t - colbias_t) (so q sums to 1 per row).  V <=
+ * dinox_ce_onepass_max_views(); more views (or a Sinkhorn-Knopp teacher, whose row offsets are inputs) take
+ * dinox_rows_lse + dinox_ce_fwd.  workspace: dinox_ce_onepass_workspace_bytes(groups, V, Vg, K) bytes. */
+DINOX_API int dinox_ce_onepass_max_views(void);
+DINOX_API size_t dinox_ce_onepass_workspace_bytes(int64_t groups, int V, int Vg, int64_t K);
+DINOX_API int dinox_ce_fwd_onepass(const void* student, int s_dtype, const void* teacher, int t_dtype,
+                                   int64_t groups, int V, int Vg, int64_t K, int64_t ld_s, int64_t ld_t,
+                                   float inv_tau_s, float inv_tau_t, const float* colbias_t,
+                                   const float* group_w, float norm, int exclude_same, float* loss_out,
+                                   float* lse_s_out, float* rowbias_t_out, void* workspace,
+                                   dinox_stream_t stream);
 /* grad[v,g,k] = (*upstream) * norm * w[g] * inv_tau_s * ( n_q(v) * softmax(us)[k] - sum_{iq} q[iq,g,k] )
  * written in the student's dtype (autograd of log_softmax(s/tau), :706). upstream: device fp32. */
 DINOX_API int dinox_ce_bwd(const void* student, int s_dtype, const void* teacher, int t_dtype,

@@ -20,6 +20,7 @@ ps = [torch.randn(n_params // 8, device=dev) for _ in range(8)]; pt = [torch.ran
 plan = ops.EmaPlan(ps, pt)
 for fn in (lambda: ops.rows_lse(s, 10.0), lambda: ops.rows_lse(t, 25.0, colb), lambda: ops.cols_lse(t, 25.0, rowb),
            lambda: ops.cols_sum(t), lambda: ops.ce_fwd(s, t, B, V, Vg, 10.0, 25.0, colb, rowb, lse_s, None, norm, True),
+           lambda: ops.ce_fwd_onepass(s, t, B, V, Vg, 10.0, 25.0, colb, None, norm, True),
            lambda: ops.ce_bwd(s, t, B, V, Vg, 10.0, 25.0, colb, rowb, lse_s, None, norm, True, up),
            lambda: ops.center_ema_(center, colsum, Mt, 0.9), lambda: losshead.sinkhorn_knopp_biases(t, 0.04, 3, None),
            lambda: plan.apply(0.996)):
