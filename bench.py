@@ -303,7 +303,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # HBM-bound kernels of the materialised-logit path (DINOLoss drop-in, Sinkhorn-Knopp, centre EMA): achieved GB/s
 # ---------------------------------------------------------------------------------------------------
-def hbm_kernel_table(dev, sh, hbm_peak: float, reps: int = 20):
+def hbm_kernel_table(dev, sh, hbm_peak: float, reps: int = 20, only=None):
     """CUDA-event medians of the row / column reduction kernels at this config's logit shapes, each launched on
     a cold L2 (a 512 MB buffer is rewritten between calls), with their ALGORITHMIC bytes (every logit read once
     per pass, fp32) -> GB/s and fraction of the measured HBM copy bandwidth.  Shapes at C2: student 640 x 65536,
@@ -337,6 +337,8 @@ def hbm_kernel_table(dev, sh, hbm_peak: float, reps: int = 20):
     }
     out = {}
     for name, (fn, nbytes) in cases.items():
+        if only and name not in only:
+            continue
         fn()
         ts = []
         for _ in range(reps):

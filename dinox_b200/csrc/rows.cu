@@ -5,6 +5,7 @@
 // units (one FFMA + one MUFU.EX2 per element), warp-shuffle + shared-memory block reductions in
 // a fixed order (deterministic; no fp32 atomics).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace dinox {
 
@@ -86,30 +87,39 @@ rows_lse_kernel(const T* __restrict__ x, int64_t K, int64_t ld, float scale2 /* 
   const T* row = x + (int64_t)blockIdx.x * ld;
   float m = -INFINITY, s = 0.f, e = 0.f;
   const bool want_ent = entropy != nullptr;
-  for (int64_t k = (int64_t)threadIdx.x * 4; k < K; k += (int64_t)kThreads * 8) {
-    const int64_t kb = k + (int64_t)kThreads * 4;
-    const bool hb = kb < K;
-    float va[4], vb[4], ca[4], cb[4];
-    load4<T, kVec>(row, k, K, va, 0.f);
-    if (hb) load4<T, kVec>(row, kb, K, vb, 0.f);
-    loadf4<kVec>(colbias, k, K, ca, 0.f);
-    if (hb) loadf4<kVec>(colbias, kb, K, cb, 0.f);
-    float u[8];
+  constexpr int kU = 2;   // 16-byte loads in flight per thread (four need 60 registers: 640 rows no longer fit one wave)
+  for (int64_t k = (int64_t)threadIdx.x * 4; k < K; k += (int64_t)kThreads * 4 * kU) {
+    float v[kU][4], cb[kU][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      u[j] = fmaf(va[j], scale2, -ca[j] * DINOX_LOG2E);
-      if (!kVec && k + j >= K) u[j] = -INFINITY;
-      u[4 + j] = hb ? fmaf(vb[j], scale2, -cb[j] * DINOX_LOG2E) : -INFINITY;
-      if (!kVec && kb + j >= K) u[4 + j] = -INFINITY;
+    for (int i = 0; i < kU; ++i) {
+      const int64_t ki = k + (int64_t)i * kThreads * 4;
+      if (ki < K) {
+        load4<T, kVec>(row, ki, K, v[i], 0.f);
+        loadf4<kVec>(colbias, ki, K, cb[i], 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[i][j] = 0.f; cb[i][j] = 0.f; }
+      }
     }
-    float mv = fmaxf(fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3])), fmaxf(fmaxf(u[4], u[5]), fmaxf(u[6], u[7])));
+    float u[kU * 4];
+    float mv = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kU; ++i) {
+      const int64_t ki = k + (int64_t)i * kThreads * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool in = kVec ? (ki < K) : (ki + j < K);
+        u[i * 4 + j] = in ? fmaf(v[i][j], scale2, -cb[i][j] * DINOX_LOG2E) : -INFINITY;
+        mv = fmaxf(mv, u[i * 4 + j]);
+      }
+    }
     float mn = fmaxf(m, mv);
     if (mn == -INFINITY) continue;
     float r = exp2f(m - mn);  // m == -inf -> 0
     s *= r;
     e *= r;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < kU * 4; ++j) {
       float p = exp2f(u[j] - mn);
       s += p;
       if (want_ent) e += (u[j] == -INFINITY) ? 0.f : p * u[j];
@@ -514,72 +524,61 @@ ce_fwd_onepass_kernel(const TS* __restrict__ student, const TT* __restrict__ tea
   for (int v = 0; v < kMaxV; ++v) { sm[v] = -INFINITY; ss[v] = 0.f; }
 
   for (int64_t k = k0 + (int64_t)threadIdx.x * 4; k < k1; k += (int64_t)kCeThreads * 4) {
+    // phase A: every load of this 4-column block is issued before any arithmetic (predicated, no branches), so one
+    // trip to memory covers all rows - processing row by row behind its own load serialised five round trips
     float cb[4];
     loadf4<kVec>(a.colbias_t, k, k1, cb, 0.f);
-    float tu[kMaxGlobalViews][4];
+    float tr[kMaxGlobalViews][4], sr[kMaxV][4];
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) load4<TT, kVec>(teacher + (q * a.groups + g) * a.ld_t, k, k1, tr[q], 0.f);
+      else { tr[q][0] = tr[q][1] = tr[q][2] = tr[q][3] = 0.f; }
+    }
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) {
+      if (v < a.V) load4<TS, kVec>(student + (v * a.groups + g) * a.ld_s, k, k1, sr[v], 0.f);
+      else { sr[v][0] = sr[v][1] = sr[v][2] = sr[v][3] = 0.f; }
+    }
+    // phase B
+    float stot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) {
+      if (v < a.V) {
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          stot[j] += sr[v][j];
+          x[j] = (!kVec && k + j >= k1) ? -INFINITY : sr[v][j] * a.s2;
+        }
+        const float mn = fmaxf(sm[v], fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
+        const float mref = (mn == -INFINITY) ? 0.f : mn;   // nothing finite yet: every term below is 2^-inf = 0
+        float acc = ss[v] * exp2f(sm[v] - mref);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc += exp2f(x[j] - mref);
+        ss[v] = acc;
+        sm[v] = mn;
+      }
+    }
 #pragma unroll
     for (int q = 0; q < kMaxGlobalViews; ++q) {
       if (q < a.Vg) {
-        float t[4];
-        load4<TT, kVec>(teacher + (q * a.groups + g) * a.ld_t, k, k1, t, 0.f);
+        float u[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          tu[q][j] = (!kVec && k + j >= k1) ? -INFINITY : fmaf(t[j], a.t2, -cb[j] * DINOX_LOG2E);
-      }
-    }
-    float stot[4] = {0.f, 0.f, 0.f, 0.f};
-    float sown[kMaxGlobalViews][4];
+          u[j] = (!kVec && k + j >= k1) ? -INFINITY : fmaf(tr[q][j], a.t2, -cb[j] * DINOX_LOG2E);
+        const float mn = fmaxf(tm[q], fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3])));
+        const float mref = (mn == -INFINITY) ? 0.f : mn;
+        const float r = exp2f(tm[q] - mref);
+        float z = tz[q] * r, c = tc[q] * r;
 #pragma unroll
-    for (int q = 0; q < kMaxGlobalViews; ++q) { sown[q][0] = sown[q][1] = sown[q][2] = sown[q][3] = 0.f; }
-#pragma unroll
-    for (int v0 = 0; v0 < kMaxV; v0 += 4) {
-      float s[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {   // four row loads in flight
-        if (v0 + u < a.V) load4<TS, kVec>(student + ((v0 + u) * a.groups + g) * a.ld_s, k, k1, s[u], 0.f);
-        else { s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.f; }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int v = v0 + u;
-        if (v < a.V) {
-          float x[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            stot[j] += s[u][j];
-            x[j] = (!kVec && k + j >= k1) ? -INFINITY : s[u][j] * a.s2;
-          }
-          if (v < kMaxGlobalViews) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sown[v < kMaxGlobalViews ? v : 0][j] = s[u][j];
-          }
-          const float mn = fmaxf(sm[v], fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])));
-          if (mn != -INFINITY) {
-            float acc = ss[v] * exp2f(sm[v] - mn);   // first chunk: 0 * 2^-inf = 0
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc += exp2f(x[j] - mn);
-            ss[v] = acc;
-            sm[v] = mn;
-          }
+        for (int j = 0; j < 4; ++j) {
+          // the student views this teacher view pairs with: all, or all but its own (row q of the student block)
+          const float other = a.exclude_same ? (stot[j] - sr[q < kMaxV ? q : 0][j]) : stot[j];
+          const float p = exp2f(u[j] - mref);
+          z += p;
+          c = fmaf(p, other, c);
         }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < kMaxGlobalViews; ++q) {
-      if (q < a.Vg) {
-        const float mn = fmaxf(tm[q], fmaxf(fmaxf(tu[q][0], tu[q][1]), fmaxf(tu[q][2], tu[q][3])));
-        if (mn != -INFINITY) {
-          const float r = exp2f(tm[q] - mn);
-          float z = tz[q] * r, c = tc[q] * r;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float other = a.exclude_same ? (stot[j] - sown[q][j]) : stot[j];
-            const float p = exp2f(tu[q][j] - mn);
-            z += p;
-            c = fmaf(p, other, c);
-          }
-          tz[q] = z; tc[q] = c; tm[q] = mn;
-        }
+        tz[q] = z; tc[q] = c; tm[q] = mn;
       }
     }
   }
@@ -627,52 +626,60 @@ ce_fwd_onepass_kernel(const TS* __restrict__ student, const TT* __restrict__ tea
   }
 }
 
-// one CTA: merges the K-splits of every group in split order, writes the natural-log LSEs of all rows (the backward
-// kernel's inputs) and the loss; fixed summation order => deterministic
+// one CTA.  Phase 1: one thread per (group, row) merges that row's K-splits in split order (online max / rescale) and
+// writes the natural-log LSE - the backward kernel's inputs - and, for teacher rows, the normalised cross term c / z.
+// Phase 2: one thread per group forms the pair sums.  Fixed summation order throughout => deterministic.
 __global__ void __launch_bounds__(1024)
 ce_onepass_finalize_kernel(const float* __restrict__ partial, CeArgs a, float inv_tau_s, float* __restrict__ loss_out,
-                           float* __restrict__ lse_s_out, float* __restrict__ rowbias_t_out) {
+                           float* lse_s_out, float* rowbias_t_out, float* cz /* (Vg, groups) scratch */) {
   __shared__ float red[64];
   const int stride = 3 * a.Vg + 2 * a.V;
+  const int R = a.V + a.Vg;
+  const int64_t items = a.groups * R;
+  for (int64_t it = threadIdx.x; it < items; it += 1024) {
+    const int64_t g = it / R;
+    const int r = (int)(it - g * R);
+    const float* pg = partial + g * a.ksplit * stride;
+    if (r < a.V) {
+      const float* p = pg + 3 * a.Vg + 2 * r;
+      float M = -INFINITY, S = 0.f;
+#pragma unroll 4
+      for (int sp = 0; sp < a.ksplit; ++sp) {
+        const float m = p[sp * stride], sv = p[sp * stride + 1];
+        const float mn = fmaxf(M, m);
+        const float mref = (mn == -INFINITY) ? 0.f : mn;
+        S = S * exp2f(M - mref) + sv * exp2f(m - mref);
+        M = mn;
+      }
+      lse_s_out[r * a.groups + g] = DINOX_LN2 * (M + log2f(S));
+    } else {
+      const int q = r - a.V;
+      const float* p = pg + 3 * q;
+      float M = -INFINITY, Z = 0.f, C = 0.f;
+#pragma unroll 4
+      for (int sp = 0; sp < a.ksplit; ++sp) {
+        const float m = p[sp * stride], zv = p[sp * stride + 1], cv = p[sp * stride + 2];
+        const float mn = fmaxf(M, m);
+        const float mref = (mn == -INFINITY) ? 0.f : mn;
+        const float r0 = exp2f(M - mref), r1 = exp2f(m - mref);
+        Z = Z * r0 + zv * r1;
+        C = C * r0 + cv * r1;
+        M = mn;
+      }
+      rowbias_t_out[q * a.groups + g] = DINOX_LN2 * (M + log2f(Z));
+      cz[q * a.groups + g] = C / Z;   // sum_k q[k] * (sum of the paired student rows)[k], q = 2^(u - M) / Z
+    }
+  }
+  __syncthreads();   // one CTA: the global writes above are visible to the whole block
   float acc = 0.f;
   for (int64_t g = threadIdx.x; g < a.groups; g += 1024) {
-    const float* pg = partial + g * a.ksplit * stride;
-    float lse_tot = 0.f, lse_own[kMaxGlobalViews];
-#pragma unroll
-    for (int q = 0; q < kMaxGlobalViews; ++q) lse_own[q] = 0.f;
-    for (int v = 0; v < a.V; ++v) {
-      float M = -INFINITY;
-      for (int sp = 0; sp < a.ksplit; ++sp) M = fmaxf(M, pg[sp * stride + 3 * a.Vg + 2 * v]);
-      float s = 0.f;
-      for (int sp = 0; sp < a.ksplit; ++sp) {
-        const float m = pg[sp * stride + 3 * a.Vg + 2 * v];
-        s += pg[sp * stride + 3 * a.Vg + 2 * v + 1] * ((m == -INFINITY) ? 0.f : exp2f(m - M));
-      }
-      const float lse = DINOX_LN2 * (M + log2f(s));
-      lse_s_out[v * a.groups + g] = lse;
-      lse_tot += lse;
-#pragma unroll
-      for (int q = 0; q < kMaxGlobalViews; ++q)
-        if (q == v) lse_own[q] = lse;
-    }
+    float lse_tot = 0.f;
+    for (int v = 0; v < a.V; ++v) lse_tot += lse_s_out[v * a.groups + g];
     float lg = 0.f;
-#pragma unroll
-    for (int q = 0; q < kMaxGlobalViews; ++q) {
-      if (q < a.Vg) {
-        float M = -INFINITY;
-        for (int sp = 0; sp < a.ksplit; ++sp) M = fmaxf(M, pg[sp * stride + 3 * q]);
-        float z = 0.f, c = 0.f;
-        for (int sp = 0; sp < a.ksplit; ++sp) {
-          const float m = pg[sp * stride + 3 * q];
-          const float sc = (m == -INFINITY) ? 0.f : exp2f(m - M);
-          z += pg[sp * stride + 3 * q + 1] * sc;
-          c += pg[sp * stride + 3 * q + 2] * sc;
-        }
-        rowbias_t_out[q * a.groups + g] = DINOX_LN2 * (M + log2f(z));
-        // sum over the pairs of this teacher view of [ lse_v - (1/tau_s) sum_k q[k] s_v[k] ], q = 2^(u - M) / z
-        const float lse_sum = a.exclude_same ? lse_tot - lse_own[q] : lse_tot;
-        lg += lse_sum - (c / z) * inv_tau_s;
-      }
+    for (int q = 0; q < a.Vg; ++q) {
+      // sum over the pairs of this teacher view of [ lse_v - (1/tau_s) sum_k q[k] s_v[k] ]
+      const float lse_sum = a.exclude_same ? lse_tot - lse_s_out[q * a.groups + g] : lse_tot;
+      lg += lse_sum - cz[q * a.groups + g] * inv_tau_s;
     }
     acc += lg * (a.group_w ? a.group_w[g] : 1.f);
   }
@@ -680,8 +687,11 @@ ce_onepass_finalize_kernel(const float* __restrict__ partial, CeArgs a, float in
   if (threadIdx.x == 0) *loss_out = tot * a.norm;
 }
 
-template <typename TS, typename TT, bool kVec>
-__global__ void __launch_bounds__(kCeThreads, kCeBwdCtasPerSm)
+// kBatch student rows are loaded together with the teacher rows before any arithmetic (kBatch = 12 covers every row
+// of up to 12 views in ONE trip to memory per 4-column block; more views take further batches), then written back
+// row by row.  kBatch = 4 is the small-register form for <= 4 views.
+template <typename TS, typename TT, bool kVec, int kBatch>
+__global__ void __launch_bounds__(kCeThreads, kBatch <= 4 ? kCeBwdCtasPerSm : kOnePassCtasPerSm)
 ce_bwd_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, CeArgs a,
               const float* __restrict__ upstream, TS* __restrict__ grad) {
   const int64_t g = blockIdx.x;
@@ -693,49 +703,67 @@ ce_bwd_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, Ce
 #pragma unroll
   for (int q = 0; q < kMaxGlobalViews; ++q)
     rb2[q] = (q < a.Vg) ? a.rowbias_t[q * a.groups + g] * DINOX_LOG2E : 0.f;
+  float lse2_first[kBatch];   // log2 LSEs of the first batch of student rows: constant over the K sweep
+#pragma unroll
+  for (int u = 0; u < kBatch; ++u) lse2_first[u] = (u < a.V) ? a.lse_s[u * a.groups + g] * DINOX_LOG2E : 0.f;
 
   for (int64_t k = k0 + (int64_t)threadIdx.x * 4; k < k1; k += (int64_t)kCeThreads * 4) {
+    // phase A: teacher rows, column offsets and the first batch of student rows - all loads before any arithmetic
     float cb[4];
     loadf4<kVec>(a.colbias_t, k, k1, cb, 0.f);
+    float tr[kMaxGlobalViews][4];
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) load4<TT, kVec>(teacher + (q * a.groups + g) * a.ld_t, k, k1, tr[q], 0.f);
+      else { tr[q][0] = tr[q][1] = tr[q][2] = tr[q][3] = 0.f; }
+    }
+    float sb[kBatch][4];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (u < a.V) load4<TS, kVec>(student + (u * a.groups + g) * a.ld_s, k, k1, sb[u], 0.f);
+      else { sb[u][0] = sb[u][1] = sb[u][2] = sb[u][3] = 0.f; }
+    }
+    // phase B
     float qv[kMaxGlobalViews][4];
     float qtot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < kMaxGlobalViews; ++q) {
-      if (q < a.Vg) {
-        float t[4];
-        load4<TT, kVec>(teacher + (q * a.groups + g) * a.ld_t, k, k1, t, 0.f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float u = fmaf(t[j], a.t2, -cb[j] * DINOX_LOG2E) - rb2[q];
-          qv[q][j] = exp2f(u);
-          qtot[j] += qv[q][j];
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float u = fmaf(tr[q][j], a.t2, -cb[j] * DINOX_LOG2E) - rb2[q];
+        qv[q][j] = (q < a.Vg) ? exp2f(u) : 0.f;
+        qtot[j] += qv[q][j];
       }
     }
-    for (int v0 = 0; v0 < a.V; v0 += 4) {   // four student rows in flight per thread
-      float s4[4][4], lse2[4];
+    for (int v0 = 0; v0 < a.V; v0 += kBatch) {
+      float lse2[kBatch];
+      if (v0 > 0) {   // more views than one batch holds
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t r = (v0 + u) * a.groups + g;
-        if (v0 + u < a.V) {
-          load4<TS, kVec>(student + r * a.ld_s, k, k1, s4[u], 0.f);
-          lse2[u] = a.lse_s[r] * DINOX_LOG2E;
-        } else {
-          s4[u][0] = s4[u][1] = s4[u][2] = s4[u][3] = 0.f;
-          lse2[u] = 0.f;
+        for (int u = 0; u < kBatch; ++u) {
+          const int64_t r = (int64_t)(v0 + u) * a.groups + g;
+          if (v0 + u < a.V) {
+            load4<TS, kVec>(student + r * a.ld_s, k, k1, sb[u], 0.f);
+            lse2[u] = a.lse_s[r] * DINOX_LOG2E;
+          } else {
+            sb[u][0] = sb[u][1] = sb[u][2] = sb[u][3] = 0.f;
+            lse2[u] = 0.f;
+          }
         }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) lse2[u] = lse2_first[u];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kBatch; ++u) {
         const int v = v0 + u;
         if (v >= a.V) break;
-        const int64_t r = v * a.groups + g;
+        const int64_t r = (int64_t)v * a.groups + g;
         const bool own = a.exclude_same && v < a.Vg;
         const float nq = (float)(a.Vg - (own ? 1 : 0));
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float p = exp2f(fmaf(s4[u][j], a.s2, -lse2[u]));
+          float p = exp2f(fmaf(sb[u][j], a.s2, -lse2[u]));
           float target = qtot[j];
 #pragma unroll
           for (int q = 0; q < kMaxGlobalViews; ++q)
@@ -950,6 +978,15 @@ size_t dinox_ce_workspace_bytes(int64_t groups, int64_t K) {
   return (size_t)groups * 64 * kMaxGlobalViews * 2 * sizeof(float);
 }
 
+// measurement knob (read once): DINOX_CE_BWD_BATCH=4 forces the four-rows-at-a-time backward (64 registers, 4 CTAs
+// per SM) for any view count.  Measured equal at the C2 shapes (73.7 us both; profiles/r02_hbm_kernels_tuning.txt), as
+// was an L2 prefetch of the next column block in both kernels (no gain, removed).
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+static int ce_bwd_batch() { static const int v = env_int("DINOX_CE_BWD_BATCH", 0); return v; }
+
 static int ce_args(CeArgs& a, const void* student, const void* teacher, int64_t groups, int V, int Vg,
                    int64_t K, int64_t ld_s, int64_t ld_t, float inv_tau_s, float inv_tau_t,
                    const float* colbias_t, const float* rowbias_t, const float* lse_s,
@@ -995,7 +1032,7 @@ int dinox_ce_onepass_max_views(void) { return kOnePassMaxViews; }
 
 size_t dinox_ce_onepass_workspace_bytes(int64_t groups, int V, int Vg, int64_t K) {
   if (groups <= 0 || K <= 0 || V < 1 || Vg < 1) return 0;
-  return (size_t)groups * 64 * (size_t)(3 * Vg + 2 * V) * sizeof(float);
+  return ((size_t)groups * 64 * (size_t)(3 * Vg + 2 * V) + (size_t)groups * Vg) * sizeof(float);
 }
 
 int dinox_ce_fwd_onepass(const void* student, int s_dtype, const void* teacher, int t_dtype, int64_t groups,
@@ -1023,7 +1060,8 @@ int dinox_ce_fwd_onepass(const void* student, int s_dtype, const void* teacher, 
 #undef DINOX_ONEPASS_LAUNCH
   rc = check_launch("ce_fwd_onepass_kernel", stream);
   if (rc) return rc;
-  ce_onepass_finalize_kernel<<<1, 1024, 0, stream>>>(partial, a, inv_tau_s, loss_out, lse_s_out, rowbias_t_out);
+  ce_onepass_finalize_kernel<<<1, 1024, 0, stream>>>(partial, a, inv_tau_s, loss_out, lse_s_out, rowbias_t_out,
+                                                       partial + (size_t)groups * 64 * (size_t)(3 * Vg + 2 * V));
   return check_launch("ce_onepass_finalize_kernel", stream);
 }
 
@@ -1034,17 +1072,21 @@ int dinox_ce_bwd(const void* student, int s_dtype, const void* teacher, int t_dt
                  int64_t ld_g, dinox_stream_t stream) {
   CeArgs a;
   int rc = ce_args(a, student, teacher, groups, V, Vg, K, ld_s, ld_t, inv_tau_s, inv_tau_t, colbias_t,
-                   rowbias_t, lse_s, group_w, norm, exclude_same, kCeBwdCtasPerSm);
+                   rowbias_t, lse_s, group_w, norm, exclude_same,
+                   (V <= 4 || ce_bwd_batch() == 4) ? kCeBwdCtasPerSm : kOnePassCtasPerSm);
   if (rc) return rc;
   DINOX_REQUIRE(upstream && grad && ld_g >= K, DINOX_E_BADARG, "ce_bwd: null upstream/grad or ld_g < K");
   a.ld_g = ld_g;
   const bool vec = vec_ok(student, s_dtype, K, ld_s) && vec_ok(teacher, t_dtype, K, ld_t) &&
                    vec_ok(grad, s_dtype, K, ld_g) && fvec_ok(colbias_t);
   dim3 grid((unsigned)groups, (unsigned)a.ksplit);
-  DISPATCH_T(s_dtype, TS, DISPATCH_T(t_dtype, TT, {
-    if (vec) ce_bwd_kernel<TS, TT, true><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, upstream, (TS*)grad);
-    else ce_bwd_kernel<TS, TT, false><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, upstream, (TS*)grad);
-  }));
+#define DINOX_CE_BWD_LAUNCH(BATCH)                                                                                          \
+  DISPATCH_T(s_dtype, TS, DISPATCH_T(t_dtype, TT, {                                                                         \
+    if (vec) ce_bwd_kernel<TS, TT, true, BATCH><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, upstream, (TS*)grad); \
+    else ce_bwd_kernel<TS, TT, false, BATCH><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, upstream, (TS*)grad);    \
+  }))
+  if (V <= 4 || ce_bwd_batch() == 4) { DINOX_CE_BWD_LAUNCH(4); } else { DINOX_CE_BWD_LAUNCH(kOnePassMaxViews); }
+#undef DINOX_CE_BWD_LAUNCH
   return check_launch("ce_bwd_kernel", stream);
 }
 

@@ -154,5 +154,5 @@ def test_dinoloss_forward_modes_agree(V):
     for mode, (loss, grad, centre) in out.items():
         assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item()), mode
         assert rel(grad, so.grad) <= 1e-5, mode
-    assert rel(out["onepass"][1], out["passes"][1]) <= 1e-6
+    assert rel(out["onepass"][1], out["passes"][1]) <= 5e-6   # two fp32 summation orders of the same LSEs
     assert torch.equal(out["onepass"][2], out["passes"][2])   # the centre update is the same kernel pair

@@ -11,4 +11,7 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 peaks = bench._peaks()
 sh = synth.LossHeadShapes(**synth.CONFIGS[cfg])
-print(json.dumps({"config": cfg, "hbm_peak_gbs": peaks["hbm"], "hbm_kernels": bench.hbm_kernel_table(dev, sh, peaks["hbm"])}))
+only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None
+knobs = {k: v for k, v in os.environ.items() if k.startswith("DINOX_")}
+print(json.dumps({"config": cfg, "env": knobs, "hbm_peak_gbs": peaks["hbm"],
+                  "hbm_kernels": bench.hbm_kernel_table(dev, sh, peaks["hbm"], only=only)}))
