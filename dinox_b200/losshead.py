@@ -230,7 +230,9 @@ class DINOLoss(nn.Module):
         if self.n_local and V != Vg + self.n_local:
             raise ValueError(f"student rows imply {V} views, expected {Vg + self.n_local}")
         n_terms = Vg * V - Vg
-        if self.teacher_mode == "center" and _CE_FORWARD[0] == "onepass" and V <= ops.ce_onepass_max_views():
+        onepass = (self.teacher_mode == "center" and _CE_FORWARD[0] == "onepass" and V <= ops.ce_onepass_max_views()
+                   and s.shape[0] * s.stride(0) < 2 ** 32 and t.shape[0] * t.stride(0) < 2 ** 32)   # 32-bit offsets
+        if onepass:
             with torch.no_grad():
                 colbias = ops.axpb(self.center.reshape(-1), 1.0 / teacher_temp)
             loss = _RowCEOnePass.apply(s, t, colbias, None, B, V, Vg, 1.0 / student_temp, 1.0 / teacher_temp,
