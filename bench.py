@@ -305,7 +305,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 def hbm_kernel_table(dev, sh, hbm_peak: float, reps: int = 20, only=None):
     """CUDA-event medians of the row / column reduction kernels at this config's logit shapes, each launched on
-    a cold L2 (a 512 MB buffer is rewritten between calls), with their ALGORITHMIC bytes (every logit read once
+    a cold, CLEAN L2 (a 512 MB buffer is rewritten and half of it read back between calls), with their ALGORITHMIC bytes (every logit read once
     per pass, fp32) -> GB/s and fraction of the measured HBM copy bandwidth.  Shapes at C2: student 640 x 65536,
     teacher 128 x 65536 - the small ones are launch-latency bound and say so."""
     from dinox_b200 import losshead, ops
@@ -315,6 +315,8 @@ def hbm_kernel_table(dev, sh, hbm_peak: float, reps: int = 20, only=None):
     t = torch.randn(Mt, K, generator=g).to(dev)
     center = torch.zeros(K, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    flush_words = flush.view(torch.int64)
+    sink = torch.zeros((), dtype=torch.int64, device=dev)
     colb = ops.axpb(center, 25.0)
     rowb = ops.rows_lse(t, 25.0, colb)
     lse_s = ops.rows_lse(s, 10.0)
@@ -342,7 +344,11 @@ def hbm_kernel_table(dev, sh, hbm_peak: float, reps: int = 20, only=None):
         fn()
         ts = []
         for _ in range(reps):
-            flush.fill_(1)                      # evict the logits from L2 (not timed)
+            # evict the logits from L2 (not timed): rewrite 512 MB, then READ 256 MB of it so that the cache is left
+            # full of CLEAN lines - after the write alone up to 126 MB of dirty lines are written back during the
+            # timed kernel (a 168 MB read-only pass then moves 294 MB of HBM traffic and reads as 0.5 of peak)
+            flush.fill_(1)
+            sink.copy_(flush_words[: (256 << 20) // 8].max())
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()

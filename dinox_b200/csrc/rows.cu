@@ -5,6 +5,7 @@
 // units (one FFMA + one MUFU.EX2 per element), warp-shuffle + shared-memory block reductions in
 // a fixed order (deterministic; no fp32 atomics).
 #include "common.cuh"
+#include "sm100.cuh"
 #include <stdlib.h>
 
 namespace dinox {
@@ -705,6 +706,212 @@ ce_onepass_finalize_kernel(const float* __restrict__ partial, CeArgs a, float in
   if (threadIdx.x == 0) *loss_out = tot * a.norm;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same one-pass forward as a PERSISTENT, shared-memory staged stream (the default when alignment allows):
+// one CTA per SM; a producer thread copies the next 2048-column block of every row of a (group, K-split) work item
+// into shared memory with 1-D bulk copies (cp.async.bulk, mbarrier complete_tx) while 512 consumer threads run the
+// online LSE / cross-term arithmetic on the previous block.  Loads need no registers, run kStages blocks ahead and
+// straight across work-item boundaries, so no CTA start-up latency is exposed after the first block; the consumers
+// are left with ~45 registers of running state.  Same partial layout and finalize kernel as the register form.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStreamConsumers = 512;
+constexpr int kStreamThreads = kStreamConsumers + 32;
+constexpr int kStreamCols = kStreamConsumers * 4;       // columns per stage
+constexpr int kStreamMaxStages = 4;
+constexpr int kStreamSmemBudget = 220 * 1024;           // of the 227 KB a CTA may own
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sm100::smem_u32(dst)), "l"(src), "r"(bytes), "r"(sm100::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kStreamConsumers) : "memory"); }
+
+struct StreamArgs {
+  int stages;            // 2..kStreamMaxStages
+  int64_t per;           // columns per K-split (multiple of 8)
+  int64_t items;         // groups * ksplit
+  uint32_t row_s, row_t; // bytes of one staged student / teacher row (kStreamCols elements)
+  uint32_t off_t, off_cb, stage_bytes;   // teacher rows / column offsets inside a stage; bytes per stage
+};
+
+template <typename TS, typename TT, int kMaxV>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+ce_fwd_onepass_stream_kernel(const TS* __restrict__ student, const TT* __restrict__ teacher, CeArgs a, StreamArgs sa,
+                             float* __restrict__ partial /* [groups][ksplit][3 Vg + 2 V] */) {
+  static_assert(kMaxV % 4 == 0 && kMaxV >= kMaxGlobalViews, "views");
+  constexpr int kWarps = kStreamConsumers / 32;
+  constexpr int kVals = 3 * kMaxGlobalViews + 2 * kMaxV;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[kStreamMaxStages], empty[kStreamMaxStages];
+  __shared__ float red[2][kWarps][kVals];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStreamMaxStages; ++i) { sm100::mbar_init(&full[i], 1); sm100::mbar_init(&empty[i], kWarps); }
+    sm100::fence_barrier_init();
+  }
+  __syncthreads();
+  const int stride = 3 * a.Vg + 2 * a.V;
+
+  if (threadIdx.x >= kStreamConsumers) {
+    // ---------------- producer: one thread walks (item, block) and keeps `stages` blocks in flight ----------------
+    if (threadIdx.x != kStreamConsumers) return;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t item = blockIdx.x; item < sa.items; item += gridDim.x) {
+      const int64_t g = item / a.ksplit;
+      const int split = (int)(item - g * a.ksplit);
+      const int64_t k0 = split * sa.per, k1 = (k0 + sa.per < a.K) ? k0 + sa.per : a.K;
+      for (int64_t k = k0; k < k1; k += kStreamCols) {
+        const uint32_t cols = (uint32_t)((k1 - k < kStreamCols) ? (k1 - k) : kStreamCols);
+        sm100::mbar_wait(&empty[stage], phase ^ 1u, 31);
+        uint8_t* st = smem + (size_t)stage * sa.stage_bytes;
+        const uint32_t bs = cols * (uint32_t)sizeof(TS), bt = cols * (uint32_t)sizeof(TT);
+        sm100::mbar_expect_tx(&full[stage], (uint32_t)a.V * bs + (uint32_t)a.Vg * bt + (a.colbias_t ? cols * 4u : 0u));
+        for (int v = 0; v < a.V; ++v)
+          bulk_g2s(st + (size_t)v * sa.row_s, student + (v * a.groups + g) * a.ld_s + k, bs, &full[stage]);
+        for (int q = 0; q < a.Vg; ++q)
+          bulk_g2s(st + sa.off_t + (size_t)q * sa.row_t, teacher + (q * a.groups + g) * a.ld_t + k, bt, &full[stage]);
+        if (a.colbias_t) bulk_g2s(st + sa.off_cb, a.colbias_t + k, cols * 4u, &full[stage]);
+        if (++stage == sa.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  // Arithmetic in packed fp32 pairs (FFMA2 / FADD2, sm_100); the running maximum of a row is only touched when a block
+  // raises it (rare after the first blocks), otherwise a row costs one LDS.128, three FMNMX, one compare and, per pair
+  // of prototypes, one FFMA2 + two MUFU.EX2 + one FADD2.  -1e30 stands for "no maximum yet": 2^(x + 1e30) never
+  // appears because the first finite block raises the maximum before any term is formed, and -inf inputs give 0.
+  constexpr float kNoMax = -1.0e30f;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  int stage = 0;
+  uint32_t phase = 0;
+  int flip = 0;
+  const float2 s22 = make_float2(a.s2, a.s2), t22 = make_float2(a.t2, a.t2);
+  for (int64_t item = blockIdx.x; item < sa.items; item += gridDim.x) {
+    const int64_t g = item / a.ksplit;
+    const int split = (int)(item - g * a.ksplit);
+    const int64_t k0 = split * sa.per, k1 = (k0 + sa.per < a.K) ? k0 + sa.per : a.K;
+    float tm[kMaxGlobalViews];
+    float2 tz[kMaxGlobalViews], tc[kMaxGlobalViews];
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) { tm[q] = kNoMax; tz[q] = make_float2(0.f, 0.f); tc[q] = make_float2(0.f, 0.f); }
+    float sm[kMaxV];
+    float2 ss[kMaxV];
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) { sm[v] = kNoMax; ss[v] = make_float2(0.f, 0.f); }
+
+    for (int64_t k = k0; k < k1; k += kStreamCols) {
+      const uint32_t cols = (uint32_t)((k1 - k < kStreamCols) ? (k1 - k) : kStreamCols);
+      sm100::mbar_wait(&full[stage], phase, 32);
+      const uint8_t* st = smem + (size_t)stage * sa.stage_bytes;
+      if ((uint32_t)t * 4u < cols) {
+        float2 stot0 = make_float2(0.f, 0.f), stot1 = make_float2(0.f, 0.f);
+        const uint8_t* srow = st + (size_t)t * (4 * sizeof(TS));
+#pragma unroll
+        for (int v = 0; v < kMaxV; ++v) {
+          if (v < a.V) {
+            float raw[4];
+            Vec4<TS>::load(reinterpret_cast<const TS*>(srow), raw);
+            srow += sa.row_s;
+            const float2 r0 = make_float2(raw[0], raw[1]), r1 = make_float2(raw[2], raw[3]);
+            stot0 = __fadd2_rn(stot0, r0);
+            stot1 = __fadd2_rn(stot1, r1);
+            const float cand = a.s2 * fmaxf(fmaxf(raw[0], raw[1]), fmaxf(raw[2], raw[3]));
+            if (cand > sm[v]) {   // the block raises this thread's maximum of the row: rescale the running sums
+              const float r = ex2_approx(sm[v] - cand);   // first block: 2^(-1e30 - cand) = 0
+              ss[v] = __fmul2_rn(ss[v], make_float2(r, r));
+              sm[v] = cand;
+            }
+            const float2 nm = make_float2(-sm[v], -sm[v]);
+            const float2 x0 = __ffma2_rn(r0, s22, nm), x1 = __ffma2_rn(r1, s22, nm);
+            ss[v] = __fadd2_rn(ss[v], make_float2(ex2_approx(x0.x), ex2_approx(x0.y)));
+            ss[v] = __fadd2_rn(ss[v], make_float2(ex2_approx(x1.x), ex2_approx(x1.y)));
+          }
+        }
+        float2 cb0 = make_float2(0.f, 0.f), cb1 = make_float2(0.f, 0.f);
+        if (a.colbias_t) {
+          float cb[4];
+          Vec4<float>::load(reinterpret_cast<const float*>(st + sa.off_cb) + 4 * t, cb);
+          cb0 = make_float2(-cb[0] * DINOX_LOG2E, -cb[1] * DINOX_LOG2E);
+          cb1 = make_float2(-cb[2] * DINOX_LOG2E, -cb[3] * DINOX_LOG2E);
+        }
+        const uint8_t* trow = st + sa.off_t + (size_t)t * (4 * sizeof(TT));
+        const uint8_t* orow = st + (size_t)t * (4 * sizeof(TS));
+#pragma unroll
+        for (int q = 0; q < kMaxGlobalViews; ++q) {
+          if (q < a.Vg) {
+            float tr[4], own[4] = {0.f, 0.f, 0.f, 0.f};
+            Vec4<TT>::load(reinterpret_cast<const TT*>(trow), tr);
+            if (a.exclude_same) Vec4<TS>::load(reinterpret_cast<const TS*>(orow), own);
+            trow += sa.row_t;
+            orow += sa.row_s;
+            const float2 u0 = __ffma2_rn(make_float2(tr[0], tr[1]), t22, cb0), u1 = __ffma2_rn(make_float2(tr[2], tr[3]), t22, cb1);
+            const float cand = fmaxf(fmaxf(u0.x, u0.y), fmaxf(u1.x, u1.y));
+            if (cand > tm[q]) {
+              const float r = ex2_approx(tm[q] - cand);
+              const float2 r2 = make_float2(r, r);
+              tz[q] = __fmul2_rn(tz[q], r2);
+              tc[q] = __fmul2_rn(tc[q], r2);
+              tm[q] = cand;
+            }
+            const float2 nm = make_float2(-tm[q], -tm[q]);
+            const float2 e0 = __fadd2_rn(u0, nm), e1 = __fadd2_rn(u1, nm);
+            const float2 p0 = make_float2(ex2_approx(e0.x), ex2_approx(e0.y)), p1 = make_float2(ex2_approx(e1.x), ex2_approx(e1.y));
+            // the student views this teacher view pairs with: all, or all but its own (row q of the student block)
+            const float2 o0 = __fadd2_rn(stot0, make_float2(-own[0], -own[1])), o1 = __fadd2_rn(stot1, make_float2(-own[2], -own[3]));
+            tz[q] = __fadd2_rn(tz[q], __fadd2_rn(p0, p1));
+            tc[q] = __ffma2_rn(p0, o0, tc[q]);
+            tc[q] = __ffma2_rn(p1, o1, tc[q]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&empty[stage]);   // this warp has read the stage
+      if (++stage == sa.stages) { stage = 0; phase ^= 1u; }
+    }
+    // merge of the work item: warp shuffles, one thread per row walks the warps in order (fixed order)
+#pragma unroll
+    for (int q = 0; q < kMaxGlobalViews; ++q) {
+      if (q < a.Vg) {
+        float m = tm[q], z = tz[q].x + tz[q].y, c = tc[q].x + tc[q].y;
+        warp_merge3(m, z, c);
+        if (lane == 0) { red[flip][w][3 * q] = m; red[flip][w][3 * q + 1] = z; red[flip][w][3 * q + 2] = c; }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < kMaxV; ++v) {
+      if (v < a.V) {
+        float m = sm[v], sv = ss[v].x + ss[v].y, dummy = 0.f;
+        warp_merge3(m, sv, dummy);
+        if (lane == 0) { red[flip][w][3 * kMaxGlobalViews + 2 * v] = m; red[flip][w][3 * kMaxGlobalViews + 2 * v + 1] = sv; }
+      }
+    }
+    consumer_sync();   // red[flip] complete; red[flip ^ 1] (previous item) has been read by everyone who passes here
+    float* out = partial + item * stride;
+    if (t < a.Vg) {
+      float M = -INFINITY;
+      for (int i = 0; i < kWarps; ++i) M = fmaxf(M, red[flip][i][3 * t]);
+      float z = 0.f, c = 0.f;
+      for (int i = 0; i < kWarps; ++i) {
+        const float sc = exp2f(red[flip][i][3 * t] - M);   // maxima are finite (>= -1e30): no inf - inf
+        z += red[flip][i][3 * t + 1] * sc;
+        c += red[flip][i][3 * t + 2] * sc;
+      }
+      out[3 * t] = M; out[3 * t + 1] = z; out[3 * t + 2] = c;
+    } else if (t >= 32 && t < 32 + a.V) {
+      const int v = t - 32;
+      float M = -INFINITY;
+      for (int i = 0; i < kWarps; ++i) M = fmaxf(M, red[flip][i][3 * kMaxGlobalViews + 2 * v]);
+      float sv = 0.f;
+      for (int i = 0; i < kWarps; ++i)
+        sv += red[flip][i][3 * kMaxGlobalViews + 2 * v + 1] * exp2f(red[flip][i][3 * kMaxGlobalViews + 2 * v] - M);
+      out[3 * a.Vg + 2 * v] = M; out[3 * a.Vg + 2 * v + 1] = sv;
+    }
+    flip ^= 1;
+  }
+}
+
 // kBatch student rows are loaded together with the teacher rows before any arithmetic (kBatch = 12 covers every row
 // of up to 12 views in ONE trip to memory per 4-column block; more views take further batches), then written back
 // row by row.  kBatch = 4 is the small-register form for <= 4 views.
@@ -1055,6 +1262,61 @@ int dinox_ce_fwd(const void* student, int s_dtype, const void* teacher, int t_dt
   return check_launch("ce_finalize_kernel", stream);
 }
 
+}  // extern "C"
+
+namespace dinox {
+static int ce_stream() { static const int v = env_int("DINOX_CE_STREAM", 1); return v; }
+
+// K-split of the persistent stream: work items = groups * splits are dealt round-robin to one CTA per SM; the smallest
+// split count (each split keeps >= 2 blocks of kStreamCols columns) within 2 % of the best balance
+static int pick_ksplit_stream(int64_t groups, int64_t K) {
+  const int64_t nsm = num_sms();
+  int64_t maxs = K / (2 * kStreamCols);
+  if (maxs < 1) maxs = 1;
+  if (maxs > 64) maxs = 64;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int64_t ks = 1; ks <= maxs; ++ks) {
+    const int64_t items = groups * ks;
+    const double eff = (double)items / (double)(((items + nsm - 1) / nsm) * nsm);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = (int)ks; }
+  }
+  return best;
+}
+
+template <typename TS, typename TT, int MAXV>
+static int launch_onepass_stream(const void* student, const void* teacher, CeArgs& a, float* partial, cudaStream_t stream) {
+  StreamArgs sa;
+  sa.row_s = kStreamCols * (uint32_t)sizeof(TS);
+  sa.row_t = kStreamCols * (uint32_t)sizeof(TT);
+  sa.off_t = (uint32_t)a.V * sa.row_s;
+  sa.off_cb = sa.off_t + (uint32_t)a.Vg * sa.row_t;
+  sa.stage_bytes = sa.off_cb + (a.colbias_t ? kStreamCols * 4u : 0u);
+  int stages = (int)(kStreamSmemBudget / sa.stage_bytes);
+  if (stages > kStreamMaxStages) stages = kStreamMaxStages;
+  if (stages < 2) return 1;   // not for this shape: the caller takes the register kernel
+  sa.stages = stages;
+  a.ksplit = pick_ksplit_stream(a.groups, a.K);
+  sa.per = ((a.K + a.ksplit - 1) / a.ksplit + 7) & ~int64_t(7);
+  sa.items = a.groups * a.ksplit;
+  auto kern = ce_fwd_onepass_stream_kernel<TS, TT, MAXV>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    DINOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBudget));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int64_t nsm = num_sms();
+  const unsigned grid = (unsigned)(sa.items < nsm ? sa.items : nsm);
+  kern<<<grid, kStreamThreads, (size_t)stages * sa.stage_bytes, stream>>>((const TS*)student, (const TT*)teacher, a, sa, partial);
+  return 0;
+}
+}  // namespace dinox
+
+extern "C" {
+using namespace dinox;
+
 int dinox_ce_onepass_max_views(void) { return kOnePassMaxViews; }
 
 size_t dinox_ce_onepass_workspace_bytes(int64_t groups, int V, int Vg, int64_t K) {
@@ -1079,8 +1341,27 @@ int dinox_ce_fwd_onepass(const void* student, int s_dtype, const void* teacher, 
                 V, kOnePassMaxViews);
   DINOX_REQUIRE(loss_out && workspace, DINOX_E_BADARG, "ce_fwd_onepass: null output/workspace");
   const bool vec = vec_ok(student, s_dtype, K, ld_s) && vec_ok(teacher, t_dtype, K, ld_t) && fvec_ok(colbias_t);
-  dim3 grid((unsigned)groups, (unsigned)a.ksplit);
   float* partial = (float*)workspace;
+  // persistent shared-memory staged form: rows 16-byte aligned in both matrices (bulk copies), >= 2 stages fit
+  const size_t es = elt_size(s_dtype), et = elt_size(t_dtype);
+  const bool bulk_ok = vec && ce_stream() && aligned16(student) && aligned16(teacher) && (ld_s * es) % 16 == 0 &&
+                       (ld_t * et) % 16 == 0 && (K * es) % 16 == 0 && (K * et) % 16 == 0;
+  if (bulk_ok) {
+    int r = 1;
+#define DINOX_STREAM_LAUNCH(MAXV) \
+    DISPATCH_T(s_dtype, TS, DISPATCH_T(t_dtype, TT, { r = launch_onepass_stream<TS, TT, MAXV>(student, teacher, a, partial, stream); }))
+    if (V <= 4) { DINOX_STREAM_LAUNCH(4); } else { DINOX_STREAM_LAUNCH(kOnePassMaxViews); }
+#undef DINOX_STREAM_LAUNCH
+    if (r < 0) return r;
+    if (r == 0) {
+      rc = check_launch("ce_fwd_onepass_stream_kernel", stream);
+      if (rc) return rc;
+      ce_onepass_finalize_kernel<<<1, 1024, 0, stream>>>(partial, a, inv_tau_s, loss_out, lse_s_out, rowbias_t_out,
+                                                         partial + (size_t)groups * 64 * (size_t)(3 * Vg + 2 * V));
+      return check_launch("ce_onepass_finalize_kernel", stream);
+    }
+  }
+  dim3 grid((unsigned)groups, (unsigned)a.ksplit);
 #define DINOX_ONEPASS_LAUNCH(MAXV)                                                                                          \
   DISPATCH_T(s_dtype, TS, DISPATCH_T(t_dtype, TT, {                                                                         \
     if (vec) ce_fwd_onepass_kernel<TS, TT, true, MAXV><<<grid, kCeThreads, 0, stream>>>((const TS*)student, (const TT*)teacher, a, partial); \

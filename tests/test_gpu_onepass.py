@@ -156,3 +156,31 @@ def test_dinoloss_forward_modes_agree(V):
         assert rel(grad, so.grad) <= 1e-5, mode
     assert rel(out["onepass"][1], out["passes"][1]) <= 5e-6   # two fp32 summation orders of the same LSEs
     assert torch.equal(out["onepass"][2], out["passes"][2])   # the centre update is the same kernel pair
+
+
+def test_onepass_register_form_in_a_child_process():
+    """Aligned shapes take the persistent shared-memory staged kernel; DINOX_CE_STREAM=0 (read once per process) keeps
+    them on the register form, which must agree with the oracle just the same."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import math, torch
+from oracle import losshead_oracle as O
+from dinox_b200 import ops
+for (B, V, Vg, K, dt) in ((4, 2, 2, 128, torch.float32), (5, 10, 2, 16384, torch.float32), (6, 10, 2, 8192, torch.bfloat16)):
+    gen = torch.Generator().manual_seed(K + V)
+    s = (torch.randn(V * B, K, generator=gen) * 1.5).to(dt); t = (torch.randn(Vg * B, K, generator=gen) * 1.5).to(dt)
+    c = torch.randn(1, K, generator=gen) * 0.1
+    ref = O.multicrop_dino_loss(s.float(), t.float(), c, 0.1, 0.04, Vg, V - Vg)
+    colb = ops.axpb(c.reshape(-1).cuda(), 25.0)
+    loss, lse_s, rowb = ops.ce_fwd_onepass(s.cuda(), t.cuda(), B, V, Vg, 10.0, 25.0, colb, None, 1.0 / ((Vg * V - Vg) * B), True)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item()), (B, V, K, loss.item(), ref.item())
+    l = torch.logsumexp(s.float() / 0.1, -1)
+    assert ((lse_s.cpu() - l).norm() / l.norm()).item() <= 1e-6
+print("REGISTER FORM OK")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DINOX_CE_STREAM="0", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "REGISTER FORM OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
