@@ -284,3 +284,103 @@ def test_loss_term_seeds_round_like_the_fanout_kernel():
         for w in (1.0, 0.5, 0.1, 3.0):
             v = np.float32(np.float32(1.0) * np.float32(1.0 / accum)) * np.float32(w)
             assert st._seed(w).item() == float(v)
+
+
+class _CeStandIns:
+    """torch stand-ins for the row kernels `DINOLoss.forward` calls, recording which ones ran."""
+
+    def __init__(self, max_views=12):
+        self.calls, self.max_views = [], max_views
+
+    def ce_onepass_max_views(self):
+        return self.max_views
+
+    def axpb(self, a, alpha, beta=0.0, out=None):
+        return a * alpha + beta
+
+    def rows_lse(self, x, inv_tau, colbias=None, want_entropy=False):
+        self.calls.append("rows_lse")
+        u = x.float() * inv_tau - (colbias[None, :] if colbias is not None else 0.0)
+        return torch.logsumexp(u, dim=1)
+
+    def cols_lse(self, x, inv_tau, rowbias=None):
+        self.calls.append("cols_lse")
+        u = x.float() * inv_tau - (rowbias[:, None] if rowbias is not None else 0.0)
+        return torch.logsumexp(u, dim=0)
+
+    def lse_combine(self, gathered, add=0.0):
+        return torch.logsumexp(gathered, dim=0) + add
+
+    def _loss(self, s, t, B, V, Vg, inv_ts, inv_tt, colb, rowb, lse_s, norm):
+        q = torch.exp(t.float() * inv_tt - colb[None, :] - rowb[:, None])
+        logp = s.float() * inv_ts - lse_s[:, None]
+        tot = 0.0
+        for iq in range(Vg):
+            for v in range(V):
+                if v != iq:
+                    tot = tot - (q[iq * B:(iq + 1) * B] * logp[v * B:(v + 1) * B]).sum()
+        return tot * norm
+
+    def ce_fwd(self, s, t, B, V, Vg, inv_ts, inv_tt, colb, rowb, lse_s, group_w, norm, exclude_same):
+        self.calls.append("ce_fwd")
+        return self._loss(s, t, B, V, Vg, inv_ts, inv_tt, colb, rowb, lse_s, norm)
+
+    def ce_fwd_onepass(self, s, t, B, V, Vg, inv_ts, inv_tt, colb, group_w, norm, exclude_same):
+        self.calls.append("ce_fwd_onepass")
+        lse_s = torch.logsumexp(s.float() * inv_ts, dim=1)
+        rowb = torch.logsumexp(t.float() * inv_tt - colb[None, :], dim=1)
+        return self._loss(s, t, B, V, Vg, inv_ts, inv_tt, colb, rowb, lse_s, norm), lse_s, rowb
+
+    def cols_sum(self, x, out=None):
+        return x.float().sum(0)
+
+    def center_ema_(self, center, colsum, global_rows, momentum):
+        center.copy_(center * momentum + (colsum / global_rows).reshape(1, -1) * (1 - momentum))
+
+
+@pytest.mark.parametrize("mode,teacher,V,expect", [
+    ("onepass", "center", 2, ["ce_fwd_onepass"]),                               # the reference's call: one pass
+    ("onepass", "center", 10, ["ce_fwd_onepass"]),
+    ("onepass", "center", 14, ["rows_lse", "rows_lse", "ce_fwd"]),              # more views than the kernel holds
+    ("passes", "center", 2, ["rows_lse", "rows_lse", "ce_fwd"]),
+    ("onepass", "sinkhorn", 2, ["cols_lse", "rows_lse"] * 3 + ["rows_lse", "ce_fwd"]),   # SK row offsets are inputs
+])
+def test_dinoloss_forward_dispatch_and_value(monkeypatch, mode, teacher, V, expect):
+    """Which kernels the drop-in forward takes (one pass vs teacher LSE + student LSE + CE), on CPU with torch
+    stand-ins for the kernels; every route returns the oracle's loss and (centre mode) moves the centre alike."""
+    k = _CeStandIns()
+    monkeypatch.setattr(losshead, "ops", k)
+    monkeypatch.setattr(losshead, "_as_rows", lambda t: t)
+    monkeypatch.setattr(losshead._RowCE, "apply", staticmethod(lambda s, t, cb, rb, lse, gw, B, V_, Vg, its, itt, n, ex:
+                                                               k.ce_fwd(s, t, B, V_, Vg, its, itt, cb, rb, lse, gw, n, ex)))
+    monkeypatch.setattr(losshead._RowCEOnePass, "apply", staticmethod(lambda s, t, cb, gw, B, V_, Vg, its, itt, n, ex:
+                                                                      k.ce_fwd_onepass(s, t, B, V_, Vg, its, itt, cb, gw, n, ex)[0]))
+    monkeypatch.setattr(losshead, "sinkhorn_knopp_biases",
+                        (lambda f: (lambda t, tau, n=3, pg=None, _k=None: f(t, tau, n, pg, _k=k)))(losshead.sinkhorn_knopp_biases))
+    orig_update = losshead.DINOLoss.update_center      # its kernel namespace is a default argument
+    monkeypatch.setattr(losshead.DINOLoss, "update_center", lambda self, t: orig_update(self, t, _k=k))
+    prev = losshead.set_ce_forward(mode)
+    try:
+        g = torch.Generator().manual_seed(5)
+        B, Vg, K = 3, 2, 96
+        s = torch.randn(V * B, K, generator=g)
+        t = torch.randn(Vg * B, K, generator=g)
+        crit = losshead.DINOLoss(K, 0.9, n_global=Vg, n_local=V - Vg, teacher_mode=teacher)
+        c0 = torch.randn(1, K, generator=g) * 0.1
+        crit.center.copy_(c0)
+        loss = crit(s, t, 0.1, 0.04)
+    finally:
+        losshead.set_ce_forward(prev)
+    assert k.calls == expect, k.calls
+    ref = O.multicrop_dino_loss(s, t, c0, 0.1, 0.04, Vg, V - Vg, teacher_mode=teacher)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    if teacher == "center":
+        assert torch.allclose(crit.center, c0 * 0.9 + t.mean(0, keepdim=True) * 0.1, atol=1e-6)
+    else:
+        assert torch.equal(crit.center, c0)
+
+
+def test_ce_forward_switch_validates():
+    with pytest.raises(ValueError):
+        losshead.set_ce_forward("twice")
+    assert losshead.set_ce_forward("onepass") in ("onepass", "passes")
