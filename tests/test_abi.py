@@ -77,6 +77,9 @@ def test_sass_uses_blackwell_tensor_path(built_lib):
     sass = subprocess.run([exe, "-sass", _ext.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
     assert not re.search(r"\bHMMA\b", sass)
+    # the streaming one-pass cross-entropy: 1-D bulk copies into shared memory behind an mbarrier transaction count,
+    # packed fp32 pairs in the consumers
+    assert "UBLKCP" in sass and "SYNCS.ARRIVE.TRANS64" in sass and "FFMA2" in sass
 
 
 def test_header_is_plain_c_and_links_from_c(tmp_path):
