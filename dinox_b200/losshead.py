@@ -168,6 +168,8 @@ class _RowCEOnePass(torch.autograd.Function):
 # in the forward (dinox_ce_fwd_onepass); "passes" is the three-pass form (teacher LSE, student LSE, cross-entropy)
 # that the Sinkhorn-Knopp teacher and V > 12 views always take.  DINOX_CE_FORWARD overrides at import.
 _CE_FORWARD = [os.environ.get("DINOX_CE_FORWARD", "onepass")]
+if _CE_FORWARD[0] not in ("onepass", "passes"):
+    raise ValueError(f"DINOX_CE_FORWARD={_CE_FORWARD[0]!r}: expected onepass or passes")
 
 
 def set_ce_forward(mode: str) -> str:
