@@ -712,7 +712,7 @@ ce_onepass_finalize_kernel(const float* __restrict__ partial, CeArgs a, float in
 // into shared memory with 1-D bulk copies (cp.async.bulk, mbarrier complete_tx) while 512 consumer threads run the
 // online LSE / cross-term arithmetic on the previous block.  Loads need no registers, run kStages blocks ahead and
 // straight across work-item boundaries, so no CTA start-up latency is exposed after the first block; the consumers
-// are left with ~45 registers of running state.  Same partial layout and finalize kernel as the register form.
+// hold only the running (max, sum, cross) state of the rows (96 registers per thread in all).  Same partial layout and finalize kernel as the register form.
 // ---------------------------------------------------------------------------------------------
 constexpr int kStreamConsumers = 512;
 constexpr int kStreamThreads = kStreamConsumers + 32;
