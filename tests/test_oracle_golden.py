@@ -176,6 +176,62 @@ def test_sinkhorn_properties_and_dp_equivalence():
     assert torch.isfinite(O.sinkhorn_knopp(t * 50.0, 0.04, 3)).all()
 
 
+def test_sinkhorn_log_domain_oracle_equals_the_published_probability_domain_form():
+    """E2 has no reference implementation to pin against; what can be pinned is the ALGORITHM: the published
+    DINOv2 / SwAV iteration written literally in the probability domain in float64 numpy (Q = exp(t/tau)^T; Q /= sum Q;
+    3 x { Q /= rowsum; Q /= K; Q /= colsum; Q /= B }; Q *= B) against the oracle's log-domain evaluation, on one
+    process and with the batch split over two "ranks" whose per-prototype sums are added (the all-reduce)."""
+    g = torch.Generator().manual_seed(21)
+    t = (torch.randn(24, 96, generator=g) * 0.3).double().numpy()   # small enough that exp(t / 0.04) stays in range
+    tau, n_it = 0.04, 3
+
+    def published(tt, world_split=None):
+        Q = np.exp(tt / tau).T                       # (K, B)
+        K, B = Q.shape
+        Q /= Q.sum()
+        for _ in range(n_it):
+            if world_split is None:
+                rows = Q.sum(axis=1, keepdims=True)
+            else:                                    # per-rank partial sums, then the all-reduce
+                rows = sum(Q[:, sl].sum(axis=1, keepdims=True) for sl in world_split)
+            Q /= rows
+            Q /= K
+            Q /= Q.sum(axis=0, keepdims=True)
+            Q /= B
+        Q *= B
+        return Q.T
+
+    ref = published(t.copy())
+    got = O.sinkhorn_knopp(torch.from_numpy(t), tau, n_it).double().numpy()
+    assert np.abs(got - ref).max() <= 2e-6 * ref.max(), np.abs(got - ref).max()
+    ref2 = published(t.copy(), world_split=[slice(0, 10), slice(10, 24)])
+    assert np.abs(ref2 - ref).max() <= 1e-12
+    np.testing.assert_allclose(ref.sum(1), 1.0, rtol=1e-12)
+
+
+def test_multicrop_oracle_equals_the_published_dino_v1_loop():
+    """E1: the public DINO-v1 loss loop written literally (teacher chunks x student chunks, skip v == iq, mean over the
+    batch, divide by the number of terms; centre subtracted before the teacher softmax) in float64 against the oracle."""
+    g = torch.Generator().manual_seed(22)
+    B, Vg, Vl, K = 5, 2, 6, 48
+    s = torch.randn((Vg + Vl) * B, K, generator=g).double()
+    t = torch.randn(Vg * B, K, generator=g).double()
+    c = (torch.randn(1, K, generator=g) * 0.1).double()
+    student = (s / 0.1).chunk(Vg + Vl)
+    teacher = torch.softmax((t - c) / 0.04, dim=-1).chunk(Vg)
+    total, n_terms = 0.0, 0
+    for iq, q in enumerate(teacher):
+        for v in range(len(student)):
+            if v == iq:
+                continue
+            total = total + torch.sum(-q * torch.log_softmax(student[v], dim=-1), dim=-1).mean()
+            n_terms += 1
+    total = total / n_terms
+    got = O.multicrop_dino_loss(s.float(), t.float(), c.float(), 0.1, 0.04, Vg, Vl)
+    assert n_terms == Vg * (Vg + Vl) - Vg
+    close(got, total.float(), rtol=2e-6)
+
+
 def test_ibot_reduces_to_plain_ce():
     g = torch.Generator().manual_seed(12)
     s = torch.randn(10, 40, generator=g)
