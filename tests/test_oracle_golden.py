@@ -232,6 +232,23 @@ def test_multicrop_oracle_equals_the_published_dino_v1_loop():
     close(got, total.float(), rtol=2e-6)
 
 
+def test_ibot_oracle_equals_the_published_forward_masked_form():
+    """E3: DINOv2's iBOTPatchLoss.forward_masked written literally in float64 (per-token CE, weighted by
+    1 / n_masked(image), summed, divided by the number of images) against the oracle, with ragged mask counts."""
+    g = torch.Generator().manual_seed(23)
+    counts = [3, 7, 1, 5]                                    # masked tokens per image (global crop)
+    Mm, K = sum(counts), 40
+    s = torch.randn(Mm, K, generator=g).double()
+    t = torch.randn(Mm, K, generator=g).double()
+    c = (torch.randn(1, K, generator=g) * 0.1).double()
+    w = torch.cat([torch.full((n,), 1.0 / n) for n in counts]).double()
+    tprob = torch.softmax((t - c) / 0.04, dim=-1)
+    loss = torch.sum(tprob * torch.log_softmax(s / 0.1, dim=-1), dim=-1) * w
+    ref = -loss.sum() / len(counts)
+    got = O.ibot_patch_loss(s.float(), t.float(), c.float(), 0.1, 0.04, w.float(), n_images=len(counts))
+    close(got, ref.float(), rtol=2e-6)
+
+
 def test_ibot_reduces_to_plain_ce():
     g = torch.Generator().manual_seed(12)
     s = torch.randn(10, 40, generator=g)
