@@ -173,6 +173,64 @@ def main():
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f))} bytes")
 
 
+def window_sequence_golden():
+    """KAT 9: TWO optimizer windows of the reference loop on head features (scripts/phase5_big_run.py:1738-1802):
+    accum = 2 micro-steps each, loss = (L_dino + 0.5 L_gram) / accum, backward, then torch.optim.AdamW on the student
+    head (:1621) and the EMA of the teacher head (:1798-1802).  Pins the glue over time: the centre after every
+    micro-step, the accumulated head gradients at each window end, the student head after AdamW and the teacher
+    head after the EMA.  Inputs are fixed random features (no backbone), written next to the outputs."""
+    from phase5_big_run import DINOLoss, compute_gram_anchoring_loss
+    from zoo.arch import DinoStudentTeacher
+    torch.manual_seed(11)
+    torch.set_num_threads(1)
+
+    class _BB(torch.nn.Module):          # DinoStudentTeacher only needs .dim of its backbone to build the head
+        dim = 24
+    D, K, B, T, accum, windows = 24, 160, 3, 6, 2, 2
+    student, teacher = DinoStudentTeacher(_BB(), out_dim=K), DinoStudentTeacher(_BB(), out_dim=K)
+    with torch.no_grad():
+        for p in teacher.parameters():
+            p.add_(torch.randn(p.shape) * 0.05)
+            p.requires_grad_(False)
+    dl = DINOLoss(K, 0.9)
+    opt = torch.optim.AdamW(student.head.parameters(), lr=1e-2, weight_decay=0.04)
+    g = torch.Generator().manual_seed(12)
+    out = {"accum": accum, "windows": windows, "gram_weight": 0.5, "ema": 0.99, "lr": 1e-2, "weight_decay": 0.04,
+           "student_temp": 0.1, "teacher_temp": 0.04, "momentum": 0.9}
+    for k, v in student.head.state_dict().items():
+        out[f"s0_{k.replace('.', '_')}"] = _np(v)
+    for k, v in teacher.head.state_dict().items():
+        out[f"t0_{k.replace('.', '_')}"] = _np(v)
+    step = 0
+    for w in range(windows):
+        opt.zero_grad(set_to_none=True)
+        for _ in range(accum):
+            s_feats = torch.randn(2 * B, T, D, generator=g)
+            t_feats = torch.randn(2 * B, T, D, generator=g)
+            out[f"s_feats_{step}"], out[f"t_feats_{step}"] = _np(s_feats), _np(t_feats)
+            student_out = student.head(s_feats[:, 0])
+            with torch.no_grad():
+                teacher_out = teacher.head(t_feats[:, 0])
+            loss_dino = dl(student_out, teacher_out, 0.1, 0.04)
+            loss_gram = compute_gram_anchoring_loss(s_feats, t_feats)
+            ((loss_dino + 0.5 * loss_gram) / accum).backward()
+            out[f"loss_dino_{step}"], out[f"loss_gram_{step}"] = _np(loss_dino), _np(loss_gram)
+            out[f"center_{step}"] = _np(dl.center)
+            step += 1
+        for n, p in student.head.named_parameters():
+            out[f"grad_w{w}_{n.replace('.', '_')}"] = _np(p.grad)
+        opt.step()
+        with torch.no_grad():
+            for p_s, p_t in zip(student.parameters(), teacher.parameters()):
+                p_t.data.mul_(0.99).add_(p_s.data, alpha=1.0 - 0.99)
+        for k, v in student.head.state_dict().items():
+            out[f"s_w{w}_{k.replace('.', '_')}"] = _np(v)
+        for k, v in teacher.head.state_dict().items():
+            out[f"t_w{w}_{k.replace('.', '_')}"] = _np(v)
+    np.savez(os.path.join(OUT, "window_sequence.npz"), **out)
+    print("  window_sequence.npz:", os.path.getsize(os.path.join(OUT, "window_sequence.npz")), "bytes")
+
+
 def koleo_golden():
     """KoLeoLoss of the reference (scripts/phase5_big_run.py:742-773) with its autograd gradient on
     spread-out, clustered (near-duplicate rows: the cancellation-prone case) and wide-K inputs."""
@@ -196,6 +254,10 @@ def koleo_golden():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "koleo":
         koleo_golden()      # adds one file, leaves the other vectors untouched
+    elif len(sys.argv) > 1 and sys.argv[1] == "windows":
+        os.makedirs(OUT, exist_ok=True)
+        window_sequence_golden()
     else:
         main()
         koleo_golden()
+        window_sequence_golden()

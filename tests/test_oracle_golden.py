@@ -153,6 +153,41 @@ def test_whole_microstep_matches_reference_loop(golden):
         close(t.grad, g[f"g_head_{k}"], rtol=1e-4, atol=1e-8)
 
 
+def test_two_optimizer_windows_match_reference_loop(golden):
+    """a9 over time (scripts/phase5_big_run.py:1738-1802): two windows of accum = 2 micro-steps run by the REFERENCE
+    (its DINOLoss, Gram loss, head, torch.optim.AdamW, EMA loop) against the oracle driven the same way: losses and
+    the centre after every micro-step, the accumulated head gradients at each window end, the student head after
+    AdamW and the teacher head after the EMA."""
+    g = golden("window_sequence.npz")
+    keys = ("0_weight", "0_bias", "2_weight", "2_bias")
+    sp = O.HeadParams(*[T(g[f"s0_{k}"]).clone().requires_grad_(True) for k in keys])
+    tp = O.HeadParams(*[T(g[f"t0_{k}"]).clone() for k in keys])
+    K = sp.w2.shape[0]
+    accum, windows = int(g["accum"]), int(g["windows"])
+    orc = O.LossHeadOracle(sp, tp, out_dim=K, center_momentum=float(g["momentum"]), n_global=2, n_local=0,
+                           gram_weight=float(g["gram_weight"]), policy="fp32")
+    opt = torch.optim.AdamW(sp.tensors(), lr=float(g["lr"]), weight_decay=float(g["weight_decay"]))
+    step = 0
+    for w in range(windows):
+        opt.zero_grad(set_to_none=True)
+        for _ in range(accum):
+            sf, tf = T(g[f"s_feats_{step}"]).clone().requires_grad_(True), T(g[f"t_feats_{step}"])
+            out = orc.step(sf[:, 0], tf[:, 0], float(g["student_temp"]), float(g["teacher_temp"]),
+                           student_tok=sf, teacher_tok=tf, accum=accum)
+            close(out["loss_dino"], g[f"loss_dino_{step}"], rtol=2e-6)
+            close(out["loss_gram"], g[f"loss_gram_{step}"], rtol=2e-6)
+            close(orc.center, g[f"center_{step}"])
+            step += 1
+        for k, p in zip(keys, sp.tensors()):
+            close(p.grad, g[f"grad_w{w}_{k}"], rtol=1e-4, atol=1e-8)
+        opt.step()
+        with torch.no_grad():
+            O.ema_update(tp.tensors(), [p.detach() for p in sp.tensors()], float(g["ema"]))
+        for k, p, q in zip(keys, sp.tensors(), tp.tensors()):
+            close(p, g[f"s_w{w}_{k}"], rtol=1e-5, atol=1e-7)
+            close(q, g[f"t_w{w}_{k}"], rtol=1e-6, atol=1e-7)
+
+
 def test_bf16_policy_is_close_to_fp32(golden):
     """The bf16-operand policy (what the CUDA tensor-core path computes) stays within the
     north_star tolerance (rtol 1e-3 on the loss) of the fp32 reference on identical inputs."""
